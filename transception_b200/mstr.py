@@ -1,0 +1,725 @@
+"""Drop-in ``MSTransception`` for the reference's ``networks.MSTr``.
+
+Boundary: the ``nn.Module`` surface is the reference's plugin interface —
+``from networks.MSTr import MSTransception`` (reference ``train_MSTransception.py:12``,
+``test.py:14``).  Every class below keeps the reference's constructor signature, the
+attribute names (=> identical ``state_dict`` keys, 2 200 of them, dead and aliased ones
+included) and the reference's construction order (=> identical same-seed initialisation,
+reference ``MSTr.py:2759-2823``).  The modules only *hold* parameters; all arithmetic is
+done by hand-written sm_100a kernels reached through the C-ABI library
+(``transception_b200.ops`` -> ``libtransception_sm100.so``).  There is no PyTorch/CPU
+fallback: calling ``forward`` without the CUDA library raises.
+
+Layout: activations are tokens-major / NHWC fp32 end to end.  Wherever the reference's
+sub-module boundary is an NCHW map, this file returns an NCHW-*shaped* view of NHWC
+storage (torch ``channels_last`` strides): same shapes and values as the reference, no
+transposition kernels.
+
+Only the default structure of the entry scripts is built (``Stage_3or4=3``,
+``concat='coord'``, ``have_bridge='original'``; any ``br_ch_att_list`` permutation); other
+structural values raise ``NotImplementedError``.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_LN_EPS = 1e-5
+
+
+def _nhwc(x):
+    """NCHW-shaped tensor (any strides) -> contiguous [B,H,W,C] (free for channels_last)."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _as_nchw(x_nhwc):
+    """[B,H,W,C] storage -> NCHW-shaped view (channels_last strides)."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+def _xavier_convs(mods):
+    for m in mods:
+        if isinstance(m, nn.Conv2d):
+            nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+
+def _bn(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+
+
+def _check_eval_bn(mod):
+    if mod.training:
+        raise NotImplementedError(
+            "transception_b200: BatchNorm batch-statistics (train mode) kernels are not built yet; "
+            "call .eval() (round-1 scope is the forward path, see DESIGN.md)")
+
+
+# --------------------------------------------------------------------------------------
+# Mix-FFN (reference MSTr.py:21-31 DWConv, :48-61 / :889-902 MixFFN_skip)
+# --------------------------------------------------------------------------------------
+class DWConv(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, groups=dim)
+
+    def forward(self, x, H, W):
+        B, N, C = x.shape
+        return ops.dwconv_tokens(x.contiguous(), H, W, self.dwconv.weight, self.dwconv.bias, add_input=False)
+
+
+class MixFFN_skip(nn.Module):
+    """fc2(GELU(LN(dw3x3(fc1 x) + fc1 x))); ``norm2``/``norm3`` are dead parameters kept for
+    state_dict compatibility (reference MSTr.py:56-57)."""
+
+    def __init__(self, c1, c2):
+        super().__init__()
+        self.fc1 = nn.Linear(c1, c2)
+        self.dwconv = DWConv(c2)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(c2, c1)
+        self.norm1 = nn.LayerNorm(c2)
+        self.norm2 = nn.LayerNorm(c2)
+        self.norm3 = nn.LayerNorm(c2)
+
+    def args(self):
+        return (self.fc1.weight, self.fc1.bias, self.dwconv.dwconv.weight, self.dwconv.dwconv.bias,
+                self.norm1.weight, self.norm1.bias, self.norm1.eps, self.fc2.weight, self.fc2.bias)
+
+    def forward(self, x, H, W):
+        return ops.mixffn_skip(x, H, W, *self.args())
+
+
+# --------------------------------------------------------------------------------------
+# Stage-1 / decoder efficient attention (reference MSTr.py:80-173)
+# --------------------------------------------------------------------------------------
+class EfficientAttention(nn.Module):
+    def __init__(self, in_channels, key_channels, value_channels, head_count=1):
+        super().__init__()
+        if head_count != 1 or key_channels != in_channels or value_channels != in_channels:
+            raise NotImplementedError("EfficientAttention is built for head_count=1, key=value=in channels "
+                                      "(the only configuration reachable from MSTransception)")
+        self.in_channels, self.key_channels = in_channels, key_channels
+        self.head_count, self.value_channels = head_count, value_channels
+        self.keys = nn.Conv2d(in_channels, key_channels, 1)
+        self.queries = nn.Conv2d(in_channels, key_channels, 1)
+        self.values = nn.Conv2d(in_channels, value_channels, 1)
+        self.reprojection = nn.Conv2d(value_channels, in_channels, 1)
+
+    def args(self):
+        return (self.keys.weight, self.keys.bias, self.queries.weight, self.queries.bias,
+                self.values.weight, self.values.bias, self.reprojection.weight, self.reprojection.bias)
+
+    def forward(self, input_):
+        x = _nhwc(input_)
+        B, H, W, C = x.shape
+        y = ops.eff_attn(x.view(B, H * W, C), *self.args(), residual=None, reinterpret=False)
+        return _as_nchw(y.view(B, H, W, C))
+
+
+class EfficientTransformerBlock(nn.Module):
+    """``head_count`` is accepted and ignored exactly like the reference (MSTr.py:154-155)."""
+
+    def __init__(self, in_dim, key_dim, value_dim, head_count=1, token_mlp='mix'):
+        super().__init__()
+        if token_mlp != 'mix_skip':
+            raise NotImplementedError("only token_mlp='mix_skip' is built")
+        self.norm1 = nn.LayerNorm(in_dim)
+        self.attn = EfficientAttention(in_channels=in_dim, key_channels=key_dim,
+                                       value_channels=value_dim, head_count=1)
+        self.norm2 = nn.LayerNorm(in_dim)
+        self.mlp = MixFFN_skip(in_dim, int(in_dim * 4))
+
+    def forward(self, x, H, W):
+        x = x.contiguous()
+        n1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        tx = ops.eff_attn(n1, *self.attn.args(), residual=x, reinterpret=False)
+        n2 = ops.layernorm(tx, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return ops.mixffn_skip(n2, H, W, *self.mlp.args(), residual=tx)
+
+
+# --------------------------------------------------------------------------------------
+# Decoder (reference MSTr.py:176-290) — SURVEY §8f rank 1
+# --------------------------------------------------------------------------------------
+class PatchExpand(nn.Module):
+    def __init__(self, input_resolution, dim, dim_scale=2, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.dim = dim
+        self.expand = nn.Linear(dim, 2 * dim, bias=False) if dim_scale == 2 else nn.Identity()
+        self.norm = norm_layer(dim // dim_scale)
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        return ops.patch_expand(x.contiguous(), H, W, self.expand.weight, 2,
+                                self.norm.weight, self.norm.bias, self.norm.eps)
+
+
+class FinalPatchExpand_X4(nn.Module):
+    def __init__(self, input_resolution, dim, dim_scale=4, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.dim = dim
+        self.dim_scale = dim_scale
+        self.expand = nn.Linear(dim, 16 * dim, bias=False)
+        self.output_dim = dim
+        self.norm = norm_layer(self.output_dim)
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        B, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        return ops.patch_expand(x.contiguous(), H, W, self.expand.weight, self.dim_scale,
+                                self.norm.weight, self.norm.bias, self.norm.eps)
+
+
+class MyDecoderLayer(nn.Module):
+    def __init__(self, input_size, in_out_chan, head_count, token_mlp_mode, n_class=9,
+                 norm_layer=nn.LayerNorm, is_last=False):
+        super().__init__()
+        dims, out_dim, key_dim, value_dim = in_out_chan
+        if not is_last:
+            self.concat_linear = nn.Linear(dims * 2, out_dim)
+            self.layer_up = PatchExpand(input_resolution=input_size, dim=out_dim, dim_scale=2, norm_layer=norm_layer)
+            self.last_layer = None
+        else:
+            self.concat_linear = nn.Linear(dims * 4, out_dim)
+            self.layer_up = FinalPatchExpand_X4(input_resolution=input_size, dim=out_dim, dim_scale=4,
+                                                norm_layer=norm_layer)
+            self.last_layer = nn.Conv2d(out_dim, n_class, 1)
+        self.layer_former_1 = EfficientTransformerBlock(out_dim, key_dim, value_dim, head_count, token_mlp_mode)
+        self.layer_former_2 = EfficientTransformerBlock(out_dim, key_dim, value_dim, head_count, token_mlp_mode)
+        # reference MSTr.py:255-269 (pre-order walk: xavier on every Linear/Conv2d weight, zero biases)
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Conv2d)):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x1, x2=None):
+        if x2 is None:
+            return self.layer_up(x1)
+        b, h, w, c = x2.shape
+        cat_linear_x = ops.concat_linear(x1.contiguous(), x2.reshape(b, h * w, c).contiguous(),
+                                         self.concat_linear.weight, self.concat_linear.bias)
+        t1 = self.layer_former_1(cat_linear_x, h, w)
+        t2 = self.layer_former_2(t1, h, w)
+        if self.last_layer is not None:
+            up = self.layer_up
+            # fused: expand GEMM -> pixel shuffle x4 -> LN(64) -> 1x1 conv to classes, NCHW logits
+            return ops.final_expand_head(t2, h, w, up.expand.weight, up.norm.weight, up.norm.bias, up.norm.eps,
+                                         self.last_layer.weight, self.last_layer.bias)
+        return self.layer_up(t2)
+
+
+# --------------------------------------------------------------------------------------
+# Stage-1 stem (reference MSTr.py:292-304)
+# --------------------------------------------------------------------------------------
+class OverlapPatchEmbeddings(nn.Module):
+    def __init__(self, img_size=224, patch_size=7, stride=4, padding=1, in_ch=3, dim=768):
+        super().__init__()
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_ch, dim, patch_size, stride, padding)
+        self.norm = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        k, s, p = self.proj.kernel_size[0], self.proj.stride[0], self.proj.padding[0]
+        H = (x.shape[2] + 2 * p - k) // s + 1
+        W = (x.shape[3] + 2 * p - k) // s + 1
+        y = ops.patch_embed_ln(x.contiguous(), self.proj.weight, self.proj.bias, s, p,
+                               self.norm.weight, self.norm.bias, self.norm.eps)
+        return y, H, W
+
+
+# --------------------------------------------------------------------------------------
+# RIPM: ResInception Patch Merging (reference MSTr.py:309-404, :670-732, :996-1050)
+# --------------------------------------------------------------------------------------
+class DWConv2d_BN(nn.Module):
+    def __init__(self, in_ch, out_ch, kernel_size=1, stride=1, norm_layer=nn.BatchNorm2d,
+                 act_layer=nn.Hardswish, bn_weight_init=1, norm_cfg="BN"):
+        super().__init__()
+        if in_ch != out_ch or kernel_size != 3 or act_layer is not nn.Hardswish:
+            raise NotImplementedError("DWConv2d_BN is built for the RIPM shape (3x3, in==out, Hardswish)")
+        self.dwconv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, (kernel_size - 1) // 2, groups=out_ch, bias=False)
+        self.pwconv = nn.Conv2d(out_ch, out_ch, 1, 1, 0, bias=False)
+        self.bn = nn.BatchNorm2d(out_ch)
+        self.act = act_layer()
+        _xavier_convs(self.modules())
+        self.bn.weight.data.fill_(bn_weight_init)
+        self.bn.bias.data.zero_()
+
+    def nhwc(self, x_nhwc, out=None):
+        _check_eval_bn(self)
+        return ops.ripm_dwsep_bn_hs(x_nhwc, self.dwconv.stride[0], self.dwconv.weight, self.pwconv.weight,
+                                    *_bn(self.bn), out=out)
+
+    def forward(self, x):
+        return _as_nchw(self.nhwc(_nhwc(x)))
+
+
+class Conv2d_BN(nn.Module):
+    """Parameter holder for the 1x1 conv + BN inside ``ResBlock``."""
+
+    def __init__(self, in_ch, out_ch, kernel_size=1, stride=1, pad=0, dilation=1, groups=1,
+                 bn_weight_init=1, act_layer=None, norm_cfg="BN"):
+        super().__init__()
+        if kernel_size != 1 or stride != 1 or groups != 1:
+            raise NotImplementedError("Conv2d_BN is built for 1x1/stride 1 only")
+        self.conv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, pad, dilation, groups, bias=False)
+        self.bn = nn.BatchNorm2d(out_ch)
+        nn.init.constant_(self.bn.weight, bn_weight_init)
+        nn.init.constant_(self.bn.bias, 0)
+        _xavier_convs(self.modules())
+        self.hardswish = act_layer is nn.Hardswish
+        if act_layer is not None and not self.hardswish:
+            raise NotImplementedError("Conv2d_BN: only Hardswish / no activation are built")
+        self.act_layer = act_layer() if act_layer is not None else nn.Identity()
+
+    def forward(self, x):
+        _check_eval_bn(self)
+        xh = _nhwc(x)
+        B, H, W, C = xh.shape
+        y = ops.linear_bn_act(xh.view(-1, C), self.conv.weight, *_bn(self.bn), hardswish=self.hardswish)
+        return _as_nchw(y.view(B, H, W, -1))
+
+
+class DWCPatchEmbed(nn.Module):
+    def __init__(self, in_chans=3, embed_dim=768, patch_size=16, stride=1, pad=0,
+                 act_layer=nn.Hardswish, norm_cfg='BN'):
+        super().__init__()
+        self.stride = stride
+        self.patch_conv = DWConv2d_BN(in_chans, embed_dim, kernel_size=patch_size, stride=stride,
+                                      act_layer=nn.Hardswish, norm_cfg=norm_cfg)
+
+    def forward(self, x):
+        return self.patch_conv(x)
+
+
+class Patch_Embed_stage(nn.Module):
+    """Three chained dw3x3 -> pw1x1 -> BN -> Hardswish blocks; returns the three intermediate maps.
+    The three outputs are written into one stacked [3,B,H,W,C] buffer so the Multi-Branch stage can run its
+    three branches as one grouped launch."""
+
+    def __init__(self, embed_dim, num_path=3, isPool=False, norm_cfg=dict(type="BN")):
+        super().__init__()
+        self.patch_embeds = nn.ModuleList([
+            DWCPatchEmbed(in_chans=embed_dim, embed_dim=embed_dim, patch_size=3,
+                          stride=2 if isPool and idx == 0 else 1, pad=1, norm_cfg='BN')
+            for idx in range(num_path)])
+
+    def nhwc(self, x_nhwc):
+        B, H, W, C = x_nhwc.shape
+        s0 = self.patch_embeds[0].stride
+        Ho, Wo = (H + 2 - 3) // s0 + 1, (W + 2 - 3) // s0 + 1
+        stacked = torch.empty((len(self.patch_embeds), B, Ho, Wo, C), device=x_nhwc.device, dtype=x_nhwc.dtype)
+        cur = x_nhwc
+        for i, pe in enumerate(self.patch_embeds):
+            cur = pe.patch_conv.nhwc(cur, out=stacked[i])
+        return stacked
+
+    def forward(self, x):
+        stacked = self.nhwc(_nhwc(x))
+        return [_as_nchw(stacked[i]) for i in range(stacked.shape[0])]
+
+
+class ResBlock(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.Hardswish, norm_cfg="BN"):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.conv1 = Conv2d_BN(in_features, hidden_features, act_layer=act_layer, norm_cfg=norm_cfg)
+        self.dwconv = nn.Conv2d(hidden_features, hidden_features, 3, 1, 1, bias=False, groups=hidden_features)
+        self.norm = nn.BatchNorm2d(hidden_features)
+        self.act = act_layer()
+        self.conv2 = Conv2d_BN(hidden_features, out_features, norm_cfg=norm_cfg)
+        # reference MSTr.py:1025-1039 via self.apply (children first): conv1.conv, dwconv, conv2.conv
+        _xavier_convs([self.conv1.conv, self.dwconv, self.conv2.conv])
+
+    def nhwc(self, x_nhwc):
+        _check_eval_bn(self)
+        return ops.resblock(x_nhwc, self.conv1.conv.weight, _bn(self.conv1.bn), self.dwconv.weight, _bn(self.norm),
+                            self.conv2.conv.weight, _bn(self.conv2.bn))
+
+    def forward(self, x):
+        return _as_nchw(self.nhwc(_nhwc(x)))
+
+
+# --------------------------------------------------------------------------------------
+# Multi-Branch transformer (reference MSTr.py:734-993)
+# --------------------------------------------------------------------------------------
+class ConvPosEnc(nn.Module):
+    def __init__(self, dim, k=3):
+        super().__init__()
+        self.proj = nn.Conv2d(dim, dim, k, 1, k // 2, groups=dim)
+
+    def forward(self, x, size):
+        H, W = size
+        return ops.dwconv_tokens(x.contiguous(), H, W, self.proj.weight, self.proj.bias, add_input=True)
+
+
+class ConvRelPosEnc(nn.Module):
+    def __init__(self, Ch, h, window):
+        super().__init__()
+        if isinstance(window, int):
+            window = {window: h}
+        elif not isinstance(window, dict):
+            raise ValueError()
+        self.window = window
+        self.conv_list = nn.ModuleList()
+        self.head_splits = []
+        for cur_window, cur_head_split in window.items():
+            ch = cur_head_split * Ch
+            self.conv_list.append(nn.Conv2d(ch, ch, kernel_size=(cur_window, cur_window),
+                                            padding=(cur_window // 2, cur_window // 2), groups=ch))
+            self.head_splits.append(cur_head_split)
+        self.channel_splits = [x * Ch for x in self.head_splits]
+
+    def forward(self, q, v, size):
+        """q, v: [B,h,N,Ch] -> q * dwconv(v)  (reference MSTr.py:801-823)."""
+        H, W = size
+        return ops.crpe(q.contiguous(), v.contiguous(), H, W, [c.weight for c in self.conv_list],
+                        [c.bias for c in self.conv_list], self.head_splits)
+
+
+class FactorAtt_ConvRelPosEnc(nn.Module):
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0,
+                 shared_crpe=None):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.crpe = shared_crpe
+
+    def args(self):
+        c = self.crpe
+        return (self.num_heads, self.scale, self.qkv.weight, self.qkv.bias,
+                [m.weight for m in c.conv_list], [m.bias for m in c.conv_list], list(c.head_splits),
+                self.proj.weight, self.proj.bias)
+
+    def forward(self, x, size):
+        H, W = size
+        return ops.mb_factor_attn(x.contiguous(), H, W, *self.args(), residual=None)
+
+
+class MHCABlock(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=3, drop_path=0.0, qkv_bias=True, qk_scale=None,
+                 norm_layer='LN', shared_cpe=None, shared_crpe=None):
+        super().__init__()
+        self.cpe = shared_cpe
+        self.crpe = shared_crpe
+        self.factoratt_crpe = FactorAtt_ConvRelPosEnc(dim, num_heads=num_heads, qkv_bias=qkv_bias,
+                                                      qk_scale=qk_scale, shared_crpe=shared_crpe)
+        self.mlp = MixFFN_skip(dim, dim * mlp_ratio)
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+
+    def forward(self, x, size):
+        return ops.mhca_blocks(x.contiguous().unsqueeze(0), size[0], size[1], [[self]])[0]
+
+
+class MHCAEncoder(nn.Module):
+    def __init__(self, dim, num_layers=1, num_heads=8, mlp_ratio=3, drop_path_list=[], qk_scale=None,
+                 crpe_window={3: 2, 5: 3, 7: 3}):
+        super().__init__()
+        self.num_layers = num_layers
+        self.cpe = ConvPosEnc(dim, k=3)
+        self.crpe = ConvRelPosEnc(Ch=dim // num_heads, h=num_heads, window=crpe_window)
+        self.MHCA_layers = nn.ModuleList([
+            MHCABlock(dim, num_heads=num_heads, mlp_ratio=mlp_ratio, drop_path=drop_path_list[idx],
+                      qk_scale=qk_scale, shared_cpe=self.cpe, shared_crpe=self.crpe)
+            for idx in range(self.num_layers)])
+
+    def forward(self, x, size):
+        H, W = size
+        B = x.shape[0]
+        y = ops.mhca_blocks(x.contiguous().unsqueeze(0), H, W, [list(self.MHCA_layers)])[0]
+        return _as_nchw(y.view(B, H, W, -1))
+
+
+def dpr_generator(drop_path_rate, num_layers, num_stages):
+    vals = [v.item() for v in torch.linspace(0, drop_path_rate, sum(num_layers))]
+    out, cur = [], 0
+    for i in range(num_stages):
+        out.append(vals[cur:cur + num_layers[i]])
+        cur += num_layers[i]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# IFF: coordinate attention over the four concatenated maps (reference MSTr.py:1270-1348)
+# --------------------------------------------------------------------------------------
+class silu_sigmoid(nn.Module):
+    def __init__(self, inplace=True):
+        super().__init__()
+        self.silu = nn.SiLU(inplace=inplace)
+
+
+class silu_swish(nn.Module):
+    """t * min(SiLU(t+3)/6, 1); evaluated inside the IFF kernel (holder only)."""
+
+    def __init__(self, inplace=True):
+        super().__init__()
+        self.sigmoid = silu_sigmoid(inplace=inplace)
+
+
+class CoordAtt(nn.Module):
+    def __init__(self, inp, oup, reduction=32):
+        super().__init__()
+        mip = max(8, inp // reduction)
+        self.conv1 = nn.Conv2d(inp, mip, kernel_size=1, stride=1, padding=0)
+        self.bn1 = nn.BatchNorm2d(mip)
+        self.act = silu_swish()
+        self.conv_h = nn.Conv2d(mip, inp, kernel_size=1, stride=1, padding=0)
+        self.conv_w = nn.Conv2d(mip, inp, kernel_size=1, stride=1, padding=0)
+        self.conv_in_out = nn.Conv2d(inp, oup, kernel_size=1, stride=1, padding=0)
+
+    def nhwc(self, maps):
+        """maps: list of NHWC tensors whose channel concatenation is the reference's input."""
+        _check_eval_bn(self)
+        return ops.iff_coordatt(maps, self.conv1.weight, self.conv1.bias, _bn(self.bn1),
+                                self.conv_h.weight, self.conv_h.bias, self.conv_w.weight, self.conv_w.bias,
+                                self.conv_in_out.weight, self.conv_in_out.bias)
+
+    def forward(self, x):
+        return _as_nchw(self.nhwc([_nhwc(x)]))
+
+
+class MHCA_stage(nn.Module):
+    def __init__(self, embed_dim, out_embed_dim, num_layers=1, num_heads=8, mlp_ratio=3, num_path=4,
+                 norm_cfg="BN", drop_path_list=[], concat='normal', use_sa=True, sa_ker=7):
+        super().__init__()
+        if concat != 'coord':
+            raise NotImplementedError("only concat='coord' (IFF, the default of the entry scripts) is built")
+        self.concat = concat
+        self.mhca_blks = nn.ModuleList([
+            MHCAEncoder(embed_dim, num_layers, num_heads, mlp_ratio, drop_path_list=drop_path_list)
+            for _ in range(num_path)])
+        self.InvRes = ResBlock(in_features=embed_dim, out_features=embed_dim, norm_cfg=norm_cfg)
+        self.aggregate = CoordAtt(inp=embed_dim * (num_path + 1), oup=out_embed_dim, reduction=16)
+
+    def nhwc(self, stacked):
+        """stacked: [P,B,H,W,C] RIPM outputs -> [B,H,W,C_out]."""
+        P, B, H, W, C = stacked.shape
+        res = self.InvRes.nhwc(stacked[0])
+        enc = ops.mhca_blocks(stacked.view(P, B, H * W, C), H, W,
+                              [list(e.MHCA_layers) for e in self.mhca_blks])
+        maps = [res] + [enc[i].view(B, H, W, C) for i in range(P)]
+        return self.aggregate.nhwc(maps)
+
+    def forward(self, inputs):
+        stacked = torch.stack([_nhwc(x) for x in inputs], 0)
+        return _as_nchw(self.nhwc(stacked))
+
+
+class MSViT(nn.Module):
+    def __init__(self, image_size, in_dim, key_dim, value_dim, layers, head_count=1, dil_conv=1,
+                 token_mlp='mix_skip', MSViT_config=1, concat='normal', use_sa_list=[True, True, False], sa_ker=7):
+        super().__init__()
+        self.Hs = [56, 28, 14, 7]
+        self.Ws = [56, 28, 14, 7]
+        # dead 1x1 convs, kept for state_dict/init parity (reference MSTr.py:1567-1570)
+        for i in range(4):
+            setattr(self, 'conv1_1_s%d' % (i + 1), nn.Conv2d(3 * in_dim[i], in_dim[i], 1))
+        num_path, num_layers, num_heads, mlp_ratios = [3, 3, 3], [3, 8, 3], [8, 8, 8], [4, 4, 4]
+        dpr = dpr_generator(0.0, num_layers, 3)
+        for s in range(3):
+            setattr(self, 'patch_embed_stage%d' % (s + 2),
+                    Patch_Embed_stage(in_dim[s], num_path=num_path[s], isPool=True, norm_cfg='BN'))
+        for s in range(3):
+            setattr(self, 'mhca_stage%d' % (s + 2),
+                    MHCA_stage(in_dim[s], in_dim[s + 1], num_layers[s], num_heads[s], mlp_ratios[s], num_path[s],
+                               norm_cfg='BN', drop_path_list=dpr[s], concat=concat, use_sa=use_sa_list[s],
+                               sa_ker=sa_ker))
+        self.patch_embed1 = OverlapPatchEmbeddings(image_size, 7, 4, 3, 3, in_dim[0])
+        self.cpe = ConvPosEnc(in_dim[0], k=3)  # dead (call commented out in the reference, MSTr.py:1716)
+        self.block1 = nn.ModuleList([
+            EfficientTransformerBlock(in_dim[0], key_dim[0], value_dim[0], head_count, token_mlp)
+            for _ in range(layers[0])])
+        self.norm1 = nn.LayerNorm(in_dim[0])
+
+    def nhwc(self, x):
+        """[B,3,H,W] image -> four NHWC maps."""
+        B = x.shape[0]
+        t, H, W = self.patch_embed1(x)
+        for blk in self.block1:
+            t = blk(t, H, W)
+        t = ops.layernorm(t, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        cur = t.view(B, H, W, -1)
+        outs = [cur]
+        for s in (2, 3, 4):
+            stacked = getattr(self, 'patch_embed_stage%d' % s).nhwc(cur)
+            cur = getattr(self, 'mhca_stage%d' % s).nhwc(stacked)
+            outs.append(cur)
+        return outs
+
+    def forward(self, x):
+        return [_as_nchw(m) for m in self.nhwc(x)]
+
+
+# --------------------------------------------------------------------------------------
+# Dual Transformer Bridge (reference MSTr.py:2209-2442)
+# --------------------------------------------------------------------------------------
+class Scale_reduce(nn.Module):
+    def __init__(self, dim, reduction_ratio):
+        super().__init__()
+        if len(reduction_ratio) != 4:
+            raise NotImplementedError("Scale_reduce is built for the 4-scale bridge")
+        self.dim = dim
+        self.reduction_ratio = reduction_ratio
+        self.sr0 = nn.Conv2d(dim, dim, reduction_ratio[3], reduction_ratio[3])
+        self.sr1 = nn.Conv2d(dim * 2, dim * 2, reduction_ratio[2], reduction_ratio[2])
+        self.sr2 = nn.Conv2d(dim * 5, dim * 5, reduction_ratio[1], reduction_ratio[1])
+        self.norm = nn.LayerNorm(dim)
+
+    def args(self):
+        return (self.sr0.weight, self.sr0.bias, self.sr1.weight, self.sr1.bias, self.sr2.weight, self.sr2.bias,
+                self.norm.weight, self.norm.bias, self.norm.eps)
+
+    def forward(self, x):
+        return ops.scale_reduce(x.contiguous(), *self.args())
+
+
+class M_EfficientSelfAtten(nn.Module):
+    def __init__(self, dim, head, reduction_ratio):
+        super().__init__()
+        if head != 1 or dim != 64:
+            raise NotImplementedError("bridge attention is built for dim=64, head=1")
+        self.head = head
+        self.reduction_ratio = reduction_ratio
+        self.scale = (dim // head) ** -0.5
+        self.q = nn.Linear(dim, dim, bias=True)
+        self.kv = nn.Linear(dim, dim * 2, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        if reduction_ratio is not None:
+            self.scale_reduce = Scale_reduce(dim, reduction_ratio)
+
+    def args(self):
+        return (self.scale, self.q.weight, self.q.bias, self.kv.weight, self.kv.bias,
+                self.proj.weight, self.proj.bias) + self.scale_reduce.args()
+
+    def forward(self, x, residual=None):
+        return ops.bridge_sr_attn(x.contiguous(), *self.args(), residual=residual)
+
+
+class M_EfficientChannelAtten(nn.Module):
+    """Layer-1 bridge attention; its ``scale_reduce`` is dead (reference MSTr.py:2306-2307)."""
+
+    def __init__(self, dim, head, reduction_ratio):
+        super().__init__()
+        if head != 1:
+            raise NotImplementedError("bridge channel attention is built for head=1")
+        self.head = head
+        self.reduction_ratio = reduction_ratio
+        self.scale = (dim // head) ** -0.5
+        self.q = nn.Linear(dim, dim, bias=True)
+        self.k = nn.Linear(dim, dim, bias=True)
+        self.v = nn.Linear(dim, dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        if reduction_ratio is not None:
+            self.scale_reduce = Scale_reduce(dim, reduction_ratio)
+
+    def forward(self, x, residual=None):
+        return ops.eff_attn(x.contiguous(), self.k.weight, self.k.bias, self.q.weight, self.q.bias,
+                            self.v.weight, self.v.bias, self.proj.weight, self.proj.bias,
+                            residual=residual, reinterpret=True)
+
+
+class BridgLayer_4(nn.Module):
+    def __init__(self, dims, head, reduction_ratios, ch_att):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dims)
+        self.attn = (M_EfficientChannelAtten if ch_att else M_EfficientSelfAtten)(dims, head, reduction_ratios)
+        self.norm2 = nn.LayerNorm(dims)
+        self.mixffn1 = MixFFN_skip(dims, dims * 4)
+        self.mixffn2 = MixFFN_skip(dims * 2, dims * 8)
+        self.mixffn3 = MixFFN_skip(dims * 5, dims * 20)
+        self.mixffn4 = MixFFN_skip(dims * 8, dims * 32)
+
+    def forward(self, inputs):
+        if isinstance(inputs, (list, tuple)):
+            # a C_k-channel NHWC pixel is C_k/64 consecutive 64-wide tokens
+            inputs = ops.bridge_regroup([_nhwc(c) for c in inputs])
+        x = inputs.contiguous()
+        B, N, C = x.shape
+        n1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        tx1 = self.attn(n1, residual=x)
+        tx = ops.layernorm(tx1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return ops.bridge_mixffn(tx, tx1, [m.args() for m in (self.mixffn1, self.mixffn2, self.mixffn3, self.mixffn4)])
+
+
+class BridgeBlock_4(nn.Module):
+    def __init__(self, dims, head, reduction_ratios, br_ch_att_list):
+        super().__init__()
+        for i in range(4):
+            setattr(self, 'bridge_layer%d' % (i + 1), BridgLayer_4(dims, head, reduction_ratios, br_ch_att_list[i]))
+
+    def tokens(self, x):
+        for i in range(4):
+            x = getattr(self, 'bridge_layer%d' % (i + 1))(x)
+        return x
+
+    def forward(self, x):
+        t = self.tokens(x)
+        B, _, C = t.shape
+        outs, off = [], 0
+        for hw, mult in ((56, 1), (28, 2), (14, 5), (7, 8)):
+            n = hw * hw * mult
+            outs.append(t[:, off:off + n, :].reshape(B, hw, hw, C * mult).permute(0, 3, 1, 2))
+            off += n
+        return outs
+
+
+# --------------------------------------------------------------------------------------
+# Top level (reference MSTr.py:2759-2852)
+# --------------------------------------------------------------------------------------
+class MSTransception(nn.Module):
+    def __init__(self, num_classes=9, head_count=8, dil_conv=1, token_mlp_mode="mix_skip", MSViT_config=2,
+                 concat='coord', have_bridge='original', use_sa_config=1, sa_ker=7, Stage_3or4=3, inter='res',
+                 num_sp=1, br_ch_att_list=[True, False, False, False]):
+        super().__init__()
+        if Stage_3or4 != 3:
+            raise NotImplementedError("only Stage_3or4=3 (MSViT) is built")
+        if have_bridge in ('sp', 'para'):
+            raise NotImplementedError("only have_bridge='original' (BridgeBlock_4) is built")
+        dims = [64, 128, 320, 512]
+        use_sa_list = [True, True, True, False]
+        self.backbone = MSViT(image_size=224, in_dim=dims, key_dim=dims, value_dim=dims, layers=[2, 2, 2, 2],
+                              head_count=head_count, dil_conv=dil_conv, token_mlp=token_mlp_mode,
+                              MSViT_config=MSViT_config, concat=concat, use_sa_list=use_sa_list, sa_ker=sa_ker)
+        self.reduction_ratios = [1, 2, 4, 8]
+        self.have_bridge = have_bridge
+        self.bridge = BridgeBlock_4(64, 1, self.reduction_ratios, br_ch_att_list)
+        fs = 7
+        io = [[32, 64, 64, 64], [144, 128, 128, 128], [288, 320, 320, 320], [512, 512, 512, 512]]
+        self.decoder_3 = MyDecoderLayer((fs, fs), io[3], head_count, token_mlp_mode, n_class=num_classes)
+        self.decoder_2 = MyDecoderLayer((fs * 2, fs * 2), io[2], head_count, token_mlp_mode, n_class=num_classes)
+        self.decoder_1 = MyDecoderLayer((fs * 4, fs * 4), io[1], head_count, token_mlp_mode, n_class=num_classes)
+        self.decoder_0 = MyDecoderLayer((fs * 8, fs * 8), io[0], head_count, token_mlp_mode, n_class=num_classes,
+                                        is_last=True)
+
+    def forward(self, x):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "transception_b200 round 1 builds the forward path only: call under torch.no_grad() "
+                "(backward kernels are scheduled next, see DESIGN.md)")
+        ops.require_cuda(x)
+        if x.size(1) == 1:
+            x = x.expand(-1, 3, -1, -1)  # stem kernel reads the grey plane three times; no copy
+        maps = self.backbone.nhwc(x)
+        if self.have_bridge != "None":
+            maps = [m.permute(0, 2, 3, 1) for m in self.bridge(ops.bridge_regroup(maps))]
+        b, _, _, c = maps[3].shape
+        t3 = self.decoder_3(maps[3].reshape(b, -1, c))
+        t2 = self.decoder_2(t3, maps[2])
+        t1 = self.decoder_1(t2, maps[1])
+        return self.decoder_0(t1, maps[0])
