@@ -1,0 +1,134 @@
+/* transception_sm100.h — C ABI of libtransception_sm100.so (sm_100a only).
+ *
+ * The reference (xmindflow/TransCeption) has no FFI: its plugin surface for the hot path is the nn.Module
+ * forward of networks/MSTr.py.  Each entry point below replaces the ATen op sequence of ONE reference
+ * forward (cited per function, lines of /root/reference/networks/MSTr.py) and is what a cgo/JNI/ctypes
+ * style binding of that forward would call.  The Python binding used by this repo is
+ * transception_b200/ops.py (ctypes); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every tensor is dense fp32 in device memory, tokens-major [B,N,C] / NHWC [B,H,W,C] unless stated;
+ *  - the library never allocates, frees or retains device memory: outputs and `ws` scratch are caller-owned,
+ *    sized by the matching *_workspace_bytes() call; pointers must be 16-byte aligned;
+ *  - kernels are enqueued on `stream` (a cudaStream_t) of the current device, no host synchronisation
+ *    (safe under CUDA-graph capture);
+ *  - return value 0 = OK; non-zero = failure, message via tcx_last_error() (thread-local);
+ *  - BatchNorm arguments are (weight, bias, running_mean, running_var, eps): inference statistics.
+ *  - `p` arguments are host arrays of device pointers in the documented slot order.
+ */
+#ifndef TRANSCEPTION_SM100_H
+#define TRANSCEPTION_SM100_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* tcx_version(void);
+const char* tcx_last_error(void);
+/* 1 when a usable sm_100 device is current, else 0 (with tcx_last_error set) */
+int tcx_device_ok(void);
+/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc"}; value 0/1; returns previous value */
+int tcx_set_flag(const char* name, int value);
+
+/* K10 — nn.LayerNorm over the last dim (MSTr.py:153,156,1671,2360,2366; eps 1e-6 at :932-933) */
+int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,
+                      void* stream);
+
+/* nn.Linear: y[M,N] = act(x[M,K] w[N,K]^T + bias) + residual;  act: 0 none 1 GELU(erf) 2 Hardswish 3 sigmoid */
+int tcx_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
+                   int K, int act, void* stream);
+/* Conv2d_BN 1x1 (MSTr.py:399-404): y = act(BN(x w^T)) */
+int tcx_linear_bn_act_fwd(const float* x, const float* w, const float* bn_w, const float* bn_b, const float* bn_rm,
+                          const float* bn_rv, float bn_eps, int act, float* y, int M, int N, int K, void* stream);
+
+/* K9 — OverlapPatchEmbeddings.forward (MSTr.py:299-304): conv7x7/4 pad 3 (3->64) + LayerNorm.
+ * x is NCHW [B,Cin,H,W] with Cin in {1,3}; Cin==1 is read as three identical planes (MSTr.py:2828-2829). */
+int tcx_patch_embed_ln_fwd(const float* x, int B, int Cin, int H, int W, const float* w, const float* bias,
+                           const float* lnw, const float* lnb, float eps, float* out, void* stream);
+
+/* K3 — ConvPosEnc / DWConv (MSTr.py:744-752, :26-31): y = dw3x3(x)+b (+x when add_input) */
+int tcx_dwconv_tokens_fwd(const float* x, const float* w, const float* b, float* y, int B, int H, int W, int C,
+                          int add_input, void* stream);
+
+/* K8 — EfficientAttention.forward (MSTr.py:106-143) and, with reinterpret=1, M_EfficientChannelAtten.forward
+ * (MSTr.py:2309-2353, raw [N,C]->[C,N] reinterpretation).  y = residual + reproj(att(xn)).
+ * p = {k_w,k_b,q_w,q_b,v_w,v_b,reproj_w,reproj_b} */
+size_t tcx_eff_attn_workspace_bytes(int B, int N, int C);
+int tcx_eff_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C,
+                     int reinterpret, void* ws, void* stream);
+
+/* K1 — MixFFN_skip.forward (MSTr.py:58-61): y = residual + fc2(GELU(LN(dw3x3(fc1 x)+fc1 x)))
+ * p = {fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b} */
+size_t tcx_mixffn_skip_workspace_bytes(int B, int N, int C4);
+int tcx_mixffn_skip_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B,
+                        int H, int W, int C, int C4, void* ws, void* stream);
+
+/* K2 — FactorAtt_ConvRelPosEnc.forward (MSTr.py:852-886, ConvRelPosEnc :801-823)
+ * p = {qkv_w,qkv_b,crpe_w3,crpe_b3,crpe_w5,crpe_b5,crpe_w7,crpe_b7,proj_w,proj_b}; y = residual + proj(...) */
+size_t tcx_mb_factor_attn_workspace_bytes(int B, int N, int C);
+int tcx_mb_factor_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W,
+                           int C, int heads, void* ws, void* stream);
+
+/* K2+K3+K1 — G parallel branches x L chained MHCABlock.forward (MSTr.py:935-946), in place on x[G][B][N][C].
+ * p holds G*L blocks of TCX_MHCA_NP pointers:
+ * {cpe_w,cpe_b,n1_w,n1_b,qkv_w,qkv_b,crpe_w3,crpe_b3,crpe_w5,crpe_b5,crpe_w7,crpe_b7,proj_w,proj_b,
+ *  n2_w,n2_b,fc1_w,fc1_b,dw_w,dw_b,mlp_ln_w,mlp_ln_b,fc2_w,fc2_b}, block (g,l) at p[(g*L+l)*TCX_MHCA_NP] */
+#define TCX_MHCA_NP 24
+size_t tcx_mhca_blocks_workspace_bytes(int G, int B, int N, int C);
+int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int H, int W, int C, int heads,
+                        float ln_eps, float mlp_ln_eps, void* ws, void* stream);
+
+/* K4 — DWConv2d_BN.forward (MSTr.py:355-362): Hardswish(BN(pw1x1(dw3x3_stride(x)))), NHWC */
+size_t tcx_ripm_dwsep_bn_hs_workspace_bytes(int B, int H, int W, int C, int stride);
+int tcx_ripm_dwsep_bn_hs_fwd(const float* x, const float* dw_w, const float* pw_w, const float* bn_w,
+                             const float* bn_b, const float* bn_rm, const float* bn_rv, float bn_eps, float* y, int B,
+                             int H, int W, int C, int stride, void* ws, void* stream);
+
+/* K5 — ResBlock.forward (MSTr.py:1042-1050), NHWC.
+ * p = {c1_w, bn1_w,bn1_b,bn1_rm,bn1_rv, dw_w, bn2_w,bn2_b,bn2_rm,bn2_rv, c2_w, bn3_w,bn3_b,bn3_rm,bn3_rv} */
+size_t tcx_resblock_workspace_bytes(int B, int H, int W, int C);
+int tcx_resblock_fwd(const float* x, const void* const* p, float bn_eps, float* y, int B, int H, int W, int C,
+                     void* ws, void* stream);
+
+/* K6 — IFF: CoordAtt.forward (MSTr.py:1322-1348) over the channel concatenation of nsrc NHWC maps of C channels
+ * each (nsrc*C = inp; the concatenation is never materialised).
+ * p = {conv1_w,conv1_b,bn_w,bn_b,bn_rm,bn_rv,convh_w,convh_b,convw_w,convw_b,out_w,out_b} */
+size_t tcx_iff_coordatt_workspace_bytes(int B, int HW, int C, int mip);
+int tcx_iff_coordatt_fwd(const void* const* maps, const void* const* p, float bn_eps, float* y, int B, int HW, int C,
+                         int mip, int Cout, void* ws, void* stream);
+
+/* K10 — BridgLayer_4 tokenisation (MSTr.py:2380-2386): four NHWC maps [B,S/2^k,S/2^k,{64,128,320,512}]
+ * -> [B, Ntok, 64]; S = side of the stage-1 map (56 at 224x224). */
+int tcx_bridge_regroup_fwd(const void* const* maps, float* tokens, int B, int S, void* stream);
+
+/* Scale_reduce.forward (MSTr.py:2225-2249) -> [B, Nred, 64].  p = {sr0_w,sr0_b,sr1_w,sr1_b,sr2_w,sr2_b,ln_w,ln_b} */
+size_t tcx_scale_reduce_workspace_bytes(int B, int S);
+int tcx_scale_reduce_fwd(const float* x, const void* const* p, float ln_eps, float* out, int B, int S, void* ws,
+                         void* stream);
+
+/* K7 — M_EfficientSelfAtten.forward (MSTr.py:2267-2292): y = residual + proj(softmax(q k^T / 8) v)
+ * p = {q_w,q_b,kv_w,kv_b,proj_w,proj_b, sr0_w,sr0_b,sr1_w,sr1_b,sr2_w,sr2_b,srln_w,srln_b} */
+size_t tcx_bridge_sr_attn_workspace_bytes(int B, int S);
+int tcx_bridge_sr_attn_fwd(const float* xn, const void* const* p, float scale, float ln_eps, const float* residual,
+                           float* y, int B, int S, void* ws, void* stream);
+
+/* BridgLayer_4.forward tail (MSTr.py:2394-2406): y = tx1 + cat_k MixFFN_k(tx slab k).  p = 4 x the K1 slots. */
+size_t tcx_bridge_mixffn_workspace_bytes(int B, int S);
+int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* p, float ln_eps, float* y, int B,
+                          int S, void* ws, void* stream);
+
+/* decoder — MyDecoderLayer.forward pieces (MSTr.py:273-290, :184-201, :212-227) */
+int tcx_concat_linear_fwd(const float* x1, const float* x2, const float* w, const float* b, float* y, int M, int C1,
+                          int C2, int N, void* stream);
+size_t tcx_patch_expand_workspace_bytes(int B, int H, int W, int C, int scale);
+int tcx_patch_expand_fwd(const float* x, const float* w, const float* lnw, const float* lnb, float eps, float* y,
+                         int B, int H, int W, int C, int scale, void* ws, void* stream);
+size_t tcx_final_expand_head_workspace_bytes(int B, int H, int W);
+int tcx_final_expand_head_fwd(const float* x, const float* w, const float* lnw, const float* lnb, float eps,
+                              const float* cls_w, const float* cls_b, int ncls, float* logits_nchw, int B, int H,
+                              int W, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

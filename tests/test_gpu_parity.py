@@ -1,0 +1,301 @@
+"""GPU parity: every fused op of the hot path (called through the drop-in modules -> C ABI -> sm_100a kernels)
+against the CPU oracle on the same seeded weights and inputs.
+
+Tolerances (stated): tensor-core kernels compute in TF32 / bf16 with fp32 accumulation, so the bar
+for fp32-IO with tensor-core MMA applies: max-abs <= 2e-2 * max(1, absmax) per op, logits max-abs <= 5e-2,
+mean-abs <= 5e-3, argmax Dice >= 0.99.  With the tensor-core back ends switched off (FFMA kernels) the strict
+fp32 bar applies: <= 1e-4 * max(1, absmax).
+"""
+import pytest
+import torch
+
+from oracle import mstr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TC_TOL = 2e-2
+FP32_TOL = 1e-4
+
+
+def _randomise(net, seed=5):
+    """Make every affine / running-stat tensor non-trivial so parity exercises it."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (torch.nn.LayerNorm, torch.nn.BatchNorm2d)):
+                m.weight.copy_(1 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear)) and m.bias is not None:
+                m.bias.copy_(0.05 * torch.randn(m.bias.shape, generator=g))
+    return net
+
+
+@pytest.fixture(scope="module")
+def model(cuda_lib):
+    from networks.MSTr import MSTransception
+    torch.manual_seed(1234)
+    net = _randomise(MSTransception(num_classes=9)).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    return net.cuda(), sd
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def _close(got, want, tol, what):
+    got = got.float().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    if want.numel() == 0:
+        return 0.0
+    assert torch.isfinite(got).all(), what + ": non-finite output"
+    err = (got - want).abs().max().item()
+    ref = max(1.0, want.abs().max().item())
+    assert err <= tol * ref, "%s: max-abs err %.3e > %.1e * %.3g" % (what, err, tol, ref)
+    return err
+
+
+@pytest.fixture(params=["tc", "ffma"])
+def backend(request, cuda_lib):
+    from transception_b200 import ops
+    on = 1 if request.param == "tc" else 0
+    ops.set_flag("gemm_tc", on)
+    ops.set_flag("flash_tc", on)
+    yield (TC_TOL if on else FP32_TOL)
+    ops.set_flag("gemm_tc", 1)
+    ops.set_flag("flash_tc", 1)
+
+
+# ---- primitives ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,C", [(7, 64), (1000, 128), (333, 320), (50, 512), (9, 1280), (5, 2048), (0, 64)])
+def test_layernorm(cuda_lib, M, C):
+    from transception_b200 import ops
+    x, w, b = _rand(M, C, seed=1, scale=3.0) + 0.5, _rand(C, seed=2), _rand(C, seed=3)
+    want = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-6)
+    got = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6)
+    _close(got, want, 2e-5, "layernorm")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 192, 64), (777, 320, 1280), (49, 2048, 512), (130, 9, 64),
+                                   (3, 16, 256), (12544, 256, 64), (257, 960, 320)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear(backend, M, N, K, act):
+    from transception_b200 import ops
+    x, w, b, r = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3), _rand(M, N, seed=4)
+    want = torch.nn.functional.linear(x, w, b)
+    if act == 1:
+        want = torch.nn.functional.gelu(want)
+    want = want + r
+    got = ops.linear(x.cuda(), w.cuda(), b.cuda(), act=act, residual=r.cuda())
+    _close(got, want, backend, "linear")
+
+
+# ---- stage 1 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cin", [1, 3])
+def test_patch_embed(model, cin):
+    net, sd = model
+    x = _rand(2, cin, 224, 224, seed=11)
+    want, H, W = O.patch_embed(sd, 'backbone.patch_embed1', x.repeat(1, 3, 1, 1) if cin == 1 else x)
+    got, h, w = net.backbone.patch_embed1(x.cuda())
+    assert (h, w) == (H, W) == (56, 56)
+    _close(got, want, FP32_TOL, "patch_embed_ln")
+
+
+def test_efficient_block(model, backend):
+    net, sd = model
+    x = _rand(2, 3136, 64, seed=12)
+    want = O.efficient_block(sd, 'backbone.block1.0', x, 56, 56)
+    got = net.backbone.block1[0](x.cuda(), 56, 56)
+    _close(got, want, backend, "EfficientTransformerBlock")
+
+
+def test_efficient_attention_nchw(model, backend):
+    net, sd = model
+    x = _rand(2, 64, 56, 56, seed=13)
+    want = O.efficient_attention(sd, 'backbone.block1.1.attn', x)
+    got = net.backbone.block1[1].attn(x.cuda())
+    _close(got, want, backend, "EfficientAttention")
+
+
+@pytest.mark.parametrize("path,hw,C", [("backbone.block1.0.mlp", 56, 64), ("backbone.mhca_stage3.mhca_blks.1.MHCA_layers.2.mlp", 14, 128),
+                                       ("backbone.mhca_stage4.mhca_blks.0.MHCA_layers.0.mlp", 7, 320),
+                                       ("bridge.bridge_layer2.mixffn4", 7, 512), ("bridge.bridge_layer1.mixffn2", 28, 128)])
+def test_mixffn_skip(model, backend, path, hw, C):
+    net, sd = model
+    mod = net.get_submodule(path)
+    x = _rand(3, hw * hw, C, seed=14)
+    want = O.mixffn_skip(sd, path, x, hw, hw)
+    got = mod(x.cuda(), hw, hw)
+    _close(got, want, backend, "MixFFN_skip " + path)
+
+
+# ---- RIPM / ResBlock / MB stage / IFF ----------------------------------------------------------------
+@pytest.mark.parametrize("stage,C,hw", [(2, 64, 56), (3, 128, 28), (4, 320, 14)])
+def test_ripm(model, backend, stage, C, hw):
+    net, sd = model
+    x = _rand(2, C, hw, hw, seed=15)
+    p = 'backbone.patch_embed_stage%d' % stage
+    want = O.patch_embed_stage(sd, p, x)
+    got = net.get_submodule(p)(x.cuda())
+    for i in range(3):
+        _close(got[i], want[i], backend, "RIPM path %d" % i)
+
+
+@pytest.mark.parametrize("stage,C,hw", [(2, 64, 28), (3, 128, 14), (4, 320, 7)])
+def test_resblock(model, backend, stage, C, hw):
+    net, sd = model
+    x = _rand(2, C, hw, hw, seed=16)
+    p = 'backbone.mhca_stage%d.InvRes' % stage
+    _close(net.get_submodule(p)(x.cuda()), O.resblock(sd, p, x), backend, "ResBlock")
+
+
+@pytest.mark.parametrize("stage,C,hw", [(2, 64, 28), (3, 128, 14), (4, 320, 7)])
+def test_mb_attention(model, backend, stage, C, hw):
+    net, sd = model
+    x = _rand(2, hw * hw, C, seed=17)
+    p = 'backbone.mhca_stage%d.mhca_blks.1.MHCA_layers.0.factoratt_crpe' % stage
+    want = O.factor_att(sd, p, x, hw, hw)
+    got = net.get_submodule(p)(x.cuda(), (hw, hw))
+    _close(got, want, backend, "FactorAtt_ConvRelPosEnc")
+
+
+@pytest.mark.parametrize("stage,C,hw,L", [(2, 64, 28, 3), (3, 128, 14, 8), (4, 320, 7, 3)])
+def test_mhca_encoder(model, backend, stage, C, hw, L):
+    net, sd = model
+    x = _rand(2, hw * hw, C, seed=18)
+    p = 'backbone.mhca_stage%d.mhca_blks.2' % stage
+    want = O.mhca_encoder(sd, p, x, hw, hw, L)
+    got = net.get_submodule(p)(x.cuda(), (hw, hw))
+    _close(got, want, backend * 2, "MHCAEncoder")
+
+
+@pytest.mark.parametrize("stage,C,hw", [(2, 64, 28), (3, 128, 14), (4, 320, 7)])
+def test_iff_coordatt(model, backend, stage, C, hw):
+    net, sd = model
+    x = _rand(2, 4 * C, hw, hw, seed=19)
+    p = 'backbone.mhca_stage%d.aggregate' % stage
+    _close(net.get_submodule(p)(x.cuda()), O.coord_att(sd, p, x), backend, "CoordAtt")
+
+
+@pytest.mark.parametrize("stage,C,hw,L", [(2, 64, 28, 3), (4, 320, 7, 3)])
+def test_mhca_stage(model, backend, stage, C, hw, L):
+    net, sd = model
+    xs = [_rand(2, C, hw, hw, seed=20 + i) for i in range(3)]
+    p = 'backbone.mhca_stage%d' % stage
+    want = O.mhca_stage(sd, p, xs, L)
+    got = net.get_submodule(p)([x.cuda() for x in xs])
+    _close(got, want, backend * 2, "MHCA_stage")
+
+
+# ---- bridge ----------------------------------------------------------------------------------------------
+def _bridge_maps(seed):
+    return [_rand(2, c, s, s, seed=seed + i) for i, (c, s) in enumerate(((64, 56), (128, 28), (320, 14), (512, 7)))]
+
+
+def test_bridge_regroup(model):
+    from transception_b200 import ops
+    maps = _bridge_maps(30)
+    want = O.bridge_tokens(maps)
+    got = ops.bridge_regroup([m.permute(0, 2, 3, 1).contiguous().cuda() for m in maps])
+    assert torch.equal(got.cpu(), want)
+
+
+def test_scale_reduce(model, backend):
+    net, sd = model
+    x = _rand(2, 6076, 64, seed=31)
+    p = 'bridge.bridge_layer2.attn.scale_reduce'
+    _close(net.get_submodule(p)(x.cuda()), O.scale_reduce(sd, p, x), backend, "Scale_reduce")
+
+
+@pytest.mark.parametrize("scale", [1.0, 6.0])
+def test_bridge_self_attention(model, backend, scale):
+    net, sd = model
+    x = _rand(2, 6076, 64, seed=32, scale=scale)   # scale 6 drives attention scores to |s| ~ 20
+    p = 'bridge.bridge_layer3.attn'
+    _close(net.get_submodule(p)(x.cuda()), O.bridge_self_atten(sd, p, x), backend, "M_EfficientSelfAtten")
+
+
+def test_bridge_channel_attention(model, backend):
+    net, sd = model
+    x = _rand(2, 6076, 64, seed=33)
+    p = 'bridge.bridge_layer1.attn'
+    _close(net.get_submodule(p)(x.cuda()), O.bridge_channel_atten(sd, p, x), backend, "M_EfficientChannelAtten")
+
+
+@pytest.mark.parametrize("layer,ch", [(1, True), (2, False)])
+def test_bridge_layer(model, backend, layer, ch):
+    net, sd = model
+    maps = _bridge_maps(34)
+    p = 'bridge.bridge_layer%d' % layer
+    want = O.bridge_layer(sd, p, O.bridge_tokens(maps), ch)
+    got = net.get_submodule(p)([m.cuda() for m in maps])
+    _close(got, want, backend * 2, "BridgLayer_4")
+
+
+# ---- decoder ---------------------------------------------------------------------------------------------
+def test_decoder_layers(model, backend):
+    net, sd = model
+    x3 = _rand(2, 49, 512, seed=40)
+    want3 = O.decoder_layer(sd, 'decoder_3', x3)
+    got3 = net.decoder_3(x3.cuda())
+    _close(got3, want3, backend, "decoder_3")
+    x2 = _rand(2, 14, 14, 320, seed=41)
+    want2 = O.decoder_layer(sd, 'decoder_2', want3, x2)
+    got2 = net.decoder_2(want3.cuda(), x2.cuda())
+    _close(got2, want2, backend * 2, "decoder_2")
+    x0 = _rand(2, 56, 56, 64, seed=42)
+    t1 = _rand(2, 3136, 64, seed=43)
+    want0 = O.decoder_layer(sd, 'decoder_0', t1, x0, is_last=True)
+    got0 = net.decoder_0(t1.cuda(), x0.cuda())
+    _close(got0, want0, backend * 2, "decoder_0")
+
+
+# ---- whole model ---------------------------------------------------------------------------------------------
+def _dice(a, b, ncls):
+    d = []
+    for c in range(ncls):
+        x, y = a == c, b == c
+        den = x.sum().item() + y.sum().item()
+        if den:
+            d.append(2.0 * (x & y).sum().item() / den)
+    return min(d)
+
+
+@pytest.mark.parametrize("cin,bs", [(1, 2), (3, 1)])
+def test_whole_model(model, backend, cin, bs):
+    net, sd = model
+    x = torch.rand(bs, cin, 224, 224, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    want = O.forward(sd, x, return_all=True)
+    with torch.no_grad():
+        maps = net.backbone(x.cuda())
+        for i in range(4):
+            _close(maps[i], want['enc'][i], backend * 3, "encoder map %d" % i)
+        br = net.bridge(maps)
+        for i in range(4):
+            _close(br[i], want['bridge'][i], backend * 3, "bridge map %d" % i)
+        got = net(x.cuda()).float().cpu()
+    w = want['logits']
+    assert got.shape == w.shape == (bs, 9, 224, 224)
+    err, mean = (got - w).abs().max().item(), (got - w).abs().mean().item()
+    dice = _dice(got.argmax(1), w.argmax(1), 9)
+    print("logits max-abs %.3e mean-abs %.3e min-class Dice %.5f" % (err, mean, dice))
+    if backend == FP32_TOL:
+        assert err <= 2e-4 and dice >= 0.999
+    else:
+        assert err <= 5e-2 and mean <= 5e-3 and dice >= 0.99
+
+
+def test_forward_fails_loudly_on_cpu_tensor(model):
+    net, _ = model
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            net(torch.zeros(1, 3, 224, 224))
+
+
+def test_train_mode_refused(model):
+    net, _ = model
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 224, 224, device="cuda"))

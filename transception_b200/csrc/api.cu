@@ -1,0 +1,608 @@
+// extern "C" surface of libtransception_sm100.so: one entry point per reference forward (see
+// include/transception_sm100.h).  Each function only carves the caller's workspace and enqueues kernels.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/transception_sm100.h"
+#include "common.cuh"
+#include "attention.cuh"
+#include "misc.cuh"
+
+// ---- error state -----------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void tcx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int tcx_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    tcx_set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+static int g_flag_gemm_tc = 1;
+static int g_flag_flash_tc = 1;
+bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
+bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
+
+namespace {
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline const float* F(const void* p) { return reinterpret_cast<const float*>(p); }
+
+struct Carver {
+  float* base;
+  size_t off = 0;
+  explicit Carver(void* ws) : base(reinterpret_cast<float*>(ws)) {}
+  float* take(size_t nfloats) {
+    float* p = base + off;
+    off += (nfloats + 63) / 64 * 64;   // keep 256-byte alignment
+    return p;
+  }
+};
+inline size_t rnd(size_t nfloats) { return (nfloats + 63) / 64 * 64; }
+
+struct BridgeGeom {
+  int hw[4], ch[4], off[5], ntok;
+  int P, pp, red_off[4], nred;
+};
+inline bool bridge_geom(int S0, BridgeGeom& g) {
+  if (S0 <= 0 || S0 % 8) return false;
+  const int ch[4] = {64, 128, 320, 512};
+  g.off[0] = 0;
+  for (int k = 0; k < 4; k++) {
+    g.hw[k] = S0 >> k;
+    g.ch[k] = ch[k];
+    g.off[k + 1] = g.off[k] + g.hw[k] * g.hw[k] * (ch[k] / 64);
+  }
+  g.ntok = g.off[4];
+  g.P = S0 / 8;
+  g.pp = g.P * g.P;
+  g.red_off[0] = 0;
+  g.red_off[1] = g.pp;
+  g.red_off[2] = g.pp * 3;
+  g.red_off[3] = g.pp * 8;
+  g.nred = g.pp * 8 + (g.off[4] - g.off[3]);
+  return true;
+}
+
+GemmParams gemm1(const float* A, const float* W, float* C, int M, int N, int K) {
+  GemmParams p{};
+  p.groups = 1; p.batch = 1;
+  p.M = M; p.N = N; p.K = K; p.lda = K; p.ldw = K; p.ldc = N;
+  p.g[0].A = A; p.g[0].W = W; p.g[0].C = C;
+  p.g[0].epi.ldr = N;
+  return p;
+}
+
+// Mix-FFN on G groups: xn -> y (+residual). hbuf/abuf: [G][B*N*C4]
+int run_mixffn(int G, const float* const* xn, const void* const* const* pp, float eps, const float* const* residual,
+               float* const* y, int B, int H, int W, int C, int C4, float* hbuf, float* abuf, cudaStream_t st) {
+  const int M = B * H * W;
+  const size_t per = (size_t)M * C4;
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, M, C4, C);
+    g.groups = G;
+    for (int i = 0; i < G; i++) {
+      g.g[i].A = xn[i]; g.g[i].W = F(pp[i][0]); g.g[i].C = hbuf + i * per;
+      g.g[i].epi.bias = F(pp[i][1]); g.g[i].epi.ldr = C4;
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  {
+    MixMidGroup mg[TCX_MAX_GROUPS];
+    for (int i = 0; i < G; i++)
+      mg[i] = MixMidGroup{hbuf + i * per, F(pp[i][2]), F(pp[i][3]), F(pp[i][4]), F(pp[i][5]), abuf + i * per};
+    TCX_TRY(launch_mixffn_mid(mg, G, B, H, W, C4, eps, st));
+  }
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, M, C, C4);
+    g.groups = G;
+    for (int i = 0; i < G; i++) {
+      g.g[i].A = abuf + i * per; g.g[i].W = F(pp[i][6]); g.g[i].C = y[i];
+      g.g[i].epi.bias = F(pp[i][7]); g.g[i].epi.residual = residual ? residual[i] : nullptr; g.g[i].epi.ldr = C;
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  return 0;
+}
+
+// MB attention on G groups: xn -> y = residual + proj(attn). qkv [G][M*3C], ctx [G][B*C*Ch], att [G][M*C]
+int run_mb_attn(int G, const float* const* xn, const void* const* const* pp, const float* const* residual,
+                float* const* y, int B, int H, int W, int C, int heads, float* qkv, float* ctx, float* att,
+                cudaStream_t st) {
+  const int M = B * H * W, Ch = C / heads;
+  const size_t pq = (size_t)M * 3 * C, pc = (size_t)B * C * Ch, pa = (size_t)M * C;
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, M, 3 * C, C);
+    g.groups = G;
+    for (int i = 0; i < G; i++) {
+      g.g[i].A = xn[i]; g.g[i].W = F(pp[i][0]); g.g[i].C = qkv + i * pq;
+      g.g[i].epi.bias = F(pp[i][1]); g.g[i].epi.ldr = 3 * C;
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  {
+    MbAttnArgs a{};
+    a.groups = G; a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads;
+    a.scale = 1.0f / sqrtf((float)Ch);
+    for (int i = 0; i < G; i++) {
+      a.qkv[i] = qkv + i * pq; a.ctx[i] = ctx + i * pc; a.out[i] = att + i * pa;
+      for (int j = 0; j < 3; j++) { a.cw[i][j] = F(pp[i][2 + 2 * j]); a.cb[i][j] = F(pp[i][3 + 2 * j]); }
+    }
+    TCX_TRY(launch_mb_attention(a, st));
+  }
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, M, C, C);
+    g.groups = G;
+    for (int i = 0; i < G; i++) {
+      g.g[i].A = att + i * pa; g.g[i].W = F(pp[i][8]); g.g[i].C = y[i];
+      g.g[i].epi.bias = F(pp[i][9]); g.g[i].epi.residual = residual ? residual[i] : nullptr; g.g[i].epi.ldr = C;
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  return 0;
+}
+
+int run_scale_reduce(const float* x, const void* const* p, float eps, float* out, int B, const BridgeGeom& g, float* ws,
+                     cudaStream_t st) {
+  Carver c(ws);
+  const int ratio[3] = {8, 4, 2};
+  SrPackArgs a{};
+  const long long xs_b = (long long)g.ntok * 64;
+  for (int k = 0; k < 3; k++) {
+    const int r = ratio[k], Cin = g.ch[k];
+    const int K = Cin * r * r, M = B * g.pp;
+    float* A = c.take((size_t)M * K);
+    float* conv = c.take((size_t)M * Cin);
+    TCX_TRY(launch_sr_im2row(x + (long long)g.off[k] * 64, xs_b, g.hw[k], Cin, r, B, A, st));
+    GemmParams gp = gemm1(A, F(p[2 * k]), conv, M, Cin, K);
+    gp.g[0].epi.bias = F(p[2 * k + 1]);
+    TCX_TRY(launch_gemm(gp, st));
+    a.conv[k] = conv;
+    a.gmul[k] = Cin / 64;
+    a.pp[k] = g.pp;
+  }
+  a.x = x; a.xs_b = xs_b; a.raw_tok0 = g.off[3];
+  for (int i = 0; i < 4; i++) a.red_off[i] = g.red_off[i];
+  a.nred = g.nred; a.B = B;
+  a.lnw = F(p[6]); a.lnb = F(p[7]); a.eps = eps; a.out = out;
+  return launch_sr_pack_ln(a, st);
+}
+size_t scale_reduce_ws_floats(int B, const BridgeGeom& g) {
+  const int ratio[3] = {8, 4, 2};
+  size_t n = 0;
+  for (int k = 0; k < 3; k++) {
+    const size_t M = (size_t)B * g.pp;
+    n += rnd(M * g.ch[k] * ratio[k] * ratio[k]) + rnd(M * g.ch[k]);
+  }
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tcx_version(void) { return "transception_sm100 0.1.0 (sm_100a)"; }
+const char* tcx_last_error(void) { return g_err; }
+
+int tcx_device_ok(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    tcx_set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
+  if (prop.major != 10) {
+    tcx_set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    return 0;
+  }
+  return 1;
+}
+
+int tcx_set_flag(const char* name, int value) {
+  int* f = nullptr;
+  if (!strcmp(name, "gemm_tc")) f = &g_flag_gemm_tc;
+  else if (!strcmp(name, "flash_tc")) f = &g_flag_flash_tc;
+  if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
+  const int old = *f;
+  *f = value;
+  return old;
+}
+
+int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,
+                      void* stream) {
+  return launch_layernorm(x, w, b, y, M, C, eps, S(stream));
+}
+
+int tcx_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
+                   int K, int act, void* stream) {
+  return launch_linear(x, w, bias, residual, y, M, N, K, act, S(stream));
+}
+
+int tcx_linear_bn_act_fwd(const float* x, const float* w, const float* bn_w, const float* bn_b, const float* bn_rm,
+                          const float* bn_rv, float bn_eps, int act, float* y, int M, int N, int K, void* stream) {
+  GemmParams g = gemm1(x, w, y, M, N, K);
+  g.g[0].epi.bn = BnParams{bn_w, bn_b, bn_rm, bn_rv, bn_eps};
+  g.g[0].epi.act = act;
+  return launch_gemm(g, S(stream));
+}
+
+int tcx_patch_embed_ln_fwd(const float* x, int B, int Cin, int H, int W, const float* w, const float* bias,
+                           const float* lnw, const float* lnb, float eps, float* out, void* stream) {
+  TCX_REQUIRE(Cin == 1 || Cin == 3, "patch_embed: Cin must be 1 or 3 (got %d)", Cin);
+  const long long plane = (long long)H * W;
+  return launch_patch_embed_ln(x, Cin * plane, Cin == 1 ? 0 : plane, B, H, W, w, bias, lnw, lnb, eps, out, S(stream));
+}
+
+int tcx_dwconv_tokens_fwd(const float* x, const float* w, const float* b, float* y, int B, int H, int W, int C,
+                          int add_input, void* stream) {
+  DwGroup g{x, w, b, y};
+  return launch_dwconv3x3(&g, 1, B, H, W, C, 1, add_input ? DW_ADD_INPUT : DW_PLAIN, BnParams{}, S(stream));
+}
+
+// ---- K8 --------------------------------------------------------------------------------
+size_t tcx_eff_attn_workspace_bytes(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  return 4 * (rnd(3 * bnc) + rnd(bnc) + rnd(bnc) + rnd((size_t)B * C * C) + rnd(ea_workspace_floats(B, N, C)));
+}
+
+int tcx_eff_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C,
+                     int reinterpret, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  Carver c(ws);
+  const size_t bnc = (size_t)B * N * C;
+  float* kqv = c.take(3 * bnc);
+  float* qsm = c.take(bnc);
+  float* att = c.take(bnc);
+  float* ctxT = c.take((size_t)B * C * C);
+  float* part = c.take(ea_workspace_floats(B, N, C));
+  const int M = B * N;
+  GemmParams g = gemm1(xn, nullptr, nullptr, M, C, C);
+  g.groups = 3;
+  EaView v{};
+  for (int i = 0; i < 3; i++) {
+    g.g[i].A = xn; g.g[i].W = F(p[2 * i]); g.g[i].epi.bias = F(p[2 * i + 1]);
+    g.g[i].C = reinterpret ? kqv + i * bnc : kqv + i * C;
+  }
+  if (reinterpret) {
+    g.ldc = C;
+    v = EaView{kqv, kqv + bnc, kqv + 2 * bnc, (long long)N * C, (long long)N, 1};
+  } else {
+    g.ldc = 3 * C;
+    v = EaView{kqv, kqv + C, kqv + 2 * C, (long long)N * 3 * C, 1, (long long)3 * C};
+  }
+  TCX_TRY(launch_gemm(g, st));
+  TCX_TRY(launch_ea_context(v, reinterpret != 0, B, N, C, part, ctxT, st));
+  TCX_TRY(launch_ea_qsoftmax(v, reinterpret != 0, B, N, C, qsm, st));
+  {  // att[b] = qsm[b] (N x C) * ctx[b] (C x C): W = ctxT[b]
+    GemmParams a = gemm1(qsm, ctxT, att, N, C, C);
+    a.batch = B; a.strideA = (long long)N * C; a.strideW = (long long)C * C; a.strideC = (long long)N * C;
+    TCX_TRY(launch_gemm(a, st));
+  }
+  GemmParams r = gemm1(att, F(p[6]), y, M, C, C);
+  r.g[0].epi.bias = F(p[7]);
+  r.g[0].epi.residual = residual;
+  return launch_gemm(r, st);
+}
+
+// ---- K1 --------------------------------------------------------------------------------
+size_t tcx_mixffn_skip_workspace_bytes(int B, int N, int C4) { return 4 * 2 * rnd((size_t)B * N * C4); }
+
+int tcx_mixffn_skip_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B,
+                        int H, int W, int C, int C4, void* ws, void* stream) {
+  Carver c(ws);
+  float* h = c.take((size_t)B * H * W * C4);
+  float* a = c.take((size_t)B * H * W * C4);
+  const float* xs[1] = {xn};
+  const void* const* ps[1] = {p};
+  const float* rs[1] = {residual};
+  float* ys[1] = {y};
+  return run_mixffn(1, xs, ps, ln_eps, residual ? rs : nullptr, ys, B, H, W, C, C4, h, a, S(stream));
+}
+
+// ---- K2 --------------------------------------------------------------------------------
+size_t tcx_mb_factor_attn_workspace_bytes(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  return 4 * (rnd(3 * bnc) + rnd((size_t)B * C * C) + rnd(bnc));
+}
+
+int tcx_mb_factor_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W,
+                           int C, int heads, void* ws, void* stream) {
+  Carver c(ws);
+  const size_t bnc = (size_t)B * H * W * C;
+  float* qkv = c.take(3 * bnc);
+  float* ctx = c.take((size_t)B * C * C);
+  float* att = c.take(bnc);
+  const float* xs[1] = {xn};
+  const void* const* ps[1] = {p};
+  const float* rs[1] = {residual};
+  float* ys[1] = {y};
+  return run_mb_attn(1, xs, ps, residual ? rs : nullptr, ys, B, H, W, C, heads, qkv, ctx, att, S(stream));
+}
+
+// ---- MHCA blocks -------------------------------------------------------------------------
+size_t tcx_mhca_blocks_workspace_bytes(int G, int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  // xa, ln, xb, att (1 each), qkv (3), h, ax (4 each), ctx
+  return 4 * (size_t)G * (4 * rnd(bnc) + rnd(3 * bnc) + 2 * rnd(4 * bnc) + rnd((size_t)B * C * C));
+}
+
+int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int H, int W, int C, int heads,
+                        float ln_eps, float mlp_ln_eps, void* ws, void* stream) {
+  TCX_REQUIRE(G >= 1 && G <= TCX_MAX_GROUPS, "mhca_blocks: G=%d out of range", G);
+  cudaStream_t st = S(stream);
+  const int N = H * W, M = B * N;
+  const size_t bnc = (size_t)M * C;
+  Carver c(ws);
+  float* xa = c.take(G * bnc);
+  float* ln = c.take(G * bnc);
+  float* xb = c.take(G * bnc);
+  float* att = c.take(G * bnc);
+  float* qkv = c.take(G * 3 * bnc);
+  float* hb = c.take(G * 4 * bnc);
+  float* ab = c.take(G * 4 * bnc);
+  float* ctx = c.take((size_t)G * B * C * C);
+  for (int l = 0; l < L; l++) {
+    const void* const* blk[TCX_MAX_GROUPS];
+    for (int g = 0; g < G; g++) blk[g] = p + ((size_t)g * L + l) * TCX_MHCA_NP;
+    {  // x = x + dw3x3(x) + b   (ConvPosEnc, shared weights, applied in every block)
+      DwGroup dg[TCX_MAX_GROUPS];
+      for (int g = 0; g < G; g++) dg[g] = DwGroup{x + g * bnc, F(blk[g][0]), F(blk[g][1]), xa + g * bnc};
+      TCX_TRY(launch_dwconv3x3(dg, G, B, H, W, C, 1, DW_ADD_INPUT, BnParams{}, st));
+    }
+    {
+      LnGroup lg[TCX_MAX_GROUPS];
+      for (int g = 0; g < G; g++) lg[g] = LnGroup{xa + g * bnc, F(blk[g][2]), F(blk[g][3]), ln + g * bnc};
+      TCX_TRY(launch_layernorm_grouped(lg, G, M, C, ln_eps, st));
+    }
+    {
+      const float* xs[TCX_MAX_GROUPS]; const void* const* ps[TCX_MAX_GROUPS];
+      const float* rs[TCX_MAX_GROUPS]; float* ys[TCX_MAX_GROUPS];
+      for (int g = 0; g < G; g++) { xs[g] = ln + g * bnc; ps[g] = blk[g] + 4; rs[g] = xa + g * bnc; ys[g] = xb + g * bnc; }
+      TCX_TRY(run_mb_attn(G, xs, ps, rs, ys, B, H, W, C, heads, qkv, ctx, att, st));
+    }
+    {
+      LnGroup lg[TCX_MAX_GROUPS];
+      for (int g = 0; g < G; g++) lg[g] = LnGroup{xb + g * bnc, F(blk[g][14]), F(blk[g][15]), ln + g * bnc};
+      TCX_TRY(launch_layernorm_grouped(lg, G, M, C, ln_eps, st));
+    }
+    {
+      const float* xs[TCX_MAX_GROUPS]; const void* const* ps[TCX_MAX_GROUPS];
+      const float* rs[TCX_MAX_GROUPS]; float* ys[TCX_MAX_GROUPS];
+      for (int g = 0; g < G; g++) { xs[g] = ln + g * bnc; ps[g] = blk[g] + 16; rs[g] = xb + g * bnc; ys[g] = x + g * bnc; }
+      TCX_TRY(run_mixffn(G, xs, ps, mlp_ln_eps, rs, ys, B, H, W, C, 4 * C, hb, ab, st));
+    }
+  }
+  return 0;
+}
+
+// ---- K4 / K5 -----------------------------------------------------------------------------
+size_t tcx_ripm_dwsep_bn_hs_workspace_bytes(int B, int H, int W, int C, int stride) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  return 4 * rnd((size_t)B * Ho * Wo * C);
+}
+
+int tcx_ripm_dwsep_bn_hs_fwd(const float* x, const float* dw_w, const float* pw_w, const float* bn_w,
+                             const float* bn_b, const float* bn_rm, const float* bn_rv, float bn_eps, float* y, int B,
+                             int H, int W, int C, int stride, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  float* t = reinterpret_cast<float*>(ws);
+  DwGroup g{x, dw_w, nullptr, t};
+  TCX_TRY(launch_dwconv3x3(&g, 1, B, H, W, C, stride, DW_PLAIN, BnParams{}, st));
+  GemmParams gp = gemm1(t, pw_w, y, B * Ho * Wo, C, C);
+  gp.g[0].epi.bn = BnParams{bn_w, bn_b, bn_rm, bn_rv, bn_eps};
+  gp.g[0].epi.act = ACT_HARDSWISH;
+  return launch_gemm(gp, st);
+}
+
+size_t tcx_resblock_workspace_bytes(int B, int H, int W, int C) { return 4 * 2 * rnd((size_t)B * H * W * C); }
+
+int tcx_resblock_fwd(const float* x, const void* const* p, float bn_eps, float* y, int B, int H, int W, int C,
+                     void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  Carver c(ws);
+  const int M = B * H * W;
+  float* t1 = c.take((size_t)M * C);
+  float* t2 = c.take((size_t)M * C);
+  GemmParams g1 = gemm1(x, F(p[0]), t1, M, C, C);
+  g1.g[0].epi.bn = BnParams{F(p[1]), F(p[2]), F(p[3]), F(p[4]), bn_eps};
+  g1.g[0].epi.act = ACT_HARDSWISH;
+  TCX_TRY(launch_gemm(g1, st));
+  DwGroup dg{t1, F(p[5]), nullptr, t2};
+  TCX_TRY(launch_dwconv3x3(&dg, 1, B, H, W, C, 1, DW_BN_HS, BnParams{F(p[6]), F(p[7]), F(p[8]), F(p[9]), bn_eps}, st));
+  GemmParams g2 = gemm1(t2, F(p[10]), y, M, C, C);
+  g2.g[0].epi.bn = BnParams{F(p[11]), F(p[12]), F(p[13]), F(p[14]), bn_eps};
+  g2.g[0].epi.residual = x;
+  return launch_gemm(g2, st);
+}
+
+// ---- K6 ------------------------------------------------------------------------------------
+size_t tcx_iff_coordatt_workspace_bytes(int B, int HW, int C, int mip) {
+  const size_t inp = 4 * (size_t)C;
+  return 4 * (rnd((size_t)B * 2 * HW * inp) + rnd((size_t)B * 2 * HW * mip) + 2 * rnd((size_t)B * HW * inp) +
+              rnd((size_t)B * HW * HW * inp));
+}
+
+int tcx_iff_coordatt_fwd(const void* const* maps, const void* const* p, float bn_eps, float* y, int B, int HW, int C,
+                         int mip, int Cout, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  Carver c(ws);
+  const int inp = 4 * C;
+  float* pooled = c.take((size_t)B * 2 * HW * inp);
+  float* yv = c.take((size_t)B * 2 * HW * mip);
+  float* ah = c.take((size_t)B * HW * inp);
+  float* aw = c.take((size_t)B * HW * inp);
+  float* gated = c.take((size_t)B * HW * HW * inp);
+  IffSrc src{};
+  for (int i = 0; i < 4; i++) src.p[i] = F(maps[i]);
+  TCX_TRY(launch_iff_pool(src, B, HW, C, pooled, st));
+  {
+    GemmParams g = gemm1(pooled, F(p[0]), yv, B * 2 * HW, mip, inp);
+    g.g[0].epi.bias = F(p[1]);
+    g.g[0].epi.bn = BnParams{F(p[2]), F(p[3]), F(p[4]), F(p[5]), bn_eps};
+    g.g[0].epi.act = ACT_SILU_SWISH;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, HW, inp, mip);
+    g.groups = 2; g.batch = B;
+    g.strideA = (long long)2 * HW * mip; g.strideW = 0; g.strideC = (long long)HW * inp;
+    g.g[0].A = yv; g.g[0].W = F(p[6]); g.g[0].C = ah; g.g[0].epi.bias = F(p[7]); g.g[0].epi.act = ACT_SIGMOID;
+    g.g[1].A = yv + (size_t)HW * mip; g.g[1].W = F(p[8]); g.g[1].C = aw; g.g[1].epi.bias = F(p[9]); g.g[1].epi.act = ACT_SIGMOID;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  TCX_TRY(launch_iff_gate(src, B, HW, HW, C, ah, aw, gated, st));
+  GemmParams g = gemm1(gated, F(p[10]), y, B * HW * HW, Cout, inp);
+  g.g[0].epi.bias = F(p[11]);
+  return launch_gemm(g, st);
+}
+
+// ---- bridge ---------------------------------------------------------------------------------
+int tcx_bridge_regroup_fwd(const void* const* maps, float* tokens, int B, int S0, void* stream) {
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  RegroupArgs a{};
+  for (int i = 0; i < 4; i++) a.src[i] = F(maps[i]);
+  for (int i = 0; i < 5; i++) a.tok_off[i] = g.off[i];
+  a.dst = tokens; a.ntok = g.ntok; a.B = B;
+  return launch_regroup(a, S(stream));
+}
+
+size_t tcx_scale_reduce_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  return 4 * scale_reduce_ws_floats(B, g);
+}
+
+int tcx_scale_reduce_fwd(const float* x, const void* const* p, float ln_eps, float* out, int B, int S0, void* ws,
+                         void* stream) {
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  return run_scale_reduce(x, p, ln_eps, out, B, g, reinterpret_cast<float*>(ws), S(stream));
+}
+
+size_t tcx_bridge_sr_attn_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  const size_t bn = (size_t)B * g.ntok * 64;
+  return 4 * (2 * rnd(bn) + rnd((size_t)B * g.nred * 64) + rnd((size_t)B * g.nred * 128) + scale_reduce_ws_floats(B, g));
+}
+
+int tcx_bridge_sr_attn_fwd(const float* xn, const void* const* p, float scale, float ln_eps, const float* residual,
+                           float* y, int B, int S0, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  Carver c(ws);
+  const size_t bn = (size_t)B * g.ntok * 64;
+  float* q = c.take(bn);
+  float* o = c.take(bn);
+  float* red = c.take((size_t)B * g.nred * 64);
+  float* kv = c.take((size_t)B * g.nred * 128);
+  float* srws = c.take(scale_reduce_ws_floats(B, g));
+  const int M = B * g.ntok;
+  GemmParams gq = gemm1(xn, F(p[0]), q, M, 64, 64);
+  gq.g[0].epi.bias = F(p[1]);
+  TCX_TRY(launch_gemm(gq, st));
+  TCX_TRY(run_scale_reduce(xn, p + 6, ln_eps, red, B, g, srws, st));
+  GemmParams gk = gemm1(red, F(p[2]), kv, B * g.nred, 128, 64);
+  gk.g[0].epi.bias = F(p[3]);
+  TCX_TRY(launch_gemm(gk, st));
+  if (flash_tc_enabled()) TCX_TRY(launch_flash_tc(q, kv, o, B, g.ntok, g.nred, scale, st));
+  else TCX_TRY(launch_flash_ffma(q, kv, o, B, g.ntok, g.nred, scale, st));
+  GemmParams gp = gemm1(o, F(p[4]), y, M, 64, 64);
+  gp.g[0].epi.bias = F(p[5]);
+  gp.g[0].epi.residual = residual;
+  return launch_gemm(gp, st);
+}
+
+size_t tcx_bridge_mixffn_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  size_t n = 0;
+  for (int k = 0; k < 4; k++) n += 2 * rnd((size_t)B * g.hw[k] * g.hw[k] * g.ch[k] * 4);
+  return 4 * n;
+}
+
+int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* p, float ln_eps, float* y, int B,
+                          int S0, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  Carver c(ws);
+  const long long sb = (long long)g.ntok * 64;
+  for (int k = 0; k < 4; k++) {
+    const int hw = g.hw[k], C = g.ch[k], C4 = 4 * C, Mi = hw * hw;
+    const void* const* pk = p + 8 * k;
+    float* h = c.take((size_t)B * Mi * C4);
+    float* a = c.take((size_t)B * Mi * C4);
+    const long long off = (long long)g.off[k] * 64;
+    {
+      GemmParams gp = gemm1(tx + off, F(pk[0]), h, Mi, C4, C);
+      gp.batch = B; gp.strideA = sb; gp.strideC = (long long)Mi * C4;
+      gp.g[0].epi.bias = F(pk[1]);
+      TCX_TRY(launch_gemm(gp, st));
+    }
+    MixMidGroup mg{h, F(pk[2]), F(pk[3]), F(pk[4]), F(pk[5]), a};
+    TCX_TRY(launch_mixffn_mid(&mg, 1, B, hw, hw, C4, ln_eps, st));
+    {
+      GemmParams gp = gemm1(a, F(pk[6]), y + off, Mi, C, C4);
+      gp.batch = B; gp.strideA = (long long)Mi * C4; gp.strideC = sb;
+      gp.g[0].epi.bias = F(pk[7]);
+      gp.g[0].epi.residual = tx1 + off; gp.g[0].epi.ldr = C; gp.g[0].epi.strideR = sb;
+      TCX_TRY(launch_gemm(gp, st));
+    }
+  }
+  return 0;
+}
+
+// ---- decoder ----------------------------------------------------------------------------------
+int tcx_concat_linear_fwd(const float* x1, const float* x2, const float* w, const float* b, float* y, int M, int C1,
+                          int C2, int N, void* stream) {
+  cudaStream_t st = S(stream);
+  // y = x2 * W[:, C1:]^T + b, then y += x1 * W[:, :C1]^T   (the concatenation is never materialised)
+  GemmParams g = gemm1(x2, w + C1, y, M, N, C2);
+  g.ldw = C1 + C2;
+  g.g[0].epi.bias = b;
+  TCX_TRY(launch_gemm(g, st));
+  GemmParams h = gemm1(x1, w, y, M, N, C1);
+  h.ldw = C1 + C2;
+  h.g[0].epi.residual = y;
+  return launch_gemm(h, st);
+}
+
+size_t tcx_patch_expand_workspace_bytes(int B, int H, int W, int C, int scale) {
+  const size_t nout = scale == 2 ? 2 * (size_t)C : 16 * (size_t)C;
+  return 4 * rnd((size_t)B * H * W * nout);
+}
+
+int tcx_patch_expand_fwd(const float* x, const float* w, const float* lnw, const float* lnb, float eps, float* y,
+                         int B, int H, int W, int C, int scale, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  TCX_REQUIRE(scale == 2 || scale == 4, "patch_expand: scale must be 2 or 4");
+  const int nout = scale == 2 ? 2 * C : 16 * C;
+  float* e = reinterpret_cast<float*>(ws);
+  GemmParams g = gemm1(x, w, e, B * H * W, nout, C);
+  TCX_TRY(launch_gemm(g, st));
+  return launch_shuffle_ln(e, B, H, W, scale, nout / (scale * scale), lnw, lnb, eps, y, st);
+}
+
+size_t tcx_final_expand_head_workspace_bytes(int B, int H, int W) { return 4 * rnd((size_t)B * H * W * 1024); }
+
+int tcx_final_expand_head_fwd(const float* x, const float* w, const float* lnw, const float* lnb, float eps,
+                              const float* cls_w, const float* cls_b, int ncls, float* logits_nchw, int B, int H,
+                              int W, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  float* e = reinterpret_cast<float*>(ws);
+  GemmParams g = gemm1(x, w, e, B * H * W, 1024, 64);
+  TCX_TRY(launch_gemm(g, st));
+  return launch_final_head(e, B, H, W, lnw, lnb, eps, cls_w, cls_b, ncls, logits_nchw, st);
+}
+
+}  // extern "C"

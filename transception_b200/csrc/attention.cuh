@@ -1,0 +1,28 @@
+#pragma once
+#include "common.cuh"
+
+// element (b, c, n) of K/Q/V lives at ptr + b*sb + c*sc + n*sn
+struct EaView {
+  const float* k;
+  const float* q;
+  const float* v;
+  long long sb, sc, sn;
+};
+size_t ea_workspace_floats(int B, int N, int C);
+int launch_ea_context(const EaView& v, bool reinterpret, int B, int N, int C, float* ws, float* ctxT, cudaStream_t st);
+int launch_ea_qsoftmax(const EaView& v, bool reinterpret, int B, int N, int C, float* dst, cudaStream_t st);
+
+struct MbAttnArgs {
+  int groups, B, H, W, C, heads;
+  float scale;
+  const float* qkv[TCX_MAX_GROUPS];
+  float* ctx[TCX_MAX_GROUPS];
+  float* out[TCX_MAX_GROUPS];
+  const float* cw[TCX_MAX_GROUPS][3];
+  const float* cb[TCX_MAX_GROUPS][3];
+};
+int launch_mb_attention(const MbAttnArgs& a, cudaStream_t st);
+
+int launch_flash_ffma(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, cudaStream_t st);
+int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, cudaStream_t st);
+bool flash_tc_enabled();

@@ -1,0 +1,136 @@
+// Shared helpers for the transception_sm100 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define TCX_MAX_GROUPS 4
+
+// ---- error plumbing (C-ABI: every export returns int, 0 = OK) ------------------------
+void tcx_set_error(const char* fmt, ...);
+int tcx_check_launch(const char* what);
+
+#define TCX_TRY(expr)                       \
+  do {                                      \
+    int _e = (expr);                        \
+    if (_e != 0) return _e;                 \
+  } while (0)
+
+#define TCX_REQUIRE(cond, ...)              \
+  do {                                      \
+    if (!(cond)) {                          \
+      tcx_set_error(__VA_ARGS__);           \
+      return -1;                            \
+    }                                       \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- activations -----------------------------------------------------------------------
+enum TcxAct { ACT_NONE = 0, ACT_GELU = 1, ACT_HARDSWISH = 2, ACT_SIGMOID = 3, ACT_SILU_SWISH = 4 };
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float hardswish(float x) { return x * fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// reference MSTr.py:1275-1286: t * min(SiLU(t+3)/6, 1)
+__device__ __forceinline__ float silu_swish(float t) {
+  float u = t + 3.0f;
+  float s = u * sigmoidf_(u) * (1.0f / 6.0f);
+  return t * fminf(s, 1.0f);
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return gelu_erf(v);
+    case ACT_HARDSWISH: return hardswish(v);
+    case ACT_SIGMOID: return sigmoidf_(v);
+    case ACT_SILU_SWISH: return silu_swish(v);
+    default: return v;
+  }
+}
+
+// ---- warp helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// BatchNorm (eval) folded to y = x*scale + shift, computed on the fly from the four vectors.
+struct BnParams {
+  const float* w;
+  const float* b;
+  const float* rm;
+  const float* rv;
+  float eps;
+};
+__device__ __forceinline__ void bn_fold(const BnParams& bn, int c, float& scale, float& shift) {
+  float s = bn.w[c] * rsqrtf(bn.rv[c] + bn.eps);
+  scale = s;
+  shift = bn.b[c] - bn.rm[c] * s;
+}
+
+// ---- GEMM front end (gemm.cu): C[M,N] = epi(A[M,K] * W[N,K]^T) -----------------------------
+struct GemmEpi {
+  const float* bias;      // [N] or null
+  BnParams bn;            // bn.w == null -> none (applied after bias, before act)
+  int act;                // TcxAct
+  const float* residual;  // [M, ldr] or null (added after act)
+  int ldr;
+  long long strideR;      // batch stride of residual
+};
+struct GemmGroup {
+  const float* A;
+  const float* W;
+  float* C;
+  GemmEpi epi;
+};
+struct GemmParams {
+  GemmGroup g[TCX_MAX_GROUPS];
+  int groups;   // blockIdx.z = group * batch + b
+  int batch;
+  long long strideA, strideW, strideC;  // per-batch element strides (0 = shared)
+  int M, N, K;
+  int lda, ldw, ldc;
+};
+int launch_gemm(const GemmParams& p, cudaStream_t st);
+
+// convenience: single plain linear
+int launch_linear(const float* A, const float* W, const float* bias, const float* residual, float* C, int M, int N,
+                  int K, int act, cudaStream_t st);
+
+// ---- elementwise / normalisation (elementwise.cu) -----------------------------------------
+int launch_layernorm(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,
+                     cudaStream_t st);
+struct LnGroup {
+  const float* x;
+  const float* w;
+  const float* b;
+  float* y;
+};
+int launch_layernorm_grouped(const LnGroup* g, int groups, long long M, int C, float eps, cudaStream_t st);
+
+enum DwEpi { DW_PLAIN = 0, DW_ADD_INPUT = 1, DW_BN_HS = 2 };
+struct DwGroup {
+  const float* x;   // [B,H,W,C]
+  const float* w;   // [C,1,k,k]
+  const float* b;   // [C] or null
+  float* y;         // [B,Ho,Wo,C]
+};
+int launch_dwconv3x3(const DwGroup* g, int groups, int B, int H, int W, int C, int stride, int epi, BnParams bn,
+                     cudaStream_t st);
+
+struct MixMidGroup {
+  const float* h;    // [B,H,W,C4] fc1 output
+  const float* dww;  // [C4,1,3,3]
+  const float* dwb;  // [C4]
+  const float* lnw;
+  const float* lnb;
+  float* y;          // GELU(LN(dw(h)+b+h))
+};
+int launch_mixffn_mid(const MixMidGroup* g, int groups, int B, int H, int W, int C4, float eps, cudaStream_t st);

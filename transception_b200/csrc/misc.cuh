@@ -1,0 +1,42 @@
+#pragma once
+#include "common.cuh"
+
+int launch_patch_embed_ln(const float* x, long long xs_b, long long xs_c, int B, int Hin, int Win, const float* w,
+                          const float* bias, const float* lnw, const float* lnb, float eps, float* out, cudaStream_t st);
+
+struct RegroupArgs {
+  const float* src[4];   // NHWC maps, dense
+  float* dst;            // [B][ntok][64]
+  int tok_off[5];        // token offsets of the four slabs (+ total)
+  int ntok, B;
+};
+int launch_regroup(const RegroupArgs& a, cudaStream_t st);
+
+int launch_sr_im2row(const float* x, long long xs_b, int HW, int Cin, int r, int B, float* A, cudaStream_t st);
+
+struct SrPackArgs {
+  const float* conv[3];  // conv outputs [B*pp][64*g]
+  const float* x;        // token buffer (raw stage-4 tokens are copied through)
+  long long xs_b;
+  int raw_tok0;
+  int red_off[4];        // offsets of the 4 parts in the reduced sequence
+  int gmul[3], pp[3];
+  int nred, B;
+  const float* lnw;
+  const float* lnb;
+  float eps;
+  float* out;            // [B][nred][64]
+};
+int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st);
+
+struct IffSrc {
+  const float* p[4];
+};
+int launch_iff_pool(const IffSrc& src, int B, int HW, int C, float* pooled, cudaStream_t st);
+int launch_iff_gate(const IffSrc& src, int B, int H, int W, int C, const float* ah, const float* aw, float* out,
+                    cudaStream_t st);
+
+int launch_shuffle_ln(const float* in, int B, int H, int W, int s, int c, const float* lnw, const float* lnb, float eps,
+                      float* out, cudaStream_t st);
+int launch_final_head(const float* in, int B, int H, int W, const float* lnw, const float* lnb, float eps,
+                      const float* cw, const float* cb, int ncls, float* out, cudaStream_t st);

@@ -713,8 +713,7 @@ class MSTransception(nn.Module):
                 "transception_b200 round 1 builds the forward path only: call under torch.no_grad() "
                 "(backward kernels are scheduled next, see DESIGN.md)")
         ops.require_cuda(x)
-        if x.size(1) == 1:
-            x = x.expand(-1, 3, -1, -1)  # stem kernel reads the grey plane three times; no copy
+        # a 1-channel input is read three times by the stem kernel (reference repeats it, MSTr.py:2828-2829)
         maps = self.backbone.nhwc(x)
         if self.have_bridge != "None":
             maps = [m.permute(0, 2, 3, 1) for m in self.bridge(ops.bridge_regroup(maps))]

@@ -1,0 +1,406 @@
+"""ctypes binding of ``libtransception_sm100.so`` (C ABI: ``include/transception_sm100.h``).
+
+PyTorch is used for device memory (outputs and scratch come from the caching allocator) and for the current
+stream; every FLOP of the hot path is executed by the library's kernels.  There is no fallback: if the shared
+library is missing, or the tensor is not on an sm_100 CUDA device, the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtransception_sm100.so")
+MHCA_NP = 24
+
+_lib = None
+_lock = threading.Lock()
+_launches = 0          # C-ABI calls issued (each enqueues >= 1 kernel); see kernel_launch_estimate in bench.py
+
+_vp, _i, _f, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t
+_pp = ctypes.POINTER(ctypes.c_void_p)
+
+_PROTOS = {
+    "tcx_version": (ctypes.c_char_p, []),
+    "tcx_last_error": (ctypes.c_char_p, []),
+    "tcx_device_ok": (_i, []),
+    "tcx_set_flag": (_i, [ctypes.c_char_p, _i]),
+    "tcx_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
+    "tcx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_linear_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _i, _i, _i, _vp]),
+    "tcx_patch_embed_ln_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
+    "tcx_dwconv_tokens_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "tcx_eff_attn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_eff_attn_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mixffn_skip_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_mixffn_skip_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mb_factor_attn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_mb_factor_attn_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mhca_blocks_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_mhca_blocks_fwd": (_i, [_vp, _pp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
+    "tcx_ripm_dwsep_bn_hs_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "tcx_ripm_dwsep_bn_hs_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_resblock_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_resblock_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_iff_coordatt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_iff_coordatt_fwd": (_i, [_pp, _pp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_bridge_regroup_fwd": (_i, [_pp, _vp, _i, _i, _vp]),
+    "tcx_scale_reduce_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_scale_reduce_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
+    "tcx_bridge_sr_attn_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_bridge_sr_attn_fwd": (_i, [_vp, _pp, _f, _f, _vp, _vp, _i, _i, _vp, _vp]),
+    "tcx_bridge_mixffn_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_bridge_mixffn_fwd": (_i, [_vp, _vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
+    "tcx_concat_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_patch_expand_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "tcx_patch_expand_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_final_expand_head_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_final_expand_head_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+}
+EXPORTS = tuple(_PROTOS)
+
+
+def load_library():
+    """dlopen the in-tree shared library and declare every prototype. Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "transception_b200: %s is missing — build it with `python -m transception_b200.build` "
+                    "(there is no CPU/PyTorch fallback)" % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in _PROTOS.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def launches():
+    return _launches
+
+
+def set_flag(name, value):
+    return load_library().tcx_set_flag(name.encode(), int(value))
+
+
+def require_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("transception_b200 kernels run on sm_100a CUDA tensors only (got device %s); "
+                           "there is no CPU fallback" % x.device)
+
+
+def _chk(rc):
+    global _launches
+    _launches += 1
+    if rc != 0:
+        raise RuntimeError("libtransception_sm100: " + load_library().tcx_last_error().decode())
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise RuntimeError("transception_b200: expected a contiguous fp32 CUDA tensor, got %s %s contiguous=%s on %s"
+                           % (tuple(t.shape), t.dtype, t.is_contiguous(), t.device))
+    return t.data_ptr()
+
+
+def _table(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = _ptr(t.detach() if t is not None else None)
+    return arr
+
+
+def _ws(nbytes, like):
+    return torch.empty((max(int(nbytes), 16) + 3) // 4, dtype=torch.float32, device=like.device)
+
+
+def _d(t):
+    return t.detach() if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+def layernorm(x, w, b, eps):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    C = x.shape[-1]
+    _chk(lib.tcx_layernorm_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), x.numel() // C, C, eps, _stream()))
+    return y
+
+
+def linear(x, w, b=None, act=0, residual=None):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    K = x.shape[-1]
+    N = w.shape[0]
+    M = x.numel() // K
+    y = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=x.dtype)
+    _chk(lib.tcx_linear_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(residual), _ptr(y), M, N, K, act, _stream()))
+    return y
+
+
+def linear_bn_act(x, w, bn_w, bn_b, bn_rm, bn_rv, bn_eps, hardswish=False):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), device=x.device, dtype=x.dtype)
+    _chk(lib.tcx_linear_bn_act_fwd(_ptr(x), _ptr(_d(w).reshape(N, K)), _ptr(_d(bn_w)), _ptr(_d(bn_b)), _ptr(bn_rm),
+                                   _ptr(bn_rv), bn_eps, 2 if hardswish else 0, _ptr(y), M, N, K, _stream()))
+    return y
+
+
+def patch_embed_ln(x, w, b, stride, padding, lnw, lnb, eps):
+    require_cuda(x)
+    lib = load_library()
+    B, Cin, H, W = x.shape
+    if tuple(w.shape) != (64, 3, 7, 7) or stride != 4 or padding != 3:
+        raise NotImplementedError("patch_embed_ln is built for the stage-1 stem (3->64, 7x7, stride 4, pad 3)")
+    Ho, Wo = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+    out = torch.empty((B, Ho * Wo, 64), device=x.device, dtype=x.dtype)
+    _chk(lib.tcx_patch_embed_ln_fwd(_ptr(x), B, Cin, H, W, _ptr(_d(w)), _ptr(_d(b)), _ptr(_d(lnw)), _ptr(_d(lnb)),
+                                    eps, _ptr(out), _stream()))
+    return out
+
+
+def dwconv_tokens(x, H, W, w, b, add_input):
+    require_cuda(x)
+    lib = load_library()
+    B, N, C = x.shape
+    y = torch.empty_like(x)
+    _chk(lib.tcx_dwconv_tokens_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), B, H, W, C, int(add_input), _stream()))
+    return y
+
+
+def eff_attn(xn, kw, kb, qw, qb, vw, vb, rw, rb, residual=None, reinterpret=False):
+    require_cuda(xn)
+    lib = load_library()
+    B, N, C = xn.shape
+    y = torch.empty_like(xn)
+    ws = _ws(lib.tcx_eff_attn_workspace_bytes(B, N, C), xn)
+    tab = _table([kw.reshape(C, C), kb, qw.reshape(C, C), qb, vw.reshape(C, C), vb, rw.reshape(C, C), rb])
+    _chk(lib.tcx_eff_attn_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, N, C, int(reinterpret), _ptr(ws), _stream()))
+    return y
+
+
+def mixffn_skip(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):
+    require_cuda(xn)
+    lib = load_library()
+    xn = xn.contiguous()
+    B, N, C = xn.shape
+    C4 = fc1w.shape[0]
+    y = torch.empty_like(xn)
+    ws = _ws(lib.tcx_mixffn_skip_workspace_bytes(B, N, C4), xn)
+    tab = _table([fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b])
+    _chk(lib.tcx_mixffn_skip_fwd(_ptr(xn), tab, eps, _ptr(residual), _ptr(y), B, H, W, C, C4, _ptr(ws), _stream()))
+    return y
+
+
+def mb_factor_attn(xn, H, W, heads, scale, qkvw, qkvb, crpe_w, crpe_b, head_splits, projw, projb, residual=None):
+    require_cuda(xn)
+    lib = load_library()
+    B, N, C = xn.shape
+    _check_crpe(head_splits, crpe_w, heads)
+    y = torch.empty_like(xn)
+    ws = _ws(lib.tcx_mb_factor_attn_workspace_bytes(B, N, C), xn)
+    tab = _table([qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2], projw, projb])
+    _chk(lib.tcx_mb_factor_attn_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, H, W, C, heads, _ptr(ws), _stream()))
+    return y
+
+
+def _check_crpe(head_splits, crpe_w, heads):
+    if list(head_splits) != [2, 3, 3] or heads != 8 or [w.shape[-1] for w in crpe_w] != [3, 5, 7]:
+        raise NotImplementedError("conv relative position encoding is built for crpe_window={3:2,5:3,7:3}, 8 heads")
+
+
+def crpe(q, v, H, W, weights, biases, head_splits):
+    raise NotImplementedError("ConvRelPosEnc is fused into the MB attention kernel; call FactorAtt_ConvRelPosEnc")
+
+
+def _block_params(blk):
+    f, m, c = blk.factoratt_crpe, blk.mlp, blk.factoratt_crpe.crpe
+    _check_crpe(c.head_splits, [k.weight for k in c.conv_list], f.num_heads)
+    cl = c.conv_list
+    return [blk.cpe.proj.weight, blk.cpe.proj.bias, blk.norm1.weight, blk.norm1.bias, f.qkv.weight, f.qkv.bias,
+            cl[0].weight, cl[0].bias, cl[1].weight, cl[1].bias, cl[2].weight, cl[2].bias, f.proj.weight, f.proj.bias,
+            blk.norm2.weight, blk.norm2.bias, m.fc1.weight, m.fc1.bias, m.dwconv.dwconv.weight, m.dwconv.dwconv.bias,
+            m.norm1.weight, m.norm1.bias, m.fc2.weight, m.fc2.bias]
+
+
+def mhca_blocks(x, H, W, branches):
+    """x: [G,B,N,C]; branches: G lists of L MHCABlock modules. Returns a new [G,B,N,C] tensor."""
+    require_cuda(x)
+    lib = load_library()
+    G, B, N, C = x.shape
+    L = len(branches[0])
+    assert len(branches) == G and all(len(b) == L for b in branches)
+    flat = []
+    for br in branches:
+        for blk in br:
+            flat.extend(_block_params(blk))
+    b0 = branches[0][0]
+    y = x.contiguous().clone()
+    ws = _ws(lib.tcx_mhca_blocks_workspace_bytes(G, B, N, C), x)
+    _chk(lib.tcx_mhca_blocks_fwd(_ptr(y), _table(flat), G, L, B, H, W, C, b0.factoratt_crpe.num_heads,
+                                 b0.norm1.eps, b0.mlp.norm1.eps, _ptr(ws), _stream()))
+    return y
+
+
+def ripm_dwsep_bn_hs(x, stride, dww, pww, bn_w, bn_b, bn_rm, bn_rv, bn_eps, out=None):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, C), device=x.device, dtype=x.dtype)
+    ws = _ws(lib.tcx_ripm_dwsep_bn_hs_workspace_bytes(B, H, W, C, stride), x)
+    _chk(lib.tcx_ripm_dwsep_bn_hs_fwd(_ptr(x), _ptr(_d(dww)), _ptr(_d(pww).reshape(C, C)), _ptr(_d(bn_w)),
+                                      _ptr(_d(bn_b)), _ptr(bn_rm), _ptr(bn_rv), bn_eps, _ptr(out), B, H, W, C, stride,
+                                      _ptr(ws), _stream()))
+    return out
+
+
+def resblock(x, c1w, bn1, dww, bn2, c2w, bn3):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    ws = _ws(lib.tcx_resblock_workspace_bytes(B, H, W, C), x)
+    tab = _table([c1w.reshape(C, C), *bn1[:4], dww, *bn2[:4], c2w.reshape(C, C), *bn3[:4]])
+    _chk(lib.tcx_resblock_fwd(_ptr(x), tab, bn1[4], _ptr(y), B, H, W, C, _ptr(ws), _stream()))
+    return y
+
+
+def iff_coordatt(maps, c1w, c1b, bn, chw, chb, cww, cwb, cow, cob):
+    require_cuda(maps[0])
+    lib = load_library()
+    if len(maps) == 1:   # a single pre-concatenated NHWC map: split channel-wise into 4 dense sources
+        B, H, W, C4 = maps[0].shape
+        maps = [m.contiguous() for m in maps[0].split(C4 // 4, dim=3)]
+    maps = [m.contiguous() for m in maps]
+    B, H, W, C = maps[0].shape
+    assert H == W and len(maps) == 4
+    mip, inp, Cout = c1w.shape[0], 4 * C, cow.shape[0]
+    y = torch.empty((B, H, W, Cout), device=maps[0].device, dtype=maps[0].dtype)
+    ws = _ws(lib.tcx_iff_coordatt_workspace_bytes(B, H, C, mip), maps[0])
+    tab = _table([c1w.reshape(mip, inp), c1b, *bn[:4], chw.reshape(inp, mip), chb, cww.reshape(inp, mip), cwb,
+                  cow.reshape(Cout, inp), cob])
+    _chk(lib.tcx_iff_coordatt_fwd(_table(maps), tab, bn[4], _ptr(y), B, H, C, mip, Cout, _ptr(ws), _stream()))
+    return y
+
+
+def _bridge_side(ntok):
+    # ntok = S^2 * (1 + 2/4 + 5/16 + 8/64) = S^2 * 1.9375
+    S = int(round((ntok / 1.9375) ** 0.5))
+    if S * S * 31 != ntok * 16:
+        raise RuntimeError("bridge: token count %d does not correspond to a 4-scale pyramid" % ntok)
+    return S
+
+
+def bridge_regroup(maps):
+    require_cuda(maps[0])
+    lib = load_library()
+    maps = [m.contiguous() for m in maps]
+    B, S = maps[0].shape[0], maps[0].shape[1]
+    exp = [(B, S >> k, S >> k, c) for k, c in enumerate((64, 128, 320, 512))]
+    if [tuple(m.shape) for m in maps] != exp:
+        raise RuntimeError("bridge_regroup: expected NHWC maps %s, got %s" % (exp, [tuple(m.shape) for m in maps]))
+    ntok = sum(m.shape[1] * m.shape[2] * m.shape[3] // 64 for m in maps)
+    out = torch.empty((B, ntok, 64), device=maps[0].device, dtype=maps[0].dtype)
+    _chk(lib.tcx_bridge_regroup_fwd(_table(maps), _ptr(out), B, S, _stream()))
+    return out
+
+
+def scale_reduce(x, s0w, s0b, s1w, s1b, s2w, s2b, lnw, lnb, eps):
+    require_cuda(x)
+    lib = load_library()
+    B, ntok, C = x.shape
+    S = _bridge_side(ntok)
+    nred = (S // 8) ** 2 * 8 + (S // 8) ** 2 * 8
+    out = torch.empty((B, nred, 64), device=x.device, dtype=x.dtype)
+    ws = _ws(lib.tcx_scale_reduce_workspace_bytes(B, S), x)
+    tab = _table([s0w.reshape(64, -1), s0b, s1w.reshape(128, -1), s1b, s2w.reshape(320, -1), s2b, lnw, lnb])
+    _chk(lib.tcx_scale_reduce_fwd(_ptr(x), tab, eps, _ptr(out), B, S, _ptr(ws), _stream()))
+    return out
+
+
+def bridge_sr_attn(xn, scale, qw, qb, kvw, kvb, pw, pb, s0w, s0b, s1w, s1b, s2w, s2b, lnw, lnb, eps, residual=None):
+    require_cuda(xn)
+    lib = load_library()
+    B, ntok, C = xn.shape
+    S = _bridge_side(ntok)
+    y = torch.empty_like(xn)
+    ws = _ws(lib.tcx_bridge_sr_attn_workspace_bytes(B, S), xn)
+    tab = _table([qw, qb, kvw, kvb, pw, pb, s0w.reshape(64, -1), s0b, s1w.reshape(128, -1), s1b,
+                  s2w.reshape(320, -1), s2b, lnw, lnb])
+    _chk(lib.tcx_bridge_sr_attn_fwd(_ptr(xn), tab, scale, eps, _ptr(residual), _ptr(y), B, S, _ptr(ws), _stream()))
+    return y
+
+
+def bridge_mixffn(tx, tx1, mix_args):
+    require_cuda(tx)
+    lib = load_library()
+    B, ntok, C = tx.shape
+    S = _bridge_side(ntok)
+    y = torch.empty_like(tx)
+    flat, eps = [], mix_args[0][6]
+    for a in mix_args:
+        flat.extend([a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8]])
+    ws = _ws(lib.tcx_bridge_mixffn_workspace_bytes(B, S), tx)
+    _chk(lib.tcx_bridge_mixffn_fwd(_ptr(tx), _ptr(tx1), _table(flat), eps, _ptr(y), B, S, _ptr(ws), _stream()))
+    return y
+
+
+def concat_linear(x1, x2, w, b):
+    require_cuda(x1)
+    lib = load_library()
+    B, N, C1 = x1.shape
+    C2 = x2.shape[-1]
+    Nout = w.shape[0]
+    y = torch.empty((B, N, Nout), device=x1.device, dtype=x1.dtype)
+    _chk(lib.tcx_concat_linear_fwd(_ptr(x1), _ptr(x2), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), B * N, C1, C2, Nout,
+                                   _stream()))
+    return y
+
+
+def patch_expand(x, H, W, w, scale, lnw, lnb, eps):
+    require_cuda(x)
+    lib = load_library()
+    B, N, C = x.shape
+    c = w.shape[0] // (scale * scale)
+    y = torch.empty((B, N * scale * scale, c), device=x.device, dtype=x.dtype)
+    ws = _ws(lib.tcx_patch_expand_workspace_bytes(B, H, W, C, scale), x)
+    _chk(lib.tcx_patch_expand_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(lnw)), _ptr(_d(lnb)), eps, _ptr(y), B, H, W, C, scale,
+                                  _ptr(ws), _stream()))
+    return y
+
+
+def final_expand_head(x, H, W, ew, lnw, lnb, eps, cw, cb):
+    require_cuda(x)
+    lib = load_library()
+    B, N, C = x.shape
+    if C != 64:
+        raise NotImplementedError("final_expand_head is built for dim 64")
+    ncls = cw.shape[0]
+    y = torch.empty((B, ncls, 4 * H, 4 * W), device=x.device, dtype=x.dtype)
+    ws = _ws(lib.tcx_final_expand_head_workspace_bytes(B, H, W), x)
+    _chk(lib.tcx_final_expand_head_fwd(_ptr(x), _ptr(_d(ew)), _ptr(_d(lnw)), _ptr(_d(lnb)), eps,
+                                       _ptr(_d(cw).reshape(ncls, 64)), _ptr(_d(cb)), ncls, _ptr(y), B, H, W,
+                                       _ptr(ws), _stream()))
+    return y
