@@ -30,6 +30,14 @@ int tcx_device_ok(void);
 /* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc"}; value 0/1; returns previous value */
 int tcx_set_flag(const char* name, int value);
 
+/* number of kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
+long long tcx_launch_count(void);
+/* per-kernel timing for bench.py's roofline leg: record a CUDA-event pair on the launching stream around every
+ * launch of the named kernel ("flash_tc", "gemm_tc", "gemm_ffma", "flash_ffma", "mixffn_mid"); "" disables.
+ * tcx_profile_read synchronises on the recorded events, returns their summed duration and count, and resets. */
+int tcx_profile_enable(const char* kernel_name);
+int tcx_profile_read(double* total_ms, int* count);
+
 /* K10 — nn.LayerNorm over the last dim (MSTr.py:153,156,1671,2360,2366; eps 1e-6 at :932-933) */
 int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,
                       void* stream);

@@ -16,13 +16,40 @@ void tcx_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static long long g_launches = 0;
 int tcx_check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     tcx_set_error("%s: %s", what, cudaGetErrorString(e));
     return (int)e;
   }
   return 0;
+}
+
+// ---- per-kernel event timing --------------------------------------------------------------
+#include <vector>
+#include <string>
+bool g_tcx_prof_on = false;
+static std::string g_prof_name;
+static std::vector<cudaEvent_t> g_prof_ev;   // start/stop pairs
+static size_t g_prof_used = 0;
+static bool g_prof_open = false;
+void tcx_prof_begin(const char* name, cudaStream_t st) {
+  if (g_prof_name != name) return;
+  if (g_prof_used + 2 > g_prof_ev.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    g_prof_ev.push_back(a); g_prof_ev.push_back(b);
+  }
+  cudaEventRecord(g_prof_ev[g_prof_used], st);
+  g_prof_open = true;
+}
+void tcx_prof_end(const char* name, cudaStream_t st) {
+  if (!g_prof_open || g_prof_name != name) return;
+  cudaEventRecord(g_prof_ev[g_prof_used + 1], st);
+  g_prof_used += 2;
+  g_prof_open = false;
 }
 
 static int g_flag_gemm_tc = 1;
@@ -202,6 +229,28 @@ int tcx_device_ok(void) {
     return 0;
   }
   return 1;
+}
+
+long long tcx_launch_count(void) { return g_launches; }
+
+int tcx_profile_enable(const char* kernel_name) {
+  g_prof_used = 0; g_prof_open = false;
+  if (kernel_name && kernel_name[0]) { g_prof_name = kernel_name; g_tcx_prof_on = true; }
+  else { g_prof_name.clear(); g_tcx_prof_on = false; }
+  return 0;
+}
+
+int tcx_profile_read(double* total_ms, int* count) {
+  double t = 0; int n = 0;
+  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+    if (cudaEventSynchronize(g_prof_ev[i + 1]) != cudaSuccess) { tcx_set_error("profile: event sync failed"); return -1; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[i], g_prof_ev[i + 1]) != cudaSuccess) { tcx_set_error("profile: elapsed failed"); return -1; }
+    t += ms; n++;
+  }
+  *total_ms = t; *count = n;
+  g_prof_used = 0;
+  return 0;
 }
 
 int tcx_set_flag(const char* name, int value) {

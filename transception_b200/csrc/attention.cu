@@ -452,6 +452,7 @@ int launch_mb_attention(const MbAttnArgs& a, cudaStream_t st) {
 
 int launch_flash_ffma(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, cudaStream_t st) {
   dim3 grid(cdiv(Nq, FQ), B);
+  ProfScope prof("flash_ffma", st);
   flash_ffma_kernel<<<grid, 128, 0, st>>>(q, kv, out, Nq, Nk, scale);
   return tcx_check_launch("flash_ffma");
 }

@@ -10,6 +10,18 @@
 void tcx_set_error(const char* fmt, ...);
 int tcx_check_launch(const char* what);
 
+// Optional per-kernel timing (bench.py's roofline leg): when profiling of `name` is enabled, the scope records a
+// CUDA event pair on the launching stream around the launch. Disabled = one predictable branch.
+extern bool g_tcx_prof_on;
+void tcx_prof_begin(const char* name, cudaStream_t st);
+void tcx_prof_end(const char* name, cudaStream_t st);
+struct ProfScope {
+  const char* name;
+  cudaStream_t st;
+  ProfScope(const char* n, cudaStream_t s) : name(n), st(s) { if (g_tcx_prof_on) tcx_prof_begin(name, st); }
+  ~ProfScope() { if (g_tcx_prof_on) tcx_prof_end(name, st); }
+};
+
 #define TCX_TRY(expr)                       \
   do {                                      \
     int _e = (expr);                        \

@@ -239,6 +239,7 @@ int launch_mixffn_mid(const MixMidGroup* g, int groups, int B, int H, int W, int
   for (int i = 0; i < groups; i++) gs.g[i] = g[i];
   const long long total = (long long)B * H * W;
   dim3 grid((unsigned)((total + 7) / 8), groups);
+  ProfScope prof("mixffn_mid", st);
 #define CALL(NV) mixffn_mid_kernel<NV><<<grid, 256, 0, st>>>(gs, B, H, W, C4, eps)
   DISPATCH_NV(C4, CALL);
 #undef CALL

@@ -88,6 +88,7 @@ int launch_gemm_ffma(const GemmParams& p, cudaStream_t st) {
     TCX_REQUIRE((((uintptr_t)p.g[i].A | (uintptr_t)p.g[i].W) & 15) == 0, "gemm: A/W must be 16-byte aligned");
   TCX_REQUIRE(((p.strideA | p.strideW) & 3) == 0, "gemm: batch strides must be multiples of 4");
   dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN), p.groups * p.batch);
+  ProfScope prof("gemm_ffma", st);
   gemm_ffma_kernel<<<grid, 256, 0, st>>>(p);
   return tcx_check_launch("gemm_ffma");
 }

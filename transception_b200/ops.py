@@ -26,6 +26,9 @@ _PROTOS = {
     "tcx_last_error": (ctypes.c_char_p, []),
     "tcx_device_ok": (_i, []),
     "tcx_set_flag": (_i, [ctypes.c_char_p, _i]),
+    "tcx_launch_count": (_ll, []),
+    "tcx_profile_enable": (_i, [ctypes.c_char_p]),
+    "tcx_profile_read": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i)]),
     "tcx_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "tcx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tcx_linear_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _i, _i, _i, _vp]),
@@ -81,7 +84,18 @@ def load_library():
 
 
 def launches():
-    return _launches
+    """Kernels enqueued by the library so far (counted inside the library, one per launch)."""
+    return int(load_library().tcx_launch_count())
+
+
+def profile_enable(kernel_name):
+    load_library().tcx_profile_enable((kernel_name or "").encode())
+
+
+def profile_read():
+    ms, n = ctypes.c_double(0), ctypes.c_int(0)
+    _chk(load_library().tcx_profile_read(ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value
 
 
 def set_flag(name, value):
