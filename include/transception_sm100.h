@@ -120,6 +120,12 @@ size_t tcx_bridge_sr_attn_workspace_bytes(int B, int S);
 int tcx_bridge_sr_attn_fwd(const float* xn, const void* const* p, float scale, float ln_eps, const float* residual,
                            float* y, int B, int S, void* ws, void* stream);
 
+/* the softmax(q k^T * scale) v core of K7 alone (MSTr.py:2281-2285), exposed for parity tests at ragged sizes:
+ * q [B][Nq][64], kv [B][Nk][128] (k | v), out [B][Nq][64]; tcgen05 kernel unless the "flash_tc" flag is 0. */
+size_t tcx_flash_attn_workspace_bytes(int B, int Nk);
+int tcx_flash_attn_fwd(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
+                       void* stream);
+
 /* BridgLayer_4.forward tail (MSTr.py:2394-2406): y = tx1 + cat_k MixFFN_k(tx slab k).  p = 4 x the K1 slots. */
 size_t tcx_bridge_mixffn_workspace_bytes(int B, int S);
 int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* p, float ln_eps, float* y, int B,

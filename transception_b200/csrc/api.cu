@@ -540,7 +540,8 @@ size_t tcx_bridge_sr_attn_workspace_bytes(int B, int S0) {
   BridgeGeom g;
   if (!bridge_geom(S0, g)) return 0;
   const size_t bn = (size_t)B * g.ntok * 64;
-  return 4 * (2 * rnd(bn) + rnd((size_t)B * g.nred * 64) + rnd((size_t)B * g.nred * 128) + scale_reduce_ws_floats(B, g));
+  return 4 * (2 * rnd(bn) + rnd((size_t)B * g.nred * 64) + rnd((size_t)B * g.nred * 128) + scale_reduce_ws_floats(B, g) +
+              rnd(flash_tc_workspace_bytes(B, g.nred) / 4 + 64));
 }
 
 int tcx_bridge_sr_attn_fwd(const float* xn, const void* const* p, float scale, float ln_eps, const float* residual,
@@ -555,6 +556,7 @@ int tcx_bridge_sr_attn_fwd(const float* xn, const void* const* p, float scale, f
   float* red = c.take((size_t)B * g.nred * 64);
   float* kv = c.take((size_t)B * g.nred * 128);
   float* srws = c.take(scale_reduce_ws_floats(B, g));
+  float* fws = c.take(flash_tc_workspace_bytes(B, g.nred) / 4 + 64);
   const int M = B * g.ntok;
   GemmParams gq = gemm1(xn, F(p[0]), q, M, 64, 64);
   gq.g[0].epi.bias = F(p[1]);
@@ -563,12 +565,22 @@ int tcx_bridge_sr_attn_fwd(const float* xn, const void* const* p, float scale, f
   GemmParams gk = gemm1(red, F(p[2]), kv, B * g.nred, 128, 64);
   gk.g[0].epi.bias = F(p[3]);
   TCX_TRY(launch_gemm(gk, st));
-  if (flash_tc_enabled()) TCX_TRY(launch_flash_tc(q, kv, o, B, g.ntok, g.nred, scale, st));
+  if (flash_tc_enabled()) TCX_TRY(launch_flash_tc(q, kv, o, B, g.ntok, g.nred, scale, fws, st));
   else TCX_TRY(launch_flash_ffma(q, kv, o, B, g.ntok, g.nred, scale, st));
   GemmParams gp = gemm1(o, F(p[4]), y, M, 64, 64);
   gp.g[0].epi.bias = F(p[5]);
   gp.g[0].epi.residual = residual;
   return launch_gemm(gp, st);
+}
+
+size_t tcx_flash_attn_workspace_bytes(int B, int Nk) { return flash_tc_workspace_bytes(B, Nk) + 256; }
+
+int tcx_flash_attn_fwd(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
+                       void* stream) {
+  TCX_REQUIRE(B >= 0 && Nq >= 0 && Nk >= 1, "flash_attn: bad sizes B=%d Nq=%d Nk=%d", B, Nq, Nk);
+  if (B == 0 || Nq == 0) return 0;
+  if (flash_tc_enabled()) return launch_flash_tc(q, kv, out, B, Nq, Nk, scale, ws, S(stream));
+  return launch_flash_ffma(q, kv, out, B, Nq, Nk, scale, S(stream));
 }
 
 size_t tcx_bridge_mixffn_workspace_bytes(int B, int S0) {

@@ -24,5 +24,7 @@ struct MbAttnArgs {
 int launch_mb_attention(const MbAttnArgs& a, cudaStream_t st);
 
 int launch_flash_ffma(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, cudaStream_t st);
-int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, cudaStream_t st);
+size_t flash_tc_workspace_bytes(int B, int Nk);
+int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
+                    cudaStream_t st);
 bool flash_tc_enabled();

@@ -53,6 +53,8 @@ _PROTOS = {
     "tcx_scale_reduce_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_bridge_sr_attn_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_sr_attn_fwd": (_i, [_vp, _pp, _f, _f, _vp, _vp, _i, _i, _vp, _vp]),
+    "tcx_flash_attn_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_flash_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "tcx_bridge_mixffn_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_mixffn_fwd": (_i, [_vp, _vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_concat_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -365,6 +367,21 @@ def bridge_sr_attn(xn, scale, qw, qb, kvw, kvb, pw, pb, s0w, s0b, s1w, s1b, s2w,
                   s2w.reshape(320, -1), s2b, lnw, lnb])
     _chk(lib.tcx_bridge_sr_attn_fwd(_ptr(xn), tab, scale, eps, _ptr(residual), _ptr(y), B, S, _ptr(ws), _stream()))
     return y
+
+
+def flash_attn(q, kv, scale):
+    """softmax(q k^T * scale) v for one 64-wide head: q [B,Nq,64], kv [B,Nk,128] (k | v) -> [B,Nq,64]."""
+    require_cuda(q)
+    lib = load_library()
+    q, kv = q.contiguous(), kv.contiguous()
+    B, Nq, D = q.shape
+    Nk = kv.shape[1]
+    if D != 64 or kv.shape[2] != 128 or kv.shape[0] != B:
+        raise RuntimeError("flash_attn: expected q [B,Nq,64] and kv [B,Nk,128], got %s %s" % (tuple(q.shape), tuple(kv.shape)))
+    out = torch.empty_like(q)
+    ws = _ws(lib.tcx_flash_attn_workspace_bytes(B, Nk), q)
+    _chk(lib.tcx_flash_attn_fwd(_ptr(q), _ptr(kv), _ptr(out), B, Nq, Nk, scale, _ptr(ws), _stream()))
+    return out
 
 
 def bridge_mixffn(tx, tx1, mix_args):
