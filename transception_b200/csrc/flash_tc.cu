@@ -8,8 +8,10 @@
 //  * K and V^T tiles (fp16) arrive by TMA (128-byte swizzle) through a 3-stage mbarrier ring; Q rows are read as
 //    fp32, pre-multiplied by scale*log2(e), converted to fp16 and written to swizzled shared memory by their owner
 //    threads; P = 2^(S - m) goes to swizzled shared memory as the A operand of the P V MMA.
-//  * exact online softmax: running max / sum in fp32 registers; every P V product is written to a fresh TMEM
-//    buffer and folded into the register accumulator O = O*alpha + PV, so no TMEM read-modify-write is needed.
+//  * exact online softmax in fp32: a thread pulls its whole 112-column S row into registers with four TMEM loads in
+//    flight and immediately hands the S buffer back (Q K^T of the next kv tile overlaps the exp phase); O accumulates
+//    in TMEM across kv tiles and is rescaled lazily, only when a row maximum grew by more than 2^8 (warp-uniform
+//    vote), so P <= 2^8 stays well inside fp16 and the read-modify-write of O is rare.
 //  Scores (N_q x N_k per image) never touch HBM: algorithmic traffic per image is q + out (fp32) + k,v (fp16).
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -30,9 +32,10 @@ constexpr int FT_STAGE_BYTES = FT_K_BYTES + FT_V_BYTES;
 constexpr int FT_OFF_P = 2 * FT_Q_BYTES;
 constexpr int FT_OFF_KV = FT_OFF_P + 2 * FT_P_BYTES;
 constexpr int FT_OFF_BAR = FT_OFF_KV + FT_STAGES * FT_STAGE_BYTES;
-constexpr int FT_NBAR = 2 * FT_STAGES + 8;
+constexpr int FT_NBAR = 2 * FT_STAGES + 10;
+constexpr float FT_LAZY = 8.0f;                        // rescale O only when the row max grew by > 2^8 (log2 units)
 constexpr int FT_SMEM = FT_OFF_BAR + FT_NBAR * 8 + 16 + 1024;
-constexpr int FT_THREADS = 320;
+constexpr int FT_THREADS = 384;                        // 2 softmax warpgroups + 1 service warpgroup (TMA, MMA, 2 idle)
 constexpr uint32_t FT_TMEM_COLS = 512;                 // S[2] at 0,128 ; PV[2] at 256,320
 
 struct FlashMaps {
@@ -53,43 +56,28 @@ __device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tc::smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// pass 1 over NC columns starting at c0: running max (columns >= ncols are padding)
-template <int NC, bool MASK>
-__device__ __forceinline__ float chunk_max(uint32_t taddr, int c0, int ncols, float mx) {
-  uint32_t v[NC];
-  if constexpr (NC == 32) tc::tmem_ld32(taddr + c0, v); else tc::tmem_ld16(taddr + c0, v);
-  tc::tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < NC; j++) {
-    const float s = __uint_as_float(v[j]);
-    if (!MASK || c0 + j < ncols) mx = fmaxf(mx, s);
-  }
-  return mx;
+// S tile row (112 fp32 columns) TMEM -> registers: four loads in flight, one wait.  Constant indices only, so the
+// row stays in registers (taking the address of a sub-array would demote it to local memory).
+template <int O>
+__device__ __forceinline__ void ld32_at(uint32_t taddr, uint32_t (&s)[FT_BN]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(s[O + 0]), "=r"(s[O + 1]), "=r"(s[O + 2]), "=r"(s[O + 3]), "=r"(s[O + 4]), "=r"(s[O + 5]), "=r"(s[O + 6]), "=r"(s[O + 7]), "=r"(s[O + 8]), "=r"(s[O + 9]), "=r"(s[O + 10]), "=r"(s[O + 11]), "=r"(s[O + 12]), "=r"(s[O + 13]), "=r"(s[O + 14]), "=r"(s[O + 15]), "=r"(s[O + 16]), "=r"(s[O + 17]), "=r"(s[O + 18]), "=r"(s[O + 19]), "=r"(s[O + 20]), "=r"(s[O + 21]), "=r"(s[O + 22]), "=r"(s[O + 23]), "=r"(s[O + 24]), "=r"(s[O + 25]), "=r"(s[O + 26]), "=r"(s[O + 27]), "=r"(s[O + 28]), "=r"(s[O + 29]), "=r"(s[O + 30]), "=r"(s[O + 31])
+               : "r"(taddr)
+               : "memory");
 }
-
-// pass 2: p = 2^(s - m) -> fp16 -> swizzled smem (row base rowP, swizzle key sw); returns the partial row sum
-template <int NC, bool MASK>
-__device__ __forceinline__ float chunk_exp(uint32_t taddr, int c0, int ncols, float m, uint8_t* rowP, int sw) {
-  uint32_t v[NC];
-  if constexpr (NC == 32) tc::tmem_ld32(taddr + c0, v); else tc::tmem_ld16(taddr + c0, v);
+template <int O>
+__device__ __forceinline__ void ld16_at(uint32_t taddr, uint32_t (&s)[FT_BN]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(s[O + 0]), "=r"(s[O + 1]), "=r"(s[O + 2]), "=r"(s[O + 3]), "=r"(s[O + 4]), "=r"(s[O + 5]), "=r"(s[O + 6]), "=r"(s[O + 7]), "=r"(s[O + 8]), "=r"(s[O + 9]), "=r"(s[O + 10]), "=r"(s[O + 11]), "=r"(s[O + 12]), "=r"(s[O + 13]), "=r"(s[O + 14]), "=r"(s[O + 15])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void load_s_row(uint32_t tS, uint32_t (&s)[FT_BN]) {
+  ld32_at<0>(tS, s);
+  ld32_at<32>(tS + 32, s);
+  ld32_at<64>(tS + 64, s);
+  ld16_at<96>(tS + 96, s);
   tc::tmem_ld_wait();
-  float sum = 0.f;
-#pragma unroll
-  for (int g = 0; g < NC / 8; g++) {
-    float p[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int col = c0 + g * 8 + j;
-      float e = ex2f(__uint_as_float(v[g * 8 + j]) - m);
-      if (MASK && col >= ncols) e = 0.f;
-      p[j] = e;
-      sum += e;
-    }
-    const int cc = (c0 >> 3) + g;                 // 16-byte chunk index along kv (0..13)
-    uint8_t* dst = rowP + (cc >> 3) * (FT_BM * 128) + (((cc & 7) ^ sw) << 4);
-    st_shared_v4(dst, pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
-  }
-  return sum;
 }
 
 __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_constant__ FlashMaps maps,
@@ -106,7 +94,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   uint64_t* s_full = q_full + 2;             // [2]
   uint64_t* p_full = s_full + 2;             // [2]
   uint64_t* o_full = p_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = (Nq + FT_BM - 1) / FT_BM;
@@ -123,6 +112,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       tc::mbar_init(&s_full[w], 1);
       tc::mbar_init(&p_full[w], 128);
       tc::mbar_init(&o_full[w], 1);
+      tc::mbar_init(&s_free[w], 128);
     }
     tc::fence_barrier_init();
   }
@@ -135,6 +125,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // register redistribution (the service warpgroup gives registers to the two softmax warpgroups); issued inside the
+  // role branches so that ptxas allocates each region against its own budget.  The pool is the CTA's launch allocation
+  // (168 x 384): 2 x (208 - 168) x 128 taken == (168 - 88) x 128 released, otherwise the second inc blocks forever.
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 8) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -159,49 +153,54 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       constexpr uint32_t idesc_o = tc::umma_idesc(0, FT_BM, FT_D);    // 128 x 64
       const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP), kv_addr = tc::smem_u32(sKV);
       uint32_t kvi = 0, it = 0, cnt = 0;   // cnt: kv tiles issued so far for this CTA (per warpgroup)
+      auto issue_qk = [&](int w, uint32_t stage) {
+        const uint64_t ad = tc::umma_desc_sw128(q_addr + w * FT_Q_BYTES);
+        const uint64_t bd = tc::umma_desc_sw128(kv_addr + stage * FT_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < FT_D / 16; k++)
+          tc::umma_f16(tmem_base + w * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, k != 0);
+        tc::umma_commit(&s_full[w]);
+      };
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, it++) {
         tc::mbar_wait(&q_full[0], it & 1);
         tc::mbar_wait(&q_full[1], it & 1);
+        tc::mbar_wait(&kv_full[kvi % FT_STAGES], (kvi / FT_STAGES) & 1);
         tc::fence_after_sync();
-        for (int t = 0; t <= nkt; t++) {
-          const uint32_t st_cur = (kvi + t) % FT_STAGES, st_prev = (kvi + t - 1 + FT_STAGES) % FT_STAGES;
-          if (t < nkt) {
-            tc::mbar_wait(&kv_full[st_cur], ((kvi + t) / FT_STAGES) & 1);
-            tc::fence_after_sync();
-          }
-          for (int w = 0; w < 2; w++) {
-            if (t >= 1) {   // P_w(t-1) is in smem, S_w and the PV_w buffer have been drained by the softmax warpgroup
-              tc::mbar_wait(&p_full[w], (cnt + t - 1) & 1);
+        // S buffers are free: the warpgroups drained the previous pair's last S tile before their last p_full arrival
+        issue_qk(0, kvi % FT_STAGES);
+        issue_qk(1, kvi % FT_STAGES);
+        for (int t = 0; t < nkt; t++) {
+          const uint32_t st_cur = (kvi + t) % FT_STAGES, st_next = (kvi + t + 1) % FT_STAGES;
+          if (t + 1 < nkt) {
+            tc::mbar_wait(&kv_full[st_next], ((kvi + t + 1) / FT_STAGES) & 1);
+            for (int w = 0; w < 2; w++) {     // S_w(t) is in registers -> the tensor core may overwrite it
+              tc::mbar_wait(&s_free[w], (cnt + t) & 1);
               tc::fence_after_sync();
-            }
-            if (t < nkt) {
-              const uint64_t ad = tc::umma_desc_sw128(q_addr + w * FT_Q_BYTES);
-              const uint64_t bd = tc::umma_desc_sw128(kv_addr + st_cur * FT_STAGE_BYTES);
-#pragma unroll
-              for (int k = 0; k < FT_D / 16; k++)
-                tc::umma_f16(tmem_base + w * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, k != 0);
-              tc::umma_commit(&s_full[w]);
-            }
-            if (t >= 1) {
-              const uint32_t pa = p_addr + w * FT_P_BYTES;
-              const uint32_t va = kv_addr + st_prev * FT_STAGE_BYTES + FT_K_BYTES;
-#pragma unroll
-              for (int k = 0; k < FT_BN / 16; k++) {
-                const uint64_t ad = tc::umma_desc_sw128(pa + (k >> 2) * (FT_BM * 128)) + (uint64_t)((k & 3) * 2);
-                const uint64_t bd = tc::umma_desc_sw128(va + (k >> 2) * (FT_D * 128)) + (uint64_t)((k & 3) * 2);
-                tc::umma_f16(tmem_base + 256 + w * 64, ad, bd, idesc_o, k != 0);
-              }
-              tc::umma_commit(&o_full[w]);
+              issue_qk(w, st_next);
             }
           }
-          if (t >= 1) tc::umma_commit(&kv_empty[st_prev]);
+          for (int w = 0; w < 2; w++) {       // P_w(t) is in smem (and O_w has been rescaled if needed)
+            tc::mbar_wait(&p_full[w], (cnt + t) & 1);
+            tc::fence_after_sync();
+            const uint32_t pa = p_addr + w * FT_P_BYTES;
+            const uint32_t va = kv_addr + st_cur * FT_STAGE_BYTES + FT_K_BYTES;
+#pragma unroll
+            for (int k = 0; k < FT_BN / 16; k++) {
+              const uint64_t ad = tc::umma_desc_sw128(pa + (k >> 2) * (FT_BM * 128)) + (uint64_t)((k & 3) * 2);
+              const uint64_t bd = tc::umma_desc_sw128(va + (k >> 2) * (FT_D * 128)) + (uint64_t)((k & 3) * 2);
+              tc::umma_f16(tmem_base + 256 + w * 64, ad, bd, idesc_o, (t | k) != 0);
+            }
+            tc::umma_commit(&o_full[w]);
+          }
+          tc::umma_commit(&kv_empty[st_cur]);
         }
         kvi += nkt;
         cnt += nkt;
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ================= softmax warpgroups =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int w = warp >> 2;
     const int r = threadIdx.x & 127;
     const int sw = r & 7;
@@ -230,70 +229,73 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       tc::fence_proxy_async();
       tc::mbar_arrive(&q_full[w]);
 
-      float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-      float O[FT_D];
-#pragma unroll
-      for (int i = 0; i < FT_D; i++) O[i] = 0.f;
-
+      float m = -INFINITY, l = 0.f;   // m: the max the probabilities are currently expressed against (may lag)
       for (int t = 0; t < nkt; t++, cnt++) {
         const int ncols = min(FT_BN, Nk - t * FT_BN);
+        uint32_t sv[FT_BN];
         tc::mbar_wait(&s_full[w], cnt & 1);
         tc::fence_after_sync();
-        float tmax = -INFINITY;
-        if (ncols == FT_BN) {
-          tmax = chunk_max<32, false>(tS, 0, ncols, tmax);
-          tmax = chunk_max<32, false>(tS, 32, ncols, tmax);
-          tmax = chunk_max<32, false>(tS, 64, ncols, tmax);
-          tmax = chunk_max<16, false>(tS, 96, ncols, tmax);
-        } else {
-          tmax = chunk_max<32, true>(tS, 0, ncols, tmax);
-          tmax = chunk_max<32, true>(tS, 32, ncols, tmax);
-          tmax = chunk_max<32, true>(tS, 64, ncols, tmax);
-          tmax = chunk_max<16, true>(tS, 96, ncols, tmax);
+        load_s_row(tS, sv);
+        tc::fence_before_sync();
+        tc::mbar_arrive(&s_free[w]);          // S is in registers: Q K^T of the next kv tile may start
+        if (ncols < FT_BN) {
+#pragma unroll
+          for (int j = 0; j < FT_BN; j++)
+            if (j >= ncols) sv[j] = 0xff800000u;   // -inf
         }
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < FT_BN; j++) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
         const float m_new = fmaxf(m, tmax);
-        const float alpha = ex2f(m - m_new);
-        if (t > 0) {   // fold P(t-1) V(t-1) into the register accumulator; also frees the P buffer
-          tc::mbar_wait(&o_full[w], (cnt - 1) & 1);
+        if (t == 0) {
+          m = m_new;
+        } else {
+          tc::mbar_wait(&o_full[w], (cnt - 1) & 1);   // P(t-1) V(t-1) retired: P buffer reusable, O stable
           tc::fence_after_sync();
+          if (__any_sync(0xffffffffu, m_new - m > FT_LAZY)) {
+            const float alpha = ex2f(m - m_new);
+            m = m_new;
+            l *= alpha;
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            uint32_t v[32];
-            tc::tmem_ld32(tO + h * 32, v);
-            tc::tmem_ld_wait();
+            for (int h = 0; h < 2; h++) {
+              uint32_t v[32];
+              tc::tmem_ld32(tO + h * 32, v);
+              tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j++) O[h * 32 + j] = fmaf(O[h * 32 + j], alpha_prev, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+              tc::tmem_st32(tO + h * 32, v);
+            }
+            tc::tmem_st_wait();
           }
         }
         float lsum = 0.f;
-        if (ncols == FT_BN) {
-          lsum += chunk_exp<32, false>(tS, 0, ncols, m_new, rowP, sw);
-          lsum += chunk_exp<32, false>(tS, 32, ncols, m_new, rowP, sw);
-          lsum += chunk_exp<32, false>(tS, 64, ncols, m_new, rowP, sw);
-          lsum += chunk_exp<16, false>(tS, 96, ncols, m_new, rowP, sw);
-        } else {
-          lsum += chunk_exp<32, true>(tS, 0, ncols, m_new, rowP, sw);
-          lsum += chunk_exp<32, true>(tS, 32, ncols, m_new, rowP, sw);
-          lsum += chunk_exp<32, true>(tS, 64, ncols, m_new, rowP, sw);
-          lsum += chunk_exp<16, true>(tS, 96, ncols, m_new, rowP, sw);
+#pragma unroll
+        for (int g = 0; g < FT_BN / 8; g++) {
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            p[j] = ex2f(__uint_as_float(sv[g * 8 + j]) - m);
+            lsum += p[j];
+          }
+          uint8_t* dst = rowP + (g >> 3) * (FT_BM * 128) + (((g & 7) ^ sw) << 4);
+          st_shared_v4(dst, pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
         }
-        l = fmaf(l, alpha, lsum);
-        m = m_new;
-        alpha_prev = alpha;
+        l += lsum;
         tc::fence_before_sync();
         tc::fence_proxy_async();
         tc::mbar_arrive(&p_full[w]);
       }
-      // last P V product
+      // all P V products have been accumulated in TMEM
       tc::mbar_wait(&o_full[w], (cnt - 1) & 1);
       tc::fence_after_sync();
+      float O[FT_D];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         uint32_t v[32];
         tc::tmem_ld32(tO + h * 32, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j++) O[h * 32 + j] = fmaf(O[h * 32 + j], alpha_prev, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j++) O[h * 32 + j] = __uint_as_float(v[j]);
       }
       if (valid) {
         const float inv = 1.f / l;
