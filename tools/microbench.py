@@ -9,6 +9,30 @@ from transception_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=3):
+    """CUDA-graph replay of `iters` back-to-back calls (no host launch overhead in the number)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        fn()
+        st.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e3
+
+
+def timeit_eager(fn, iters=20, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
