@@ -1,0 +1,114 @@
+"""CPU tests of the host side: C-ABI surface, drop-in mirror, loud failure without CUDA, world-size-2 sharding."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "transception_sm100.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tcx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from transception_b200 import ops
+    assert os.path.exists(ops.LIB_PATH), "build the library first: python -m transception_b200.build"
+    lib = ctypes.CDLL(ops.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # the ctypes binding declares a prototype for every export, and nothing that is not in the header
+    assert sorted(ops.EXPORTS) == names
+    lib.tcx_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.tcx_version()
+
+
+def test_mirror_state_dict_surface():
+    from networks.MSTr import MSTransception
+    torch.manual_seed(1234)
+    net = MSTransception(num_classes=9)
+    sd = net.state_dict()
+    assert len(sd) == 2200
+    assert sum(p.numel() for p in net.parameters()) == 47316553
+    # aliases created by the shared cpe/crpe modules
+    a = "backbone.mhca_stage2.mhca_blks.0.cpe.proj.weight"
+    b = "backbone.mhca_stage2.mhca_blks.0.MHCA_layers.1.cpe.proj.weight"
+    assert sd[a].data_ptr() == sd[b].data_ptr()
+    for dead in ("backbone.conv1_1_s1.weight", "backbone.cpe.proj.weight",
+                 "bridge.bridge_layer1.attn.scale_reduce.sr0.weight", "backbone.block1.0.mlp.norm2.weight"):
+        assert dead in sd
+
+
+def test_constructor_contract():
+    from networks.MSTr import MSTransception
+    for kw in (dict(Stage_3or4=4), dict(have_bridge="sp"), dict(have_bridge="para"), dict(concat="cbam")):
+        with pytest.raises(NotImplementedError):
+            MSTransception(num_classes=9, **kw)
+    net = MSTransception(num_classes=2, br_ch_att_list=[False, True, False, False])
+    assert type(net.bridge.bridge_layer2.attn).__name__ == "M_EfficientChannelAtten"
+    assert net.decoder_0.last_layer.weight.shape[0] == 2
+
+
+def test_no_cpu_fallback():
+    from networks.MSTr import MSTransception
+    net = MSTransception(num_classes=9).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 1, 224, 224))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "transception_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, "%s mentions the oracle" % f
+
+
+def test_shard_range():
+    from transception_b200 import shard
+    assert shard.shard_range(128, 3, 8) == (48, 64)
+    assert [shard.shard_range(32, r, 2) for r in range(2)] == [(0, 16), (16, 32)]
+    with pytest.raises(ValueError):
+        shard.shard_range(30, 0, 4)
+    with pytest.raises(ValueError):
+        shard.shard_range(32, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transception_b200 import shard
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(8, 1, 4, 4, generator=g)                # same global batch on every rank
+    mine = shard.shard_batch(x, rank, world)
+    y = mine * 2 + 1                                       # stand-in for the per-image forward (no collective)
+    full = shard.gather_rows(y, world)
+    ms = shard.max_over_ranks([10.0 + rank, 5.0 - rank])
+    q.put((rank, torch.equal(full, x * 2 + 1), ms))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, ms in res:
+        assert ok, "rank %d: gathered shards differ from the unsharded result" % rank
+        assert ms == [11.0, 5.0]

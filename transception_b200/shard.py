@@ -1,0 +1,42 @@
+"""Data-parallel plumbing for the hot path: images shard across ranks, one process per GPU.
+
+The forward needs no data-path collective — rank ``r`` of ``W`` owns images ``[r*per, (r+1)*per)`` of the global
+batch (reference ``trainer.py:86``: ``batch_size * n_gpu``) — so the only cross-rank traffic here is the
+max-over-ranks reduction of device-measured times used by ``bench.py``.  Works on any ``torch.distributed``
+backend (NCCL on the GPU box, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch, rank, world):
+    """Half-open image range of ``rank``; the global batch must divide evenly (weak scaling: fixed per-rank batch)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    if global_batch % world:
+        raise ValueError("global batch %d does not divide over %d ranks" % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_batch(x, rank, world):
+    """The slice of a global batch tensor ``[B, ...]`` owned by ``rank``."""
+    lo, hi = shard_range(x.shape[0], rank, world)
+    return x[lo:hi]
+
+
+def max_over_ranks(values, device="cpu"):
+    """Element-wise MAX of a list of floats over all ranks (identity when not initialised / world 1)."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def gather_rows(x, world):
+    """All-gather equal-sized shards back into the global batch order (used by tests / multi-GPU inference)."""
+    if not (dist.is_available() and dist.is_initialized()) or world == 1:
+        return x
+    parts = [torch.empty_like(x) for _ in range(world)]
+    dist.all_gather(parts, x.contiguous())
+    return torch.cat(parts, 0)
