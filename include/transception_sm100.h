@@ -27,7 +27,7 @@ const char* tcx_version(void);
 const char* tcx_last_error(void);
 /* 1 when a usable sm_100 device is current, else 0 (with tcx_last_error set) */
 int tcx_device_ok(void);
-/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc"}; value 0/1; returns previous value */
+/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc","f16_pipeline"}; value 0/1; returns previous value */
 int tcx_set_flag(const char* name, int value);
 
 /* number of kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
@@ -45,6 +45,19 @@ int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
 /* nn.Linear: y[M,N] = act(x[M,K] w[N,K]^T + bias) + residual;  act: 0 none 1 GELU(erf) 2 Hardswish 3 sigmoid */
 int tcx_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
                    int K, int act, void* stream);
+/* fp16-operand form of nn.Linear (tcgen05 kind::f16, fp32 accumulate; fp16 has TF32's 10-bit mantissa):
+ * x16 [M,K] and w16 [N,K] are fp16 (tcx_f32_to_f16), y is fp32 (+bias, +fp32 residual) or, with out_f16, fp16 (+bias). */
+int tcx_f32_to_f16(const float* src, void* dst, long long n, void* stream);
+int tcx_linear_f16_fwd(const void* x16, const void* w16, const float* bias, const float* residual, void* y, int M, int N,
+                       int K, int out_f16, void* stream);
+/* Prepared weights: the fp16-intermediate pipeline (default) needs an fp16 copy of every GEMM weight matrix
+ * (nn.Linear / 1x1 conv `*_w` slots of the `p` tables).  tcx_prepare_weight_f16 converts w32 into the caller-owned
+ * buffer w16 and records the pair; an op whose matrices are all prepared runs with fp16 tensor-core operands and fp16
+ * intermediates (fp32 residual streams, fp32 accumulation), otherwise it runs its fp32-storage / TF32 form.  This
+ * registry is the only state the library keeps: w16 must stay valid until tcx_forget_weight(w32), and must be
+ * re-prepared when the values at w32 change.  Flag "f16_pipeline" = 0 disables the lookup. */
+int tcx_prepare_weight_f16(const float* w32, void* w16, long long numel, void* stream);
+int tcx_forget_weight(const float* w32);
 /* Conv2d_BN 1x1 (MSTr.py:399-404): y = act(BN(x w^T)) */
 int tcx_linear_bn_act_fwd(const float* x, const float* w, const float* bn_w, const float* bn_b, const float* bn_rm,
                           const float* bn_rv, float bn_eps, int act, float* y, int M, int N, int K, void* stream);
@@ -130,6 +143,20 @@ int tcx_flash_attn_fwd(const float* q, const float* kv, float* out, int B, int N
 size_t tcx_bridge_mixffn_workspace_bytes(int B, int S);
 int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* p, float ln_eps, float* y, int B,
                           int S, void* ws, void* stream);
+
+/* EfficientTransformerBlock.forward (MSTr.py:164-173): tx = x + Attn(LN1 x); y = tx + MixFFN(LN2 tx).
+ * p = {n1_w,n1_b, k_w,k_b,q_w,q_b,v_w,v_b,reproj_w,reproj_b, n2_w,n2_b, fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b} */
+size_t tcx_eff_block_workspace_bytes(int B, int N, int C);
+int tcx_eff_block_fwd(const float* x, const void* const* p, float ln_eps, float mlp_ln_eps, float* y, int B, int H, int W,
+                      int C, void* ws, void* stream);
+
+/* BridgLayer_4.forward (MSTr.py:2373-2409) on the token buffer x [B][Ntok][64] (tcx_bridge_regroup_fwd) -> y.
+ * p (TCX_BRIDGE_NP slots) = {n1_w,n1_b, attn[14], n2_w,n2_b, 4 x {fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b}};
+ * attn = the tcx_bridge_sr_attn_fwd table, or with channel_att the tcx_eff_attn_fwd table (8 slots, rest unused). */
+#define TCX_BRIDGE_NP 50
+size_t tcx_bridge_layer_workspace_bytes(int B, int S);
+int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, float scale, float ln_eps, float* y,
+                         int B, int S, void* ws, void* stream);
 
 /* decoder — MyDecoderLayer.forward pieces (MSTr.py:273-290, :184-201, :212-227) */
 int tcx_concat_linear_fwd(const float* x1, const float* x2, const float* w, const float* b, float* y, int M, int C1,

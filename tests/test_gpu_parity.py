@@ -1,7 +1,7 @@
 """GPU parity: every fused op of the hot path (called through the drop-in modules -> C ABI -> sm_100a kernels)
 against the CPU oracle on the same seeded weights and inputs.
 
-Tolerances (stated): tensor-core kernels compute in TF32 / bf16 with fp32 accumulation, so the bar
+Tolerances (stated): tensor-core kernels compute in TF32 / fp16 with fp32 accumulation, so the bar
 for fp32-IO with tensor-core MMA applies: max-abs <= 2e-2 * max(1, absmax) per op, logits max-abs <= 5e-2,
 mean-abs <= 5e-3, argmax Dice >= 0.99.  With the tensor-core back ends switched off (FFMA kernels) the strict
 fp32 bar applies: <= 1e-4 * max(1, absmax).
@@ -58,15 +58,19 @@ def _close(got, want, tol, what):
     return err
 
 
-@pytest.fixture(params=["tc", "ffma"])
+@pytest.fixture(params=["f16", "tf32", "ffma"])
 def backend(request, cuda_lib):
+    """f16: default pipeline (fp16 tensor-core operands + fp16 intermediates); tf32: fp32 storage, TF32 MMA;
+    ffma: strict fp32 CUDA-core kernels."""
     from transception_b200 import ops
-    on = 1 if request.param == "tc" else 0
+    on = 0 if request.param == "ffma" else 1
     ops.set_flag("gemm_tc", on)
     ops.set_flag("flash_tc", on)
+    ops.set_flag("f16_pipeline", 1 if request.param == "f16" else 0)
     yield (TC_TOL if on else FP32_TOL)
     ops.set_flag("gemm_tc", 1)
     ops.set_flag("flash_tc", 1)
+    ops.set_flag("f16_pipeline", 1)
 
 
 # ---- primitives ---------------------------------------------------------------------------------
@@ -94,6 +98,23 @@ def test_linear(backend, M, N, K, act):
 
 
 # ---- stage 1 ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 192, 64), (777, 320, 1280), (12544, 256, 64), (300, 2048, 512),
+                                   (33, 64, 128), (4097, 128, 320)])
+@pytest.mark.parametrize("out16", [False, True])
+def test_linear_f16(cuda_lib, M, N, K, out16):
+    """fp16-operand tcgen05 GEMM (kind::f16) with fp32 or fp16 output, against fp64 on the unrounded operands."""
+    from transception_b200 import ops
+    x, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2) * K ** -0.5, _rand(N, seed=3)
+    res = None if out16 else _rand(M, N, seed=4)
+    want = x.double() @ w.double().T + b.double()
+    if res is not None:
+        want = want + res.double()
+    got = ops.linear_f16(ops.to_f16(x.cuda()), ops.to_f16(w.cuda()), b.cuda(), residual=None if res is None else res.cuda(),
+                         out_f16=out16)
+    assert got.dtype == (torch.float16 if out16 else torch.float32)
+    _close(got, want.float(), TC_TOL, "linear_f16 %dx%dx%d" % (M, N, K))
+
+
 @pytest.mark.parametrize("cin", [1, 3])
 def test_patch_embed(model, cin):
     net, sd = model

@@ -62,6 +62,13 @@ def main():
             gb = (M * K + N * K + M * N) * 4 / 1e9
             rows.append("linear M=%6d N=%4d K=%4d : %7.1f us  (+res %7.1f, gelu %7.1f)  min-bytes %.1f MB -> %.0f GB/s, %.1f TF/s" % (
                 M, N, K, t0, t1, t2, gb * 1e3, gb / (t0 * 1e-6), 2.0 * M * N * K / (t0 * 1e-6) / 1e12))
+    for (M, N, K) in [(50176, 256, 64), (50176, 64, 256), (12544, 192, 64), (12544, 512, 128), (3136, 128, 512),
+                      (784, 1280, 320), (97216, 64, 64)]:
+        x, w, b, res = r(M, K).half(), r(N, K).half(), r(N), r(M, N)
+        if "linear".startswith(only) or only in "linear":
+            t0 = timeit(lambda: ops.linear_f16(x, w, b, out_f16=True))
+            t1 = timeit(lambda: ops.linear_f16(x, w, b, residual=res))
+            rows.append("linear_f16 M=%6d N=%4d K=%4d : f16 out %7.1f us   f32 out + res %7.1f us" % (M, N, K, t0, t1))
     for (M, C) in [(50176, 64), (97216, 64), (12544, 128), (3136, 320), (784, 512)]:
         x, w, b = r(M, C), r(C), r(C)
         t0 = timeit(lambda: ops.layernorm(x, w, b, 1e-5))

@@ -7,6 +7,9 @@
 #include "common.cuh"
 #include "attention.cuh"
 #include "misc.cuh"
+#include "fused16.cuh"
+#include <mutex>
+#include <unordered_map>
 
 // ---- error state -----------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -54,8 +57,20 @@ void tcx_prof_end(const char* name, cudaStream_t st) {
 
 static int g_flag_gemm_tc = 1;
 static int g_flag_flash_tc = 1;
+static int g_flag_f16 = 1;
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
 bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
+
+// Prepared-weight registry: fp32 weight pointer -> caller-owned fp16 copy (tcx_prepare_weight_f16).  The fp16
+// pipeline is taken only when every matrix of an op has a prepared copy; otherwise the op runs its fp32/TF32 form.
+static std::mutex g_w16_mu;
+static std::unordered_map<const void*, const void*> g_w16;
+static const __half* w16_of(const void* w32) {
+  if (!g_flag_f16 || !g_flag_gemm_tc) return nullptr;
+  std::lock_guard<std::mutex> lk(g_w16_mu);
+  auto it = g_w16.find(w32);
+  return it == g_w16.end() ? nullptr : reinterpret_cast<const __half*>(it->second);
+}
 
 namespace {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -210,6 +225,74 @@ size_t scale_reduce_ws_floats(int B, const BridgeGeom& g) {
   return n;
 }
 
+
+// ---- fp16-intermediate pipeline ---------------------------------------------------------------------------------
+inline __half* H16(float* p) { return reinterpret_cast<__half*>(p); }
+
+struct Mix16 {
+  const __half* xn;  long long xn_bs;     // [B*N, C] dense (xn_bs = 0) or per-image slabs with batch stride xn_bs
+  const __half* w1;  const float* b1;
+  const float* dww;  const float* dwb;  const float* lnw;  const float* lnb;
+  const __half* w2;  const float* b2;
+  const float* res;  long long res_bs;
+  float* y;          long long y_bs;
+};
+// all matrices of a Mix-FFN parameter block {fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b} prepared?
+inline bool mix16_fill(const void* const* p, Mix16& m) {
+  m.w1 = w16_of(p[0]); m.w2 = w16_of(p[6]);
+  m.b1 = F(p[1]); m.dww = F(p[2]); m.dwb = F(p[3]); m.lnw = F(p[4]); m.lnb = F(p[5]); m.b2 = F(p[7]);
+  return m.w1 && m.w2;
+}
+// y = res + fc2(GELU(LN(dw3x3(fc1 xn) + fc1 xn))) with fp16 h / a buffers ([G][B*N*C4] halfs each)
+int run_mixffn16(int G, const Mix16* m, float eps, int B, int H, int W, int C, int C4, __half* hbuf, __half* abuf,
+                 cudaStream_t st) {
+  const int N = H * W;
+  const bool strided = m[0].xn_bs != 0;
+  const size_t per = (size_t)B * N * C4;
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, strided ? N : B * N, C4, C);
+    g.groups = G; g.ab16 = 1; g.out16 = 1;
+    if (strided) { g.batch = B; g.strideA = m[0].xn_bs; g.strideC = (long long)N * C4; }
+    for (int i = 0; i < G; i++) {
+      g.g[i].A = F(m[i].xn); g.g[i].W = F(m[i].w1); g.g[i].C = reinterpret_cast<float*>(hbuf + i * per);
+      g.g[i].epi.bias = m[i].b1;
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  {
+    DwLnArgs a{};
+    a.B = B; a.H = H; a.W = W; a.C = C4; a.eps = eps; a.gelu = 1;
+    for (int i = 0; i < G; i++)
+      a.g[i] = DwLnGroup{hbuf + i * per, m[i].dww, m[i].dwb, m[i].lnw, m[i].lnb, nullptr, abuf + i * per};
+    TCX_TRY(launch_dwln(a, G, true, st));
+  }
+  {
+    GemmParams g = gemm1(nullptr, nullptr, nullptr, strided ? N : B * N, C, C4);
+    g.groups = G; g.ab16 = 1;
+    if (strided) { g.batch = B; g.strideA = (long long)N * C4; g.strideC = m[0].y_bs; }
+    for (int i = 0; i < G; i++) {
+      g.g[i].A = F(abuf + i * per); g.g[i].W = F(m[i].w2); g.g[i].C = m[i].y;
+      g.g[i].epi.bias = m[i].b2; g.g[i].epi.residual = m[i].res; g.g[i].epi.ldr = C; g.g[i].epi.strideR = m[i].res_bs;
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  return 0;
+}
+
+int run_ln16(int G, const float* const* x, const float* const* w, const float* const* b, __half* const* y16,
+             float* const* y32, long long M, int C, float eps, cudaStream_t st) {
+  Ln16Args a{};
+  a.M = M; a.C = C; a.eps = eps;
+  for (int i = 0; i < G; i++) a.g[i] = Ln16Group{x[i], w[i], b[i], y16 ? y16[i] : nullptr, y32 ? y32[i] : nullptr};
+  return launch_ln16(a, G, st);
+}
+int run_ln16_1(const float* x, const float* w, const float* b, __half* y16, float* y32, long long M, int C, float eps,
+               cudaStream_t st) {
+  const float* xs[1] = {x}; const float* ws[1] = {w}; const float* bs[1] = {b};
+  __half* y16s[1] = {y16}; float* y32s[1] = {y32};
+  return run_ln16(1, xs, ws, bs, y16 ? y16s : nullptr, y32 ? y32s : nullptr, M, C, eps, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -257,6 +340,7 @@ int tcx_set_flag(const char* name, int value) {
   int* f = nullptr;
   if (!strcmp(name, "gemm_tc")) f = &g_flag_gemm_tc;
   else if (!strcmp(name, "flash_tc")) f = &g_flag_flash_tc;
+  else if (!strcmp(name, "f16_pipeline")) f = &g_flag_f16;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
   *f = value;
@@ -271,6 +355,33 @@ int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
 int tcx_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
                    int K, int act, void* stream) {
   return launch_linear(x, w, bias, residual, y, M, N, K, act, S(stream));
+}
+
+int tcx_f32_to_f16(const float* src, void* dst, long long n, void* stream) {
+  return launch_f32_to_f16(src, dst, n, S(stream));
+}
+
+int tcx_prepare_weight_f16(const float* w32, void* w16, long long numel, void* stream) {
+  TCX_REQUIRE(w32 && w16 && numel > 0, "prepare_weight: null pointer or empty weight");
+  TCX_TRY(launch_f32_to_f16(w32, w16, numel, S(stream)));
+  std::lock_guard<std::mutex> lk(g_w16_mu);
+  g_w16[w32] = w16;
+  return 0;
+}
+
+int tcx_forget_weight(const float* w32) {
+  std::lock_guard<std::mutex> lk(g_w16_mu);
+  g_w16.erase(w32);
+  return 0;
+}
+
+int tcx_linear_f16_fwd(const void* x16, const void* w16, const float* bias, const float* residual, void* y, int M, int N,
+                       int K, int out_f16, void* stream) {
+  GemmParams g = gemm1(F(x16), F(w16), reinterpret_cast<float*>(y), M, N, K);
+  g.ab16 = 1; g.out16 = out_f16 ? 1 : 0;
+  g.g[0].epi.bias = bias;
+  g.g[0].epi.residual = residual;
+  return launch_gemm(g, S(stream));
 }
 
 int tcx_linear_bn_act_fwd(const float* x, const float* w, const float* bn_w, const float* bn_b, const float* bn_rm,
@@ -340,13 +451,20 @@ int tcx_eff_attn_fwd(const float* xn, const void* const* p, const float* residua
 }
 
 // ---- K1 --------------------------------------------------------------------------------
-size_t tcx_mixffn_skip_workspace_bytes(int B, int N, int C4) { return 4 * 2 * rnd((size_t)B * N * C4); }
+size_t tcx_mixffn_skip_workspace_bytes(int B, int N, int C4) { return 4 * 3 * rnd((size_t)B * N * C4); }
 
 int tcx_mixffn_skip_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B,
                         int H, int W, int C, int C4, void* ws, void* stream) {
   Carver c(ws);
   float* h = c.take((size_t)B * H * W * C4);
   float* a = c.take((size_t)B * H * W * C4);
+  Mix16 m{};
+  if (mix16_fill(p, m)) {
+    __half* xn16 = H16(c.take((size_t)B * H * W * C4));
+    TCX_TRY(launch_f32_to_f16(xn, xn16, (long long)B * H * W * C, S(stream)));
+    m.xn = xn16; m.res = residual; m.y = y;
+    return run_mixffn16(1, &m, ln_eps, B, H, W, C, C4, H16(h), H16(a), S(stream));
+  }
   const float* xs[1] = {xn};
   const void* const* ps[1] = {p};
   const float* rs[1] = {residual};
@@ -396,6 +514,72 @@ int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int
   float* hb = c.take(G * 4 * bnc);
   float* ab = c.take(G * 4 * bnc);
   float* ctx = c.take((size_t)G * B * C * C);
+  bool fast = true;
+  for (int i = 0; i < G * L && fast; i++) {
+    const void* const* b = p + (size_t)i * TCX_MHCA_NP;
+    fast = w16_of(b[4]) && w16_of(b[12]) && w16_of(b[16]) && w16_of(b[22]);
+  }
+  if (fast) {
+    // fp16 intermediates: cpe+norm1 fused (fp32 stream xa + fp16 LN), fp16 qkv / attention output / Mix-FFN hidden
+    __half* ln16 = H16(ln);
+    __half* qkv16 = H16(qkv);
+    __half* att16 = H16(att);
+    const int Ch = C / heads;
+    for (int l = 0; l < L; l++) {
+      const void* const* blk[TCX_MAX_GROUPS];
+      for (int g = 0; g < G; g++) blk[g] = p + ((size_t)g * L + l) * TCX_MHCA_NP;
+      {
+        DwLnArgs a{};
+        a.B = B; a.H = H; a.W = W; a.C = C; a.eps = ln_eps; a.gelu = 0;
+        for (int g = 0; g < G; g++)
+          a.g[g] = DwLnGroup{x + g * bnc, F(blk[g][0]), F(blk[g][1]), F(blk[g][2]), F(blk[g][3]), xa + g * bnc, ln16 + g * bnc};
+        TCX_TRY(launch_dwln(a, G, false, st));
+      }
+      {
+        GemmParams gp = gemm1(nullptr, nullptr, nullptr, M, 3 * C, C);
+        gp.groups = G; gp.ab16 = 1; gp.out16 = 1;
+        for (int g = 0; g < G; g++) {
+          gp.g[g].A = F(ln16 + g * bnc); gp.g[g].W = F(w16_of(blk[g][4])); gp.g[g].C = reinterpret_cast<float*>(qkv16 + g * 3 * bnc);
+          gp.g[g].epi.bias = F(blk[g][5]);
+        }
+        TCX_TRY(launch_gemm(gp, st));
+      }
+      {
+        Mb16Args a{};
+        a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.scale = 1.0f / sqrtf((float)Ch);
+        for (int g = 0; g < G; g++) {
+          a.qkv[g] = qkv16 + g * 3 * bnc; a.ctx[g] = ctx + (size_t)g * B * C * Ch; a.out[g] = att16 + g * bnc;
+          for (int j = 0; j < 3; j++) { a.cw[g][j] = F(blk[g][6 + 2 * j]); a.cb[g][j] = F(blk[g][7 + 2 * j]); }
+        }
+        TCX_TRY(launch_mb_attention16(a, G, st));
+      }
+      {
+        GemmParams gp = gemm1(nullptr, nullptr, nullptr, M, C, C);
+        gp.groups = G; gp.ab16 = 1;
+        for (int g = 0; g < G; g++) {
+          gp.g[g].A = F(att16 + g * bnc); gp.g[g].W = F(w16_of(blk[g][12])); gp.g[g].C = xb + g * bnc;
+          gp.g[g].epi.bias = F(blk[g][13]); gp.g[g].epi.residual = xa + g * bnc; gp.g[g].epi.ldr = C;
+        }
+        TCX_TRY(launch_gemm(gp, st));
+      }
+      {
+        const float* xs[TCX_MAX_GROUPS]; const float* ws[TCX_MAX_GROUPS]; const float* bs[TCX_MAX_GROUPS];
+        __half* ys[TCX_MAX_GROUPS];
+        for (int g = 0; g < G; g++) { xs[g] = xb + g * bnc; ws[g] = F(blk[g][14]); bs[g] = F(blk[g][15]); ys[g] = ln16 + g * bnc; }
+        TCX_TRY(run_ln16(G, xs, ws, bs, ys, nullptr, M, C, ln_eps, st));
+      }
+      {
+        Mix16 m[TCX_MAX_GROUPS];
+        for (int g = 0; g < G; g++) {
+          m[g] = Mix16{};
+          mix16_fill(blk[g] + 16, m[g]);
+          m[g].xn = ln16 + g * bnc; m[g].res = xb + g * bnc; m[g].y = x + g * bnc;
+        }
+        TCX_TRY(run_mixffn16(G, m, mlp_ln_eps, B, H, W, C, 4 * C, H16(hb), H16(ab), st));
+      }
+    }
+    return 0;
+  }
   for (int l = 0; l < L; l++) {
     const void* const* blk[TCX_MAX_GROUPS];
     for (int g = 0; g < G; g++) blk[g] = p + ((size_t)g * L + l) * TCX_MHCA_NP;
@@ -591,11 +775,42 @@ size_t tcx_bridge_mixffn_workspace_bytes(int B, int S0) {
   return 4 * n;
 }
 
+// the four per-scale Mix-FFNs of one bridge layer on the fp16 LayerNorm output tx16 [B][ntok][64]
+static int bridge_mixffn16(const __half* tx16, const float* tx1, const void* const* p, float ln_eps, float* y, int B,
+                           const BridgeGeom& g, float* ws, cudaStream_t st) {
+  Carver c(ws);
+  const long long sb = (long long)g.ntok * 64;
+  for (int k = 0; k < 4; k++) {
+    const int hw = g.hw[k], C = g.ch[k], C4 = 4 * C, Mi = hw * hw;
+    __half* h = H16(c.take((size_t)B * Mi * C4 / 2));
+    __half* a = H16(c.take((size_t)B * Mi * C4 / 2));
+    const long long off = (long long)g.off[k] * 64;
+    Mix16 m{};
+    TCX_REQUIRE(mix16_fill(p + 8 * k, m), "bridge_mixffn16: weights of scale %d are not prepared", k);
+    m.xn = tx16 + off; m.xn_bs = sb; m.res = tx1 + off; m.res_bs = sb; m.y = y + off; m.y_bs = sb;
+    TCX_TRY(run_mixffn16(1, &m, ln_eps, B, hw, hw, C, C4, h, a, st));
+  }
+  return 0;
+}
+static bool bridge_mix_prepared(const void* const* p) {
+  for (int k = 0; k < 4; k++)
+    if (!w16_of(p[8 * k]) || !w16_of(p[8 * k + 6])) return false;
+  return true;
+}
+
 int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* p, float ln_eps, float* y, int B,
                           int S0, void* ws, void* stream) {
   cudaStream_t st = S(stream);
   BridgeGeom g;
   TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  if (bridge_mix_prepared(p)) {
+    // fp16 copy of tx goes to the tail of the workspace (the fp16 h/a buffers need only half of the fp32 budget)
+    size_t nfl = 0;
+    for (int k = 0; k < 4; k++) nfl += 2 * rnd((size_t)B * g.hw[k] * g.hw[k] * g.ch[k] * 4 / 2);
+    __half* tx16 = H16(reinterpret_cast<float*>(ws) + nfl);
+    TCX_TRY(launch_f32_to_f16(tx, tx16, (long long)B * g.ntok * 64, st));
+    return bridge_mixffn16(tx16, tx1, p, ln_eps, y, B, g, reinterpret_cast<float*>(ws), st);
+  }
   Carver c(ws);
   const long long sb = (long long)g.ntok * 64;
   for (int k = 0; k < 4; k++) {
@@ -621,6 +836,76 @@ int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* 
     }
   }
   return 0;
+}
+
+// ---- fused per-forward entries (one call per reference forward, fp16 intermediates when weights are prepared) ----
+size_t tcx_eff_block_workspace_bytes(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  return 4 * (2 * rnd(bnc)) + tcx_eff_attn_workspace_bytes(B, N, C) + tcx_mixffn_skip_workspace_bytes(B, N, 4 * C) + 1024;
+}
+
+int tcx_eff_block_fwd(const float* x, const void* const* p, float ln_eps, float mlp_ln_eps, float* y, int B, int H, int W,
+                      int C, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  const int N = H * W;
+  const size_t bnc = (size_t)B * N * C;
+  Carver c(ws);
+  float* n = c.take(bnc);
+  float* tx = c.take(bnc);
+  float* aws = c.take(tcx_eff_attn_workspace_bytes(B, N, C) / 4);
+  float* mws = c.take(tcx_mixffn_skip_workspace_bytes(B, N, 4 * C) / 4);
+  TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n, (long long)B * N, C, ln_eps, st));
+  TCX_TRY(tcx_eff_attn_fwd(n, p + 2, x, tx, B, N, C, 0, aws, stream));
+  Mix16 m{};
+  if (mix16_fill(p + 12, m)) {
+    __half* n16 = H16(n);
+    TCX_TRY(run_ln16_1(tx, F(p[10]), F(p[11]), n16, nullptr, (long long)B * N, C, ln_eps, st));
+    Carver mc(mws);
+    __half* h = H16(mc.take(bnc * 2));     // B*N*4C halfs
+    __half* a = H16(mc.take(bnc * 2));
+    m.xn = n16; m.res = tx; m.y = y;
+    return run_mixffn16(1, &m, mlp_ln_eps, B, H, W, C, 4 * C, h, a, st);
+  }
+  TCX_TRY(run_ln16_1(tx, F(p[10]), F(p[11]), nullptr, n, (long long)B * N, C, ln_eps, st));
+  return tcx_mixffn_skip_fwd(n, p + 12, mlp_ln_eps, tx, y, B, H, W, C, 4 * C, mws, stream);
+}
+
+size_t tcx_bridge_layer_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  const size_t bn = (size_t)B * g.ntok * 64;
+  size_t att = tcx_eff_attn_workspace_bytes(B, g.ntok, 64);
+  const size_t sr = tcx_bridge_sr_attn_workspace_bytes(B, S0);
+  if (sr > att) att = sr;
+  return 4 * (3 * rnd(bn)) + att + tcx_bridge_mixffn_workspace_bytes(B, S0) + 1024;
+}
+
+int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, float scale, float ln_eps, float* y,
+                         int B, int S0, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  const size_t bn = (size_t)B * g.ntok * 64;
+  const long long M = (long long)B * g.ntok;
+  Carver c(ws);
+  float* n1 = c.take(bn);
+  float* tx1 = c.take(bn);
+  float* tx = c.take(bn);
+  size_t att = tcx_eff_attn_workspace_bytes(B, g.ntok, 64);
+  const size_t sr = tcx_bridge_sr_attn_workspace_bytes(B, S0);
+  if (sr > att) att = sr;
+  float* aws = c.take(att / 4);
+  float* mws = c.take(tcx_bridge_mixffn_workspace_bytes(B, S0) / 4);
+  TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n1, M, 64, ln_eps, st));
+  if (channel_att) TCX_TRY(tcx_eff_attn_fwd(n1, p + 2, x, tx1, B, g.ntok, 64, 1, aws, stream));
+  else TCX_TRY(tcx_bridge_sr_attn_fwd(n1, p + 2, scale, ln_eps, x, tx1, B, S0, aws, stream));
+  if (bridge_mix_prepared(p + 18)) {
+    __half* tx16 = H16(tx);
+    TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), tx16, nullptr, M, 64, ln_eps, st));
+    return bridge_mixffn16(tx16, tx1, p + 18, ln_eps, y, B, g, mws, st);
+  }
+  TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), nullptr, tx, M, 64, ln_eps, st));
+  return tcx_bridge_mixffn_fwd(tx, tx1, p + 18, ln_eps, y, B, S0, mws, stream);
 }
 
 // ---- decoder ----------------------------------------------------------------------------------

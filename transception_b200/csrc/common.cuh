@@ -109,12 +109,17 @@ struct GemmParams {
   long long strideA, strideW, strideC;  // per-batch element strides (0 = shared)
   int M, N, K;
   int lda, ldw, ldc;
+  // tensor-core kernel only: A and W point at fp16 data (kind::f16 MMA) / C is written as fp16.  Leading dimensions
+  // and strides stay in elements of the respective type.  fp16 output: bias only (no BN / activation / residual).
+  int ab16, out16;
 };
 int launch_gemm(const GemmParams& p, cudaStream_t st);
 
 // convenience: single plain linear
 int launch_linear(const float* A, const float* W, const float* bias, const float* residual, float* C, int M, int N,
                   int K, int act, cudaStream_t st);
+
+int launch_f32_to_f16(const float* src, void* dst, long long n, cudaStream_t st);
 
 // ---- elementwise / normalisation (elementwise.cu) -----------------------------------------
 int launch_layernorm(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,

@@ -1,6 +1,7 @@
 // Normalisation and depthwise-convolution kernels on tokens-major / NHWC fp32 activations.
 // All of these are HBM/L2-bound: one warp owns one token row (coalesced float4 along channels),
 // reductions are warp shuffles, no shared-memory staging is needed because a row is read once.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -186,7 +187,28 @@ __global__ void __launch_bounds__(256) mixffn_mid_kernel(const MixMidGroups gs, 
   }
 }
 
+// fp32 -> fp16 (round to nearest, saturating), 8 elements per thread
+__global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y),
+                    __floats2half2_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<uint4*>(h);
+  } else {
+    for (long long j = i; j < n; j++) dst[j] = __float2half_rn(src[j]);
+  }
+}
+
 }  // namespace
+
+int launch_f32_to_f16(const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f32_to_f16: pointers must be 16-byte aligned");
+  const long long threads = (n + 7) / 8;
+  f32_to_f16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), n);
+  return tcx_check_launch("f32_to_f16");
+}
 
 #define DISPATCH_NV(C, CALL)                                         \
   do {                                                               \

@@ -1,0 +1,523 @@
+// HBM/L2-bound glue kernels of the fp16-intermediate pipeline (fp32 residual streams, fp16 tensor-core operands):
+//  * dwln_kernel   — u = dw3x3(x) + b + x ; y = [GELU](LayerNorm(u))  (reference MSTr.py:59 Mix-FFN middle with fp16 h;
+//                    MSTr.py:939-942 ConvPosEnc + norm1 with an fp32 stream).  One warp (or half warp) per token, the row
+//                    stays in registers between the convolution and the normalisation; filter taps, bias and LN affine
+//                    are staged once per block in shared memory (tap-major); a warp walks consecutive tokens so 6 of
+//                    the 9 neighbour rows hit L1.
+//  * ln16_kernel   — LayerNorm of an fp32 stream to fp16 (and/or fp32).
+//  * mb_ctx16 / mb_apply16 — Multi-Branch factorized attention + conv relative position encoding (MSTr.py:852-886,
+//                    :801-823) on an fp16 qkv buffer: per (image, head) column softmax + K^T V in shared memory, then a
+//                    row-band kernel with the V band (+3 halo rows), Q band, context and the 3x3/5x5/7x7 filters in smem.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "fused16.cuh"
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int LPT>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+  for (int o = LPT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dw3x3 + skip + LayerNorm (+GELU)
+// ------------------------------------------------------------------------------------------------------------------
+template <bool IN16, int LPT, int NV>
+__global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
+  constexpr int VEC = IN16 ? 8 : 4;
+  constexpr int SLOTS = 32 / LPT;
+  extern __shared__ float wsm[];            // [9][C] taps (centre + 1 = skip), then bias[C], lnw[C], lnb[C]
+  const DwLnGroup& g = a.g[blockIdx.y];
+  const int C = a.C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 9 * C; i += 256) {
+    const int c = i / 9, t = i - c * 9;
+    wsm[t * C + c] = g.dww[i] + (t == 4 ? 1.f : 0.f);
+  }
+  float* bsm = wsm + 9 * C;
+  for (int i = tid; i < C; i += 256) {
+    bsm[i] = g.dwb ? g.dwb[i] : 0.f;
+    bsm[C + i] = g.lnw[i];
+    bsm[2 * C + i] = g.lnb[i];
+  }
+  __syncthreads();
+  const int slot = lane / LPT, sl = lane % LPT;
+  const long long total = (long long)a.B * a.H * a.W;
+  const long long base = ((long long)blockIdx.x * 8 + warp) * (SLOTS * a.tpw);
+  const int H = a.H, W = a.W;
+  const float invC = 1.f / (float)C;
+  for (int it = 0; it < a.tpw; it++) {
+    const long long tok = base + (long long)it * SLOTS + slot;
+    if (base + (long long)it * SLOTS >= total) break;      // warp-uniform
+    const bool live = tok < total;
+    const int wq = (int)(tok % W), hq = (int)((tok / W) % H);
+    float acc[NV][VEC];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int c0 = (sl + i * LPT) * VEC;
+#pragma unroll
+      for (int q = 0; q < VEC / 4; q++) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bsm + c0 + q * 4);
+        acc[i][q * 4 + 0] = b4.x; acc[i][q * 4 + 1] = b4.y; acc[i][q * 4 + 2] = b4.z; acc[i][q * 4 + 3] = b4.w;
+      }
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int hi = hq - 1 + ky, wi = wq - 1 + kx;
+        if (!(live && hi >= 0 && hi < H && wi >= 0 && wi < W)) continue;
+        const long long nb = tok + (long long)(ky - 1) * W + (kx - 1);
+        const float* wt = wsm + (ky * 3 + kx) * C;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+          const int c0 = (sl + i * LPT) * VEC;
+          float xv[VEC];
+          if (IN16) {
+            const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g.x) + nb * C + c0);
+            float f[8];
+            unpack8(r, f);
+#pragma unroll
+            for (int j = 0; j < VEC; j++) xv[j] = f[j];
+          } else {
+            const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.x) + nb * C + c0);
+            xv[0] = r.x; xv[1] = r.y; xv[2] = r.z; xv[3] = r.w;
+          }
+#pragma unroll
+          for (int q = 0; q < VEC / 4; q++) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + c0 + q * 4);
+            acc[i][q * 4 + 0] = fmaf(xv[q * 4 + 0], w4.x, acc[i][q * 4 + 0]);
+            acc[i][q * 4 + 1] = fmaf(xv[q * 4 + 1], w4.y, acc[i][q * 4 + 1]);
+            acc[i][q * 4 + 2] = fmaf(xv[q * 4 + 2], w4.z, acc[i][q * 4 + 2]);
+            acc[i][q * 4 + 3] = fmaf(xv[q * 4 + 3], w4.w, acc[i][q * 4 + 3]);
+          }
+        }
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+#pragma unroll
+      for (int j = 0; j < VEC; j++) s += acc[i][j];
+    const float mean = seg_sum<LPT>(s) * invC;
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++)
+#pragma unroll
+      for (int j = 0; j < VEC; j++) { const float d = acc[i][j] - mean; q2 = fmaf(d, d, q2); }
+    const float rstd = rsqrtf(seg_sum<LPT>(q2) * invC + a.eps);
+    if (!live) continue;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int c0 = (sl + i * LPT) * VEC;
+      if (g.u) {
+#pragma unroll
+        for (int q = 0; q < VEC / 4; q++)
+          *reinterpret_cast<float4*>(g.u + tok * C + c0 + q * 4) =
+              make_float4(acc[i][q * 4], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
+      }
+      float o[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC / 4; q++) {
+        const float4 w4 = *reinterpret_cast<const float4*>(bsm + C + c0 + q * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(bsm + 2 * C + c0 + q * 4);
+        o[q * 4 + 0] = fmaf((acc[i][q * 4 + 0] - mean) * rstd, w4.x, b4.x);
+        o[q * 4 + 1] = fmaf((acc[i][q * 4 + 1] - mean) * rstd, w4.y, b4.y);
+        o[q * 4 + 2] = fmaf((acc[i][q * 4 + 2] - mean) * rstd, w4.z, b4.z);
+        o[q * 4 + 3] = fmaf((acc[i][q * 4 + 3] - mean) * rstd, w4.w, b4.w);
+      }
+      if (a.gelu) {
+#pragma unroll
+        for (int j = 0; j < VEC; j++) o[j] = gelu_erf(o[j]);
+      }
+      __half* yp = g.y + tok * C + c0;
+      if (VEC == 8) {
+        *reinterpret_cast<uint4*>(yp) = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[VEC - 4], o[VEC - 3]),
+                                                   pack2(o[VEC - 2], o[VEC - 1]));
+      } else {
+        *reinterpret_cast<uint2*>(yp) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm fp32 -> fp16 (and/or fp32)
+// ------------------------------------------------------------------------------------------------------------------
+template <int LPT, int NV>
+__global__ void __launch_bounds__(256) ln16_kernel(const Ln16Args a) {
+  constexpr int SLOTS = 32 / LPT;
+  const Ln16Group& g = a.g[blockIdx.y];
+  const int C = a.C, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane / LPT, sl = lane % LPT;
+  const long long base = ((long long)blockIdx.x * 8 + warp) * (SLOTS * a.tpw);
+  const float invC = 1.f / (float)C;
+  float4 wv[NV], bv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    wv[i] = *reinterpret_cast<const float4*>(g.w + (sl + i * LPT) * 4);
+    bv[i] = *reinterpret_cast<const float4*>(g.b + (sl + i * LPT) * 4);
+  }
+  for (int it = 0; it < a.tpw; it++) {
+    const long long row = base + (long long)it * SLOTS + slot;
+    if (base + (long long)it * SLOTS >= a.M) break;
+    const bool live = row < a.M;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      v[i] = live ? *reinterpret_cast<const float4*>(g.x + row * C + (sl + i * LPT) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = seg_sum<LPT>(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(seg_sum<LPT>(q) * invC + a.eps);
+    if (!live) continue;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int c0 = (sl + i * LPT) * 4;
+      const float o0 = fmaf((v[i].x - mean) * rstd, wv[i].x, bv[i].x), o1 = fmaf((v[i].y - mean) * rstd, wv[i].y, bv[i].y);
+      const float o2 = fmaf((v[i].z - mean) * rstd, wv[i].z, bv[i].z), o3 = fmaf((v[i].w - mean) * rstd, wv[i].w, bv[i].w);
+      if (g.y16) *reinterpret_cast<uint2*>(g.y16 + row * C + c0) = make_uint2(pack2(o0, o1), pack2(o2, o3));
+      if (g.y32) *reinterpret_cast<float4*>(g.y32 + row * C + c0) = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-Branch factorized attention, fp16 qkv
+// ------------------------------------------------------------------------------------------------------------------
+// grid (heads, B, G), 256 threads.  ctx[b][h][k][v] = scale * sum_n softmax_n(K)[n,k] V[n,v]
+__global__ void __launch_bounds__(256) mb_ctx16_kernel(const Mb16Args a) {
+  extern __shared__ float sm[];
+  const int N = a.H * a.W, C = a.C, Ch = a.C / a.heads;
+  float* ks = sm;                       // [N][Ch]
+  float* vs = ks + (size_t)N * Ch;      // [N][Ch]
+  float* red = vs + (size_t)N * Ch;     // [256]
+  float* mx = red + 256;                // [Ch]
+  float* ss = mx + Ch;                  // [Ch]
+  float* cacc = ss + Ch;                // [Ch*Ch]
+  const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y, gi = blockIdx.z;
+  const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
+  const int vpr = Ch / 8;               // 16-byte vectors per row slice
+  for (int i = tid; i < N * vpr * 2; i += 256) {
+    const int which = i / (N * vpr);    // 0 = K, 1 = V
+    const int r = i - which * N * vpr;
+    const int n = r / vpr, j = r - n * vpr;
+    const uint4 raw = *reinterpret_cast<const uint4*>(base + (long long)n * 3 * C + (1 + which) * C + h * Ch + j * 8);
+    float f[8];
+    unpack8(raw, f);
+    float* dst = (which ? vs : ks) + n * Ch + j * 8;
+#pragma unroll
+    for (int q = 0; q < 8; q++) dst[q] = f[q];
+  }
+  for (int i = tid; i < Ch * Ch; i += 256) cacc[i] = 0.f;
+  __syncthreads();
+  const int nsl = 256 / Ch;             // token slices per column
+  const int ck = tid % Ch, slc = tid / Ch;
+  float m = -INFINITY;
+  if (slc < nsl)
+    for (int n = slc; n < N; n += nsl) m = fmaxf(m, ks[n * Ch + ck]);
+  red[tid] = m;
+  __syncthreads();
+  if (tid < Ch) {
+    float mm = -INFINITY;
+    for (int s = 0; s < nsl; s++) mm = fmaxf(mm, red[s * Ch + tid]);
+    mx[tid] = mm;
+  }
+  __syncthreads();
+  float sum = 0.f;
+  if (slc < nsl) {
+    const float mc = mx[ck];
+    for (int n = slc; n < N; n += nsl) {
+      const float e = __expf(ks[n * Ch + ck] - mc);
+      ks[n * Ch + ck] = e;
+      sum += e;
+    }
+  }
+  red[tid] = slc < nsl ? sum : 0.f;
+  __syncthreads();
+  if (tid < Ch) {
+    float t = 0.f;
+    for (int s = 0; s < nsl; s++) t += red[s * Ch + tid];
+    ss[tid] = t;
+  }
+  // ctx pairs: nsp token splits per (k, v) pair when Ch*Ch < 256
+  const int npairs = Ch * Ch;
+  const int nsp = npairs >= 256 ? 1 : 256 / npairs;
+  for (int p0 = 0; p0 < npairs * nsp; p0 += 256) {
+    const int idx = p0 + tid;
+    if (idx < npairs * nsp) {
+      const int p = idx % npairs, sp = idx / npairs;
+      const int k = p / Ch, v = p - k * Ch;
+      float a0 = 0.f, a1 = 0.f;
+      int n = sp;
+      for (; n + nsp < N; n += 2 * nsp) {
+        a0 = fmaf(ks[n * Ch + k], vs[n * Ch + v], a0);
+        a1 = fmaf(ks[(n + nsp) * Ch + k], vs[(n + nsp) * Ch + v], a1);
+      }
+      if (n < N) a0 = fmaf(ks[n * Ch + k], vs[n * Ch + v], a0);
+      if (nsp > 1) atomicAdd(&cacc[p], a0 + a1);
+      else cacc[p] = a0 + a1;
+    }
+  }
+  __syncthreads();
+  float* __restrict__ out = a.ctx[gi] + ((long long)b * a.heads + h) * npairs;
+  for (int p = tid; p < npairs; p += 256) out[p] = a.scale * cacc[p] / ss[p / Ch];
+}
+
+// conv relative position encoding + factorized attention for the channels of one window group (WIN x WIN filters):
+// a thread owns T adjacent tokens of one channel pair, slides the V window along x in registers and reuses each filter
+// tap for the T outputs.  All loops are compile-time unrolled; a warp never mixes window sizes.
+template <int WIN, int T>
+__device__ __forceinline__ void mb_apply_group(const __half* __restrict__ vt, const __half* __restrict__ qt,
+                                               const float* __restrict__ ctx, const float* __restrict__ wt,
+                                               const float* __restrict__ bs, __half* __restrict__ outp, int rows, int W,
+                                               int C, int CP, int Ch, int c_begin, int nch, int tid) {
+  constexpr int R = WIN / 2;
+  const int np = nch / 2, xg_n = W / T;
+  const int items = rows * xg_n * np;
+  for (int i = tid; i < items; i += 256) {
+    const int p = i % np, xg = (i / np) % xg_n, ty = i / (np * xg_n);
+    const int cl = 2 * p, c = c_begin + cl, x0 = xg * T;
+    const int h = c / Ch, cv = c - h * Ch;
+    float v0[T], v1[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) { v0[t] = bs[c]; v1[t] = bs[c + 1]; }
+#pragma unroll
+    for (int ky = 0; ky < WIN; ky++) {
+      const __half* vrow = vt + ((size_t)(ty + 3 + ky - R) * W) * CP + c;
+      float2 win[T + WIN - 1];
+#pragma unroll
+      for (int j = 0; j < T + WIN - 1; j++) {
+        const int xx = x0 + j - R;
+        win[j] = (xx >= 0 && xx < W) ? __half22float2(*reinterpret_cast<const __half2*>(vrow + (size_t)xx * CP))
+                                     : make_float2(0.f, 0.f);
+      }
+      const float* wrow = wt + (size_t)(ky * WIN) * nch + cl;
+#pragma unroll
+      for (int kx = 0; kx < WIN; kx++) {
+        const float2 ww = *reinterpret_cast<const float2*>(wrow + (size_t)kx * nch);
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          v0[t] = fmaf(win[t + kx].x, ww.x, v0[t]);
+          v1[t] = fmaf(win[t + kx].y, ww.y, v1[t]);
+        }
+      }
+    }
+    float f0[T], f1[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) { f0[t] = 0.f; f1[t] = 0.f; }
+    const float* crow = ctx + (size_t)h * Ch * Ch + cv;
+    const __half* qbase = qt + ((size_t)ty * W + x0) * C;
+    for (int k = 0; k < Ch; k += 2) {
+      const float2 ca = *reinterpret_cast<const float2*>(crow + (size_t)k * Ch);
+      const float2 cb = *reinterpret_cast<const float2*>(crow + (size_t)(k + 1) * Ch);
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        const float2 q2 = __half22float2(*reinterpret_cast<const __half2*>(qbase + (size_t)t * C + h * Ch + k));
+        f0[t] = fmaf(q2.x, ca.x, f0[t]); f1[t] = fmaf(q2.x, ca.y, f1[t]);
+        f0[t] = fmaf(q2.y, cb.x, f0[t]); f1[t] = fmaf(q2.y, cb.y, f1[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const float2 qc = __half22float2(*reinterpret_cast<const __half2*>(qbase + (size_t)t * C + c));
+      *reinterpret_cast<uint32_t*>(outp + ((size_t)ty * W + x0 + t) * C + c) = pack2(fmaf(qc.x, v0[t], f0[t]), fmaf(qc.y, v1[t], f1[t]));
+    }
+  }
+}
+
+// grid (bands, B, G), 256 threads. out[n,c] = sum_k q[n,h*Ch+k] ctx[h][k][cv] + q[n,c] * (dwconv_win(h)(V)[n,c] + bias[c])
+template <int T>
+__global__ void __launch_bounds__(256) mb_apply16_kernel(const Mb16Args a, int R) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int H = a.H, W = a.W, C = a.C, Ch = a.C / a.heads, N = H * W;
+  const int CP = C + 8;                 // padded channel pitch of the V band (bank spreading)
+  const int tid = threadIdx.x, b = blockIdx.y, gi = blockIdx.z;
+  const int r0 = blockIdx.x * R;
+  const int rows = min(R, H - r0);
+  const int c3 = 2 * Ch, c5 = 3 * Ch, c7 = 3 * Ch;
+  __half* vt = reinterpret_cast<__half*>(smraw);                   // [(R+6)][W][CP]
+  __half* qt = vt + (size_t)(R + 6) * W * CP;                      // [R][W][C]
+  float* ctx = reinterpret_cast<float*>(qt + (size_t)R * W * C);   // [heads][Ch][Ch]
+  float* w3 = ctx + C * Ch;                                        // [9][c3]
+  float* w5 = w3 + 9 * c3;                                         // [25][c5]
+  float* w7 = w5 + 25 * c5;                                        // [49][c7]
+  float* bs = w7 + 49 * c7;                                        // [C]
+  const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
+  const int vpr = C / 8;
+  // V band with 3 halo rows on each side (zero outside the map)
+  for (int i = tid; i < (R + 6) * W * vpr; i += 256) {
+    const int j = i % vpr, px = (i / vpr) % W, ry = i / (vpr * W);
+    const int y = r0 - 3 + ry;
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && ry < rows + 6) raw = *reinterpret_cast<const uint4*>(base + (long long)(y * W + px) * 3 * C + 2 * C + j * 8);
+    *reinterpret_cast<uint4*>(vt + ((size_t)ry * W + px) * CP + j * 8) = raw;
+  }
+  for (int i = tid; i < rows * W * vpr; i += 256) {
+    const int j = i % vpr, px = (i / vpr) % W, ry = i / (vpr * W);
+    *reinterpret_cast<uint4*>(qt + ((size_t)ry * W + px) * C + j * 8) =
+        *reinterpret_cast<const uint4*>(base + (long long)((r0 + ry) * W + px) * 3 * C + j * 8);
+  }
+  const float* __restrict__ cg = a.ctx[gi] + (long long)b * C * Ch;
+  for (int i = tid; i < C * Ch; i += 256) ctx[i] = cg[i];
+  for (int i = tid; i < 9 * c3; i += 256) { const int ch = i / 9, t = i - ch * 9; w3[t * c3 + ch] = a.cw[gi][0][i]; }
+  for (int i = tid; i < 25 * c5; i += 256) { const int ch = i / 25, t = i - ch * 25; w5[t * c5 + ch] = a.cw[gi][1][i]; }
+  for (int i = tid; i < 49 * c7; i += 256) { const int ch = i / 49, t = i - ch * 49; w7[t * c7 + ch] = a.cw[gi][2][i]; }
+  for (int i = tid; i < C; i += 256) bs[i] = i < c3 ? a.cb[gi][0][i] : (i < c3 + c5 ? a.cb[gi][1][i - c3] : a.cb[gi][2][i - c3 - c5]);
+  __syncthreads();
+  __half* __restrict__ outp = a.out[gi] + ((long long)b * N + (long long)r0 * W) * C;
+  // heads 0-1: 3x3, heads 2-4: 5x5, heads 5-7: 7x7 (MSTr.py:958); the largest windows first (longest items)
+  mb_apply_group<7, T>(vt, qt, ctx, w7, bs, outp, rows, W, C, CP, Ch, c3 + c5, c7, tid);
+  mb_apply_group<5, T>(vt, qt, ctx, w5, bs, outp, rows, W, C, CP, Ch, c3, c5, tid);
+  mb_apply_group<3, T>(vt, qt, ctx, w3, bs, outp, rows, W, C, CP, Ch, 0, c3, tid);
+}
+
+// opt in to > 48 KB of dynamic shared memory, once per kernel (keyed by the function address)
+template <typename K>
+int set_smem(K kernel, size_t bytes, const char* what) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> granted;
+  if (bytes <= 48 * 1024) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& g = granted[reinterpret_cast<const void*>(kernel)];
+  if (bytes > g) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) { tcx_set_error("%s: cannot opt in to %zu bytes of shared memory: %s", what, bytes, cudaGetErrorString(e)); return -1; }
+    g = bytes;
+  }
+  return 0;
+}
+
+int tokens_per_warp(long long rows, int slots) {
+  // enough warps to fill the chip twice, at most 8 consecutive tokens per warp slot
+  long long tpw = rows / ((long long)148 * 8 * 2 * slots);
+  if (tpw < 1) tpw = 1;
+  if (tpw > 8) tpw = 8;
+  return (int)tpw;
+}
+
+}  // namespace
+
+#define DWLN_CASE(IN16, LPT, NV)                                                                         \
+  do {                                                                                                   \
+    TCX_TRY(set_smem(dwln_kernel<IN16, LPT, NV>, smem, "dwln"));                                         \
+    dwln_kernel<IN16, LPT, NV><<<grid, 256, smem, st>>>(a);                                              \
+  } while (0)
+
+int launch_dwln(DwLnArgs a, int groups, bool in16, cudaStream_t st) {
+  const int VEC = in16 ? 8 : 4;
+  TCX_REQUIRE(a.C % (16 * VEC) == 0, "dwln: C=%d must be a multiple of %d", a.C, 16 * VEC);
+  const int LPT = a.C % (32 * VEC) == 0 ? 32 : 16;
+  const int NV = a.C / (LPT * VEC);
+  const long long total = (long long)a.B * a.H * a.W;
+  if (total == 0) return 0;
+  const int slots = 32 / LPT;
+  a.tpw = tokens_per_warp(total, slots);
+  const long long per_block = (long long)8 * slots * a.tpw;
+  dim3 grid((unsigned)((total + per_block - 1) / per_block), groups);
+  const size_t smem = (size_t)12 * a.C * sizeof(float);
+  ProfScope prof("dwln", st);
+  bool ok = true;
+  if (in16) {
+    if (LPT == 32 && NV == 1) DWLN_CASE(true, 32, 1);
+    else if (LPT == 32 && NV == 2) DWLN_CASE(true, 32, 2);
+    else if (LPT == 32 && NV == 4) DWLN_CASE(true, 32, 4);
+    else if (LPT == 32 && NV == 5) DWLN_CASE(true, 32, 5);
+    else if (LPT == 32 && NV == 8) DWLN_CASE(true, 32, 8);
+    else if (LPT == 16 && NV == 1) DWLN_CASE(true, 16, 1);
+    else if (LPT == 16 && NV == 5) DWLN_CASE(true, 16, 5);
+    else ok = false;
+  } else {
+    if (LPT == 32 && NV == 1) DWLN_CASE(false, 32, 1);
+    else if (LPT == 32 && NV == 2) DWLN_CASE(false, 32, 2);
+    else if (LPT == 32 && NV == 4) DWLN_CASE(false, 32, 4);
+    else if (LPT == 16 && NV == 1) DWLN_CASE(false, 16, 1);
+    else if (LPT == 16 && NV == 5) DWLN_CASE(false, 16, 5);
+    else ok = false;
+  }
+  TCX_REQUIRE(ok, "dwln: unsupported width C=%d (in16=%d)", a.C, (int)in16);
+  return tcx_check_launch("dwln");
+}
+
+int launch_ln16(Ln16Args a, int groups, cudaStream_t st) {
+  TCX_REQUIRE(a.C % 64 == 0, "ln16: C=%d must be a multiple of 64", a.C);
+  if (a.M == 0) return 0;
+  const int LPT = a.C % 128 == 0 ? 32 : 16;
+  const int NV = a.C / (LPT * 4);
+  const int slots = 32 / LPT;
+  a.tpw = tokens_per_warp(a.M, slots);
+  const long long per_block = (long long)8 * slots * a.tpw;
+  dim3 grid((unsigned)((a.M + per_block - 1) / per_block), groups);
+  ProfScope prof("ln16", st);
+  if (LPT == 16 && NV == 1) ln16_kernel<16, 1><<<grid, 256, 0, st>>>(a);
+  else if (LPT == 16 && NV == 5) ln16_kernel<16, 5><<<grid, 256, 0, st>>>(a);
+  else if (LPT == 32 && NV == 1) ln16_kernel<32, 1><<<grid, 256, 0, st>>>(a);
+  else if (LPT == 32 && NV == 2) ln16_kernel<32, 2><<<grid, 256, 0, st>>>(a);
+  else if (LPT == 32 && NV == 4) ln16_kernel<32, 4><<<grid, 256, 0, st>>>(a);
+  else { tcx_set_error("ln16: unsupported width C=%d", a.C); return -1; }
+  return tcx_check_launch("ln16");
+}
+
+int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st) {
+  TCX_REQUIRE(a.heads == 8 && a.C % a.heads == 0, "mb_attn16: needs 8 heads (crpe window map {3:2,5:3,7:3})");
+  const int Ch = a.C / a.heads, N = a.H * a.W;
+  TCX_REQUIRE(Ch % 8 == 0 && Ch <= 64, "mb_attn16: head dim %d must be a multiple of 8 and <= 64", Ch);
+  {
+    const size_t smem = ((size_t)2 * N * Ch + 256 + 2 * Ch + (size_t)Ch * Ch) * sizeof(float);
+    TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: %d tokens x head dim %d does not fit in shared memory", N, Ch);
+    TCX_TRY(set_smem(mb_ctx16_kernel, smem, "mb_ctx16"));
+    dim3 grid(a.heads, a.B, groups);
+    mb_ctx16_kernel<<<grid, 256, smem, st>>>(a);
+    TCX_TRY(tcx_check_launch("mb_ctx16"));
+  }
+  {
+    int R = (int)(((long long)a.H * a.B * groups + 147) / 148);
+    if (R < 1) R = 1;
+    if (R > 8) R = 8;
+    if (R > a.H) R = a.H;
+    auto smem_of = [&](int r) {
+      return (size_t)(r + 6) * a.W * (a.C + 8) * 2 + (size_t)r * a.W * a.C * 2 +
+             ((size_t)a.C * Ch + (size_t)(9 * 2 + 25 * 3 + 49 * 3) * Ch + a.C) * sizeof(float);
+    };
+    while (R > 1 && smem_of(R) > 200 * 1024) R--;
+    const size_t smem = smem_of(R);
+    TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: row band does not fit in shared memory (W=%d C=%d)", a.W, a.C);
+    dim3 grid(cdiv(a.H, R), a.B, groups);
+    ProfScope prof("mb_apply16", st);
+    if (a.W % 4 == 0) {
+      TCX_TRY(set_smem(mb_apply16_kernel<4>, smem, "mb_apply16"));
+      mb_apply16_kernel<4><<<grid, 256, smem, st>>>(a, R);
+    } else if (a.W % 2 == 0) {
+      TCX_TRY(set_smem(mb_apply16_kernel<2>, smem, "mb_apply16"));
+      mb_apply16_kernel<2><<<grid, 256, smem, st>>>(a, R);
+    } else {
+      TCX_TRY(set_smem(mb_apply16_kernel<1>, smem, "mb_apply16"));
+      mb_apply16_kernel<1><<<grid, 256, smem, st>>>(a, R);
+    }
+    TCX_TRY(tcx_check_launch("mb_apply16"));
+  }
+  return 0;
+}

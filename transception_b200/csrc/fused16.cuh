@@ -1,0 +1,48 @@
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+struct DwLnGroup {
+  const void* x;      // [B,H,W,C] fp32 or fp16
+  const float* dww;   // [C,1,3,3]
+  const float* dwb;   // [C] or null
+  const float* lnw;   // [C]
+  const float* lnb;   // [C]
+  float* u;           // optional fp32 output: dw3x3(x) + b + x
+  __half* y;          // fp16 output: [GELU](LayerNorm(u))
+};
+struct DwLnArgs {
+  DwLnGroup g[TCX_MAX_GROUPS];
+  int B, H, W, C;
+  float eps;
+  int tpw;            // tokens per warp slot (set by the launcher)
+  int gelu;
+};
+int launch_dwln(DwLnArgs a, int groups, bool in16, cudaStream_t st);
+
+struct Ln16Group {
+  const float* x;     // [M,C] fp32
+  const float* w;
+  const float* b;
+  __half* y16;        // optional
+  float* y32;         // optional
+};
+struct Ln16Args {
+  Ln16Group g[TCX_MAX_GROUPS];
+  long long M;
+  int C;
+  float eps;
+  int tpw;
+};
+int launch_ln16(Ln16Args a, int groups, cudaStream_t st);
+
+struct Mb16Args {
+  int B, H, W, C, heads;
+  float scale;
+  const __half* qkv[TCX_MAX_GROUPS];    // [B*N][3C]
+  float* ctx[TCX_MAX_GROUPS];           // [B][heads][Ch][Ch]
+  __half* out[TCX_MAX_GROUPS];          // [B*N][C]
+  const float* cw[TCX_MAX_GROUPS][3];   // crpe filters 3x3 / 5x5 / 7x7
+  const float* cb[TCX_MAX_GROUPS][3];
+};
+int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st);

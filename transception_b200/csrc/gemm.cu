@@ -97,6 +97,8 @@ int launch_gemm(const GemmParams& p, cudaStream_t st) {
   TCX_REQUIRE(p.groups >= 1 && p.groups <= TCX_MAX_GROUPS && p.batch >= 1, "gemm: bad groups/batch");
   if (p.M == 0 || p.N == 0) return 0;
   if (gemm_tc_eligible(p)) return launch_gemm_tc(p, st);
+  TCX_REQUIRE(!p.ab16 && !p.out16, "gemm: fp16 operands/outputs need the tensor-core kernel (M=%d N=%d K=%d not eligible)",
+              p.M, p.N, p.K);
   return launch_gemm_ffma(p, st);
 }
 

@@ -12,6 +12,7 @@
 //    access of the kernel is a full-line TMA transaction; ragged M / N edges are clipped by the tensor maps.
 //  * grouped (up to 4 independent problems of one shape, e.g. the three Multi-Branch encoders) and strided-batched
 //    problems are folded into the tile list through rank-3 tensor maps.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -42,7 +43,7 @@ int tcx_make_operand_map(CUtensorMap* map, const void* base, int elem_bytes, lon
   if (strides[1] < strides[0]) strides[1] = strides[0];
   cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TCX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): K=%lld rows=%lld ld=%lld batch=%lld stride=%lld",
@@ -52,11 +53,14 @@ int tcx_make_operand_map(CUtensorMap* map, const void* base, int elem_bytes, lon
 
 namespace {
 
-constexpr int BM = 128, BK = 32;              // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGE_A = BM * BK * 4;          // 16 KB
-constexpr int SLAB = 32;                      // epilogue slab: 128 rows x 32 fp32 columns (16 KB, one SW128 box)
-constexpr int SLAB_BYTES = BM * SLAB * 4;
-constexpr int GT_THREADS = 192;
+constexpr int BM = 128;
+constexpr int KB_BYTES = 128;                 // one k-block = one 128-byte swizzle row: 32 tf32 or 64 fp16 elements
+constexpr int STAGE_A = BM * KB_BYTES;        // 16 KB
+constexpr int EPI_WARPS = 8;
+constexpr int GT_THREADS = 64 + EPI_WARPS * 32;
+constexpr int SUB_BYTES = 32 * 128;           // per-warp epilogue sub-slab: 32 rows x 128 bytes
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct TmaSet {
   CUtensorMap a[TCX_MAX_GROUPS];
@@ -65,18 +69,9 @@ struct TmaSet {
   CUtensorMap r[TCX_MAX_GROUPS];   // residual (valid only when the group has one)
 };
 
-template <int BN, int STAGES>
-struct Smem {
-  static constexpr int STAGE_B = BN * BK * 4;
-  static constexpr int OFF_B = STAGES * STAGE_A;
-  static constexpr int OFF_OUT = OFF_B + STAGES * STAGE_B;          // 2 output slabs
-  static constexpr int OFF_RES = OFF_OUT + 2 * SLAB_BYTES;          // 2 residual slabs
-  static constexpr int OFF_COL = OFF_RES + 2 * SLAB_BYTES;          // [2 tiles][scale BN | shift BN] fp32
-  static constexpr int OFF_BAR = OFF_COL + 2 * 2 * BN * 4;
-  static constexpr int NBAR = 2 * STAGES + 6;
-  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16;
-  static constexpr int DYN = TOTAL + 1024;                           // slack for 1024-byte alignment
-  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512
+// dynamic shared memory plan (host-computed): [A stages][B stages][out 8x2x4K][res 8x2x4K]?[col 8x1K][barriers]
+struct SmemPlan {
+  int off_b, off_out, off_res, off_col, off_bar, stages, total;
 };
 
 struct TileCoord {
@@ -104,78 +99,120 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-// one 128 x 32 epilogue slab row: y = act(acc * scale + shift) (+ residual) -> swizzled smem.  The activation and the
-// optional terms are template parameters so the 32-element body is branch-free straight-line code.
-template <int ACT, bool SCALE, bool RES>
-__device__ __forceinline__ void slab_row(const uint32_t (&v)[32], const float* __restrict__ scv,
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply(float y) {
+  if (ACT == ACT_GELU) return gelu_erf(y);
+  if (ACT == ACT_HARDSWISH) return hardswish(y);
+  if (ACT == ACT_SIGMOID) return sigmoidf_(y);
+  if (ACT == ACT_SILU_SWISH) return silu_swish(y);
+  return y;
+}
+
+// one epilogue row of a slab: y = act(acc * scale + shift) (+ residual) -> 128 swizzled bytes of shared memory.
+// fp32 output: 32 columns; fp16 output: 64 columns.  All options are template parameters (branch-free body).
+template <int ACT, bool SCALE, bool RES, bool OUT16, int NC>
+__device__ __forceinline__ void slab_row(const uint32_t (&v)[NC], const float* __restrict__ scv,
                                          const float* __restrict__ shv, const uint8_t* __restrict__ rrow,
                                          uint8_t* __restrict__ orow, int sw) {
+  static_assert(NC == (OUT16 ? 64 : 32), "slab width");
 #pragma unroll
-  for (int c = 0; c < 8; c++) {
-    const float4 sh = *reinterpret_cast<const float4*>(shv + c * 4);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (SCALE) sc = *reinterpret_cast<const float4*>(scv + c * 4);
-    float x[4] = {__uint_as_float(v[c * 4 + 0]), __uint_as_float(v[c * 4 + 1]), __uint_as_float(v[c * 4 + 2]),
-                  __uint_as_float(v[c * 4 + 3])};
-    const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
+  for (int c = 0; c < 8; c++) {          // 16-byte output chunks
+    constexpr int PER = OUT16 ? 8 : 4;
+    float x[PER];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      float y = SCALE ? fmaf(x[j], scs[j], shs[j]) : x[j] + shs[j];
-      if (ACT == ACT_GELU) y = gelu_erf(y);
-      else if (ACT == ACT_HARDSWISH) y = hardswish(y);
-      else if (ACT == ACT_SIGMOID) y = sigmoidf_(y);
-      else if (ACT == ACT_SILU_SWISH) y = silu_swish(y);
-      x[j] = y;
+    for (int q = 0; q < PER / 4; q++) {
+      const float4 sh = *reinterpret_cast<const float4*>(shv + c * PER + q * 4);
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (SCALE) sc = *reinterpret_cast<const float4*>(scv + c * PER + q * 4);
+      const float scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float a = __uint_as_float(v[c * PER + q * 4 + j]);
+        x[q * 4 + j] = act_apply<ACT>(SCALE ? fmaf(a, scs[j], shs[j]) : a + shs[j]);
+      }
     }
     const int phys = (c ^ sw) << 4;
-    if (RES) {
-      const float4 rv = *reinterpret_cast<const float4*>(rrow + phys);
-      x[0] += rv.x; x[1] += rv.y; x[2] += rv.z; x[3] += rv.w;
+    if (OUT16) {
+      *reinterpret_cast<uint4*>(orow + phys) =
+          make_uint4(pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[PER - 4], x[PER - 3]), pack_h2(x[PER - 2], x[PER - 1]));
+    } else {
+      if (RES) {
+        const float4 rv = *reinterpret_cast<const float4*>(rrow + phys);
+        x[0] += rv.x; x[1] += rv.y; x[2] += rv.z; x[3] += rv.w;
+      }
+      *reinterpret_cast<float4*>(orow + phys) = make_float4(x[0], x[1], x[2], x[3]);
     }
-    *reinterpret_cast<float4*>(orow + phys) = make_float4(x[0], x[1], x[2], x[3]);
   }
 }
-template <int ACT>
-__device__ __forceinline__ void slab_act(bool scale, bool res, const uint32_t (&v)[32], const float* scv, const float* shv,
+template <int ACT, bool OUT16, int NC>
+__device__ __forceinline__ void slab_act(bool scale, bool res, const uint32_t (&v)[NC], const float* scv, const float* shv,
                                          const uint8_t* rrow, uint8_t* orow, int sw) {
   if (scale) {
-    if (res) slab_row<ACT, true, true>(v, scv, shv, rrow, orow, sw);
-    else slab_row<ACT, true, false>(v, scv, shv, rrow, orow, sw);
+    if (res) slab_row<ACT, true, true, OUT16, NC>(v, scv, shv, rrow, orow, sw);
+    else slab_row<ACT, true, false, OUT16, NC>(v, scv, shv, rrow, orow, sw);
   } else {
-    if (res) slab_row<ACT, false, true>(v, scv, shv, rrow, orow, sw);
-    else slab_row<ACT, false, false>(v, scv, shv, rrow, orow, sw);
+    if (res) slab_row<ACT, false, true, OUT16, NC>(v, scv, shv, rrow, orow, sw);
+    else slab_row<ACT, false, false, OUT16, NC>(v, scv, shv, rrow, orow, sw);
   }
 }
-__device__ __forceinline__ void slab_dispatch(int act, bool scale, bool res, const uint32_t (&v)[32], const float* scv,
-                                           const float* shv, const uint8_t* rrow, uint8_t* orow, int sw) {
-  switch (act) {
-    case ACT_GELU: slab_act<ACT_GELU>(scale, res, v, scv, shv, rrow, orow, sw); break;
-    case ACT_HARDSWISH: slab_act<ACT_HARDSWISH>(scale, res, v, scv, shv, rrow, orow, sw); break;
-    case ACT_SIGMOID: slab_act<ACT_SIGMOID>(scale, res, v, scv, shv, rrow, orow, sw); break;
-    case ACT_SILU_SWISH: slab_act<ACT_SILU_SWISH>(scale, res, v, scv, shv, rrow, orow, sw); break;
-    default: slab_act<ACT_NONE>(scale, res, v, scv, shv, rrow, orow, sw); break;
+// FULL: every activation / BatchNorm-fold / residual combination (fp32-operand kernels).  !FULL: bias (+ residual for
+// fp32 output) only — the fp16-operand kernels are used for plain nn.Linear sites.
+template <bool FULL, bool OUT16, int NC>
+__device__ __forceinline__ void slab_dispatch(int act, bool scale, bool res, const uint32_t (&v)[NC], const float* scv,
+                                              const float* shv, const uint8_t* rrow, uint8_t* orow, int sw) {
+  if constexpr (OUT16) {
+    slab_row<ACT_NONE, false, false, true, NC>(v, scv, shv, rrow, orow, sw);
+  } else if constexpr (!FULL) {
+    if (res) slab_row<ACT_NONE, false, true, false, NC>(v, scv, shv, rrow, orow, sw);
+    else slab_row<ACT_NONE, false, false, false, NC>(v, scv, shv, rrow, orow, sw);
+  } else {
+    switch (act) {
+      case ACT_GELU: slab_act<ACT_GELU, false, NC>(scale, res, v, scv, shv, rrow, orow, sw); break;
+      case ACT_HARDSWISH: slab_act<ACT_HARDSWISH, false, NC>(scale, res, v, scv, shv, rrow, orow, sw); break;
+      case ACT_SIGMOID: slab_act<ACT_SIGMOID, false, NC>(scale, res, v, scv, shv, rrow, orow, sw); break;
+      case ACT_SILU_SWISH: slab_act<ACT_SILU_SWISH, false, NC>(scale, res, v, scv, shv, rrow, orow, sw); break;
+      default: slab_act<ACT_NONE, false, NC>(scale, res, v, scv, shv, rrow, orow, sw); break;
+    }
   }
 }
 
-template <int BN, int STAGES>
+template <int O, int N>
+__device__ __forceinline__ void ld32_at(uint32_t taddr, uint32_t (&s)[N]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(s[O + 0]), "=r"(s[O + 1]), "=r"(s[O + 2]), "=r"(s[O + 3]), "=r"(s[O + 4]), "=r"(s[O + 5]), "=r"(s[O + 6]), "=r"(s[O + 7]), "=r"(s[O + 8]), "=r"(s[O + 9]), "=r"(s[O + 10]), "=r"(s[O + 11]), "=r"(s[O + 12]), "=r"(s[O + 13]), "=r"(s[O + 14]), "=r"(s[O + 15]), "=r"(s[O + 16]), "=r"(s[O + 17]), "=r"(s[O + 18]), "=r"(s[O + 19]), "=r"(s[O + 20]), "=r"(s[O + 21]), "=r"(s[O + 22]), "=r"(s[O + 23]), "=r"(s[O + 24]), "=r"(s[O + 25]), "=r"(s[O + 26]), "=r"(s[O + 27]), "=r"(s[O + 28]), "=r"(s[O + 29]), "=r"(s[O + 30]), "=r"(s[O + 31])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <int BN, bool AB16, bool OUT16>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmaSet maps,
-                                                                const __grid_constant__ GemmParams p) {
-  using L = Smem<BN, STAGES>;
+                                                                const __grid_constant__ GemmParams p,
+                                                                const __grid_constant__ SmemPlan sp) {
+  constexpr int STAGE_B = BN * KB_BYTES;
+  constexpr int KBE = AB16 ? 64 : 32;                 // elements per k-block
+  constexpr int SLABC = OUT16 ? 64 : 32;              // output columns per 128-byte slab row
+  constexpr int NSLAB = BN / SLABC;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;    // [2]
-  uint64_t* acc_empty = acc_full + 2;     // [2]
-  uint64_t* res_full = acc_empty + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  const int STAGES = sp.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + sp.off_bar);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* acc_full = empty + MAX_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint64_t* res_full = acc_empty + 2;        // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.M + BM - 1) / BM, nt = (p.N + BN - 1) / BN;
   const int ntiles = mt * nt * p.groups * p.batch;
-  const int nkb = (p.K + BK - 1) / BK;
+  const int nkb = (p.K + KBE - 1) / KBE;
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < p.groups; g++) {
@@ -187,13 +224,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) {
       tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], 128);
-      tc::mbar_init(&res_full[a], 1);
+      tc::mbar_init(&acc_empty[a], EPI_WARPS * 32);
     }
+    for (int i = 0; i < 2 * EPI_WARPS; i++) tc::mbar_init(&res_full[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tc::tmem_alloc(tmem_slot, TMEM_COLS);
     tc::tmem_relinquish();
   }
   tc::fence_before_sync();
@@ -204,142 +241,154 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == 0) {
     // ================= TMA producer: A / W k-blocks of every tile of this CTA, back to back =================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(tile, mt, nt, p.batch, BN);
         const int za = p.strideA ? t.bi : 0, zw = p.strideW ? t.bi : 0;
-        for (int kb = 0; kb < nkb; kb++, it++) {
-          const int s = it % STAGES;
-          tc::mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(&full[s], STAGE_A + L::STAGE_B);
-          tc::tma_load_3d(smem + s * STAGE_A, &maps.a[t.gi], kb * BK, t.m0, za, &full[s]);
-          tc::tma_load_3d(smem + L::OFF_B + s * L::STAGE_B, &maps.w[t.gi], kb * BK, t.n0, zw, &full[s]);
+        for (int kb = 0; kb < nkb; kb++) {
+          tc::mbar_wait(&empty[s], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&full[s], STAGE_A + STAGE_B);
+          tc::tma_load_3d(smem + s * STAGE_A, &maps.a[t.gi], kb * KBE, t.m0, za, &full[s]);
+          tc::tma_load_3d(smem + sp.off_b + s * STAGE_B, &maps.w[t.gi], kb * KBE, t.n0, zw, &full[s]);
+          if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc(2, BM, BN);
-      uint32_t it = 0, ti = 0;
+      constexpr uint32_t idesc = tc::umma_idesc(AB16 ? 0 : 2, BM, BN);
+      uint32_t s = 0, ph = 0, ti = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
         const uint32_t a = ti & 1;
         tc::mbar_wait(&acc_empty[a], ((ti >> 1) & 1) ^ 1);     // epilogue drained this accumulator
         tc::fence_after_sync();
         const uint32_t acc = tmem_base + a * BN;
-        for (int kb = 0; kb < nkb; kb++, it++) {
-          const int s = it % STAGES;
-          tc::mbar_wait(&full[s], (it / STAGES) & 1);
+        for (int kb = 0; kb < nkb; kb++) {
+          tc::mbar_wait(&full[s], ph);
           tc::fence_after_sync();
           const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(smem + s * STAGE_A));
-          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(smem + L::OFF_B + s * L::STAGE_B));
+          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(smem + sp.off_b + s * STAGE_B));
 #pragma unroll
-          for (int k = 0; k < BK / 8; k++)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address inside the atom
-            tc::umma_tf32(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; k++) {     // one MMA consumes 32 bytes of K: advance the start address inside the atom
+            if (AB16) tc::umma_f16(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else tc::umma_tf32(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           tc::umma_commit(&empty[s]);        // frees the smem stage when these MMAs retire
+          if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
         }
         tc::umma_commit(&acc_full[a]);
       }
     }
   } else {
-    // ================= epilogue warps 2..5: TMEM lanes [32*(warp%4), +32) =================
+    // ================= epilogue warps 2..9: independent pipelines, no CTA-wide barriers =================
+    // warp -> TMEM lane quarter (hardware rule: warp % 4) and column half; each warp owns 32 rows x its slabs,
+    // stages them in its own swizzled 4 KB buffers and issues its own TMA stores / residual prefetches.
+    const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;                 // row inside the tile == TMEM lane
-    const int et = threadIdx.x - 64;                   // 0..127
-    const bool leader = (et == 0);
-    const int sw = r & 7;
-    uint8_t* out_slab = smem + L::OFF_OUT;
-    uint8_t* res_slab = smem + L::OFF_RES;
-    float* colc = reinterpret_cast<float*>(smem + L::OFF_COL);
-    constexpr int NSLAB = BN / SLAB;
+    const int half = ew >> 2;
+    const int sw = lane & 7;
+    uint8_t* out_w = smem + sp.off_out + ew * 2 * SUB_BYTES;
+    uint8_t* res_w = smem + sp.off_res + ew * 2 * SUB_BYTES;
+    float* col_w = reinterpret_cast<float*>(smem + sp.off_col + ew * 1024);   // [2][scale 64 | shift 64]
+    uint64_t* rbar = res_full + ew * 2;
 
-    // residual prefetch cursor (leader only): slabs are numbered consecutively over this CTA's tiles
-    int pf_tile = blockIdx.x, pf_slab = 0;
+    int pf_tile = blockIdx.x, pf_slab = half;
     uint32_t pf_count = 0;
-    auto prefetch_res = [&]() {
-      while (pf_tile < ntiles) {
+    auto prefetch_res = [&]() {      // lane 0: next live residual sub-slab of this warp
+      while (pf_tile < ntiles && half < NSLAB) {
         const TileCoord t = tile_coord(pf_tile, mt, nt, p.batch, BN);
-        const bool live = p.g[t.gi].epi.residual != nullptr && t.n0 + pf_slab * SLAB < p.N;
+        const bool live = p.g[t.gi].epi.residual != nullptr && t.n0 + pf_slab * SLABC < p.N;
         if (live) {
           const uint32_t b = pf_count & 1;
-          tc::mbar_arrive_expect_tx(&res_full[b], SLAB_BYTES);
-          tc::tma_load_3d(res_slab + b * SLAB_BYTES, &maps.r[t.gi], t.n0 + pf_slab * SLAB, t.m0,
-                          p.g[t.gi].epi.strideR ? t.bi : 0, &res_full[b]);
+          tc::mbar_arrive_expect_tx(&rbar[b], SUB_BYTES);
+          tc::tma_load_3d(res_w + b * SUB_BYTES, &maps.r[t.gi], t.n0 + pf_slab * SLABC, t.m0 + quarter * 32,
+                          p.g[t.gi].epi.strideR ? t.bi : 0, &rbar[b]);
           pf_count++;
         }
-        if (++pf_slab == NSLAB) { pf_slab = 0; pf_tile += gridDim.x; }
+        pf_slab += 2;
+        if (pf_slab >= NSLAB) { pf_slab = half; pf_tile += gridDim.x; }
         if (live) return;
       }
     };
-    if (leader) prefetch_res();
+    if (lane == 0 && !OUT16) prefetch_res();
 
-    uint32_t ti = 0, slab_count = 0, res_count = 0;
+    uint32_t ti = 0, out_count = 0, res_count = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
       const TileCoord t = tile_coord(tile, mt, nt, p.batch, BN);
       const GemmEpi& e = p.g[t.gi].epi;
-      const bool has_res = e.residual != nullptr;
+      const bool has_res = !OUT16 && e.residual != nullptr;
       const bool has_scale = e.bn.w != nullptr;
       const int act = e.act;
       const uint32_t a = ti & 1;
-      // per-tile column constants: y = act(acc * scale + shift) with bias and BatchNorm folded
-      float* cs = colc + a * 2 * BN;
-      for (int j = et; j < BN; j += 128) {
-        const int col = t.n0 + j;
-        float sc = 1.f, sh = 0.f;
-        if (col < p.N) {
-          const float bias = e.bias ? __ldg(e.bias + col) : 0.f;
-          if (has_scale) {
-            float bs, bt;
-            bn_fold(e.bn, col, bs, bt);
-            sc = bs;
-            sh = fmaf(bias, bs, bt);
-          } else {
-            sh = bias;
-          }
-        }
-        cs[j] = sc;
-        cs[BN + j] = sh;
-      }
       tc::mbar_wait(&acc_full[a], (ti >> 1) & 1);
       tc::fence_after_sync();
       const uint32_t tacc = tmem_base + a * BN + ((uint32_t)(quarter * 32) << 16);
+      bool arrived = false;
 #pragma unroll 1
-      for (int s = 0; s < NSLAB; s++) {
-        if (t.n0 + s * SLAB >= p.N) break;                      // uniform: slab entirely past N
-        uint32_t v[32];
-        tc::tmem_ld32(tacc + s * SLAB, v);
-        const uint32_t ob = slab_count & 1;
-        if (leader) bulk_wait_read<1>();                        // the store that last read out_slab[ob] is done with smem
-        if (has_res && leader) prefetch_res();                  // next live residual slab (this one is already in flight)
-        epi_bar(1);                                             // out_slab[ob] free; column constants visible
+      for (int s = half; s < NSLAB; s += 2) {
+        const int col0 = t.n0 + s * SLABC;
+        if (col0 >= p.N) break;
+        const uint32_t ob = out_count & 1;
+        uint32_t v[SLABC];
+        ld32_at<0>(tacc + s * SLABC, v);
+        if constexpr (OUT16) ld32_at<SLABC - 32>(tacc + s * SLABC + 32, v);
+        // per-slab column constants y = act(acc * scale + shift): bias and BatchNorm folded, one column per lane
+        float* cs = col_w + ob * 128;
+#pragma unroll
+        for (int j = lane; j < SLABC; j += 32) {
+          const int col = col0 + j;
+          float sc = 1.f, sh = 0.f;
+          if (col < p.N) {
+            const float bias = e.bias ? __ldg(e.bias + col) : 0.f;
+            if (has_scale) {
+              float bs, bt;
+              bn_fold(e.bn, col, bs, bt);
+              sc = bs;
+              sh = fmaf(bias, bs, bt);
+            } else {
+              sh = bias;
+            }
+          }
+          cs[j] = sc;
+          cs[64 + j] = sh;
+        }
+        if (lane == 0) {
+          bulk_wait_read<1>();                                   // the store that last read out buffer `ob` is done with it
+          if (has_res) prefetch_res();                           // next live residual (the current one is already in flight)
+        }
+        __syncwarp();
         tc::tmem_ld_wait();
-        if (s == NSLAB - 1 || t.n0 + (s + 1) * SLAB >= p.N) {   // last TMEM read of this tile: release the accumulator
+        if (s + 2 >= NSLAB || col0 + 2 * SLABC >= p.N) {         // last TMEM read of this tile by this warp
           tc::fence_before_sync();
           tc::mbar_arrive(&acc_empty[a]);
+          arrived = true;
         }
-        const float* scv = cs + s * SLAB;
-        const float* shv = cs + BN + s * SLAB;
-        uint8_t* orow = out_slab + ob * SLAB_BYTES + r * 128;
-        const uint8_t* rrow = res_slab + (res_count & 1) * SLAB_BYTES + r * 128;
-        if (has_res) tc::mbar_wait(&res_full[res_count & 1], (res_count >> 1) & 1);
-        slab_dispatch(act, has_scale, has_res, v, scv, shv, rrow, orow, sw);
+        uint8_t* orow = out_w + ob * SUB_BYTES + lane * 128;
+        const uint8_t* rrow = res_w + (res_count & 1) * SUB_BYTES + lane * 128;
+        if (has_res) tc::mbar_wait(&rbar[res_count & 1], (res_count >> 1) & 1);
+        slab_dispatch<!AB16, OUT16, SLABC>(act, has_scale, has_res, v, cs, cs + 64, rrow, orow, sw);
         if (has_res) res_count++;
         tc::fence_proxy_async();
-        epi_bar(2);                                             // slab complete (and residual slab consumed)
-        if (leader) {
-          tma_store_3d(&maps.c[t.gi], out_slab + ob * SLAB_BYTES, t.n0 + s * SLAB, t.m0, p.strideC ? t.bi : 0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps.c[t.gi], out_w + ob * SUB_BYTES, col0, t.m0 + quarter * 32, p.strideC ? t.bi : 0);
           bulk_commit();
         }
-        slab_count++;
+        out_count++;
+      }
+      if (!arrived) {
+        tc::fence_before_sync();
+        tc::mbar_arrive(&acc_empty[a]);
       }
     }
-    if (leader) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
   }
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
+    tc::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -354,21 +403,44 @@ int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, int STAGES>
-int launch_cfg(const TmaSet& maps, const GemmParams& p, cudaStream_t st) {
-  using L = Smem<BN, STAGES>;
-  static_assert(L::DYN <= 227 * 1024, "smem budget");
+SmemPlan make_plan(int bn, bool has_res) {
+  SmemPlan sp{};
+  const int stage = STAGE_A + bn * KB_BYTES;
+  const int fixed = EPI_WARPS * 2 * SUB_BYTES * (has_res ? 2 : 1) + EPI_WARPS * 1024 + 512;
+  int stages = (SMEM_BUDGET - 1024 - fixed) / stage;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  sp.stages = stages;
+  sp.off_b = stages * STAGE_A;
+  sp.off_out = sp.off_b + stages * bn * KB_BYTES;
+  sp.off_res = sp.off_out + EPI_WARPS * 2 * SUB_BYTES;
+  sp.off_col = sp.off_res + (has_res ? EPI_WARPS * 2 * SUB_BYTES : 0);
+  sp.off_bar = sp.off_col + EPI_WARPS * 1024;
+  sp.total = sp.off_bar + 512 + 1024;   // + slack for the 1024-byte alignment of the dynamic base
+  return sp;
+}
+
+template <int BN, bool AB16, bool OUT16>
+int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AB16, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BUDGET);
     TCX_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     done = true;
   }
+  TCX_REQUIRE(sp.stages >= 2 && sp.total <= SMEM_BUDGET, "gemm_tc: smem plan does not fit (BN=%d stages=%d)", BN, sp.stages);
   const int ntiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.groups * p.batch;
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
   ProfScope prof("gemm_tc", st);
-  gemm_tc_kernel<BN, STAGES><<<grid, GT_THREADS, L::DYN, st>>>(maps, p);
+  gemm_tc_kernel<BN, AB16, OUT16><<<grid, GT_THREADS, sp.total, st>>>(maps, p, sp);
   return tcx_check_launch("gemm_tc");
+}
+
+template <bool AB16, bool OUT16>
+int launch_bn(int bn, const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cudaStream_t st) {
+  if (bn == 256) return launch_cfg<256, AB16, OUT16>(maps, p, sp, st);
+  if (bn == 128) return launch_cfg<128, AB16, OUT16>(maps, p, sp, st);
+  return launch_cfg<64, AB16, OUT16>(maps, p, sp, st);
 }
 
 }  // namespace
@@ -376,36 +448,46 @@ int launch_cfg(const TmaSet& maps, const GemmParams& p, cudaStream_t st) {
 bool gemm_tc_eligible(const GemmParams& p) {
   if (!tcx_flag_gemm_tc()) return false;
   if (p.N < 16 || p.K < 16 || p.M < 32) return false;
-  if ((p.K | p.lda | p.ldw | p.ldc) & 3) return false;
-  if ((p.strideA | p.strideW | p.strideC) & 3) return false;
+  const int am = p.ab16 ? 7 : 3, cm = p.out16 ? 7 : 3;     // 16-byte row pitches
+  if ((p.K | p.lda | p.ldw) & am) return false;
+  if (p.ldc & cm) return false;
+  if ((p.strideA | p.strideW) & am) return false;
+  if (p.strideC & cm) return false;
   for (int i = 0; i < p.groups; i++) {
     if (((uintptr_t)p.g[i].A | (uintptr_t)p.g[i].W | (uintptr_t)p.g[i].C) & 15) return false;
     const GemmEpi& e = p.g[i].epi;
     if (e.residual && ((((uintptr_t)e.residual) & 15) || (e.ldr & 3) || (e.strideR & 3))) return false;
+    if (p.out16 && (e.residual || e.bn.w || e.act != ACT_NONE)) return false;
+    if (p.ab16 && (e.bn.w || e.act != ACT_NONE)) return false;
   }
   return tcx_get_encode_tiled() != nullptr;
 }
 
 int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   const long long mtiles = (long long)cdiv(p.M, BM) * p.groups * p.batch;
+  bool has_res = false;
+  for (int i = 0; i < p.groups; i++) has_res |= p.g[i].epi.residual != nullptr;
   int bn = 64;
-  if (p.N % 256 == 0 && mtiles * (p.N / 256) >= 2 * sm_count()) bn = 256;
+  if (!has_res && p.N % 256 == 0 && mtiles * (p.N / 256) >= 2 * sm_count()) bn = 256;
   else if (p.N % 128 == 0 && mtiles * (p.N / 128) >= 2 * sm_count()) bn = 128;
+  const int ae = p.ab16 ? 2 : 4, ce = p.out16 ? 2 : 4;
+  const int kbe = KB_BYTES / ae, slabc = 128 / ce;
   TmaSet maps;
   for (int i = 0; i < p.groups; i++) {
     const GemmEpi& e = p.g[i].epi;
-    TCX_TRY(tcx_make_operand_map(&maps.a[i], p.g[i].A, 4, p.K, p.M, p.lda, p.batch, p.strideA, BK, BM));
-    TCX_TRY(tcx_make_operand_map(&maps.w[i], p.g[i].W, 4, p.K, p.N, p.ldw, p.batch, p.strideW, BK, bn));
-    TCX_TRY(tcx_make_operand_map(&maps.c[i], p.g[i].C, 4, p.N, p.M, p.ldc, p.batch, p.strideC, SLAB, BM));
+    TCX_TRY(tcx_make_operand_map(&maps.a[i], p.g[i].A, ae, p.K, p.M, p.lda, p.batch, p.strideA, kbe, BM));
+    TCX_TRY(tcx_make_operand_map(&maps.w[i], p.g[i].W, ae, p.K, p.N, p.ldw, p.batch, p.strideW, kbe, bn));
+    TCX_TRY(tcx_make_operand_map(&maps.c[i], p.g[i].C, ce, p.N, p.M, p.ldc, p.batch, p.strideC, slabc, 32));
     if (e.residual)
-      TCX_TRY(tcx_make_operand_map(&maps.r[i], e.residual, 4, p.N, p.M, e.ldr, p.batch, e.strideR, SLAB, BM));
+      TCX_TRY(tcx_make_operand_map(&maps.r[i], e.residual, 4, p.N, p.M, e.ldr, p.batch, e.strideR, 32, 32));
     else
       maps.r[i] = maps.c[i];
   }
   for (int i = p.groups; i < TCX_MAX_GROUPS; i++) {
     maps.a[i] = maps.a[0]; maps.w[i] = maps.w[0]; maps.c[i] = maps.c[0]; maps.r[i] = maps.r[0];
   }
-  if (bn == 256) return launch_cfg<256, 3>(maps, p, st);
-  if (bn == 128) return launch_cfg<128, 4>(maps, p, st);
-  return launch_cfg<64, 6>(maps, p, st);
+  const SmemPlan sp = make_plan(bn, has_res);
+  if (p.ab16) return p.out16 ? launch_bn<true, true>(bn, maps, p, sp, st) : launch_bn<true, false>(bn, maps, p, sp, st);
+  TCX_REQUIRE(!p.out16, "gemm_tc: fp16 output needs fp16 operands");
+  return launch_bn<false, false>(bn, maps, p, sp, st);
 }

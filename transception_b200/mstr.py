@@ -132,11 +132,8 @@ class EfficientTransformerBlock(nn.Module):
         self.mlp = MixFFN_skip(in_dim, int(in_dim * 4))
 
     def forward(self, x, H, W):
-        x = x.contiguous()
-        n1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        tx = ops.eff_attn(n1, *self.attn.args(), residual=x, reinterpret=False)
-        n2 = ops.layernorm(tx, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return ops.mixffn_skip(n2, H, W, *self.mlp.args(), residual=tx)
+        return ops.eff_block(x, H, W, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.attn.args(),
+                             self.norm2.weight, self.norm2.bias, self.mlp.args())
 
 
 # --------------------------------------------------------------------------------------
@@ -607,6 +604,13 @@ class M_EfficientSelfAtten(nn.Module):
         return (self.scale, self.q.weight, self.q.bias, self.kv.weight, self.kv.bias,
                 self.proj.weight, self.proj.bias) + self.scale_reduce.args()
 
+    def slots(self):
+        """The 14 pointer slots of tcx_bridge_sr_attn_fwd."""
+        sr = self.scale_reduce
+        return [self.q.weight, self.q.bias, self.kv.weight, self.kv.bias, self.proj.weight, self.proj.bias,
+                sr.sr0.weight.reshape(64, -1), sr.sr0.bias, sr.sr1.weight.reshape(128, -1), sr.sr1.bias,
+                sr.sr2.weight.reshape(320, -1), sr.sr2.bias, sr.norm.weight, sr.norm.bias]
+
     def forward(self, x, residual=None):
         return ops.bridge_sr_attn(x.contiguous(), *self.args(), residual=residual)
 
@@ -627,6 +631,11 @@ class M_EfficientChannelAtten(nn.Module):
         self.proj = nn.Linear(dim, dim)
         if reduction_ratio is not None:
             self.scale_reduce = Scale_reduce(dim, reduction_ratio)
+
+    def slots(self):
+        """The 8 pointer slots of tcx_eff_attn_fwd."""
+        return [self.k.weight, self.k.bias, self.q.weight, self.q.bias, self.v.weight, self.v.bias,
+                self.proj.weight, self.proj.bias]
 
     def forward(self, x, residual=None):
         return ops.eff_attn(x.contiguous(), self.k.weight, self.k.bias, self.q.weight, self.q.bias,
@@ -649,12 +658,10 @@ class BridgLayer_4(nn.Module):
         if isinstance(inputs, (list, tuple)):
             # a C_k-channel NHWC pixel is C_k/64 consecutive 64-wide tokens
             inputs = ops.bridge_regroup([_nhwc(c) for c in inputs])
-        x = inputs.contiguous()
-        B, N, C = x.shape
-        n1 = ops.layernorm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        tx1 = self.attn(n1, residual=x)
-        tx = ops.layernorm(tx1, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return ops.bridge_mixffn(tx, tx1, [m.args() for m in (self.mixffn1, self.mixffn2, self.mixffn3, self.mixffn4)])
+        ch = isinstance(self.attn, M_EfficientChannelAtten)
+        return ops.bridge_layer(inputs, self.norm1.weight, self.norm1.bias, self.norm1.eps, ch, self.attn.slots(),
+                                self.attn.scale, self.norm2.weight, self.norm2.bias,
+                                [m.args() for m in (self.mixffn1, self.mixffn2, self.mixffn3, self.mixffn4)])
 
 
 class BridgeBlock_4(nn.Module):

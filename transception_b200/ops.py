@@ -31,6 +31,14 @@ _PROTOS = {
     "tcx_profile_read": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i)]),
     "tcx_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "tcx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_f32_to_f16": (_i, [_vp, _vp, _ll, _vp]),
+    "tcx_linear_f16_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_prepare_weight_f16": (_i, [_vp, _vp, _ll, _vp]),
+    "tcx_forget_weight": (_i, [_vp]),
+    "tcx_eff_block_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_eff_block_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_bridge_layer_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_bridge_layer_fwd": (_i, [_vp, _pp, _i, _f, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_linear_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _i, _i, _i, _vp]),
     "tcx_patch_embed_ln_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
     "tcx_dwconv_tokens_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -121,6 +129,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _ptr16(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float16 or not t.is_contiguous() or not t.is_cuda:
+        raise RuntimeError("transception_b200: expected a contiguous fp16 CUDA tensor, got %s %s on %s"
+                           % (tuple(t.shape), t.dtype, t.device))
+    return t.data_ptr()
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -130,8 +147,49 @@ def _ptr(t):
     return t.data_ptr()
 
 
-def _table(tensors):
+# ---- prepared (fp16) GEMM weights ----------------------------------------------------------------
+# id(tensor) -> (weakref, version, data_ptr, fp16 copy).  A weight is (re)prepared when it is first seen, when its
+# version counter moved (in-place update, load_state_dict) or when its storage moved (.cuda(), .to()).
+import weakref
+
+_prepared = {}
+USE_F16 = True
+
+
+def prepare_weight(w):
+    """Register an fp16 copy of a GEMM weight matrix with the library (include/transception_sm100.h)."""
+    if not USE_F16 or w is None or not w.is_cuda:
+        return
+    key = id(w)
+    ent = _prepared.get(key)
+    if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
+        return
+    lib = load_library()
+    if ent is not None and ent[2] != w.data_ptr():
+        lib.tcx_forget_weight(ent[2])
+    w16 = torch.empty(w.numel(), dtype=torch.float16, device=w.device)
+    src = w.detach()
+    if not src.is_contiguous():
+        raise RuntimeError("transception_b200: weight matrices must be contiguous")
+    rc = lib.tcx_prepare_weight_f16(src.data_ptr(), w16.data_ptr(), w.numel(), _stream())
+    if rc != 0:
+        raise RuntimeError("libtransception_sm100: " + lib.tcx_last_error().decode())
+    ptr = w.data_ptr()
+
+    def _gone(_ref, key=key, ptr=ptr):
+        e = _prepared.get(key)
+        if e is not None and e[2] == ptr and e[0]() is None:
+            _prepared.pop(key, None)
+            if _lib is not None:
+                _lib.tcx_forget_weight(ptr)
+    _prepared[key] = (weakref.ref(w, _gone), w._version, ptr, w16)
+
+
+def _table(tensors, mats=()):
+    """Host array of device pointers; slots listed in ``mats`` are GEMM weight matrices (prepared on first use)."""
     arr = (ctypes.c_void_p * len(tensors))()
+    for i in mats:
+        prepare_weight(tensors[i])
     for i, t in enumerate(tensors):
         arr[i] = _ptr(t.detach() if t is not None else None)
     return arr
@@ -165,6 +223,29 @@ def linear(x, w, b=None, act=0, residual=None):
     M = x.numel() // K
     y = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=x.dtype)
     _chk(lib.tcx_linear_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(residual), _ptr(y), M, N, K, act, _stream()))
+    return y
+
+
+def to_f16(x):
+    """fp32 -> fp16 copy made by the library's own conversion kernel."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    _chk(lib.tcx_f32_to_f16(_ptr(x.detach()), _ptr16(y), x.numel(), _stream()))
+    return y
+
+
+def linear_f16(x16, w16, b=None, residual=None, out_f16=False):
+    """fp16-operand nn.Linear: x16 [..,K] fp16, w16 [N,K] fp16 -> fp32 (+bias +residual) or fp16 (+bias)."""
+    require_cuda(x16)
+    lib = load_library()
+    K = x16.shape[-1]
+    N = w16.shape[0]
+    M = x16.numel() // K
+    y = torch.empty(x16.shape[:-1] + (N,), device=x16.device, dtype=torch.float16 if out_f16 else torch.float32)
+    _chk(lib.tcx_linear_f16_fwd(_ptr16(x16), _ptr16(w16), _ptr(_d(b)), _ptr(residual),
+                                _ptr16(y) if out_f16 else _ptr(y), M, N, K, int(out_f16), _stream()))
     return y
 
 
@@ -221,7 +302,7 @@ def mixffn_skip(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, resid
     C4 = fc1w.shape[0]
     y = torch.empty_like(xn)
     ws = _ws(lib.tcx_mixffn_skip_workspace_bytes(B, N, C4), xn)
-    tab = _table([fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b])
+    tab = _table([fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b], mats=(0, 6))
     _chk(lib.tcx_mixffn_skip_fwd(_ptr(xn), tab, eps, _ptr(residual), _ptr(y), B, H, W, C, C4, _ptr(ws), _stream()))
     return y
 
@@ -271,7 +352,8 @@ def mhca_blocks(x, H, W, branches):
     b0 = branches[0][0]
     y = x.contiguous().clone()
     ws = _ws(lib.tcx_mhca_blocks_workspace_bytes(G, B, N, C), x)
-    _chk(lib.tcx_mhca_blocks_fwd(_ptr(y), _table(flat), G, L, B, H, W, C, b0.factoratt_crpe.num_heads,
+    mats = [k * MHCA_NP + j for k in range(G * L) for j in (4, 12, 16, 22)]
+    _chk(lib.tcx_mhca_blocks_fwd(_ptr(y), _table(flat, mats), G, L, B, H, W, C, b0.factoratt_crpe.num_heads,
                                  b0.norm1.eps, b0.mlp.norm1.eps, _ptr(ws), _stream()))
     return y
 
@@ -394,7 +476,49 @@ def bridge_mixffn(tx, tx1, mix_args):
     for a in mix_args:
         flat.extend([a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8]])
     ws = _ws(lib.tcx_bridge_mixffn_workspace_bytes(B, S), tx)
-    _chk(lib.tcx_bridge_mixffn_fwd(_ptr(tx), _ptr(tx1), _table(flat), eps, _ptr(y), B, S, _ptr(ws), _stream()))
+    mats = [8 * k + j for k in range(4) for j in (0, 6)]
+    _chk(lib.tcx_bridge_mixffn_fwd(_ptr(tx), _ptr(tx1), _table(flat, mats), eps, _ptr(y), B, S, _ptr(ws), _stream()))
+    return y
+
+
+def _mix_slots(a):
+    """MixFFN_skip.args() -> the 8 C-ABI slots {fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b} and its LN eps."""
+    return [a[0], a[1], a[2], a[3], a[4], a[5], a[7], a[8]], a[6]
+
+
+def eff_block(x, H, W, n1w, n1b, ln_eps, attn_args, n2w, n2b, mix_args):
+    """EfficientTransformerBlock.forward (reference MSTr.py:164-173) in one call."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, N, C = x.shape
+    kw, kb, qw, qb, vw, vb, rw, rb = attn_args
+    mix, mlp_eps = _mix_slots(mix_args)
+    slots = [n1w, n1b, kw.reshape(C, C), kb, qw.reshape(C, C), qb, vw.reshape(C, C), vb, rw.reshape(C, C), rb,
+             n2w, n2b] + mix
+    y = torch.empty_like(x)
+    ws = _ws(lib.tcx_eff_block_workspace_bytes(B, N, C), x)
+    _chk(lib.tcx_eff_block_fwd(_ptr(x), _table(slots, mats=(12, 18)), ln_eps, mlp_eps, _ptr(y), B, H, W, C, _ptr(ws),
+                               _stream()))
+    return y
+
+
+def bridge_layer(x, n1w, n1b, ln_eps, channel_att, attn_slots, scale, n2w, n2b, mix_args_list):
+    """BridgLayer_4.forward (reference MSTr.py:2373-2409) on the token buffer in one call."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, ntok, C = x.shape
+    S = _bridge_side(ntok)
+    attn_slots = list(attn_slots) + [None] * (14 - len(attn_slots))
+    slots = [n1w, n1b] + attn_slots + [n2w, n2b]
+    for a in mix_args_list:
+        slots.extend(_mix_slots(a)[0])
+    mats = [18 + 8 * k + j for k in range(4) for j in (0, 6)]
+    y = torch.empty_like(x)
+    ws = _ws(lib.tcx_bridge_layer_workspace_bytes(B, S), x)
+    _chk(lib.tcx_bridge_layer_fwd(_ptr(x), _table(slots, mats), int(channel_att), scale, ln_eps, _ptr(y), B, S,
+                                  _ptr(ws), _stream()))
     return y
 
 
