@@ -57,6 +57,8 @@ int tcx_linear_f16_fwd(const void* x16, const void* w16, const float* bias, cons
  * registry is the only state the library keeps: w16 must stay valid until tcx_forget_weight(w32), and must be
  * re-prepared when the values at w32 change.  Flag "f16_pipeline" = 0 disables the lookup. */
 int tcx_prepare_weight_f16(const float* w32, void* w16, long long numel, void* stream);
+/* strided patchify conv weight [N][Cin][r][r] (Scale_reduce sr0/sr1/sr2): prepared as [N][(ky,kx,cin)] fp16 */
+int tcx_prepare_conv_weight_f16(const float* w32, void* w16, int N, int Cin, int r, void* stream);
 int tcx_forget_weight(const float* w32);
 /* Conv2d_BN 1x1 (MSTr.py:399-404): y = act(BN(x w^T)) */
 int tcx_linear_bn_act_fwd(const float* x, const float* w, const float* bn_w, const float* bn_b, const float* bn_rm,

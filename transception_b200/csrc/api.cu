@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "misc.cuh"
 #include "fused16.cuh"
+#include "ea16.cuh"
 #include <mutex>
 #include <unordered_map>
 
@@ -293,6 +294,108 @@ int run_ln16_1(const float* x, const float* w, const float* b, __half* y16, floa
   return run_ln16(1, xs, ws, bs, y16 ? y16s : nullptr, y32 ? y32s : nullptr, M, C, eps, st);
 }
 
+// efficient / channel attention with fp16 K/Q/V, context and attention output; y = residual + reproj(att) in fp32
+int run_eff_attn16(const __half* xn16, const void* const* p, const float* residual, float* y, int B, int N, int C,
+                   int reinterpret, float* ws, cudaStream_t st) {
+  Carver c(ws);
+  const size_t bnc = (size_t)B * N * C;
+  __half* kqv = H16(c.take(3 * bnc / 2 + 64));
+  __half* qsm = H16(c.take(bnc / 2 + 64));
+  __half* att = H16(c.take(bnc / 2 + 64));
+  __half* ctxT = H16(c.take((size_t)B * C * C / 2 + 64));
+  float* part = c.take(ea16_workspace_floats(B, N, C));
+  const int M = B * N;
+  GemmParams g = gemm1(F(xn16), nullptr, nullptr, M, C, C);
+  g.groups = 3; g.ab16 = 1; g.out16 = 1;
+  Ea16View v{};
+  for (int i = 0; i < 3; i++) {
+    g.g[i].A = F(xn16); g.g[i].W = F(w16_of(p[2 * i])); g.g[i].epi.bias = F(p[2 * i + 1]);
+    g.g[i].C = reinterpret_cast<float*>(reinterpret ? kqv + i * bnc : kqv + i * C);
+  }
+  if (reinterpret) {
+    g.ldc = C;
+    v = Ea16View{kqv, kqv + bnc, kqv + 2 * bnc, (long long)N * C, C, 1};
+  } else {
+    g.ldc = 3 * C;
+    v = Ea16View{kqv, kqv + C, kqv + 2 * C, (long long)N * 3 * C, 3 * C, 0};
+  }
+  TCX_TRY(launch_gemm(g, st));
+  TCX_TRY(launch_ea16_context(v, B, N, C, part, ctxT, st));
+  TCX_TRY(launch_ea16_qsoftmax(v, B, N, C, qsm, st));
+  {  // att[b] = qsm[b] (N x C) * ctx[b] (C x C): W = ctxT[b]
+    GemmParams a = gemm1(F(qsm), F(ctxT), reinterpret_cast<float*>(att), N, C, C);
+    a.batch = B; a.strideA = (long long)N * C; a.strideW = (long long)C * C; a.strideC = (long long)N * C;
+    a.ab16 = 1; a.out16 = 1;
+    TCX_TRY(launch_gemm(a, st));
+  }
+  GemmParams r = gemm1(F(att), F(w16_of(p[6])), y, M, C, C);
+  r.ab16 = 1;
+  r.g[0].epi.bias = F(p[7]);
+  r.g[0].epi.residual = residual;
+  return launch_gemm(r, st);
+}
+inline bool eff_attn_prepared(const void* const* p, int N, int C, int reinterpret) {
+  if (N < 32 || C % 64) return false;
+  if (reinterpret && (C != 64 || N % 4)) return false;
+  return w16_of(p[0]) && w16_of(p[2]) && w16_of(p[4]) && w16_of(p[6]);
+}
+
+// bridge spatial-reduction attention with fp16 q / reduced tokens / kv / attention output (MSTr.py:2267-2292)
+inline bool bridge_sr_prepared(const void* const* p) {
+  return w16_of(p[0]) && w16_of(p[2]) && w16_of(p[4]) && w16_of(p[6]) && w16_of(p[8]) && w16_of(p[10]);
+}
+int run_bridge_sr_attn16(const __half* xn16, const void* const* p, float scale, float ln_eps, const float* residual, float* y,
+                         int B, const BridgeGeom& g, float* ws, cudaStream_t st) {
+  Carver c(ws);
+  const size_t bn = (size_t)B * g.ntok * 64;
+  __half* q = H16(c.take(bn / 2 + 64));
+  __half* o = H16(c.take(bn / 2 + 64));
+  __half* red = H16(c.take((size_t)B * g.nred * 32 + 64));
+  __half* kv = H16(c.take((size_t)B * g.nred * 64 + 64));
+  float* fws = c.take(flash_tc_workspace_bytes(B, g.nred) / 4 + 64);
+  const int M = B * g.ntok;
+  {
+    GemmParams gq = gemm1(F(xn16), F(w16_of(p[0])), reinterpret_cast<float*>(q), M, 64, 64);
+    gq.ab16 = 1; gq.out16 = 1;
+    gq.g[0].epi.bias = F(p[1]);
+    TCX_TRY(launch_gemm(gq, st));
+  }
+  {  // Scale_reduce: patchify convs as GEMMs on (ky,kx,cin)-ordered rows, then pack + LayerNorm
+    const int ratio[3] = {8, 4, 2};
+    SrPackArgs a{};
+    const long long xs_b = (long long)g.ntok * 64;
+    for (int k = 0; k < 3; k++) {
+      const int r = ratio[k], Cin = g.ch[k];
+      const int K = Cin * r * r, Mk = B * g.pp;
+      __half* A = H16(c.take((size_t)Mk * K / 2 + 64));
+      float* conv = c.take((size_t)Mk * Cin);
+      TCX_TRY(launch_sr_im2row16(xn16 + (long long)g.off[k] * 64, xs_b, g.hw[k], Cin, r, B, A, st));
+      GemmParams gp = gemm1(F(A), F(w16_of(p[6 + 2 * k])), conv, Mk, Cin, K);
+      gp.ab16 = 1;
+      gp.g[0].epi.bias = F(p[7 + 2 * k]);
+      TCX_TRY(launch_gemm(gp, st));
+      a.conv[k] = conv; a.gmul[k] = Cin / 64; a.pp[k] = g.pp;
+    }
+    a.x = nullptr; a.xs_b = xs_b; a.raw_tok0 = g.off[3];
+    for (int i = 0; i < 4; i++) a.red_off[i] = g.red_off[i];
+    a.nred = g.nred; a.B = B;
+    a.lnw = F(p[12]); a.lnb = F(p[13]); a.eps = ln_eps; a.out = nullptr;
+    TCX_TRY(launch_sr_pack_ln16(a, xn16, red, st));
+  }
+  {
+    GemmParams gk = gemm1(F(red), F(w16_of(p[2])), reinterpret_cast<float*>(kv), B * g.nred, 128, 64);
+    gk.ab16 = 1; gk.out16 = 1;
+    gk.g[0].epi.bias = F(p[3]);
+    TCX_TRY(launch_gemm(gk, st));
+  }
+  TCX_TRY(launch_flash_tc16(q, kv, o, B, g.ntok, g.nred, scale, fws, st));
+  GemmParams gp = gemm1(F(o), F(w16_of(p[4])), y, M, 64, 64);
+  gp.ab16 = 1;
+  gp.g[0].epi.bias = F(p[5]);
+  gp.g[0].epi.residual = residual;
+  return launch_gemm(gp, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -369,6 +472,14 @@ int tcx_prepare_weight_f16(const float* w32, void* w16, long long numel, void* s
   return 0;
 }
 
+int tcx_prepare_conv_weight_f16(const float* w32, void* w16, int N, int Cin, int r, void* stream) {
+  TCX_REQUIRE(w32 && w16 && N > 0 && Cin > 0 && r > 0, "prepare_conv_weight: bad arguments");
+  TCX_TRY(launch_conv_weight_perm16(w32, w16, N, Cin, r, S(stream)));
+  std::lock_guard<std::mutex> lk(g_w16_mu);
+  g_w16[w32] = w16;
+  return 0;
+}
+
 int tcx_forget_weight(const float* w32) {
   std::lock_guard<std::mutex> lk(g_w16_mu);
   g_w16.erase(w32);
@@ -408,12 +519,23 @@ int tcx_dwconv_tokens_fwd(const float* x, const float* w, const float* b, float*
 // ---- K8 --------------------------------------------------------------------------------
 size_t tcx_eff_attn_workspace_bytes(int B, int N, int C) {
   const size_t bnc = (size_t)B * N * C;
-  return 4 * (rnd(3 * bnc) + rnd(bnc) + rnd(bnc) + rnd((size_t)B * C * C) + rnd(ea_workspace_floats(B, N, C)));
+  size_t part = ea_workspace_floats(B, N, C);
+  if (ea16_workspace_floats(B, N, C) > part) part = ea16_workspace_floats(B, N, C);
+  return 4 * (rnd(3 * bnc) + rnd(bnc) + rnd(bnc) + rnd((size_t)B * C * C) + rnd(part) + rnd(bnc) + 1024);
 }
 
 int tcx_eff_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C,
                      int reinterpret, void* ws, void* stream) {
   cudaStream_t st = S(stream);
+  if (eff_attn_prepared(p, N, C, reinterpret)) {
+    // standalone entry: the caller's LayerNorm output is fp32 -> one conversion pass, then the fp16 form
+    const size_t bnc0 = (size_t)B * N * C;
+    size_t part = ea_workspace_floats(B, N, C);
+    if (ea16_workspace_floats(B, N, C) > part) part = ea16_workspace_floats(B, N, C);
+    float* tail = reinterpret_cast<float*>(ws) + rnd(3 * bnc0) + 2 * rnd(bnc0) + rnd((size_t)B * C * C) + rnd(part);
+    TCX_TRY(launch_f32_to_f16(xn, tail, (long long)bnc0, st));
+    return run_eff_attn16(H16(tail), p, residual, y, B, N, C, reinterpret, reinterpret_cast<float*>(ws), st);
+  }
   Carver c(ws);
   const size_t bnc = (size_t)B * N * C;
   float* kqv = c.take(3 * bnc);
@@ -854,8 +976,13 @@ int tcx_eff_block_fwd(const float* x, const void* const* p, float ln_eps, float 
   float* tx = c.take(bnc);
   float* aws = c.take(tcx_eff_attn_workspace_bytes(B, N, C) / 4);
   float* mws = c.take(tcx_mixffn_skip_workspace_bytes(B, N, 4 * C) / 4);
-  TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n, (long long)B * N, C, ln_eps, st));
-  TCX_TRY(tcx_eff_attn_fwd(n, p + 2, x, tx, B, N, C, 0, aws, stream));
+  if (eff_attn_prepared(p + 2, N, C, 0)) {
+    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n), nullptr, (long long)B * N, C, ln_eps, st));
+    TCX_TRY(run_eff_attn16(H16(n), p + 2, x, tx, B, N, C, 0, aws, st));
+  } else {
+    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n, (long long)B * N, C, ln_eps, st));
+    TCX_TRY(tcx_eff_attn_fwd(n, p + 2, x, tx, B, N, C, 0, aws, stream));
+  }
   Mix16 m{};
   if (mix16_fill(p + 12, m)) {
     __half* n16 = H16(n);
@@ -896,9 +1023,17 @@ int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, 
   if (sr > att) att = sr;
   float* aws = c.take(att / 4);
   float* mws = c.take(tcx_bridge_mixffn_workspace_bytes(B, S0) / 4);
-  TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n1, M, 64, ln_eps, st));
-  if (channel_att) TCX_TRY(tcx_eff_attn_fwd(n1, p + 2, x, tx1, B, g.ntok, 64, 1, aws, stream));
-  else TCX_TRY(tcx_bridge_sr_attn_fwd(n1, p + 2, scale, ln_eps, x, tx1, B, S0, aws, stream));
+  if (channel_att && eff_attn_prepared(p + 2, g.ntok, 64, 1)) {
+    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
+    TCX_TRY(run_eff_attn16(H16(n1), p + 2, x, tx1, B, g.ntok, 64, 1, aws, st));
+  } else if (!channel_att && flash_tc_enabled() && bridge_sr_prepared(p + 2)) {
+    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
+    TCX_TRY(run_bridge_sr_attn16(H16(n1), p + 2, scale, ln_eps, x, tx1, B, g, aws, st));
+  } else {
+    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n1, M, 64, ln_eps, st));
+    if (channel_att) TCX_TRY(tcx_eff_attn_fwd(n1, p + 2, x, tx1, B, g.ntok, 64, 1, aws, stream));
+    else TCX_TRY(tcx_bridge_sr_attn_fwd(n1, p + 2, scale, ln_eps, x, tx1, B, S0, aws, stream));
+  }
   if (bridge_mix_prepared(p + 18)) {
     __half* tx16 = H16(tx);
     TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), tx16, nullptr, M, 64, ln_eps, st));

@@ -27,4 +27,6 @@ int launch_flash_ffma(const float* q, const float* kv, float* out, int B, int Nq
 size_t flash_tc_workspace_bytes(int B, int Nk);
 int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
                     cudaStream_t st);
+int launch_flash_tc16(const void* q16, const void* kv16, void* out16, int B, int Nq, int Nk, float scale, void* ws,
+                      cudaStream_t st);
 bool flash_tc_enabled();

@@ -1,0 +1,18 @@
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+// K/Q/V of the efficient attention in fp16.
+//  tokens-major (reint = 0): element (n, c) at ptr + b*sb + n*ldt + c
+//  reinterpreted (reint = 1, MSTr.py:2312-2314): element (c', n') at ptr + b*sb + c'*N + n'
+struct Ea16View {
+  const __half* k;
+  const __half* q;
+  const __half* v;
+  long long sb;
+  int ldt;
+  int reint;
+};
+size_t ea16_workspace_floats(int B, int N, int C);
+int launch_ea16_context(const Ea16View& v, int B, int N, int C, float* ws, __half* ctxT, cudaStream_t st);
+int launch_ea16_qsoftmax(const Ea16View& v, int B, int N, int C, __half* dst, cudaStream_t st);

@@ -80,8 +80,11 @@ __device__ __forceinline__ void load_s_row(uint32_t tS, uint32_t (&s)[FT_BN]) {
   tc::tmem_ld_wait();
 }
 
+// Q16 / O16: q rows and the output are fp16 (the fp16 pipeline) instead of fp32.  q is staged UNSCALED; the softmax
+// scale (times log2 e) is applied to the scores inside the exponent FFMA, which costs nothing extra.
+template <bool Q16, bool O16>
 __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_constant__ FlashMaps maps,
-                                                                 const float* __restrict__ q, float* __restrict__ out,
+                                                                 const void* __restrict__ qv, void* __restrict__ outv,
                                                                  int B, int Nq, int Nk, float qscale) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -215,14 +218,23 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       const int tile = (pair - b * pairs_per_img) * 2 + w;
       const int row = tile * FT_BM + r;
       const bool valid = row < Nq;
-      {
-        const float4* __restrict__ qrow = reinterpret_cast<const float4*>(q + ((long long)b * Nq + (valid ? row : 0)) * FT_D);
+      if (Q16) {
+        const uint4* __restrict__ qrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(qv) +
+                                                                        ((long long)b * Nq + (valid ? row : 0)) * FT_D);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          uint4 a = make_uint4(0u, 0u, 0u, 0u);
+          if (valid) a = qrow[c];
+          st_shared_v4(rowQ + ((c ^ sw) << 4), a.x, a.y, a.z, a.w);
+        }
+      } else {
+        const float4* __restrict__ qrow = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(qv) +
+                                                                          ((long long)b * Nq + (valid ? row : 0)) * FT_D);
 #pragma unroll
         for (int c = 0; c < 8; c++) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d = a;
           if (valid) { a = qrow[2 * c]; d = qrow[2 * c + 1]; }
-          st_shared_v4(rowQ + ((c ^ sw) << 4), pack_h2(a.x * qscale, a.y * qscale), pack_h2(a.z * qscale, a.w * qscale),
-                       pack_h2(d.x * qscale, d.y * qscale), pack_h2(d.z * qscale, d.w * qscale));
+          st_shared_v4(rowQ + ((c ^ sw) << 4), pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(d.x, d.y), pack_h2(d.z, d.w));
         }
       }
       tc::fence_before_sync();
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
         float tmax = -INFINITY;
 #pragma unroll
         for (int j = 0; j < FT_BN; j++) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
-        const float m_new = fmaxf(m, tmax);
+        const float m_new = fmaxf(m, tmax * qscale);   // running max in log2 units (qscale > 0)
         if (t == 0) {
           m = m_new;
         } else {
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
           float p[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            p[j] = ex2f(__uint_as_float(sv[g * 8 + j]) - m);
+            p[j] = ex2f(fmaf(__uint_as_float(sv[g * 8 + j]), qscale, -m));
             lsum += p[j];
           }
           uint8_t* dst = rowP + (g >> 3) * (FT_BM * 128) + (((g & 7) ^ sw) << 4);
@@ -299,10 +311,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       }
       if (valid) {
         const float inv = 1.f / l;
-        float4* __restrict__ orow = reinterpret_cast<float4*>(out + ((long long)b * Nq + row) * FT_D);
+        if (O16) {
+          uint4* __restrict__ orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(outv) + ((long long)b * Nq + row) * FT_D);
 #pragma unroll
-        for (int i = 0; i < FT_D / 4; i++)
-          orow[i] = make_float4(O[4 * i] * inv, O[4 * i + 1] * inv, O[4 * i + 2] * inv, O[4 * i + 3] * inv);
+          for (int i = 0; i < FT_D / 8; i++)
+            orow[i] = make_uint4(pack_h2(O[8 * i] * inv, O[8 * i + 1] * inv), pack_h2(O[8 * i + 2] * inv, O[8 * i + 3] * inv),
+                                 pack_h2(O[8 * i + 4] * inv, O[8 * i + 5] * inv), pack_h2(O[8 * i + 6] * inv, O[8 * i + 7] * inv));
+        } else {
+          float4* __restrict__ orow = reinterpret_cast<float4*>(reinterpret_cast<float*>(outv) + ((long long)b * Nq + row) * FT_D);
+#pragma unroll
+          for (int i = 0; i < FT_D / 4; i++)
+            orow[i] = make_float4(O[4 * i] * inv, O[4 * i + 1] * inv, O[4 * i + 2] * inv, O[4 * i + 3] * inv);
+        }
       }
     }
   }
@@ -336,11 +356,58 @@ __global__ void __launch_bounds__(256) flash_pack_kv_kernel(const float* __restr
   }
 }
 
+// fp16 kv [B][Nk][128] (k | v) -> vt16 [B][64][Nkp] (V transposed, kv contiguous); K is consumed in place
+__global__ void __launch_bounds__(256) flash_pack_vt16_kernel(const __half* __restrict__ kv, __half* __restrict__ vt16, int Nk,
+                                                              int Nkp) {
+  __shared__ __half vs[32][66];
+  const int b = blockIdx.y, n0 = blockIdx.x * 32, tid = threadIdx.x;
+  const __half* __restrict__ src = kv + ((long long)b * Nk + n0) * 128 + 64;
+  {
+    const int n = tid >> 3, j = tid & 7;      // 32 rows x 8 vectors of 8 halfs
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (n0 + n < Nk) r = *reinterpret_cast<const uint4*>(src + (long long)n * 128 + j * 8);
+    const __half* h = reinterpret_cast<const __half*>(&r);
+#pragma unroll
+    for (int q = 0; q < 8; q++) vs[n][j * 8 + q] = h[q];
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * 32; i += 256) {
+    const int d = i >> 5, n = i & 31;
+    if (n0 + n < Nkp) vt16[((long long)b * 64 + d) * Nkp + n0 + n] = vs[n][d];
+  }
+}
+
 }  // namespace
 
 size_t flash_tc_workspace_bytes(int B, int Nk) {
   const int Nkp = (Nk + 7) / 8 * 8;
   return align_up((size_t)B * Nk * 64 * 2, 1024) + align_up((size_t)B * 64 * Nkp * 2, 1024);
+}
+
+static int flash_tc_launch(const FlashMaps& maps, const void* q, void* out, int B, int Nq, int Nk, float scale, bool f16io,
+                           cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(flash_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(flash_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+    TCX_REQUIRE(e == cudaSuccess, "flash_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    done = true;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int tiles_per_img = cdiv(Nq, FT_BM);
+  const int npairs = B * ((tiles_per_img + 1) / 2);
+  const float qscale = scale * 1.4426950408889634f;
+  ProfScope prof("flash_tc", st);
+  if (f16io) flash_tc_kernel<true, true><<<min(npairs, sms), FT_THREADS, FT_SMEM, st>>>(maps, q, out, B, Nq, Nk, qscale);
+  else flash_tc_kernel<false, false><<<min(npairs, sms), FT_THREADS, FT_SMEM, st>>>(maps, q, out, B, Nq, Nk, qscale);
+  return tcx_check_launch("flash_tc");
 }
 
 int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
@@ -357,23 +424,22 @@ int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, 
   FlashMaps maps;
   TCX_TRY(tcx_make_operand_map(&maps.k, k16, 2, 64, Nk, 64, B, (long long)Nk * 64, 64, FT_BN));
   TCX_TRY(tcx_make_operand_map(&maps.vt, vt16, 2, Nkp, 64, Nkp, B, (long long)64 * Nkp, 64, 64));
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
-    TCX_REQUIRE(e == cudaSuccess, "flash_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    done = true;
+  return flash_tc_launch(maps, q, out, B, Nq, Nk, scale, false, st);
+}
+
+// fp16 form: q16 [B][Nq][64], kv16 [B][Nk][128] (k | v), out16 [B][Nq][64]; ws holds V^T only
+int launch_flash_tc16(const void* q16, const void* kv16, void* out16, int B, int Nq, int Nk, float scale, void* ws,
+                      cudaStream_t st) {
+  TCX_REQUIRE(ws != nullptr && ((uintptr_t)ws & 127) == 0, "flash_tc: workspace must be 128-byte aligned");
+  const int Nkp = (Nk + 7) / 8 * 8;
+  __half* vt16 = reinterpret_cast<__half*>(ws);
+  {
+    dim3 grid(cdiv(Nkp, 32), B);
+    flash_pack_vt16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(kv16), vt16, Nk, Nkp);
+    TCX_TRY(tcx_check_launch("flash_pack_vt16"));
   }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  const int tiles_per_img = cdiv(Nq, FT_BM);
-  const int npairs = B * ((tiles_per_img + 1) / 2);
-  const float qscale = scale * 1.4426950408889634f;
-  ProfScope prof("flash_tc", st);
-  flash_tc_kernel<<<min(npairs, sms), FT_THREADS, FT_SMEM, st>>>(maps, q, out, B, Nq, Nk, qscale);
-  return tcx_check_launch("flash_tc");
+  FlashMaps maps;
+  TCX_TRY(tcx_make_operand_map(&maps.k, kv16, 2, 64, Nk, 128, B, (long long)Nk * 128, 64, FT_BN));
+  TCX_TRY(tcx_make_operand_map(&maps.vt, vt16, 2, Nkp, 64, Nkp, B, (long long)64 * Nkp, 64, 64));
+  return flash_tc_launch(maps, q16, out16, B, Nq, Nk, scale, true, st);
 }

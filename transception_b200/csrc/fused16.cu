@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "fused16.cuh"
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 namespace {
@@ -39,69 +40,109 @@ __device__ __forceinline__ float seg_sum(float v) {
 // ------------------------------------------------------------------------------------------------------------------
 // dw3x3 + skip + LayerNorm (+GELU)
 // ------------------------------------------------------------------------------------------------------------------
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16
+// output quantum): one MUFU.RCP + one MUFU.EX2 + a 5-term Horner chain, no branches / selects.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * __expf(-z * z);            // 1 - erf(z), z >= 0
+  const float h = 0.5f * x;
+  return x >= 0.f ? fmaf(-h, e, x) : h * e;          // x>=0: 0.5x(2-e) ; x<0: 0.5x(1-(1-e)) = 0.5 x e
+}
+
+// channel c of a token row -> position inside the per-tap smem vectors: lanes read contiguous 16-byte pieces
+template <int LPT, int VEC>
+__device__ __forceinline__ int wperm(int c) {
+  if (VEC == 4) return c;
+  const int blk = c / (LPT * 8), r = c - blk * (LPT * 8);      // NV block, offset inside it
+  const int sl = r >> 3, q = (r >> 2) & 1, j = r & 3;
+  return blk * (LPT * 8) + q * (LPT * 4) + sl * 4 + j;
+}
+
 template <bool IN16, int LPT, int NV>
 __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
   constexpr int VEC = IN16 ? 8 : 4;
   constexpr int SLOTS = 32 / LPT;
-  extern __shared__ float wsm[];            // [9][C] taps (centre + 1 = skip), then bias[C], lnw[C], lnb[C]
+  extern __shared__ float wsm[];            // [9][C] taps (centre + 1 = skip), then bias[C], lnw[C], lnb[C] (permuted)
   const DwLnGroup& g = a.g[blockIdx.y];
   const int C = a.C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 9 * C; i += 256) {
     const int c = i / 9, t = i - c * 9;
-    wsm[t * C + c] = g.dww[i] + (t == 4 ? 1.f : 0.f);
+    wsm[t * C + wperm<LPT, VEC>(c)] = g.dww[i] + (t == 4 ? 1.f : 0.f);
   }
   float* bsm = wsm + 9 * C;
   for (int i = tid; i < C; i += 256) {
-    bsm[i] = g.dwb ? g.dwb[i] : 0.f;
-    bsm[C + i] = g.lnw[i];
-    bsm[2 * C + i] = g.lnb[i];
+    const int pc = wperm<LPT, VEC>(i);
+    bsm[pc] = g.dwb ? g.dwb[i] : 0.f;
+    bsm[C + pc] = g.lnw[i];
+    bsm[2 * C + pc] = g.lnb[i];
   }
   __syncthreads();
   const int slot = lane / LPT, sl = lane % LPT;
-  const long long total = (long long)a.B * a.H * a.W;
-  const long long base = ((long long)blockIdx.x * 8 + warp) * (SLOTS * a.tpw);
+  const int total = a.B * a.H * a.W;
   const int H = a.H, W = a.W;
   const float invC = 1.f / (float)C;
-  for (int it = 0; it < a.tpw; it++) {
-    const long long tok = base + (long long)it * SLOTS + slot;
-    if (base + (long long)it * SLOTS >= total) break;      // warp-uniform
-    const bool live = tok < total;
-    const int wq = (int)(tok % W), hq = (int)((tok / W) % H);
-    float acc[NV][VEC];
+  const int chunk = SLOTS * a.tpw;                       // consecutive tokens per warp visit
+  const int nchunks = (total + chunk - 1) / chunk;
+  for (int ch = blockIdx.x * 8 + warp; ch < nchunks; ch += gridDim.x * 8) {
+    const int base = ch * chunk;
+    int tok = base + slot;
+    int wq = tok % W, hq = (tok / W) % H;
+    for (int it = 0; it < a.tpw; it++, tok += SLOTS) {
+      if (base + it * SLOTS >= total) break;             // warp-uniform
+      const bool live = tok < total;
+      float acc[NV][VEC];
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
-      const int c0 = (sl + i * LPT) * VEC;
+      for (int i = 0; i < NV; i++) {
 #pragma unroll
-      for (int q = 0; q < VEC / 4; q++) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bsm + c0 + q * 4);
-        acc[i][q * 4 + 0] = b4.x; acc[i][q * 4 + 1] = b4.y; acc[i][q * 4 + 2] = b4.z; acc[i][q * 4 + 3] = b4.w;
+        for (int q = 0; q < VEC / 4; q++) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bsm + i * LPT * VEC + q * LPT * 4 + sl * 4);
+          acc[i][q * 4 + 0] = b4.x; acc[i][q * 4 + 1] = b4.y; acc[i][q * 4 + 2] = b4.z; acc[i][q * 4 + 3] = b4.w;
+        }
       }
-    }
+      const size_t row0 = (size_t)(live ? tok : 0) * C + sl * VEC;
+      // branch-free taps: every load is issued (out-of-map neighbours read the centre row and are zeroed), so the
+      // 9 x NV loads of a token are all in flight together
+      const bool rv0 = hq > 0, rv2 = hq + 1 < H, cv0 = wq > 0, cv2 = wq + 1 < W;
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++) {
+      for (int i = 0; i < NV; i++) {
+        // the 9 taps of one 16-byte channel vector: loads first (all in flight), then the FMAs
+        typename std::conditional<IN16, uint4, float4>::type raw[9];
 #pragma unroll
-      for (int kx = 0; kx < 3; kx++) {
-        const int hi = hq - 1 + ky, wi = wq - 1 + kx;
-        if (!(live && hi >= 0 && hi < H && wi >= 0 && wi < W)) continue;
-        const long long nb = tok + (long long)(ky - 1) * W + (kx - 1);
-        const float* wt = wsm + (ky * 3 + kx) * C;
+        for (int t = 0; t < 9; t++) {
+          const int ky = t / 3, kx = t % 3;
+          const bool valid = live && (ky == 0 ? rv0 : (ky == 2 ? rv2 : true)) && (kx == 0 ? cv0 : (kx == 2 ? cv2 : true));
+          const size_t nb = (valid ? row0 + (ptrdiff_t)((ky - 1) * W + (kx - 1)) * C : row0) + i * LPT * VEC;
+          if (IN16) {
+            uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g.x) + nb);
+            if (!valid) r = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(&raw[t]) = r;
+          } else {
+            float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.x) + nb);
+            if (!valid) r = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(&raw[t]) = r;
+          }
+        }
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-          const int c0 = (sl + i * LPT) * VEC;
+        for (int t = 0; t < 9; t++) {
+          const float* wt = wsm + t * C + sl * 4 + i * LPT * VEC;
           float xv[VEC];
           if (IN16) {
-            const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g.x) + nb * C + c0);
             float f[8];
-            unpack8(r, f);
+            unpack8(*reinterpret_cast<const uint4*>(&raw[t]), f);
 #pragma unroll
             for (int j = 0; j < VEC; j++) xv[j] = f[j];
           } else {
-            const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.x) + nb * C + c0);
+            const float4 r = *reinterpret_cast<const float4*>(&raw[t]);
             xv[0] = r.x; xv[1] = r.y; xv[2] = r.z; xv[3] = r.w;
           }
 #pragma unroll
           for (int q = 0; q < VEC / 4; q++) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + c0 + q * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + q * LPT * 4);
             acc[i][q * 4 + 0] = fmaf(xv[q * 4 + 0], w4.x, acc[i][q * 4 + 0]);
             acc[i][q * 4 + 1] = fmaf(xv[q * 4 + 1], w4.y, acc[i][q * 4 + 1]);
             acc[i][q * 4 + 2] = fmaf(xv[q * 4 + 2], w4.z, acc[i][q * 4 + 2]);
@@ -109,50 +150,54 @@ __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
           }
         }
       }
-    }
-    float s = 0.f;
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; i++)
+      for (int i = 0; i < NV; i++)
 #pragma unroll
-      for (int j = 0; j < VEC; j++) s += acc[i][j];
-    const float mean = seg_sum<LPT>(s) * invC;
-    float q2 = 0.f;
+        for (int j = 0; j < VEC; j++) s += acc[i][j];
+      const float mean = seg_sum<LPT>(s) * invC;
+      float q2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; i++)
+      for (int i = 0; i < NV; i++)
 #pragma unroll
-      for (int j = 0; j < VEC; j++) { const float d = acc[i][j] - mean; q2 = fmaf(d, d, q2); }
-    const float rstd = rsqrtf(seg_sum<LPT>(q2) * invC + a.eps);
-    if (!live) continue;
+        for (int j = 0; j < VEC; j++) { const float d = acc[i][j] - mean; q2 = fmaf(d, d, q2); }
+      const float rstd = rsqrtf(seg_sum<LPT>(q2) * invC + a.eps);
+      if (live) {
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
-      const int c0 = (sl + i * LPT) * VEC;
-      if (g.u) {
+        for (int i = 0; i < NV; i++) {
+          const size_t off = (size_t)tok * C + sl * VEC + i * LPT * VEC;
+          if (g.u) {
 #pragma unroll
-        for (int q = 0; q < VEC / 4; q++)
-          *reinterpret_cast<float4*>(g.u + tok * C + c0 + q * 4) =
-              make_float4(acc[i][q * 4], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
+            for (int q = 0; q < VEC / 4; q++)
+              *reinterpret_cast<float4*>(g.u + off + q * 4) =
+                  make_float4(acc[i][q * 4], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
+          }
+          float o[VEC];
+#pragma unroll
+          for (int q = 0; q < VEC / 4; q++) {
+            const float4 w4 = *reinterpret_cast<const float4*>(bsm + C + i * LPT * VEC + q * LPT * 4 + sl * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bsm + 2 * C + i * LPT * VEC + q * LPT * 4 + sl * 4);
+            o[q * 4 + 0] = fmaf((acc[i][q * 4 + 0] - mean) * rstd, w4.x, b4.x);
+            o[q * 4 + 1] = fmaf((acc[i][q * 4 + 1] - mean) * rstd, w4.y, b4.y);
+            o[q * 4 + 2] = fmaf((acc[i][q * 4 + 2] - mean) * rstd, w4.z, b4.z);
+            o[q * 4 + 3] = fmaf((acc[i][q * 4 + 3] - mean) * rstd, w4.w, b4.w);
+          }
+          if (a.gelu) {
+#pragma unroll
+            for (int j = 0; j < VEC; j++) o[j] = gelu_fast(o[j]);
+          }
+          __half* yp = g.y + off;
+          if (VEC == 8) {
+            *reinterpret_cast<uint4*>(yp) = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[VEC - 4], o[VEC - 3]),
+                                                       pack2(o[VEC - 2], o[VEC - 1]));
+          } else {
+            *reinterpret_cast<uint2*>(yp) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+          }
+        }
       }
-      float o[VEC];
-#pragma unroll
-      for (int q = 0; q < VEC / 4; q++) {
-        const float4 w4 = *reinterpret_cast<const float4*>(bsm + C + c0 + q * 4);
-        const float4 b4 = *reinterpret_cast<const float4*>(bsm + 2 * C + c0 + q * 4);
-        o[q * 4 + 0] = fmaf((acc[i][q * 4 + 0] - mean) * rstd, w4.x, b4.x);
-        o[q * 4 + 1] = fmaf((acc[i][q * 4 + 1] - mean) * rstd, w4.y, b4.y);
-        o[q * 4 + 2] = fmaf((acc[i][q * 4 + 2] - mean) * rstd, w4.z, b4.z);
-        o[q * 4 + 3] = fmaf((acc[i][q * 4 + 3] - mean) * rstd, w4.w, b4.w);
-      }
-      if (a.gelu) {
-#pragma unroll
-        for (int j = 0; j < VEC; j++) o[j] = gelu_erf(o[j]);
-      }
-      __half* yp = g.y + tok * C + c0;
-      if (VEC == 8) {
-        *reinterpret_cast<uint4*>(yp) = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[VEC - 4], o[VEC - 3]),
-                                                   pack2(o[VEC - 2], o[VEC - 1]));
-      } else {
-        *reinterpret_cast<uint2*>(yp) = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
-      }
+      // next token of this slot: SLOTS further along the row-major token order
+      wq += SLOTS;
+      if (wq >= W) { wq -= W; if (++hq >= H) hq = 0; }
     }
   }
 }
@@ -287,6 +332,12 @@ __global__ void __launch_bounds__(256) mb_ctx16_kernel(const Mb16Args a) {
   for (int p = tid; p < npairs; p += 256) out[p] = a.scale * cacc[p] / ss[p / Ch];
 }
 
+// exact i / d for 0 <= i < 2^20 and small d via one multiply (inv = 1.0f / d): (i + 0.5) / d is never within 2^-20
+// of an integer, so float rounding cannot cross a boundary.
+__device__ __forceinline__ int fdiv(int i, float inv) { return (int)(((float)i + 0.5f) * inv); }
+
+constexpr int MBA_THREADS = 512;
+
 // conv relative position encoding + factorized attention for the channels of one window group (WIN x WIN filters):
 // a thread owns T adjacent tokens of one channel pair, slides the V window along x in registers and reuses each filter
 // tap for the T outputs.  All loops are compile-time unrolled; a warp never mixes window sizes.
@@ -298,8 +349,10 @@ __device__ __forceinline__ void mb_apply_group(const __half* __restrict__ vt, co
   constexpr int R = WIN / 2;
   const int np = nch / 2, xg_n = W / T;
   const int items = rows * xg_n * np;
-  for (int i = tid; i < items; i += 256) {
-    const int p = i % np, xg = (i / np) % xg_n, ty = i / (np * xg_n);
+  const float inv_np = 1.0f / (float)np, inv_xg = 1.0f / (float)xg_n;
+  for (int i = tid; i < items; i += MBA_THREADS) {
+    const int i1 = fdiv(i, inv_np), p = i - i1 * np;
+    const int ty = fdiv(i1, inv_xg), xg = i1 - ty * xg_n;
     const int cl = 2 * p, c = c_begin + cl, x0 = xg * T;
     const int h = c / Ch, cv = c - h * Ch;
     float v0[T], v1[T];
@@ -351,7 +404,7 @@ __device__ __forceinline__ void mb_apply_group(const __half* __restrict__ vt, co
 
 // grid (bands, B, G), 256 threads. out[n,c] = sum_k q[n,h*Ch+k] ctx[h][k][cv] + q[n,c] * (dwconv_win(h)(V)[n,c] + bias[c])
 template <int T>
-__global__ void __launch_bounds__(256) mb_apply16_kernel(const Mb16Args a, int R) {
+__global__ void __launch_bounds__(MBA_THREADS) mb_apply16_kernel(const Mb16Args a, int R) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int H = a.H, W = a.W, C = a.C, Ch = a.C / a.heads, N = H * W;
   const int CP = C + 8;                 // padded channel pitch of the V band (bank spreading)
@@ -368,25 +421,28 @@ __global__ void __launch_bounds__(256) mb_apply16_kernel(const Mb16Args a, int R
   float* bs = w7 + 49 * c7;                                        // [C]
   const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
   const int vpr = C / 8;
+  const float inv_vpr = 1.0f / (float)vpr, inv_w = 1.0f / (float)W;
   // V band with 3 halo rows on each side (zero outside the map)
-  for (int i = tid; i < (R + 6) * W * vpr; i += 256) {
-    const int j = i % vpr, px = (i / vpr) % W, ry = i / (vpr * W);
+  for (int i = tid; i < (R + 6) * W * vpr; i += MBA_THREADS) {
+    const int i1 = fdiv(i, inv_vpr), j = i - i1 * vpr;
+    const int ry = fdiv(i1, inv_w), px = i1 - ry * W;
     const int y = r0 - 3 + ry;
     uint4 raw = make_uint4(0u, 0u, 0u, 0u);
     if (y >= 0 && y < H && ry < rows + 6) raw = *reinterpret_cast<const uint4*>(base + (long long)(y * W + px) * 3 * C + 2 * C + j * 8);
     *reinterpret_cast<uint4*>(vt + ((size_t)ry * W + px) * CP + j * 8) = raw;
   }
-  for (int i = tid; i < rows * W * vpr; i += 256) {
-    const int j = i % vpr, px = (i / vpr) % W, ry = i / (vpr * W);
-    *reinterpret_cast<uint4*>(qt + ((size_t)ry * W + px) * C + j * 8) =
-        *reinterpret_cast<const uint4*>(base + (long long)((r0 + ry) * W + px) * 3 * C + j * 8);
+  for (int i = tid; i < rows * W * vpr; i += MBA_THREADS) {
+    const int i1 = fdiv(i, inv_vpr), j = i - i1 * vpr;
+    *reinterpret_cast<uint4*>(qt + (size_t)i1 * C + j * 8) =
+        *reinterpret_cast<const uint4*>(base + (long long)(r0 * W + i1) * 3 * C + j * 8);
   }
   const float* __restrict__ cg = a.ctx[gi] + (long long)b * C * Ch;
-  for (int i = tid; i < C * Ch; i += 256) ctx[i] = cg[i];
-  for (int i = tid; i < 9 * c3; i += 256) { const int ch = i / 9, t = i - ch * 9; w3[t * c3 + ch] = a.cw[gi][0][i]; }
-  for (int i = tid; i < 25 * c5; i += 256) { const int ch = i / 25, t = i - ch * 25; w5[t * c5 + ch] = a.cw[gi][1][i]; }
-  for (int i = tid; i < 49 * c7; i += 256) { const int ch = i / 49, t = i - ch * 49; w7[t * c7 + ch] = a.cw[gi][2][i]; }
-  for (int i = tid; i < C; i += 256) bs[i] = i < c3 ? a.cb[gi][0][i] : (i < c3 + c5 ? a.cb[gi][1][i - c3] : a.cb[gi][2][i - c3 - c5]);
+  for (int i = tid; i < C * Ch / 4; i += MBA_THREADS)
+    reinterpret_cast<float4*>(ctx)[i] = reinterpret_cast<const float4*>(cg)[i];
+  for (int i = tid; i < 9 * c3; i += MBA_THREADS) { const int ch = i / 9, t = i - ch * 9; w3[t * c3 + ch] = a.cw[gi][0][i]; }
+  for (int i = tid; i < 25 * c5; i += MBA_THREADS) { const int ch = i / 25, t = i - ch * 25; w5[t * c5 + ch] = a.cw[gi][1][i]; }
+  for (int i = tid; i < 49 * c7; i += MBA_THREADS) { const int ch = i / 49, t = i - ch * 49; w7[t * c7 + ch] = a.cw[gi][2][i]; }
+  for (int i = tid; i < C; i += MBA_THREADS) bs[i] = i < c3 ? a.cb[gi][0][i] : (i < c3 + c5 ? a.cb[gi][1][i - c3] : a.cb[gi][2][i - c3 - c5]);
   __syncthreads();
   __half* __restrict__ outp = a.out[gi] + ((long long)b * N + (long long)r0 * W) * C;
   // heads 0-1: 3x3, heads 2-4: 5x5, heads 5-7: 7x7 (MSTr.py:958); the largest windows first (longest items)
@@ -435,9 +491,13 @@ int launch_dwln(DwLnArgs a, int groups, bool in16, cudaStream_t st) {
   const long long total = (long long)a.B * a.H * a.W;
   if (total == 0) return 0;
   const int slots = 32 / LPT;
+  TCX_REQUIRE(total * a.C < (1ll << 31), "dwln: tensor too large for 32-bit indexing");
   a.tpw = tokens_per_warp(total, slots);
   const long long per_block = (long long)8 * slots * a.tpw;
-  dim3 grid((unsigned)((total + per_block - 1) / per_block), groups);
+  long long nblk = (total + per_block - 1) / per_block;
+  const long long cap = (long long)148 * 4 / groups > 0 ? (long long)148 * 4 / groups : 1;   // ~4 resident blocks per SM
+  if (nblk > cap) nblk = cap;
+  dim3 grid((unsigned)nblk, groups);
   const size_t smem = (size_t)12 * a.C * sizeof(float);
   ProfScope prof("dwln", st);
   bool ok = true;
@@ -494,7 +554,7 @@ int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st) {
     TCX_TRY(tcx_check_launch("mb_ctx16"));
   }
   {
-    int R = (int)(((long long)a.H * a.B * groups + 147) / 148);
+    int R = (int)(((long long)a.H * a.B * groups + 295) / 296);   // ~2 row bands per SM
     if (R < 1) R = 1;
     if (R > 8) R = 8;
     if (R > a.H) R = a.H;
@@ -509,13 +569,13 @@ int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st) {
     ProfScope prof("mb_apply16", st);
     if (a.W % 4 == 0) {
       TCX_TRY(set_smem(mb_apply16_kernel<4>, smem, "mb_apply16"));
-      mb_apply16_kernel<4><<<grid, 256, smem, st>>>(a, R);
+      mb_apply16_kernel<4><<<grid, MBA_THREADS, smem, st>>>(a, R);
     } else if (a.W % 2 == 0) {
       TCX_TRY(set_smem(mb_apply16_kernel<2>, smem, "mb_apply16"));
-      mb_apply16_kernel<2><<<grid, 256, smem, st>>>(a, R);
+      mb_apply16_kernel<2><<<grid, MBA_THREADS, smem, st>>>(a, R);
     } else {
       TCX_TRY(set_smem(mb_apply16_kernel<1>, smem, "mb_apply16"));
-      mb_apply16_kernel<1><<<grid, 256, smem, st>>>(a, R);
+      mb_apply16_kernel<1><<<grid, MBA_THREADS, smem, st>>>(a, R);
     }
     TCX_TRY(tcx_check_launch("mb_apply16"));
   }

@@ -1,4 +1,5 @@
 // Stem, bridge regroup / spatial-reduction packing, IFF pooling+gating and decoder pixel-shuffle kernels.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "misc.cuh"
 
@@ -153,6 +154,68 @@ __global__ void __launch_bounds__(256) sr_pack_ln_kernel(SrPackArgs a) {
   float* dst = a.out + row * 64;
   dst[lane] = d0 * rstd * a.lnw[lane] + a.lnb[lane];
   dst[lane + 32] = d1 * rstd * a.lnw[lane + 32] + a.lnb[lane + 32];
+}
+
+// ---- fp16 forms -------------------------------------------------------------------------------------------------
+// im2row with K ordered (ky, kx, cin): every (patch, ky) piece is r*Cin contiguous halfs of the NHWC slab -> pure
+// 16-byte vector copies (the prepared conv weight is permuted to the same K order, tcx_prepare_conv_weight_f16).
+__global__ void __launch_bounds__(256) sr_im2row16_kernel(const __half* __restrict__ x, long long xs_b, int HW, int Cin, int r,
+                                                          int B, __half* __restrict__ A) {
+  const int P = HW / r;
+  const int seg = r * Cin / 8;                       // vectors per (patch, ky) piece
+  const long long total = (long long)B * P * P * r * seg;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx % seg);
+  long long t = idx / seg;
+  const int ky = (int)(t % r); t /= r;
+  const int j = (int)(t % P); t /= P;
+  const int i = (int)(t % P);
+  const int b = (int)(t / P);
+  const uint4 val = *reinterpret_cast<const uint4*>(x + (long long)b * xs_b + ((long long)(i * r + ky) * HW + j * r) * Cin + v * 8);
+  *reinterpret_cast<uint4*>(A + (((long long)(b * P + i) * P + j) * r + ky) * (long long)(r * Cin) + v * 8) = val;
+}
+
+// [N][Cin][r][r] fp32 conv weight -> [N][(ky, kx, cin)] fp16
+__global__ void __launch_bounds__(256) conv_weight_perm16_kernel(const float* __restrict__ w, __half* __restrict__ o, int N, int Cin,
+                                                                 int r) {
+  const long long total = (long long)N * Cin * r * r;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cin = (int)(idx % Cin);
+  long long t = idx / Cin;
+  const int kx = (int)(t % r); t /= r;
+  const int ky = (int)(t % r);
+  const int n = (int)(t / r);
+  o[idx] = __float2half_rn(w[(((long long)n * Cin + cin) * r + ky) * r + kx]);
+}
+
+// pack conv outputs (fp32) + raw stage-4 tokens (fp16) into the reduced sequence, LayerNorm(64), write fp16
+__global__ void __launch_bounds__(256) sr_pack_ln16_kernel(SrPackArgs a, const __half* __restrict__ x16, __half* __restrict__ out16) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)a.B * a.nred) return;
+  const int b = (int)(row / a.nred), t = (int)(row % a.nred);
+  float v0, v1;
+  if (t >= a.red_off[3]) {
+    const __half* src = x16 + (long long)b * a.xs_b + (long long)(a.raw_tok0 + t - a.red_off[3]) * 64;
+    v0 = __half2float(src[lane]); v1 = __half2float(src[lane + 32]);
+  } else {
+    int k = 0;
+    if (t >= a.red_off[1]) k = 1;
+    if (t >= a.red_off[2]) k = 2;
+    const int g = a.gmul[k], pp = a.pp[k];
+    const int tl = t - a.red_off[k];
+    const int cm = tl / pp, s = tl % pp;
+    const float* src = a.conv[k] + ((long long)b * pp + s) * (64 * g) + cm;
+    v0 = src[lane * g]; v1 = src[(lane + 32) * g];
+  }
+  const float mean = warp_sum(v0 + v1) * (1.f / 64.f);
+  const float d0 = v0 - mean, d1 = v1 - mean;
+  const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + a.eps);
+  __half* dst = out16 + row * 64;
+  dst[lane] = __float2half_rn(d0 * rstd * a.lnw[lane] + a.lnb[lane]);
+  dst[lane + 32] = __float2half_rn(d1 * rstd * a.lnw[lane + 32] + a.lnb[lane + 32]);
 }
 
 // =====================================================================================
@@ -353,4 +416,29 @@ int launch_final_head(const float* in, int B, int H, int W, const float* lnw, co
   const long long total = (long long)B * H * 4 * W * 4;
   final_head_kernel<32><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(in, B, H, W, lnw, lnb, eps, cw, cb, ncls, out);
   return tcx_check_launch("final_head");
+}
+
+int launch_sr_im2row16(const void* x16, long long xs_b, int HW, int Cin, int r, int B, void* A16, cudaStream_t st) {
+  TCX_REQUIRE(HW % r == 0 && (r * Cin) % 8 == 0, "sr_im2row16: bad geometry HW=%d r=%d Cin=%d", HW, r, Cin);
+  const int P = HW / r;
+  const long long total = (long long)B * P * P * r * (r * Cin / 8);
+  if (total == 0) return 0;
+  sr_im2row16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x16), xs_b, HW, Cin, r, B,
+                                                                    reinterpret_cast<__half*>(A16));
+  return tcx_check_launch("sr_im2row16");
+}
+
+int launch_conv_weight_perm16(const float* w, void* o16, int N, int Cin, int r, cudaStream_t st) {
+  const long long total = (long long)N * Cin * r * r;
+  if (total == 0) return 0;
+  conv_weight_perm16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, reinterpret_cast<__half*>(o16), N, Cin, r);
+  return tcx_check_launch("conv_weight_perm16");
+}
+
+int launch_sr_pack_ln16(const SrPackArgs& a, const void* x16, void* out16, cudaStream_t st) {
+  const long long rows = (long long)a.B * a.nred;
+  if (rows == 0) return 0;
+  sr_pack_ln16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a, reinterpret_cast<const __half*>(x16),
+                                                                 reinterpret_cast<__half*>(out16));
+  return tcx_check_launch("sr_pack_ln16");
 }

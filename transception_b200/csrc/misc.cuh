@@ -29,6 +29,10 @@ struct SrPackArgs {
 };
 int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st);
 
+int launch_sr_im2row16(const void* x16, long long xs_b, int HW, int Cin, int r, int B, void* A16, cudaStream_t st);
+int launch_conv_weight_perm16(const float* w, void* o16, int N, int Cin, int r, cudaStream_t st);
+int launch_sr_pack_ln16(const SrPackArgs& a, const void* x16, void* out16, cudaStream_t st);
+
 struct IffSrc {
   const float* p[4];
 };

@@ -34,6 +34,7 @@ _PROTOS = {
     "tcx_f32_to_f16": (_i, [_vp, _vp, _ll, _vp]),
     "tcx_linear_f16_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tcx_prepare_weight_f16": (_i, [_vp, _vp, _ll, _vp]),
+    "tcx_prepare_conv_weight_f16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "tcx_forget_weight": (_i, [_vp]),
     "tcx_eff_block_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_eff_block_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -156,10 +157,14 @@ _prepared = {}
 USE_F16 = True
 
 
-def prepare_weight(w):
-    """Register an fp16 copy of a GEMM weight matrix with the library (include/transception_sm100.h)."""
+def prepare_weight(w, conv=None):
+    """Register an fp16 copy of a GEMM weight matrix with the library (include/transception_sm100.h).
+    ``conv=(N, Cin, r)``: a strided patchify conv weight, stored with its K axis permuted to (ky, kx, cin)."""
     if not USE_F16 or w is None or not w.is_cuda:
         return
+    base = w._base        # a full-size view (e.g. conv1x1 weight .reshape(C, C)) is tracked through its parameter
+    if base is not None and base.data_ptr() == w.data_ptr() and base.numel() == w.numel():
+        w = base
     key = id(w)
     ent = _prepared.get(key)
     if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
@@ -171,7 +176,10 @@ def prepare_weight(w):
     src = w.detach()
     if not src.is_contiguous():
         raise RuntimeError("transception_b200: weight matrices must be contiguous")
-    rc = lib.tcx_prepare_weight_f16(src.data_ptr(), w16.data_ptr(), w.numel(), _stream())
+    if conv is not None:
+        rc = lib.tcx_prepare_conv_weight_f16(src.data_ptr(), w16.data_ptr(), conv[0], conv[1], conv[2], _stream())
+    else:
+        rc = lib.tcx_prepare_weight_f16(src.data_ptr(), w16.data_ptr(), w.numel(), _stream())
     if rc != 0:
         raise RuntimeError("libtransception_sm100: " + lib.tcx_last_error().decode())
     ptr = w.data_ptr()
@@ -289,7 +297,7 @@ def eff_attn(xn, kw, kb, qw, qb, vw, vb, rw, rb, residual=None, reinterpret=Fals
     B, N, C = xn.shape
     y = torch.empty_like(xn)
     ws = _ws(lib.tcx_eff_attn_workspace_bytes(B, N, C), xn)
-    tab = _table([kw.reshape(C, C), kb, qw.reshape(C, C), qb, vw.reshape(C, C), vb, rw.reshape(C, C), rb])
+    tab = _table([kw.reshape(C, C), kb, qw.reshape(C, C), qb, vw.reshape(C, C), vb, rw.reshape(C, C), rb], mats=(0, 2, 4, 6))
     _chk(lib.tcx_eff_attn_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, N, C, int(reinterpret), _ptr(ws), _stream()))
     return y
 
@@ -498,7 +506,7 @@ def eff_block(x, H, W, n1w, n1b, ln_eps, attn_args, n2w, n2b, mix_args):
              n2w, n2b] + mix
     y = torch.empty_like(x)
     ws = _ws(lib.tcx_eff_block_workspace_bytes(B, N, C), x)
-    _chk(lib.tcx_eff_block_fwd(_ptr(x), _table(slots, mats=(12, 18)), ln_eps, mlp_eps, _ptr(y), B, H, W, C, _ptr(ws),
+    _chk(lib.tcx_eff_block_fwd(_ptr(x), _table(slots, mats=(2, 4, 6, 8, 12, 18)), ln_eps, mlp_eps, _ptr(y), B, H, W, C, _ptr(ws),
                                _stream()))
     return y
 
@@ -515,6 +523,12 @@ def bridge_layer(x, n1w, n1b, ln_eps, channel_att, attn_slots, scale, n2w, n2b, 
     for a in mix_args_list:
         slots.extend(_mix_slots(a)[0])
     mats = [18 + 8 * k + j for k in range(4) for j in (0, 6)]
+    if channel_att:
+        mats += [2, 4, 6, 8]
+    else:
+        mats += [2, 4, 6]
+        for k, (cin, r) in enumerate(((64, 8), (128, 4), (320, 2))):
+            prepare_weight(slots[8 + 2 * k], conv=(cin, cin, r))
     y = torch.empty_like(x)
     ws = _ws(lib.tcx_bridge_layer_workspace_bytes(B, S), x)
     _chk(lib.tcx_bridge_layer_fwd(_ptr(x), _table(slots, mats), int(channel_att), scale, ln_eps, _ptr(y), B, S,
