@@ -59,6 +59,7 @@ void tcx_prof_end(const char* name, cudaStream_t st) {
 static int g_flag_gemm_tc = 1;
 static int g_flag_flash_tc = 1;
 static int g_flag_f16 = 1;
+int g_tcx_pdl = 1;
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
 bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
 
@@ -227,6 +228,51 @@ size_t scale_reduce_ws_floats(int B, const BridgeGeom& g) {
 }
 
 
+// ---- fork / join onto auxiliary streams ---------------------------------------------------------------------------
+// Independent kernel chains of one forward (the four per-scale Mix-FFNs of a bridge layer, the three spatial-reduction
+// convolutions) are enqueued on per-device auxiliary streams between a fork and a join event.  Eagerly they overlap on
+// the GPU; under stream capture the events become fork/join edges, so the replayed CUDA graph has parallel branches.
+constexpr int TCX_AUX = 3;
+struct AuxStreams {
+  cudaStream_t s[TCX_AUX] = {};
+  cudaEvent_t fork = nullptr, join[TCX_AUX] = {};
+  bool ok = false;
+};
+static std::mutex g_aux_mu;
+static std::unordered_map<int, AuxStreams> g_aux;
+static int g_flag_fork = 1;
+AuxStreams* aux_streams() {
+  if (!g_flag_fork) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  AuxStreams& a = g_aux[dev];
+  if (!a.ok) {
+    bool good = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < TCX_AUX && good; i++)
+      good = cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) { cudaGetLastError(); return nullptr; }
+    a.ok = true;
+  }
+  return &a;
+}
+// aux streams [0, n) start after everything enqueued on `st` so far
+inline int fork_streams(AuxStreams* a, cudaStream_t st, int n) {
+  if (cudaEventRecord(a->fork, st) != cudaSuccess) { tcx_set_error("fork: cudaEventRecord failed"); return -1; }
+  for (int i = 0; i < n; i++)
+    if (cudaStreamWaitEvent(a->s[i], a->fork, 0) != cudaSuccess) { tcx_set_error("fork: cudaStreamWaitEvent failed"); return -1; }
+  return 0;
+}
+// `waiter` continues after everything enqueued on aux stream i
+inline int join_stream(AuxStreams* a, int i, cudaStream_t waiter) {
+  if (cudaEventRecord(a->join[i], a->s[i]) != cudaSuccess || cudaStreamWaitEvent(waiter, a->join[i], 0) != cudaSuccess) {
+    tcx_set_error("join: event record/wait failed");
+    return -1;
+  }
+  return 0;
+}
+
 // ---- fp16-intermediate pipeline ---------------------------------------------------------------------------------
 inline __half* H16(float* p) { return reinterpret_cast<__half*>(p); }
 
@@ -354,6 +400,10 @@ int run_bridge_sr_attn16(const __half* xn16, const void* const* p, float scale, 
   __half* kv = H16(c.take((size_t)B * g.nred * 64 + 64));
   float* fws = c.take(flash_tc_workspace_bytes(B, g.nred) / 4 + 64);
   const int M = B * g.ntok;
+  // q projection on st; the reduced-token chain (3 patchify convs in parallel -> pack+LN -> kv projection) on aux streams
+  AuxStreams* aux = aux_streams();
+  if (aux) TCX_TRY(fork_streams(aux, st, 3));
+  cudaStream_t s0 = aux ? aux->s[0] : st;
   {
     GemmParams gq = gemm1(F(xn16), F(w16_of(p[0])), reinterpret_cast<float*>(q), M, 64, 64);
     gq.ab16 = 1; gq.out16 = 1;
@@ -369,25 +419,28 @@ int run_bridge_sr_attn16(const __half* xn16, const void* const* p, float scale, 
       const int K = Cin * r * r, Mk = B * g.pp;
       __half* A = H16(c.take((size_t)Mk * K / 2 + 64));
       float* conv = c.take((size_t)Mk * Cin);
-      TCX_TRY(launch_sr_im2row16(xn16 + (long long)g.off[k] * 64, xs_b, g.hw[k], Cin, r, B, A, st));
+      cudaStream_t sk = aux ? aux->s[k] : st;
+      TCX_TRY(launch_sr_im2row16(xn16 + (long long)g.off[k] * 64, xs_b, g.hw[k], Cin, r, B, A, sk));
       GemmParams gp = gemm1(F(A), F(w16_of(p[6 + 2 * k])), conv, Mk, Cin, K);
       gp.ab16 = 1;
       gp.g[0].epi.bias = F(p[7 + 2 * k]);
-      TCX_TRY(launch_gemm(gp, st));
+      TCX_TRY(launch_gemm(gp, sk));
       a.conv[k] = conv; a.gmul[k] = Cin / 64; a.pp[k] = g.pp;
     }
+    if (aux) { TCX_TRY(join_stream(aux, 1, s0)); TCX_TRY(join_stream(aux, 2, s0)); }
     a.x = nullptr; a.xs_b = xs_b; a.raw_tok0 = g.off[3];
     for (int i = 0; i < 4; i++) a.red_off[i] = g.red_off[i];
     a.nred = g.nred; a.B = B;
     a.lnw = F(p[12]); a.lnb = F(p[13]); a.eps = ln_eps; a.out = nullptr;
-    TCX_TRY(launch_sr_pack_ln16(a, xn16, red, st));
+    TCX_TRY(launch_sr_pack_ln16(a, xn16, red, s0));
   }
   {
     GemmParams gk = gemm1(F(red), F(w16_of(p[2])), reinterpret_cast<float*>(kv), B * g.nred, 128, 64);
     gk.ab16 = 1; gk.out16 = 1;
     gk.g[0].epi.bias = F(p[3]);
-    TCX_TRY(launch_gemm(gk, st));
+    TCX_TRY(launch_gemm(gk, s0));
   }
+  if (aux) TCX_TRY(join_stream(aux, 0, st));
   TCX_TRY(launch_flash_tc16(q, kv, o, B, g.ntok, g.nred, scale, fws, st));
   GemmParams gp = gemm1(F(o), F(w16_of(p[4])), y, M, 64, 64);
   gp.ab16 = 1;
@@ -444,6 +497,8 @@ int tcx_set_flag(const char* name, int value) {
   if (!strcmp(name, "gemm_tc")) f = &g_flag_gemm_tc;
   else if (!strcmp(name, "flash_tc")) f = &g_flag_flash_tc;
   else if (!strcmp(name, "f16_pipeline")) f = &g_flag_f16;
+  else if (!strcmp(name, "fork")) f = &g_flag_fork;
+  else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
   *f = value;
@@ -902,7 +957,9 @@ static int bridge_mixffn16(const __half* tx16, const float* tx1, const void* con
                            const BridgeGeom& g, float* ws, cudaStream_t st) {
   Carver c(ws);
   const long long sb = (long long)g.ntok * 64;
-  for (int k = 0; k < 4; k++) {
+  AuxStreams* aux = aux_streams();
+  if (aux) TCX_TRY(fork_streams(aux, st, 3));
+  for (int k = 0; k < 4; k++) {       // the four scales are independent chains: scale 0 on st, 1..3 on aux streams
     const int hw = g.hw[k], C = g.ch[k], C4 = 4 * C, Mi = hw * hw;
     __half* h = H16(c.take((size_t)B * Mi * C4 / 2));
     __half* a = H16(c.take((size_t)B * Mi * C4 / 2));
@@ -910,8 +967,11 @@ static int bridge_mixffn16(const __half* tx16, const float* tx1, const void* con
     Mix16 m{};
     TCX_REQUIRE(mix16_fill(p + 8 * k, m), "bridge_mixffn16: weights of scale %d are not prepared", k);
     m.xn = tx16 + off; m.xn_bs = sb; m.res = tx1 + off; m.res_bs = sb; m.y = y + off; m.y_bs = sb;
-    TCX_TRY(run_mixffn16(1, &m, ln_eps, B, hw, hw, C, C4, h, a, st));
+    cudaStream_t sk = (aux && k > 0) ? aux->s[k - 1] : st;
+    TCX_TRY(run_mixffn16(1, &m, ln_eps, B, hw, hw, C, C4, h, a, sk));
   }
+  if (aux)
+    for (int k = 0; k < 3; k++) TCX_TRY(join_stream(aux, k, st));
   return 0;
 }
 static bool bridge_mix_prepared(const void* const* p) {

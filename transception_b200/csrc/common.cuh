@@ -22,6 +22,30 @@ struct ProfScope {
   ~ProfScope() { if (g_tcx_prof_on) tcx_prof_end(name, st); }
 };
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// Kernels of the fp16 pipeline are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel calls
+// pdl_trigger() at its top (the next kernel in the stream may then be scheduled as SMs free up) and pdl_wait() before
+// its first access to activations / workspace (blocks until the preceding kernel has completed and flushed).  Only
+// module parameters and prepared weights — never written inside a forward — may be read before pdl_wait(), so a
+// kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch, filter staging) overlaps its predecessor's
+// tail.  Both instructions are no-ops for a kernel launched without the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+extern int g_tcx_pdl;   // flag "pdl" (default 1)
+template <typename... KArgs, typename... Args>
+inline cudaError_t tcx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_tcx_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define TCX_TRY(expr)                       \
   do {                                      \
     int _e = (expr);                        \

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) ea16_ctx_partial_kernel(Ea16View v, int N
   __shared__ __align__(16) __half V[EA_T * EA_VP];
   __shared__ float red[4][64];
   __shared__ float mx[64];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, b = blockIdx.y;
   const int tiles = C >> 6;
   const int tk = blockIdx.z / tiles, tv = blockIdx.z % tiles;
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(256) ea16_ctx_partial_kernel(Ea16View v, int N
 __global__ void __launch_bounds__(256) ea16_ctx_combine_kernel(const float* __restrict__ part_ctx, const float* __restrict__ part_m,
                                                                const float* __restrict__ part_s, int nchunks, int C,
                                                                __half* __restrict__ ctxT) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= C * C) return;
@@ -159,6 +163,8 @@ template <int LPT, int NV>
 __global__ void __launch_bounds__(256) ea16_qsoftmax_kernel(const __half* __restrict__ q, int ldt, long long total, int C,
                                                             __half* __restrict__ dst) {
   constexpr int SLOTS = 32 / LPT;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int slot = lane / LPT, sl = lane % LPT;
   const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * SLOTS + slot;
@@ -199,6 +205,8 @@ __global__ void __launch_bounds__(256) ea16_qsoftmax_kernel(const __half* __rest
 __global__ void __launch_bounds__(256) ea16_qsoftmax_reint_kernel(const __half* __restrict__ q, long long sb, int N,
                                                                   __half* __restrict__ dst) {
   __shared__ float t[64][65];   // [c][n_local]
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, n0 = blockIdx.x * 64, tid = threadIdx.x;
   const __half* __restrict__ qb = q + (long long)b * sb;
   for (int i = tid; i < 64 * 16; i += 256) {
@@ -259,11 +267,11 @@ int launch_ea16_context(const Ea16View& v, int B, int N, int C, float* ws, __hal
   const int tiles = C / 64;
   dim3 grid(nchunks, B, tiles * tiles);
   ProfScope prof("ea16_ctx", st);
-  if (v.reint) ea16_ctx_partial_kernel<true><<<grid, 256, 0, st>>>(v, N, C, part_ctx, part_m, part_s);
-  else ea16_ctx_partial_kernel<false><<<grid, 256, 0, st>>>(v, N, C, part_ctx, part_m, part_s);
+  if (v.reint) tcx_launch_pdl(ea16_ctx_partial_kernel<true>, grid, dim3(256), 0, st, v, N, C, part_ctx, part_m, part_s);
+  else tcx_launch_pdl(ea16_ctx_partial_kernel<false>, grid, dim3(256), 0, st, v, N, C, part_ctx, part_m, part_s);
   TCX_TRY(tcx_check_launch("ea16_ctx_partial"));
   dim3 g2(cdiv(C * C, 256), B);
-  ea16_ctx_combine_kernel<<<g2, 256, 0, st>>>(part_ctx, part_m, part_s, nchunks, C, ctxT);
+  tcx_launch_pdl(ea16_ctx_combine_kernel, g2, dim3(256), 0, st, part_ctx, part_m, part_s, nchunks, C, ctxT);
   return tcx_check_launch("ea16_ctx_combine");
 }
 
@@ -271,7 +279,7 @@ int launch_ea16_qsoftmax(const Ea16View& v, int B, int N, int C, __half* dst, cu
   if (v.reint) {
     TCX_REQUIRE(C == 64 && N % 4 == 0, "eff_attn16(reinterpret): needs C == 64 and N %% 4 == 0");
     dim3 grid(cdiv(N, 64), B);
-    ea16_qsoftmax_reint_kernel<<<grid, 256, 0, st>>>(v.q, v.sb, N, dst);
+    tcx_launch_pdl(ea16_qsoftmax_reint_kernel, grid, dim3(256), 0, st, v.q, v.sb, N, dst);
     return tcx_check_launch("ea16_qsoftmax_reint");
   }
   const long long total = (long long)B * N;
@@ -283,11 +291,11 @@ int launch_ea16_qsoftmax(const Ea16View& v, int B, int N, int C, __half* dst, cu
   const int NV = nv8 / LPT;
   const long long per_block = 8 * (32 / LPT);
   const unsigned grid = (unsigned)((total + per_block - 1) / per_block);
-  if (LPT == 8 && NV == 1) ea16_qsoftmax_kernel<8, 1><<<grid, 256, 0, st>>>(v.q, v.ldt, total, C, dst);
-  else if (LPT == 8 && NV == 5) ea16_qsoftmax_kernel<8, 5><<<grid, 256, 0, st>>>(v.q, v.ldt, total, C, dst);
-  else if (LPT == 16 && NV == 1) ea16_qsoftmax_kernel<16, 1><<<grid, 256, 0, st>>>(v.q, v.ldt, total, C, dst);
-  else if (LPT == 32 && NV == 1) ea16_qsoftmax_kernel<32, 1><<<grid, 256, 0, st>>>(v.q, v.ldt, total, C, dst);
-  else if (LPT == 32 && NV == 2) ea16_qsoftmax_kernel<32, 2><<<grid, 256, 0, st>>>(v.q, v.ldt, total, C, dst);
+  if (LPT == 8 && NV == 1) tcx_launch_pdl(ea16_qsoftmax_kernel<8, 1>, dim3(grid), dim3(256), 0, st, v.q, v.ldt, total, C, dst);
+  else if (LPT == 8 && NV == 5) tcx_launch_pdl(ea16_qsoftmax_kernel<8, 5>, dim3(grid), dim3(256), 0, st, v.q, v.ldt, total, C, dst);
+  else if (LPT == 16 && NV == 1) tcx_launch_pdl(ea16_qsoftmax_kernel<16, 1>, dim3(grid), dim3(256), 0, st, v.q, v.ldt, total, C, dst);
+  else if (LPT == 32 && NV == 1) tcx_launch_pdl(ea16_qsoftmax_kernel<32, 1>, dim3(grid), dim3(256), 0, st, v.q, v.ldt, total, C, dst);
+  else if (LPT == 32 && NV == 2) tcx_launch_pdl(ea16_qsoftmax_kernel<32, 2>, dim3(grid), dim3(256), 0, st, v.q, v.ldt, total, C, dst);
   else { tcx_set_error("eff_attn16: unsupported channel count %d", C); return -1; }
   return tcx_check_launch("ea16_qsoftmax");
 }

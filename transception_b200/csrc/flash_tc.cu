@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   uint64_t* s_free = o_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = (Nq + FT_BM - 1) / FT_BM;
   const int pairs_per_img = (tiles_per_img + 1) / 2;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // register redistribution (the service warpgroup gives registers to the two softmax warpgroups); issued inside the
   // role branches so that ptxas allocates each region against its own budget.  The pool is the CTA's launch allocation
@@ -360,6 +362,8 @@ __global__ void __launch_bounds__(256) flash_pack_kv_kernel(const float* __restr
 __global__ void __launch_bounds__(256) flash_pack_vt16_kernel(const __half* __restrict__ kv, __half* __restrict__ vt16, int Nk,
                                                               int Nkp) {
   __shared__ __half vs[32][66];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, n0 = blockIdx.x * 32, tid = threadIdx.x;
   const __half* __restrict__ src = kv + ((long long)b * Nk + n0) * 128 + 64;
   {
@@ -405,8 +409,10 @@ static int flash_tc_launch(const FlashMaps& maps, const void* q, void* out, int 
   const int npairs = B * ((tiles_per_img + 1) / 2);
   const float qscale = scale * 1.4426950408889634f;
   ProfScope prof("flash_tc", st);
-  if (f16io) flash_tc_kernel<true, true><<<min(npairs, sms), FT_THREADS, FT_SMEM, st>>>(maps, q, out, B, Nq, Nk, qscale);
-  else flash_tc_kernel<false, false><<<min(npairs, sms), FT_THREADS, FT_SMEM, st>>>(maps, q, out, B, Nq, Nk, qscale);
+  cudaError_t le;
+  if (f16io) le = tcx_launch_pdl(flash_tc_kernel<true, true>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, B, Nq, Nk, qscale);
+  else le = tcx_launch_pdl(flash_tc_kernel<false, false>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, B, Nq, Nk, qscale);
+  TCX_REQUIRE(le == cudaSuccess, "flash_tc: launch failed: %s", cudaGetErrorString(le));
   return tcx_check_launch("flash_tc");
 }
 
@@ -435,7 +441,7 @@ int launch_flash_tc16(const void* q16, const void* kv16, void* out16, int B, int
   __half* vt16 = reinterpret_cast<__half*>(ws);
   {
     dim3 grid(cdiv(Nkp, 32), B);
-    flash_pack_vt16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(kv16), vt16, Nk, Nkp);
+    tcx_launch_pdl(flash_pack_vt16_kernel, grid, dim3(256), 0, st, reinterpret_cast<const __half*>(kv16), vt16, Nk, Nkp);
     TCX_TRY(tcx_check_launch("flash_pack_vt16"));
   }
   FlashMaps maps;

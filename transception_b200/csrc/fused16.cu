@@ -67,88 +67,122 @@ template <bool IN16, int LPT, int NV>
 __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
   constexpr int VEC = IN16 ? 8 : 4;
   constexpr int SLOTS = 32 / LPT;
+  constexpr int C = LPT * VEC * NV;          // the row width is fixed by the instantiation: all offsets are immediates
+  using elem_t = typename std::conditional<IN16, __half, float>::type;
+  using vec_t = typename std::conditional<IN16, uint4, float4>::type;
   extern __shared__ float wsm[];            // [9][C] taps (centre + 1 = skip), then bias[C], lnw[C], lnb[C] (permuted)
   const DwLnGroup& g = a.g[blockIdx.y];
-  const int C = a.C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 9 * C; i += 256) {
-    const int c = i / 9, t = i - c * 9;
-    wsm[t * C + wperm<LPT, VEC>(c)] = g.dww[i] + (t == 4 ? 1.f : 0.f);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  // (filters, bias and LN affine are module parameters: staged before pdl_wait, overlapping the previous kernel)
+  // staging: loads are issued in batches of 8 before the dependent smem stores, so a thread has 8 requests in flight
+  // (a one-load-per-iteration loop costs one L2 round trip per element and dominated the small-map launches)
+  constexpr int NB = 8;
+  for (int i0 = tid; i0 < 9 * C; i0 += 256 * NB) {
+    float v[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) { const int i = i0 + j * 256; v[j] = i < 9 * C ? __ldg(g.dww + i) : 0.f; }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int i = i0 + j * 256;
+      if (i < 9 * C) { const int c = i / 9, t = i - c * 9; wsm[t * C + wperm<LPT, VEC>(c)] = v[j] + (t == 4 ? 1.f : 0.f); }
+    }
   }
   float* bsm = wsm + 9 * C;
-  for (int i = tid; i < C; i += 256) {
-    const int pc = wperm<LPT, VEC>(i);
-    bsm[pc] = g.dwb ? g.dwb[i] : 0.f;
-    bsm[C + pc] = g.lnw[i];
-    bsm[2 * C + pc] = g.lnb[i];
+  {
+    constexpr int PER = (C + 255) / 256;
+    float vb[PER], vw[PER], vl[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const int i = tid + j * 256;
+      vb[j] = (g.dwb && i < C) ? __ldg(g.dwb + i) : 0.f;
+      vw[j] = i < C ? __ldg(g.lnw + i) : 0.f;
+      vl[j] = i < C ? __ldg(g.lnb + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const int i = tid + j * 256;
+      if (i < C) { const int pc = wperm<LPT, VEC>(i); bsm[pc] = vb[j]; bsm[C + pc] = vw[j]; bsm[2 * C + pc] = vl[j]; }
+    }
   }
   __syncthreads();
+  pdl_wait();
   const int slot = lane / LPT, sl = lane % LPT;
   const int total = a.B * a.H * a.W;
   const int H = a.H, W = a.W;
-  const float invC = 1.f / (float)C;
+  constexpr float invC = 1.f / (float)C;
   const int chunk = SLOTS * a.tpw;                       // consecutive tokens per warp visit
   const int nchunks = (total + chunk - 1) / chunk;
+  const float* wl = wsm + sl * 4;                        // this lane's slice of every per-channel smem vector
+  const float* bl = bsm + sl * 4;
+  const elem_t* __restrict__ xin = reinterpret_cast<const elem_t*>(g.x) + sl * VEC;
+  const ptrdiff_t rowpitch = (ptrdiff_t)W * C;
+  // the 9 taps of channel vector i of one token: [row pointer + immediate] under a predicate, so the loads are
+  // independent and all in flight together; out-of-map taps read nothing and stay zero
+  auto load9 = [&](int tok, int wq, int hq, int i, vec_t (&raw)[9]) {
+    const bool live = tok < total;
+    const elem_t* pc = xin + (size_t)(live ? tok : 0) * C + i * LPT * VEC;
+    const elem_t* prow[3] = {pc - rowpitch, pc, pc + rowpitch};
+    const bool rv[3] = {live && hq > 0, live, live && hq + 1 < H};
+    const bool cv[3] = {wq > 0, true, wq + 1 < W};
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int ky = t / 3, kx = t % 3;
+      if (IN16) *reinterpret_cast<uint4*>(&raw[t]) = make_uint4(0u, 0u, 0u, 0u);
+      else *reinterpret_cast<float4*>(&raw[t]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rv[ky] && cv[kx]) raw[t] = *reinterpret_cast<const vec_t*>(prow[ky] + (kx - 1) * C);
+    }
+  };
   for (int ch = blockIdx.x * 8 + warp; ch < nchunks; ch += gridDim.x * 8) {
     const int base = ch * chunk;
     int tok = base + slot;
     int wq = tok % W, hq = (tok / W) % H;
+    vec_t cur[9], nxt[9];
+    load9(tok, wq, hq, 0, cur);
     for (int it = 0; it < a.tpw; it++, tok += SLOTS) {
       if (base + it * SLOTS >= total) break;             // warp-uniform
       const bool live = tok < total;
+      // position of this slot's next token (SLOTS further along the row-major token order)
+      int wn = wq + SLOTS, hn = hq;
+      if (wn >= W) { wn -= W; if (++hn >= H) hn = 0; }
       float acc[NV][VEC];
 #pragma unroll
       for (int i = 0; i < NV; i++) {
 #pragma unroll
         for (int q = 0; q < VEC / 4; q++) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bsm + i * LPT * VEC + q * LPT * 4 + sl * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(bl + i * LPT * VEC + q * LPT * 4);
           acc[i][q * 4 + 0] = b4.x; acc[i][q * 4 + 1] = b4.y; acc[i][q * 4 + 2] = b4.z; acc[i][q * 4 + 3] = b4.w;
         }
       }
-      const size_t row0 = (size_t)(live ? tok : 0) * C + sl * VEC;
-      // branch-free taps: every load is issued (out-of-map neighbours read the centre row and are zeroed), so the
-      // 9 x NV loads of a token are all in flight together
-      const bool rv0 = hq > 0, rv2 = hq + 1 < H, cv0 = wq > 0, cv2 = wq + 1 < W;
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        // the 9 taps of one 16-byte channel vector: loads first (all in flight), then the FMAs
-        typename std::conditional<IN16, uint4, float4>::type raw[9];
+        // software pipeline: the next batch (next channel vector, or the first one of the next token) is requested
+        // before this one is consumed
+        if (i + 1 < NV) load9(tok, wq, hq, i + 1, nxt);
+        else if (it + 1 < a.tpw) load9(tok + SLOTS, wn, hn, 0, nxt);
 #pragma unroll
         for (int t = 0; t < 9; t++) {
-          const int ky = t / 3, kx = t % 3;
-          const bool valid = live && (ky == 0 ? rv0 : (ky == 2 ? rv2 : true)) && (kx == 0 ? cv0 : (kx == 2 ? cv2 : true));
-          const size_t nb = (valid ? row0 + (ptrdiff_t)((ky - 1) * W + (kx - 1)) * C : row0) + i * LPT * VEC;
-          if (IN16) {
-            uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(g.x) + nb);
-            if (!valid) r = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(&raw[t]) = r;
-          } else {
-            float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.x) + nb);
-            if (!valid) r = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(&raw[t]) = r;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 9; t++) {
-          const float* wt = wsm + t * C + sl * 4 + i * LPT * VEC;
           float xv[VEC];
           if (IN16) {
             float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(&raw[t]), f);
+            unpack8(*reinterpret_cast<const uint4*>(&cur[t]), f);
 #pragma unroll
             for (int j = 0; j < VEC; j++) xv[j] = f[j];
           } else {
-            const float4 r = *reinterpret_cast<const float4*>(&raw[t]);
+            const float4 r = *reinterpret_cast<const float4*>(&cur[t]);
             xv[0] = r.x; xv[1] = r.y; xv[2] = r.z; xv[3] = r.w;
           }
 #pragma unroll
           for (int q = 0; q < VEC / 4; q++) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + q * LPT * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(wl + t * C + i * LPT * VEC + q * LPT * 4);
             acc[i][q * 4 + 0] = fmaf(xv[q * 4 + 0], w4.x, acc[i][q * 4 + 0]);
             acc[i][q * 4 + 1] = fmaf(xv[q * 4 + 1], w4.y, acc[i][q * 4 + 1]);
             acc[i][q * 4 + 2] = fmaf(xv[q * 4 + 2], w4.z, acc[i][q * 4 + 2]);
             acc[i][q * 4 + 3] = fmaf(xv[q * 4 + 3], w4.w, acc[i][q * 4 + 3]);
           }
         }
+#pragma unroll
+        for (int t = 0; t < 9; t++) cur[t] = nxt[t];
       }
       float s = 0.f;
 #pragma unroll
@@ -163,20 +197,20 @@ __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
         for (int j = 0; j < VEC; j++) { const float d = acc[i][j] - mean; q2 = fmaf(d, d, q2); }
       const float rstd = rsqrtf(seg_sum<LPT>(q2) * invC + a.eps);
       if (live) {
+        const size_t off0 = (size_t)tok * C + sl * VEC;
 #pragma unroll
         for (int i = 0; i < NV; i++) {
-          const size_t off = (size_t)tok * C + sl * VEC + i * LPT * VEC;
           if (g.u) {
 #pragma unroll
             for (int q = 0; q < VEC / 4; q++)
-              *reinterpret_cast<float4*>(g.u + off + q * 4) =
+              *reinterpret_cast<float4*>(g.u + off0 + i * LPT * VEC + q * 4) =
                   make_float4(acc[i][q * 4], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
           }
           float o[VEC];
 #pragma unroll
           for (int q = 0; q < VEC / 4; q++) {
-            const float4 w4 = *reinterpret_cast<const float4*>(bsm + C + i * LPT * VEC + q * LPT * 4 + sl * 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(bsm + 2 * C + i * LPT * VEC + q * LPT * 4 + sl * 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(bl + C + i * LPT * VEC + q * LPT * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bl + 2 * C + i * LPT * VEC + q * LPT * 4);
             o[q * 4 + 0] = fmaf((acc[i][q * 4 + 0] - mean) * rstd, w4.x, b4.x);
             o[q * 4 + 1] = fmaf((acc[i][q * 4 + 1] - mean) * rstd, w4.y, b4.y);
             o[q * 4 + 2] = fmaf((acc[i][q * 4 + 2] - mean) * rstd, w4.z, b4.z);
@@ -186,7 +220,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
 #pragma unroll
             for (int j = 0; j < VEC; j++) o[j] = gelu_fast(o[j]);
           }
-          __half* yp = g.y + off;
+          __half* yp = g.y + off0 + i * LPT * VEC;
           if (VEC == 8) {
             *reinterpret_cast<uint4*>(yp) = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[VEC - 4], o[VEC - 3]),
                                                        pack2(o[VEC - 2], o[VEC - 1]));
@@ -195,9 +229,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
           }
         }
       }
-      // next token of this slot: SLOTS further along the row-major token order
-      wq += SLOTS;
-      if (wq >= W) { wq -= W; if (++hq >= H) hq = 0; }
+      wq = wn; hq = hn;
     }
   }
 }
@@ -213,12 +245,14 @@ __global__ void __launch_bounds__(256) ln16_kernel(const Ln16Args a) {
   const int slot = lane / LPT, sl = lane % LPT;
   const long long base = ((long long)blockIdx.x * 8 + warp) * (SLOTS * a.tpw);
   const float invC = 1.f / (float)C;
+  pdl_trigger();
   float4 wv[NV], bv[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) {
     wv[i] = *reinterpret_cast<const float4*>(g.w + (sl + i * LPT) * 4);
     bv[i] = *reinterpret_cast<const float4*>(g.b + (sl + i * LPT) * 4);
   }
+  pdl_wait();
   for (int it = 0; it < a.tpw; it++) {
     const long long row = base + (long long)it * SLOTS + slot;
     if (base + (long long)it * SLOTS >= a.M) break;
@@ -264,6 +298,8 @@ __global__ void __launch_bounds__(256) mb_ctx16_kernel(const Mb16Args a) {
   float* ss = mx + Ch;                  // [Ch]
   float* cacc = ss + Ch;                // [Ch*Ch]
   const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y, gi = blockIdx.z;
+  pdl_trigger();
+  pdl_wait();
   const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
   const int vpr = Ch / 8;               // 16-byte vectors per row slice
   for (int i = tid; i < N * vpr * 2; i += 256) {
@@ -419,6 +455,13 @@ __global__ void __launch_bounds__(MBA_THREADS) mb_apply16_kernel(const Mb16Args 
   float* w5 = w3 + 9 * c3;                                         // [25][c5]
   float* w7 = w5 + 25 * c5;                                        // [49][c7]
   float* bs = w7 + 49 * c7;                                        // [C]
+  pdl_trigger();
+  // conv filters and biases are module parameters: staged before pdl_wait (overlaps the previous kernel)
+  for (int i = tid; i < 9 * c3; i += MBA_THREADS) { const int ch = i / 9, t = i - ch * 9; w3[t * c3 + ch] = a.cw[gi][0][i]; }
+  for (int i = tid; i < 25 * c5; i += MBA_THREADS) { const int ch = i / 25, t = i - ch * 25; w5[t * c5 + ch] = a.cw[gi][1][i]; }
+  for (int i = tid; i < 49 * c7; i += MBA_THREADS) { const int ch = i / 49, t = i - ch * 49; w7[t * c7 + ch] = a.cw[gi][2][i]; }
+  for (int i = tid; i < C; i += MBA_THREADS) bs[i] = i < c3 ? a.cb[gi][0][i] : (i < c3 + c5 ? a.cb[gi][1][i - c3] : a.cb[gi][2][i - c3 - c5]);
+  pdl_wait();
   const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
   const int vpr = C / 8;
   const float inv_vpr = 1.0f / (float)vpr, inv_w = 1.0f / (float)W;
@@ -439,10 +482,6 @@ __global__ void __launch_bounds__(MBA_THREADS) mb_apply16_kernel(const Mb16Args 
   const float* __restrict__ cg = a.ctx[gi] + (long long)b * C * Ch;
   for (int i = tid; i < C * Ch / 4; i += MBA_THREADS)
     reinterpret_cast<float4*>(ctx)[i] = reinterpret_cast<const float4*>(cg)[i];
-  for (int i = tid; i < 9 * c3; i += MBA_THREADS) { const int ch = i / 9, t = i - ch * 9; w3[t * c3 + ch] = a.cw[gi][0][i]; }
-  for (int i = tid; i < 25 * c5; i += MBA_THREADS) { const int ch = i / 25, t = i - ch * 25; w5[t * c5 + ch] = a.cw[gi][1][i]; }
-  for (int i = tid; i < 49 * c7; i += MBA_THREADS) { const int ch = i / 49, t = i - ch * 49; w7[t * c7 + ch] = a.cw[gi][2][i]; }
-  for (int i = tid; i < C; i += MBA_THREADS) bs[i] = i < c3 ? a.cb[gi][0][i] : (i < c3 + c5 ? a.cb[gi][1][i - c3] : a.cb[gi][2][i - c3 - c5]);
   __syncthreads();
   __half* __restrict__ outp = a.out[gi] + ((long long)b * N + (long long)r0 * W) * C;
   // heads 0-1: 3x3, heads 2-4: 5x5, heads 5-7: 7x7 (MSTr.py:958); the largest windows first (longest items)
@@ -452,6 +491,189 @@ __global__ void __launch_bounds__(MBA_THREADS) mb_apply16_kernel(const Mb16Args 
 }
 
 // opt in to > 48 KB of dynamic shared memory, once per kernel (keyed by the function address)
+// ------------------------------------------------------------------------------------------------------------------
+// Fused Multi-Branch attention, one block per (head, image, branch): column softmax of K over the tokens, the Ch x Ch
+// context, the factorized-attention product and the conv relative position encoding of that head's channels, all from
+// one shared-memory copy of the head's q / k / v slices (the whole H x W map of a head fits: <= 50 KB at 28 x 28).
+// The window size is uniform inside a block (heads 0-1: 3x3, 2-4: 5x5, 5-7: 7x7, MSTr.py:958).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int MBF_THREADS = 256;
+
+template <int WIN, int T>
+__device__ __forceinline__ void mbf_apply(const __half* __restrict__ qs, const __half* __restrict__ vs, const float* __restrict__ ctx,
+                                          const float* __restrict__ wt, const float* __restrict__ bs, __half* __restrict__ outp,
+                                          int H, int W, int C, int Ch, int CHP, int tid) {
+  constexpr int R = WIN / 2;
+  const int np = Ch / 2, xg_n = W / T;
+  const int items = H * xg_n * np;
+  const float inv_np = 1.0f / (float)np, inv_xg = 1.0f / (float)xg_n;
+  for (int i = tid; i < items; i += MBF_THREADS) {
+    const int i1 = fdiv(i, inv_np), p = i - i1 * np;
+    const int y = fdiv(i1, inv_xg), xg = i1 - y * xg_n;
+    const int c = 2 * p, x0 = xg * T;
+    float v0[T], v1[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) { v0[t] = bs[c]; v1[t] = bs[c + 1]; }
+#pragma unroll
+    for (int ky = 0; ky < WIN; ky++) {
+      const int yy = y + ky - R;
+      if (yy < 0 || yy >= H) continue;
+      const __half* vrow = vs + (size_t)(yy * W) * CHP + c;
+      float2 win[T + WIN - 1];
+#pragma unroll
+      for (int j = 0; j < T + WIN - 1; j++) {
+        const int xx = x0 + j - R;
+        win[j] = (xx >= 0 && xx < W) ? __half22float2(*reinterpret_cast<const __half2*>(vrow + (size_t)xx * CHP))
+                                     : make_float2(0.f, 0.f);
+      }
+      const float* wrow = wt + (size_t)(ky * WIN) * Ch + c;
+#pragma unroll
+      for (int kx = 0; kx < WIN; kx++) {
+        const float2 ww = *reinterpret_cast<const float2*>(wrow + (size_t)kx * Ch);
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          v0[t] = fmaf(win[t + kx].x, ww.x, v0[t]);
+          v1[t] = fmaf(win[t + kx].y, ww.y, v1[t]);
+        }
+      }
+    }
+    float f0[T], f1[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) { f0[t] = 0.f; f1[t] = 0.f; }
+    const __half* qbase = qs + (size_t)(y * W + x0) * CHP;
+    for (int k = 0; k < Ch; k += 2) {
+      const float2 ca = *reinterpret_cast<const float2*>(ctx + (size_t)k * Ch + c);
+      const float2 cb = *reinterpret_cast<const float2*>(ctx + (size_t)(k + 1) * Ch + c);
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        const float2 q2 = __half22float2(*reinterpret_cast<const __half2*>(qbase + (size_t)t * CHP + k));
+        f0[t] = fmaf(q2.x, ca.x, f0[t]); f1[t] = fmaf(q2.x, ca.y, f1[t]);
+        f0[t] = fmaf(q2.y, cb.x, f0[t]); f1[t] = fmaf(q2.y, cb.y, f1[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      const float2 qc = __half22float2(*reinterpret_cast<const __half2*>(qbase + (size_t)t * CHP + c));
+      *reinterpret_cast<uint32_t*>(outp + (size_t)(y * W + x0 + t) * C + c) = pack2(fmaf(qc.x, v0[t], f0[t]), fmaf(qc.y, v1[t], f1[t]));
+    }
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(MBF_THREADS) mb_fused16_kernel(const Mb16Args a) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int H = a.H, W = a.W, C = a.C, Ch = a.C / a.heads, N = H * W;
+  const int CHP = Ch + 2;                         // padded pitch (halfs) of the q / v tiles: spreads banks
+  const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y, gi = blockIdx.z;
+  const int wi = h < 2 ? 0 : (h < 5 ? 1 : 2), win = 3 + 2 * wi;
+  const int cl0 = (h - (wi == 0 ? 0 : (wi == 1 ? 2 : 5))) * Ch;     // first channel of this head inside its filter group
+  float* E = reinterpret_cast<float*>(smraw);                       // [N][Ch] exp(k - max)
+  float* ctx = E + (size_t)N * Ch;                                  // [Ch][Ch]
+  float* wt = ctx + Ch * Ch;                                        // [win*win][Ch]
+  float* bs = wt + 49 * Ch;                                         // [Ch]
+  float* red = bs + Ch;                                             // [256]
+  float* mx = red + 256;                                            // [Ch]
+  float* ss = mx + Ch;                                              // [Ch]
+  __half* qs = reinterpret_cast<__half*>(ss + Ch);                  // [N][CHP]
+  __half* vs = qs + (size_t)N * CHP;                                // [N][CHP]
+  pdl_trigger();
+  // filters / bias of this head (module parameters) before pdl_wait
+  {
+    const float* __restrict__ gw = a.cw[gi][wi] + (size_t)cl0 * win * win;
+    const int nt = win * win;
+    for (int i = tid; i < nt * Ch; i += MBF_THREADS) {
+      const int ch = i / nt, t = i - ch * nt;
+      wt[t * Ch + ch] = gw[i];
+    }
+    for (int i = tid; i < Ch; i += MBF_THREADS) bs[i] = a.cb[gi][wi][cl0 + i];
+    for (int i = tid; i < Ch * Ch; i += MBF_THREADS) ctx[i] = 0.f;
+  }
+  pdl_wait();
+  const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C + h * Ch;
+  const int vpr = Ch / 8;
+  const float inv_vpr = 1.0f / (float)vpr;
+  for (int i = tid; i < N * vpr; i += MBF_THREADS) {
+    const int n = fdiv(i, inv_vpr), j = i - n * vpr;
+    const __half* src = base + (long long)n * 3 * C + j * 8;
+    const uint4 rq = *reinterpret_cast<const uint4*>(src);
+    const uint4 rk = *reinterpret_cast<const uint4*>(src + C);
+    const uint4 rv = *reinterpret_cast<const uint4*>(src + 2 * C);
+    float f[8];
+    unpack8(rk, f);
+    float* ed = E + n * Ch + j * 8;
+    *reinterpret_cast<float4*>(ed) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(ed + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    uint32_t* qd = reinterpret_cast<uint32_t*>(qs + (size_t)n * CHP + j * 8);
+    uint32_t* vd = reinterpret_cast<uint32_t*>(vs + (size_t)n * CHP + j * 8);
+    qd[0] = rq.x; qd[1] = rq.y; qd[2] = rq.z; qd[3] = rq.w;
+    vd[0] = rv.x; vd[1] = rv.y; vd[2] = rv.z; vd[3] = rv.w;
+  }
+  __syncthreads();
+  const int nsl = MBF_THREADS / Ch;
+  const int ck = tid % Ch, slc = tid / Ch;
+  {
+    float m = -INFINITY;
+    if (slc < nsl)
+      for (int n = slc; n < N; n += nsl) m = fmaxf(m, E[n * Ch + ck]);
+    red[tid] = m;
+  }
+  __syncthreads();
+  if (tid < Ch) {
+    float mm = -INFINITY;
+    for (int s2 = 0; s2 < nsl; s2++) mm = fmaxf(mm, red[s2 * Ch + tid]);
+    mx[tid] = mm;
+  }
+  __syncthreads();
+  {
+    float sum = 0.f;
+    if (slc < nsl) {
+      const float mc = mx[ck];
+      for (int n = slc; n < N; n += nsl) {
+        const float e = __expf(E[n * Ch + ck] - mc);
+        E[n * Ch + ck] = e;
+        sum += e;
+      }
+    }
+    red[tid] = slc < nsl ? sum : 0.f;
+  }
+  __syncthreads();
+  if (tid < Ch) {
+    float t = 0.f;
+    for (int s2 = 0; s2 < nsl; s2++) t += red[s2 * Ch + tid];
+    ss[tid] = t;
+  }
+  // context: 2 x 2 register tiles of (k, v) pairs, token range split over the remaining threads
+  {
+    const int tiles = (Ch / 2) * (Ch / 2);
+    const int nsp = tiles >= MBF_THREADS ? 1 : MBF_THREADS / tiles;
+    for (int idx = tid; idx < tiles * nsp; idx += MBF_THREADS) {
+      const int tl = idx % tiles, sp = idx / tiles;
+      const int k = (tl / (Ch / 2)) * 2, v = (tl % (Ch / 2)) * 2;
+      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+      for (int n = sp; n < N; n += nsp) {
+        const float2 e = *reinterpret_cast<const float2*>(E + n * Ch + k);
+        const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(vs + (size_t)n * CHP + v));
+        a00 = fmaf(e.x, vv.x, a00); a01 = fmaf(e.x, vv.y, a01);
+        a10 = fmaf(e.y, vv.x, a10); a11 = fmaf(e.y, vv.y, a11);
+      }
+      if (nsp > 1) {
+        atomicAdd(&ctx[k * Ch + v], a00); atomicAdd(&ctx[k * Ch + v + 1], a01);
+        atomicAdd(&ctx[(k + 1) * Ch + v], a10); atomicAdd(&ctx[(k + 1) * Ch + v + 1], a11);
+      } else {
+        ctx[k * Ch + v] = a00; ctx[k * Ch + v + 1] = a01;
+        ctx[(k + 1) * Ch + v] = a10; ctx[(k + 1) * Ch + v + 1] = a11;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Ch * Ch; i += MBF_THREADS) ctx[i] = a.scale * ctx[i] / ss[i / Ch];
+  __syncthreads();
+  __half* __restrict__ outp = a.out[gi] + (long long)b * N * C + h * Ch;
+  if (wi == 0) mbf_apply<3, T>(qs, vs, ctx, wt, bs, outp, H, W, C, Ch, CHP, tid);
+  else if (wi == 1) mbf_apply<5, T>(qs, vs, ctx, wt, bs, outp, H, W, C, Ch, CHP, tid);
+  else mbf_apply<7, T>(qs, vs, ctx, wt, bs, outp, H, W, C, Ch, CHP, tid);
+}
+
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* what) {
   static std::mutex mu;
@@ -477,11 +699,30 @@ int tokens_per_warp(long long rows, int slots) {
 
 }  // namespace
 
-#define DWLN_CASE(IN16, LPT, NV)                                                                         \
-  do {                                                                                                   \
-    TCX_TRY(set_smem(dwln_kernel<IN16, LPT, NV>, smem, "dwln"));                                         \
-    dwln_kernel<IN16, LPT, NV><<<grid, 256, smem, st>>>(a);                                              \
-  } while (0)
+template <bool IN16, int LPT, int NV>
+int dwln_launch(DwLnArgs a, int groups, cudaStream_t st) {
+  constexpr int slots = 32 / LPT;
+  const long long total = (long long)a.B * a.H * a.W;
+  const size_t smem = (size_t)12 * a.C * sizeof(float);
+  TCX_TRY(set_smem(dwln_kernel<IN16, LPT, NV>, smem, "dwln"));
+  static int occ = 0;                               // resident blocks per SM of this instantiation (same smem every call)
+  if (!occ) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwln_kernel<IN16, LPT, NV>, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+  }
+  // one visit per warp: tokens are split evenly over the resident warps, each warp walking `tpw` consecutive tokens
+  // per slot with a one-deep software pipeline
+  long long cap = (long long)148 * occ / groups;
+  if (cap < 1) cap = 1;
+  long long nblk = (total + 8 * slots - 1) / (8 * slots);        // at least one token per warp slot
+  if (nblk > cap) nblk = cap;
+  long long tpw = (total + nblk * 8 * slots - 1) / (nblk * 8 * slots);
+  if (tpw > 16) tpw = 16;                                         // larger inputs take several visits per warp
+  a.tpw = (int)tpw;
+  dim3 grid((unsigned)nblk, groups);
+  ProfScope prof("dwln", st);
+  tcx_launch_pdl(dwln_kernel<IN16, LPT, NV>, grid, dim3(256), smem, st, a);
+  return tcx_check_launch("dwln");
+}
 
 int launch_dwln(DwLnArgs a, int groups, bool in16, cudaStream_t st) {
   const int VEC = in16 ? 8 : 4;
@@ -490,36 +731,24 @@ int launch_dwln(DwLnArgs a, int groups, bool in16, cudaStream_t st) {
   const int NV = a.C / (LPT * VEC);
   const long long total = (long long)a.B * a.H * a.W;
   if (total == 0) return 0;
-  const int slots = 32 / LPT;
   TCX_REQUIRE(total * a.C < (1ll << 31), "dwln: tensor too large for 32-bit indexing");
-  a.tpw = tokens_per_warp(total, slots);
-  const long long per_block = (long long)8 * slots * a.tpw;
-  long long nblk = (total + per_block - 1) / per_block;
-  const long long cap = (long long)148 * 4 / groups > 0 ? (long long)148 * 4 / groups : 1;   // ~4 resident blocks per SM
-  if (nblk > cap) nblk = cap;
-  dim3 grid((unsigned)nblk, groups);
-  const size_t smem = (size_t)12 * a.C * sizeof(float);
-  ProfScope prof("dwln", st);
-  bool ok = true;
   if (in16) {
-    if (LPT == 32 && NV == 1) DWLN_CASE(true, 32, 1);
-    else if (LPT == 32 && NV == 2) DWLN_CASE(true, 32, 2);
-    else if (LPT == 32 && NV == 4) DWLN_CASE(true, 32, 4);
-    else if (LPT == 32 && NV == 5) DWLN_CASE(true, 32, 5);
-    else if (LPT == 32 && NV == 8) DWLN_CASE(true, 32, 8);
-    else if (LPT == 16 && NV == 1) DWLN_CASE(true, 16, 1);
-    else if (LPT == 16 && NV == 5) DWLN_CASE(true, 16, 5);
-    else ok = false;
+    if (LPT == 32 && NV == 1) return dwln_launch<true, 32, 1>(a, groups, st);
+    if (LPT == 32 && NV == 2) return dwln_launch<true, 32, 2>(a, groups, st);
+    if (LPT == 32 && NV == 4) return dwln_launch<true, 32, 4>(a, groups, st);
+    if (LPT == 32 && NV == 5) return dwln_launch<true, 32, 5>(a, groups, st);
+    if (LPT == 32 && NV == 8) return dwln_launch<true, 32, 8>(a, groups, st);
+    if (LPT == 16 && NV == 1) return dwln_launch<true, 16, 1>(a, groups, st);
+    if (LPT == 16 && NV == 5) return dwln_launch<true, 16, 5>(a, groups, st);
   } else {
-    if (LPT == 32 && NV == 1) DWLN_CASE(false, 32, 1);
-    else if (LPT == 32 && NV == 2) DWLN_CASE(false, 32, 2);
-    else if (LPT == 32 && NV == 4) DWLN_CASE(false, 32, 4);
-    else if (LPT == 16 && NV == 1) DWLN_CASE(false, 16, 1);
-    else if (LPT == 16 && NV == 5) DWLN_CASE(false, 16, 5);
-    else ok = false;
+    if (LPT == 32 && NV == 1) return dwln_launch<false, 32, 1>(a, groups, st);
+    if (LPT == 32 && NV == 2) return dwln_launch<false, 32, 2>(a, groups, st);
+    if (LPT == 32 && NV == 4) return dwln_launch<false, 32, 4>(a, groups, st);
+    if (LPT == 16 && NV == 1) return dwln_launch<false, 16, 1>(a, groups, st);
+    if (LPT == 16 && NV == 5) return dwln_launch<false, 16, 5>(a, groups, st);
   }
-  TCX_REQUIRE(ok, "dwln: unsupported width C=%d (in16=%d)", a.C, (int)in16);
-  return tcx_check_launch("dwln");
+  tcx_set_error("dwln: unsupported width C=%d (in16=%d)", a.C, (int)in16);
+  return -1;
 }
 
 int launch_ln16(Ln16Args a, int groups, cudaStream_t st) {
@@ -532,11 +761,11 @@ int launch_ln16(Ln16Args a, int groups, cudaStream_t st) {
   const long long per_block = (long long)8 * slots * a.tpw;
   dim3 grid((unsigned)((a.M + per_block - 1) / per_block), groups);
   ProfScope prof("ln16", st);
-  if (LPT == 16 && NV == 1) ln16_kernel<16, 1><<<grid, 256, 0, st>>>(a);
-  else if (LPT == 16 && NV == 5) ln16_kernel<16, 5><<<grid, 256, 0, st>>>(a);
-  else if (LPT == 32 && NV == 1) ln16_kernel<32, 1><<<grid, 256, 0, st>>>(a);
-  else if (LPT == 32 && NV == 2) ln16_kernel<32, 2><<<grid, 256, 0, st>>>(a);
-  else if (LPT == 32 && NV == 4) ln16_kernel<32, 4><<<grid, 256, 0, st>>>(a);
+  if (LPT == 16 && NV == 1) tcx_launch_pdl(ln16_kernel<16, 1>, grid, dim3(256), 0, st, a);
+  else if (LPT == 16 && NV == 5) tcx_launch_pdl(ln16_kernel<16, 5>, grid, dim3(256), 0, st, a);
+  else if (LPT == 32 && NV == 1) tcx_launch_pdl(ln16_kernel<32, 1>, grid, dim3(256), 0, st, a);
+  else if (LPT == 32 && NV == 2) tcx_launch_pdl(ln16_kernel<32, 2>, grid, dim3(256), 0, st, a);
+  else if (LPT == 32 && NV == 4) tcx_launch_pdl(ln16_kernel<32, 4>, grid, dim3(256), 0, st, a);
   else { tcx_set_error("ln16: unsupported width C=%d", a.C); return -1; }
   return tcx_check_launch("ln16");
 }
@@ -545,39 +774,20 @@ int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st) {
   TCX_REQUIRE(a.heads == 8 && a.C % a.heads == 0, "mb_attn16: needs 8 heads (crpe window map {3:2,5:3,7:3})");
   const int Ch = a.C / a.heads, N = a.H * a.W;
   TCX_REQUIRE(Ch % 8 == 0 && Ch <= 64, "mb_attn16: head dim %d must be a multiple of 8 and <= 64", Ch);
-  {
-    const size_t smem = ((size_t)2 * N * Ch + 256 + 2 * Ch + (size_t)Ch * Ch) * sizeof(float);
-    TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: %d tokens x head dim %d does not fit in shared memory", N, Ch);
-    TCX_TRY(set_smem(mb_ctx16_kernel, smem, "mb_ctx16"));
-    dim3 grid(a.heads, a.B, groups);
-    mb_ctx16_kernel<<<grid, 256, smem, st>>>(a);
-    TCX_TRY(tcx_check_launch("mb_ctx16"));
+  const size_t smem = ((size_t)N * Ch + (size_t)Ch * Ch + 49 * Ch + Ch + 256 + 2 * Ch) * sizeof(float) +
+                      (size_t)2 * N * (Ch + 2) * sizeof(__half);
+  TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: %d tokens x head dim %d does not fit in shared memory", N, Ch);
+  dim3 grid(a.heads, a.B, groups);
+  ProfScope prof("mb_fused16", st);
+  if (a.W % 4 == 0) {
+    TCX_TRY(set_smem(mb_fused16_kernel<4>, smem, "mb_fused16"));
+    tcx_launch_pdl(mb_fused16_kernel<4>, grid, dim3(MBF_THREADS), smem, st, a);
+  } else if (a.W % 2 == 0) {
+    TCX_TRY(set_smem(mb_fused16_kernel<2>, smem, "mb_fused16"));
+    tcx_launch_pdl(mb_fused16_kernel<2>, grid, dim3(MBF_THREADS), smem, st, a);
+  } else {
+    TCX_TRY(set_smem(mb_fused16_kernel<1>, smem, "mb_fused16"));
+    tcx_launch_pdl(mb_fused16_kernel<1>, grid, dim3(MBF_THREADS), smem, st, a);
   }
-  {
-    int R = (int)(((long long)a.H * a.B * groups + 295) / 296);   // ~2 row bands per SM
-    if (R < 1) R = 1;
-    if (R > 8) R = 8;
-    if (R > a.H) R = a.H;
-    auto smem_of = [&](int r) {
-      return (size_t)(r + 6) * a.W * (a.C + 8) * 2 + (size_t)r * a.W * a.C * 2 +
-             ((size_t)a.C * Ch + (size_t)(9 * 2 + 25 * 3 + 49 * 3) * Ch + a.C) * sizeof(float);
-    };
-    while (R > 1 && smem_of(R) > 200 * 1024) R--;
-    const size_t smem = smem_of(R);
-    TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: row band does not fit in shared memory (W=%d C=%d)", a.W, a.C);
-    dim3 grid(cdiv(a.H, R), a.B, groups);
-    ProfScope prof("mb_apply16", st);
-    if (a.W % 4 == 0) {
-      TCX_TRY(set_smem(mb_apply16_kernel<4>, smem, "mb_apply16"));
-      mb_apply16_kernel<4><<<grid, MBA_THREADS, smem, st>>>(a, R);
-    } else if (a.W % 2 == 0) {
-      TCX_TRY(set_smem(mb_apply16_kernel<2>, smem, "mb_apply16"));
-      mb_apply16_kernel<2><<<grid, MBA_THREADS, smem, st>>>(a, R);
-    } else {
-      TCX_TRY(set_smem(mb_apply16_kernel<1>, smem, "mb_apply16"));
-      mb_apply16_kernel<1><<<grid, MBA_THREADS, smem, st>>>(a, R);
-    }
-    TCX_TRY(tcx_check_launch("mb_apply16"));
-  }
-  return 0;
+  return tcx_check_launch("mb_fused16");
 }

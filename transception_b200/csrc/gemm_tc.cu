@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint64_t* res_full = acc_empty + 2;        // [EPI_WARPS][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2 * EPI_WARPS);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.M + BM - 1) / BM, nt = (p.N + BN - 1) / BN;
   const int ntiles = mt * nt * p.groups * p.batch;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything above overlapped the previous kernel; no global access before this point
 
   if (warp == 0) {
     // ================= TMA producer: A / W k-blocks of every tile of this CTA, back to back =================
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         tc::mbar_arrive(&acc_empty[a]);
       }
     }
-    if (lane == 0) bulk_wait_all();
+    if (lane == 0) bulk_wait_read<0>();   // smem may be released; the stores themselves complete before the grid does
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -432,7 +434,8 @@ int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cuda
   const int ntiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.groups * p.batch;
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
   ProfScope prof("gemm_tc", st);
-  gemm_tc_kernel<BN, AB16, OUT16><<<grid, GT_THREADS, sp.total, st>>>(maps, p, sp);
+  cudaError_t le = tcx_launch_pdl(gemm_tc_kernel<BN, AB16, OUT16>, dim3(grid), dim3(GT_THREADS), (size_t)sp.total, st, maps, p, sp);
+  TCX_REQUIRE(le == cudaSuccess, "gemm_tc: launch failed: %s", cudaGetErrorString(le));
   return tcx_check_launch("gemm_tc");
 }
 

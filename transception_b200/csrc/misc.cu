@@ -11,22 +11,32 @@ namespace {
 // =====================================================================================
 constexpr int PE_T = 8, PE_K = 7, PE_S = 4, PE_IN = (PE_T - 1) * PE_S + PE_K;  // 35
 
+// CIN = 3: three input planes.  CIN = 1: the reference repeats the grey plane three times (MSTr.py:2828-2829), which is
+// the same as convolving it once with the filters summed over their input channels -> 49 taps instead of 147.
+template <int CIN>
 __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __restrict__ x, long long xs_b, long long xs_c,
                                                              int Hin, int Win, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ lnw,
                                                              const float* __restrict__ lnb, float eps, int Ho, int Wo,
                                                              float* __restrict__ out) {
+  constexpr int NTAP = CIN * 49;
   extern __shared__ float sm[];
-  float* ws = sm;                        // [147][64]  (tap-major)
-  float* tile = ws + 147 * 64;           // [3][35][36]
+  float* ws = sm;                        // [NTAP][64]  (tap-major)
+  float* tile = ws + NTAP * 64;          // [CIN][35][36]
   const int tid = threadIdx.x, b = blockIdx.z;
   const int oy0 = blockIdx.y * PE_T, ox0 = blockIdx.x * PE_T;
-  for (int i = tid; i < 147 * 64; i += 256) {
-    const int co = i & 63, tap = i >> 6;          // w[co][ci][ky][kx] = w[co*147 + tap]
-    ws[i] = w[co * 147 + tap];
+  pdl_trigger();
+  // filters (module parameters): coalesced reads in their native [co][ci][ky][kx] order, transposed in shared memory
+  for (int i = tid; i < 64 * NTAP; i += 256) {
+    const int co = i / NTAP, tap = i - co * NTAP;
+    float v;
+    if (CIN == 1) v = __ldg(w + co * 147 + tap) + __ldg(w + co * 147 + 49 + tap) + __ldg(w + co * 147 + 98 + tap);
+    else v = __ldg(w + i);
+    ws[tap * 64 + co] = v;
   }
+  pdl_wait();
   const int iy0 = oy0 * PE_S - 3, ix0 = ox0 * PE_S - 3;
-  for (int i = tid; i < 3 * PE_IN * PE_IN; i += 256) {
+  for (int i = tid; i < CIN * PE_IN * PE_IN; i += 256) {
     const int xx = i % PE_IN, yy = (i / PE_IN) % PE_IN, ci = i / (PE_IN * PE_IN);
     const int gy = iy0 + yy, gx = ix0 + xx;
     float v = 0.f;
@@ -39,7 +49,9 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) acc[i] = bias[cg * 16 + i];
-  for (int ci = 0; ci < 3; ci++)
+#pragma unroll 1
+  for (int ci = 0; ci < CIN; ci++)
+#pragma unroll 1
     for (int ky = 0; ky < 7; ky++) {
       const float* trow = tile + (ci * PE_IN + py * PE_S + ky) * 36 + px * PE_S;
       const float* wrow = ws + ((ci * 7 + ky) * 7) * 64 + cg * 16;
@@ -161,6 +173,8 @@ __global__ void __launch_bounds__(256) sr_pack_ln_kernel(SrPackArgs a) {
 // 16-byte vector copies (the prepared conv weight is permuted to the same K order, tcx_prepare_conv_weight_f16).
 __global__ void __launch_bounds__(256) sr_im2row16_kernel(const __half* __restrict__ x, long long xs_b, int HW, int Cin, int r,
                                                           int B, __half* __restrict__ A) {
+  pdl_trigger();
+  pdl_wait();
   const int P = HW / r;
   const int seg = r * Cin / 8;                       // vectors per (patch, ky) piece
   const long long total = (long long)B * P * P * r * seg;
@@ -192,6 +206,8 @@ __global__ void __launch_bounds__(256) conv_weight_perm16_kernel(const float* __
 
 // pack conv outputs (fp32) + raw stage-4 tokens (fp16) into the reduced sequence, LayerNorm(64), write fp16
 __global__ void __launch_bounds__(256) sr_pack_ln16_kernel(SrPackArgs a, const __half* __restrict__ x16, __half* __restrict__ out16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)a.B * a.nred) return;
@@ -352,14 +368,17 @@ __global__ void __launch_bounds__(128) final_head_kernel(const float* __restrict
 int launch_patch_embed_ln(const float* x, long long xs_b, long long xs_c, int B, int Hin, int Win, const float* w,
                           const float* bias, const float* lnw, const float* lnb, float eps, float* out, cudaStream_t st) {
   const int Ho = (Hin + 6 - 7) / 4 + 1, Wo = (Win + 6 - 7) / 4 + 1;
-  const size_t smem = (size_t)(147 * 64 + 3 * PE_IN * 36) * sizeof(float);
+  const bool grey = xs_c == 0;           // one plane read three times
+  const int cin = grey ? 1 : 3;
+  const size_t smem = (size_t)(cin * 49 * 64 + cin * PE_IN * 36) * sizeof(float);
   static bool done = false;
   if (!done) {
-    cudaFuncSetAttribute(patch_embed_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(patch_embed_ln_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((147 * 64 + 3 * PE_IN * 36) * sizeof(float)));
     done = true;
   }
   dim3 grid(cdiv(Wo, PE_T), cdiv(Ho, PE_T), B);
-  patch_embed_ln_kernel<<<grid, 256, smem, st>>>(x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);
+  if (grey) tcx_launch_pdl(patch_embed_ln_kernel<1>, grid, dim3(256), smem, st, x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);
+  else tcx_launch_pdl(patch_embed_ln_kernel<3>, grid, dim3(256), smem, st, x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);
   return tcx_check_launch("patch_embed_ln");
 }
 
@@ -423,8 +442,8 @@ int launch_sr_im2row16(const void* x16, long long xs_b, int HW, int Cin, int r, 
   const int P = HW / r;
   const long long total = (long long)B * P * P * r * (r * Cin / 8);
   if (total == 0) return 0;
-  sr_im2row16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(x16), xs_b, HW, Cin, r, B,
-                                                                    reinterpret_cast<__half*>(A16));
+  tcx_launch_pdl(sr_im2row16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                 reinterpret_cast<const __half*>(x16), xs_b, HW, Cin, r, B, reinterpret_cast<__half*>(A16));
   return tcx_check_launch("sr_im2row16");
 }
 
@@ -438,7 +457,7 @@ int launch_conv_weight_perm16(const float* w, void* o16, int N, int Cin, int r, 
 int launch_sr_pack_ln16(const SrPackArgs& a, const void* x16, void* out16, cudaStream_t st) {
   const long long rows = (long long)a.B * a.nred;
   if (rows == 0) return 0;
-  sr_pack_ln16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a, reinterpret_cast<const __half*>(x16),
-                                                                 reinterpret_cast<__half*>(out16));
+  tcx_launch_pdl(sr_pack_ln16_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, a,
+                 reinterpret_cast<const __half*>(x16), reinterpret_cast<__half*>(out16));
   return tcx_check_launch("sr_pack_ln16");
 }
