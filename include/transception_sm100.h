@@ -37,6 +37,9 @@ long long tcx_launch_count(void);
  * tcx_profile_read synchronises on the recorded events, returns their summed duration and count, and resets. */
 int tcx_profile_enable(const char* kernel_name);
 int tcx_profile_read(double* total_ms, int* count);
+/* same, plus the summed algorithmic work of the timed launches: bytes for the HBM-bound kernels ("gemm_tc", "dwln",
+ * "ln16", "mb_fused16", "ea16_ctx"), FLOPs for "flash_tc" */
+int tcx_profile_read_work(double* total_ms, int* count, double* work);
 
 /* K10 — nn.LayerNorm over the last dim (MSTr.py:153,156,1671,2360,2366; eps 1e-6 at :932-933) */
 int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,
@@ -92,14 +95,14 @@ size_t tcx_mb_factor_attn_workspace_bytes(int B, int N, int C);
 int tcx_mb_factor_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W,
                            int C, int heads, void* ws, void* stream);
 
-/* K2+K3+K1 — G parallel branches x L chained MHCABlock.forward (MSTr.py:935-946), in place on x[G][B][N][C].
+/* K2+K3+K1 — G parallel branches x L chained MHCABlock.forward (MSTr.py:935-946): x_in[G][B][N][C] -> x (x_in may equal x).
  * p holds G*L blocks of TCX_MHCA_NP pointers:
  * {cpe_w,cpe_b,n1_w,n1_b,qkv_w,qkv_b,crpe_w3,crpe_b3,crpe_w5,crpe_b5,crpe_w7,crpe_b7,proj_w,proj_b,
  *  n2_w,n2_b,fc1_w,fc1_b,dw_w,dw_b,mlp_ln_w,mlp_ln_b,fc2_w,fc2_b}, block (g,l) at p[(g*L+l)*TCX_MHCA_NP] */
 #define TCX_MHCA_NP 24
 size_t tcx_mhca_blocks_workspace_bytes(int G, int B, int N, int C);
-int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int H, int W, int C, int heads,
-                        float ln_eps, float mlp_ln_eps, void* ws, void* stream);
+int tcx_mhca_blocks_fwd(const float* x_in, float* x, const void* const* p, int G, int L, int B, int H, int W, int C,
+                        int heads, float ln_eps, float mlp_ln_eps, void* ws, void* stream);
 
 /* K4 — DWConv2d_BN.forward (MSTr.py:355-362): Hardswish(BN(pw1x1(dw3x3_stride(x)))), NHWC */
 size_t tcx_ripm_dwsep_bn_hs_workspace_bytes(int B, int H, int W, int C, int stride);

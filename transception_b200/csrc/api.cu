@@ -39,6 +39,7 @@ static std::string g_prof_name;
 static std::vector<cudaEvent_t> g_prof_ev;   // start/stop pairs
 static size_t g_prof_used = 0;
 static bool g_prof_open = false;
+static double g_prof_work = 0.0;
 void tcx_prof_begin(const char* name, cudaStream_t st) {
   if (g_prof_name != name) return;
   if (g_prof_used + 2 > g_prof_ev.size()) {
@@ -49,11 +50,12 @@ void tcx_prof_begin(const char* name, cudaStream_t st) {
   cudaEventRecord(g_prof_ev[g_prof_used], st);
   g_prof_open = true;
 }
-void tcx_prof_end(const char* name, cudaStream_t st) {
+void tcx_prof_end(const char* name, cudaStream_t st, double work) {
   if (!g_prof_open || g_prof_name != name) return;
   cudaEventRecord(g_prof_ev[g_prof_used + 1], st);
   g_prof_used += 2;
   g_prof_open = false;
+  g_prof_work += work;
 }
 
 static int g_flag_gemm_tc = 1;
@@ -239,14 +241,12 @@ struct AuxStreams {
   bool ok = false;
 };
 static std::mutex g_aux_mu;
-static std::unordered_map<int, AuxStreams> g_aux;
+static std::unordered_map<const void*, AuxStreams> g_aux;   // one set per calling stream (independent forward chains)
 static int g_flag_fork = 1;
-AuxStreams* aux_streams() {
+AuxStreams* aux_streams(cudaStream_t st) {
   if (!g_flag_fork) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lk(g_aux_mu);
-  AuxStreams& a = g_aux[dev];
+  AuxStreams& a = g_aux[reinterpret_cast<const void*>(st)];
   if (!a.ok) {
     bool good = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < TCX_AUX && good; i++)
@@ -366,8 +366,13 @@ int run_eff_attn16(const __half* xn16, const void* const* p, const float* residu
     v = Ea16View{kqv, kqv + C, kqv + 2 * C, (long long)N * 3 * C, 3 * C, 0};
   }
   TCX_TRY(launch_gemm(g, st));
-  TCX_TRY(launch_ea16_context(v, B, N, C, part, ctxT, st));
-  TCX_TRY(launch_ea16_qsoftmax(v, B, N, C, qsm, st));
+  {  // the context (partials + combine) and the query softmax are independent: run them side by side
+    AuxStreams* aux = aux_streams(st);
+    if (aux) TCX_TRY(fork_streams(aux, st, 1));
+    TCX_TRY(launch_ea16_qsoftmax(v, B, N, C, qsm, aux ? aux->s[0] : st));
+    TCX_TRY(launch_ea16_context(v, B, N, C, part, ctxT, st));
+    if (aux) TCX_TRY(join_stream(aux, 0, st));
+  }
   {  // att[b] = qsm[b] (N x C) * ctx[b] (C x C): W = ctxT[b]
     GemmParams a = gemm1(F(qsm), F(ctxT), reinterpret_cast<float*>(att), N, C, C);
     a.batch = B; a.strideA = (long long)N * C; a.strideW = (long long)C * C; a.strideC = (long long)N * C;
@@ -401,7 +406,7 @@ int run_bridge_sr_attn16(const __half* xn16, const void* const* p, float scale, 
   float* fws = c.take(flash_tc_workspace_bytes(B, g.nred) / 4 + 64);
   const int M = B * g.ntok;
   // q projection on st; the reduced-token chain (3 patchify convs in parallel -> pack+LN -> kv projection) on aux streams
-  AuxStreams* aux = aux_streams();
+  AuxStreams* aux = aux_streams(st);
   if (aux) TCX_TRY(fork_streams(aux, st, 3));
   cudaStream_t s0 = aux ? aux->s[0] : st;
   {
@@ -473,10 +478,18 @@ int tcx_device_ok(void) {
 long long tcx_launch_count(void) { return g_launches; }
 
 int tcx_profile_enable(const char* kernel_name) {
-  g_prof_used = 0; g_prof_open = false;
+  g_prof_used = 0; g_prof_open = false; g_prof_work = 0.0;
   if (kernel_name && kernel_name[0]) { g_prof_name = kernel_name; g_tcx_prof_on = true; }
   else { g_prof_name.clear(); g_tcx_prof_on = false; }
   return 0;
+}
+
+int tcx_profile_read_work(double* total_ms, int* count, double* work) {
+  const double w = g_prof_work;
+  const int rc = tcx_profile_read(total_ms, count);
+  *work = w;
+  g_prof_work = 0.0;
+  return rc;
 }
 
 int tcx_profile_read(double* total_ms, int* count) {
@@ -676,8 +689,8 @@ size_t tcx_mhca_blocks_workspace_bytes(int G, int B, int N, int C) {
   return 4 * (size_t)G * (4 * rnd(bnc) + rnd(3 * bnc) + 2 * rnd(4 * bnc) + rnd((size_t)B * C * C));
 }
 
-int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int H, int W, int C, int heads,
-                        float ln_eps, float mlp_ln_eps, void* ws, void* stream) {
+int tcx_mhca_blocks_fwd(const float* x_in, float* x, const void* const* p, int G, int L, int B, int H, int W, int C,
+                        int heads, float ln_eps, float mlp_ln_eps, void* ws, void* stream) {
   TCX_REQUIRE(G >= 1 && G <= TCX_MAX_GROUPS, "mhca_blocks: G=%d out of range", G);
   cudaStream_t st = S(stream);
   const int N = H * W, M = B * N;
@@ -709,7 +722,8 @@ int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int
         DwLnArgs a{};
         a.B = B; a.H = H; a.W = W; a.C = C; a.eps = ln_eps; a.gelu = 0;
         for (int g = 0; g < G; g++)
-          a.g[g] = DwLnGroup{x + g * bnc, F(blk[g][0]), F(blk[g][1]), F(blk[g][2]), F(blk[g][3]), xa + g * bnc, ln16 + g * bnc};
+          a.g[g] = DwLnGroup{(l == 0 ? x_in : x) + g * bnc, F(blk[g][0]), F(blk[g][1]), F(blk[g][2]), F(blk[g][3]), xa + g * bnc,
+                             ln16 + g * bnc};
         TCX_TRY(launch_dwln(a, G, false, st));
       }
       {
@@ -762,7 +776,7 @@ int tcx_mhca_blocks_fwd(float* x, const void* const* p, int G, int L, int B, int
     for (int g = 0; g < G; g++) blk[g] = p + ((size_t)g * L + l) * TCX_MHCA_NP;
     {  // x = x + dw3x3(x) + b   (ConvPosEnc, shared weights, applied in every block)
       DwGroup dg[TCX_MAX_GROUPS];
-      for (int g = 0; g < G; g++) dg[g] = DwGroup{x + g * bnc, F(blk[g][0]), F(blk[g][1]), xa + g * bnc};
+      for (int g = 0; g < G; g++) dg[g] = DwGroup{(l == 0 ? x_in : x) + g * bnc, F(blk[g][0]), F(blk[g][1]), xa + g * bnc};
       TCX_TRY(launch_dwconv3x3(dg, G, B, H, W, C, 1, DW_ADD_INPUT, BnParams{}, st));
     }
     {
@@ -957,7 +971,7 @@ static int bridge_mixffn16(const __half* tx16, const float* tx1, const void* con
                            const BridgeGeom& g, float* ws, cudaStream_t st) {
   Carver c(ws);
   const long long sb = (long long)g.ntok * 64;
-  AuxStreams* aux = aux_streams();
+  AuxStreams* aux = aux_streams(st);
   if (aux) TCX_TRY(fork_streams(aux, st, 3));
   for (int k = 0; k < 4; k++) {       // the four scales are independent chains: scale 0 on st, 1..3 on aux streams
     const int hw = g.hw[k], C = g.ch[k], C4 = 4 * C, Mi = hw * hw;

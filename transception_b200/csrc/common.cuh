@@ -14,12 +14,13 @@ int tcx_check_launch(const char* what);
 // CUDA event pair on the launching stream around the launch. Disabled = one predictable branch.
 extern bool g_tcx_prof_on;
 void tcx_prof_begin(const char* name, cudaStream_t st);
-void tcx_prof_end(const char* name, cudaStream_t st);
+void tcx_prof_end(const char* name, cudaStream_t st, double work);
 struct ProfScope {
   const char* name;
   cudaStream_t st;
-  ProfScope(const char* n, cudaStream_t s) : name(n), st(s) { if (g_tcx_prof_on) tcx_prof_begin(name, st); }
-  ~ProfScope() { if (g_tcx_prof_on) tcx_prof_end(name, st); }
+  double work;     // algorithmic bytes (HBM-bound kernels) or FLOPs (tensor-bound) of this launch, for the roofline leg
+  ProfScope(const char* n, cudaStream_t s, double w = 0.0) : name(n), st(s), work(w) { if (g_tcx_prof_on) tcx_prof_begin(name, st); }
+  ~ProfScope() { if (g_tcx_prof_on) tcx_prof_end(name, st, work); }
 };
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------

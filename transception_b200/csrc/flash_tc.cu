@@ -408,7 +408,7 @@ static int flash_tc_launch(const FlashMaps& maps, const void* q, void* out, int 
   const int tiles_per_img = cdiv(Nq, FT_BM);
   const int npairs = B * ((tiles_per_img + 1) / 2);
   const float qscale = scale * 1.4426950408889634f;
-  ProfScope prof("flash_tc", st);
+  ProfScope prof("flash_tc", st, 4.0 * B * (double)Nq * Nk * FT_D);   // QK^T + PV FLOPs
   cudaError_t le;
   if (f16io) le = tcx_launch_pdl(flash_tc_kernel<true, true>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, B, Nq, Nk, qscale);
   else le = tcx_launch_pdl(flash_tc_kernel<false, false>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, B, Nq, Nk, qscale);

@@ -719,7 +719,9 @@ int dwln_launch(DwLnArgs a, int groups, cudaStream_t st) {
   if (tpw > 16) tpw = 16;                                         // larger inputs take several visits per warp
   a.tpw = (int)tpw;
   dim3 grid((unsigned)nblk, groups);
-  ProfScope prof("dwln", st);
+  double bytes = 0.0;
+  for (int i = 0; i < groups; i++) bytes += (double)total * a.C * ((IN16 ? 2.0 : 4.0) + 2.0 + (a.g[i].u ? 4.0 : 0.0));
+  ProfScope prof("dwln", st, bytes);
   tcx_launch_pdl(dwln_kernel<IN16, LPT, NV>, grid, dim3(256), smem, st, a);
   return tcx_check_launch("dwln");
 }
@@ -778,7 +780,7 @@ int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st) {
                       (size_t)2 * N * (Ch + 2) * sizeof(__half);
   TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: %d tokens x head dim %d does not fit in shared memory", N, Ch);
   dim3 grid(a.heads, a.B, groups);
-  ProfScope prof("mb_fused16", st);
+  ProfScope prof("mb_fused16", st, (double)groups * a.B * N * a.C * 2.0 * 4.0);   // qkv read + output written (fp16)
   if (a.W % 4 == 0) {
     TCX_TRY(set_smem(mb_fused16_kernel<4>, smem, "mb_fused16"));
     tcx_launch_pdl(mb_fused16_kernel<4>, grid, dim3(MBF_THREADS), smem, st, a);

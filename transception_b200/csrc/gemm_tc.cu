@@ -433,7 +433,15 @@ int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cuda
   TCX_REQUIRE(sp.stages >= 2 && sp.total <= SMEM_BUDGET, "gemm_tc: smem plan does not fit (BN=%d stages=%d)", BN, sp.stages);
   const int ntiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.groups * p.batch;
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
-  ProfScope prof("gemm_tc", st);
+  // algorithmic bytes: every operand read once, the output written once
+  const double ae = AB16 ? 2.0 : 4.0, ce = OUT16 ? 2.0 : 4.0;
+  double bytes = 0.0;
+  for (int i = 0; i < p.groups; i++) {
+    const double nb = (double)p.batch;
+    bytes += nb * p.M * p.K * ae + (p.strideW ? nb : 1.0) * p.N * p.K * ae + nb * p.M * p.N * ce +
+             (p.g[i].epi.residual ? nb * p.M * p.N * 4.0 : 0.0);
+  }
+  ProfScope prof("gemm_tc", st, bytes);
   cudaError_t le = tcx_launch_pdl(gemm_tc_kernel<BN, AB16, OUT16>, dim3(grid), dim3(GT_THREADS), (size_t)sp.total, st, maps, p, sp);
   TCX_REQUIRE(le == cudaSuccess, "gemm_tc: launch failed: %s", cudaGetErrorString(le));
   return tcx_check_launch("gemm_tc");

@@ -29,6 +29,7 @@ _PROTOS = {
     "tcx_launch_count": (_ll, []),
     "tcx_profile_enable": (_i, [ctypes.c_char_p]),
     "tcx_profile_read": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i)]),
+    "tcx_profile_read_work": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double)]),
     "tcx_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "tcx_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tcx_f32_to_f16": (_i, [_vp, _vp, _ll, _vp]),
@@ -50,7 +51,7 @@ _PROTOS = {
     "tcx_mb_factor_attn_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_mb_factor_attn_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mhca_blocks_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "tcx_mhca_blocks_fwd": (_i, [_vp, _pp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
+    "tcx_mhca_blocks_fwd": (_i, [_vp, _vp, _pp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "tcx_ripm_dwsep_bn_hs_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tcx_ripm_dwsep_bn_hs_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_resblock_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -107,6 +108,13 @@ def profile_read():
     ms, n = ctypes.c_double(0), ctypes.c_int(0)
     _chk(load_library().tcx_profile_read(ctypes.byref(ms), ctypes.byref(n)))
     return ms.value, n.value
+
+
+def profile_read_work():
+    """(total ms, launches, summed algorithmic bytes-or-FLOPs) of the kernel selected by profile_enable."""
+    ms, n, w = ctypes.c_double(0), ctypes.c_int(0), ctypes.c_double(0)
+    _chk(load_library().tcx_profile_read_work(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)))
+    return ms.value, n.value, w.value
 
 
 def set_flag(name, value):
@@ -358,10 +366,11 @@ def mhca_blocks(x, H, W, branches):
         for blk in br:
             flat.extend(_block_params(blk))
     b0 = branches[0][0]
-    y = x.contiguous().clone()
+    x = x.contiguous()
+    y = torch.empty_like(x)
     ws = _ws(lib.tcx_mhca_blocks_workspace_bytes(G, B, N, C), x)
     mats = [k * MHCA_NP + j for k in range(G * L) for j in (4, 12, 16, 22)]
-    _chk(lib.tcx_mhca_blocks_fwd(_ptr(y), _table(flat, mats), G, L, B, H, W, C, b0.factoratt_crpe.num_heads,
+    _chk(lib.tcx_mhca_blocks_fwd(_ptr(x), _ptr(y), _table(flat, mats), G, L, B, H, W, C, b0.factoratt_crpe.num_heads,
                                  b0.norm1.eps, b0.mlp.norm1.eps, _ptr(ws), _stream()))
     return y
 
