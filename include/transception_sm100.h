@@ -144,6 +144,11 @@ size_t tcx_flash_attn_workspace_bytes(int B, int Nk);
 int tcx_flash_attn_fwd(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
                        void* stream);
 
+/* fp16 form used by the fp16 pipeline: q16 [B][Nq][64], kv16 [B][Nk][128] (k | v), out16 [B][Nq][64] are fp16; q and k
+ * tiles arrive by TMA straight from these buffers (ws only holds the transposed V). tcgen05 kernel only. */
+int tcx_flash_attn_f16_fwd(const void* q16, const void* kv16, void* out16, int B, int Nq, int Nk, float scale, void* ws,
+                           void* stream);
+
 /* BridgLayer_4.forward tail (MSTr.py:2394-2406): y = tx1 + cat_k MixFFN_k(tx slab k).  p = 4 x the K1 slots. */
 size_t tcx_bridge_mixffn_workspace_bytes(int B, int S);
 int tcx_bridge_mixffn_fwd(const float* tx, const float* tx1, const void* const* p, float ln_eps, float* y, int B,

@@ -250,6 +250,20 @@ def test_flash_attention_ragged(backend, B, Nq, Nk):
     _close(got, want, 3e-3 if backend == TC_TOL else FP32_TOL, "flash_attn %s" % ((B, Nq, Nk),))
 
 
+@pytest.mark.parametrize("B,Nq,Nk", [(1, 1, 1), (2, 60, 16), (1, 128, 112), (3, 129, 113), (2, 6076, 784), (1, 7936, 1024),
+                                     (2, 300, 230), (5, 1000, 784)])
+def test_flash_attention_f16(cuda_lib, B, Nq, Nk):
+    """fp16-IO tcgen05 flash kernel (TMA-fed q, cross-pair overlap) against fp64 softmax(q k^T / 8) v."""
+    from transception_b200 import ops
+    q, kv = _rand(B, Nq, 64, seed=11), _rand(B, Nk, 128, seed=12)
+    q16, kv16 = q.half(), kv.half()
+    k, v = kv16[..., :64].double(), kv16[..., 64:].double()
+    want = torch.softmax(q16.double() @ k.transpose(1, 2) * 0.125, -1) @ v
+    got = ops.flash_attn_f16(q16.cuda(), kv16.cuda(), 0.125)
+    assert got.dtype == torch.float16
+    _close(got, want.float(), 5e-3, "flash_f16 %d %d %d" % (B, Nq, Nk))
+
+
 def test_flash_attention_properties(cuda_lib):
     """Size-independent properties at the full bs16 size: rows of softmax sum to one (v = const -> out = const),
     invariance to a per-row shift of the scores (k -> k, q -> q: adding a constant key offset along q's direction

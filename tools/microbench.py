@@ -83,6 +83,9 @@ def main():
     q, kv = r(16, 6076, 64), r(16, 784, 128)
     t0 = timeit(lambda: ops.flash_attn(q, kv, 0.125))
     rows.append("flash_attn 16x6076x784 : %7.1f us -> %.1f TF/s" % (t0, 4.0 * 16 * 6076 * 784 * 64 / (t0 * 1e-6) / 1e12))
+    q16, kv16 = q.half(), kv.half()
+    t1 = timeit(lambda: ops.flash_attn_f16(q16, kv16, 0.125))
+    rows.append("flash_attn_f16 16x6076x784 : %7.1f us -> %.1f TF/s (incl. V^T pack)" % (t1, 4.0 * 16 * 6076 * 784 * 64 / (t1 * 1e-6) / 1e12))
     print("\n".join(rows))
 
 

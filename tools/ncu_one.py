@@ -15,9 +15,16 @@ if what == "linear":
     res = len(sys.argv) > 5
     x, w, b, rr = r(M, K), r(N, K), r(N), r(M, N)
     fn = lambda: ops.linear(x, w, b, residual=rr if res else None)
+elif what == "linear16":
+    M, N, K, o16 = (int(a) for a in sys.argv[2:6])
+    x, w, b, rr = r(M, K).half(), r(N, K).half(), r(N), r(M, N)
+    fn = lambda: ops.linear_f16(x, w, b, residual=None if o16 else rr, out_f16=bool(o16))
 elif what == "flash":
     q, kv = r(16, 6076, 64), r(16, 784, 128)
     fn = lambda: ops.flash_attn(q, kv, 0.125)
+elif what == "flash16":
+    q, kv = r(16, 6076, 64).half(), r(16, 784, 128).half()
+    fn = lambda: ops.flash_attn_f16(q, kv, 0.125)
 elif what == "mixffn":
     B, hw, C = (int(a) for a in sys.argv[2:5])
     x = r(B, hw * hw, C)

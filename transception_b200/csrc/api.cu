@@ -958,6 +958,13 @@ int tcx_flash_attn_fwd(const float* q, const float* kv, float* out, int B, int N
   return launch_flash_ffma(q, kv, out, B, Nq, Nk, scale, S(stream));
 }
 
+int tcx_flash_attn_f16_fwd(const void* q16, const void* kv16, void* out16, int B, int Nq, int Nk, float scale, void* ws,
+                           void* stream) {
+  TCX_REQUIRE(B >= 0 && Nq >= 0 && Nk >= 1, "flash_attn_f16: bad sizes B=%d Nq=%d Nk=%d", B, Nq, Nk);
+  if (B == 0 || Nq == 0) return 0;
+  return launch_flash_tc16(q16, kv16, out16, B, Nq, Nk, scale, ws, S(stream));
+}
+
 size_t tcx_bridge_mixffn_workspace_bytes(int B, int S0) {
   BridgeGeom g;
   if (!bridge_geom(S0, g)) return 0;

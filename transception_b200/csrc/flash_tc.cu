@@ -29,18 +29,20 @@ constexpr int FT_P_BYTES = FT_BM * 128 * 2;            // 32 KB   two [128][64] 
 constexpr int FT_K_BYTES = FT_BN * FT_D * 2;           // 14 KB   [112 kv][64 d]
 constexpr int FT_V_BYTES = 2 * FT_D * 64 * 2;          // 16 KB   two [64 d][64 kv] sub-tiles of V^T
 constexpr int FT_STAGE_BYTES = FT_K_BYTES + FT_V_BYTES;
-constexpr int FT_OFF_P = 2 * FT_Q_BYTES;
+constexpr int FT_OFF_P = 4 * FT_Q_BYTES;               // Q: [warpgroup][2 buffers] (fp16 q arrives by TMA one pair ahead)
 constexpr int FT_OFF_KV = FT_OFF_P + 2 * FT_P_BYTES;
 constexpr int FT_OFF_BAR = FT_OFF_KV + FT_STAGES * FT_STAGE_BYTES;
-constexpr int FT_NBAR = 2 * FT_STAGES + 10;
+constexpr int FT_NBAR = 2 * FT_STAGES + 16;
 constexpr float FT_LAZY = 8.0f;                        // rescale O only when the row max grew by > 2^8 (log2 units)
 constexpr int FT_SMEM = FT_OFF_BAR + FT_NBAR * 8 + 16 + 1024;
 constexpr int FT_THREADS = 384;                        // 2 softmax warpgroups + 1 service warpgroup (TMA, MMA, 2 idle)
-constexpr uint32_t FT_TMEM_COLS = 512;                 // S[2] at 0,128 ; PV[2] at 256,320
+constexpr uint32_t FT_TMEM_COLS = 512;                 // S[2] at 0,128 ; PV[2] at 256,320 ; P[2] (fp16 pairs) at 384,448
+constexpr bool FT_P_TMEM = true;                       // P = 2^(S-m) handed to the P V MMA through tensor memory (A from TMEM)
 
 struct FlashMaps {
   CUtensorMap k;    // k16  [B][Nk][64]      box {64, 112, 1}
   CUtensorMap vt;   // vt16 [B][64][Nkp]     box {64, 64, 1}
+  CUtensorMap q;    // q16  [B][Nq][64]      box {64, 128, 1}   (fp16 path only)
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -93,8 +95,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   uint8_t* sKV = smem + FT_OFF_KV;
   uint64_t* kv_full = reinterpret_cast<uint64_t*>(smem + FT_OFF_BAR);
   uint64_t* kv_empty = kv_full + FT_STAGES;
-  uint64_t* q_full = kv_empty + FT_STAGES;   // [2]
-  uint64_t* s_full = q_full + 2;             // [2]
+  uint64_t* q_full = kv_empty + FT_STAGES;   // [warpgroup][buffer]
+  uint64_t* q_empty = q_full + 4;            // [warpgroup][buffer]
+  uint64_t* s_full = q_empty + 4;            // [2]
   uint64_t* p_full = s_full + 2;             // [2]
   uint64_t* o_full = p_full + 2;             // [2]
   uint64_t* s_free = o_full + 2;             // [2]
@@ -110,9 +113,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   if (warp == 8 && lane == 0) {
     tc::prefetch_tmap(&maps.k);
     tc::prefetch_tmap(&maps.vt);
+    if (Q16) tc::prefetch_tmap(&maps.q);
     for (int s = 0; s < FT_STAGES; s++) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
+    for (int i = 0; i < 4; i++) { tc::mbar_init(&q_full[i], Q16 ? 1 : 128); tc::mbar_init(&q_empty[i], 1); }
     for (int w = 0; w < 2; w++) {
-      tc::mbar_init(&q_full[w], 128);
       tc::mbar_init(&s_full[w], 1);
       tc::mbar_init(&p_full[w], 128);
       tc::mbar_init(&o_full[w], 1);
@@ -137,9 +141,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
   if (warp == 8) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t kvi = 0;
-      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      uint32_t kvi = 0, it = 0;
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, it++) {
         const int b = pair / pairs_per_img;
+        if (Q16) {   // both query tiles of this pair, into buffer it & 1 (free once the previous user's Q K^T retired)
+          const uint32_t buf = it & 1;
+          for (int w = 0; w < 2; w++) {
+            const int tile = (pair - b * pairs_per_img) * 2 + w;
+            tc::mbar_wait(&q_empty[w * 2 + buf], ((it >> 1) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(&q_full[w * 2 + buf], FT_Q_BYTES);
+            tc::tma_load_3d(sQ + (w * 2 + buf) * FT_Q_BYTES, &maps.q, 0, tile * FT_BM, b, &q_full[w * 2 + buf]);
+          }
+        }
         for (int t = 0; t < nkt; t++, kvi++) {
           const int s = kvi % FT_STAGES;
           tc::mbar_wait(&kv_empty[s], ((kvi / FT_STAGES) & 1) ^ 1);
@@ -158,22 +171,45 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       constexpr uint32_t idesc_o = tc::umma_idesc(0, FT_BM, FT_D);    // 128 x 64
       const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP), kv_addr = tc::smem_u32(sKV);
       uint32_t kvi = 0, it = 0, cnt = 0;   // cnt: kv tiles issued so far for this CTA (per warpgroup)
-      auto issue_qk = [&](int w, uint32_t stage) {
-        const uint64_t ad = tc::umma_desc_sw128(q_addr + w * FT_Q_BYTES);
+      uint32_t qbuf = 0;
+      auto issue_qk = [&](int w, uint32_t stage, bool last) {
+        const uint64_t ad = tc::umma_desc_sw128(q_addr + (w * 2 + qbuf) * FT_Q_BYTES);
         const uint64_t bd = tc::umma_desc_sw128(kv_addr + stage * FT_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < FT_D / 16; k++)
           tc::umma_f16(tmem_base + w * 128, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, k != 0);
         tc::umma_commit(&s_full[w]);
+        if (Q16 && last) tc::umma_commit(&q_empty[w * 2 + qbuf]);   // this Q buffer may be refilled once these retire
       };
+      auto issue_pv = [&](int w, int t, uint32_t stage) {
+        const uint32_t pa = p_addr + w * FT_P_BYTES;
+        const uint32_t va = kv_addr + stage * FT_STAGE_BYTES + FT_K_BYTES;
+#pragma unroll
+        for (int k = 0; k < FT_BN / 16; k++) {
+          const uint64_t bd = tc::umma_desc_sw128(va + (k >> 2) * (FT_D * 128)) + (uint64_t)((k & 3) * 2);
+          if (FT_P_TMEM) {
+            // A = P from tensor memory: lane = query row, 8 columns (16 fp16) per K step
+            tc::umma_f16_ts(tmem_base + 256 + w * 64, tmem_base + 384 + w * 64 + k * 8, bd, idesc_o, (t | k) != 0);
+          } else {
+            const uint64_t ad = tc::umma_desc_sw128(pa + (k >> 2) * (FT_BM * 128)) + (uint64_t)((k & 3) * 2);
+            tc::umma_f16(tmem_base + 256 + w * 64, ad, bd, idesc_o, (t | k) != 0);
+          }
+        }
+        tc::umma_commit(&o_full[w]);
+      };
+      // Fixed issue order per kv tile (blocking waits; a polling scheduler was measured slower: every probe of an
+      // mbarrier costs ~60-90 cycles):  QK_0(t+1), QK_1(t+1), PV_0(t), PV_1(t).
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, it++) {
-        tc::mbar_wait(&q_full[0], it & 1);
-        tc::mbar_wait(&q_full[1], it & 1);
+        qbuf = Q16 ? (it & 1) : 0;
         tc::mbar_wait(&kv_full[kvi % FT_STAGES], (kvi / FT_STAGES) & 1);
-        tc::fence_after_sync();
-        // S buffers are free: the warpgroups drained the previous pair's last S tile before their last p_full arrival
-        issue_qk(0, kvi % FT_STAGES);
-        issue_qk(1, kvi % FT_STAGES);
+        for (int w = 0; w < 2; w++) {
+          tc::mbar_wait(&q_full[w * 2 + qbuf], Q16 ? ((it >> 1) & 1) : (it & 1));
+          // with q arriving by TMA the first Q K^T of a pair no longer waits for the warpgroup's whole previous pair:
+          // it only needs the S buffer, i.e. the previous pair's last S tile copied to registers
+          if (Q16 && cnt > 0) tc::mbar_wait(&s_free[w], (cnt - 1) & 1);
+          tc::fence_after_sync();
+          issue_qk(w, kvi % FT_STAGES, nkt == 1);
+        }
         for (int t = 0; t < nkt; t++) {
           const uint32_t st_cur = (kvi + t) % FT_STAGES, st_next = (kvi + t + 1) % FT_STAGES;
           if (t + 1 < nkt) {
@@ -181,21 +217,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
             for (int w = 0; w < 2; w++) {     // S_w(t) is in registers -> the tensor core may overwrite it
               tc::mbar_wait(&s_free[w], (cnt + t) & 1);
               tc::fence_after_sync();
-              issue_qk(w, st_next);
+              issue_qk(w, st_next, t + 2 == nkt);
             }
           }
           for (int w = 0; w < 2; w++) {       // P_w(t) is in smem (and O_w has been rescaled if needed)
             tc::mbar_wait(&p_full[w], (cnt + t) & 1);
             tc::fence_after_sync();
-            const uint32_t pa = p_addr + w * FT_P_BYTES;
-            const uint32_t va = kv_addr + st_cur * FT_STAGE_BYTES + FT_K_BYTES;
-#pragma unroll
-            for (int k = 0; k < FT_BN / 16; k++) {
-              const uint64_t ad = tc::umma_desc_sw128(pa + (k >> 2) * (FT_BM * 128)) + (uint64_t)((k & 3) * 2);
-              const uint64_t bd = tc::umma_desc_sw128(va + (k >> 2) * (FT_D * 128)) + (uint64_t)((k & 3) * 2);
-              tc::umma_f16(tmem_base + 256 + w * 64, ad, bd, idesc_o, (t | k) != 0);
-            }
-            tc::umma_commit(&o_full[w]);
+            issue_pv(w, t, st_cur);
           }
           tc::umma_commit(&kv_empty[st_cur]);
         }
@@ -212,7 +240,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_sel + w * 128;
     const uint32_t tO = tmem_base + lane_sel + 256 + w * 64;
-    uint8_t* rowQ = sQ + w * FT_Q_BYTES + r * 128;
+    uint8_t* rowQ = sQ + (w * 2) * FT_Q_BYTES + r * 128;
     uint8_t* rowP = sP + w * FT_P_BYTES + r * 128;
     uint32_t cnt = 0;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -220,16 +248,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       const int tile = (pair - b * pairs_per_img) * 2 + w;
       const int row = tile * FT_BM + r;
       const bool valid = row < Nq;
-      if (Q16) {
-        const uint4* __restrict__ qrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(qv) +
-                                                                        ((long long)b * Nq + (valid ? row : 0)) * FT_D);
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-          uint4 a = make_uint4(0u, 0u, 0u, 0u);
-          if (valid) a = qrow[c];
-          st_shared_v4(rowQ + ((c ^ sw) << 4), a.x, a.y, a.z, a.w);
-        }
-      } else {
+      if (!Q16) {   // fp32 queries: converted to fp16 and staged by their owner threads (the fp16 path uses TMA)
         const float4* __restrict__ qrow = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(qv) +
                                                                           ((long long)b * Nq + (valid ? row : 0)) * FT_D);
 #pragma unroll
@@ -238,10 +257,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
           if (valid) { a = qrow[2 * c]; d = qrow[2 * c + 1]; }
           st_shared_v4(rowQ + ((c ^ sw) << 4), pack_h2(a.x, a.y), pack_h2(a.z, a.w), pack_h2(d.x, d.y), pack_h2(d.z, d.w));
         }
+        tc::fence_before_sync();
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&q_full[w * 2]);
       }
-      tc::fence_before_sync();
-      tc::fence_proxy_async();
-      tc::mbar_arrive(&q_full[w]);
 
       float m = -INFINITY, l = 0.f;   // m: the max the probabilities are currently expressed against (may lag)
       for (int t = 0; t < nkt; t++, cnt++) {
@@ -257,9 +276,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
           for (int j = 0; j < FT_BN; j++)
             if (j >= ncols) sv[j] = 0xff800000u;   // -inf
         }
-        float tmax = -INFINITY;
+        // four independent chains for the row maximum and the row sum: a single chain of 112 dependent ops per thread
+        // is latency-bound with only two softmax warps per scheduler
+        float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < FT_BN; j++) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
+        for (int j = 0; j < FT_BN; j += 4) {
+          tm[0] = fmaxf(tm[0], __uint_as_float(sv[j]));
+          tm[1] = fmaxf(tm[1], __uint_as_float(sv[j + 1]));
+          tm[2] = fmaxf(tm[2], __uint_as_float(sv[j + 2]));
+          tm[3] = fmaxf(tm[3], __uint_as_float(sv[j + 3]));
+        }
+        const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
         const float m_new = fmaxf(m, tmax * qscale);   // running max in log2 units (qscale > 0)
         if (t == 0) {
           m = m_new;
@@ -282,19 +309,51 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
             tc::tmem_st_wait();
           }
         }
-        float lsum = 0.f;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FT_P_TMEM) {
+          const uint32_t tP = tmem_base + lane_sel + 384 + w * 64;
+          uint32_t pk[32];
+#pragma unroll
+          for (int g = 0; g < 32; g++) {        // columns 0..31  (scores 0..63)
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[2 * g]), qscale, -m));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[2 * g + 1]), qscale, -m));
+            ls[(2 * g) & 3] += p0; ls[(2 * g + 1) & 3] += p1;
+            pk[g] = pack_h2(p0, p1);
+          }
+          tc::tmem_st32(tP, pk);
+          uint32_t pk2[16];
+#pragma unroll
+          for (int g = 0; g < 16; g++) {        // columns 32..47 (scores 64..95)
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[64 + 2 * g]), qscale, -m));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[64 + 2 * g + 1]), qscale, -m));
+            ls[(2 * g) & 3] += p0; ls[(2 * g + 1) & 3] += p1;
+            pk2[g] = pack_h2(p0, p1);
+          }
+          tc::tmem_st16(tP + 32, pk2);
+          uint32_t pk3[8];
+#pragma unroll
+          for (int g = 0; g < 8; g++) {         // columns 48..55 (scores 96..111)
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[96 + 2 * g]), qscale, -m));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[96 + 2 * g + 1]), qscale, -m));
+            ls[(2 * g) & 3] += p0; ls[(2 * g + 1) & 3] += p1;
+            pk3[g] = pack_h2(p0, p1);
+          }
+          tc::tmem_st8(tP + 48, pk3);
+          tc::tmem_st_wait();
+        } else {
 #pragma unroll
         for (int g = 0; g < FT_BN / 8; g++) {
           float p[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             p[j] = ex2f(fmaf(__uint_as_float(sv[g * 8 + j]), qscale, -m));
-            lsum += p[j];
+            ls[j & 3] += p[j];
           }
           uint8_t* dst = rowP + (g >> 3) * (FT_BM * 128) + (((g & 7) ^ sw) << 4);
           st_shared_v4(dst, pack_h2(p[0], p[1]), pack_h2(p[2], p[3]), pack_h2(p[4], p[5]), pack_h2(p[6], p[7]));
         }
-        l += lsum;
+        }
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
         tc::fence_before_sync();
         tc::fence_proxy_async();
         tc::mbar_arrive(&p_full[w]);
@@ -430,6 +489,7 @@ int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, 
   FlashMaps maps;
   TCX_TRY(tcx_make_operand_map(&maps.k, k16, 2, 64, Nk, 64, B, (long long)Nk * 64, 64, FT_BN));
   TCX_TRY(tcx_make_operand_map(&maps.vt, vt16, 2, Nkp, 64, Nkp, B, (long long)64 * Nkp, 64, 64));
+  maps.q = maps.k;   // unused by the fp32-query kernel
   return flash_tc_launch(maps, q, out, B, Nq, Nk, scale, false, st);
 }
 
@@ -447,5 +507,6 @@ int launch_flash_tc16(const void* q16, const void* kv16, void* out16, int B, int
   FlashMaps maps;
   TCX_TRY(tcx_make_operand_map(&maps.k, kv16, 2, 64, Nk, 128, B, (long long)Nk * 128, 64, FT_BN));
   TCX_TRY(tcx_make_operand_map(&maps.vt, vt16, 2, Nkp, 64, Nkp, B, (long long)64 * Nkp, 64, 64));
+  TCX_TRY(tcx_make_operand_map(&maps.q, q16, 2, 64, Nq, 64, B, (long long)Nq * 64, 64, FT_BM));
   return flash_tc_launch(maps, q16, out16, B, Nq, Nk, scale, true, st);
 }

@@ -65,6 +65,7 @@ _PROTOS = {
     "tcx_bridge_sr_attn_fwd": (_i, [_vp, _pp, _f, _f, _vp, _vp, _i, _i, _vp, _vp]),
     "tcx_flash_attn_workspace_bytes": (_sz, [_i, _i]),
     "tcx_flash_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "tcx_flash_attn_f16_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "tcx_bridge_mixffn_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_mixffn_fwd": (_i, [_vp, _vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_concat_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -480,6 +481,20 @@ def flash_attn(q, kv, scale):
     out = torch.empty_like(q)
     ws = _ws(lib.tcx_flash_attn_workspace_bytes(B, Nk), q)
     _chk(lib.tcx_flash_attn_fwd(_ptr(q), _ptr(kv), _ptr(out), B, Nq, Nk, scale, _ptr(ws), _stream()))
+    return out
+
+
+def flash_attn_f16(q16, kv16, scale):
+    """fp16 form of flash_attn: q16 [B,Nq,64], kv16 [B,Nk,128] (k | v) -> fp16 [B,Nq,64] (tcgen05 kernel)."""
+    require_cuda(q16)
+    lib = load_library()
+    B, Nq, D = q16.shape
+    Nk = kv16.shape[1]
+    if D != 64 or kv16.shape[2] != 128 or kv16.shape[0] != B:
+        raise RuntimeError("flash_attn_f16: expected q [B,Nq,64] and kv [B,Nk,128]")
+    out = torch.empty_like(q16)
+    ws = _ws(lib.tcx_flash_attn_workspace_bytes(B, Nk), q16)
+    _chk(lib.tcx_flash_attn_f16_fwd(_ptr16(q16), _ptr16(kv16), _ptr16(out), B, Nq, Nk, scale, _ptr(ws), _stream()))
     return out
 
 
