@@ -520,6 +520,7 @@ int tcx_set_flag(const char* name, int value) {
 
 int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, long long M, int C, float eps,
                       void* stream) {
+  if (C == 64 || C == 128 || C == 256 || C == 320 || C == 512) return run_ln16_1(x, w, b, nullptr, y, M, C, eps, S(stream));   // exact fp32, vectorised
   return launch_layernorm(x, w, b, y, M, C, eps, S(stream));
 }
 
@@ -1161,6 +1162,8 @@ int tcx_final_expand_head_fwd(const float* x, const float* w, const float* lnw, 
                               const float* cls_w, const float* cls_b, int ncls, float* logits_nchw, int B, int H,
                               int W, void* ws, void* stream) {
   cudaStream_t st = S(stream);
+  if (head_tc_eligible(x, w, ncls))   // one kernel: the 1024-wide expand output never reaches memory
+    return launch_head_tc(x, w, B, H, W, lnw, lnb, eps, cls_w, cls_b, ncls, logits_nchw, reinterpret_cast<float*>(ws), st);
   float* e = reinterpret_cast<float*>(ws);
   GemmParams g = gemm1(x, w, e, B * H * W, 1024, 64);
   TCX_TRY(launch_gemm(g, st));

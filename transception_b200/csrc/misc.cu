@@ -237,28 +237,22 @@ __global__ void __launch_bounds__(256) sr_pack_ln16_kernel(SrPackArgs a, const _
 // =====================================================================================
 // IFF / coordinate attention (reference MSTr.py:1322-1348)
 // =====================================================================================
-// pooled[b][h][k] = mean_w x, pooled[b][H+w][k] = mean_h x  for the 4 concatenated sources. grid (B, 4)
-template <int HW>
-__global__ void iff_pool_kernel(IffSrc src, int C, float* __restrict__ pooled) {
-  const int b = blockIdx.x, s = blockIdx.y, c = threadIdx.x;
-  if (c >= C) return;
-  const float* __restrict__ x = src.p[s] + (long long)b * HW * HW * C + c;
-  float rows[HW], cols[HW];
-#pragma unroll
-  for (int i = 0; i < HW; i++) { rows[i] = 0.f; cols[i] = 0.f; }
-#pragma unroll
-  for (int h = 0; h < HW; h++)
-#pragma unroll
+// pooled[b][h][k] = mean_w x, pooled[b][H+w][k] = mean_h x  for the 4 concatenated sources.
+// grid (H, 4, B), one thread per channel: a block owns one map row (coalesced over channels), writes its row mean and
+// adds its row into the column sums (fp32 atomics on a zeroed buffer; H*W*C per image and source).
+__global__ void __launch_bounds__(512) iff_pool_kernel(IffSrc src, int HW, int C, float* __restrict__ pooled) {
+  const int h = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
+  const float inv = 1.f / (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* __restrict__ x = src.p[s] + (((long long)b * HW + h) * HW) * C + c;
+    float* __restrict__ o = pooled + (long long)b * 2 * HW * 4 * C + s * C + c;
+    float row = 0.f;
     for (int w = 0; w < HW; w++) {
-      const float v = x[(long long)(h * HW + w) * C];
-      rows[h] += v; cols[w] += v;
+      const float v = x[(long long)w * C];
+      row += v;
+      atomicAdd(o + (long long)(HW + w) * 4 * C, v * inv);
     }
-  float* __restrict__ o = pooled + (long long)b * 2 * HW * 4 * C + s * C + c;
-  const float inv = 1.f / HW;
-#pragma unroll
-  for (int i = 0; i < HW; i++) {
-    o[(long long)i * 4 * C] = rows[i] * inv;
-    o[(long long)(HW + i) * 4 * C] = cols[i] * inv;
+    o[(long long)h * 4 * C] = row * inv;
   }
 }
 
@@ -402,15 +396,13 @@ int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st) {
 }
 
 int launch_iff_pool(const IffSrc& src, int B, int HW, int C, float* pooled, cudaStream_t st) {
-  dim3 grid(B, 4);
-  const int threads = (C + 31) / 32 * 32;
-  if (HW == 28) iff_pool_kernel<28><<<grid, threads, 0, st>>>(src, C, pooled);
-  else if (HW == 14) iff_pool_kernel<14><<<grid, threads, 0, st>>>(src, C, pooled);
-  else if (HW == 7) iff_pool_kernel<7><<<grid, threads, 0, st>>>(src, C, pooled);
-  else if (HW == 32) iff_pool_kernel<32><<<grid, threads, 0, st>>>(src, C, pooled);
-  else if (HW == 16) iff_pool_kernel<16><<<grid, threads, 0, st>>>(src, C, pooled);
-  else if (HW == 8) iff_pool_kernel<8><<<grid, threads, 0, st>>>(src, C, pooled);
-  else { tcx_set_error("iff_pool: unsupported map size %d", HW); return -1; }
+  // the column-mean half of `pooled` is accumulated with atomics: zero the buffer first
+  cudaError_t e = cudaMemsetAsync(pooled, 0, (size_t)B * 2 * HW * 4 * C * sizeof(float), st);
+  TCX_REQUIRE(e == cudaSuccess, "iff_pool: memset failed: %s", cudaGetErrorString(e));
+  dim3 grid(HW, 4, B);
+  int threads = (C + 31) / 32 * 32;
+  if (threads > 512) threads = 512;
+  iff_pool_kernel<<<grid, threads, 0, st>>>(src, HW, C, pooled);
   return tcx_check_launch("iff_pool");
 }
 

@@ -44,3 +44,9 @@ int launch_shuffle_ln(const float* in, int B, int H, int W, int s, int c, const 
                       float* out, cudaStream_t st);
 int launch_final_head(const float* in, int B, int H, int W, const float* lnw, const float* lnb, float eps,
                       const float* cw, const float* cb, int ncls, float* out, cudaStream_t st);
+
+// fused FinalPatchExpand_X4 + LayerNorm + class head (head_tc.cu)
+bool head_tc_eligible(const float* x, const float* w, int ncls);
+size_t head_tc_workspace_floats();
+int launch_head_tc(const float* x, const float* w, int B, int H, int W, const float* lnw, const float* lnb, float eps,
+                   const float* cw, const float* cb, int ncls, float* out, float* ws, cudaStream_t st);
