@@ -276,6 +276,17 @@ inline int join_stream(AuxStreams* a, int i, cudaStream_t waiter) {
 // ---- fp16-intermediate pipeline ---------------------------------------------------------------------------------
 inline __half* H16(float* p) { return reinterpret_cast<__half*>(p); }
 
+// optional LayerNorm second output of a GEMM (fused in the tensor-core epilogue when the row is one 64-column group)
+struct LnOut {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  float eps = 0.f;
+  __half* out = nullptr;
+};
+inline void set_ln(GemmEpi& e, const LnOut& ln, int ld, long long stride) {
+  e.ln_w = ln.w; e.ln_b = ln.b; e.ln_eps = ln.eps; e.ln_out = ln.out; e.ld_ln = ld; e.stride_ln = stride;
+}
+
 struct Mix16 {
   const __half* xn;  long long xn_bs;     // [B*N, C] dense (xn_bs = 0) or per-image slabs with batch stride xn_bs
   const __half* w1;  const float* b1;
@@ -342,7 +353,7 @@ int run_ln16_1(const float* x, const float* w, const float* b, __half* y16, floa
 
 // efficient / channel attention with fp16 K/Q/V, context and attention output; y = residual + reproj(att) in fp32
 int run_eff_attn16(const __half* xn16, const void* const* p, const float* residual, float* y, int B, int N, int C,
-                   int reinterpret, float* ws, cudaStream_t st) {
+                   int reinterpret, float* ws, cudaStream_t st, const LnOut& ln = LnOut()) {
   Carver c(ws);
   const size_t bnc = (size_t)B * N * C;
   __half* kqv = H16(c.take(3 * bnc / 2 + 64));
@@ -383,6 +394,7 @@ int run_eff_attn16(const __half* xn16, const void* const* p, const float* residu
   r.ab16 = 1;
   r.g[0].epi.bias = F(p[7]);
   r.g[0].epi.residual = residual;
+  if (ln.out) set_ln(r.g[0].epi, ln, C, 0);      // caller guarantees C == 64
   return launch_gemm(r, st);
 }
 inline bool eff_attn_prepared(const void* const* p, int N, int C, int reinterpret) {
@@ -396,7 +408,7 @@ inline bool bridge_sr_prepared(const void* const* p) {
   return w16_of(p[0]) && w16_of(p[2]) && w16_of(p[4]) && w16_of(p[6]) && w16_of(p[8]) && w16_of(p[10]);
 }
 int run_bridge_sr_attn16(const __half* xn16, const void* const* p, float scale, float ln_eps, const float* residual, float* y,
-                         int B, const BridgeGeom& g, float* ws, cudaStream_t st) {
+                         int B, const BridgeGeom& g, float* ws, cudaStream_t st, const LnOut& ln = LnOut()) {
   Carver c(ws);
   const size_t bn = (size_t)B * g.ntok * 64;
   __half* q = H16(c.take(bn / 2 + 64));
@@ -451,6 +463,7 @@ int run_bridge_sr_attn16(const __half* xn16, const void* const* p, float scale, 
   gp.ab16 = 1;
   gp.g[0].epi.bias = F(p[5]);
   gp.g[0].epi.residual = residual;
+  if (ln.out) set_ln(gp.g[0].epi, ln, 64, 0);
   return launch_gemm(gp, st);
 }
 
@@ -751,10 +764,14 @@ int tcx_mhca_blocks_fwd(const float* x_in, float* x, const void* const* p, int G
         for (int g = 0; g < G; g++) {
           gp.g[g].A = F(att16 + g * bnc); gp.g[g].W = F(w16_of(blk[g][12])); gp.g[g].C = xb + g * bnc;
           gp.g[g].epi.bias = F(blk[g][13]); gp.g[g].epi.residual = xa + g * bnc; gp.g[g].epi.ldr = C;
+          if (C == 64) {       // norm2 in the projection's epilogue
+            LnOut ln; ln.w = F(blk[g][14]); ln.b = F(blk[g][15]); ln.eps = ln_eps; ln.out = ln16 + g * bnc;
+            set_ln(gp.g[g].epi, ln, C, 0);
+          }
         }
         TCX_TRY(launch_gemm(gp, st));
       }
-      {
+      if (C != 64) {
         const float* xs[TCX_MAX_GROUPS]; const float* ws[TCX_MAX_GROUPS]; const float* bs[TCX_MAX_GROUPS];
         __half* ys[TCX_MAX_GROUPS];
         for (int g = 0; g < G; g++) { xs[g] = xb + g * bnc; ws[g] = F(blk[g][14]); bs[g] = F(blk[g][15]); ys[g] = ln16 + g * bnc; }
@@ -1058,6 +1075,20 @@ int tcx_eff_block_fwd(const float* x, const void* const* p, float ln_eps, float 
   float* tx = c.take(bnc);
   float* aws = c.take(tcx_eff_attn_workspace_bytes(B, N, C) / 4);
   float* mws = c.take(tcx_mixffn_skip_workspace_bytes(B, N, 4 * C) / 4);
+  Mix16 mprobe{};
+  const bool fuse_ln2 = C == 64 && eff_attn_prepared(p + 2, N, C, 0) && mix16_fill(p + 12, mprobe);
+  // n16b: fp16 norm2 output written by the reprojection GEMM's epilogue (second half of the n buffer)
+  __half* n16b = H16(n) + bnc;
+  if (fuse_ln2) {
+    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n), nullptr, (long long)B * N, C, ln_eps, st));
+    LnOut ln; ln.w = F(p[10]); ln.b = F(p[11]); ln.eps = ln_eps; ln.out = n16b;
+    TCX_TRY(run_eff_attn16(H16(n), p + 2, x, tx, B, N, C, 0, aws, st, ln));
+    Carver mc(mws);
+    __half* h = H16(mc.take(bnc * 2));
+    __half* a = H16(mc.take(bnc * 2));
+    mprobe.xn = n16b; mprobe.res = tx; mprobe.y = y;
+    return run_mixffn16(1, &mprobe, mlp_ln_eps, B, H, W, C, 4 * C, h, a, st);
+  }
   if (eff_attn_prepared(p + 2, N, C, 0)) {
     TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n), nullptr, (long long)B * N, C, ln_eps, st));
     TCX_TRY(run_eff_attn16(H16(n), p + 2, x, tx, B, N, C, 0, aws, st));
@@ -1105,20 +1136,26 @@ int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, 
   if (sr > att) att = sr;
   float* aws = c.take(att / 4);
   float* mws = c.take(tcx_bridge_mixffn_workspace_bytes(B, S0) / 4);
+  const bool mixp = bridge_mix_prepared(p + 18);
+  LnOut ln2;       // norm2 fused into the attention's output projection (64-wide rows) when the Mix-FFNs take fp16
+  if (mixp) { ln2.w = F(p[16]); ln2.b = F(p[17]); ln2.eps = ln_eps; ln2.out = H16(tx); }
+  bool ln2_done = false;
   if (channel_att && eff_attn_prepared(p + 2, g.ntok, 64, 1)) {
     TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
-    TCX_TRY(run_eff_attn16(H16(n1), p + 2, x, tx1, B, g.ntok, 64, 1, aws, st));
+    TCX_TRY(run_eff_attn16(H16(n1), p + 2, x, tx1, B, g.ntok, 64, 1, aws, st, ln2));
+    ln2_done = mixp;
   } else if (!channel_att && flash_tc_enabled() && bridge_sr_prepared(p + 2)) {
     TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
-    TCX_TRY(run_bridge_sr_attn16(H16(n1), p + 2, scale, ln_eps, x, tx1, B, g, aws, st));
+    TCX_TRY(run_bridge_sr_attn16(H16(n1), p + 2, scale, ln_eps, x, tx1, B, g, aws, st, ln2));
+    ln2_done = mixp;
   } else {
     TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n1, M, 64, ln_eps, st));
     if (channel_att) TCX_TRY(tcx_eff_attn_fwd(n1, p + 2, x, tx1, B, g.ntok, 64, 1, aws, stream));
     else TCX_TRY(tcx_bridge_sr_attn_fwd(n1, p + 2, scale, ln_eps, x, tx1, B, S0, aws, stream));
   }
-  if (bridge_mix_prepared(p + 18)) {
+  if (mixp) {
     __half* tx16 = H16(tx);
-    TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), tx16, nullptr, M, 64, ln_eps, st));
+    if (!ln2_done) TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), tx16, nullptr, M, 64, ln_eps, st));
     return bridge_mixffn16(tx16, tx1, p + 18, ln_eps, y, B, g, mws, st);
   }
   TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), nullptr, tx, M, 64, ln_eps, st));

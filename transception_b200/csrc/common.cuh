@@ -120,6 +120,14 @@ struct GemmEpi {
   const float* residual;  // [M, ldr] or null (added after act)
   int ldr;
   long long strideR;      // batch stride of residual
+  // optional second output (tensor-core kernel, fp16 operands, fp32 C): ln_out[m, 64g .. 64g+63] = fp16 LayerNorm over
+  // each 64-column group of the finished row (affine ln_w / ln_b of length 64) — the consumer GEMM's A operand
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  void* ln_out;           // fp16 [M, ld_ln] or null
+  int ld_ln;
+  long long stride_ln;
 };
 struct GemmGroup {
   const float* A;

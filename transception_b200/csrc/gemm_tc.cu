@@ -67,12 +67,14 @@ struct TmaSet {
   CUtensorMap w[TCX_MAX_GROUPS];
   CUtensorMap c[TCX_MAX_GROUPS];
   CUtensorMap r[TCX_MAX_GROUPS];   // residual (valid only when the group has one)
+  CUtensorMap l[TCX_MAX_GROUPS];   // fp16 LayerNorm output (LN kernels only)
 };
 
 // dynamic shared memory plan (host-computed): [A stages][B stages][out 8x2x4K][res 8x2x4K]?[col 8x1K][barriers]
 struct SmemPlan {
-  int off_b, off_out, off_res, off_col, off_bar, stages, total;
+  int off_b, off_out, off_res, off_ln, off_col, off_bar, stages, total;
 };
+constexpr int COL_BYTES = 2048;               // per epilogue warp: [2][scale 64 | shift 64] + LN weight 64 + LN bias 64
 
 struct TileCoord {
   int gi, bi, m0, n0;
@@ -190,7 +192,7 @@ __device__ __forceinline__ void ld32_at(uint32_t taddr, uint32_t (&s)[N]) {
                : "memory");
 }
 
-template <int BN, bool AB16, bool OUT16>
+template <int BN, bool AB16, bool OUT16, bool LN>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmaSet maps,
                                                                 const __grid_constant__ GemmParams p,
                                                                 const __grid_constant__ SmemPlan sp) {
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) {
       tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], EPI_WARPS * 32);
+      tc::mbar_init(&acc_empty[a], LN ? EPI_WARPS * 16 : EPI_WARPS * 32);   // LN: one warp set per accumulator
     }
     for (int i = 0; i < 2 * EPI_WARPS; i++) tc::mbar_init(&res_full[i], 1);
     tc::fence_barrier_init();
@@ -292,13 +294,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int sw = lane & 7;
     uint8_t* out_w = smem + sp.off_out + ew * 2 * SUB_BYTES;
     uint8_t* res_w = smem + sp.off_res + ew * 2 * SUB_BYTES;
-    float* col_w = reinterpret_cast<float*>(smem + sp.off_col + ew * 1024);   // [2][scale 64 | shift 64]
+    float* col_w = reinterpret_cast<float*>(smem + sp.off_col + ew * COL_BYTES);   // [2][scale 64 | shift 64] | LN w, b
+    uint8_t* ln_w_buf = smem + sp.off_ln + ew * SUB_BYTES;
+    // LN kernels: the thread needs its whole 64-column row, so a tile is finished by ONE warp set (half == accumulator
+    // index) instead of both sets splitting the slabs; the two sets then work on alternate tiles
+    constexpr int S0_STEP = LN ? 1 : 2;
     uint64_t* rbar = res_full + ew * 2;
 
-    int pf_tile = blockIdx.x, pf_slab = half;
+    int pf_tile = blockIdx.x + (LN ? half * (int)gridDim.x : 0), pf_slab = LN ? 0 : half;
+    const int pf_tile_step = LN ? 2 * (int)gridDim.x : (int)gridDim.x;
     uint32_t pf_count = 0;
     auto prefetch_res = [&]() {      // lane 0: next live residual sub-slab of this warp
-      while (pf_tile < ntiles && half < NSLAB) {
+      while (pf_tile < ntiles && (LN || half < NSLAB)) {
         const TileCoord t = tile_coord(pf_tile, mt, nt, p.batch, BN);
         const bool live = p.g[t.gi].epi.residual != nullptr && t.n0 + pf_slab * SLABC < p.N;
         if (live) {
@@ -308,8 +315,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
                           p.g[t.gi].epi.strideR ? t.bi : 0, &rbar[b]);
           pf_count++;
         }
-        pf_slab += 2;
-        if (pf_slab >= NSLAB) { pf_slab = half; pf_tile += gridDim.x; }
+        pf_slab += S0_STEP;
+        if (pf_slab >= NSLAB) { pf_slab = LN ? 0 : half; pf_tile += pf_tile_step; }
         if (live) return;
       }
     };
@@ -317,6 +324,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     uint32_t ti = 0, out_count = 0, res_count = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
+      if (LN && (int)(ti & 1) != half) continue;
       const TileCoord t = tile_coord(tile, mt, nt, p.batch, BN);
       const GemmEpi& e = p.g[t.gi].epi;
       const bool has_res = !OUT16 && e.residual != nullptr;
@@ -327,6 +335,88 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::fence_after_sync();
       const uint32_t tacc = tmem_base + a * BN + ((uint32_t)(quarter * 32) << 16);
       bool arrived = false;
+      if constexpr (LN) {
+        static_assert(!LN || (BN == 64 && !OUT16), "LN epilogue: BN = 64, fp32 C");
+        float yv[BN];
+        float* lnc = col_w + 256;                       // LN weight | bias of this tile's group
+        lnc[lane] = __ldg(e.ln_w + lane); lnc[lane + 32] = __ldg(e.ln_w + lane + 32);
+        lnc[64 + lane] = __ldg(e.ln_b + lane); lnc[96 + lane] = __ldg(e.ln_b + lane + 32);
+#pragma unroll
+        for (int s = 0; s < NSLAB; s++) {
+          const int col0 = t.n0 + s * SLABC;
+          const uint32_t ob = out_count & 1;
+          uint32_t v[SLABC];
+          ld32_at<0>(tacc + s * SLABC, v);
+          float* cs = col_w + ob * 128;
+          cs[64 + lane] = (e.bias && col0 + lane < p.N) ? __ldg(e.bias + col0 + lane) : 0.f;
+          if (lane == 0) {
+            bulk_wait_read<2>();                                 // groups per tile: slab, slab, LN (three buffers)
+            if (has_res) prefetch_res();
+          }
+          __syncwarp();
+          tc::tmem_ld_wait();
+          if (s == NSLAB - 1) {
+            tc::fence_before_sync();
+            tc::mbar_arrive(&acc_empty[a]);
+            arrived = true;
+          }
+          uint8_t* orow = out_w + ob * SUB_BYTES + lane * 128;
+          const uint8_t* rrow = res_w + (res_count & 1) * SUB_BYTES + lane * 128;
+          if (has_res) tc::mbar_wait(&rbar[res_count & 1], (res_count >> 1) & 1);
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const float4 sh = *reinterpret_cast<const float4*>(cs + 64 + c * 4);
+            const int phys = (c ^ sw) << 4;
+            float4 y = make_float4(__uint_as_float(v[c * 4]) + sh.x, __uint_as_float(v[c * 4 + 1]) + sh.y,
+                                   __uint_as_float(v[c * 4 + 2]) + sh.z, __uint_as_float(v[c * 4 + 3]) + sh.w);
+            if (has_res) {
+              const float4 rv = *reinterpret_cast<const float4*>(rrow + phys);
+              y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+            }
+            yv[s * 32 + c * 4] = y.x; yv[s * 32 + c * 4 + 1] = y.y; yv[s * 32 + c * 4 + 2] = y.z; yv[s * 32 + c * 4 + 3] = y.w;
+            *reinterpret_cast<float4*>(orow + phys) = y;
+          }
+          if (has_res) res_count++;
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&maps.c[t.gi], out_w + ob * SUB_BYTES, col0, t.m0 + quarter * 32, p.strideC ? t.bi : 0);
+            bulk_commit();
+          }
+          out_count++;
+        }
+        // LayerNorm of the finished 64-column row (exact two-pass statistics in registers) -> fp16 slab
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) { s0 += yv[i]; s1 += yv[i + 1]; s2 += yv[i + 2]; s3 += yv[i + 3]; }
+        const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / BN);
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < BN; i += 4) {
+          const float d0 = yv[i] - mean, d1 = yv[i + 1] - mean, d2 = yv[i + 2] - mean, d3 = yv[i + 3] - mean;
+          q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+        }
+        const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.f / BN) + e.ln_eps);
+        if (lane == 0) bulk_wait_read<2>();                      // the previous tile's LN store has left ln_w_buf
+        __syncwarp();
+        uint8_t* lrow = ln_w_buf + lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const float4 w0 = *reinterpret_cast<const float4*>(lnc + c * 8), w1 = *reinterpret_cast<const float4*>(lnc + c * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(lnc + 64 + c * 8), b1 = *reinterpret_cast<const float4*>(lnc + 64 + c * 8 + 4);
+          *reinterpret_cast<uint4*>(lrow + ((c ^ sw) << 4)) = make_uint4(
+              pack_h2(fmaf((yv[c * 8 + 0] - mean) * rstd, w0.x, b0.x), fmaf((yv[c * 8 + 1] - mean) * rstd, w0.y, b0.y)),
+              pack_h2(fmaf((yv[c * 8 + 2] - mean) * rstd, w0.z, b0.z), fmaf((yv[c * 8 + 3] - mean) * rstd, w0.w, b0.w)),
+              pack_h2(fmaf((yv[c * 8 + 4] - mean) * rstd, w1.x, b1.x), fmaf((yv[c * 8 + 5] - mean) * rstd, w1.y, b1.y)),
+              pack_h2(fmaf((yv[c * 8 + 6] - mean) * rstd, w1.z, b1.z), fmaf((yv[c * 8 + 7] - mean) * rstd, w1.w, b1.w)));
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps.l[t.gi], ln_w_buf, t.n0, t.m0 + quarter * 32, e.stride_ln ? t.bi : 0);
+          bulk_commit();
+        }
+      } else {
 #pragma unroll 1
       for (int s = half; s < NSLAB; s += 2) {
         const int col0 = t.n0 + s * SLABC;
@@ -379,6 +469,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
         out_count++;
       }
+      }
       if (!arrived) {
         tc::fence_before_sync();
         tc::mbar_arrive(&acc_empty[a]);
@@ -405,27 +496,29 @@ int sm_count() {
   return g_sm_count;
 }
 
-SmemPlan make_plan(int bn, bool has_res) {
+SmemPlan make_plan(int bn, bool has_res, bool ln) {
   SmemPlan sp{};
   const int stage = STAGE_A + bn * KB_BYTES;
-  const int fixed = EPI_WARPS * 2 * SUB_BYTES * (has_res ? 2 : 1) + EPI_WARPS * 1024 + 512;
+  const int sub = EPI_WARPS * 2 * SUB_BYTES;
+  const int fixed = sub + (has_res ? sub : 0) + (ln ? EPI_WARPS * SUB_BYTES : 0) + EPI_WARPS * COL_BYTES + 512;
   int stages = (SMEM_BUDGET - 1024 - fixed) / stage;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   sp.stages = stages;
   sp.off_b = stages * STAGE_A;
   sp.off_out = sp.off_b + stages * bn * KB_BYTES;
-  sp.off_res = sp.off_out + EPI_WARPS * 2 * SUB_BYTES;
-  sp.off_col = sp.off_res + (has_res ? EPI_WARPS * 2 * SUB_BYTES : 0);
-  sp.off_bar = sp.off_col + EPI_WARPS * 1024;
+  sp.off_res = sp.off_out + sub;
+  sp.off_ln = sp.off_res + (has_res ? sub : 0);
+  sp.off_col = sp.off_ln + (ln ? EPI_WARPS * SUB_BYTES : 0);
+  sp.off_bar = sp.off_col + EPI_WARPS * COL_BYTES;
   sp.total = sp.off_bar + 512 + 1024;   // + slack for the 1024-byte alignment of the dynamic base
   return sp;
 }
 
-template <int BN, bool AB16, bool OUT16>
+template <int BN, bool AB16, bool OUT16, bool LN = false>
 int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AB16, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AB16, OUT16, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SMEM_BUDGET);
     TCX_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     done = true;
@@ -439,10 +532,10 @@ int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cuda
   for (int i = 0; i < p.groups; i++) {
     const double nb = (double)p.batch;
     bytes += nb * p.M * p.K * ae + (p.strideW ? nb : 1.0) * p.N * p.K * ae + nb * p.M * p.N * ce +
-             (p.g[i].epi.residual ? nb * p.M * p.N * 4.0 : 0.0);
+             (p.g[i].epi.residual ? nb * p.M * p.N * 4.0 : 0.0) + (LN ? nb * p.M * p.N * 2.0 : 0.0);
   }
   ProfScope prof("gemm_tc", st, bytes);
-  cudaError_t le = tcx_launch_pdl(gemm_tc_kernel<BN, AB16, OUT16>, dim3(grid), dim3(GT_THREADS), (size_t)sp.total, st, maps, p, sp);
+  cudaError_t le = tcx_launch_pdl(gemm_tc_kernel<BN, AB16, OUT16, LN>, dim3(grid), dim3(GT_THREADS), (size_t)sp.total, st, maps, p, sp);
   TCX_REQUIRE(le == cudaSuccess, "gemm_tc: launch failed: %s", cudaGetErrorString(le));
   return tcx_check_launch("gemm_tc");
 }
@@ -469,6 +562,8 @@ bool gemm_tc_eligible(const GemmParams& p) {
     const GemmEpi& e = p.g[i].epi;
     if (e.residual && ((((uintptr_t)e.residual) & 15) || (e.ldr & 3) || (e.strideR & 3))) return false;
     if (p.out16 && (e.residual || e.bn.w || e.act != ACT_NONE)) return false;
+    if (e.ln_out && (!p.ab16 || p.out16 || (p.N & 63) || (e.ld_ln & 7) || (e.stride_ln & 7) || (((uintptr_t)e.ln_out) & 15) ||
+                     !e.ln_w || !e.ln_b)) return false;
     if (p.ab16 && (e.bn.w || e.act != ACT_NONE)) return false;
   }
   return tcx_get_encode_tiled() != nullptr;
@@ -478,8 +573,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   const long long mtiles = (long long)cdiv(p.M, BM) * p.groups * p.batch;
   bool has_res = false;
   for (int i = 0; i < p.groups; i++) has_res |= p.g[i].epi.residual != nullptr;
+  bool ln = false;
+  for (int i = 0; i < p.groups; i++) ln |= p.g[i].epi.ln_out != nullptr;
+  if (ln)
+    for (int i = 0; i < p.groups; i++) TCX_REQUIRE(p.g[i].epi.ln_out != nullptr, "gemm_tc: LN output must be set for every group");
   int bn = 64;
-  if (!has_res && p.N % 256 == 0 && mtiles * (p.N / 256) >= 2 * sm_count()) bn = 256;
+  if (ln) bn = 64;            // one 64-column LayerNorm group per tile
+  else if (!has_res && p.N % 256 == 0 && mtiles * (p.N / 256) >= 2 * sm_count()) bn = 256;
   else if (p.N % 128 == 0 && mtiles * (p.N / 128) >= 2 * sm_count()) bn = 128;
   const int ae = p.ab16 ? 2 : 4, ce = p.out16 ? 2 : 4;
   const int kbe = KB_BYTES / ae, slabc = 128 / ce;
@@ -493,11 +593,16 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
       TCX_TRY(tcx_make_operand_map(&maps.r[i], e.residual, 4, p.N, p.M, e.ldr, p.batch, e.strideR, 32, 32));
     else
       maps.r[i] = maps.c[i];
+    if (e.ln_out)
+      TCX_TRY(tcx_make_operand_map(&maps.l[i], e.ln_out, 2, p.N, p.M, e.ld_ln, p.batch, e.stride_ln, 64, 32));
+    else
+      maps.l[i] = maps.c[i];
   }
   for (int i = p.groups; i < TCX_MAX_GROUPS; i++) {
-    maps.a[i] = maps.a[0]; maps.w[i] = maps.w[0]; maps.c[i] = maps.c[0]; maps.r[i] = maps.r[0];
+    maps.a[i] = maps.a[0]; maps.w[i] = maps.w[0]; maps.c[i] = maps.c[0]; maps.r[i] = maps.r[0]; maps.l[i] = maps.l[0];
   }
-  const SmemPlan sp = make_plan(bn, has_res);
+  const SmemPlan sp = make_plan(bn, has_res, ln);
+  if (ln) return launch_cfg<64, true, false, true>(maps, p, sp, st);
   if (p.ab16) return p.out16 ? launch_bn<true, true>(bn, maps, p, sp, st) : launch_bn<true, false>(bn, maps, p, sp, st);
   TCX_REQUIRE(!p.out16, "gemm_tc: fp16 output needs fp16 operands");
   return launch_bn<false, false>(bn, maps, p, sp, st);
