@@ -168,6 +168,13 @@ size_t tcx_bridge_layer_workspace_bytes(int B, int S);
 int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, float scale, float ln_eps, float* y,
                          int B, int S, void* ws, void* stream);
 
+/* BridgeBlock_4.forward (MSTr.py:2422-2431): L chained BridgLayer_4 on the token buffer, p = L x TCX_BRIDGE_NP slots,
+ * channel_att[l] selects the attention of layer l.  Same arithmetic as L calls of tcx_bridge_layer_fwd; in the fp16
+ * pipeline the norm1 of layer l+1 is produced by the Mix-FFN epilogues of layer l. */
+size_t tcx_bridge_block_workspace_bytes(int B, int S);
+int tcx_bridge_block_fwd(const float* x, const void* const* p, const int* channel_att, int L, float scale, float ln_eps,
+                         float* y, int B, int S, void* ws, void* stream);
+
 /* decoder — MyDecoderLayer.forward pieces (MSTr.py:273-290, :184-201, :212-227) */
 int tcx_concat_linear_fwd(const float* x1, const float* x2, const float* w, const float* b, float* y, int M, int C1,
                           int C2, int N, void* stream);

@@ -294,6 +294,7 @@ struct Mix16 {
   const __half* w2;  const float* b2;
   const float* res;  long long res_bs;
   float* y;          long long y_bs;
+  LnOut ln;          long long ln_bs;     // optional fp16 LayerNorm (64-column groups) of y, fused in fc2's epilogue
 };
 // all matrices of a Mix-FFN parameter block {fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b} prepared?
 inline bool mix16_fill(const void* const* p, Mix16& m) {
@@ -331,6 +332,7 @@ int run_mixffn16(int G, const Mix16* m, float eps, int B, int H, int W, int C, i
     for (int i = 0; i < G; i++) {
       g.g[i].A = F(abuf + i * per); g.g[i].W = F(m[i].w2); g.g[i].C = m[i].y;
       g.g[i].epi.bias = m[i].b2; g.g[i].epi.residual = m[i].res; g.g[i].epi.ldr = C; g.g[i].epi.strideR = m[i].res_bs;
+      if (m[i].ln.out) set_ln(g.g[i].epi, m[i].ln, C, m[i].ln_bs);
     }
     TCX_TRY(launch_gemm(g, st));
   }
@@ -993,7 +995,7 @@ size_t tcx_bridge_mixffn_workspace_bytes(int B, int S0) {
 
 // the four per-scale Mix-FFNs of one bridge layer on the fp16 LayerNorm output tx16 [B][ntok][64]
 static int bridge_mixffn16(const __half* tx16, const float* tx1, const void* const* p, float ln_eps, float* y, int B,
-                           const BridgeGeom& g, float* ws, cudaStream_t st) {
+                           const BridgeGeom& g, float* ws, cudaStream_t st, const LnOut* next = nullptr) {
   Carver c(ws);
   const long long sb = (long long)g.ntok * 64;
   AuxStreams* aux = aux_streams(st);
@@ -1006,6 +1008,11 @@ static int bridge_mixffn16(const __half* tx16, const float* tx1, const void* con
     Mix16 m{};
     TCX_REQUIRE(mix16_fill(p + 8 * k, m), "bridge_mixffn16: weights of scale %d are not prepared", k);
     m.xn = tx16 + off; m.xn_bs = sb; m.res = tx1 + off; m.res_bs = sb; m.y = y + off; m.y_bs = sb;
+    // The LN epilogue leaves the GEMM only two smem stages; with fc2's long K loop (4C = 256..2048) that costs more than
+    // the separate LayerNorm kernel it saves (measured: +5 us per GEMM), so it is taken only for short-K tiles.
+    if (next && next->out && C4 <= 128) {   // next layer's norm1 over every 64-wide token of this slab, as fp16 tokens
+      m.ln = *next; m.ln.out = next->out + off; m.ln_bs = sb;
+    }
     cudaStream_t sk = (aux && k > 0) ? aux->s[k - 1] : st;
     TCX_TRY(run_mixffn16(1, &m, ln_eps, B, hw, hw, C, C4, h, a, sk));
   }
@@ -1120,8 +1127,12 @@ size_t tcx_bridge_layer_workspace_bytes(int B, int S0) {
   return 4 * (3 * rnd(bn)) + att + tcx_bridge_mixffn_workspace_bytes(B, S0) + 1024;
 }
 
-int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, float scale, float ln_eps, float* y,
-                         int B, int S0, void* ws, void* stream) {
+// n1_in: this layer's norm1 output already computed (fp16) by the previous layer's epilogues, or null.
+// next: norm1 of the FOLLOWING layer to be produced by this layer's fc2 epilogues (fp16 pipeline only), or null;
+// *next_done tells the caller whether that happened.
+static int bridge_layer_impl(const float* x, const void* const* p, int channel_att, float scale, float ln_eps, float* y,
+                             int B, int S0, void* ws, void* stream, const __half* n1_in, const LnOut* next, bool* next_done) {
+  if (next_done) *next_done = false;
   cudaStream_t st = S(stream);
   BridgeGeom g;
   TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
@@ -1141,12 +1152,12 @@ int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, 
   if (mixp) { ln2.w = F(p[16]); ln2.b = F(p[17]); ln2.eps = ln_eps; ln2.out = H16(tx); }
   bool ln2_done = false;
   if (channel_att && eff_attn_prepared(p + 2, g.ntok, 64, 1)) {
-    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
-    TCX_TRY(run_eff_attn16(H16(n1), p + 2, x, tx1, B, g.ntok, 64, 1, aws, st, ln2));
+    if (!n1_in) TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
+    TCX_TRY(run_eff_attn16(n1_in ? n1_in : H16(n1), p + 2, x, tx1, B, g.ntok, 64, 1, aws, st, ln2));
     ln2_done = mixp;
   } else if (!channel_att && flash_tc_enabled() && bridge_sr_prepared(p + 2)) {
-    TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
-    TCX_TRY(run_bridge_sr_attn16(H16(n1), p + 2, scale, ln_eps, x, tx1, B, g, aws, st, ln2));
+    if (!n1_in) TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), H16(n1), nullptr, M, 64, ln_eps, st));
+    TCX_TRY(run_bridge_sr_attn16(n1_in ? n1_in : H16(n1), p + 2, scale, ln_eps, x, tx1, B, g, aws, st, ln2));
     ln2_done = mixp;
   } else {
     TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), nullptr, n1, M, 64, ln_eps, st));
@@ -1156,10 +1167,53 @@ int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, 
   if (mixp) {
     __half* tx16 = H16(tx);
     if (!ln2_done) TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), tx16, nullptr, M, 64, ln_eps, st));
-    return bridge_mixffn16(tx16, tx1, p + 18, ln_eps, y, B, g, mws, st);
+    if (next_done) *next_done = false;     // see bridge_mixffn16: the fc2 epilogue fusion is not taken at these K
+    return bridge_mixffn16(tx16, tx1, p + 18, ln_eps, y, B, g, mws, st, next);
   }
   TCX_TRY(run_ln16_1(tx1, F(p[16]), F(p[17]), nullptr, tx, M, 64, ln_eps, st));
   return tcx_bridge_mixffn_fwd(tx, tx1, p + 18, ln_eps, y, B, S0, mws, stream);
+}
+
+int tcx_bridge_layer_fwd(const float* x, const void* const* p, int channel_att, float scale, float ln_eps, float* y,
+                         int B, int S0, void* ws, void* stream) {
+  return bridge_layer_impl(x, p, channel_att, scale, ln_eps, y, B, S0, ws, stream, nullptr, nullptr, nullptr);
+}
+
+size_t tcx_bridge_block_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  const size_t bn = (size_t)B * g.ntok * 64;
+  return 4 * (rnd(bn) + 2 * rnd(bn / 2 + 64)) + tcx_bridge_layer_workspace_bytes(B, S0) + 1024;
+}
+
+int tcx_bridge_block_fwd(const float* x, const void* const* p, const int* channel_att, int L, float scale, float ln_eps,
+                         float* y, int B, int S0, void* ws, void* stream) {
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  TCX_REQUIRE(L >= 1, "bridge_block: L must be >= 1");
+  const size_t bn = (size_t)B * g.ntok * 64;
+  Carver c(ws);
+  float* xb = c.take(bn);                      // ping-pong partner of y for the layer outputs
+  __half* n1buf[2] = {H16(c.take(bn / 2 + 64)), H16(c.take(bn / 2 + 64))};
+  float* lws = c.take(tcx_bridge_layer_workspace_bytes(B, S0) / 4);
+  const float* cur = x;
+  const __half* n1_in = nullptr;
+  for (int l = 0; l < L; l++) {
+    // layer outputs alternate so that the last one lands in y
+    float* dst = ((L - 1 - l) & 1) ? xb : y;
+    const void* const* pl = p + (size_t)l * TCX_BRIDGE_NP;
+    LnOut next;
+    if (l + 1 < L) {
+      const void* const* pn = p + (size_t)(l + 1) * TCX_BRIDGE_NP;
+      next.w = F(pn[0]); next.b = F(pn[1]); next.eps = ln_eps; next.out = n1buf[l & 1];
+    }
+    bool done = false;
+    TCX_TRY(bridge_layer_impl(cur, pl, channel_att[l], scale, ln_eps, dst, B, S0, lws, stream, n1_in,
+                              l + 1 < L ? &next : nullptr, &done));
+    n1_in = done ? n1buf[l & 1] : nullptr;
+    cur = dst;
+  }
+  return 0;
 }
 
 // ---- decoder ----------------------------------------------------------------------------------

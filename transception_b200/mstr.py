@@ -671,9 +671,16 @@ class BridgeBlock_4(nn.Module):
             setattr(self, 'bridge_layer%d' % (i + 1), BridgLayer_4(dims, head, reduction_ratios, br_ch_att_list[i]))
 
     def tokens(self, x):
+        if isinstance(x, (list, tuple)):
+            x = ops.bridge_regroup([_nhwc(c) for c in x])
+        layers = []
         for i in range(4):
-            x = getattr(self, 'bridge_layer%d' % (i + 1))(x)
-        return x
+            lay = getattr(self, 'bridge_layer%d' % (i + 1))
+            layers.append((lay.norm1.weight, lay.norm1.bias, isinstance(lay.attn, M_EfficientChannelAtten), lay.attn.slots(),
+                           lay.norm2.weight, lay.norm2.bias,
+                           [m.args() for m in (lay.mixffn1, lay.mixffn2, lay.mixffn3, lay.mixffn4)]))
+        l0 = self.bridge_layer1
+        return ops.bridge_block(x, layers, l0.attn.scale, l0.norm1.eps)
 
     def forward(self, x):
         t = self.tokens(x)

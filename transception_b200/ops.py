@@ -41,6 +41,8 @@ _PROTOS = {
     "tcx_eff_block_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_layer_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_layer_fwd": (_i, [_vp, _pp, _i, _f, _f, _vp, _i, _i, _vp, _vp]),
+    "tcx_bridge_block_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_bridge_block_fwd": (_i, [_vp, _pp, ctypes.POINTER(_i), _i, _f, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_linear_bn_act_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _i, _i, _i, _vp]),
     "tcx_patch_embed_ln_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
     "tcx_dwconv_tokens_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -557,6 +559,42 @@ def bridge_layer(x, n1w, n1b, ln_eps, channel_att, attn_slots, scale, n2w, n2b, 
     ws = _ws(lib.tcx_bridge_layer_workspace_bytes(B, S), x)
     _chk(lib.tcx_bridge_layer_fwd(_ptr(x), _table(slots, mats), int(channel_att), scale, ln_eps, _ptr(y), B, S,
                                   _ptr(ws), _stream()))
+    return y
+
+
+def _bridge_layer_slots(n1w, n1b, channel_att, attn_slots, n2w, n2b, mix_args_list):
+    attn_slots = list(attn_slots) + [None] * (14 - len(attn_slots))
+    slots = [n1w, n1b] + attn_slots + [n2w, n2b]
+    for a in mix_args_list:
+        slots.extend(_mix_slots(a)[0])
+    mats = [18 + 8 * k + j for k in range(4) for j in (0, 6)]
+    if channel_att:
+        mats += [2, 4, 6, 8]
+    else:
+        mats += [2, 4, 6]
+        for k, (cin, r) in enumerate(((64, 8), (128, 4), (320, 2))):
+            prepare_weight(slots[8 + 2 * k], conv=(cin, cin, r))
+    return slots, mats
+
+
+def bridge_block(x, layers, scale, ln_eps):
+    """BridgeBlock_4.forward on the token buffer: ``layers`` = [(n1w, n1b, channel_att, attn_slots, n2w, n2b, mix_args_list)]."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, ntok, C = x.shape
+    S = _bridge_side(ntok)
+    slots, mats, flags = [], [], []
+    for i, lay in enumerate(layers):
+        sl, mt = _bridge_layer_slots(*lay)
+        mats += [i * 50 + m for m in mt]
+        slots += sl
+        flags.append(int(lay[2]))
+    y = torch.empty_like(x)
+    ws = _ws(lib.tcx_bridge_block_workspace_bytes(B, S), x)
+    fl = (ctypes.c_int * len(flags))(*flags)
+    _chk(lib.tcx_bridge_block_fwd(_ptr(x), _table(slots, mats), fl, len(layers), scale, ln_eps, _ptr(y), B, S, _ptr(ws),
+                                  _stream()))
     return y
 
 
