@@ -95,7 +95,7 @@ def cpu_reference_time(torch, steps, warmup, budget_s=150.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
-    sd = {k: v for k, v in MSTransception(num_classes=NCLS).state_dict().items()}
+    sd = {k: v for k, v in MSTransception(num_classes=NCLS, image_size=SIZE).state_dict().items()}
     bs = BATCH
     x = _make_inputs(torch, bs, 0)
     with torch.no_grad():
@@ -148,7 +148,7 @@ def run_ours(args):
     peaks, peak_kind = _peaks()
 
     torch.manual_seed(1234)
-    net = MSTransception(num_classes=NCLS).eval().to(dev)
+    net = MSTransception(num_classes=NCLS, image_size=SIZE).eval().to(dev)
     runner = GraphRunner(net, BATCH, IN_CH, SIZE, device=dev, microbatches=args.microbatches)
     x_host = _make_inputs(torch, BATCH, rank).pin_memory()
     y_host = torch.empty((BATCH, NCLS, SIZE, SIZE), dtype=torch.float32).pin_memory()
@@ -222,8 +222,10 @@ def run_ours(args):
         line = {"metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16/tf32 tensor-core MMA, f32 accumulate, f32 IO", "data": "synthetic",
-                "config": {"workload": "TransCeption Synapse 224x224 bs16 fp32 forward (BASELINE configs[1]), "
-                                       "per-GPU batch 16, %d class logits" % NCLS,
+                "config": {"workload": "TransCeption Synapse %dx%d bs16 fp32 forward (%s), "
+                                       "per-GPU batch 16, %d class logits" % (
+                                           SIZE, SIZE, "BASELINE configs[1]" if SIZE == 224 and NCLS == 9 else
+                                           "non-headline geometry", NCLS),
                            "l2": "256 MiB memset between timed steps (untimed); step footprint > L2",
                            "timing": "per-step CUDA events on the replay stream, summed; max over ranks",
                            "graph": "whole forward replayed as one CUDA graph"},
@@ -261,15 +263,23 @@ def run_ours(args):
 
 
 def main():
+    global SIZE, NCLS, IN_CH, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--size", type=int, default=SIZE, help="input side (default 224 = the headline workload; 256 = config 5)")
+    ap.add_argument("--classes", type=int, default=NCLS)
+    ap.add_argument("--in-ch", type=int, default=IN_CH)
     ap.add_argument("--microbatches", type=int, default=1,
                     help="split each rank's batch of 16 into this many slices captured on parallel streams")
     args = ap.parse_args()
+    if (args.size, args.classes, args.in_ch) != (SIZE, NCLS, IN_CH):
+        SIZE, NCLS, IN_CH = args.size, args.classes, args.in_ch
+        METRIC = "images/sec fwd @%dx%d bs16 (TransCeption MSTransception, %d classes, fp32 IO) [non-headline geometry]" % (
+            SIZE, SIZE, NCLS)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -23,6 +23,25 @@ import torch.nn.functional as F
 TOK = (3136, 4704, 5684, 6076)  # bridge token offsets at 224x224 (MSTr.py:2228-2231)
 
 
+def bridge_geometry(ntok):
+    """Stage-1 side S and the cumulative token offsets of the 4-scale pyramid whose 64-wide token count is ``ntok``.
+
+    The reference hard-codes the 224x224 values (S = 56, offsets 3136/4704/5684/6076: MSTr.py:2228-2231, :2394-2397,
+    :2432-2435) and therefore fails on any other input size.  This is the generalisation SURVEY.md section 8c asks for
+    (56/28/14/7 -> S, S/2, S/4, S/8); at ntok = 6076 it returns exactly the reference constants, which
+    tests/test_oracle.py pins against the live reference's outputs."""
+    s2 = ntok * 16 // 31
+    S = int(math.isqrt(s2))
+    if S * S * 31 != ntok * 16 or S % 8:
+        raise ValueError("token count %d is not a 4-scale pyramid" % ntok)
+    sides = (S, S // 2, S // 4, S // 8)
+    offs, acc = [], 0
+    for hw, mult in zip(sides, (1, 2, 5, 8)):
+        acc += hw * hw * mult
+        offs.append(acc)
+    return S, sides, tuple(offs)
+
+
 def _p(sd, key):
     return sd[key]
 
@@ -202,10 +221,11 @@ def msvit(sd, p, x):
 # ---- bridge: MSTr.py:2225-2249, :2267-2292, :2309-2353, :2373-2409, :2422-2442 --------
 def scale_reduce(sd, p, x):
     B, N, C = x.shape
-    t0 = x[:, :TOK[0]].reshape(B, 56, 56, C).permute(0, 3, 1, 2)
-    t1 = x[:, TOK[0]:TOK[1]].reshape(B, 28, 28, C * 2).permute(0, 3, 1, 2)
-    t2 = x[:, TOK[1]:TOK[2]].reshape(B, 14, 14, C * 5).permute(0, 3, 1, 2)
-    t3 = x[:, TOK[2]:TOK[3]]
+    _, (h0, h1, h2, _h3), tok = bridge_geometry(N)
+    t0 = x[:, :tok[0]].reshape(B, h0, h0, C).permute(0, 3, 1, 2)
+    t1 = x[:, tok[0]:tok[1]].reshape(B, h1, h1, C * 2).permute(0, 3, 1, 2)
+    t2 = x[:, tok[1]:tok[2]].reshape(B, h2, h2, C * 5).permute(0, 3, 1, 2)
+    t3 = x[:, tok[2]:tok[3]]
     s0 = conv(sd, p + '.sr0', t0, 8).reshape(B, C, -1).permute(0, 2, 1)
     s1 = conv(sd, p + '.sr1', t1, 4).reshape(B, C, -1).permute(0, 2, 1)
     s2 = conv(sd, p + '.sr2', t2, 2).reshape(B, C, -1).permute(0, 2, 1)
@@ -243,7 +263,8 @@ def bridge_layer(sd, p, x, ch_att):
     tx1 = x + attn(sd, p + '.attn', layernorm(sd, p + '.norm1', x))
     tx = layernorm(sd, p + '.norm2', tx1)
     parts, off = [], 0
-    for i, (hw, mult) in enumerate(((56, 1), (28, 2), (14, 5), (7, 8))):
+    sides = bridge_geometry(x.shape[1])[1]
+    for i, (hw, mult) in enumerate(zip(sides, (1, 2, 5, 8))):
         n = hw * hw * mult
         t = tx[:, off:off + n].reshape(B, -1, C * mult)
         parts.append(mixffn_skip(sd, '%s.mixffn%d' % (p, i + 1), t, hw, hw).reshape(B, -1, C))
@@ -257,7 +278,7 @@ def bridge_block(sd, p, maps, ch_att_list=(True, False, False, False)):
         x = bridge_layer(sd, '%s.bridge_layer%d' % (p, i + 1), x, ch_att_list[i])
     B, _, C = x.shape
     outs, off = [], 0
-    for hw, mult in ((56, 1), (28, 2), (14, 5), (7, 8)):
+    for hw, mult in zip(bridge_geometry(x.shape[1])[1], (1, 2, 5, 8)):
         n = hw * hw * mult
         outs.append(x[:, off:off + n].reshape(B, hw, hw, C * mult).permute(0, 3, 1, 2))
         off += n
@@ -290,7 +311,8 @@ def decoder_layer(sd, p, x1, x2=None, is_last=False):
 
 # ---- top level: MSTr.py:2826-2852 ------------------------------------------------------
 def forward(sd, x, ch_att_list=(True, False, False, False), return_all=False):
-    """sd: reference-format state_dict; x: [B,1|3,224,224]. Returns logits (and, optionally, every map)."""
+    """sd: reference-format state_dict; x: [B,1|3,H,H] with H = 224 in the reference (any multiple of 32 here, see
+    bridge_geometry). Returns logits (and, optionally, every map)."""
     if x.shape[1] == 1:
         x = x.repeat(1, 3, 1, 1)
     enc = msvit(sd, 'backbone', x)

@@ -99,7 +99,7 @@ def test_linear(backend, M, N, K, act):
 
 # ---- stage 1 ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 192, 64), (777, 320, 1280), (12544, 256, 64), (300, 2048, 512),
-                                   (33, 64, 128), (4097, 128, 320)])
+                                   (33, 64, 128), (4097, 128, 320), (5, 64, 64), (25, 960, 320), (1, 128, 512)])
 @pytest.mark.parametrize("out16", [False, True])
 def test_linear_f16(cuda_lib, M, N, K, out16):
     """fp16-operand tcgen05 GEMM (kind::f16) with fp32 or fp16 output, against fp64 on the unrounded operands."""
@@ -348,6 +348,29 @@ def test_whole_model(model, backend, cin, bs):
         assert err <= 2e-4 and dice >= 0.999
     else:
         assert err <= 5e-2 and mean <= 5e-3 and dice >= 0.99
+
+
+@pytest.mark.parametrize("size,ncls,cin,bs", [(256, 1, 3, 2), (160, 9, 1, 1)])
+def test_whole_model_other_geometry(cuda_lib, size, ncls, cin, bs):
+    """BASELINE config 5 geometry (256x256, 1 class) and a small odd one: the reference hard-codes 224 and fails there;
+    the oracle's generalised bridge geometry (pinned at 224 by the golden vectors) is the checker."""
+    from networks.MSTr import MSTransception
+    torch.manual_seed(4321)
+    net = _randomise(MSTransception(num_classes=ncls, image_size=size)).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.rand(bs, cin, size, size, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    want = O.forward(sd, x, return_all=True)
+    net = net.cuda()
+    with torch.no_grad():
+        maps = net.backbone(x.cuda())
+        for i in range(4):
+            _close(maps[i], want['enc'][i], TC_TOL * 3, "encoder map %d @%d" % (i, size))
+        got = net(x.cuda()).float().cpu()
+    w = want['logits']
+    assert got.shape == w.shape == (bs, ncls, size, size)
+    err, mean = (got - w).abs().max().item(), (got - w).abs().mean().item()
+    print("size %d logits max-abs %.3e mean-abs %.3e" % (size, err, mean))
+    assert err <= 5e-2 and mean <= 5e-3
 
 
 def test_forward_fails_loudly_on_cpu_tensor(model):

@@ -551,7 +551,7 @@ int launch_bn(int bn, const TmaSet& maps, const GemmParams& p, const SmemPlan& s
 
 bool gemm_tc_eligible(const GemmParams& p) {
   if (!tcx_flag_gemm_tc()) return false;
-  if (p.N < 16 || p.K < 16 || p.M < 32) return false;
+  if (p.N < 16 || p.K < 16 || p.M < 1) return false;   // ragged / tiny M is clipped by the tensor maps
   const int am = p.ab16 ? 7 : 3, cm = p.out16 ? 7 : 3;     // 16-byte row pitches
   if ((p.K | p.lda | p.ldw) & am) return false;
   if (p.ldc & cm) return false;

@@ -684,9 +684,10 @@ class BridgeBlock_4(nn.Module):
 
     def forward(self, x):
         t = self.tokens(x)
-        B, _, C = t.shape
+        B, ntok, C = t.shape
         outs, off = [], 0
-        for hw, mult in ((56, 1), (28, 2), (14, 5), (7, 8)):
+        S = ops._bridge_side(ntok)      # 56 at 224x224 (the reference hard-codes 56/28/14/7, MSTr.py:2432-2435)
+        for hw, mult in ((S, 1), (S // 2, 2), (S // 4, 5), (S // 8, 8)):
             n = hw * hw * mult
             outs.append(t[:, off:off + n, :].reshape(B, hw, hw, C * mult).permute(0, 3, 1, 2))
             off += n
@@ -699,21 +700,25 @@ class BridgeBlock_4(nn.Module):
 class MSTransception(nn.Module):
     def __init__(self, num_classes=9, head_count=8, dil_conv=1, token_mlp_mode="mix_skip", MSViT_config=2,
                  concat='coord', have_bridge='original', use_sa_config=1, sa_ker=7, Stage_3or4=3, inter='res',
-                 num_sp=1, br_ch_att_list=[True, False, False, False]):
+                 num_sp=1, br_ch_att_list=[True, False, False, False], image_size=224):
+        """``image_size`` is an extension (the reference hard-codes 224 and fails on other sizes, SURVEY.md section 0
+        defect 4): any multiple of 32 builds the same parameters and runs, e.g. 256 for BASELINE config 5."""
         super().__init__()
+        if image_size % 32:
+            raise ValueError("image_size must be a multiple of 32")
         if Stage_3or4 != 3:
             raise NotImplementedError("only Stage_3or4=3 (MSViT) is built")
         if have_bridge in ('sp', 'para'):
             raise NotImplementedError("only have_bridge='original' (BridgeBlock_4) is built")
         dims = [64, 128, 320, 512]
         use_sa_list = [True, True, True, False]
-        self.backbone = MSViT(image_size=224, in_dim=dims, key_dim=dims, value_dim=dims, layers=[2, 2, 2, 2],
+        self.backbone = MSViT(image_size=image_size, in_dim=dims, key_dim=dims, value_dim=dims, layers=[2, 2, 2, 2],
                               head_count=head_count, dil_conv=dil_conv, token_mlp=token_mlp_mode,
                               MSViT_config=MSViT_config, concat=concat, use_sa_list=use_sa_list, sa_ker=sa_ker)
         self.reduction_ratios = [1, 2, 4, 8]
         self.have_bridge = have_bridge
         self.bridge = BridgeBlock_4(64, 1, self.reduction_ratios, br_ch_att_list)
-        fs = 7
+        fs = image_size // 32
         io = [[32, 64, 64, 64], [144, 128, 128, 128], [288, 320, 320, 320], [512, 512, 512, 512]]
         self.decoder_3 = MyDecoderLayer((fs, fs), io[3], head_count, token_mlp_mode, n_class=num_classes)
         self.decoder_2 = MyDecoderLayer((fs * 2, fs * 2), io[2], head_count, token_mlp_mode, n_class=num_classes)
