@@ -373,6 +373,44 @@ def test_whole_model_other_geometry(cuda_lib, size, ncls, cin, bs):
     assert err <= 5e-2 and mean <= 5e-3
 
 
+def test_graph_runner_host_roundtrip(model):
+    """GraphRunner.run_host (CUDA-graph replay, pipelined D2H on a copy stream) returns the eager forward's logits for
+    every step, also when steps are issued back to back."""
+    from transception_b200.runtime import GraphRunner
+    net, _ = model
+    runner = GraphRunner(net, 2, 1, 224, device="cuda")
+    xs = [(torch.rand(2, 1, 224, 224, generator=torch.Generator().manual_seed(s)) * 2 - 1).pin_memory() for s in range(3)]
+    ys = [torch.empty(2, 9, 224, 224).pin_memory() for _ in range(3)]
+    for x, y in zip(xs, ys):
+        runner.run_host(x, y)
+    runner.drain()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for x, y in zip(xs, ys):
+            want = net(x.cuda()).float().cpu()
+            assert torch.equal(y, want), "graph replay differs from the eager forward"
+
+
+def test_forward_is_bit_reproducible(model):
+    """No atomics and no order-dependent reductions anywhere: two forwards agree bit for bit, and so do the forwards
+    with programmatic dependent launch / auxiliary-stream forking switched off (a hazard between overlapped kernels
+    would show up here)."""
+    from transception_b200 import ops
+    net, _ = model
+    x = (torch.rand(2, 1, 224, 224, generator=torch.Generator().manual_seed(3)) * 2 - 1).cuda()
+    try:
+        with torch.no_grad():
+            ref = net(x).clone()
+            assert torch.equal(net(x), ref)
+            for pdl, fork in ((0, 1), (1, 0), (0, 0)):
+                ops.set_flag("pdl", pdl)
+                ops.set_flag("fork", fork)
+                assert torch.equal(net(x), ref), "forward changes with pdl=%d fork=%d" % (pdl, fork)
+    finally:
+        ops.set_flag("pdl", 1)
+        ops.set_flag("fork", 1)
+
+
 def test_forward_fails_loudly_on_cpu_tensor(model):
     net, _ = model
     with pytest.raises(RuntimeError):

@@ -574,7 +574,8 @@ __global__ void __launch_bounds__(MBF_THREADS) mb_fused16_kernel(const Mb16Args 
   float* red = bs + Ch;                                             // [256]
   float* mx = red + 256;                                            // [Ch]
   float* ss = mx + Ch;                                              // [Ch]
-  __half* qs = reinterpret_cast<__half*>(ss + Ch);                  // [N][CHP]
+  float* pbuf = ss + Ch;                                            // [1024] per-split partial contexts
+  __half* qs = reinterpret_cast<__half*>(pbuf + 1024);              // [N][CHP]
   __half* vs = qs + (size_t)N * CHP;                                // [N][CHP]
   pdl_trigger();
   // filters / bias of this head (module parameters) before pdl_wait
@@ -642,7 +643,8 @@ __global__ void __launch_bounds__(MBF_THREADS) mb_fused16_kernel(const Mb16Args 
     for (int s2 = 0; s2 < nsl; s2++) t += red[s2 * Ch + tid];
     ss[tid] = t;
   }
-  // context: 2 x 2 register tiles of (k, v) pairs, token range split over the remaining threads
+  // context: 2 x 2 register tiles of (k, v) pairs, token range split over the remaining threads; the per-split partial
+  // sums are combined in a fixed order (no atomics: the forward is bit-reproducible run to run)
   {
     const int tiles = (Ch / 2) * (Ch / 2);
     const int nsp = tiles >= MBF_THREADS ? 1 : MBF_THREADS / tiles;
@@ -657,11 +659,23 @@ __global__ void __launch_bounds__(MBF_THREADS) mb_fused16_kernel(const Mb16Args 
         a10 = fmaf(e.y, vv.x, a10); a11 = fmaf(e.y, vv.y, a11);
       }
       if (nsp > 1) {
-        atomicAdd(&ctx[k * Ch + v], a00); atomicAdd(&ctx[k * Ch + v + 1], a01);
-        atomicAdd(&ctx[(k + 1) * Ch + v], a10); atomicAdd(&ctx[(k + 1) * Ch + v + 1], a11);
+        *reinterpret_cast<float4*>(pbuf + ((size_t)sp * tiles + tl) * 4) = make_float4(a00, a01, a10, a11);
       } else {
         ctx[k * Ch + v] = a00; ctx[k * Ch + v + 1] = a01;
         ctx[(k + 1) * Ch + v] = a10; ctx[(k + 1) * Ch + v + 1] = a11;
+      }
+    }
+    if (nsp > 1) {
+      __syncthreads();
+      for (int tl = tid; tl < tiles; tl += MBF_THREADS) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < nsp; sp++) {
+          const float4 t = *reinterpret_cast<const float4*>(pbuf + ((size_t)sp * tiles + tl) * 4);
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const int k = (tl / (Ch / 2)) * 2, v = (tl % (Ch / 2)) * 2;
+        ctx[k * Ch + v] = acc.x; ctx[k * Ch + v + 1] = acc.y;
+        ctx[(k + 1) * Ch + v] = acc.z; ctx[(k + 1) * Ch + v + 1] = acc.w;
       }
     }
   }
@@ -776,7 +790,7 @@ int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st) {
   TCX_REQUIRE(a.heads == 8 && a.C % a.heads == 0, "mb_attn16: needs 8 heads (crpe window map {3:2,5:3,7:3})");
   const int Ch = a.C / a.heads, N = a.H * a.W;
   TCX_REQUIRE(Ch % 8 == 0 && Ch <= 64, "mb_attn16: head dim %d must be a multiple of 8 and <= 64", Ch);
-  const size_t smem = ((size_t)N * Ch + (size_t)Ch * Ch + 49 * Ch + Ch + 256 + 2 * Ch) * sizeof(float) +
+  const size_t smem = ((size_t)N * Ch + (size_t)Ch * Ch + 49 * Ch + Ch + 256 + 2 * Ch + 1024) * sizeof(float) +
                       (size_t)2 * N * (Ch + 2) * sizeof(__half);
   TCX_REQUIRE(smem <= 200 * 1024, "mb_attn16: %d tokens x head dim %d does not fit in shared memory", N, Ch);
   dim3 grid(a.heads, a.B, groups);

@@ -238,21 +238,21 @@ __global__ void __launch_bounds__(256) sr_pack_ln16_kernel(SrPackArgs a, const _
 // IFF / coordinate attention (reference MSTr.py:1322-1348)
 // =====================================================================================
 // pooled[b][h][k] = mean_w x, pooled[b][H+w][k] = mean_h x  for the 4 concatenated sources.
-// grid (H, 4, B), one thread per channel: a block owns one map row (coalesced over channels), writes its row mean and
-// adds its row into the column sums (fp32 atomics on a zeroed buffer; H*W*C per image and source).
-__global__ void __launch_bounds__(512) iff_pool_kernel(IffSrc src, int HW, int C, float* __restrict__ pooled) {
-  const int h = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
+// grid (HW, 4, 2B), one thread per channel (coalesced): blockIdx.z < B -> the row mean of map row blockIdx.x,
+// otherwise the column mean of map column blockIdx.x.  Fixed summation order: deterministic, no atomics.
+__global__ void __launch_bounds__(512) iff_pool_kernel(IffSrc src, int B, int HW, int C, float* __restrict__ pooled) {
+  const int i = blockIdx.x, s = blockIdx.y;
+  const bool col = (int)blockIdx.z >= B;
+  const int b = col ? blockIdx.z - B : blockIdx.z;
   const float inv = 1.f / (float)HW;
+  const long long step = col ? (long long)HW * C : C;                       // walk down a column / along a row
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* __restrict__ x = src.p[s] + (((long long)b * HW + h) * HW) * C + c;
-    float* __restrict__ o = pooled + (long long)b * 2 * HW * 4 * C + s * C + c;
-    float row = 0.f;
-    for (int w = 0; w < HW; w++) {
-      const float v = x[(long long)w * C];
-      row += v;
-      atomicAdd(o + (long long)(HW + w) * 4 * C, v * inv);
-    }
-    o[(long long)h * 4 * C] = row * inv;
+    const float* __restrict__ x = src.p[s] + (long long)b * HW * HW * C + (col ? (long long)i * C : (long long)i * HW * C) + c;
+    float a0 = 0.f, a1 = 0.f;
+    int j = 0;
+    for (; j + 1 < HW; j += 2) { a0 += x[j * step]; a1 += x[(j + 1) * step]; }
+    if (j < HW) a0 += x[j * step];
+    pooled[(long long)b * 2 * HW * 4 * C + (long long)((col ? HW : 0) + i) * 4 * C + s * C + c] = (a0 + a1) * inv;
   }
 }
 
@@ -396,13 +396,10 @@ int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st) {
 }
 
 int launch_iff_pool(const IffSrc& src, int B, int HW, int C, float* pooled, cudaStream_t st) {
-  // the column-mean half of `pooled` is accumulated with atomics: zero the buffer first
-  cudaError_t e = cudaMemsetAsync(pooled, 0, (size_t)B * 2 * HW * 4 * C * sizeof(float), st);
-  TCX_REQUIRE(e == cudaSuccess, "iff_pool: memset failed: %s", cudaGetErrorString(e));
-  dim3 grid(HW, 4, B);
+  dim3 grid(HW, 4, 2 * B);
   int threads = (C + 31) / 32 * 32;
   if (threads > 512) threads = 512;
-  iff_pool_kernel<<<grid, threads, 0, st>>>(src, HW, C, pooled);
+  iff_pool_kernel<<<grid, threads, 0, st>>>(src, B, HW, C, pooled);
   return tcx_check_launch("iff_pool");
 }
 
