@@ -177,7 +177,7 @@ int tcx_bridge_block_fwd(const float* x, const void* const* p, const int* channe
 
 /* decoder — MyDecoderLayer.forward pieces (MSTr.py:273-290, :184-201, :212-227) */
 int tcx_concat_linear_fwd(const float* x1, const float* x2, const float* w, const float* b, float* y, int M, int C1,
-                          int C2, int N, void* stream);
+                          int C2, int N, int batch, long long x2_batch_stride, void* stream);
 size_t tcx_patch_expand_workspace_bytes(int B, int H, int W, int C, int scale);
 int tcx_patch_expand_fwd(const float* x, const float* w, const float* lnw, const float* lnb, float eps, float* y,
                          int B, int H, int W, int C, int scale, void* ws, void* stream);

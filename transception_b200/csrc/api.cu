@@ -1218,16 +1218,21 @@ int tcx_bridge_block_fwd(const float* x, const void* const* p, const int* channe
 
 // ---- decoder ----------------------------------------------------------------------------------
 int tcx_concat_linear_fwd(const float* x1, const float* x2, const float* w, const float* b, float* y, int M, int C1,
-                          int C2, int N, void* stream) {
+                          int C2, int N, int batch, long long x2_batch_stride, void* stream) {
   cudaStream_t st = S(stream);
-  // y = x2 * W[:, C1:]^T + b, then y += x1 * W[:, :C1]^T   (the concatenation is never materialised)
+  TCX_REQUIRE(batch >= 1, "concat_linear: batch must be >= 1");
+  // y = x2 * W[:, C1:]^T + b, then y += x1 * W[:, :C1]^T   (the concatenation is never materialised).
+  // batch > 1: M rows per image, x1 / y dense, x2 a per-image slab with pitch x2_batch_stride (a bridge output map
+  // viewed in place inside the token buffer, MSTr.py:2432-2435 -> :2847-2850).
   GemmParams g = gemm1(x2, w + C1, y, M, N, C2);
   g.ldw = C1 + C2;
   g.g[0].epi.bias = b;
+  if (batch > 1) { g.batch = batch; g.strideA = x2_batch_stride; g.strideC = (long long)M * N; }
   TCX_TRY(launch_gemm(g, st));
   GemmParams h = gemm1(x1, w, y, M, N, C1);
   h.ldw = C1 + C2;
   h.g[0].epi.residual = y;
+  if (batch > 1) { h.batch = batch; h.strideA = (long long)M * C1; h.strideC = (long long)M * N; h.g[0].epi.strideR = (long long)M * N; }
   return launch_gemm(h, st);
 }
 

@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   constexpr int SLABC = OUT16 ? 64 : 32;              // output columns per 128-byte slab row
   constexpr int NSLAB = BN / SLABC;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // ALT: a tile is finished by ONE epilogue warp set (set index == accumulator index) and the two sets take alternate
+  // tiles — used when a thread needs its whole row (LN) and when a tile has a single slab (otherwise one set would idle)
+  constexpr bool ALT = LN || NSLAB == 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int STAGES = sp.stages;
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) {
       tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], LN ? EPI_WARPS * 16 : EPI_WARPS * 32);   // LN: one warp set per accumulator
+      tc::mbar_init(&acc_empty[a], ALT ? EPI_WARPS * 16 : EPI_WARPS * 32);   // ALT: one warp set per accumulator
     }
     for (int i = 0; i < 2 * EPI_WARPS; i++) tc::mbar_init(&res_full[i], 1);
     tc::fence_barrier_init();
@@ -298,14 +301,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
     uint8_t* ln_w_buf = smem + sp.off_ln + ew * SUB_BYTES;
     // LN kernels: the thread needs its whole 64-column row, so a tile is finished by ONE warp set (half == accumulator
     // index) instead of both sets splitting the slabs; the two sets then work on alternate tiles
-    constexpr int S0_STEP = LN ? 1 : 2;
+    constexpr int S0_STEP = ALT ? 1 : 2;
     uint64_t* rbar = res_full + ew * 2;
 
-    int pf_tile = blockIdx.x + (LN ? half * (int)gridDim.x : 0), pf_slab = LN ? 0 : half;
-    const int pf_tile_step = LN ? 2 * (int)gridDim.x : (int)gridDim.x;
+    int pf_tile = blockIdx.x + (ALT ? half * (int)gridDim.x : 0), pf_slab = ALT ? 0 : half;
+    const int pf_tile_step = ALT ? 2 * (int)gridDim.x : (int)gridDim.x;
     uint32_t pf_count = 0;
     auto prefetch_res = [&]() {      // lane 0: next live residual sub-slab of this warp
-      while (pf_tile < ntiles && (LN || half < NSLAB)) {
+      while (pf_tile < ntiles && (ALT || half < NSLAB)) {
         const TileCoord t = tile_coord(pf_tile, mt, nt, p.batch, BN);
         const bool live = p.g[t.gi].epi.residual != nullptr && t.n0 + pf_slab * SLABC < p.N;
         if (live) {
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           pf_count++;
         }
         pf_slab += S0_STEP;
-        if (pf_slab >= NSLAB) { pf_slab = LN ? 0 : half; pf_tile += pf_tile_step; }
+        if (pf_slab >= NSLAB) { pf_slab = ALT ? 0 : half; pf_tile += pf_tile_step; }
         if (live) return;
       }
     };
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     uint32_t ti = 0, out_count = 0, res_count = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
-      if (LN && (int)(ti & 1) != half) continue;
+      if (ALT && (int)(ti & 1) != half) continue;
       const TileCoord t = tile_coord(tile, mt, nt, p.batch, BN);
       const GemmEpi& e = p.g[t.gi].epi;
       const bool has_res = !OUT16 && e.residual != nullptr;
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
       } else {
 #pragma unroll 1
-      for (int s = half; s < NSLAB; s += 2) {
+      for (int s = ALT ? 0 : half; s < NSLAB; s += S0_STEP) {
         const int col0 = t.n0 + s * SLABC;
         if (col0 >= p.N) break;
         const uint32_t ob = out_count & 1;
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
         __syncwarp();
         tc::tmem_ld_wait();
-        if (s + 2 >= NSLAB || col0 + 2 * SLABC >= p.N) {         // last TMEM read of this tile by this warp
+        if (s + S0_STEP >= NSLAB || col0 + S0_STEP * SLABC >= p.N) {   // last TMEM read of this tile by this warp
           tc::fence_before_sync();
           tc::mbar_arrive(&acc_empty[a]);
           arrived = true;

@@ -27,6 +27,18 @@ from . import ops
 _LN_EPS = 1e-5
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    """One auxiliary stream per device for module-level parallel branches (streams, not a tracing compiler)."""
+    key = torch.device(device).index
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _nhwc(x):
     """NCHW-shaped tensor (any strides) -> contiguous [B,H,W,C] (free for channels_last)."""
     return x.permute(0, 2, 3, 1).contiguous()
@@ -203,8 +215,7 @@ class MyDecoderLayer(nn.Module):
         if x2 is None:
             return self.layer_up(x1)
         b, h, w, c = x2.shape
-        cat_linear_x = ops.concat_linear(x1.contiguous(), x2.reshape(b, h * w, c).contiguous(),
-                                         self.concat_linear.weight, self.concat_linear.bias)
+        cat_linear_x = ops.concat_linear(x1, x2.reshape(b, h * w, c), self.concat_linear.weight, self.concat_linear.bias)
         t1 = self.layer_former_1(cat_linear_x, h, w)
         t2 = self.layer_former_2(t1, h, w)
         if self.last_layer is not None:
@@ -507,9 +518,17 @@ class MHCA_stage(nn.Module):
     def nhwc(self, stacked):
         """stacked: [P,B,H,W,C] RIPM outputs -> [B,H,W,C_out]."""
         P, B, H, W, C = stacked.shape
-        res = self.InvRes.nhwc(stacked[0])
+        # the residual branch only needs path 0 of the RIPM output: it runs on a side stream next to the three
+        # transformer branches (a parallel branch of the captured graph)
+        main = torch.cuda.current_stream(stacked.device)
+        side = _side_stream(stacked.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            res = self.InvRes.nhwc(stacked[0])
         enc = ops.mhca_blocks(stacked.view(P, B, H * W, C), H, W,
                               [list(e.MHCA_layers) for e in self.mhca_blks])
+        main.wait_stream(side)
+        res.record_stream(main)
         maps = [res] + [enc[i].view(B, H, W, C) for i in range(P)]
         return self.aggregate.nhwc(maps)
 

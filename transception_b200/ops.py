@@ -70,7 +70,7 @@ _PROTOS = {
     "tcx_flash_attn_f16_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "tcx_bridge_mixffn_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_mixffn_fwd": (_i, [_vp, _vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
-    "tcx_concat_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_concat_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp]),
     "tcx_patch_expand_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "tcx_patch_expand_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_final_expand_head_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -599,14 +599,23 @@ def bridge_block(x, layers, scale, ln_eps):
 
 
 def concat_linear(x1, x2, w, b):
+    """Linear(cat[x1, x2]) without materialising the concatenation.  ``x2`` may be a per-image slab of a larger buffer
+    ([B,N,C2] with dense rows and an arbitrary batch pitch): it is read in place."""
     require_cuda(x1)
     lib = load_library()
     B, N, C1 = x1.shape
     C2 = x2.shape[-1]
     Nout = w.shape[0]
+    x1 = x1.contiguous()
+    slab = (x2.dim() == 3 and x2.stride(2) == 1 and x2.stride(1) == C2 and x2.stride(0) % 4 == 0 and
+            x2.dtype == torch.float32 and x2.is_cuda and x2.data_ptr() % 16 == 0)
     y = torch.empty((B, N, Nout), device=x1.device, dtype=x1.dtype)
-    _chk(lib.tcx_concat_linear_fwd(_ptr(x1), _ptr(x2), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), B * N, C1, C2, Nout,
-                                   _stream()))
+    if slab and not x2.is_contiguous():
+        _chk(lib.tcx_concat_linear_fwd(_ptr(x1), x2.data_ptr(), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), N, C1, C2, Nout,
+                                       B, x2.stride(0), _stream()))
+    else:
+        _chk(lib.tcx_concat_linear_fwd(_ptr(x1), _ptr(x2.contiguous()), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), B * N, C1, C2,
+                                       Nout, 1, 0, _stream()))
     return y
 
 
