@@ -5,9 +5,9 @@
 //                    are staged once per block in shared memory (tap-major); a warp walks consecutive tokens so 6 of
 //                    the 9 neighbour rows hit L1.
 //  * ln16_kernel   — LayerNorm of an fp32 stream to fp16 (and/or fp32).
-//  * mb_ctx16 / mb_apply16 — Multi-Branch factorized attention + conv relative position encoding (MSTr.py:852-886,
-//                    :801-823) on an fp16 qkv buffer: per (image, head) column softmax + K^T V in shared memory, then a
-//                    row-band kernel with the V band (+3 halo rows), Q band, context and the 3x3/5x5/7x7 filters in smem.
+//  * mb_fused16    — Multi-Branch factorized attention + conv relative position encoding (MSTr.py:852-886, :801-823) on
+//                    an fp16 qkv buffer, one block per (head, image, branch): column softmax, K^T V, q x ctx and the
+//                    head's 3x3 / 5x5 / 7x7 depthwise filter from one shared-memory copy of the head's q / k / v.
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "fused16.cuh"
@@ -284,213 +284,10 @@ __global__ void __launch_bounds__(256) ln16_kernel(const Ln16Args a) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Multi-Branch factorized attention, fp16 qkv
-// ------------------------------------------------------------------------------------------------------------------
-// grid (heads, B, G), 256 threads.  ctx[b][h][k][v] = scale * sum_n softmax_n(K)[n,k] V[n,v]
-__global__ void __launch_bounds__(256) mb_ctx16_kernel(const Mb16Args a) {
-  extern __shared__ float sm[];
-  const int N = a.H * a.W, C = a.C, Ch = a.C / a.heads;
-  float* ks = sm;                       // [N][Ch]
-  float* vs = ks + (size_t)N * Ch;      // [N][Ch]
-  float* red = vs + (size_t)N * Ch;     // [256]
-  float* mx = red + 256;                // [Ch]
-  float* ss = mx + Ch;                  // [Ch]
-  float* cacc = ss + Ch;                // [Ch*Ch]
-  const int tid = threadIdx.x, h = blockIdx.x, b = blockIdx.y, gi = blockIdx.z;
-  pdl_trigger();
-  pdl_wait();
-  const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
-  const int vpr = Ch / 8;               // 16-byte vectors per row slice
-  for (int i = tid; i < N * vpr * 2; i += 256) {
-    const int which = i / (N * vpr);    // 0 = K, 1 = V
-    const int r = i - which * N * vpr;
-    const int n = r / vpr, j = r - n * vpr;
-    const uint4 raw = *reinterpret_cast<const uint4*>(base + (long long)n * 3 * C + (1 + which) * C + h * Ch + j * 8);
-    float f[8];
-    unpack8(raw, f);
-    float* dst = (which ? vs : ks) + n * Ch + j * 8;
-#pragma unroll
-    for (int q = 0; q < 8; q++) dst[q] = f[q];
-  }
-  for (int i = tid; i < Ch * Ch; i += 256) cacc[i] = 0.f;
-  __syncthreads();
-  const int nsl = 256 / Ch;             // token slices per column
-  const int ck = tid % Ch, slc = tid / Ch;
-  float m = -INFINITY;
-  if (slc < nsl)
-    for (int n = slc; n < N; n += nsl) m = fmaxf(m, ks[n * Ch + ck]);
-  red[tid] = m;
-  __syncthreads();
-  if (tid < Ch) {
-    float mm = -INFINITY;
-    for (int s = 0; s < nsl; s++) mm = fmaxf(mm, red[s * Ch + tid]);
-    mx[tid] = mm;
-  }
-  __syncthreads();
-  float sum = 0.f;
-  if (slc < nsl) {
-    const float mc = mx[ck];
-    for (int n = slc; n < N; n += nsl) {
-      const float e = __expf(ks[n * Ch + ck] - mc);
-      ks[n * Ch + ck] = e;
-      sum += e;
-    }
-  }
-  red[tid] = slc < nsl ? sum : 0.f;
-  __syncthreads();
-  if (tid < Ch) {
-    float t = 0.f;
-    for (int s = 0; s < nsl; s++) t += red[s * Ch + tid];
-    ss[tid] = t;
-  }
-  // ctx pairs: nsp token splits per (k, v) pair when Ch*Ch < 256
-  const int npairs = Ch * Ch;
-  const int nsp = npairs >= 256 ? 1 : 256 / npairs;
-  for (int p0 = 0; p0 < npairs * nsp; p0 += 256) {
-    const int idx = p0 + tid;
-    if (idx < npairs * nsp) {
-      const int p = idx % npairs, sp = idx / npairs;
-      const int k = p / Ch, v = p - k * Ch;
-      float a0 = 0.f, a1 = 0.f;
-      int n = sp;
-      for (; n + nsp < N; n += 2 * nsp) {
-        a0 = fmaf(ks[n * Ch + k], vs[n * Ch + v], a0);
-        a1 = fmaf(ks[(n + nsp) * Ch + k], vs[(n + nsp) * Ch + v], a1);
-      }
-      if (n < N) a0 = fmaf(ks[n * Ch + k], vs[n * Ch + v], a0);
-      if (nsp > 1) atomicAdd(&cacc[p], a0 + a1);
-      else cacc[p] = a0 + a1;
-    }
-  }
-  __syncthreads();
-  float* __restrict__ out = a.ctx[gi] + ((long long)b * a.heads + h) * npairs;
-  for (int p = tid; p < npairs; p += 256) out[p] = a.scale * cacc[p] / ss[p / Ch];
-}
-
 // exact i / d for 0 <= i < 2^20 and small d via one multiply (inv = 1.0f / d): (i + 0.5) / d is never within 2^-20
 // of an integer, so float rounding cannot cross a boundary.
 __device__ __forceinline__ int fdiv(int i, float inv) { return (int)(((float)i + 0.5f) * inv); }
 
-constexpr int MBA_THREADS = 512;
-
-// conv relative position encoding + factorized attention for the channels of one window group (WIN x WIN filters):
-// a thread owns T adjacent tokens of one channel pair, slides the V window along x in registers and reuses each filter
-// tap for the T outputs.  All loops are compile-time unrolled; a warp never mixes window sizes.
-template <int WIN, int T>
-__device__ __forceinline__ void mb_apply_group(const __half* __restrict__ vt, const __half* __restrict__ qt,
-                                               const float* __restrict__ ctx, const float* __restrict__ wt,
-                                               const float* __restrict__ bs, __half* __restrict__ outp, int rows, int W,
-                                               int C, int CP, int Ch, int c_begin, int nch, int tid) {
-  constexpr int R = WIN / 2;
-  const int np = nch / 2, xg_n = W / T;
-  const int items = rows * xg_n * np;
-  const float inv_np = 1.0f / (float)np, inv_xg = 1.0f / (float)xg_n;
-  for (int i = tid; i < items; i += MBA_THREADS) {
-    const int i1 = fdiv(i, inv_np), p = i - i1 * np;
-    const int ty = fdiv(i1, inv_xg), xg = i1 - ty * xg_n;
-    const int cl = 2 * p, c = c_begin + cl, x0 = xg * T;
-    const int h = c / Ch, cv = c - h * Ch;
-    float v0[T], v1[T];
-#pragma unroll
-    for (int t = 0; t < T; t++) { v0[t] = bs[c]; v1[t] = bs[c + 1]; }
-#pragma unroll
-    for (int ky = 0; ky < WIN; ky++) {
-      const __half* vrow = vt + ((size_t)(ty + 3 + ky - R) * W) * CP + c;
-      float2 win[T + WIN - 1];
-#pragma unroll
-      for (int j = 0; j < T + WIN - 1; j++) {
-        const int xx = x0 + j - R;
-        win[j] = (xx >= 0 && xx < W) ? __half22float2(*reinterpret_cast<const __half2*>(vrow + (size_t)xx * CP))
-                                     : make_float2(0.f, 0.f);
-      }
-      const float* wrow = wt + (size_t)(ky * WIN) * nch + cl;
-#pragma unroll
-      for (int kx = 0; kx < WIN; kx++) {
-        const float2 ww = *reinterpret_cast<const float2*>(wrow + (size_t)kx * nch);
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-          v0[t] = fmaf(win[t + kx].x, ww.x, v0[t]);
-          v1[t] = fmaf(win[t + kx].y, ww.y, v1[t]);
-        }
-      }
-    }
-    float f0[T], f1[T];
-#pragma unroll
-    for (int t = 0; t < T; t++) { f0[t] = 0.f; f1[t] = 0.f; }
-    const float* crow = ctx + (size_t)h * Ch * Ch + cv;
-    const __half* qbase = qt + ((size_t)ty * W + x0) * C;
-    for (int k = 0; k < Ch; k += 2) {
-      const float2 ca = *reinterpret_cast<const float2*>(crow + (size_t)k * Ch);
-      const float2 cb = *reinterpret_cast<const float2*>(crow + (size_t)(k + 1) * Ch);
-#pragma unroll
-      for (int t = 0; t < T; t++) {
-        const float2 q2 = __half22float2(*reinterpret_cast<const __half2*>(qbase + (size_t)t * C + h * Ch + k));
-        f0[t] = fmaf(q2.x, ca.x, f0[t]); f1[t] = fmaf(q2.x, ca.y, f1[t]);
-        f0[t] = fmaf(q2.y, cb.x, f0[t]); f1[t] = fmaf(q2.y, cb.y, f1[t]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < T; t++) {
-      const float2 qc = __half22float2(*reinterpret_cast<const __half2*>(qbase + (size_t)t * C + c));
-      *reinterpret_cast<uint32_t*>(outp + ((size_t)ty * W + x0 + t) * C + c) = pack2(fmaf(qc.x, v0[t], f0[t]), fmaf(qc.y, v1[t], f1[t]));
-    }
-  }
-}
-
-// grid (bands, B, G), 256 threads. out[n,c] = sum_k q[n,h*Ch+k] ctx[h][k][cv] + q[n,c] * (dwconv_win(h)(V)[n,c] + bias[c])
-template <int T>
-__global__ void __launch_bounds__(MBA_THREADS) mb_apply16_kernel(const Mb16Args a, int R) {
-  extern __shared__ __align__(16) uint8_t smraw[];
-  const int H = a.H, W = a.W, C = a.C, Ch = a.C / a.heads, N = H * W;
-  const int CP = C + 8;                 // padded channel pitch of the V band (bank spreading)
-  const int tid = threadIdx.x, b = blockIdx.y, gi = blockIdx.z;
-  const int r0 = blockIdx.x * R;
-  const int rows = min(R, H - r0);
-  const int c3 = 2 * Ch, c5 = 3 * Ch, c7 = 3 * Ch;
-  __half* vt = reinterpret_cast<__half*>(smraw);                   // [(R+6)][W][CP]
-  __half* qt = vt + (size_t)(R + 6) * W * CP;                      // [R][W][C]
-  float* ctx = reinterpret_cast<float*>(qt + (size_t)R * W * C);   // [heads][Ch][Ch]
-  float* w3 = ctx + C * Ch;                                        // [9][c3]
-  float* w5 = w3 + 9 * c3;                                         // [25][c5]
-  float* w7 = w5 + 25 * c5;                                        // [49][c7]
-  float* bs = w7 + 49 * c7;                                        // [C]
-  pdl_trigger();
-  // conv filters and biases are module parameters: staged before pdl_wait (overlaps the previous kernel)
-  for (int i = tid; i < 9 * c3; i += MBA_THREADS) { const int ch = i / 9, t = i - ch * 9; w3[t * c3 + ch] = a.cw[gi][0][i]; }
-  for (int i = tid; i < 25 * c5; i += MBA_THREADS) { const int ch = i / 25, t = i - ch * 25; w5[t * c5 + ch] = a.cw[gi][1][i]; }
-  for (int i = tid; i < 49 * c7; i += MBA_THREADS) { const int ch = i / 49, t = i - ch * 49; w7[t * c7 + ch] = a.cw[gi][2][i]; }
-  for (int i = tid; i < C; i += MBA_THREADS) bs[i] = i < c3 ? a.cb[gi][0][i] : (i < c3 + c5 ? a.cb[gi][1][i - c3] : a.cb[gi][2][i - c3 - c5]);
-  pdl_wait();
-  const __half* __restrict__ base = a.qkv[gi] + (long long)b * N * 3 * C;
-  const int vpr = C / 8;
-  const float inv_vpr = 1.0f / (float)vpr, inv_w = 1.0f / (float)W;
-  // V band with 3 halo rows on each side (zero outside the map)
-  for (int i = tid; i < (R + 6) * W * vpr; i += MBA_THREADS) {
-    const int i1 = fdiv(i, inv_vpr), j = i - i1 * vpr;
-    const int ry = fdiv(i1, inv_w), px = i1 - ry * W;
-    const int y = r0 - 3 + ry;
-    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < H && ry < rows + 6) raw = *reinterpret_cast<const uint4*>(base + (long long)(y * W + px) * 3 * C + 2 * C + j * 8);
-    *reinterpret_cast<uint4*>(vt + ((size_t)ry * W + px) * CP + j * 8) = raw;
-  }
-  for (int i = tid; i < rows * W * vpr; i += MBA_THREADS) {
-    const int i1 = fdiv(i, inv_vpr), j = i - i1 * vpr;
-    *reinterpret_cast<uint4*>(qt + (size_t)i1 * C + j * 8) =
-        *reinterpret_cast<const uint4*>(base + (long long)(r0 * W + i1) * 3 * C + j * 8);
-  }
-  const float* __restrict__ cg = a.ctx[gi] + (long long)b * C * Ch;
-  for (int i = tid; i < C * Ch / 4; i += MBA_THREADS)
-    reinterpret_cast<float4*>(ctx)[i] = reinterpret_cast<const float4*>(cg)[i];
-  __syncthreads();
-  __half* __restrict__ outp = a.out[gi] + ((long long)b * N + (long long)r0 * W) * C;
-  // heads 0-1: 3x3, heads 2-4: 5x5, heads 5-7: 7x7 (MSTr.py:958); the largest windows first (longest items)
-  mb_apply_group<7, T>(vt, qt, ctx, w7, bs, outp, rows, W, C, CP, Ch, c3 + c5, c7, tid);
-  mb_apply_group<5, T>(vt, qt, ctx, w5, bs, outp, rows, W, C, CP, Ch, c3, c5, tid);
-  mb_apply_group<3, T>(vt, qt, ctx, w3, bs, outp, rows, W, C, CP, Ch, 0, c3, tid);
-}
-
-// opt in to > 48 KB of dynamic shared memory, once per kernel (keyed by the function address)
 // ------------------------------------------------------------------------------------------------------------------
 // Fused Multi-Branch attention, one block per (head, image, branch): column softmax of K over the tokens, the Ch x Ch
 // context, the factorized-attention product and the conv relative position encoding of that head's channels, all from
