@@ -153,6 +153,26 @@ def test_mixffn_skip(model, backend, path, hw, C):
     _close(got, want, backend, "MixFFN_skip " + path)
 
 
+@pytest.mark.parametrize("path,hw,C", [("backbone.block1.0.mlp", 56, 64), ("backbone.mhca_stage3.mhca_blks.1.MHCA_layers.2.mlp", 14, 128),
+                                       ("bridge.bridge_layer1.mixffn2", 28, 128)])
+def test_mixffn_fused_tail(model, path, hw, C):
+    """The optional fused tail (flag "mixtail": dw3x3+LN+GELU producer warps feeding fc2's MMA through shared memory)
+    gives the same bits as the three-kernel chain, and matches the oracle."""
+    from transception_b200 import ops
+    net, sd = model
+    mod = net.get_submodule(path)
+    x = _rand(3, hw * hw, C, seed=14)
+    want = O.mixffn_skip(sd, path, x, hw, hw)
+    base = mod(x.cuda(), hw, hw)
+    ops.set_flag("mixtail", 1)
+    try:
+        got = mod(x.cuda(), hw, hw)
+    finally:
+        ops.set_flag("mixtail", 0)
+    assert torch.equal(got, base)
+    _close(got, want, TC_TOL, "MixFFN_skip fused tail " + path)
+
+
 # ---- RIPM / ResBlock / MB stage / IFF ----------------------------------------------------------------
 @pytest.mark.parametrize("stage,C,hw", [(2, 64, 56), (3, 128, 28), (4, 320, 14)])
 def test_ripm(model, backend, stage, C, hw):

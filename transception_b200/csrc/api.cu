@@ -61,6 +61,7 @@ void tcx_prof_end(const char* name, cudaStream_t st, double work) {
 static int g_flag_gemm_tc = 1;
 static int g_flag_flash_tc = 1;
 static int g_flag_f16 = 1;
+static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
 bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
@@ -318,6 +319,13 @@ int run_mixffn16(int G, const Mix16* m, float eps, int B, int H, int W, int C, i
     }
     TCX_TRY(launch_gemm(g, st));
   }
+  if (g_flag_mixtail && !m[0].ln.out && mixtail_eligible(G, C4, (long long)B * N)) {
+    // dw3x3 + skip + LN + GELU feed fc2's A tile through shared memory: one kernel, no [M, C4] round trip
+    MixTailDesc d[TCX_MAX_GROUPS];
+    for (int i = 0; i < G; i++)
+      d[i] = MixTailDesc{hbuf + i * per, m[i].dww, m[i].dwb, m[i].lnw, m[i].lnb, m[i].w2, m[i].b2, m[i].res, m[i].y};
+    return launch_mixtail(d, G, B, H, W, C4, eps, strided ? m[0].res_bs : 0, strided ? m[0].y_bs : 0, st);
+  }
   {
     DwLnArgs a{};
     a.B = B; a.H = H; a.W = W; a.C = C4; a.eps = eps; a.gelu = 1;
@@ -526,6 +534,7 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "flash_tc")) f = &g_flag_flash_tc;
   else if (!strcmp(name, "f16_pipeline")) f = &g_flag_f16;
   else if (!strcmp(name, "fork")) f = &g_flag_fork;
+  else if (!strcmp(name, "mixtail")) f = &g_flag_mixtail;
   else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;

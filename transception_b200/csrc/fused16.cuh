@@ -46,3 +46,19 @@ struct Mb16Args {
   const float* cb[TCX_MAX_GROUPS][3];
 };
 int launch_mb_attention16(const Mb16Args& a, int groups, cudaStream_t st);
+
+// fused Mix-FFN tail: y = res + fc2(GELU(LN(dw3x3(h) + b + h))) for C4 in {256, 512} (mixtail.cu)
+struct MixTailDesc {
+  const void* h;      // [B*N][C4] fp16 fc1 output
+  const float* dww;   // [C4,1,3,3]
+  const float* dwb;   // [C4] or null
+  const float* lnw;   // [C4]
+  const float* lnb;   // [C4]
+  const void* w2;     // prepared fp16 fc2 weight [C][C4]
+  const float* b2;    // [C]
+  const float* res;   // fp32 residual rows or null
+  float* y;           // fp32 output rows
+};
+bool mixtail_eligible(int groups, int C4, long long tokens);
+int launch_mixtail(const MixTailDesc* d, int groups, int B, int H, int W, int C4, float eps, long long res_bs, long long y_bs,
+                   cudaStream_t st);
