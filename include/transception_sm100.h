@@ -186,6 +186,38 @@ int tcx_final_expand_head_fwd(const float* x, const float* w, const float* lnw, 
                               const float* cls_w, const float* cls_b, int ncls, float* logits_nchw, int B, int H,
                               int W, void* ws, void* stream);
 
+/* ---- networks/Transception.py variant; fp16 pipeline only: every GEMM weight must have been
+ * registered with tcx_prepare_weight_f16 / tcx_prepare_conv_weight_f16, otherwise the call fails (no fallback). ---- */
+
+/* FuseEfficientAttention.forward (Transception.py:49-87, head_count = 1) on LayerNorm output xn [B][N][C]:
+ * y = residual + reprojection(att) with the reference's raw [N][C] -> [C][N] re-reading of keys / queries / values.
+ * p = {keys_w,keys_b, queries_w,queries_b, values_w,values_b, reprojection_w,reprojection_b}; C % 64 == 0, C <= 512. */
+size_t tcx_fuse_eff_attn_workspace_bytes(int B, int N, int C);
+int tcx_fuse_eff_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C, void* ws,
+                          void* stream);
+
+/* EfficientTransformerBlockFuse.forward (Transception.py:213-250, two-branch case) on x [B][H1*W1 + H2*W2][C] -> y.
+ * p = {n1_w,n1_b, k_w,k_b,q_w,q_b,v_w,v_b,reproj_w,reproj_b, n2_w,n2_b, mlp1[8], mlp2[8]} (Mix-FFN slots as in
+ * tcx_mixffn_skip_fwd); N = H1*W1 + H2*W2 */
+size_t tcx_fuse_block_workspace_bytes(int B, int N, int C);
+int tcx_fuse_block_fwd(const float* x, const void* const* p, float ln_eps, float mlp_ln_eps, float* y, int B, int H1, int W1, int H2,
+                       int W2, int C, void* ws, void* stream);
+
+/* The two OverlapPatchEmbeddings_fuse branches of a stage (EffSegformer.py:117-131; Transception.py:412-419) on the NHWC
+ * map x [B][H][W][Cin]: conv k1 x k1 / k2 x k2 (shared stride and dilation) + LayerNorm each, written to the concatenated
+ * token buffer tokens [B][n1+n2][C].  p = {proj1_w,proj1_b,norm1_w,norm1_b, proj2_w,proj2_b,norm2_w,norm2_b}. */
+size_t tcx_dual_patch_embed_workspace_bytes(int B, int H, int W, int Cin, int C, int k1, int k2, int stride, int pad1, int pad2,
+                                            int dil);
+int tcx_dual_patch_embed_fwd(const float* x, const void* const* p, float ln_eps, float* tokens, int B, int H, int W, int Cin, int C,
+                             int k1, int k2, int stride, int pad1, int pad2, int dil, void* ws, void* stream);
+
+/* Stage tail of MiT_3inception.forward (Transception.py:462-476, concat='original'): LayerNorm of all tokens, branch-1 map
+ * nearest-upsampled (F.interpolate default) to H2 x W2, channel concat, 1x1 conv 2C -> C.  out [B][H2*W2][C] (NHWC map).
+ * p = {norm_w,norm_b, conv1_1_w,conv1_1_b} */
+size_t tcx_fuse_merge_workspace_bytes(int B, int N, int n2, int C);
+int tcx_fuse_merge_fwd(const float* tokens, const void* const* p, float ln_eps, float* out, int B, int H1, int W1, int H2, int W2,
+                       int C, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

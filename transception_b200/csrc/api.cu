@@ -9,6 +9,7 @@
 #include "misc.cuh"
 #include "fused16.cuh"
 #include "ea16.cuh"
+#include "fuse.cuh"
 #include <mutex>
 #include <unordered_map>
 
@@ -1273,6 +1274,176 @@ int tcx_final_expand_head_fwd(const float* x, const float* w, const float* lnw, 
   GemmParams g = gemm1(x, w, e, B * H * W, 1024, 64);
   TCX_TRY(launch_gemm(g, st));
   return launch_final_head(e, B, H, W, lnw, lnb, eps, cls_w, cls_b, ncls, logits_nchw, st);
+}
+
+// ---- networks/Transception.py variant: fp16 pipeline only ----------------------------
+static inline int fuse_np(int N) { return (N + 63) / 64 * 64; }
+static inline int conv_out(int H, int k, int stride, int pad, int dil) { return (H + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
+
+// FuseEfficientAttention (Transception.py:49-87, head_count = 1) on fp16 LayerNorm output xn16 [B*N][C]:
+// y = residual + reprojection(att).  p = {keys w,b, queries w,b, values w,b, reprojection w,b}
+static size_t fuse_ea_workspace_floats(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C, bcp = (size_t)B * C * fuse_np(N);
+  return rnd(3 * bnc / 2 + 64) + 2 * rnd(bcp / 2 + 64) + rnd((size_t)B * C * C / 2 + 64) + 2 * rnd(bnc / 2 + 64);
+}
+static int run_fuse_ea16(const __half* xn16, const void* const* p, const float* residual, float* y, int B, int N, int C,
+                         float* ws, cudaStream_t st) {
+  TCX_REQUIRE(C % 64 == 0 && C <= 512, "fuse_eff_attn: C must be a multiple of 64, at most 512 (got %d)", C);
+  for (int i = 0; i < 4; i++) TCX_REQUIRE(w16_of(p[2 * i]) != nullptr, "fuse_eff_attn: weight %d is not prepared (fp16 pipeline only)", i);
+  Carver c(ws);
+  const size_t bnc = (size_t)B * N * C;
+  const int Np = fuse_np(N);
+  __half* kqv = H16(c.take(3 * bnc / 2 + 64));
+  __half* Pk = H16(c.take((size_t)B * C * Np / 2 + 64));
+  __half* Vp = H16(c.take((size_t)B * C * Np / 2 + 64));
+  __half* ctxT = H16(c.take((size_t)B * C * C / 2 + 64));
+  __half* QsT = H16(c.take(bnc / 2 + 64));
+  __half* att = H16(c.take(bnc / 2 + 64));
+  {
+    GemmParams g = gemm1(F(xn16), nullptr, nullptr, B * N, C, C);
+    g.groups = 3; g.ab16 = 1; g.out16 = 1;
+    for (int i = 0; i < 3; i++) {
+      g.g[i].A = F(xn16); g.g[i].W = F(w16_of(p[2 * i])); g.g[i].epi.bias = F(p[2 * i + 1]);
+      g.g[i].C = reinterpret_cast<float*>(kqv + i * bnc);
+    }
+    TCX_TRY(launch_gemm(g, st));
+  }
+  {  // the context chain and the query softmax are independent
+    AuxStreams* aux = aux_streams(st);
+    if (aux) TCX_TRY(fork_streams(aux, st, 1));
+    TCX_TRY(launch_fea_qsoftmaxT(kqv + bnc, QsT, B, N, C, aux ? aux->s[0] : st));
+    TCX_TRY(launch_fea_kpack(kqv, kqv + 2 * bnc, Pk, Vp, B, N, C, Np, st));
+    // ctxT[b][cv][ck] = sum_n Vp[b][cv][n] * Pk[b][ck][n]
+    GemmParams g = gemm1(F(Vp), F(Pk), reinterpret_cast<float*>(ctxT), C, C, Np);
+    g.batch = B; g.strideA = (long long)C * Np; g.strideW = (long long)C * Np; g.strideC = (long long)C * C;
+    g.ab16 = 1; g.out16 = 1;
+    TCX_TRY(launch_gemm(g, st));
+    if (aux) TCX_TRY(join_stream(aux, 0, st));
+  }
+  {  // att[b] = QsT[b] (N x C) * ctx[b] (C x C): W = ctxT[b]
+    GemmParams a = gemm1(F(QsT), F(ctxT), reinterpret_cast<float*>(att), N, C, C);
+    a.batch = B; a.strideA = (long long)N * C; a.strideW = (long long)C * C; a.strideC = (long long)N * C;
+    a.ab16 = 1; a.out16 = 1;
+    TCX_TRY(launch_gemm(a, st));
+  }
+  GemmParams r = gemm1(F(att), F(w16_of(p[6])), y, B * N, C, C);
+  r.ab16 = 1;
+  r.g[0].epi.bias = F(p[7]);
+  r.g[0].epi.residual = residual;
+  return launch_gemm(r, st);
+}
+
+size_t tcx_fuse_eff_attn_workspace_bytes(int B, int N, int C) {
+  return 4 * (fuse_ea_workspace_floats(B, N, C) + rnd((size_t)B * N * C / 2 + 64)) + 1024;
+}
+int tcx_fuse_eff_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C, void* ws,
+                          void* stream) {
+  cudaStream_t st = S(stream);
+  Carver c(ws);
+  __half* xn16 = H16(c.take((size_t)B * N * C / 2 + 64));
+  float* rest = c.take(fuse_ea_workspace_floats(B, N, C));
+  TCX_TRY(launch_f32_to_f16(xn, xn16, (long long)B * N * C, st));
+  return run_fuse_ea16(xn16, p, residual, y, B, N, C, rest, st);
+}
+
+// EfficientTransformerBlockFuse (Transception.py:213-250, two-branch case) on the concatenated token buffer
+// x [B][n1+n2][C] (n1 = H1*W1 tokens of the dilated 3x3 branch, n2 = H2*W2 of the 1x1 branch).
+// p = {norm1 w,b, keys w,b, queries w,b, values w,b, reprojection w,b, norm2 w,b, mlp1[8], mlp2[8]} (Mix-FFN blocks as in
+// tcx_mixffn_skip_fwd)
+size_t tcx_fuse_block_workspace_bytes(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  return 4 * (rnd(bnc / 2 + 64) + rnd(bnc) + fuse_ea_workspace_floats(B, N, C) + 2 * 2 * rnd(bnc * 2 + 64)) + 1024;
+}
+int tcx_fuse_block_fwd(const float* x, const void* const* p, float ln_eps, float mlp_ln_eps, float* y, int B, int H1, int W1, int H2,
+                       int W2, int C, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  const int n1 = H1 * W1, n2 = H2 * W2, N = n1 + n2;
+  const size_t bnc = (size_t)B * N * C;
+  Carver c(ws);
+  __half* n16 = H16(c.take(bnc / 2 + 64));
+  float* tx = c.take(bnc);
+  float* aws = c.take(fuse_ea_workspace_floats(B, N, C));
+  TCX_TRY(run_ln16_1(x, F(p[0]), F(p[1]), n16, nullptr, (long long)B * N, C, ln_eps, st));
+  TCX_TRY(run_fuse_ea16(n16, p + 2, x, tx, B, N, C, aws, st));
+  TCX_TRY(run_ln16_1(tx, F(p[10]), F(p[11]), n16, nullptr, (long long)B * N, C, ln_eps, st));   // shared norm2, :230-231
+  AuxStreams* aux = aux_streams(st);
+  if (aux) TCX_TRY(fork_streams(aux, st, 1));
+  const long long sb = (long long)N * C;
+  for (int k = 0; k < 2; k++) {
+    const int h = k ? H2 : H1, w = k ? W2 : W1;
+    const long long off = k ? (long long)n1 * C : 0;
+    __half* hb = H16(c.take(bnc * 2 + 64));     // sized for the whole sequence: B*n_k*4C halfs fit
+    __half* ab = H16(c.take(bnc * 2 + 64));
+    Mix16 m{};
+    TCX_REQUIRE(mix16_fill(p + 12 + 8 * k, m), "fuse_block: Mix-FFN %d weights are not prepared (fp16 pipeline only)", k + 1);
+    m.xn = n16 + off; m.xn_bs = sb; m.res = tx + off; m.res_bs = sb; m.y = y + off; m.y_bs = sb;
+    TCX_TRY(run_mixffn16(1, &m, mlp_ln_eps, B, h, w, C, 4 * C, hb, ab, (aux && k) ? aux->s[0] : st));
+  }
+  if (aux) TCX_TRY(join_stream(aux, 0, st));
+  return 0;
+}
+
+// The two OverlapPatchEmbeddings_fuse branches of one stage (EffSegformer.py:117-131, Transception.py:383-387, :412-419)
+// on the NHWC fp32 map x [B][H][W][Cin]: k1 x k1 and k2 x k2 convs (stride / dilation shared, no padding when
+// dil_conv = 1) + their LayerNorms, written into the concatenated token buffer tokens [B][n1+n2][C].
+// p = {proj1 w,b, norm1 w,b, proj2 w,b, norm2 w,b}; proj weights prepared with tcx_prepare_conv_weight_f16.
+size_t tcx_dual_patch_embed_workspace_bytes(int B, int H, int W, int Cin, int C, int k1, int k2, int stride, int pad1, int pad2, int dil) {
+  const int H1 = conv_out(H, k1, stride, pad1, dil), W1 = conv_out(W, k1, stride, pad1, dil);
+  const int H2 = conv_out(H, k2, stride, pad2, dil), W2 = conv_out(W, k2, stride, pad2, dil);
+  const size_t r1 = (size_t)B * H1 * W1, r2 = (size_t)B * H2 * W2;
+  return 4 * (rnd(r1 * k1 * k1 * Cin / 2 + 64) + rnd(r2 * k2 * k2 * Cin / 2 + 64) + rnd(r1 * C) + rnd(r2 * C)) + 1024;
+}
+int tcx_dual_patch_embed_fwd(const float* x, const void* const* p, float ln_eps, float* tokens, int B, int H, int W, int Cin, int C,
+                             int k1, int k2, int stride, int pad1, int pad2, int dil, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  const int ks[2] = {k1, k2}, pads[2] = {pad1, pad2};
+  int Ho[2], Wo[2];
+  for (int i = 0; i < 2; i++) { Ho[i] = conv_out(H, ks[i], stride, pads[i], dil); Wo[i] = conv_out(W, ks[i], stride, pads[i], dil); }
+  TCX_REQUIRE(Ho[0] > 0 && Wo[0] > 0 && Ho[1] > 0 && Wo[1] > 0, "dual_patch_embed: empty output map");
+  const int n1 = Ho[0] * Wo[0], n2 = Ho[1] * Wo[1];
+  Carver c(ws);
+  AuxStreams* aux = aux_streams(st);
+  if (aux) TCX_TRY(fork_streams(aux, st, 1));
+  for (int i = 0; i < 2; i++) {
+    cudaStream_t sk = (aux && i) ? aux->s[0] : st;
+    const int n = i ? n2 : n1, K = ks[i] * ks[i] * Cin;
+    const void* w16 = w16_of(p[4 * i]);
+    TCX_REQUIRE(w16 != nullptr, "dual_patch_embed: conv weight %d is not prepared (fp16 pipeline only)", i + 1);
+    __half* A = H16(c.take((size_t)B * n * K / 2 + 64));
+    float* o = c.take((size_t)B * n * C);
+    TCX_TRY(launch_im2row16(x, A, B, H, W, Cin, ks[i], stride, pads[i], dil, Ho[i], Wo[i], sk));
+    GemmParams g = gemm1(F(A), F(w16), o, B * n, C, K);
+    g.ab16 = 1;
+    g.g[0].epi.bias = F(p[4 * i + 1]);
+    TCX_TRY(launch_gemm(g, sk));
+    TCX_TRY(launch_ln_scatter(o, F(p[4 * i + 2]), F(p[4 * i + 3]), tokens + (i ? (long long)n1 * C : 0), B, n, C,
+                              (long long)(n1 + n2) * C, ln_eps, sk));
+  }
+  if (aux) TCX_TRY(join_stream(aux, 0, st));
+  return 0;
+}
+
+// Stage tail of MiT_3inception (Transception.py:462-476, concat='original'): stage LayerNorm over all tokens, branch-1 map
+// nearest-upsampled to the branch-2 size, channel concat, 1x1 conv (2C -> C).  out: [B][H2*W2][C] fp32 tokens (= NHWC map).
+// p = {norm w,b, conv1_1 w,b}
+size_t tcx_fuse_merge_workspace_bytes(int B, int N, int n2, int C) {
+  return 4 * (rnd((size_t)B * N * C / 2 + 64) + rnd((size_t)B * n2 * C + 64)) + 1024;
+}
+int tcx_fuse_merge_fwd(const float* tokens, const void* const* p, float ln_eps, float* out, int B, int H1, int W1, int H2, int W2, int C,
+                       void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  const int n1 = H1 * W1, n2 = H2 * W2, N = n1 + n2;
+  const void* w16 = w16_of(p[2]);
+  TCX_REQUIRE(w16 != nullptr, "fuse_merge: 1x1 conv weight is not prepared (fp16 pipeline only)");
+  Carver c(ws);
+  __half* t16 = H16(c.take((size_t)B * N * C / 2 + 64));
+  __half* A = H16(c.take((size_t)B * n2 * C + 64));
+  TCX_TRY(run_ln16_1(tokens, F(p[0]), F(p[1]), t16, nullptr, (long long)B * N, C, ln_eps, st));
+  TCX_TRY(launch_upcat16(t16, A, B, H1, W1, H2, W2, C, st));
+  GemmParams g = gemm1(F(A), F(w16), out, B * n2, C, 2 * C);
+  g.ab16 = 1;
+  g.g[0].epi.bias = F(p[3]);
+  return launch_gemm(g, st);
 }
 
 }  // extern "C"

@@ -39,6 +39,14 @@ _PROTOS = {
     "tcx_forget_weight": (_i, [_vp]),
     "tcx_eff_block_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_eff_block_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_fuse_eff_attn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_fuse_eff_attn_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_fuse_block_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_fuse_block_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_dual_patch_embed_workspace_bytes": (_sz, [_i] * 11),
+    "tcx_dual_patch_embed_fwd": (_i, [_vp, _pp, _f, _vp] + [_i] * 11 + [_vp, _vp]),
+    "tcx_fuse_merge_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_fuse_merge_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_layer_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_layer_fwd": (_i, [_vp, _pp, _i, _f, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_bridge_block_workspace_bytes": (_sz, [_i, _i]),
@@ -644,3 +652,76 @@ def final_expand_head(x, H, W, ew, lnw, lnb, eps, cw, cb):
                                        _ptr(_d(cw).reshape(ncls, 64)), _ptr(_d(cb)), ncls, _ptr(y), B, H, W,
                                        _ptr(ws), _stream()))
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# networks/Transception.py variant — fp16 pipeline only
+# ------------------------------------------------------------------------------------------------
+def fuse_eff_attn(xn, kw, kb, qw, qb, vw, vb, rw, rb, residual=None):
+    """FuseEfficientAttention.forward (reference Transception.py:49-87, head_count=1) on tokens [B, N, C]."""
+    require_cuda(xn)
+    lib = load_library()
+    xn = xn.contiguous()
+    B, N, C = xn.shape
+    y = torch.empty_like(xn)
+    ws = _ws(lib.tcx_fuse_eff_attn_workspace_bytes(B, N, C), xn)
+    tab = _table([kw, kb, qw, qb, vw, vb, rw, rb], mats=(0, 2, 4, 6))
+    _chk(lib.tcx_fuse_eff_attn_fwd(_ptr(xn), tab, _ptr(residual.contiguous() if residual is not None else None), _ptr(y),
+                                   B, N, C, _ptr(ws), _stream()))
+    return y
+
+
+def fuse_block(x, H1, W1, H2, W2, n1w, n1b, ln_eps, attn_args, n2w, n2b, mix1_args, mix2_args):
+    """EfficientTransformerBlockFuse.forward (reference Transception.py:213-250) on [B, H1*W1 + H2*W2, C] tokens."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, N, C = x.shape
+    if N != H1 * W1 + H2 * W2:
+        raise NotImplementedError("EfficientTransformerBlockFuse is built for the two-branch token layout (n1 + n2 tokens)")
+    m1, eps1 = _mix_slots(mix1_args)
+    m2, eps2 = _mix_slots(mix2_args)
+    if eps1 != eps2:
+        raise NotImplementedError("mlp1 / mlp2 LayerNorm eps differ")
+    slots = [n1w, n1b] + list(attn_args) + [n2w, n2b] + m1 + m2
+    y = torch.empty_like(x)
+    ws = _ws(lib.tcx_fuse_block_workspace_bytes(B, N, C), x)
+    _chk(lib.tcx_fuse_block_fwd(_ptr(x), _table(slots, mats=(2, 4, 6, 8, 12, 18, 20, 26)), ln_eps, eps1, _ptr(y), B, H1, W1, H2, W2,
+                                C, _ptr(ws), _stream()))
+    return y
+
+
+def dual_patch_embed(x_nhwc, pe1, pe2, ln_eps):
+    """Both OverlapPatchEmbeddings_fuse branches of a stage (reference EffSegformer.py:117-131) on an NHWC fp32 map.
+    pe = (proj_w [C,Cin,k,k], proj_b, norm_w, norm_b, k, stride, padding, dilation).  Returns (tokens, H1, W1, H2, W2)."""
+    require_cuda(x_nhwc)
+    lib = load_library()
+    x = x_nhwc.contiguous()
+    B, H, W, Cin = x.shape
+    (w1, b1, nw1, nb1, k1, s1, p1, d1), (w2, b2, nw2, nb2, k2, s2, p2, d2) = pe1, pe2
+    if s1 != s2 or d1 != d2:
+        raise NotImplementedError("the two patch-merging branches must share stride and dilation")
+    C = w1.shape[0]
+    H1, W1 = (H + 2 * p1 - d1 * (k1 - 1) - 1) // s1 + 1, (W + 2 * p1 - d1 * (k1 - 1) - 1) // s1 + 1
+    H2, W2 = (H + 2 * p2 - d1 * (k2 - 1) - 1) // s1 + 1, (W + 2 * p2 - d1 * (k2 - 1) - 1) // s1 + 1
+    prepare_weight(w1, conv=(C, Cin, k1))
+    prepare_weight(w2, conv=(C, Cin, k2))
+    tokens = torch.empty((B, H1 * W1 + H2 * W2, C), device=x.device, dtype=torch.float32)
+    ws = _ws(lib.tcx_dual_patch_embed_workspace_bytes(B, H, W, Cin, C, k1, k2, s1, p1, p2, d1), x)
+    tab = _table([w1, b1, nw1, nb1, w2, b2, nw2, nb2])
+    _chk(lib.tcx_dual_patch_embed_fwd(_ptr(x), tab, ln_eps, _ptr(tokens), B, H, W, Cin, C, k1, k2, s1, p1, p2, d1, _ptr(ws),
+                                      _stream()))
+    return tokens, H1, W1, H2, W2
+
+
+def fuse_merge(tokens, H1, W1, H2, W2, nw, nb, ln_eps, cw, cb):
+    """Stage tail of MiT_3inception (reference Transception.py:462-476, concat='original') -> [B, H2*W2, C] tokens."""
+    require_cuda(tokens)
+    lib = load_library()
+    t = tokens.contiguous()
+    B, N, C = t.shape
+    out = torch.empty((B, H2 * W2, C), device=t.device, dtype=torch.float32)
+    ws = _ws(lib.tcx_fuse_merge_workspace_bytes(B, N, H2 * W2, C), t)
+    tab = _table([nw, nb, cw.reshape(C, 2 * C), cb], mats=(2,))
+    _chk(lib.tcx_fuse_merge_fwd(_ptr(t), tab, ln_eps, _ptr(out), B, H1, W1, H2, W2, C, _ptr(ws), _stream()))
+    return out
