@@ -88,10 +88,21 @@ def _make_inputs(torch, batch, seed):
     return torch.rand(batch, IN_CH, SIZE, SIZE, generator=g) * 2 - 1
 
 
+MODEL = "MSTransception"     # --model Transception times the networks/Transception.py variant (non-headline)
+
+
+def _model_cls():
+    import transception_b200
+    return getattr(transception_b200, MODEL)
+
+
 def cpu_reference_time(torch, steps, warmup, budget_s=150.0):
     """Time the CPU oracle forward (the reference's algorithm on host cores). Returns (img/s, cores, sample, ms/step)."""
-    from oracle import mstr_oracle as O
-    from transception_b200 import MSTransception
+    if MODEL == "Transception":
+        from oracle import transception_oracle as O
+    else:
+        from oracle import mstr_oracle as O
+    MSTransception = _model_cls()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
@@ -134,8 +145,9 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from transception_b200 import MSTransception, ops
+    from transception_b200 import ops
     from transception_b200.runtime import GraphRunner
+    MSTransception = _model_cls()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,8 +237,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f16/tf32 tensor-core MMA, f32 accumulate, f32 IO", "data": "synthetic",
                 "config": {"workload": "TransCeption Synapse %dx%d bs16 fp32 forward (%s), "
                                        "per-GPU batch 16, %d class logits" % (
-                                           SIZE, SIZE, "BASELINE configs[1]" if SIZE == 224 and NCLS == 9 else
-                                           "non-headline geometry", NCLS),
+                                           SIZE, SIZE, "BASELINE configs[1]" if SIZE == 224 and NCLS == 9 and MODEL == "MSTransception" else
+                                           "non-headline workload: " + MODEL, NCLS),
                            "l2": "256 MiB memset between timed steps (untimed); step footprint > L2",
                            "timing": "per-step CUDA events on the replay stream, summed; max over ranks",
                            "graph": "whole forward replayed as one CUDA graph"},
@@ -266,7 +278,7 @@ def run_ours(args):
 
 
 def main():
-    global SIZE, NCLS, IN_CH, METRIC
+    global SIZE, NCLS, IN_CH, METRIC, MODEL
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -278,11 +290,13 @@ def main():
     ap.add_argument("--in-ch", type=int, default=IN_CH)
     ap.add_argument("--microbatches", type=int, default=1,
                     help="split each rank's batch of 16 into this many slices captured on parallel streams")
+    ap.add_argument("--model", default=MODEL, choices=["MSTransception", "Transception"],
+                    help="MSTransception = the headline workload; Transception = the networks/Transception.py variant")
     args = ap.parse_args()
-    if (args.size, args.classes, args.in_ch) != (SIZE, NCLS, IN_CH):
-        SIZE, NCLS, IN_CH = args.size, args.classes, args.in_ch
-        METRIC = "images/sec fwd @%dx%d bs16 (TransCeption MSTransception, %d classes, fp32 IO) [non-headline geometry]" % (
-            SIZE, SIZE, NCLS)
+    if (args.size, args.classes, args.in_ch, args.model) != (SIZE, NCLS, IN_CH, MODEL):
+        SIZE, NCLS, IN_CH, MODEL = args.size, args.classes, args.in_ch, args.model
+        METRIC = "images/sec fwd @%dx%d bs16 (TransCeption %s, %d classes, fp32 IO) [non-headline workload]" % (
+            SIZE, SIZE, MODEL, NCLS)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -218,6 +218,14 @@ size_t tcx_fuse_merge_workspace_bytes(int B, int N, int n2, int C);
 int tcx_fuse_merge_fwd(const float* tokens, const void* const* p, float ln_eps, float* out, int B, int H1, int W1, int H2, int W2,
                        int C, void* ws, void* stream);
 
+/* Same stage tail with the selective-kernel fusion SK_Block (Transception.py:477-481, :328-358; concat != 'original'):
+ * S = mean(map1 + map2), Z = fc(S), softmax over the two paths of fcs_i(Z), V = sum a_i map_i, 1x1 conv -> ReLU -> BN(eval).
+ * p = {norm_w,norm_b, fc_w,fc_b, fcs0_w,fcs0_b, fcs1_w,fcs1_b, conv_w,conv_b, bn_w,bn_b,bn_running_mean,bn_running_var};
+ * d = width of fc (max(32, C/16)) */
+size_t tcx_fuse_merge_sk_workspace_bytes(int B, int N, int n2, int C);
+int tcx_fuse_merge_sk_fwd(const float* tokens, const void* const* p, float ln_eps, float bn_eps, float* out, int B, int H1, int W1,
+                          int H2, int W2, int C, int d, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,11 +10,11 @@ from oracle import transception_oracle as TO
 MODEL_SEED = 1234
 
 
-def seeded_model(num_classes=9, perturb=True):
+def seeded_model(num_classes=9, perturb=True, concat='original'):
     """The drop-in parameter mirror with the reference's same-seed init (+ perturbed affine / bias tensors), eval mode."""
     from transception_b200 import Transception
     torch.manual_seed(MODEL_SEED)
-    net = Transception(num_classes=num_classes)
+    net = Transception(num_classes=num_classes, concat=concat)
     if perturb:
         FX.randomise(net)
     return net.eval()

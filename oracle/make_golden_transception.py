@@ -54,6 +54,16 @@ def main():
                 "argmax_sub": logits.argmax(1)[:, ::2, ::2].to(torch.uint8).clone(),
                 "enc_sub": [FX.subsample(m) for m in enc], "enc_stats": [FX.stats(m) for m in enc]}
             print("model_c%d logits stats %s" % (cin, FX.stats(logits).tolist()))
+        # selective-kernel fusion (concat='sk'): same parameters, other stage tail
+        ref_sk = R.Transception(num_classes=9, concat='sk').eval()
+        ref_sk.load_state_dict(sd, strict=True)
+        x = FX.image(1, 1, seed=0)
+        enc = ref_sk.backbone(x.repeat(1, 3, 1, 1))
+        logits = ref_sk(x)
+        golden["model_sk"] = {"logits_sub": logits[:, :, ::4, ::4].clone(), "logits_stats": FX.stats(logits),
+                              "argmax_sub": logits.argmax(1)[:, ::2, ::2].to(torch.uint8).clone(),
+                              "enc_sub": [FX.subsample(m) for m in enc], "enc_stats": [FX.stats(m) for m in enc]}
+        print("model_sk logits stats %s" % FX.stats(logits).tolist())
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, "transception_golden.pt")
     torch.save(golden, path)

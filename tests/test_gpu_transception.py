@@ -102,6 +102,35 @@ def test_whole_model(model, golden, cin, bs):
     assert (got[:, :, ::4, ::4] - g["logits_sub"]).abs().max().item() <= 5e-2
 
 
+@pytest.mark.parametrize("stage,C,hw,bs", [(2, 64, 56, 2), (4, 320, 14, 3)])
+def test_inception_stage_sk_fusion(model, stage, C, hw, bs):
+    """same stage with the selective-kernel fusion tail (concat='sk': SK_Block, Transception.py:328-358)"""
+    net, sd = model
+    x = FX.rand(bs, C, hw, hw, seed=70 + stage)
+    net.backbone.concat = 'sk'
+    try:
+        with torch.no_grad():
+            want = TO.fuse_stage(sd, 'backbone', x, stage, concat='sk')
+            got = net.backbone.stage(x.cuda().permute(0, 2, 3, 1).contiguous(), stage).permute(0, 3, 1, 2)
+    finally:
+        net.backbone.concat = 'original'
+    _close(got, want, TC_TOL * 2, "inception stage %d (sk)" % stage)
+
+
+def test_whole_model_sk_fusion(cuda_lib, golden):
+    net = seeded_model(perturb=True, concat='sk')
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    x = FX.image(1, 1, seed=0)
+    with torch.no_grad():
+        want = TO.forward(sd, x, concat='sk')
+        got = net(x.cuda()).float().cpu()
+    err, mean = (got - want).abs().max().item(), (got - want).abs().mean().item()
+    print("Transception(concat='sk') logits max-abs %.3e mean-abs %.3e" % (err, mean))
+    assert err <= 5e-2 and mean <= 5e-3
+    assert (got[:, :, ::4, ::4] - golden["model_sk"]["logits_sub"]).abs().max().item() <= 5e-2
+
+
 def test_forward_is_bit_reproducible_and_graph_capturable(model):
     from transception_b200.runtime import GraphRunner
     net, _ = model

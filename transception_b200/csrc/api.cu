@@ -1446,4 +1446,34 @@ int tcx_fuse_merge_fwd(const float* tokens, const void* const* p, float ln_eps, 
   return launch_gemm(g, st);
 }
 
+// Stage tail with the selective-kernel fusion (Transception.py:477-481, SK_Block :328-358; concat != 'original'):
+// stage LayerNorm, branch-1 map nearest-upsampled, S = mean(U), Z = fc(S), softmax over the two paths of fcs_i(Z),
+// V = sum a_i * map_i, 1x1 conv -> ReLU -> BatchNorm(eval).  out [B][H2*W2][C].
+// p = {norm_w,norm_b, fc_w,fc_b, fcs0_w,fcs0_b, fcs1_w,fcs1_b, conv_w,conv_b, bn_w,bn_b,bn_rm,bn_rv}
+size_t tcx_fuse_merge_sk_workspace_bytes(int B, int N, int n2, int C) {
+  return 4 * (rnd((size_t)B * N * C / 2 + 64) + rnd((size_t)B * n2 * C / 2 + 64) + 3 * rnd((size_t)B * C + 64)) + 1024;
+}
+int tcx_fuse_merge_sk_fwd(const float* tokens, const void* const* p, float ln_eps, float bn_eps, float* out, int B, int H1, int W1,
+                          int H2, int W2, int C, int d, void* ws, void* stream) {
+  cudaStream_t st = S(stream);
+  const int n1 = H1 * W1, n2 = H2 * W2, N = n1 + n2;
+  const void* w16 = w16_of(p[8]);
+  TCX_REQUIRE(w16 != nullptr, "fuse_merge_sk: 1x1 conv weight is not prepared (fp16 pipeline only)");
+  Carver c(ws);
+  __half* t16 = H16(c.take((size_t)B * N * C / 2 + 64));
+  __half* A = H16(c.take((size_t)B * n2 * C / 2 + 64));
+  float* Sm = c.take((size_t)B * C + 64);
+  float* att = c.take(2 * (size_t)B * C + 64);
+  TCX_TRY(run_ln16_1(tokens, F(p[0]), F(p[1]), t16, nullptr, (long long)B * N, C, ln_eps, st));
+  TCX_TRY(launch_sk_pool(t16, Sm, B, H1, W1, H2, W2, C, st));
+  TCX_TRY(launch_sk_weights(Sm, F(p[2]), F(p[3]), F(p[4]), F(p[5]), F(p[6]), F(p[7]), att, B, C, d, st));
+  TCX_TRY(launch_sk_mix(t16, att, A, B, H1, W1, H2, W2, C, st));
+  GemmParams g = gemm1(F(A), F(w16), out, B * n2, C, C);
+  g.ab16 = 1;
+  g.g[0].epi.bias = F(p[9]);
+  TCX_TRY(launch_gemm(g, st));
+  BnParams bn{F(p[10]), F(p[11]), F(p[12]), F(p[13]), bn_eps};
+  return launch_relu_bn(out, (long long)B * n2, C, bn, st);
+}
+
 }  // extern "C"

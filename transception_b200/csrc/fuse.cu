@@ -183,6 +183,103 @@ __global__ void __launch_bounds__(256) upcat16_kernel(const __half* __restrict__
   *reinterpret_cast<uint4*>(A + idx * 8) = *reinterpret_cast<const uint4*>(src);
 }
 
+// ---- SK_Block (Transception.py:306-358) on the two stage maps held as fp16 tokens t16 [B][n1+n2][C] ---------------------
+__device__ __forceinline__ const __half* sk_src1(const __half* t16, int b, int i, int j, int H1, int W1, int ntok, int C, float sh, float sw) {
+  const int si = min((int)floorf((float)i * sh), H1 - 1), sj = min((int)floorf((float)j * sw), W1 - 1);
+  return t16 + ((long long)b * ntok + si * W1 + sj) * C;
+}
+// S[b][c] = mean over the H2 x W2 positions of (upsampled branch-1 + branch-2)  (:336-339).  grid (C/64, B), 256 threads =
+// 64 channels x 4 position slices, fixed-order combine (deterministic).
+__global__ void __launch_bounds__(256) sk_pool_kernel(const __half* __restrict__ t16, float* __restrict__ S, int H1, int W1, int H2, int W2,
+                                                      int C, float sh, float sw) {
+  __shared__ float part[4][64];
+  pdl_trigger();
+  pdl_wait();
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6, b = blockIdx.y;
+  const int n1 = H1 * W1, n2 = H2 * W2, ntok = n1 + n2;
+  float acc = 0.f;
+  for (int pos = slice; pos < n2; pos += 4) {
+    const int i = pos / W2, j = pos - i * W2;
+    acc += __half2float(sk_src1(t16, b, i, j, H1, W1, ntok, C, sh, sw)[c]) + __half2float(t16[((long long)b * ntok + n1 + pos) * C + c]);
+  }
+  part[slice][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    const int l = threadIdx.x;
+    S[(long long)b * C + c] = (part[0][l] + part[1][l] + part[2][l] + part[3][l]) / (float)n2;
+  }
+}
+// Z = fc(S); w_i = fcs_i(Z); a = softmax over the two paths (:340-351).  One block per image; att [B][2][C].
+__global__ void __launch_bounds__(256) sk_weights_kernel(const float* __restrict__ S, const float* __restrict__ fcw, const float* __restrict__ fcb,
+                                                         const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, float* __restrict__ att, int C, int d) {
+  extern __shared__ float sm[];      // S row [C] | Z [d]
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* srow = sm;
+  float* z = sm + C;
+  for (int c = threadIdx.x; c < C; c += 256) srow[c] = S[(long long)b * C + c];
+  __syncthreads();
+  for (int k = warp; k < d; k += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(srow[c], __ldg(fcw + (long long)k * C + c), a);
+    a = warp_sum(a);
+    if (lane == 0) z[k] = a + __ldg(fcb + k);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float u0 = __ldg(b0 + c), u1 = __ldg(b1 + c);
+    for (int k = 0; k < d; k++) {
+      u0 = fmaf(z[k], __ldg(w0 + (long long)c * d + k), u0);
+      u1 = fmaf(z[k], __ldg(w1 + (long long)c * d + k), u1);
+    }
+    const float m = fmaxf(u0, u1), e0 = __expf(u0 - m), e1 = __expf(u1 - m), inv = 1.f / (e0 + e1);
+    att[((long long)b * 2 + 0) * C + c] = e0 * inv;
+    att[((long long)b * 2 + 1) * C + c] = e1 * inv;
+  }
+}
+// V = a0 * upsampled branch-1 + a1 * branch-2 (:354) as the fp16 A operand [B*n2][C] of the 1x1 conv. Thread per 8 channels.
+__global__ void __launch_bounds__(256) sk_mix_kernel(const __half* __restrict__ t16, const float* __restrict__ att, __half* __restrict__ A, int B,
+                                                     int H1, int W1, int H2, int W2, int C, float sh, float sw) {
+  pdl_trigger();
+  pdl_wait();
+  const int c8n = C >> 3;
+  const long long total = (long long)B * H2 * W2 * c8n;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % c8n);
+  long long t = idx / c8n;
+  const int j = (int)(t % W2); t /= W2;
+  const int i = (int)(t % H2);
+  const int b = (int)(t / H2);
+  const int n1 = H1 * W1, ntok = n1 + H2 * W2;
+  const uint4 r1 = *reinterpret_cast<const uint4*>(sk_src1(t16, b, i, j, H1, W1, ntok, C, sh, sw) + c8 * 8);
+  const uint4 r2 = *reinterpret_cast<const uint4*>(t16 + ((long long)b * ntok + n1 + i * W2 + j) * C + c8 * 8);
+  const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&r2);
+  const float* a0 = att + ((long long)b * 2 + 0) * C + c8 * 8;
+  const float* a1 = att + ((long long)b * 2 + 1) * C + c8 * 8;
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float2 x1 = __half22float2(h1[q]), x2 = __half22float2(h2[q]);
+    o[q] = pk2(a0[2 * q] * x1.x + a1[2 * q] * x2.x, a0[2 * q + 1] * x1.y + a1[2 * q + 1] * x2.y);
+  }
+  *reinterpret_cast<uint4*>(A + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+// y = BatchNorm_eval(ReLU(y)) in place on [rows][C] fp32 (:322-325: conv -> ReLU -> BatchNorm2d)
+__global__ void __launch_bounds__(256) relu_bn_kernel(float* __restrict__ y, long long total, int C, BnParams bn) {
+  pdl_trigger();
+  pdl_wait();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  float scale, shift;
+  bn_fold(bn, c, scale, shift);
+  y[idx] = fmaxf(y[idx], 0.f) * scale + shift;
+}
+
 }  // namespace
 
 int launch_im2row16(const float* x, void* out16, int B, int H, int W, int Cin, int k, int stride, int pad, int dil, int Ho, int Wo,
@@ -232,4 +329,36 @@ int launch_upcat16(const void* t16, void* A, int B, int H1, int W1, int H2, int 
   tcx_launch_pdl(upcat16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(t16),
                  reinterpret_cast<__half*>(A), B, H1, W1, H2, W2, C, (float)H1 / (float)H2, (float)W1 / (float)W2);
   return tcx_check_launch("upcat16");
+}
+
+int launch_sk_pool(const void* t16, float* S, int B, int H1, int W1, int H2, int W2, int C, cudaStream_t st) {
+  TCX_REQUIRE(C % 64 == 0, "sk_pool: C must be a multiple of 64");
+  if (B == 0) return 0;
+  ProfScope prof("sk_pool", st, (double)B * H2 * W2 * C * 4);
+  tcx_launch_pdl(sk_pool_kernel, dim3(C / 64, B), dim3(256), 0, st, reinterpret_cast<const __half*>(t16), S, H1, W1, H2, W2, C,
+                 (float)H1 / (float)H2, (float)W1 / (float)W2);
+  return tcx_check_launch("sk_pool");
+}
+int launch_sk_weights(const float* S, const float* fcw, const float* fcb, const float* w0, const float* b0, const float* w1,
+                      const float* b1, float* att, int B, int C, int d, cudaStream_t st) {
+  if (B == 0) return 0;
+  ProfScope prof("sk_weights", st, (double)B * C * 12 + 3.0 * C * d * 4);
+  tcx_launch_pdl(sk_weights_kernel, dim3(B), dim3(256), (size_t)(C + d) * sizeof(float), st, S, fcw, fcb, w0, b0, w1, b1, att, C, d);
+  return tcx_check_launch("sk_weights");
+}
+int launch_sk_mix(const void* t16, const float* att, void* A, int B, int H1, int W1, int H2, int W2, int C, cudaStream_t st) {
+  TCX_REQUIRE(C % 8 == 0, "sk_mix: C must be a multiple of 8");
+  const long long total = (long long)B * H2 * W2 * (C / 8);
+  if (total == 0) return 0;
+  ProfScope prof("sk_mix", st, (double)total * 48);
+  tcx_launch_pdl(sk_mix_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const __half*>(t16), att,
+                 reinterpret_cast<__half*>(A), B, H1, W1, H2, W2, C, (float)H1 / (float)H2, (float)W1 / (float)W2);
+  return tcx_check_launch("sk_mix");
+}
+int launch_relu_bn(float* y, long long rows, int C, const BnParams& bn, cudaStream_t st) {
+  const long long total = rows * C;
+  if (total == 0) return 0;
+  ProfScope prof("relu_bn", st, (double)total * 8);
+  tcx_launch_pdl(relu_bn_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, y, total, C, bn);
+  return tcx_check_launch("relu_bn");
 }

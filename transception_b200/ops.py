@@ -47,6 +47,8 @@ _PROTOS = {
     "tcx_dual_patch_embed_fwd": (_i, [_vp, _pp, _f, _vp] + [_i] * 11 + [_vp, _vp]),
     "tcx_fuse_merge_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_fuse_merge_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_fuse_merge_sk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_fuse_merge_sk_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_layer_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_layer_fwd": (_i, [_vp, _pp, _i, _f, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_bridge_block_workspace_bytes": (_sz, [_i, _i]),
@@ -724,4 +726,19 @@ def fuse_merge(tokens, H1, W1, H2, W2, nw, nb, ln_eps, cw, cb):
     ws = _ws(lib.tcx_fuse_merge_workspace_bytes(B, N, H2 * W2, C), t)
     tab = _table([nw, nb, cw.reshape(C, 2 * C), cb], mats=(2,))
     _chk(lib.tcx_fuse_merge_fwd(_ptr(t), tab, ln_eps, _ptr(out), B, H1, W1, H2, W2, C, _ptr(ws), _stream()))
+    return out
+
+
+def fuse_merge_sk(tokens, H1, W1, H2, W2, nw, nb, ln_eps, fc, fcs0, fcs1, conv, bn):
+    """Stage tail with SK_Block fusion (reference Transception.py:477-481, :328-358) -> [B, H2*W2, C] tokens."""
+    require_cuda(tokens)
+    lib = load_library()
+    t = tokens.contiguous()
+    B, N, C = t.shape
+    d = fc.weight.shape[0]
+    out = torch.empty((B, H2 * W2, C), device=t.device, dtype=torch.float32)
+    ws = _ws(lib.tcx_fuse_merge_sk_workspace_bytes(B, N, H2 * W2, C), t)
+    tab = _table([nw, nb, fc.weight, fc.bias, fcs0.weight, fcs0.bias, fcs1.weight, fcs1.bias, conv.weight.reshape(C, C), conv.bias,
+                  bn.weight, bn.bias, bn.running_mean, bn.running_var], mats=(8,))
+    _chk(lib.tcx_fuse_merge_sk_fwd(_ptr(t), tab, ln_eps, bn.eps, _ptr(out), B, H1, W1, H2, W2, C, d, _ptr(ws), _stream()))
     return out

@@ -7,8 +7,8 @@ stay NHWC / ``[B, N, C]`` between kernels and every GEMM operand is fp16 with fp
 back end — the fp16 pipeline).
 
 Built structure: ``MiT_3inception`` (Transception.py:362-551) with ``dil_conv=1``, ``token_mlp='mix_skip'``,
-``head_count=1`` and ``concat='original'`` (1x1-conv fusion).  ``SK_Block`` (``concat != 'original'``) keeps its parameters
-for ``state_dict`` compatibility, but asking for it raises ``NotImplementedError``.  Stage 1, the Mix-FFN and the decoder are
+``head_count=1`` and both fusion modes: ``concat='original'`` (1x1 conv over the channel concat) and anything else =
+``SK_Block`` (selective-kernel fusion, eval-mode BatchNorm).  Stage 1, the Mix-FFN and the decoder are
 the modules of ``mstr.py`` (identical code in the reference: Transception.py:90-186, :892-1008; EffSegformer.py:7-46).
 """
 import torch
@@ -85,7 +85,8 @@ class EfficientTransformerBlockFuse(nn.Module):
 
 
 class SK_Block(nn.Module):
-    """Parameter holder of the selective-kernel fusion (reference Transception.py:306-358); forward not built."""
+    """Selective-kernel fusion of the two branch maps (reference Transception.py:306-358).  Inside ``MiT_3inception`` it is
+    fused with the stage LayerNorm and the nearest upsample (``ops.fuse_merge_sk``); the module itself holds the parameters."""
 
     def __init__(self, in_ch, out_ch, num_path=3, reduction=16, group=1, L=32):
         super().__init__()
@@ -97,7 +98,8 @@ class SK_Block(nn.Module):
                                         nn.BatchNorm2d(out_ch))
 
     def forward(self, x):
-        raise NotImplementedError("SK_Block fusion (concat != 'original') is not built; use concat='original'")
+        raise NotImplementedError("SK_Block runs fused inside MiT_3inception.stage (ops.fuse_merge_sk); the standalone "
+                                  "list-of-maps call is not built")
 
 
 class MiT_3inception(nn.Module):
@@ -108,8 +110,6 @@ class MiT_3inception(nn.Module):
         super().__init__()
         if not dil_conv:
             raise NotImplementedError("only dil_conv=1 (dilated 3x3 + 1x1 branches) is built")
-        if concat != 'original':
-            raise NotImplementedError("only concat='original' (1x1-conv fusion) is built")
         self.Hs = [image_size // 4, image_size // 8, image_size // 16, image_size // 32]
         self.Ws = list(self.Hs)
         dilation = 2
@@ -151,7 +151,14 @@ class MiT_3inception(nn.Module):
         for blk in getattr(self, 'block%d' % s):
             t = blk(t, H1 * W1, H2 * W2, H1, W1, H2, W2)
         norm, conv = getattr(self, 'norm%d' % s), getattr(self, 'conv1_1_s%d' % s)
-        out = ops.fuse_merge(t, H1, W1, H2, W2, norm.weight, norm.bias, norm.eps, conv.weight, conv.bias)
+        if self.concat == 'original':
+            out = ops.fuse_merge(t, H1, W1, H2, W2, norm.weight, norm.bias, norm.eps, conv.weight, conv.bias)
+        else:
+            sk = getattr(self, 'sk_concat%d' % s)
+            if sk.training:
+                raise NotImplementedError("SK_Block's BatchNorm runs with running statistics only: call .eval()")
+            out = ops.fuse_merge_sk(t, H1, W1, H2, W2, norm.weight, norm.bias, norm.eps, sk.fc, sk.fcs[0], sk.fcs[1],
+                                    sk.conv_bn_ac[0], sk.conv_bn_ac[2])
         return out.view(out.shape[0], H2, W2, -1)
 
     def nhwc(self, x):
