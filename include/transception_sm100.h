@@ -226,6 +226,24 @@ size_t tcx_fuse_merge_sk_workspace_bytes(int B, int N, int n2, int C);
 int tcx_fuse_merge_sk_fwd(const float* tokens, const void* const* p, float ln_eps, float bn_eps, float* out, int B, int H1, int W1,
                           int H2, int W2, int C, int d, void* ws, void* stream);
 
+/* ---- fused segmentation loss of the training step ----
+ * loss = w_ce * CrossEntropyLoss(logits, label) + w_dice * DiceLoss(n_classes)(logits, label, weight=class_w, softmax=True)
+ * (trainer.py:141-143 with w = 0.4 / 0.6; utils.py:11-47), forward and d loss / d logits, no host synchronisation (the
+ * reference reads one `.item()` per class per step, utils.py:45).  logits [B][K][HW] fp32 (NCHW); labels [B][HW] of
+ * label_kind 0 int64 / 1 float32 (integer-valued) / 2 int32 / 3 uint8; K <= 16; class_w = HOST array of K floats or NULL
+ * (all ones).  softmax = 0 treats `logits` as probabilities (DiceLoss(..., softmax=False)) and needs w_ce == 0.
+ * out (device, 4 + K floats) = {loss, ce, dice, number of labels outside [0,K), class_wise_dice[K] (utils.py:45)}.
+ * tcx_seg_loss_bwd needs the ws written by tcx_seg_loss_fwd on the same inputs; grad_out = device scalar or NULL (1). */
+size_t tcx_seg_loss_workspace_bytes(int B, int K, long long HW);
+int tcx_seg_loss_fwd(const float* logits, const void* labels, int label_kind, int B, int K, long long HW, int softmax, float w_ce,
+                     float w_dice, const float* class_w, float* out, void* ws, void* stream);
+int tcx_seg_loss_bwd(const float* logits, const void* labels, int label_kind, int B, int K, long long HW, int softmax, float w_ce,
+                     float w_dice, const float* class_w, const float* grad_out, float* dlogits, const void* ws, void* stream);
+
+/* Slice post-processing of utils.test_single_volume (utils.py:86): arg max over the class planes of logits [B][K][HW]
+ * -> uint8 label map [B][HW] (softmax is monotone; first index wins ties). */
+int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, int K, long long HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 #include "fused16.cuh"
 #include "ea16.cuh"
 #include "fuse.cuh"
+#include "loss.cuh"
 #include <mutex>
 #include <unordered_map>
 
@@ -1474,6 +1475,35 @@ int tcx_fuse_merge_sk_fwd(const float* tokens, const void* const* p, float ln_ep
   TCX_TRY(launch_gemm(g, st));
   BnParams bn{F(p[10]), F(p[11]), F(p[12]), F(p[13]), bn_eps};
   return launch_relu_bn(out, (long long)B * n2, C, bn, st);
+}
+
+// ---- fused training loss: 0.4 CE + 0.6 Dice of trainer.py:141-143 / utils.py:11-47 ----
+static int seg_loss_args(SegLossArgs& a, const float* logits, const void* labels, int label_kind, int B, int K, long long HW,
+                         int softmax, float w_ce, float w_dice, const float* class_w) {
+  TCX_REQUIRE(logits && labels, "seg_loss: null input");
+  a.logits = logits; a.labels = labels; a.kind = label_kind; a.B = B; a.K = K; a.HW = HW; a.softmax = softmax;
+  a.w_ce = w_ce; a.w_dice = w_dice;
+  for (int c = 0; c < SEG_LOSS_KMAX; c++) a.cw[c] = (class_w && c < K) ? class_w[c] : 1.f;     // class_w is a HOST array
+  return 0;
+}
+size_t tcx_seg_loss_workspace_bytes(int B, int K, long long HW) { return 4 * seg_loss_workspace_floats(B, K, HW); }
+int tcx_seg_loss_fwd(const float* logits, const void* labels, int label_kind, int B, int K, long long HW, int softmax, float w_ce,
+                     float w_dice, const float* class_w, float* out, void* ws, void* stream) {
+  SegLossArgs a;
+  TCX_TRY(seg_loss_args(a, logits, labels, label_kind, B, K, HW, softmax, w_ce, w_dice, class_w));
+  return launch_seg_loss_fwd(a, out, reinterpret_cast<float*>(ws), S(stream));
+}
+int tcx_seg_loss_bwd(const float* logits, const void* labels, int label_kind, int B, int K, long long HW, int softmax, float w_ce,
+                     float w_dice, const float* class_w, const float* grad_out, float* dlogits, const void* ws, void* stream) {
+  SegLossArgs a;
+  TCX_TRY(seg_loss_args(a, logits, labels, label_kind, B, K, HW, softmax, w_ce, w_dice, class_w));
+  return launch_seg_loss_bwd(a, reinterpret_cast<const float*>(ws), grad_out, dlogits, S(stream));
+}
+
+// per-pixel arg max over the class planes (utils.py:86), logits [B][K][HW] -> uint8 labels [B][HW]
+int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, int K, long long HW, void* stream) {
+  TCX_REQUIRE(logits && labels, "argmax_classes: null pointer");
+  return launch_argmax_classes(logits, labels, B, K, HW, S(stream));
 }
 
 }  // extern "C"

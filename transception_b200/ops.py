@@ -49,6 +49,10 @@ _PROTOS = {
     "tcx_fuse_merge_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_fuse_merge_sk_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_fuse_merge_sk_fwd": (_i, [_vp, _pp, _f, _f, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_seg_loss_workspace_bytes": (_sz, [_i, _i, _ll]),
+    "tcx_seg_loss_fwd": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _f, _f, ctypes.POINTER(_f), _vp, _vp, _vp]),
+    "tcx_seg_loss_bwd": (_i, [_vp, _vp, _i, _i, _i, _ll, _i, _f, _f, ctypes.POINTER(_f), _vp, _vp, _vp, _vp]),
+    "tcx_argmax_classes_fwd": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "tcx_bridge_layer_workspace_bytes": (_sz, [_i, _i]),
     "tcx_bridge_layer_fwd": (_i, [_vp, _pp, _i, _f, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_bridge_block_workspace_bytes": (_sz, [_i, _i]),
@@ -741,4 +745,60 @@ def fuse_merge_sk(tokens, H1, W1, H2, W2, nw, nb, ln_eps, fc, fcs0, fcs1, conv, 
     tab = _table([nw, nb, fc.weight, fc.bias, fcs0.weight, fcs0.bias, fcs1.weight, fcs1.bias, conv.weight.reshape(C, C), conv.bias,
                   bn.weight, bn.bias, bn.running_mean, bn.running_var], mats=(8,))
     _chk(lib.tcx_fuse_merge_sk_fwd(_ptr(t), tab, ln_eps, bn.eps, _ptr(out), B, H1, W1, H2, W2, C, d, _ptr(ws), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused training loss
+# ------------------------------------------------------------------------------------------------
+_LABEL_KIND = {torch.int64: 0, torch.float32: 1, torch.int32: 2, torch.uint8: 3}
+
+
+def _seg_loss_common(logits, labels, class_w):
+    require_cuda(logits)
+    require_cuda(labels)
+    if logits.dtype != torch.float32 or labels.dtype not in _LABEL_KIND:
+        raise TypeError("seg_loss: logits must be float32 and labels int64 / float32 / int32 / uint8 (got %s, %s)"
+                        % (logits.dtype, labels.dtype))
+    B, K = logits.shape[0], logits.shape[1]
+    HW = logits[0, 0].numel()
+    if labels.numel() != B * HW:
+        raise ValueError("predict %s & target %s shape do not match" % (tuple(logits.shape), tuple(labels.shape)))
+    cw = None
+    if class_w is not None:
+        cw = (ctypes.c_float * K)(*[float(v) for v in class_w])
+    return B, K, HW, cw
+
+
+def seg_loss_fwd(logits, labels, w_ce=0.4, w_dice=0.6, class_w=None, softmax=True):
+    """Returns (out, ws): out = device tensor [loss, ce, dice, bad_labels, class_wise_dice...]; ws feeds seg_loss_bwd."""
+    lib = load_library()
+    logits, labels = logits.contiguous(), labels.contiguous()
+    B, K, HW, cw = _seg_loss_common(logits, labels, class_w)
+    out = torch.empty(4 + K, device=logits.device, dtype=torch.float32)
+    ws = _ws(lib.tcx_seg_loss_workspace_bytes(B, K, HW), logits)
+    _chk(lib.tcx_seg_loss_fwd(_ptr(logits), labels.data_ptr(), _LABEL_KIND[labels.dtype], B, K, HW, int(softmax), w_ce, w_dice, cw,
+                              _ptr(out), _ptr(ws), _stream()))
+    return out, ws
+
+
+def seg_loss_bwd(logits, labels, ws, grad_out=None, w_ce=0.4, w_dice=0.6, class_w=None, softmax=True):
+    lib = load_library()
+    logits, labels = logits.contiguous(), labels.contiguous()
+    B, K, HW, cw = _seg_loss_common(logits, labels, class_w)
+    d = torch.empty_like(logits)
+    go = grad_out.contiguous().float() if grad_out is not None else None
+    _chk(lib.tcx_seg_loss_bwd(_ptr(logits), labels.data_ptr(), _LABEL_KIND[labels.dtype], B, K, HW, int(softmax), w_ce, w_dice, cw,
+                              _ptr(go), _ptr(d), _ptr(ws), _stream()))
+    return d
+
+
+def argmax_classes(logits):
+    """[B, K, H, W] fp32 logits -> [B, H, W] uint8 arg max over classes (reference utils.py:86)."""
+    require_cuda(logits)
+    lib = load_library()
+    logits = logits.contiguous()
+    B, K = logits.shape[:2]
+    out = torch.empty((B,) + tuple(logits.shape[2:]), device=logits.device, dtype=torch.uint8)
+    _chk(lib.tcx_argmax_classes_fwd(_ptr(logits), out.data_ptr(), B, K, out[0].numel(), _stream()))
     return out
