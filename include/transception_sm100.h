@@ -27,7 +27,7 @@ const char* tcx_version(void);
 const char* tcx_last_error(void);
 /* 1 when a usable sm_100 device is current, else 0 (with tcx_last_error set) */
 int tcx_device_ok(void);
-/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc","f16_pipeline","fork","pdl","mixtail"}; value 0/1; returns previous value */
+/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc","f16_pipeline","fork","pdl","mixtail","ea_tc"}; value 0/1; returns previous value */
 int tcx_set_flag(const char* name, int value);
 
 /* number of kernels this library has enqueued so far in this process (bench.py's gpu_launches) */

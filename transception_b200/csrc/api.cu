@@ -63,6 +63,7 @@ void tcx_prof_end(const char* name, cudaStream_t st, double work) {
 static int g_flag_gemm_tc = 1;
 static int g_flag_flash_tc = 1;
 static int g_flag_f16 = 1;
+static int g_flag_ea_tc = 1;     // efficient-attention context on the tensor core (packT + gemm_tc)
 static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
@@ -363,6 +364,16 @@ int run_ln16_1(const float* x, const float* w, const float* b, __half* y16, floa
   return run_ln16(1, xs, ws, bs, y16 ? y16s : nullptr, y32 ? y32s : nullptr, M, C, eps, st);
 }
 
+static inline int fuse_np(int N) { return (N + 63) / 64 * 64; }
+// floats carved by run_eff_attn16 from its workspace
+static size_t eff_attn16_carve_floats(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  int KS, Ks;
+  ea16_ctx_tc_splits(N, &KS, &Ks);
+  const size_t bcp = (size_t)B * KS * C * Ks;
+  return rnd(3 * bnc / 2 + 64) + 2 * rnd(bnc / 2 + 64) + rnd((size_t)B * C * C / 2 + 64) + rnd(ea16_workspace_floats(B, N, C)) +
+         rnd(ea16_ctx_tc_stats_floats(B, N, C) + 64) + 2 * rnd(bcp / 2 + 64) + rnd((size_t)B * KS * C * C + 64);
+}
 // efficient / channel attention with fp16 K/Q/V, context and attention output; y = residual + reproj(att) in fp32
 int run_eff_attn16(const __half* xn16, const void* const* p, const float* residual, float* y, int B, int N, int C,
                    int reinterpret, float* ws, cudaStream_t st, const LnOut& ln = LnOut()) {
@@ -393,7 +404,24 @@ int run_eff_attn16(const __half* xn16, const void* const* p, const float* residu
     AuxStreams* aux = aux_streams(st);
     if (aux) TCX_TRY(fork_streams(aux, st, 1));
     TCX_TRY(launch_ea16_qsoftmax(v, B, N, C, qsm, aux ? aux->s[0] : st));
-    TCX_TRY(launch_ea16_context(v, B, N, C, part, ctxT, st));
+    if (g_flag_ea_tc && !reinterpret && C <= 512) {
+      // context on the tensor core: column-softmax probabilities and values re-laid K-major and split-major
+      // ([B][KS][C][Ks]), partial[b][s][cv][ck] = sum_n Vt * Pt as one batched GEMM, then a fold over the K-splits
+      int KS, Ks;
+      ea16_ctx_tc_splits(N, &KS, &Ks);
+      float* stats = c.take(ea16_ctx_tc_stats_floats(B, N, C) + 64);
+      __half* Pt = H16(c.take((size_t)B * KS * C * Ks / 2 + 64));
+      __half* Vt = H16(c.take((size_t)B * KS * C * Ks / 2 + 64));
+      float* cpart = c.take((size_t)B * KS * C * C + 64);
+      TCX_TRY(launch_ea16_packT(v, B, N, C, stats, Pt, Vt, st));
+      GemmParams cg = gemm1(F(Vt), F(Pt), cpart, C, C, Ks);
+      cg.batch = B * KS; cg.strideA = (long long)C * Ks; cg.strideW = (long long)C * Ks; cg.strideC = (long long)C * C;
+      cg.ab16 = 1;
+      TCX_TRY(launch_gemm(cg, st));
+      TCX_TRY(launch_ea16_splitk_combine(cpart, ctxT, B, KS, C, st));
+    } else {
+      TCX_TRY(launch_ea16_context(v, B, N, C, part, ctxT, st));
+    }
     if (aux) TCX_TRY(join_stream(aux, 0, st));
   }
   {  // att[b] = qsm[b] (N x C) * ctx[b] (C x C): W = ctxT[b]
@@ -537,6 +565,7 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "f16_pipeline")) f = &g_flag_f16;
   else if (!strcmp(name, "fork")) f = &g_flag_fork;
   else if (!strcmp(name, "mixtail")) f = &g_flag_mixtail;
+  else if (!strcmp(name, "ea_tc")) f = &g_flag_ea_tc;
   else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
@@ -616,7 +645,9 @@ size_t tcx_eff_attn_workspace_bytes(int B, int N, int C) {
   const size_t bnc = (size_t)B * N * C;
   size_t part = ea_workspace_floats(B, N, C);
   if (ea16_workspace_floats(B, N, C) > part) part = ea16_workspace_floats(B, N, C);
-  return 4 * (rnd(3 * bnc) + rnd(bnc) + rnd(bnc) + rnd((size_t)B * C * C) + rnd(part) + rnd(bnc) + 1024);
+  size_t fp32_form = rnd(3 * bnc) + rnd(bnc) + rnd(bnc) + rnd((size_t)B * C * C) + rnd(part);
+  size_t f16_form = eff_attn16_carve_floats(B, N, C);
+  return 4 * ((fp32_form > f16_form ? fp32_form : f16_form) + rnd(bnc) + 1024);
 }
 
 int tcx_eff_attn_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C,
@@ -625,9 +656,7 @@ int tcx_eff_attn_fwd(const float* xn, const void* const* p, const float* residua
   if (eff_attn_prepared(p, N, C, reinterpret)) {
     // standalone entry: the caller's LayerNorm output is fp32 -> one conversion pass, then the fp16 form
     const size_t bnc0 = (size_t)B * N * C;
-    size_t part = ea_workspace_floats(B, N, C);
-    if (ea16_workspace_floats(B, N, C) > part) part = ea16_workspace_floats(B, N, C);
-    float* tail = reinterpret_cast<float*>(ws) + rnd(3 * bnc0) + 2 * rnd(bnc0) + rnd((size_t)B * C * C) + rnd(part);
+    float* tail = reinterpret_cast<float*>(ws) + eff_attn16_carve_floats(B, N, C);
     TCX_TRY(launch_f32_to_f16(xn, tail, (long long)bnc0, st));
     return run_eff_attn16(H16(tail), p, residual, y, B, N, C, reinterpret, reinterpret_cast<float*>(ws), st);
   }
@@ -1278,7 +1307,6 @@ int tcx_final_expand_head_fwd(const float* x, const float* w, const float* lnw, 
 }
 
 // ---- networks/Transception.py variant: fp16 pipeline only ----------------------------
-static inline int fuse_np(int N) { return (N + 63) / 64 * 64; }
 static inline int conv_out(int H, int k, int stride, int pad, int dil) { return (H + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
 
 // FuseEfficientAttention (Transception.py:49-87, head_count = 1) on fp16 LayerNorm output xn16 [B*N][C]:

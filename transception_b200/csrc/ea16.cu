@@ -250,6 +250,147 @@ __global__ void __launch_bounds__(256) ea16_qsoftmax_reint_kernel(const __half* 
   }
 }
 
+// ---- tensor-core context (token-major K/V): K-major operands for  ctxT[cv][ck] = sum_n Vt[cv][n] * Pt[ck][n] ------------
+constexpr int EC_SPLIT_TOK = 64;       // tokens per statistics block (8 rows per warp, all loads in flight together)
+
+// Partial column statistics of K over a token range: max and sum of exp(k - max) per channel.  grid (nsplit, B), 256
+// threads; a warp walks rows, lanes own half2 channel pairs (C <= 512).  Fixed-order combines: deterministic.
+__global__ void __launch_bounds__(256) ea16_colstats_kernel(const __half* __restrict__ k, long long sb, int ldt, int N, int C,
+                                                            float* __restrict__ pm, float* __restrict__ ps) {
+  __shared__ float red[8][512];
+  __shared__ float bm[512];
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, b = blockIdx.y, nsplit = gridDim.x;
+  const int r0 = split * EC_SPLIT_TOK, r1 = min(N, r0 + EC_SPLIT_TOK);
+  const __half* kb = k + (long long)b * sb;
+  const int npair = C >> 6;            // half2 pairs per lane
+  // this warp's 8 rows (r0 + warp + 8 i), kept in registers for both passes
+  __half2 rows[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int r = r0 + warp + 8 * i;
+    const __half2* row = reinterpret_cast<const __half2*>(kb + (long long)(r < r1 ? r : r0) * ldt);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (j < npair) rows[i][j] = r < r1 ? row[lane + 32 * j] : __float2half2_rn(-INFINITY);
+  }
+  float m[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) m[j][0] = m[j][1] = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (j < npair) {
+        const float2 f = __half22float2(rows[i][j]);
+        m[j][0] = fmaxf(m[j][0], f.x);
+        m[j][1] = fmaxf(m[j][1], f.y);
+      }
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (j < npair) { red[warp][2 * (lane + 32 * j)] = m[j][0]; red[warp][2 * (lane + 32 * j) + 1] = m[j][1]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float v = red[0][c];
+#pragma unroll
+    for (int w = 1; w < 8; w++) v = fmaxf(v, red[w][c]);
+    bm[c] = v;
+  }
+  __syncthreads();
+  float s[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) s[j][0] = s[j][1] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (j < npair) {
+        const float2 f = __half22float2(rows[i][j]);          // -inf rows (past the range) contribute exp(-inf) = 0
+        s[j][0] += __expf(f.x - bm[2 * (lane + 32 * j)]);
+        s[j][1] += __expf(f.y - bm[2 * (lane + 32 * j) + 1]);
+      }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if (j < npair) { red[warp][2 * (lane + 32 * j)] = s[j][0]; red[warp][2 * (lane + 32 * j) + 1] = s[j][1]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float v = red[0][c];
+#pragma unroll
+    for (int w = 1; w < 8; w++) v += red[w][c];
+    pm[((long long)b * nsplit + split) * C + c] = bm[c];
+    ps[((long long)b * nsplit + split) * C + c] = v;
+  }
+}
+
+// grid (ceil(N/64), B, C/64), 256 threads: fold the statistics partials of this channel group, then transpose a
+// 64-token x 64-channel tile of K (as softmax probabilities) and of V through shared memory:
+//   Pt[b][s][c][n'] = exp(k[n][c] - max_c) / sum_c,  Vt[b][s][c][n'] = v[n][c]  with n = s * Ks + n' (split-major, so a
+//   (image, K-split) pair is one batch entry of the context GEMM); columns n >= N are written as zeros.
+constexpr int EC_PITCH = 66;
+__global__ void __launch_bounds__(256) ea16_packT_kernel(const __half* __restrict__ k, const __half* __restrict__ v, long long sb, int ldt,
+                                                         int N, int C, int Ks, int KS, int nsplit, const float* __restrict__ pm,
+                                                         const float* __restrict__ ps, __half* __restrict__ Pt, __half* __restrict__ Vt) {
+  __shared__ float mx[64], inv[64];
+  __shared__ __align__(16) __half tile[64 * EC_PITCH];
+  pdl_trigger();
+  pdl_wait();
+  const int n0 = blockIdx.x * 64, b = blockIdx.y, c0 = blockIdx.z * 64;
+  if (threadIdx.x < 64) {
+    const int c = c0 + threadIdx.x;
+    float M = -INFINITY;
+    for (int sI = 0; sI < nsplit; sI++) M = fmaxf(M, pm[((long long)b * nsplit + sI) * C + c]);
+    float S = 0.f;
+    for (int sI = 0; sI < nsplit; sI++) S += ps[((long long)b * nsplit + sI) * C + c] * __expf(pm[((long long)b * nsplit + sI) * C + c] - M);
+    mx[threadIdx.x] = M;
+    inv[threadIdx.x] = 1.f / S;
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 3, j = threadIdx.x & 7;           // 32 rows x 8 channel vectors per pass
+#pragma unroll
+  for (int which = 0; which < 2; which++) {
+    const __half* src = (which ? v : k) + (long long)b * sb + c0 + j * 8;
+    const int ks = n0 / Ks;
+    __half* dst = (which ? Vt : Pt) + (((long long)b * KS + ks) * C + c0) * Ks + (n0 - ks * Ks);
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+      const int n = r + pass * 32;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      const bool live = n0 + n < N;
+      if (live) raw = *reinterpret_cast<const uint4*>(src + (long long)(n0 + n) * ldt);
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        float o = f[e];
+        if (!which) o = live ? __expf(f[e] - mx[j * 8 + e]) * inv[j * 8 + e] : 0.f;
+        tile[(j * 8 + e) * EC_PITCH + n] = __float2half_rn(o);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+      const int c = r + pass * 32;                                  // channel row of the tile; this thread writes 8 tokens
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + c * EC_PITCH + j * 8);
+      *reinterpret_cast<uint4*>(dst + (long long)c * Ks + j * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+  }
+}
+
+// ctxT16[b][i] = sum over the K-splits of the fp32 partial contexts (index order: deterministic)
+__global__ void __launch_bounds__(256) ea16_splitk_combine_kernel(const float* __restrict__ part, __half* __restrict__ ctxT, int KS, int CC) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (i >= CC) return;
+  float v = 0.f;
+  for (int s2 = 0; s2 < KS; s2++) v += part[((long long)b * KS + s2) * CC + i];
+  ctxT[(long long)b * CC + i] = __float2half_rn(v);
+}
+
 }  // namespace
 
 size_t ea16_workspace_floats(int B, int N, int C) {
@@ -298,4 +439,41 @@ int launch_ea16_qsoftmax(const Ea16View& v, int B, int N, int C, __half* dst, cu
   else if (LPT == 32 && NV == 2) tcx_launch_pdl(ea16_qsoftmax_kernel<32, 2>, dim3(grid), dim3(256), 0, st, v.q, v.ldt, total, C, dst);
   else { tcx_set_error("eff_attn16: unsupported channel count %d", C); return -1; }
   return tcx_check_launch("ea16_qsoftmax");
+}
+
+// ---- tensor-core context path: statistics -> transposed split-major pack; the C x C contraction itself is a batched
+// gemm_tc launch (one batch entry per (image, K-split)) and a small fold of the split partials ------------------------------
+int ea16_ctx_tc_nsplit(int N) { return cdiv(N, EC_SPLIT_TOK); }
+size_t ea16_ctx_tc_stats_floats(int B, int N, int C) { return 2 * (size_t)B * ea16_ctx_tc_nsplit(N) * C; }
+void ea16_ctx_tc_splits(int N, int* KS, int* Ks) {
+  const int tiles = cdiv(N, 64);
+  const int ks = tiles < 8 ? tiles : 8;
+  *KS = ks;
+  *Ks = cdiv(tiles, ks) * 64;
+}
+int launch_ea16_packT(const Ea16View& v, int B, int N, int C, float* stats, void* Pt, void* Vt, cudaStream_t st) {
+  TCX_REQUIRE(!v.reint, "ea16_packT: token-major K/V only");
+  TCX_REQUIRE(C % 64 == 0 && C <= 512, "ea16_packT: C %% 64 == 0, C <= 512 (got C=%d)", C);
+  TCX_REQUIRE(v.ldt % 8 == 0 && v.sb % 8 == 0, "ea16_packT: 16-byte row pitch needed");
+  if (B == 0 || N == 0) return 0;
+  int KS, Ks;
+  ea16_ctx_tc_splits(N, &KS, &Ks);
+  const int nsplit = ea16_ctx_tc_nsplit(N);
+  float* pm = stats;
+  float* ps = stats + (size_t)B * nsplit * C;
+  {
+    ProfScope prof("ea16_colstats", st, (double)B * N * C * 2);
+    tcx_launch_pdl(ea16_colstats_kernel, dim3(nsplit, B), dim3(256), 0, st, v.k, v.sb, v.ldt, N, C, pm, ps);
+    TCX_TRY(tcx_check_launch("ea16_colstats"));
+  }
+  ProfScope prof("ea16_packT", st, (double)B * C * (2.0 * N + 2.0 * KS * Ks) * 2);
+  tcx_launch_pdl(ea16_packT_kernel, dim3(KS * Ks / 64, B, C / 64), dim3(256), 0, st, v.k, v.v, v.sb, v.ldt, N, C, Ks, KS, nsplit,
+                 (const float*)pm, (const float*)ps, reinterpret_cast<__half*>(Pt), reinterpret_cast<__half*>(Vt));
+  return tcx_check_launch("ea16_packT");
+}
+int launch_ea16_splitk_combine(const float* part, void* ctxT, int B, int KS, int C, cudaStream_t st) {
+  if (B == 0) return 0;
+  ProfScope prof("ea16_splitk_combine", st, (double)B * C * C * (4.0 * KS + 2.0));
+  tcx_launch_pdl(ea16_splitk_combine_kernel, dim3(cdiv(C * C, 256), B), dim3(256), 0, st, part, reinterpret_cast<__half*>(ctxT), KS, C * C);
+  return tcx_check_launch("ea16_splitk_combine");
 }

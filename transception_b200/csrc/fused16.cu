@@ -40,19 +40,7 @@ __device__ __forceinline__ float seg_sum(float v) {
 // ------------------------------------------------------------------------------------------------------------------
 // dw3x3 + skip + LayerNorm (+GELU)
 // ------------------------------------------------------------------------------------------------------------------
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16
-// output quantum): one MUFU.RCP + one MUFU.EX2 + a 5-term Horner chain, no branches / selects.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * __expf(-z * z);            // 1 - erf(z), z >= 0
-  const float h = 0.5f * x;
-  return x >= 0.f ? fmaf(-h, e, x) : h * e;          // x>=0: 0.5x(2-e) ; x<0: 0.5x(1-(1-e)) = 0.5 x e
-}
+// GELU: tcx_gelu_fast (fused16.cuh)
 
 // channel c of a token row -> position inside the per-tap smem vectors: lanes read contiguous 16-byte pieces
 template <int LPT, int VEC>
@@ -218,7 +206,7 @@ __global__ void __launch_bounds__(256) dwln_kernel(const DwLnArgs a) {
           }
           if (a.gelu) {
 #pragma unroll
-            for (int j = 0; j < VEC; j++) o[j] = gelu_fast(o[j]);
+            for (int j = 0; j < VEC; j++) o[j] = tcx_gelu_fast(o[j]);
           }
           __half* yp = g.y + off0 + i * LPT * VEC;
           if (VEC == 8) {

@@ -57,18 +57,6 @@ __device__ __forceinline__ float mt_warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// erf-GELU, Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), see fused16.cu
-__device__ __forceinline__ float mt_gelu(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * __expf(-z * z);
-  const float hx = 0.5f * x;
-  return x >= 0.f ? fmaf(-hx, e, x) : hx * e;
-}
 // channel c -> position inside the per-tap smem vectors (lanes read contiguous 16-byte pieces), see fused16.cu::wperm
 __device__ __forceinline__ int mt_wperm(int c) {
   const int blk = c >> 8, r = c & 255;
@@ -258,10 +246,10 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mixtail_kernel(const __grid_con
           for (int q = 0; q < 2; q++) {
             const float4 w4 = *reinterpret_cast<const float4*>(bl + C4 + iv * 256 + q * 128);
             const float4 b4 = *reinterpret_cast<const float4*>(bl + 2 * C4 + iv * 256 + q * 128);
-            o[q * 4 + 0] = mt_gelu(fmaf((acc[iv][q * 4 + 0] - mean) * rstd, w4.x, b4.x));
-            o[q * 4 + 1] = mt_gelu(fmaf((acc[iv][q * 4 + 1] - mean) * rstd, w4.y, b4.y));
-            o[q * 4 + 2] = mt_gelu(fmaf((acc[iv][q * 4 + 2] - mean) * rstd, w4.z, b4.z));
-            o[q * 4 + 3] = mt_gelu(fmaf((acc[iv][q * 4 + 3] - mean) * rstd, w4.w, b4.w));
+            o[q * 4 + 0] = tcx_gelu_fast(fmaf((acc[iv][q * 4 + 0] - mean) * rstd, w4.x, b4.x));
+            o[q * 4 + 1] = tcx_gelu_fast(fmaf((acc[iv][q * 4 + 1] - mean) * rstd, w4.y, b4.y));
+            o[q * 4 + 2] = tcx_gelu_fast(fmaf((acc[iv][q * 4 + 2] - mean) * rstd, w4.z, b4.z));
+            o[q * 4 + 3] = tcx_gelu_fast(fmaf((acc[iv][q * 4 + 3] - mean) * rstd, w4.w, b4.w));
           }
           const int c0 = iv * 256 + lane * 8;                 // first channel of this lane's vector
           const int kb = c0 >> 6, chunk = (c0 & 63) >> 3;
