@@ -11,6 +11,6 @@ timeout 200 python tools/modbench.py > gpurun_out/modbench.txt 2>&1
 timeout 200 python tools/microbench.py > gpurun_out/microbench.txt 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
    --log-file gpurun_out/launches.csv python tools/profile_forward.py > gpurun_out/ncu_fwd.log 2>&1
-bash tools/gpu_ncu.sh gemm_tc:0:2 gemm_tc:40:2 dwln_kernel:0:1 mb_fused16:0:1 ea16_ctx_partial:0:1 > gpurun_out/ncu_kernels.log 2>&1
+bash tools/gpu_ncu.sh gemm_tc:0:2 gemm_tc:40:2 dwln_kernel:0:1 mb_fused16:0:1 ea16_packT:0:1 > gpurun_out/ncu_kernels.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:flash_tc -s 1 -c 1 -o gpurun_out/flash16_full -f python tools/ncu_one.py flash16 > gpurun_out/ncu_flash16.log 2>&1
 grep -E "passed|failed|rc=" gpurun_out/pytest.log | tail -3; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench.err
