@@ -244,6 +244,33 @@ int tcx_seg_loss_bwd(const float* logits, const void* labels, int label_kind, in
  * -> uint8 label map [B][HW] (softmax is monotone; first index wins ties). */
 int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, int K, long long HW, void* stream);
 
+/* ---- training row: backward entries.  Gradients are fp32; the GEMM-shaped parts run on the
+ * tcgen05 GEMM with TF32 operands; every reduction over tokens is two-pass in a fixed order (bit-reproducible).  These are
+ * what the autograd nodes of the drop-in modules (transception_b200/autograd.py) call where the reference relies on ATen's
+ * autograd formulas for nn.LayerNorm / nn.Linear / MixFFN_skip (MSTr.py:58-61). ---- */
+
+/* nn.LayerNorm backward: x [M][C] (the forward input), dy [M][C] -> dx [M][C], dw [C], db [C] */
+size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C);
+int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, float eps, float* dx, float* dw, float* db, long long M, int C,
+                      void* ws, void* stream);
+
+/* nn.Linear backward for y = x w^T + b: x [M][K] (fp32, or fp16 when x_f16), w [N][K], dy [M][N] ->
+ * dx [M][K] = dy w, dw [N][K] = dy^T x, db [N] = column sums of dy; any of dx / dw / db may be NULL (skipped). */
+size_t tcx_linear_bwd_workspace_bytes(long long M, int N, int K);
+int tcx_linear_bwd(const void* x, int x_f16, const float* w, const float* dy, float* dx, float* dw, float* db, long long M, int N,
+                   int K, void* ws, void* stream);
+
+/* MixFFN_skip training forward: the arithmetic of tcx_mixffn_skip_fwd (fp16 pipeline only: fc1 / fc2 must be prepared),
+ * keeping in `saved` (tcx_mixffn_skip_saved_bytes, opaque) what backward needs: fp16 xn, fc1 output, GELU output and the
+ * fp32 LayerNorm input.  tcx_mixffn_skip_bwd: dy [B*N][C] = dL/dy -> dxn [B*N][C] (NULL: skipped) and the eight parameter
+ * gradients dp = {d fc1_w, d fc1_b, d dw_w, d dw_b, d ln_w, d ln_b, d fc2_w, d fc2_b} (device pointers, shapes of p). */
+size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4);
+int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
+                              int W, int C, int C4, void* saved, void* stream);
+size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4);
+int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, float* dxn, void* const* dp, int B,
+                        int H, int W, int C, int C4, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,70 @@
+"""Autograd nodes of the training row: forward and backward both run the library's kernels.
+
+The reference gets its gradients from ATen's autograd formulas for ``nn.LayerNorm`` / ``nn.Linear`` and the op sequence
+of ``MixFFN_skip.forward`` (MSTr.py:58-61); these nodes are what the drop-in modules call instead when autograd is
+recording.  Built so far: LayerNorm, Linear, MixFFN_skip — the rest of the model still raises in train mode
+(DESIGN.md §6).  There is no PyTorch fallback inside a node.
+"""
+import torch
+
+from . import ops
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        ctx.save_for_backward(x, w)
+        ctx.eps = eps
+        return ops.layernorm(x, w, b, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(x, w, dy, ctx.eps)
+        return dx, dw, db, None
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return ops.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ops.linear_bwd(x, w, dy, need_dx=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[1],
+                                    need_db=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw, db
+
+
+class MixFFNSkipFn(torch.autograd.Function):
+    """y = fc2(GELU(LN(dw3x3(fc1 x) + fc1 x))) (MSTr.py:58-61) on x [B, N, C]."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b):
+        y, saved = ops.mixffn_skip_train(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b)
+        ctx.save_for_backward(saved, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)
+        ctx.geom = (x.shape[0], H, W, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b = ctx.saved_tensors
+        B, H, W, eps = ctx.geom
+        dx, g = ops.mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
+                                    need_dx=ctx.needs_input_grad[0])
+        return (dx, None, None, None) + tuple(g)
+
+
+def layernorm(x, w, b, eps):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+def linear(x, w, b=None):
+    return LinearFn.apply(x, w, b)
+
+
+def mixffn_skip(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b):
+    return MixFFNSkipFn.apply(x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)

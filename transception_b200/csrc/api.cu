@@ -11,6 +11,8 @@
 #include "ea16.cuh"
 #include "fuse.cuh"
 #include "loss.cuh"
+#include "bwd.cuh"
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -299,6 +301,7 @@ struct Mix16 {
   const float* res;  long long res_bs;
   float* y;          long long y_bs;
   LnOut ln;          long long ln_bs;     // optional fp16 LayerNorm (64-column groups) of y, fused in fc2's epilogue
+  float* u_save;                          // training: fp32 copy of the LayerNorm input dw3x3(h)+b+h, kept for backward
 };
 // all matrices of a Mix-FFN parameter block {fc1_w,fc1_b,dw_w,dw_b,ln_w,ln_b,fc2_w,fc2_b} prepared?
 inline bool mix16_fill(const void* const* p, Mix16& m) {
@@ -322,7 +325,7 @@ int run_mixffn16(int G, const Mix16* m, float eps, int B, int H, int W, int C, i
     }
     TCX_TRY(launch_gemm(g, st));
   }
-  if (g_flag_mixtail && !m[0].ln.out && mixtail_eligible(G, C4, (long long)B * N)) {
+  if (g_flag_mixtail && !m[0].ln.out && !m[0].u_save && mixtail_eligible(G, C4, (long long)B * N)) {
     // dw3x3 + skip + LN + GELU feed fc2's A tile through shared memory: one kernel, no [M, C4] round trip
     MixTailDesc d[TCX_MAX_GROUPS];
     for (int i = 0; i < G; i++)
@@ -333,7 +336,7 @@ int run_mixffn16(int G, const Mix16* m, float eps, int B, int H, int W, int C, i
     DwLnArgs a{};
     a.B = B; a.H = H; a.W = W; a.C = C4; a.eps = eps; a.gelu = 1;
     for (int i = 0; i < G; i++)
-      a.g[i] = DwLnGroup{hbuf + i * per, m[i].dww, m[i].dwb, m[i].lnw, m[i].lnb, nullptr, abuf + i * per};
+      a.g[i] = DwLnGroup{hbuf + i * per, m[i].dww, m[i].dwb, m[i].lnw, m[i].lnb, m[i].u_save, abuf + i * per};
     TCX_TRY(launch_dwln(a, G, true, st));
   }
   {
@@ -1532,6 +1535,146 @@ int tcx_seg_loss_bwd(const float* logits, const void* labels, int label_kind, in
 int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, int K, long long HW, void* stream) {
   TCX_REQUIRE(logits && labels, "argmax_classes: null pointer");
   return launch_argmax_classes(logits, labels, B, K, HW, S(stream));
+}
+
+}  // extern "C"
+
+// ---- training row: backward entries ----------------------------------------------------------
+namespace {
+
+size_t linear_bwd_ws_floats(long long M, int N, int K) {
+  int S, Ms;
+  bwd_wgrad_splits(M, N, K, &S, &Ms);
+  const size_t npad = (size_t)(N + 31) / 32 * 32;
+  return rnd(npad * K) + rnd((size_t)S * Ms * N) + rnd((size_t)S * Ms * K) + rnd((size_t)S * N * K) +
+         rnd((size_t)bwd_red_blocks(M) * N) + 64;
+}
+
+// nn.Linear backward: y = x w^T + b with x [M][K] (fp32, or fp16 when x16), w [N][K], dy [M][N]:
+//   dx [M][K] = dy w        (tcgen05 GEMM against the transposed weight)
+//   dw [N][K] = dy^T x      (token-split batched tcgen05 GEMM on K-major packs, fold over the splits)
+//   db [N]    = column sums of dy
+// any of dx / dw / db may be null
+int run_linear_bwd(const void* x, int x16, const float* w, const float* dy, float* dx, float* dw, float* db, long long M, int N,
+                   int K, float* ws, cudaStream_t st) {
+  TCX_REQUIRE(M < (1ll << 31) && N % 4 == 0 && K % 4 == 0, "linear_bwd: N, K must be multiples of 4 (M=%lld N=%d K=%d)", M, N, K);
+  Carver c(ws);
+  if (dx && M > 0) {
+    const int npad = (N + 31) / 32 * 32;
+    float* wT = c.take((size_t)npad * K);
+    TCX_TRY(launch_bwd_packT_f32(w, N, K, K, 1, npad, wT, st));          // wT [K][npad]
+    GemmParams g = gemm1(dy, wT, dx, (int)M, K, N);
+    g.ldw = npad;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  if (dw) {
+    if (M == 0) {
+      TCX_REQUIRE(cudaMemsetAsync(dw, 0, sizeof(float) * N * K, st) == cudaSuccess, "linear_bwd: memset failed");
+    } else {
+      int S, Ms;
+      bwd_wgrad_splits(M, N, K, &S, &Ms);
+      float* dyT = c.take((size_t)S * Ms * N);
+      float* xT = c.take((size_t)S * Ms * K);
+      float* part = c.take((size_t)S * N * K);
+      TCX_TRY(launch_bwd_packT_f32(dy, M, N, N, S, Ms, dyT, st));
+      if (x16) TCX_TRY(launch_bwd_packT_f16(reinterpret_cast<const __half*>(x), M, K, K, S, Ms, xT, st));
+      else TCX_TRY(launch_bwd_packT_f32(F(x), M, K, K, S, Ms, xT, st));
+      GemmParams g = gemm1(dyT, xT, S == 1 ? dw : part, N, K, Ms);
+      g.batch = S; g.strideA = (long long)N * Ms; g.strideW = (long long)K * Ms; g.strideC = (long long)N * K;
+      TCX_TRY(launch_gemm(g, st));
+      if (S > 1) TCX_TRY(launch_bwd_fold(part, S, (long long)N * K, dw, st));
+    }
+  }
+  if (db) {
+    float* part = c.take((size_t)bwd_red_blocks(M) * N);
+    TCX_TRY(launch_bwd_colsum(dy, M, N, N, part, db, st));
+  }
+  return 0;
+}
+
+struct MixSaved {
+  __half* h16; __half* a16; __half* xn16; float* u;
+  size_t floats;
+};
+MixSaved mix_saved(void* base, long long M, int C, int C4) {
+  Carver c(base);
+  MixSaved s;
+  s.h16 = H16(c.take((size_t)M * C4 / 2 + 64));
+  s.a16 = H16(c.take((size_t)M * C4 / 2 + 64));
+  s.xn16 = H16(c.take((size_t)M * C / 2 + 64));
+  s.u = c.take((size_t)M * C4);
+  s.floats = c.off + 64;
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C) { return 4 * (rnd(2 * (size_t)M) + rnd(2 * (size_t)bwd_red_blocks(M) * C) + 64); }
+int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, float eps, float* dx, float* dw, float* db, long long M, int C,
+                      void* ws, void* stream) {
+  TCX_REQUIRE(x && w && dy && dx && dw && db && ws, "layernorm_bwd: null pointer");
+  Carver c(ws);
+  float* stats = c.take(2 * (size_t)M);
+  float* part = c.take(2 * (size_t)bwd_red_blocks(M) * C);
+  return launch_bwd_ln(x, dy, w, nullptr, eps, 0, dx, dw, db, M, C, stats, part, S(stream));
+}
+
+size_t tcx_linear_bwd_workspace_bytes(long long M, int N, int K) { return 4 * linear_bwd_ws_floats(M, N, K); }
+int tcx_linear_bwd(const void* x, int x_f16, const float* w, const float* dy, float* dx, float* dw, float* db, long long M, int N,
+                   int K, void* ws, void* stream) {
+  TCX_REQUIRE(x && w && dy && ws, "linear_bwd: null pointer");
+  return run_linear_bwd(x, x_f16, w, dy, dx, dw, db, M, N, K, reinterpret_cast<float*>(ws), S(stream));
+}
+
+size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4) { return 4 * mix_saved(nullptr, (long long)B * N, C, C4).floats; }
+int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
+                              int W, int C, int C4, void* saved, void* stream) {
+  TCX_REQUIRE(xn && p && y && saved, "mixffn_skip_train_fwd: null pointer");
+  Mix16 m{};
+  TCX_REQUIRE(mix16_fill(p, m), "mixffn_skip_train_fwd: fc1 / fc2 weights are not prepared (tcx_prepare_weight_f16)");
+  const long long M = (long long)B * H * W;
+  MixSaved s = mix_saved(saved, M, C, C4);
+  TCX_TRY(launch_f32_to_f16(xn, s.xn16, M * C, S(stream)));
+  m.xn = s.xn16; m.res = residual; m.y = y; m.u_save = s.u;
+  return run_mixffn16(1, &m, ln_eps, B, H, W, C, C4, s.h16, s.a16, S(stream));
+}
+
+size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4) {
+  const long long M = (long long)B * N;
+  const size_t lin = std::max(linear_bwd_ws_floats(M, C, C4), linear_bwd_ws_floats(M, C4, C));
+  return 4 * (2 * rnd((size_t)M * C4) + rnd(2 * (size_t)M) + rnd(9 * (size_t)C4) + rnd(10 * (size_t)bwd_red_blocks(M) * C4) + lin + 64);
+}
+int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, float* dxn, void* const* dp, int B,
+                        int H, int W, int C, int C4, void* ws, void* stream) {
+  TCX_REQUIRE(dy && p && saved && dp && ws, "mixffn_skip_bwd: null pointer");
+  for (int i = 0; i < 8; i++) TCX_REQUIRE(dp[i] != nullptr, "mixffn_skip_bwd: gradient slot %d is null", i);
+  cudaStream_t st = S(stream);
+  const long long M = (long long)B * H * W;
+  const MixSaved s = mix_saved(const_cast<void*>(saved), M, C, C4);
+  Carver c(ws);
+  float* da = c.take((size_t)M * C4);      // dL/d a (fc2 input), later dL/d h
+  float* du = c.take((size_t)M * C4);      // dL/d u (LayerNorm input)
+  float* stats = c.take(2 * (size_t)M);
+  float* wflip = c.take(9 * (size_t)C4);
+  float* part = c.take(10 * (size_t)bwd_red_blocks(M) * C4);
+  float* lin = c.take(0);
+  auto G = [&](int i) { return reinterpret_cast<float*>(dp[i]); };
+  // fc2: a16 [M][C4] -> y [M][C]
+  TCX_TRY(run_linear_bwd(s.a16, 1, F(p[6]), dy, da, G(6), G(7), M, C, C4, lin, st));
+  // GELU(LayerNorm(u))
+  TCX_TRY(launch_bwd_ln(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, G(4), G(5), M, C4, stats, part, st));
+  // u = dw3x3(h) + b + h
+  float* dh = da;
+  TCX_TRY(launch_bwd_flip9(F(p[2]), wflip, C4, st));
+  {
+    DwGroup g{du, wflip, nullptr, dh};
+    TCX_TRY(launch_dwconv3x3(&g, 1, B, H, W, C4, 1, DW_ADD_INPUT, BnParams{}, st));
+  }
+  TCX_TRY(launch_bwd_dwconv_wgrad(du, s.h16, B, H, W, C4, G(2), G(3), part, st));
+  // fc1: xn16 [M][C] -> h [M][C4]
+  return run_linear_bwd(s.xn16, 1, F(p[0]), dh, dxn, G(0), G(1), M, C4, C, lin, st);
 }
 
 }  // extern "C"

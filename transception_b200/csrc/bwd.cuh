@@ -1,0 +1,40 @@
+// Backward building blocks of the training row (kernels in bwd.cu).
+// Gradients are fp32 in HBM (the per-pixel loss gradient of a bs16 224x224 step is ~1e-6: below fp16's normal range);
+// the GEMM-shaped parts (dgrad, wgrad) run on the tcgen05 GEMM of gemm_tc.cu with TF32 operands.  Every reduction
+// over tokens is two-pass (block partials in a fixed order, then a fold in index order): bit-reproducible.
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+// rows handled by one block of the token reductions; the partial buffers below are sized with it
+int bwd_red_blocks(long long M);
+
+// out[c] = sum_m x[m][c]   (bias gradients).  part: bwd_red_blocks(M) * C floats
+int launch_bwd_colsum(const float* x, long long M, int C, int ld, float* part, float* out, cudaStream_t st);
+
+// LayerNorm backward on rows u [M][C] (the LayerNorm input) with upstream gradient dz [M][C]:
+//   gelu = 0: y = LN(u),        dz = dL/dy
+//   gelu = 1: y = GELU(LN(u)),  dz = dL/dy (the GELU derivative is applied to the recomputed LN output)
+// du [M][C] = dL/du, dgamma / dbeta [C].  stats: 2*M floats (mean, rstd written by the row pass, read by the column
+// pass); part: 2 * bwd_red_blocks(M) * C floats.  du may not alias dz.
+int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
+                  float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st);
+
+// depthwise 3x3 (stride 1, pad 1, DWConv MSTr.py:26-31) weight / bias gradient:
+//   dw[c][ky][kx] = sum_p du[p][c] * h[p + (ky-1, kx-1)][c],  db[c] = sum_p du[p][c];   h is fp16 [B,H,W,C]
+// part: 10 * bwd_red_blocks(B*H*W) * C floats
+int launch_bwd_dwconv_wgrad(const float* du, const __half* h, int B, int H, int W, int C, float* dw, float* db, float* part,
+                            cudaStream_t st);
+// wflip[c][t] = w[c][8 - t]: the input gradient of the depthwise conv is the same conv with the taps mirrored
+int launch_bwd_flip9(const float* w, float* wflip, int C, cudaStream_t st);
+
+// K-major re-layout for the weight-gradient GEMM: src [M][C] (row pitch ld, fp32 or fp16) ->
+// dst [S][C][Ms] fp32 with token m of split s = src row s*Ms + m (zero beyond M).  Also a plain transpose (S = 1, Ms = M).
+int launch_bwd_packT_f32(const float* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st);
+int launch_bwd_packT_f16(const __half* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st);
+
+// out[i] = sum_s part[s][i], i < n (split-K fold of the weight-gradient partials)
+int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st);
+
+// split plan of the weight-gradient GEMM dW[Nout][Kin] = dY^T X over M tokens
+void bwd_wgrad_splits(long long M, int Nout, int Kin, int* S, int* Ms);

@@ -100,6 +100,10 @@ class MixFFN_skip(nn.Module):
                 self.norm1.weight, self.norm1.bias, self.norm1.eps, self.fc2.weight, self.fc2.bias)
 
     def forward(self, x, H, W):
+        if torch.is_grad_enabled() and (x.requires_grad or self.fc1.weight.requires_grad):
+            # training row: forward + backward on the library's kernels (transception_b200/autograd.py)
+            from . import autograd as tcx_autograd
+            return tcx_autograd.mixffn_skip(x, H, W, *self.args())
         return ops.mixffn_skip(x, H, W, *self.args())
 
 

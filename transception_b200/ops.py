@@ -89,6 +89,14 @@ _PROTOS = {
     "tcx_patch_expand_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_final_expand_head_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_final_expand_head_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_layernorm_bwd_workspace_bytes": (_sz, [_ll, _i]),
+    "tcx_layernorm_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
+    "tcx_linear_bwd_workspace_bytes": (_sz, [_ll, _i, _i]),
+    "tcx_linear_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_mixffn_skip_bwd": (_i, [_vp, _pp, _f, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_PROTOS)
 
@@ -802,3 +810,64 @@ def argmax_classes(logits):
     out = torch.empty((B,) + tuple(logits.shape[2:]), device=logits.device, dtype=torch.uint8)
     _chk(lib.tcx_argmax_classes_fwd(_ptr(logits), out.data_ptr(), B, K, out[0].numel(), _stream()))
     return out
+
+
+# ---- training row: backward entries (include/transception_sm100.h, "training row") ------------------------------
+def layernorm_bwd(x, w, dy, eps):
+    """(dx, dw, db) of nn.LayerNorm over the last dim."""
+    require_cuda(x)
+    lib = load_library()
+    x, dy = x.contiguous(), dy.contiguous()
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+    ws = _ws(lib.tcx_layernorm_bwd_workspace_bytes(M, C), x)
+    _chk(lib.tcx_layernorm_bwd(_ptr(x), _ptr(_d(w)), _ptr(dy), eps, _ptr(dx), _ptr(dw), _ptr(db), M, C, _ptr(ws), _stream()))
+    return dx, dw, db
+
+
+def linear_bwd(x, w, dy, need_dx=True, need_dw=True, need_db=True):
+    """(dx, dw, db) of y = x w^T + b; x fp32 or fp16 [.., K], w [N, K], dy [.., N]."""
+    require_cuda(dy)
+    lib = load_library()
+    x, dy = x.contiguous(), dy.contiguous()
+    N, K = w.shape
+    M = dy.numel() // N
+    dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if need_dx else None
+    dw = torch.empty_like(w) if need_dw else None
+    db = torch.empty(N, dtype=torch.float32, device=x.device) if need_db else None
+    ws = _ws(lib.tcx_linear_bwd_workspace_bytes(M, N, K), dy)
+    x16 = x.dtype == torch.float16
+    _chk(lib.tcx_linear_bwd(_ptr16(x) if x16 else _ptr(x), int(x16), _ptr(_d(w)), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), M, N, K,
+                            _ptr(ws), _stream()))
+    return dx, dw, db
+
+
+def mixffn_skip_train(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):
+    """Training forward of MixFFN_skip: (y, saved) with ``saved`` the opaque buffer mixffn_skip_bwd consumes."""
+    require_cuda(xn)
+    lib = load_library()
+    xn = xn.contiguous()
+    B, N, C = xn.shape
+    C4 = fc1w.shape[0]
+    y = torch.empty_like(xn)
+    saved = _ws(lib.tcx_mixffn_skip_saved_bytes(B, N, C, C4), xn)
+    tab = _table([fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b], mats=(0, 6))
+    _chk(lib.tcx_mixffn_skip_train_fwd(_ptr(xn), tab, eps, _ptr(residual), _ptr(y), B, H, W, C, C4, _ptr(saved), _stream()))
+    return y, saved
+
+
+def mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, need_dx=True):
+    """(dxn, [8 parameter gradients in slot order]) of MixFFN_skip."""
+    require_cuda(dy)
+    lib = load_library()
+    dy = dy.contiguous()
+    C4, C = fc1w.shape
+    params = [fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b]
+    grads = [torch.empty_like(p) for p in params]
+    dxn = torch.empty_like(dy) if need_dx else None
+    tab = _table(params)
+    gtab = (ctypes.c_void_p * 8)(*[_ptr(g) for g in grads])
+    ws = _ws(lib.tcx_mixffn_skip_bwd_workspace_bytes(B, H * W, C, C4), dy)
+    _chk(lib.tcx_mixffn_skip_bwd(_ptr(dy), tab, eps, _ptr(saved), _ptr(dxn), gtab, B, H, W, C, C4, _ptr(ws), _stream()))
+    return dxn, grads
