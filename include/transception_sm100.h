@@ -271,6 +271,17 @@ size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4);
 int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, float* dxn, void* const* dp, int B,
                         int H, int W, int C, int C4, void* ws, void* stream);
 
+/* EfficientAttention (MSTr.py:106-143) training forward (arithmetic of tcx_eff_attn_fwd with reinterpret = 0; fp16 pipeline
+ * only) and backward.  `saved` keeps the fp16 LayerNorm output, K | Q | V, the channel-softmax queries, the context and
+ * the attention output; the token softmax of the keys is recomputed in fp32 by backward.
+ * dy [B*N][C] -> dxn [B*N][C] (NULL: skipped), dp = gradients of {k_w,k_b,q_w,q_b,v_w,v_b,reproj_w,reproj_b}. */
+size_t tcx_eff_attn_saved_bytes(int B, int N, int C);
+int tcx_eff_attn_train_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C, void* saved,
+                           void* stream);
+size_t tcx_eff_attn_bwd_workspace_bytes(int B, int N, int C);
+int tcx_eff_attn_bwd(const float* dy, const void* const* p, const void* saved, float* dxn, void* const* dp, int B, int N, int C,
+                     void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

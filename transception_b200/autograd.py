@@ -58,6 +58,26 @@ class MixFFNSkipFn(torch.autograd.Function):
         return (dx, None, None, None) + tuple(g)
 
 
+class EffAttnFn(torch.autograd.Function):
+    """EfficientAttention.forward (MSTr.py:106-143) on tokens x [B, N, C] (the NCHW round trip of the caller is a view)."""
+
+    @staticmethod
+    def forward(ctx, x, kw, kb, qw, qb, vw, vb, rw, rb):
+        y, saved = ops.eff_attn_train(x, kw, kb, qw, qb, vw, vb, rw, rb)
+        ctx.save_for_backward(saved, kw, kb, qw, qb, vw, vb, rw, rb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved, *params = ctx.saved_tensors
+        dx, g = ops.eff_attn_bwd(dy, saved, *params, need_dx=ctx.needs_input_grad[0])
+        return (dx,) + tuple(g)
+
+
+def eff_attn(x, kw, kb, qw, qb, vw, vb, rw, rb):
+    return EffAttnFn.apply(x, kw, kb, qw, qb, vw, vb, rw, rb)
+
+
 def layernorm(x, w, b, eps):
     return LayerNormFn.apply(x, w, b, eps)
 

@@ -1628,6 +1628,116 @@ int tcx_linear_bwd(const void* x, int x_f16, const float* w, const float* dy, fl
   return run_linear_bwd(x, x_f16, w, dy, dx, dw, db, M, N, K, reinterpret_cast<float*>(ws), S(stream));
 }
 
+// ---- EfficientAttention (MSTr.py:106-143) training forward / backward ----
+size_t tcx_eff_attn_saved_bytes(int B, int N, int C) {
+  return 4 * (eff_attn16_carve_floats(B, N, C) + rnd((size_t)B * N * C / 2 + 64) + 64);
+}
+int tcx_eff_attn_train_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int N, int C, void* saved,
+                           void* stream) {
+  TCX_REQUIRE(xn && p && y && saved, "eff_attn_train_fwd: null pointer");
+  TCX_REQUIRE(eff_attn_prepared(p, N, C, 0), "eff_attn_train_fwd: needs prepared fp16 weights, N >= 32 and C %% 64 == 0 (N=%d C=%d)", N, C);
+  float* base = reinterpret_cast<float*>(saved);
+  __half* xn16 = H16(base + eff_attn16_carve_floats(B, N, C));
+  TCX_TRY(launch_f32_to_f16(xn, xn16, (long long)B * N * C, S(stream)));
+  return run_eff_attn16(xn16, p, residual, y, B, N, C, 0, base, S(stream));
+}
+
+static size_t eff_attn_bwd_ws_floats(int B, int N, int C) {
+  const size_t M = (size_t)B * N, bnc = M * C, bcc = (size_t)B * C * C;
+  int S, Ms;
+  bwd_wgrad_splits(N, C, C, &S, &Ms);
+  const size_t pack = (size_t)B * S * C * Ms, ch = (size_t)B * ea_bwd_chunks(N) * C;
+  const size_t lin = std::max(linear_bwd_ws_floats(M, C, C), linear_bwd_ws_floats(M, 3 * C, C));
+  return 6 * rnd(bnc) + rnd(3 * bnc) + 3 * rnd(bcc) + 2 * rnd(pack) + rnd((size_t)B * S * C * C) + 3 * rnd(ch) +
+         2 * rnd(3 * (size_t)C * C) + rnd(3 * (size_t)C) + lin + 64;
+}
+size_t tcx_eff_attn_bwd_workspace_bytes(int B, int N, int C) { return 4 * eff_attn_bwd_ws_floats(B, N, C); }
+
+int tcx_eff_attn_bwd(const float* dy, const void* const* p, const void* saved, float* dxn, void* const* dp, int B, int N, int C,
+                     void* ws, void* stream) {
+  TCX_REQUIRE(dy && p && saved && dp && ws, "eff_attn_bwd: null pointer");
+  for (int i = 0; i < 8; i++) TCX_REQUIRE(dp[i] != nullptr, "eff_attn_bwd: gradient slot %d is null", i);
+  cudaStream_t st = S(stream);
+  const long long M = (long long)B * N;
+  const size_t bnc = (size_t)M * C, bcc = (size_t)B * C * C;
+  // the forward's buffers (run_eff_attn16 carve order) + the fp16 LayerNorm output behind them
+  Carver sv(const_cast<void*>(saved));
+  const __half* kqv = H16(sv.take(3 * bnc / 2 + 64));
+  const __half* qsm = H16(sv.take(bnc / 2 + 64));
+  const __half* att = H16(sv.take(bnc / 2 + 64));
+  const __half* ctxT = H16(sv.take(bcc / 2 + 64));
+  const __half* xn16 = H16(reinterpret_cast<float*>(const_cast<void*>(saved)) + eff_attn16_carve_floats(B, N, C));
+  int SP, Ms;
+  bwd_wgrad_splits(N, C, C, &SP, &Ms);
+  const size_t ch = (size_t)B * ea_bwd_chunks(N) * C;
+  Carver c(ws);
+  float* datt = c.take(bnc);
+  float* dQs = c.take(bnc);
+  float* P32 = c.take(bnc);
+  float* V32 = c.take(bnc);
+  float* dP = c.take(bnc);
+  float* spare = c.take(bnc);
+  (void)spare;
+  float* dkqv = c.take(3 * bnc);
+  float* ctx32 = c.take(bcc);
+  float* dctx = c.take(bcc);
+  float* dctxT = c.take(bcc);
+  float* QsT = c.take((size_t)B * SP * C * Ms);
+  float* dattT = c.take((size_t)B * SP * C * Ms);
+  float* part = c.take((size_t)B * SP * C * C);
+  float* pm = c.take(ch);
+  float* ps = c.take(ch);
+  float* sp = c.take(ch);
+  float* Wcat = c.take(3 * (size_t)C * C);
+  float* dWcat = c.take(3 * (size_t)C * C);
+  float* dbcat = c.take(3 * (size_t)C);
+  float* lin = c.take(0);
+  auto G = [&](int i) { return reinterpret_cast<float*>(dp[i]); };
+  // reprojection: att [M][C] -> y
+  TCX_TRY(run_linear_bwd(att, 1, F(p[6]), dy, datt, G(6), G(7), M, C, C, lin, st));
+  // att[b] = Qs[b] ctx[b]:  dQs = datt ctx^T,  dctx = Qs^T datt
+  TCX_TRY(launch_bwd_packT_batched_f16(ctxT, B, C, C, C, 1, C, C, ctx32, st));     // ctx32[b][ck][cv]
+  {
+    GemmParams g = gemm1(datt, ctx32, dQs, N, C, C);
+    g.batch = B; g.strideA = (long long)N * C; g.strideW = (long long)C * C; g.strideC = (long long)N * C;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  TCX_TRY(launch_bwd_packT_batched_f16(qsm, B, N, C, C, SP, Ms, Ms, QsT, st));
+  TCX_TRY(launch_bwd_packT_batched_f32(datt, B, N, C, C, SP, Ms, Ms, dattT, st));
+  {
+    GemmParams g = gemm1(QsT, dattT, part, C, C, Ms);
+    g.batch = B * SP; g.strideA = (long long)C * Ms; g.strideW = (long long)C * Ms; g.strideC = (long long)C * C;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  TCX_TRY(launch_bwd_fold_batched(part, B, SP, C, dctx, dctxT, st));
+  // ctx = P^T V with P = softmax over tokens of K:  dV = P dctx,  dP = V dctx^T
+  TCX_TRY(launch_ea_bwd_prep(kqv, kqv + 2 * C, 3 * C, B, N, C, pm, ps, P32, V32, st));
+  {
+    GemmParams g = gemm1(P32, dctxT, dkqv + 2 * C, N, C, C);
+    g.ldc = 3 * C;
+    g.batch = B; g.strideA = (long long)N * C; g.strideW = (long long)C * C; g.strideC = (long long)N * 3 * C;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  {
+    GemmParams g = gemm1(V32, dctx, dP, N, C, C);
+    g.batch = B; g.strideA = (long long)N * C; g.strideW = (long long)C * C; g.strideC = (long long)N * C;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  TCX_TRY(launch_ea_bwd_softmax(P32, dP, qsm, dQs, B, N, C, sp, dkqv, st));
+  // the three 1x1 convolutions as one Linear with the stacked weight [Wk; Wq; Wv]
+  const size_t cc = (size_t)C * C * sizeof(float);
+  for (int i = 0; i < 3; i++)
+    TCX_REQUIRE(cudaMemcpyAsync(Wcat + (size_t)i * C * C, p[2 * i], cc, cudaMemcpyDeviceToDevice, st) == cudaSuccess,
+                "eff_attn_bwd: weight copy failed");
+  TCX_TRY(run_linear_bwd(xn16, 1, Wcat, dkqv, dxn, dWcat, dbcat, M, 3 * C, C, lin, st));
+  for (int i = 0; i < 3; i++) {
+    TCX_REQUIRE(cudaMemcpyAsync(dp[2 * i], dWcat + (size_t)i * C * C, cc, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
+                    cudaMemcpyAsync(dp[2 * i + 1], dbcat + (size_t)i * C, C * sizeof(float), cudaMemcpyDeviceToDevice, st) == cudaSuccess,
+                "eff_attn_bwd: gradient copy failed");
+  }
+  return 0;
+}
+
 size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4) { return 4 * mix_saved(nullptr, (long long)B * N, C, C4).floats; }
 int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
                               int W, int C, int C4, void* saved, void* stream) {

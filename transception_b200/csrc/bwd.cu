@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(256) bwd_flip9_kernel(const float* __restrict_
   wf[i] = w[c * 9 + 8 - t];
 }
 
-// 32 x 32 tile transpose: src rows = tokens, dst [s][c][Ms]
+// 32 x 32 tile transpose: src [batch][rows][ld] (rows = tokens), dst [batch][s][c][pitch]
 template <typename T>
-__global__ void __launch_bounds__(256) bwd_packT_kernel(const T* __restrict__ src, long long M, int C, int ld, int Ms,
+__global__ void __launch_bounds__(256) bwd_packT_kernel(const T* __restrict__ src, long long M, int C, int ld, int S, int Ms, int pitch,
                                                         float* __restrict__ dst) {
   __shared__ float tile[32][33];
   const long long t0 = (long long)blockIdx.x * 32;      // padded token index s*Ms + m (Ms % 32 == 0: a tile never straddles splits)
@@ -240,30 +240,142 @@ __global__ void __launch_bounds__(256) bwd_packT_kernel(const T* __restrict__ sr
   const int s = (int)(t0 / Ms);
   const int m0 = (int)(t0 - (long long)s * Ms);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  src += (size_t)blockIdx.z * M * ld;
+  dst += (size_t)blockIdx.z * S * C * pitch;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const long long tok = t0 + ty + i * 8;
     const int c = c0 + tx;
     float v = 0.f;
-    if (tok < M && m0 + ty + i * 8 < Ms && c < C) v = (float)src[tok * ld + c];
+    if (tok < M && c < C) v = (float)src[tok * ld + c];
     tile[ty + i * 8][tx] = v;
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const int c = c0 + ty + i * 8;
-    if (c < C) dst[((size_t)s * C + c) * Ms + m0 + tx] = tile[tx][ty + i * 8];
+    if (c < C) dst[((size_t)s * C + c) * pitch + m0 + tx] = tile[tx][ty + i * 8];
   }
 }
 
 template <typename T>
-int launch_packT(const T* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st) {
-  TCX_REQUIRE(Ms % 32 == 0 && (long long)S * Ms >= M, "bwd_packT: bad split plan (M=%lld S=%d Ms=%d)", M, S, Ms);
-  if (M == 0 || C == 0) return 0;
-  dim3 grid((unsigned)((long long)S * Ms / 32), (unsigned)cdiv(C, 32));
-  ProfScope prof("bwd_packT", st, (double)M * C * (sizeof(T) + 4.0));
-  bwd_packT_kernel<T><<<grid, 256, 0, st>>>(src, M, C, ld, Ms, dst);
+int launch_packT(const T* src, int batch, long long M, int C, int ld, int S, int Ms, int pitch, float* dst, cudaStream_t st) {
+  TCX_REQUIRE(Ms % 32 == 0 && (long long)S * Ms >= M && pitch >= Ms, "bwd_packT: bad split plan (M=%lld S=%d Ms=%d pitch=%d)", M, S, Ms, pitch);
+  if (M == 0 || C == 0 || batch == 0) return 0;
+  dim3 grid((unsigned)((long long)S * Ms / 32), (unsigned)cdiv(C, 32), (unsigned)batch);
+  ProfScope prof("bwd_packT", st, (double)batch * M * C * (sizeof(T) + 4.0));
+  bwd_packT_kernel<T><<<grid, 256, 0, st>>>(src, M, C, ld, S, Ms, pitch, dst);
   return tcx_check_launch("bwd_packT");
+}
+
+// ---- efficient attention backward (EfficientAttention.forward MSTr.py:106-143) -------------------------------------------
+// Column softmax of the keys over the N tokens of an image: chunk partials (max, sum of exp) -> fold in the consumers.
+constexpr int EA_CHUNK = 128;   // token rows per block
+
+__global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_kstats_kernel(const __half* __restrict__ k, int ld, int N, int C,
+                                                                            float* __restrict__ pm, float* __restrict__ ps) {
+  __shared__ float sm[RED_LANES][1][RED_COLS];
+  __shared__ float bm[RED_COLS];
+  const int c = blockIdx.z * RED_COLS + threadIdx.x;
+  const int b = blockIdx.y, chunks = gridDim.x;
+  const int r0 = blockIdx.x * EA_CHUNK, r1 = min(r0 + EA_CHUNK, N);
+  const __half* kb = k + (size_t)b * N * ld;
+  float m = -INFINITY;
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += RED_LANES) m = fmaxf(m, __half2float(kb[(size_t)r * ld + c]));
+  sm[threadIdx.y][0][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int l = 1; l < RED_LANES; l++) m = fmaxf(m, sm[l][0][threadIdx.x]);
+    bm[threadIdx.x] = m;
+  }
+  __syncthreads();
+  m = bm[threadIdx.x];
+  float acc[1] = {0.f};
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += RED_LANES) acc[0] += expf(__half2float(kb[(size_t)r * ld + c]) - m);
+  __syncthreads();
+  block_fold_lanes<1>(acc, sm);
+  if (threadIdx.y == 0 && c < C) {
+    pm[((size_t)b * chunks + blockIdx.x) * C + c] = m;
+    ps[((size_t)b * chunks + blockIdx.x) * C + c] = acc[0];
+  }
+}
+
+// P32 [B*N][C] = column softmax of K, V32 [B*N][C] = float(V)
+__global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_prep_kernel(const __half* __restrict__ k, const __half* __restrict__ v, int ld,
+                                                                          int N, int C, const float* __restrict__ pm,
+                                                                          const float* __restrict__ ps, float* __restrict__ P32,
+                                                                          float* __restrict__ V32) {
+  const int c = blockIdx.z * RED_COLS + threadIdx.x;
+  if (c >= C) return;
+  const int b = blockIdx.y, chunks = gridDim.x;
+  float m = -INFINITY;
+  for (int j = 0; j < chunks; j++) m = fmaxf(m, pm[((size_t)b * chunks + j) * C + c]);
+  float sum = 0.f;
+  for (int j = 0; j < chunks; j++) sum += ps[((size_t)b * chunks + j) * C + c] * expf(pm[((size_t)b * chunks + j) * C + c] - m);
+  const float inv = 1.0f / sum;
+  const int r0 = blockIdx.x * EA_CHUNK, r1 = min(r0 + EA_CHUNK, N);
+  for (int r = r0 + threadIdx.y; r < r1; r += RED_LANES) {
+    const size_t row = (size_t)b * N + r;
+    P32[row * C + c] = expf(__half2float(k[row * ld + c]) - m) * inv;
+    V32[row * C + c] = __half2float(v[row * ld + c]);
+  }
+}
+
+// chunk partials of sum_n P dP per (image, channel)
+__global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_pdp_kernel(const float* __restrict__ P, const float* __restrict__ dP, int N, int C,
+                                                                         float* __restrict__ sp) {
+  __shared__ float sm[RED_LANES][1][RED_COLS];
+  const int c = blockIdx.z * RED_COLS + threadIdx.x;
+  const int b = blockIdx.y, chunks = gridDim.x;
+  const int r0 = blockIdx.x * EA_CHUNK, r1 = min(r0 + EA_CHUNK, N);
+  float acc[1] = {0.f};
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += RED_LANES) {
+      const size_t i = ((size_t)b * N + r) * C + c;
+      acc[0] = fmaf(P[i], dP[i], acc[0]);
+    }
+  block_fold_lanes<1>(acc, sm);
+  if (threadIdx.y == 0 && c < C) sp[((size_t)b * chunks + blockIdx.x) * C + c] = acc[0];
+}
+// dK = P (dP - sum_n P dP) -> dkqv[:, 0:C] (row pitch ldo)
+__global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_dk_kernel(const float* __restrict__ P, const float* __restrict__ dP, int N, int C,
+                                                                        const float* __restrict__ sp, float* __restrict__ dk, int ldo) {
+  const int c = blockIdx.z * RED_COLS + threadIdx.x;
+  if (c >= C) return;
+  const int b = blockIdx.y, chunks = gridDim.x;
+  float s = 0.f;
+  for (int j = 0; j < chunks; j++) s += sp[((size_t)b * chunks + j) * C + c];
+  const int r0 = blockIdx.x * EA_CHUNK, r1 = min(r0 + EA_CHUNK, N);
+  for (int r = r0 + threadIdx.y; r < r1; r += RED_LANES) {
+    const size_t row = (size_t)b * N + r;
+    dk[row * ldo + c] = P[row * C + c] * (dP[row * C + c] - s);
+  }
+}
+// channel softmax backward, one warp per token: dQ = Qs (dQs - sum_c Qs dQs) -> dq (row pitch ldo)
+__global__ void __launch_bounds__(256) ea_bwd_dq_kernel(const __half* __restrict__ qs, const float* __restrict__ dqs, long long M, int C,
+                                                        float* __restrict__ dq, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) dot = fmaf(__half2float(qs[row * C + c]), dqs[row * C + c], dot);
+  dot = warp_sum(dot);
+  for (int c = lane; c < C; c += 32) dq[row * ldo + c] = __half2float(qs[row * C + c]) * (dqs[row * C + c] - dot);
+}
+
+// out[b][i] = sum_s part[(b*S + s)*n + i]; optional transposed copy outT[b][j*R + i'] of the R x R matrix
+__global__ void __launch_bounds__(256) bwd_fold_batched_kernel(const float* __restrict__ part, int S, int R, float* __restrict__ out,
+                                                               float* __restrict__ outT) {
+  const int n = R * R;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int b = blockIdx.y;
+  float s = 0.f;
+  for (int k = 0; k < S; k++) s += part[((size_t)b * S + k) * n + i];
+  out[(size_t)b * n + i] = s;
+  if (outT) outT[(size_t)b * n + (i % R) * R + i / R] = s;
 }
 
 }  // namespace
@@ -337,10 +449,47 @@ int launch_bwd_flip9(const float* w, float* wflip, int C, cudaStream_t st) {
 }
 
 int launch_bwd_packT_f32(const float* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st) {
-  return launch_packT<float>(src, M, C, ld, S, Ms, dst, st);
+  return launch_packT<float>(src, 1, M, C, ld, S, Ms, Ms, dst, st);
 }
 int launch_bwd_packT_f16(const __half* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st) {
-  return launch_packT<__half>(src, M, C, ld, S, Ms, dst, st);
+  return launch_packT<__half>(src, 1, M, C, ld, S, Ms, Ms, dst, st);
+}
+int launch_bwd_packT_batched_f32(const float* src, int batch, int N, int C, int ld, int S, int Ms, int pitch, float* dst, cudaStream_t st) {
+  return launch_packT<float>(src, batch, N, C, ld, S, Ms, pitch, dst, st);
+}
+int launch_bwd_packT_batched_f16(const __half* src, int batch, int N, int C, int ld, int S, int Ms, int pitch, float* dst, cudaStream_t st) {
+  return launch_packT<__half>(src, batch, N, C, ld, S, Ms, pitch, dst, st);
+}
+
+int launch_bwd_fold_batched(const float* part, int batch, int S, int R, float* out, float* outT, cudaStream_t st) {
+  if (batch == 0 || R == 0) return 0;
+  bwd_fold_batched_kernel<<<dim3(cdiv(R * R, 256), batch), 256, 0, st>>>(part, S, R, out, outT);
+  return tcx_check_launch("bwd_fold_batched");
+}
+
+int ea_bwd_chunks(int N) { return cdiv(N, EA_CHUNK); }
+
+int launch_ea_bwd_prep(const __half* k, const __half* v, int ld, int B, int N, int C, float* pm, float* ps, float* P32, float* V32,
+                       cudaStream_t st) {
+  if (B == 0 || N == 0) return 0;
+  const dim3 grid(ea_bwd_chunks(N), B, cdiv(C, RED_COLS)), block(RED_COLS, RED_LANES);
+  ea_bwd_kstats_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps);
+  TCX_TRY(tcx_check_launch("ea_bwd_kstats"));
+  ea_bwd_prep_kernel<<<grid, block, 0, st>>>(k, v, ld, N, C, pm, ps, P32, V32);
+  return tcx_check_launch("ea_bwd_prep");
+}
+
+int launch_ea_bwd_softmax(const float* P, const float* dP, const __half* qs, const float* dqs, int B, int N, int C, float* sp, float* dkqv,
+                          cudaStream_t st) {
+  if (B == 0 || N == 0) return 0;
+  const dim3 grid(ea_bwd_chunks(N), B, cdiv(C, RED_COLS)), block(RED_COLS, RED_LANES);
+  ea_bwd_pdp_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp);
+  TCX_TRY(tcx_check_launch("ea_bwd_pdp"));
+  ea_bwd_dk_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp, dkqv, 3 * C);
+  TCX_TRY(tcx_check_launch("ea_bwd_dk"));
+  const long long M = (long long)B * N;
+  ea_bwd_dq_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(qs, dqs, M, C, dkqv + C, 3 * C);
+  return tcx_check_launch("ea_bwd_dq");
 }
 
 void bwd_wgrad_splits(long long M, int Nout, int Kin, int* S, int* Ms) {

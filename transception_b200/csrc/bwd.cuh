@@ -33,6 +33,21 @@ int launch_bwd_flip9(const float* w, float* wflip, int C, cudaStream_t st);
 int launch_bwd_packT_f32(const float* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st);
 int launch_bwd_packT_f16(const __half* src, long long M, int C, int ld, int S, int Ms, float* dst, cudaStream_t st);
 
+// batched forms: src [batch][N][ld] -> dst [batch][S][C][pitch] (pitch >= Ms: several packs may share one row pitch)
+int launch_bwd_packT_batched_f32(const float* src, int batch, int N, int C, int ld, int S, int Ms, int pitch, float* dst, cudaStream_t st);
+int launch_bwd_packT_batched_f16(const __half* src, int batch, int N, int C, int ld, int S, int Ms, int pitch, float* dst, cudaStream_t st);
+// out[b] = sum_s part[b][s] for R x R matrices, plus the transposed copy outT[b] (may be null)
+int launch_bwd_fold_batched(const float* part, int batch, int S, int R, float* out, float* outT, cudaStream_t st);
+
+// ---- EfficientAttention backward pieces (MSTr.py:106-143; token-major fp16 K | Q | V rows of pitch ld) ----
+int ea_bwd_chunks(int N);
+// P32 [B*N][C] = softmax over the N tokens of each image of K (MSTr.py:118-122), V32 = float(V); pm / ps: B*chunks*C floats each
+int launch_ea_bwd_prep(const __half* k, const __half* v, int ld, int B, int N, int C, float* pm, float* ps, float* P32, float* V32,
+                       cudaStream_t st);
+// dkqv [B*N][3C]: columns [0,C) = dK = P (dP - sum_n P dP), [C,2C) = dQ = Qs (dQs - sum_c Qs dQs); sp: B*chunks*C floats
+int launch_ea_bwd_softmax(const float* P, const float* dP, const __half* qs, const float* dqs, int B, int N, int C, float* sp, float* dkqv,
+                          cudaStream_t st);
+
 // out[i] = sum_s part[s][i], i < n (split-K fold of the weight-gradient partials)
 int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st);
 

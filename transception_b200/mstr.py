@@ -22,6 +22,7 @@ structural values raise ``NotImplementedError``.
 import torch
 import torch.nn as nn
 
+from . import autograd as tcx_autograd
 from . import ops
 
 _LN_EPS = 1e-5
@@ -55,6 +56,11 @@ def _xavier_convs(mods):
             nn.init.xavier_uniform_(m.weight)
             if m.bias is not None:
                 nn.init.zeros_(m.bias)
+
+
+def _recording(x, w):
+    """True when autograd is recording this call: the training-row nodes (autograd.py) run instead of the fused forward."""
+    return torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
 
 
 def _bn(bn):
@@ -100,9 +106,8 @@ class MixFFN_skip(nn.Module):
                 self.norm1.weight, self.norm1.bias, self.norm1.eps, self.fc2.weight, self.fc2.bias)
 
     def forward(self, x, H, W):
-        if torch.is_grad_enabled() and (x.requires_grad or self.fc1.weight.requires_grad):
+        if _recording(x, self.fc1.weight):
             # training row: forward + backward on the library's kernels (transception_b200/autograd.py)
-            from . import autograd as tcx_autograd
             return tcx_autograd.mixffn_skip(x, H, W, *self.args())
         return ops.mixffn_skip(x, H, W, *self.args())
 
@@ -130,7 +135,10 @@ class EfficientAttention(nn.Module):
     def forward(self, input_):
         x = _nhwc(input_)
         B, H, W, C = x.shape
-        y = ops.eff_attn(x.view(B, H * W, C), *self.args(), residual=None, reinterpret=False)
+        if _recording(input_, self.keys.weight):
+            y = tcx_autograd.eff_attn(x.reshape(B, H * W, C), *self.args())
+        else:
+            y = ops.eff_attn(x.view(B, H * W, C), *self.args(), residual=None, reinterpret=False)
         return _as_nchw(y.view(B, H, W, C))
 
 
@@ -148,6 +156,12 @@ class EfficientTransformerBlock(nn.Module):
         self.mlp = MixFFN_skip(in_dim, int(in_dim * 4))
 
     def forward(self, x, H, W):
+        if _recording(x, self.norm1.weight):
+            # training row: every op is an autograd node backed by the library's forward + backward kernels; the two
+            # residual additions are the only ATen arithmetic (MSTr.py:164-173)
+            n1, n2 = self.norm1, self.norm2
+            tx = x + tcx_autograd.eff_attn(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps), *self.attn.args())
+            return tx + self.mlp(tcx_autograd.layernorm(tx, n2.weight, n2.bias, n2.eps), H, W)
         return ops.eff_block(x, H, W, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.attn.args(),
                              self.norm2.weight, self.norm2.bias, self.mlp.args())
 

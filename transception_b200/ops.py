@@ -93,6 +93,10 @@ _PROTOS = {
     "tcx_layernorm_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
     "tcx_linear_bwd_workspace_bytes": (_sz, [_ll, _i, _i]),
     "tcx_linear_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "tcx_eff_attn_saved_bytes": (_sz, [_i, _i, _i]),
+    "tcx_eff_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_eff_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_eff_attn_bwd": (_i, [_vp, _pp, _vp, _vp, _pp, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -870,4 +874,33 @@ def mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2
     gtab = (ctypes.c_void_p * 8)(*[_ptr(g) for g in grads])
     ws = _ws(lib.tcx_mixffn_skip_bwd_workspace_bytes(B, H * W, C, C4), dy)
     _chk(lib.tcx_mixffn_skip_bwd(_ptr(dy), tab, eps, _ptr(saved), _ptr(dxn), gtab, B, H, W, C, C4, _ptr(ws), _stream()))
+    return dxn, grads
+
+
+def eff_attn_train(xn, kw, kb, qw, qb, vw, vb, rw, rb, residual=None):
+    """Training forward of EfficientAttention on LayerNorm output xn [B, N, C]: (y, saved)."""
+    require_cuda(xn)
+    lib = load_library()
+    xn = xn.contiguous()
+    B, N, C = xn.shape
+    y = torch.empty_like(xn)
+    saved = _ws(lib.tcx_eff_attn_saved_bytes(B, N, C), xn)
+    tab = _table([kw, kb, qw, qb, vw, vb, rw, rb], mats=(0, 2, 4, 6))
+    _chk(lib.tcx_eff_attn_train_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, N, C, _ptr(saved), _stream()))
+    return y, saved
+
+
+def eff_attn_bwd(dy, saved, kw, kb, qw, qb, vw, vb, rw, rb, need_dx=True):
+    """(dxn, [8 parameter gradients in slot order]) of EfficientAttention."""
+    require_cuda(dy)
+    lib = load_library()
+    dy = dy.contiguous()
+    B, N, C = dy.shape
+    params = [kw, kb, qw, qb, vw, vb, rw, rb]
+    grads = [torch.empty_like(p) for p in params]
+    dxn = torch.empty_like(dy) if need_dx else None
+    tab = _table(params)
+    gtab = (ctypes.c_void_p * 8)(*[_ptr(g) for g in grads])
+    ws = _ws(lib.tcx_eff_attn_bwd_workspace_bytes(B, N, C), dy)
+    _chk(lib.tcx_eff_attn_bwd(_ptr(dy), tab, _ptr(saved), _ptr(dxn), gtab, B, N, C, _ptr(ws), _stream()))
     return dxn, grads
