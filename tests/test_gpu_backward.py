@@ -222,3 +222,53 @@ def test_efficient_block_backward(cuda_lib, B, H, W, C):
     dy = _rand(B, H * W, C, seed=6, scale=1e-3)
     checked = _grad_parity(m, "b", lambda sd, xr: O.efficient_block(sd, "b", xr, H, W), x, dy)
     assert len(checked) == 4 + 8 + 8          # two LayerNorms, attention, the live Mix-FFN parameters
+
+
+@pytest.mark.parametrize("scale,H,W,C", [(2, 7, 7, 512), (2, 14, 14, 320), (4, 14, 14, 64)])
+def test_patch_expand_backward(cuda_lib, scale, H, W, C):
+    """PatchExpand / FinalPatchExpand_X4 (MSTr.py:184-201, :212-227)."""
+    from networks.MSTr import FinalPatchExpand_X4, PatchExpand
+    torch.manual_seed(C)
+    m = _randomise(PatchExpand((H, W), C, 2) if scale == 2 else FinalPatchExpand_X4((H, W), C, 4))
+    x = _rand(2, H * W, C, seed=5)
+    cout = C // 2 if scale == 2 else C
+    dy = _rand(2, H * W * scale * scale, cout, seed=6, scale=1e-3)
+    checked = _grad_parity(m, "u", lambda sd, xr: O.patch_expand(sd, "u", xr, H, W, scale), x, dy)
+    assert len(checked) == 3
+
+
+@pytest.mark.parametrize("is_last", [False, True])
+def test_decoder_layer_backward(cuda_lib, is_last):
+    """MyDecoderLayer (MSTr.py:273-290) with a skip map: concat Linear, two efficient blocks, expand (+ class head)."""
+    from networks.MSTr import MyDecoderLayer
+    torch.manual_seed(11)
+    h = w = 14
+    io = [32, 64, 64, 64] if is_last else [144, 128, 128, 128]
+    m = _randomise(MyDecoderLayer((h, w), io, 1, "mix_skip", n_class=9, is_last=is_last))
+    c1 = io[1]
+    c2 = io[0] * (4 if is_last else 2) - c1
+    x1 = _rand(2, h * w, c1, seed=1)
+    x2 = _rand(2, h, w, c2, seed=2)
+    sd = {"d." + k: v.clone().requires_grad_() for k, v in m.state_dict().items()}
+    x1r, x2r = x1.clone().requires_grad_(), x2.clone().requires_grad_()
+    want = O.decoder_layer(sd, "d", x1r, x2r, is_last=is_last)
+    dy = _rand(*want.shape, seed=3, scale=1e-3)
+    want.backward(dy)
+    mg = m.cuda().train()
+    x1g, x2g = x1.cuda().requires_grad_(), x2.cuda().requires_grad_()
+    got = mg(x1g, x2g)
+    assert got.shape == want.shape
+    assert (got.float().cpu() - want.detach()).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    got.backward(dy.cuda())
+    floor = 1e-6 * dy.norm().item()
+    _check(x1g.grad, x1r.grad, 1e-2, "dx1")
+    _check(x2g.grad, x2r.grad, 1e-2, "dx2")
+    n = 0
+    for k, p in mg.named_parameters():
+        ref = sd["d." + k].grad
+        if ref is None:
+            assert p.grad is None, k
+            continue
+        _check(p.grad, ref, 1e-2, "d " + k, floor)
+        n += 1
+    assert n == 2 + 2 * 20 + 3 + (2 if is_last else 0)

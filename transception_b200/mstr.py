@@ -169,6 +169,16 @@ class EfficientTransformerBlock(nn.Module):
 # --------------------------------------------------------------------------------------
 # Decoder (reference MSTr.py:176-290) — SURVEY §8f rank 1
 # --------------------------------------------------------------------------------------
+def _patch_expand_train(x, H, W, w, scale, norm):
+    """PatchExpand / FinalPatchExpand_X4 (MSTr.py:184-201, :212-227) as autograd nodes: expand GEMM and LayerNorm on the
+    library's kernels, the pixel shuffle between them is a permuted copy."""
+    B = x.shape[0]
+    y = tcx_autograd.linear(x, w)
+    c = y.shape[-1] // (scale * scale)
+    y = y.view(B, H, W, scale, scale, c).permute(0, 1, 3, 2, 4, 5).reshape(B, H * scale * W * scale, c)
+    return tcx_autograd.layernorm(y, norm.weight, norm.bias, norm.eps)
+
+
 class PatchExpand(nn.Module):
     def __init__(self, input_resolution, dim, dim_scale=2, norm_layer=nn.LayerNorm):
         super().__init__()
@@ -181,6 +191,8 @@ class PatchExpand(nn.Module):
         H, W = self.input_resolution
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
+        if _recording(x, self.expand.weight):
+            return _patch_expand_train(x, H, W, self.expand.weight, 2, self.norm)
         return ops.patch_expand(x.contiguous(), H, W, self.expand.weight, 2,
                                 self.norm.weight, self.norm.bias, self.norm.eps)
 
@@ -199,6 +211,8 @@ class FinalPatchExpand_X4(nn.Module):
         H, W = self.input_resolution
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
+        if _recording(x, self.expand.weight):
+            return _patch_expand_train(x, H, W, self.expand.weight, self.dim_scale, self.norm)
         return ops.patch_expand(x.contiguous(), H, W, self.expand.weight, self.dim_scale,
                                 self.norm.weight, self.norm.bias, self.norm.eps)
 
@@ -233,6 +247,8 @@ class MyDecoderLayer(nn.Module):
         if x2 is None:
             return self.layer_up(x1)
         b, h, w, c = x2.shape
+        if _recording(x1, self.concat_linear.weight):
+            return self._forward_train(x1, x2.reshape(b, h * w, c), h, w)
         cat_linear_x = ops.concat_linear(x1, x2.reshape(b, h * w, c), self.concat_linear.weight, self.concat_linear.bias)
         t1 = self.layer_former_1(cat_linear_x, h, w)
         t2 = self.layer_former_2(t1, h, w)
@@ -242,6 +258,25 @@ class MyDecoderLayer(nn.Module):
             return ops.final_expand_head(t2, h, w, up.expand.weight, up.norm.weight, up.norm.bias, up.norm.eps,
                                          self.last_layer.weight, self.last_layer.bias)
         return self.layer_up(t2)
+
+
+    def _forward_train(self, x1, x2, h, w):
+        """Training row (MSTr.py:273-290): Linear / LayerNorm / block nodes of autograd.py; the concatenation, the pixel
+        shuffles and the NCHW view of the logits are copies."""
+        t = tcx_autograd.linear(torch.cat([x1, x2], dim=-1), self.concat_linear.weight, self.concat_linear.bias)
+        t = self.layer_former_2(self.layer_former_1(t, h, w), h, w)
+        up = self.layer_up(t)
+        if self.last_layer is None:
+            return up
+        # 1x1 conv to n_class planes = Linear over the 64 channels; the class rows are zero-padded to a multiple of 16 so
+        # that the gradient GEMMs keep 16-byte row pitches
+        cw, cb = self.last_layer.weight, self.last_layer.bias
+        k = cw.shape[0]
+        kp = (k + 15) // 16 * 16
+        wpad = torch.nn.functional.pad(cw.view(k, -1), (0, 0, 0, kp - k))
+        bpad = torch.nn.functional.pad(cb, (0, kp - k))
+        logits = tcx_autograd.linear(up, wpad, bpad)[..., :k]
+        return logits.view(x1.shape[0], 4 * h, 4 * w, k).permute(0, 3, 1, 2)
 
 
 # --------------------------------------------------------------------------------------
