@@ -163,6 +163,12 @@ def _randomise(net, seed=5):
 def _grad_parity(module, prefix, oracle_fn, x, dy, rel=1e-2, dead=()):
     """module on CUDA in autograd mode vs torch autograd over the CPU oracle; returns the parameter names checked."""
     sd = {prefix + "." + k: v.clone().requires_grad_() for k, v in module.state_dict().items()}
+    # shared modules (one ConvPosEnc / ConvRelPosEnc per MHCAEncoder) appear under several state_dict keys: the oracle reads
+    # each alias as its own leaf, so the reference gradient of the shared parameter is the sum over its aliases
+    alias = {}
+    for k, v in module.state_dict(keep_vars=True).items():
+        alias.setdefault(id(v), []).append(k)
+    alias = {ks[0]: ks for ks in alias.values()}
     xr = x.clone().requires_grad_()
     want = oracle_fn(sd, xr)
     want.backward(dy)
@@ -176,7 +182,8 @@ def _grad_parity(module, prefix, oracle_fn, x, dy, rel=1e-2, dead=()):
     params = dict(mg.named_parameters())
     checked = []
     for k, p in params.items():
-        ref = sd[prefix + "." + k].grad
+        refs = [sd[prefix + "." + a].grad for a in alias[k] if sd[prefix + "." + a].grad is not None]
+        ref = sum(refs) if refs else None
         if ref is None:
             assert p.grad is None, k + ": gradient where the reference has none"
             continue
@@ -272,3 +279,48 @@ def test_decoder_layer_backward(cuda_lib, is_last):
         _check(p.grad, ref, 1e-2, "d " + k, floor)
         n += 1
     assert n == 2 + 2 * 20 + 3 + (2 if is_last else 0)
+
+
+@pytest.mark.parametrize("B,H,W,C,add", [(2, 14, 14, 64, True), (1, 7, 9, 128, False), (2, 7, 7, 320, True)])
+def test_dwconv_tokens_backward(cuda_lib, B, H, W, C, add):
+    """ConvPosEnc (MSTr.py:744-752, with the skip) and DWConv (:26-31)."""
+    from networks.MSTr import ConvPosEnc, DWConv
+    torch.manual_seed(C)
+    m = _randomise(ConvPosEnc(C) if add else DWConv(C))
+    m._call_hw = ((H, W),) if add else (H, W)
+    x = _rand(B, H * W, C, seed=2)
+    dy = _rand(B, H * W, C, seed=3, scale=1e-3)
+
+    def oracle(sd, xr):
+        if add:
+            return O.conv_pos_enc(sd, "c", xr, H, W)
+        return O.map_to_tokens(O.conv(sd, "c.dwconv", O.tokens_to_map(xr, H, W), 1, 1, C))
+    assert len(_grad_parity(m, "c", oracle, x, dy, rel=1e-4)) == 2
+
+
+def _mhca_encoder(C, layers):
+    from networks.MSTr import MHCAEncoder
+    torch.manual_seed(C)
+    return _randomise(MHCAEncoder(C, num_layers=layers, num_heads=8, mlp_ratio=4, drop_path_list=[0.0] * layers))
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 14, 14, 64), (1, 14, 14, 128), (2, 7, 7, 320), (1, 28, 28, 64), (2, 5, 8, 64)])
+def test_factor_att_backward(cuda_lib, B, H, W, C):
+    """FactorAtt_ConvRelPosEnc (MSTr.py:852-886) with the 3/5/7 conv relative position encoding (:801-823)."""
+    enc = _mhca_encoder(C, 1)
+    m = enc.MHCA_layers[0].factoratt_crpe
+    m._call_hw = ((H, W),)
+    x = _rand(B, H * W, C, seed=2)
+    dy = _rand(B, H * W, C, seed=3, scale=1e-3)
+    checked = _grad_parity(m, "f", lambda sd, xr: O.factor_att(sd, "f", xr, H, W), x, dy)
+    assert len(checked) == 2 + 6 + 2
+
+
+@pytest.mark.parametrize("B,H,W,C,L", [(2, 14, 14, 64, 2), (1, 14, 14, 128, 1), (2, 7, 7, 320, 2)])
+def test_mhca_encoder_backward(cuda_lib, B, H, W, C, L):
+    """MHCAEncoder (MSTr.py:981-993): L MHCABlocks sharing one ConvPosEnc / ConvRelPosEnc, NCHW output."""
+    m = _mhca_encoder(C, L)
+    m._call_hw = ((H, W),)
+    x = _rand(B, H * W, C, seed=2)
+    dy = _rand(B, C, H, W, seed=3, scale=1e-3)
+    _grad_parity(m, "e", lambda sd, xr: O.mhca_encoder(sd, "e", xr, H, W, L), x, dy)

@@ -78,6 +78,52 @@ def eff_attn(x, kw, kb, qw, qb, vw, vb, rw, rb):
     return EffAttnFn.apply(x, kw, kb, qw, qb, vw, vb, rw, rb)
 
 
+class FactorAttFn(torch.autograd.Function):
+    """FactorAtt_ConvRelPosEnc.forward (MSTr.py:852-886) on LayerNorm output x [B, N, C]."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, heads, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb):
+        y, ws = ops.mb_factor_attn(x, H, W, heads, None, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
+                                   keep_ws=True)
+        ctx.save_for_backward(x, ws, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb)
+        ctx.geom = (H, W, heads)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ws, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb = ctx.saved_tensors
+        H, W, heads = ctx.geom
+        dx, g = ops.mb_factor_attn_bwd(dy, x, ws, H, W, heads, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], projw, projb,
+                                       need_dx=ctx.needs_input_grad[0])
+        return (dx, None, None, None) + tuple(g)
+
+
+class DwConvTokensFn(torch.autograd.Function):
+    """y = dw3x3(x) + b (+ x): ConvPosEnc (MSTr.py:744-752, add_input) / DWConv (:26-31)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, w, b, add_input):
+        ctx.save_for_backward(x, w)
+        ctx.geom = (H, W, add_input)
+        return ops.dwconv_tokens(x.contiguous(), H, W, w, b, add_input=add_input)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        H, W, add_input = ctx.geom
+        dx, dw, db = ops.dwconv_tokens_bwd(x, H, W, w, dy, add_input, need_dx=ctx.needs_input_grad[0])
+        return dx, None, None, dw, db, None
+
+
+def factor_att(x, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb):
+    return FactorAttFn.apply(x, H, W, heads, qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2],
+                             projw, projb)
+
+
+def dwconv_tokens(x, H, W, w, b, add_input):
+    return DwConvTokensFn.apply(x, H, W, w, b, add_input)
+
+
 def layernorm(x, w, b, eps):
     return LayerNormFn.apply(x, w, b, eps)
 

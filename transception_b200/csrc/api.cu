@@ -1738,6 +1738,116 @@ int tcx_eff_attn_bwd(const float* dy, const void* const* p, const void* saved, f
   return 0;
 }
 
+// ---- FactorAtt_ConvRelPosEnc (MSTr.py:852-886) backward; forward = tcx_mb_factor_attn_fwd, whose workspace is kept ----
+static size_t mb_attn_bwd_ws_floats(int B, int N, int C) {
+  const size_t M = (size_t)B * N, bnc = M * C, bcc = (size_t)B * C * C;
+  int S, Ms;
+  bwd_wgrad_splits(N, C, C, &S, &Ms);
+  const size_t pack = (size_t)B * S * C * Ms, ch = (size_t)B * ea_bwd_chunks(N) * C;
+  const size_t lin = std::max(linear_bwd_ws_floats(M, C, C), linear_bwd_ws_floats(M, 3 * C, C));
+  return 6 * rnd(bnc) + rnd(3 * bnc) + 3 * rnd(bcc) + 2 * rnd(pack) + rnd((size_t)B * S * C * C) + 3 * rnd(ch) +
+         rnd(bwd_dwk_wgrad_part_floats(7, M, C)) + lin + 64;
+}
+size_t tcx_mb_factor_attn_bwd_workspace_bytes(int B, int N, int C) { return 4 * mb_attn_bwd_ws_floats(B, N, C); }
+
+int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* p, const void* fwd_ws, float* dxn, void* const* dp,
+                           int B, int H, int W, int C, int heads, void* ws, void* stream) {
+  TCX_REQUIRE(dy && xn && p && fwd_ws && dp && ws, "mb_factor_attn_bwd: null pointer");
+  TCX_REQUIRE(heads == 8 && C % heads == 0 && C % 4 == 0, "mb_factor_attn_bwd: built for 8 heads (crpe windows 3/5/7 on 2/3/3 heads)");
+  for (int i = 0; i < 10; i++) TCX_REQUIRE(dp[i] != nullptr, "mb_factor_attn_bwd: gradient slot %d is null", i);
+  cudaStream_t st = S(stream);
+  const int N = H * W, Ch = C / heads;
+  const long long M = (long long)B * N;
+  const size_t bnc = (size_t)M * C, bcc = (size_t)B * C * C;
+  const float scale = 1.0f / sqrtf((float)Ch);
+  // forward buffers (tcx_mb_factor_attn_fwd carve order): q | k | v rows, context, attention output before the projection
+  Carver f(const_cast<void*>(fwd_ws));
+  const float* qkv = f.take(3 * bnc);
+  f.take(bcc);
+  const float* att = f.take(bnc);
+  const float* q = qkv; const float* k = qkv + C; const float* v = qkv + 2 * C;
+  const int ld = 3 * C;
+  int SP, Ms;
+  bwd_wgrad_splits(N, C, C, &SP, &Ms);
+  const size_t ch = (size_t)B * ea_bwd_chunks(N) * C;
+  Carver c(ws);
+  float* dxo = c.take(bnc);
+  float* P = c.take(bnc);
+  float* dP = c.take(bnc);
+  float* dqfa = c.take(bnc);
+  float* convv = c.take(bnc);
+  float* dvconv = c.take(bnc);
+  float* dqkv = c.take(3 * bnc);
+  float* ctx = c.take(bcc);
+  float* dctx = c.take(bcc);
+  float* dctxT = c.take(bcc);
+  float* packA = c.take((size_t)B * SP * C * Ms);
+  float* packB = c.take((size_t)B * SP * C * Ms);
+  float* part = c.take((size_t)B * SP * C * C);
+  float* pm = c.take(ch);
+  float* ps = c.take(ch);
+  float* sp = c.take(ch);
+  float* wpart = c.take(bwd_dwk_wgrad_part_floats(7, M, C));
+  float* lin = c.take(0);
+  auto G = [&](int i) { return reinterpret_cast<float*>(dp[i]); };
+  const int win[3] = {3, 5, 7}, c0[3] = {0, 2 * Ch, 5 * Ch}, cg[3] = {2 * Ch, 3 * Ch, 3 * Ch};
+  auto ctx_gemm = [&](const float* a, int lda_, const float* b_, int ldb_, float sc, float* out, float* outT) -> int {
+    // out[b] = sc * mask(a[b]^T b_[b]) over the tokens of image b
+    TCX_TRY(launch_bwd_packT_batched_f32(a, B, N, C, lda_, SP, Ms, Ms, packA, st));
+    TCX_TRY(launch_bwd_packT_batched_f32(b_, B, N, C, ldb_, SP, Ms, Ms, packB, st));
+    GemmParams g = gemm1(packA, packB, part, C, C, Ms);
+    g.batch = B * SP; g.strideA = (long long)C * Ms; g.strideW = (long long)C * Ms; g.strideC = (long long)C * C;
+    TCX_TRY(launch_gemm(g, st));
+    return launch_bwd_fold_mask(part, B, SP, C, Ch, sc, out, outT, st);
+  };
+  auto tok_gemm = [&](const float* a, int lda_, const float* w, float* out, int ldo, const float* res) -> int {
+    // out[b] (N x C) = a[b] (N x C) w[b]^T (+ res)
+    GemmParams g = gemm1(a, w, out, N, C, C);
+    g.lda = lda_; g.ldc = ldo;
+    g.batch = B; g.strideA = (long long)N * lda_; g.strideW = (long long)C * C; g.strideC = (long long)N * ldo;
+    if (res) { g.g[0].epi.residual = res; g.g[0].epi.ldr = C; g.g[0].epi.strideR = (long long)N * C; }
+    return launch_gemm(g, st);
+  };
+  // projection: att [M][C] -> y
+  TCX_TRY(run_linear_bwd(att, 0, F(p[8]), dy, dxo, G(8), G(9), M, C, C, lin, st));
+  // recompute: P = softmax over tokens of k, ctx = per-head P^T v, conv_v = crpe depthwise convolutions of v
+  TCX_TRY(launch_bwd_ksoftmax32(k, ld, B, N, C, pm, ps, P, st));
+  TCX_TRY(ctx_gemm(P, C, v, ld, 1.0f, ctx, nullptr));
+  for (int j = 0; j < 3; j++)
+    TCX_TRY(launch_bwd_dwk(win[j], v + c0[j], ld, F(p[2 + 2 * j]), F(p[3 + 2 * j]), convv + c0[j], C, B, H, W, cg[j], 0, 0, st));
+  // x_out = scale * q ctx + q * conv_v
+  TCX_TRY(tok_gemm(dxo, C, ctx, dqfa, C, nullptr));                       // d(q ctx)/dq, before the scale
+  TCX_TRY(ctx_gemm(q, ld, dxo, C, scale, dctx, dctxT));                   // dctx = scale * mask(q^T dxo)
+  TCX_TRY(launch_mb_bwd_dq(dxo, dqfa, convv, q, ld, scale, M, C, dqkv, ld, st));   // dq; convv <- d conv_v
+  for (int j = 0; j < 3; j++)
+    TCX_TRY(launch_bwd_dwk(win[j], convv + c0[j], C, F(p[2 + 2 * j]), nullptr, dvconv + c0[j], C, B, H, W, cg[j], 1, 0, st));
+  TCX_TRY(tok_gemm(P, C, dctxT, dqkv + 2 * C, ld, dvconv));               // dv = P dctx + conv^T(d conv_v)
+  TCX_TRY(tok_gemm(v, ld, dctx, dP, C, nullptr));                         // dP = v dctx^T
+  TCX_TRY(launch_bwd_colsoftmax(P, dP, B, N, C, sp, dqkv + C, ld, st));   // dk
+  for (int j = 0; j < 3; j++)
+    TCX_TRY(launch_bwd_dwk_wgrad(win[j], convv + c0[j], C, v + c0[j], ld, B, H, W, cg[j], G(2 + 2 * j), G(3 + 2 * j), wpart, st));
+  // qkv Linear
+  return run_linear_bwd(xn, 0, F(p[0]), dqkv, dxn, G(0), G(1), M, 3 * C, C, lin, st);
+}
+
+// ---- ConvPosEnc / DWConv (MSTr.py:744-752, :26-31) backward: y = dw3x3(x) + b (+ x) ----
+size_t tcx_dwconv_tokens_bwd_workspace_bytes(int B, int H, int W, int C) {
+  return 4 * (rnd(bwd_dwk_wgrad_part_floats(3, (long long)B * H * W, C)) + 64);
+}
+int tcx_dwconv_tokens_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int B, int H, int W, int C,
+                          int add_input, void* ws, void* stream) {
+  TCX_REQUIRE(x && w && dy && ws, "dwconv_tokens_bwd: null pointer");
+  cudaStream_t st = S(stream);
+  const long long M = (long long)B * H * W;
+  if (dx) {
+    if (add_input)
+      TCX_REQUIRE(cudaMemcpyAsync(dx, dy, sizeof(float) * M * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess, "dwconv_tokens_bwd: copy failed");
+    TCX_TRY(launch_bwd_dwk(3, dy, C, w, nullptr, dx, C, B, H, W, C, 1, add_input ? 1 : 0, st));
+  }
+  if (dw) TCX_TRY(launch_bwd_dwk_wgrad(3, dy, C, x, C, B, H, W, C, dw, db, reinterpret_cast<float*>(ws), st));
+  return 0;
+}
+
 size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4) { return 4 * mix_saved(nullptr, (long long)B * N, C, C4).floats; }
 int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
                               int W, int C, int C4, void* saved, void* stream) {

@@ -479,14 +479,19 @@ int launch_ea_bwd_prep(const __half* k, const __half* v, int ld, int B, int N, i
   return tcx_check_launch("ea_bwd_prep");
 }
 
-int launch_ea_bwd_softmax(const float* P, const float* dP, const __half* qs, const float* dqs, int B, int N, int C, float* sp, float* dkqv,
-                          cudaStream_t st) {
+int launch_bwd_colsoftmax(const float* P, const float* dP, int B, int N, int C, float* sp, float* dk, int ldo, cudaStream_t st) {
   if (B == 0 || N == 0) return 0;
   const dim3 grid(ea_bwd_chunks(N), B, cdiv(C, RED_COLS)), block(RED_COLS, RED_LANES);
   ea_bwd_pdp_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp);
   TCX_TRY(tcx_check_launch("ea_bwd_pdp"));
-  ea_bwd_dk_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp, dkqv, 3 * C);
-  TCX_TRY(tcx_check_launch("ea_bwd_dk"));
+  ea_bwd_dk_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp, dk, ldo);
+  return tcx_check_launch("ea_bwd_dk");
+}
+
+int launch_ea_bwd_softmax(const float* P, const float* dP, const __half* qs, const float* dqs, int B, int N, int C, float* sp, float* dkqv,
+                          cudaStream_t st) {
+  if (B == 0 || N == 0) return 0;
+  TCX_TRY(launch_bwd_colsoftmax(P, dP, B, N, C, sp, dkqv, 3 * C, st));
   const long long M = (long long)B * N;
   ea_bwd_dq_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(qs, dqs, M, C, dkqv + C, 3 * C);
   return tcx_check_launch("ea_bwd_dq");

@@ -48,6 +48,26 @@ int launch_ea_bwd_prep(const __half* k, const __half* v, int ld, int B, int N, i
 int launch_ea_bwd_softmax(const float* P, const float* dP, const __half* qs, const float* dqs, int B, int N, int C, float* sp, float* dkqv,
                           cudaStream_t st);
 
+// backward of a softmax over the N tokens of each image: dk[b*N+n][c] (row pitch ldo) = P (dP - sum_n P dP); sp: B*chunks*C floats
+int launch_bwd_colsoftmax(const float* P, const float* dP, int B, int N, int C, float* sp, float* dk, int ldo, cudaStream_t st);
+
+// ---- Multi-Branch attention / position-encoding convolutions (bwd_mb.cu) ----
+// depthwise K x K (K in 3, 5, 7; stride 1, zero padding) on Cg channels of rows with pitch ldx -> ldy.
+// flip = 0: y = b + conv(x) (forward); flip = 1: y = conv with mirrored taps (input gradient, no bias); add: y += instead of y =
+int launch_bwd_dwk(int K, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int B, int H, int W, int Cg, int flip,
+                   int add, cudaStream_t st);
+// dw [Cg][K*K] = sum_p g[p][c] x[p + off][c], db [Cg] = sum_p g (db may be null); part: bwd_dwk_wgrad_part_floats
+size_t bwd_dwk_wgrad_part_floats(int K, long long M, int Cg);
+int launch_bwd_dwk_wgrad(int K, const float* g, int ldg, const float* x, int ldx, int B, int H, int W, int Cg, float* dw, float* db,
+                         float* part, cudaStream_t st);
+// out[b] = scale * sum_s part[b][s] restricted to the diagonal Ch x Ch blocks of the R x R matrix (zero elsewhere), outT transposed
+int launch_bwd_fold_mask(const float* part, int batch, int S, int R, int Ch, float scale, float* out, float* outT, cudaStream_t st);
+// dq[r][c] (pitch ldo) = scale * dqfa + dxo * convv;  convv <- dxo * q (the gradient of the conv output), q rows of pitch ldq
+int launch_mb_bwd_dq(const float* dxo, const float* dqfa, float* convv, const float* q, int ldq, float scale, long long M, int C, float* dq,
+                     int ldo, cudaStream_t st);
+// P [B*N][C] = softmax over the N tokens of each image of fp32 k rows (pitch ld); pm / ps: B*chunks*C floats each
+int launch_bwd_ksoftmax32(const float* k, int ld, int B, int N, int C, float* pm, float* ps, float* P, cudaStream_t st);
+
 // out[i] = sum_s part[s][i], i < n (split-K fold of the weight-gradient partials)
 int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st);
 

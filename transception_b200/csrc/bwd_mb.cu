@@ -1,0 +1,237 @@
+// Backward kernels of the Multi-Branch attention (FactorAtt_ConvRelPosEnc MSTr.py:852-886, ConvRelPosEnc :801-823) and of
+// the depthwise position-encoding convolutions (ConvPosEnc :744-752).  fp32 tokens-major tensors with an explicit row
+// pitch (q | k | v live side by side in one [M][3C] buffer); reductions over tokens are two-pass and ordered.
+#include "bwd.cuh"
+
+namespace {
+
+constexpr int RC = 64, RL = 4;       // (64 columns x 4 row lanes) reduction block, as in bwd.cu
+
+// depthwise K x K, stride 1, zero padding K/2, on the channel range this launch was given:
+//   FLIP = false: y[p][c] = b[c] + sum_t w[c][t] x[p + off(t)][c]        (forward)
+//   FLIP = true : y[p][c] =        sum_t w[c][t] x[p - off(t)][c]        (gradient w.r.t. the conv input)
+// ADD: y += (accumulate into the destination)
+template <int K, bool FLIP, bool ADD>
+__global__ void __launch_bounds__(256) dwk_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                  const float* __restrict__ b, float* __restrict__ y, int ldy, int B, int H, int W, int Cg) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * H * W * Cg;
+  if (idx >= total) return;
+  const int c = (int)(idx % Cg);
+  const long long p = idx / Cg;
+  const int px = (int)(p % W), py = (int)((p / W) % H);
+  const float* wc = w + (size_t)c * K * K;
+  float acc = (b && !FLIP) ? b[c] : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < K; ky++) {
+    const int dy = FLIP ? K / 2 - ky : ky - K / 2;
+    const int yy = py + dy;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < K; kx++) {
+      const int dx = FLIP ? K / 2 - kx : kx - K / 2;
+      const int xx = px + dx;
+      if (xx < 0 || xx >= W) continue;
+      acc = fmaf(__ldg(wc + ky * K + kx), x[(p + (long long)dy * W + dx) * ldx + c], acc);
+    }
+  }
+  if (ADD) y[p * ldy + c] += acc; else y[p * ldy + c] = acc;
+}
+
+// weight / bias gradient of the same conv: partials [blk][K*K + 1][Cg]
+template <int K>
+__global__ void __launch_bounds__(RC * RL) dwk_wgrad_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx,
+                                                            int B, int H, int W, int Cg, int rows, float* __restrict__ part) {
+  __shared__ float sm[RL][RC];
+  const int c = blockIdx.y * RC + threadIdx.x;
+  const long long M = (long long)B * H * W;
+  const long long r0 = (long long)blockIdx.x * rows;
+  const long long r1 = r0 + rows < M ? r0 + rows : M;
+  float acc[K * K + 1];
+#pragma unroll
+  for (int t = 0; t <= K * K; t++) acc[t] = 0.f;
+  if (c < Cg) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += RL) {
+      const int px = (int)(r % W), py = (int)((r / W) % H);
+      const float gv = g[r * ldg + c];
+      acc[K * K] += gv;
+#pragma unroll
+      for (int ky = 0; ky < K; ky++) {
+        const int yy = py + ky - K / 2;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; kx++) {
+          const int xx = px + kx - K / 2;
+          if (xx < 0 || xx >= W) continue;
+          acc[ky * K + kx] = fmaf(gv, x[(r + (long long)(ky - K / 2) * W + (kx - K / 2)) * ldx + c], acc[ky * K + kx]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t <= K * K; t++) {
+    sm[threadIdx.y][threadIdx.x] = acc[t];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < Cg) {
+      float s = sm[0][threadIdx.x];
+#pragma unroll
+      for (int l = 1; l < RL; l++) s += sm[l][threadIdx.x];
+      part[((size_t)blockIdx.x * (K * K + 1) + t) * Cg + c] = s;
+    }
+    __syncthreads();
+  }
+}
+// partials [nblk][KK + 1][Cg] -> dw [Cg][KK], db [Cg] (db may be null)
+__global__ void __launch_bounds__(256) dwk_fold_kernel(const float* __restrict__ part, int nblk, int KK, int Cg, float* __restrict__ dw,
+                                                       float* __restrict__ db) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= (KK + 1) * Cg) return;
+  const int t = i / Cg, c = i - t * Cg;
+  float s = 0.f;
+  for (int k = 0; k < nblk; k++) s += part[(size_t)k * (KK + 1) * Cg + i];
+  if (t < KK) dw[(size_t)c * KK + t] = s; else if (db) db[c] = s;
+}
+
+template <int K>
+int dwk_launch(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int B, int H, int W, int Cg, bool flip, bool add,
+               cudaStream_t st) {
+  const long long total = (long long)B * H * W * Cg;
+  if (total == 0) return 0;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (!flip && !add) dwk_kernel<K, false, false><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
+  else if (!flip && add) dwk_kernel<K, false, true><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
+  else if (flip && !add) dwk_kernel<K, true, false><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
+  else dwk_kernel<K, true, true><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
+  return tcx_check_launch("bwd_dwk");
+}
+template <int K>
+int dwk_wgrad_launch(const float* g, int ldg, const float* x, int ldx, int B, int H, int W, int Cg, float* dw, float* db, float* part,
+                     cudaStream_t st) {
+  const long long M = (long long)B * H * W;
+  if (M == 0 || Cg == 0) return 0;
+  const int nblk = bwd_red_blocks(M);
+  const int rows = (int)((M + nblk - 1) / nblk + RL - 1) / RL * RL;
+  dwk_wgrad_kernel<K><<<dim3(nblk, cdiv(Cg, RC)), dim3(RC, RL), 0, st>>>(g, ldg, x, ldx, B, H, W, Cg, rows, part);
+  TCX_TRY(tcx_check_launch("bwd_dwk_wgrad"));
+  dwk_fold_kernel<<<cdiv((K * K + 1) * Cg, 256), 256, 0, st>>>(part, nblk, K * K, Cg, dw, db);
+  return tcx_check_launch("bwd_dwk_fold");
+}
+
+// out[b][i][j] = scale * sum_s part[b][s][i][j] inside the diagonal blocks of size Ch, 0 outside; outT = transposed copy
+__global__ void __launch_bounds__(256) fold_mask_kernel(const float* __restrict__ part, int S, int R, int Ch, float scale,
+                                                        float* __restrict__ out, float* __restrict__ outT) {
+  const int n = R * R;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n) return;
+  const int b = blockIdx.y, i = idx / R, j = idx - i * R;
+  float s = 0.f;
+  if (i / Ch == j / Ch) {
+    for (int k = 0; k < S; k++) s += part[((size_t)b * S + k) * n + idx];
+    s *= scale;
+  }
+  out[(size_t)b * n + idx] = s;
+  if (outT) outT[(size_t)b * n + (size_t)j * R + i] = s;
+}
+
+// dq = scale * dqfa + dxo * convv  -> dqkv[:, 0:C];   dconvv = dxo * q  (in place over convv)
+__global__ void __launch_bounds__(256) mb_dq_kernel(const float* __restrict__ dxo, const float* __restrict__ dqfa, float* __restrict__ convv,
+                                                    const float* __restrict__ q, int ldq, float scale, long long M, int C,
+                                                    float* __restrict__ dq, int ldo) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= M * C) return;
+  const long long r = idx / C;
+  const int c = (int)(idx - r * C);
+  const float g = dxo[idx];
+  dq[r * ldo + c] = fmaf(scale, dqfa[idx], g * convv[idx]);
+  convv[idx] = g * q[r * ldq + c];
+}
+
+constexpr int CHUNK = 128;
+// column softmax over the N tokens of each image (k rows of pitch ld): chunk partials, then P [B*N][C]
+__global__ void __launch_bounds__(RC * RL) kstats32_kernel(const float* __restrict__ k, int ld, int N, int C, float* __restrict__ pm,
+                                                           float* __restrict__ ps) {
+  __shared__ float sm[RL][RC];
+  __shared__ float bm[RC];
+  const int c = blockIdx.z * RC + threadIdx.x;
+  const int b = blockIdx.y, chunks = gridDim.x;
+  const int r0 = blockIdx.x * CHUNK, r1 = min(r0 + CHUNK, N);
+  const float* kb = k + (size_t)b * N * ld;
+  float m = -INFINITY;
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += RL) m = fmaxf(m, kb[(size_t)r * ld + c]);
+  sm[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int l = 1; l < RL; l++) m = fmaxf(m, sm[l][threadIdx.x]);
+    bm[threadIdx.x] = m;
+  }
+  __syncthreads();
+  m = bm[threadIdx.x];
+  float acc = 0.f;
+  if (c < C)
+    for (int r = r0 + threadIdx.y; r < r1; r += RL) acc += expf(kb[(size_t)r * ld + c] - m);
+  __syncthreads();
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = sm[0][threadIdx.x];
+    for (int l = 1; l < RL; l++) s += sm[l][threadIdx.x];
+    pm[((size_t)b * chunks + blockIdx.x) * C + c] = m;
+    ps[((size_t)b * chunks + blockIdx.x) * C + c] = s;
+  }
+}
+__global__ void __launch_bounds__(RC * RL) ksoftmax32_kernel(const float* __restrict__ k, int ld, int N, int C, const float* __restrict__ pm,
+                                                             const float* __restrict__ ps, float* __restrict__ P) {
+  const int c = blockIdx.z * RC + threadIdx.x;
+  if (c >= C) return;
+  const int b = blockIdx.y, chunks = gridDim.x;
+  float m = -INFINITY;
+  for (int j = 0; j < chunks; j++) m = fmaxf(m, pm[((size_t)b * chunks + j) * C + c]);
+  float sum = 0.f;
+  for (int j = 0; j < chunks; j++) sum += ps[((size_t)b * chunks + j) * C + c] * expf(pm[((size_t)b * chunks + j) * C + c] - m);
+  const float inv = 1.0f / sum;
+  const int r0 = blockIdx.x * CHUNK, r1 = min(r0 + CHUNK, N);
+  for (int r = r0 + threadIdx.y; r < r1; r += RL) {
+    const size_t row = (size_t)b * N + r;
+    P[row * C + c] = expf(k[row * ld + c] - m) * inv;
+  }
+}
+
+}  // namespace
+
+int launch_bwd_dwk(int K, const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int B, int H, int W, int Cg, int flip,
+                   int add, cudaStream_t st) {
+  if (K == 3) return dwk_launch<3>(x, ldx, w, b, y, ldy, B, H, W, Cg, flip, add, st);
+  if (K == 5) return dwk_launch<5>(x, ldx, w, b, y, ldy, B, H, W, Cg, flip, add, st);
+  if (K == 7) return dwk_launch<7>(x, ldx, w, b, y, ldy, B, H, W, Cg, flip, add, st);
+  tcx_set_error("bwd_dwk: window %d not built (3, 5, 7)", K);
+  return -1;
+}
+size_t bwd_dwk_wgrad_part_floats(int K, long long M, int Cg) { return (size_t)bwd_red_blocks(M) * (K * K + 1) * Cg; }
+int launch_bwd_dwk_wgrad(int K, const float* g, int ldg, const float* x, int ldx, int B, int H, int W, int Cg, float* dw, float* db,
+                         float* part, cudaStream_t st) {
+  if (K == 3) return dwk_wgrad_launch<3>(g, ldg, x, ldx, B, H, W, Cg, dw, db, part, st);
+  if (K == 5) return dwk_wgrad_launch<5>(g, ldg, x, ldx, B, H, W, Cg, dw, db, part, st);
+  if (K == 7) return dwk_wgrad_launch<7>(g, ldg, x, ldx, B, H, W, Cg, dw, db, part, st);
+  tcx_set_error("bwd_dwk_wgrad: window %d not built (3, 5, 7)", K);
+  return -1;
+}
+int launch_bwd_fold_mask(const float* part, int batch, int S, int R, int Ch, float scale, float* out, float* outT, cudaStream_t st) {
+  if (batch == 0 || R == 0) return 0;
+  fold_mask_kernel<<<dim3(cdiv(R * R, 256), batch), 256, 0, st>>>(part, S, R, Ch, scale, out, outT);
+  return tcx_check_launch("bwd_fold_mask");
+}
+int launch_mb_bwd_dq(const float* dxo, const float* dqfa, float* convv, const float* q, int ldq, float scale, long long M, int C, float* dq,
+                     int ldo, cudaStream_t st) {
+  if (M == 0) return 0;
+  mb_dq_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(dxo, dqfa, convv, q, ldq, scale, M, C, dq, ldo);
+  return tcx_check_launch("mb_bwd_dq");
+}
+int launch_bwd_ksoftmax32(const float* k, int ld, int B, int N, int C, float* pm, float* ps, float* P, cudaStream_t st) {
+  if (B == 0 || N == 0) return 0;
+  const dim3 grid(cdiv(N, CHUNK), B, cdiv(C, RC)), block(RC, RL);
+  kstats32_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps);
+  TCX_TRY(tcx_check_launch("bwd_kstats32"));
+  ksoftmax32_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps, P);
+  return tcx_check_launch("bwd_ksoftmax32");
+}

@@ -84,6 +84,8 @@ class DWConv(nn.Module):
 
     def forward(self, x, H, W):
         B, N, C = x.shape
+        if _recording(x, self.dwconv.weight):
+            return tcx_autograd.dwconv_tokens(x, H, W, self.dwconv.weight, self.dwconv.bias, False)
         return ops.dwconv_tokens(x.contiguous(), H, W, self.dwconv.weight, self.dwconv.bias, add_input=False)
 
 
@@ -421,6 +423,8 @@ class ConvPosEnc(nn.Module):
 
     def forward(self, x, size):
         H, W = size
+        if _recording(x, self.proj.weight):
+            return tcx_autograd.dwconv_tokens(x, H, W, self.proj.weight, self.proj.bias, True)
         return ops.dwconv_tokens(x.contiguous(), H, W, self.proj.weight, self.proj.bias, add_input=True)
 
 
@@ -469,6 +473,10 @@ class FactorAtt_ConvRelPosEnc(nn.Module):
 
     def forward(self, x, size):
         H, W = size
+        if _recording(x, self.qkv.weight):
+            heads, _, qkvw, qkvb, cw, cb, splits, pw, pb = self.args()
+            ops._check_crpe(splits, cw, heads)
+            return tcx_autograd.factor_att(x, H, W, heads, qkvw, qkvb, cw, cb, pw, pb)
         return ops.mb_factor_attn(x.contiguous(), H, W, *self.args(), residual=None)
 
 
@@ -485,6 +493,13 @@ class MHCABlock(nn.Module):
         self.norm2 = nn.LayerNorm(dim, eps=1e-6)
 
     def forward(self, x, size):
+        if _recording(x, self.norm1.weight):
+            # training row (MSTr.py:935-946): position-encoding conv, attention and Mix-FFN are autograd nodes on the
+            # library's kernels; the two residual additions are ATen adds
+            n1, n2 = self.norm1, self.norm2
+            x = self.cpe(x, size)
+            x = x + self.factoratt_crpe(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps), size)
+            return x + self.mlp(tcx_autograd.layernorm(x, n2.weight, n2.bias, n2.eps), size[0], size[1])
         return ops.mhca_blocks(x.contiguous().unsqueeze(0), size[0], size[1], [[self]])[0]
 
 
@@ -503,6 +518,10 @@ class MHCAEncoder(nn.Module):
     def forward(self, x, size):
         H, W = size
         B = x.shape[0]
+        if _recording(x, self.cpe.proj.weight):
+            for blk in self.MHCA_layers:
+                x = blk(x, size)
+            return _as_nchw(x.reshape(B, H, W, -1))
         y = ops.mhca_blocks(x.contiguous().unsqueeze(0), H, W, [list(self.MHCA_layers)])[0]
         return _as_nchw(y.view(B, H, W, -1))
 

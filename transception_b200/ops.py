@@ -97,6 +97,10 @@ _PROTOS = {
     "tcx_eff_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_eff_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_eff_attn_bwd": (_i, [_vp, _pp, _vp, _vp, _pp, _i, _i, _i, _vp, _vp]),
+    "tcx_mb_factor_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_mb_factor_attn_bwd": (_i, [_vp, _vp, _pp, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_dwconv_tokens_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tcx_dwconv_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -352,7 +356,8 @@ def mixffn_skip(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, resid
     return y
 
 
-def mb_factor_attn(xn, H, W, heads, scale, qkvw, qkvb, crpe_w, crpe_b, head_splits, projw, projb, residual=None):
+def mb_factor_attn(xn, H, W, heads, scale, qkvw, qkvb, crpe_w, crpe_b, head_splits, projw, projb, residual=None,
+                   keep_ws=False):
     require_cuda(xn)
     lib = load_library()
     B, N, C = xn.shape
@@ -361,6 +366,8 @@ def mb_factor_attn(xn, H, W, heads, scale, qkvw, qkvb, crpe_w, crpe_b, head_spli
     ws = _ws(lib.tcx_mb_factor_attn_workspace_bytes(B, N, C), xn)
     tab = _table([qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2], projw, projb])
     _chk(lib.tcx_mb_factor_attn_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, H, W, C, heads, _ptr(ws), _stream()))
+    if keep_ws:
+        return y, ws
     return y
 
 
@@ -904,3 +911,34 @@ def eff_attn_bwd(dy, saved, kw, kb, qw, qb, vw, vb, rw, rb, need_dx=True):
     ws = _ws(lib.tcx_eff_attn_bwd_workspace_bytes(B, N, C), dy)
     _chk(lib.tcx_eff_attn_bwd(_ptr(dy), tab, _ptr(saved), _ptr(dxn), gtab, B, N, C, _ptr(ws), _stream()))
     return dxn, grads
+
+
+def mb_factor_attn_bwd(dy, xn, fwd_ws, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb, need_dx=True):
+    """(dxn, [10 parameter gradients in slot order]) of FactorAtt_ConvRelPosEnc; fwd_ws = mb_factor_attn(..., keep_ws=True)[1]."""
+    require_cuda(dy)
+    lib = load_library()
+    dy, xn = dy.contiguous(), xn.contiguous()
+    B, N, C = dy.shape
+    params = [qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2], projw, projb]
+    grads = [torch.empty_like(p) for p in params]
+    dxn = torch.empty_like(dy) if need_dx else None
+    tab = _table(params)
+    gtab = (ctypes.c_void_p * 10)(*[_ptr(g) for g in grads])
+    ws = _ws(lib.tcx_mb_factor_attn_bwd_workspace_bytes(B, N, C), dy)
+    _chk(lib.tcx_mb_factor_attn_bwd(_ptr(dy), _ptr(xn), tab, _ptr(fwd_ws), _ptr(dxn), gtab, B, H, W, C, heads, _ptr(ws), _stream()))
+    return dxn, grads
+
+
+def dwconv_tokens_bwd(x, H, W, w, dy, add_input, need_dx=True):
+    """(dx, dw, db) of y = dw3x3(x) + b (+ x) on tokens x [B, H*W, C]."""
+    require_cuda(dy)
+    lib = load_library()
+    x, dy = x.contiguous(), dy.contiguous()
+    B, N, C = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    db = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = _ws(lib.tcx_dwconv_tokens_bwd_workspace_bytes(B, H, W, C), x)
+    _chk(lib.tcx_dwconv_tokens_bwd(_ptr(x), _ptr(_d(w)), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), B, H, W, C, int(add_input), _ptr(ws),
+                                   _stream()))
+    return dx, dw, db
