@@ -11,7 +11,7 @@ namespace {
 
 constexpr int RED_COLS = 64;     // columns per block
 constexpr int RED_LANES = 4;     // row lanes per block
-constexpr int RED_MAX_BLOCKS = 592;   // 4 x 148
+constexpr int RED_MAX_BLOCKS = 296;   // 2 x 148 row blocks (x C/64 column groups)
 
 inline int red_rows_per_block(long long M) {
   long long r = (M + RED_MAX_BLOCKS - 1) / RED_MAX_BLOCKS;
@@ -52,11 +52,9 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_colsum_kernel(const 
 
 // out[i] = sum_s part[s*n + i]
 __global__ void __launch_bounds__(256) bwd_fold_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int k = 0; k < S; k++) s += part[(size_t)k * n + i];
-  out[i] = s;
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  const float s = bwd_fold_sum(part, S, n, i, i < n);
+  if (threadIdx.y == 0 && i < n) out[i] = s;
 }
 
 // d/dz GELU_erf(z) = Phi(z) + z phi(z)
@@ -168,10 +166,9 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_ln_cols_kernel(const
 // partials [nblk][2][C] -> dgamma, dbeta
 __global__ void __launch_bounds__(256) bwd_ln_fold_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= 2 * C) return;
-  float s = 0.f;
-  for (int k = 0; k < nblk; k++) s += part[(size_t)k * 2 * C + i];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const float s = bwd_fold_sum(part, nblk, 2 * C, i, i < 2 * C);
+  if (threadIdx.y != 0 || i >= 2 * C) return;
   if (i < C) dgamma[i] = s; else dbeta[i - C] = s;
 }
 
@@ -215,11 +212,10 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_dw_wgrad_kernel(cons
 // partials [nblk][10][C] -> dw [C][9], db [C]
 __global__ void __launch_bounds__(256) bwd_dw_fold_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dw,
                                                           float* __restrict__ db) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= 10 * C) return;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const float s = bwd_fold_sum(part, nblk, 10 * C, i, i < 10 * C);
+  if (threadIdx.y != 0 || i >= 10 * C) return;
   const int t = i / C, c = i - t * C;
-  float s = 0.f;
-  for (int k = 0; k < nblk; k++) s += part[(size_t)k * 10 * C + i];
   if (t < 9) dw[c * 9 + t] = s; else if (db) db[c] = s;
 }
 
@@ -387,7 +383,7 @@ int bwd_red_blocks(long long M) {
 
 int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st) {
   if (n == 0) return 0;
-  bwd_fold_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, S, n, out);
+  bwd_fold_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 8), 0, st>>>(part, S, n, out);
   return tcx_check_launch("bwd_fold");
 }
 
@@ -425,7 +421,7 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
     else bwd_ln_cols_kernel<false><<<grid, block, 0, st>>>(u, dz, gamma, beta, stats, M, C, rows, part);
     TCX_TRY(tcx_check_launch("bwd_ln_cols"));
   }
-  bwd_ln_fold_kernel<<<cdiv(2 * C, 256), 256, 0, st>>>(part, nblk, C, dgamma, dbeta);
+  bwd_ln_fold_kernel<<<cdiv(2 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dgamma, dbeta);
   return tcx_check_launch("bwd_ln_fold");
 }
 
@@ -439,7 +435,7 @@ int launch_bwd_dwconv_wgrad(const float* du, const __half* h, int B, int H, int 
     bwd_dw_wgrad_kernel<<<dim3(nblk, cdiv(C, RED_COLS)), dim3(RED_COLS, RED_LANES), 0, st>>>(du, h, B, H, W, C, rows, part);
     TCX_TRY(tcx_check_launch("bwd_dw_wgrad"));
   }
-  bwd_dw_fold_kernel<<<cdiv(10 * C, 256), 256, 0, st>>>(part, nblk, C, dw, db);
+  bwd_dw_fold_kernel<<<cdiv(10 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dw, db);
   return tcx_check_launch("bwd_dw_fold");
 }
 

@@ -6,6 +6,34 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 
+#ifdef __CUDACC__
+// Ordered fold of S partials per output element by a (32 x 8) block: lane row y sums partials y, y+8, ... in order, then the
+// eight row sums are added in row order — a fixed association, so the result is bit-reproducible, and the S loads of one
+// element are spread over 8 threads with 4 independent loads in flight each (a single thread walking 592 partials is a
+// 592-deep dependent-latency chain).  Valid on threadIdx.y == 0.
+__device__ __forceinline__ float bwd_fold_sum(const float* __restrict__ part, int S, long long n, long long i, bool live) {
+  __shared__ float sm[8][33];
+  float a = 0.f;
+  if (live) {
+    int k = threadIdx.y;
+    for (; k + 24 < S; k += 32) {
+      const float v0 = part[(size_t)k * n + i], v1 = part[(size_t)(k + 8) * n + i];
+      const float v2 = part[(size_t)(k + 16) * n + i], v3 = part[(size_t)(k + 24) * n + i];
+      a += v0; a += v1; a += v2; a += v3;
+    }
+    for (; k < S; k += 8) a += part[(size_t)k * n + i];
+  }
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) s += sm[l][threadIdx.x];
+  }
+  return s;
+}
+#endif
+
 // rows handled by one block of the token reductions; the partial buffers below are sized with it
 int bwd_red_blocks(long long M);
 

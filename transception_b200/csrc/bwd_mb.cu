@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(RC * RL) dwk_wgrad_kernel(const float* __restr
 // partials [nblk][KK + 1][Cg] -> dw [Cg][KK], db [Cg] (db may be null)
 __global__ void __launch_bounds__(256) dwk_fold_kernel(const float* __restrict__ part, int nblk, int KK, int Cg, float* __restrict__ dw,
                                                        float* __restrict__ db) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= (KK + 1) * Cg) return;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int n = (KK + 1) * Cg;
+  const float s = bwd_fold_sum(part, nblk, n, i, i < n);
+  if (threadIdx.y != 0 || i >= n) return;
   const int t = i / Cg, c = i - t * Cg;
-  float s = 0.f;
-  for (int k = 0; k < nblk; k++) s += part[(size_t)k * (KK + 1) * Cg + i];
   if (t < KK) dw[(size_t)c * KK + t] = s; else if (db) db[c] = s;
 }
 
@@ -113,7 +113,7 @@ int dwk_wgrad_launch(const float* g, int ldg, const float* x, int ldx, int B, in
   const int rows = (int)((M + nblk - 1) / nblk + RL - 1) / RL * RL;
   dwk_wgrad_kernel<K><<<dim3(nblk, cdiv(Cg, RC)), dim3(RC, RL), 0, st>>>(g, ldg, x, ldx, B, H, W, Cg, rows, part);
   TCX_TRY(tcx_check_launch("bwd_dwk_wgrad"));
-  dwk_fold_kernel<<<cdiv((K * K + 1) * Cg, 256), 256, 0, st>>>(part, nblk, K * K, Cg, dw, db);
+  dwk_fold_kernel<<<cdiv((K * K + 1) * Cg, 32), dim3(32, 8), 0, st>>>(part, nblk, K * K, Cg, dw, db);
   return tcx_check_launch("bwd_dwk_fold");
 }
 
