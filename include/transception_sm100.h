@@ -295,6 +295,21 @@ size_t tcx_dwconv_tokens_bwd_workspace_bytes(int B, int H, int W, int C);
 int tcx_dwconv_tokens_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int B, int H, int W, int C,
                           int add_input, void* ws, void* stream);
 
+/* Backward of the bridge attention core out = softmax(q k^T * scale) v (MSTr.py:2281-2285; forward: tcx_flash_attn_fwd).
+ * q, dout [B][Nq][64], kv [B][Nk][128] (k | v) -> dq [B][Nq][64], dkv [B][Nk][128].  The probabilities are recomputed from q
+ * and k as a batched tcgen05 GEMM (fp32 scores in ws), every contraction of the backward is a tcgen05 GEMM. */
+size_t tcx_attn_core_bwd_workspace_bytes(int B, int Nq, int Nk);
+int tcx_attn_core_bwd(const float* q, const float* kv, const float* dout, float scale, float* dq, float* dkv, int B, int Nq, int Nk,
+                      void* ws, void* stream);
+
+/* Efficient-attention core on given fp32 token-major K, Q, V [B][N][C]: out = softmax_channels(Q) (softmax_tokens(K)^T V).
+ * With K, Q, V the transposed raw [C][N] re-readings of the k / q / v projections this is M_EfficientChannelAtten.forward
+ * between its Linear layers (MSTr.py:2312-2353).  Backward recomputes the two softmaxes and the context. */
+size_t tcx_ea_core_workspace_bytes(int B, int N, int C);
+int tcx_ea_core_fwd(const float* k, const float* q, const float* v, float* out, int B, int N, int C, void* ws, void* stream);
+int tcx_ea_core_bwd(const float* k, const float* q, const float* v, const float* dout, float* dk, float* dq, float* dv, int B, int N,
+                    int C, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

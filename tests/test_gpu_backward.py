@@ -324,3 +324,85 @@ def test_mhca_encoder_backward(cuda_lib, B, H, W, C, L):
     x = _rand(B, H * W, C, seed=2)
     dy = _rand(B, C, H, W, seed=3, scale=1e-3)
     _grad_parity(m, "e", lambda sd, xr: O.mhca_encoder(sd, "e", xr, H, W, L), x, dy)
+
+
+@pytest.mark.parametrize("B,Nq,Nk", [(2, 300, 64), (1, 6076, 784), (2, 1000, 200)])
+def test_attention_core_backward(cuda_lib, B, Nq, Nk):
+    """softmax(q k^T / 8) v of M_EfficientSelfAtten (MSTr.py:2281-2285): flash forward, GEMM-recompute backward."""
+    from transception_b200 import autograd as A
+    q = _rand(B, Nq, 64, seed=1)
+    kv = _rand(B, Nk, 128, seed=2)
+    dy = _rand(B, Nq, 64, seed=3, scale=1e-3)
+    qr, kvr = q.clone().requires_grad_(), kv.clone().requires_grad_()
+    want = ((qr @ kvr[..., :64].transpose(1, 2)) * 0.125).softmax(-1) @ kvr[..., 64:]
+    want.backward(dy)
+    qg, kvg = q.cuda().requires_grad_(), kv.cuda().requires_grad_()
+    got = A.attn_core(qg, kvg, 0.125)
+    assert (got.cpu() - want.detach()).abs().max().item() <= 2e-2
+    got.backward(dy.cuda())
+    _check(qg.grad, qr.grad, 1e-2, "attn dq")
+    _check(kvg.grad, kvr.grad, 1e-2, "attn dkv")
+    a, b = qg.grad.clone(), kvg.grad.clone()
+    qg.grad = kvg.grad = None
+    A.attn_core(qg, kvg, 0.125).backward(dy.cuda())
+    assert torch.equal(a, qg.grad) and torch.equal(b, kvg.grad)
+
+
+def _bridge_layer(ch_att, seed=21):
+    from networks.MSTr import BridgLayer_4
+    torch.manual_seed(seed)
+    return _randomise(BridgLayer_4(64, 1, [1, 2, 4, 8], ch_att))
+
+
+@pytest.mark.parametrize("ch_att", [True, False])
+@pytest.mark.parametrize("S", [56, 32])
+def test_bridge_attention_backward(cuda_lib, ch_att, S):
+    """M_EfficientChannelAtten (MSTr.py:2309-2353) / M_EfficientSelfAtten + Scale_reduce (:2267-2292, :2225-2249)."""
+    m = _bridge_layer(ch_att).attn
+    ntok = S * S * 31 // 16
+    x = _rand(1, ntok, 64, seed=4)
+    dy = _rand(1, ntok, 64, seed=5, scale=1e-3)
+    fn = O.bridge_channel_atten if ch_att else O.bridge_self_atten
+    checked = _grad_parity(m, "a", lambda sd, xr: fn(sd, "a", xr), x, dy)
+    assert len(checked) == (8 if ch_att else 6 + 8)      # the channel attention's scale_reduce is dead (MSTr.py:2306-2307)
+
+
+@pytest.mark.parametrize("ch_att", [True, False])
+def test_bridge_layer_backward(cuda_lib, ch_att):
+    """BridgLayer_4 (MSTr.py:2373-2409) on the 224x224 token buffer [B, 6076, 64]."""
+    m = _bridge_layer(ch_att)
+    x = _rand(2, 6076, 64, seed=6)
+    dy = _rand(2, 6076, 64, seed=7, scale=1e-3)
+    _grad_parity(m, "l", lambda sd, xr: O.bridge_layer(sd, "l", xr, ch_att), x, dy)
+
+
+def test_bridge_block_backward(cuda_lib):
+    """BridgeBlock_4 (MSTr.py:2422-2442): four maps in, four maps out, gradients w.r.t. every map and parameter."""
+    from networks.MSTr import BridgeBlock_4
+    torch.manual_seed(3)
+    m = _randomise(BridgeBlock_4(64, 1, [1, 2, 4, 8], [True, False, False, False]))
+    shapes = [(64, 56), (128, 28), (320, 14), (512, 7)]
+    maps = [_rand(1, c, h, h, seed=10 + i) for i, (c, h) in enumerate(shapes)]
+    dys = [_rand(1, c, h, h, seed=20 + i, scale=1e-3) for i, (c, h) in enumerate(shapes)]
+    sd = {"b." + k: v.clone().requires_grad_() for k, v in m.state_dict().items()}
+    mr = [t.clone().requires_grad_() for t in maps]
+    want = O.bridge_block(sd, "b", mr)
+    torch.autograd.backward(want, dys)
+    mg = m.cuda().train()
+    xg = [t.cuda().requires_grad_() for t in maps]
+    got = mg(xg)
+    for g_, w_ in zip(got, want):
+        assert (g_.float().cpu() - w_.detach()).abs().max().item() <= 2e-2 * max(1.0, w_.abs().max().item())
+    torch.autograd.backward(got, [d.cuda() for d in dys])
+    floor = 1e-6 * sum(d.norm().item() for d in dys)
+    for i in range(4):
+        _check(xg[i].grad, mr[i].grad, 1e-2, "d map %d" % i)
+    n = 0
+    for k, p in mg.named_parameters():
+        ref = sd["b." + k].grad
+        if ref is None:
+            assert p.grad is None, k
+            continue
+        _check(p.grad, ref, 1e-2, "d " + k, floor)
+        n += 1
+    assert n > 150

@@ -124,6 +124,45 @@ def dwconv_tokens(x, H, W, w, b, add_input):
     return DwConvTokensFn.apply(x, H, W, w, b, add_input)
 
 
+class AttnCoreFn(torch.autograd.Function):
+    """softmax(q k^T * scale) v of M_EfficientSelfAtten (MSTr.py:2281-2285): tcgen05 flash kernel forward, GEMM-recompute backward."""
+
+    @staticmethod
+    def forward(ctx, q, kv, scale):
+        ctx.save_for_backward(q, kv)
+        ctx.scale = scale
+        return ops.flash_attn(q.contiguous(), kv.contiguous(), scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv = ctx.saved_tensors
+        dq, dkv = ops.attn_core_bwd(q, kv, dout, ctx.scale)
+        return dq, dkv, None
+
+
+class EaCoreFn(torch.autograd.Function):
+    """softmax_channels(q) @ (softmax_tokens(k)^T v): the core of M_EfficientChannelAtten (MSTr.py:2316-2349) on the
+    transposed raw re-readings of its k / q / v projections."""
+
+    @staticmethod
+    def forward(ctx, k, q, v):
+        ctx.save_for_backward(k, q, v)
+        return ops.ea_core(k, q, v)
+
+    @staticmethod
+    def backward(ctx, dout):
+        k, q, v = ctx.saved_tensors
+        return ops.ea_core_bwd(k, q, v, dout)
+
+
+def ea_core(k, q, v):
+    return EaCoreFn.apply(k, q, v)
+
+
+def attn_core(q, kv, scale):
+    return AttnCoreFn.apply(q, kv, scale)
+
+
 def layernorm(x, w, b, eps):
     return LayerNormFn.apply(x, w, b, eps)
 

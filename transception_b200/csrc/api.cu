@@ -1609,6 +1609,88 @@ MixSaved mix_saved(void* base, long long M, int C, int C4) {
 
 }  // namespace
 
+// ---- efficient-attention core on given fp32 token-major K, Q, V [B][N][C] (the reinterpreted tensors of M_EfficientChannelAtten,
+// MSTr.py:2312-2353): ctx = softmax_tokens(K)^T V, att = softmax_channels(Q) ctx ----
+namespace {
+struct EaCorePlan { int S, Ms; size_t bnc, bcc, pack, ch; };
+EaCorePlan ea_core_plan(int B, int N, int C) {
+  EaCorePlan p;
+  bwd_wgrad_splits(N, C, C, &p.S, &p.Ms);
+  p.bnc = (size_t)B * N * C; p.bcc = (size_t)B * C * C;
+  p.pack = (size_t)B * p.S * C * p.Ms; p.ch = (size_t)B * ea_bwd_chunks(N) * C;
+  return p;
+}
+struct EaCoreBufs { float *P, *Qs, *ctx, *ctxT, *packA, *packB, *part, *pm, *ps; };
+size_t ea_core_common_floats(const EaCorePlan& p) {
+  return 2 * rnd(p.bnc) + 2 * rnd(p.bcc) + 2 * rnd(p.pack) + rnd(p.bcc * p.S) + 2 * rnd(p.ch);
+}
+EaCoreBufs ea_core_carve(Carver& c, const EaCorePlan& p) {
+  EaCoreBufs b;
+  b.P = c.take(p.bnc); b.Qs = c.take(p.bnc); b.ctx = c.take(p.bcc); b.ctxT = c.take(p.bcc);
+  b.packA = c.take(p.pack); b.packB = c.take(p.pack); b.part = c.take(p.bcc * p.S); b.pm = c.take(p.ch); b.ps = c.take(p.ch);
+  return b;
+}
+// out[b] = a[b]^T b_[b] over the N tokens of image b (C x C), outT transposed
+int ea_ctx_gemm(const float* a, const float* b_, int B, int N, int C, const EaCorePlan& p, const EaCoreBufs& w, float* out, float* outT,
+                cudaStream_t st) {
+  TCX_TRY(launch_bwd_packT_batched_f32(a, B, N, C, C, p.S, p.Ms, p.Ms, w.packA, st));
+  TCX_TRY(launch_bwd_packT_batched_f32(b_, B, N, C, C, p.S, p.Ms, p.Ms, w.packB, st));
+  GemmParams g = gemm1(w.packA, w.packB, w.part, C, C, p.Ms);
+  g.batch = B * p.S; g.strideA = (long long)C * p.Ms; g.strideW = (long long)C * p.Ms; g.strideC = (long long)C * C;
+  TCX_TRY(launch_gemm(g, st));
+  return launch_bwd_fold_mask(w.part, B, p.S, C, C, 1.0f, out, outT, st);
+}
+// out[b] (N x C) = a[b] (N x C) w[b]^T
+int ea_tok_gemm(const float* a, const float* w, float* out, int B, int N, int C, cudaStream_t st) {
+  GemmParams g = gemm1(a, w, out, N, C, C);
+  g.batch = B; g.strideA = (long long)N * C; g.strideW = (long long)C * C; g.strideC = (long long)N * C;
+  return launch_gemm(g, st);
+}
+int ea_core_recompute(const float* k, const float* q, const float* v, int B, int N, int C, const EaCorePlan& p, const EaCoreBufs& w,
+                      cudaStream_t st) {
+  TCX_TRY(launch_bwd_ksoftmax32(k, C, B, N, C, w.pm, w.ps, w.P, st));
+  TCX_TRY(launch_bwd_rowsoftmax_fwd(q, C, (long long)B * N, C, 1.0f, w.Qs, C, st));
+  return ea_ctx_gemm(w.P, v, B, N, C, p, w, w.ctx, w.ctxT, st);
+}
+}  // namespace
+
+extern "C" {
+size_t tcx_ea_core_workspace_bytes(int B, int N, int C) {
+  const EaCorePlan p = ea_core_plan(B, N, C);
+  return 4 * (ea_core_common_floats(p) + 2 * rnd(p.bnc) + 2 * rnd(p.bcc) + rnd(p.ch) + 1024);
+}
+int tcx_ea_core_fwd(const float* k, const float* q, const float* v, float* out, int B, int N, int C, void* ws, void* stream) {
+  TCX_REQUIRE(k && q && v && out && ws, "ea_core_fwd: null pointer");
+  TCX_REQUIRE(C % 4 == 0 && C >= 16, "ea_core: C must be a multiple of 4, >= 16 (got %d)", C);
+  const EaCorePlan p = ea_core_plan(B, N, C);
+  Carver c(ws);
+  const EaCoreBufs w = ea_core_carve(c, p);
+  TCX_TRY(ea_core_recompute(k, q, v, B, N, C, p, w, S(stream)));
+  return ea_tok_gemm(w.Qs, w.ctxT, out, B, N, C, S(stream));              // att = Qs ctx
+}
+int tcx_ea_core_bwd(const float* k, const float* q, const float* v, const float* dout, float* dk, float* dq, float* dv, int B, int N,
+                    int C, void* ws, void* stream) {
+  TCX_REQUIRE(k && q && v && dout && dk && dq && dv && ws, "ea_core_bwd: null pointer");
+  TCX_REQUIRE(C % 4 == 0 && C >= 16, "ea_core: C must be a multiple of 4, >= 16 (got %d)", C);
+  cudaStream_t st = S(stream);
+  const EaCorePlan p = ea_core_plan(B, N, C);
+  Carver c(ws);
+  const EaCoreBufs w = ea_core_carve(c, p);
+  float* dQs = c.take(p.bnc);
+  float* dP = c.take(p.bnc);
+  float* dctx = c.take(p.bcc);
+  float* dctxT = c.take(p.bcc);
+  float* sp = c.take(p.ch);
+  TCX_TRY(ea_core_recompute(k, q, v, B, N, C, p, w, st));
+  TCX_TRY(ea_tok_gemm(dout, w.ctx, dQs, B, N, C, st));                    // dQs = dout ctx^T
+  TCX_TRY(launch_bwd_rowsoftmax_bwd(w.Qs, C, dQs, C, (long long)B * N, C, 1.0f, dq, C, st));
+  TCX_TRY(ea_ctx_gemm(w.Qs, dout, B, N, C, p, w, dctx, dctxT, st));       // dctx = Qs^T dout
+  TCX_TRY(ea_tok_gemm(w.P, dctxT, dv, B, N, C, st));                      // dv = P dctx
+  TCX_TRY(ea_tok_gemm(v, dctx, dP, B, N, C, st));                         // dP = v dctx^T
+  return launch_bwd_colsoftmax(w.P, dP, B, N, C, sp, dk, C, st);
+}
+}  // extern "C"
+
 extern "C" {
 
 size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C) { return 4 * (rnd(2 * (size_t)M) + rnd(2 * (size_t)bwd_red_blocks(M) * C) + 64); }
@@ -1846,6 +1928,66 @@ int tcx_dwconv_tokens_bwd(const float* x, const float* w, const float* dy, float
   }
   if (dw) TCX_TRY(launch_bwd_dwk_wgrad(3, dy, C, x, C, B, H, W, C, dw, db, reinterpret_cast<float*>(ws), st));
   return 0;
+}
+
+// ---- bridge attention core softmax(q k^T scale) v (MSTr.py:2281-2285) backward; forward = tcx_flash_attn_fwd ----
+static void attn_core_plan(int Nq, int Nk, int* S, int* Ms, int* Msk) {
+  bwd_wgrad_splits(Nq, Nk, 64, S, Ms);
+  *Msk = (Nk + 31) / 32 * 32;
+}
+size_t tcx_attn_core_bwd_workspace_bytes(int B, int Nq, int Nk) {
+  int S, Ms, Msk;
+  attn_core_plan(Nq, Nk, &S, &Ms, &Msk);
+  const size_t sc = (size_t)B * Nq * Nk;
+  return 4 * (2 * rnd(sc) + rnd((size_t)B * S * Nk * Ms) + rnd((size_t)B * S * 64 * Ms) + rnd((size_t)B * S * Nk * 64) +
+              rnd((size_t)B * 64 * Msk) + 64);
+}
+int tcx_attn_core_bwd(const float* q, const float* kv, const float* dout, float scale, float* dq, float* dkv, int B, int Nq, int Nk,
+                      void* ws, void* stream) {
+  TCX_REQUIRE(q && kv && dout && dq && dkv && ws, "attn_core_bwd: null pointer");
+  TCX_REQUIRE(Nk % 4 == 0 && Nk >= 16, "attn_core_bwd: Nk must be a multiple of 4 (got %d)", Nk);
+  cudaStream_t st = S(stream);
+  if (B == 0 || Nq == 0) return 0;
+  int SP, Ms, Msk;
+  attn_core_plan(Nq, Nk, &SP, &Ms, &Msk);
+  const size_t sc = (size_t)B * Nq * Nk;
+  Carver c(ws);
+  float* P = c.take(sc);           // scores -> probabilities
+  float* dS = c.take(sc);          // dP -> dS (scaled)
+  float* big = c.take((size_t)B * SP * Nk * Ms);     // P^T / dS^T, K-major over the query tokens, split-major
+  float* small = c.take((size_t)B * SP * 64 * Ms);   // dout^T / q^T
+  float* part = c.take((size_t)B * SP * Nk * 64);
+  float* kT = c.take((size_t)B * 64 * Msk);
+  const float* k = kv; const float* v = kv + 64;
+  const long long M = (long long)B * Nq;
+  auto scores = [&](const float* a, const float* w, float* out) -> int {      // out[b] (Nq x Nk) = a[b] (Nq x 64) w[b]^T, w rows of pitch 128
+    GemmParams g = gemm1(a, w, out, Nq, Nk, 64);
+    g.ldw = 128;
+    g.batch = B; g.strideA = (long long)Nq * 64; g.strideW = (long long)Nk * 128; g.strideC = (long long)Nq * Nk;
+    return launch_gemm(g, st);
+  };
+  auto over_queries = [&](const float* big_src, const float* small_src, float sc_, float* out) -> int {
+    // out[b] (Nk x 64, pitch 128) = sc_ * big_src[b]^T (Nk x Nq) small_src[b] (Nq x 64)
+    TCX_TRY(launch_bwd_packT_batched_f32(big_src, B, Nq, Nk, Nk, SP, Ms, Ms, big, st));
+    TCX_TRY(launch_bwd_packT_batched_f32(small_src, B, Nq, 64, 64, SP, Ms, Ms, small, st));
+    GemmParams g = gemm1(big, small, part, Nk, 64, Ms);
+    g.batch = B * SP; g.strideA = (long long)Nk * Ms; g.strideW = (long long)64 * Ms; g.strideC = (long long)Nk * 64;
+    TCX_TRY(launch_gemm(g, st));
+    return launch_bwd_fold_rows(part, B, SP, Nk, 64, sc_, out, 128, st);
+  };
+  TCX_TRY(scores(q, k, P));
+  TCX_TRY(launch_bwd_rowsoftmax_fwd(P, Nk, M, Nk, scale, P, Nk, st));
+  TCX_TRY(scores(dout, v, dS));                                         // dP = dout v^T
+  TCX_TRY(over_queries(P, dout, 1.0f, dkv + 64));                       // dv = P^T dout
+  TCX_TRY(launch_bwd_rowsoftmax_bwd(P, Nk, dS, Nk, M, Nk, scale, dS, Nk, st));
+  TCX_TRY(launch_bwd_packT_batched_f32(k, B, Nk, 64, 128, 1, Msk, Msk, kT, st));
+  {
+    GemmParams g = gemm1(dS, kT, dq, Nq, 64, Nk);                        // dq = dS k
+    g.ldw = Msk;
+    g.batch = B; g.strideA = (long long)Nq * Nk; g.strideW = (long long)64 * Msk; g.strideC = (long long)Nq * 64;
+    TCX_TRY(launch_gemm(g, st));
+  }
+  return over_queries(dS, q, 1.0f, dkv);                                // dk = dS^T q
 }
 
 size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4) { return 4 * mix_saved(nullptr, (long long)B * N, C, C4).floats; }

@@ -96,6 +96,13 @@ int launch_mb_bwd_dq(const float* dxo, const float* dqfa, float* convv, const fl
 // P [B*N][C] = softmax over the N tokens of each image of fp32 k rows (pitch ld); pm / ps: B*chunks*C floats each
 int launch_bwd_ksoftmax32(const float* k, int ld, int B, int N, int C, float* pm, float* ps, float* P, cudaStream_t st);
 
+// row softmax y = softmax(scale * x) over n elements per row, and its backward ds = scale * P (dP - sum P dP) (ds may alias dP)
+int launch_bwd_rowsoftmax_fwd(const float* x, int ld, long long M, int n, float scale, float* y, int ldy, cudaStream_t st);
+int launch_bwd_rowsoftmax_bwd(const float* P, int ldp, const float* dP, int ldd, long long M, int n, float scale, float* ds, int lds,
+                              cudaStream_t st);
+// out[b][r][c] (row pitch ldo) = scale * sum_s part[b][s][r][c], r < R, c < Cc
+int launch_bwd_fold_rows(const float* part, int batch, int S, int R, int Cc, float scale, float* out, int ldo, cudaStream_t st);
+
 // out[i] = sum_s part[s][i], i < n (split-K fold of the weight-gradient partials)
 int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st);
 

@@ -235,3 +235,65 @@ int launch_bwd_ksoftmax32(const float* k, int ld, int B, int N, int C, float* pm
   ksoftmax32_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps, P);
   return tcx_check_launch("bwd_ksoftmax32");
 }
+
+// ---- row softmax forward / backward (bridge attention scores MSTr.py:2281-2284; channel softmax of the queries :124-128) ----
+namespace {
+// one warp per row of n elements (pitch ld): y = softmax(scale * x)
+__global__ void __launch_bounds__(256) rowsoftmax_fwd_kernel(const float* __restrict__ x, int ld, long long M, int n, float scale,
+                                                             float* __restrict__ y, int ldy) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + row * ld;
+  float m = -INFINITY;
+  for (int c = lane; c < n; c += 32) m = fmaxf(m, xr[c]);
+  m = warp_max(m) * scale;
+  float s = 0.f;
+  for (int c = lane; c < n; c += 32) s += expf(fmaf(xr[c], scale, -m));
+  const float inv = 1.0f / warp_sum(s);
+  float* yr = y + row * ldy;
+  for (int c = lane; c < n; c += 32) yr[c] = expf(fmaf(xr[c], scale, -m)) * inv;
+}
+// ds = scale * P (dP - sum_c P dP)   (ds may alias dP)
+__global__ void __launch_bounds__(256) rowsoftmax_bwd_kernel(const float* __restrict__ P, int ldp, const float* dP, int ldd, long long M,
+                                                             int n, float scale, float* ds, int lds) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* pr = P + row * ldp;
+  const float* dr = dP + row * ldd;
+  float dot = 0.f;
+  for (int c = lane; c < n; c += 32) dot = fmaf(pr[c], dr[c], dot);
+  dot = warp_sum(dot);
+  float* o = ds + row * lds;
+  for (int c = lane; c < n; c += 32) o[c] = scale * pr[c] * (dr[c] - dot);
+}
+// out[(b*R + r)*ldo + c] = scale * sum_s part[((b*S + s)*R + r)*Cc + c]
+__global__ void __launch_bounds__(256) fold_rows_kernel(const float* __restrict__ part, int S, int R, int Cc, float scale,
+                                                        float* __restrict__ out, int ldo) {
+  const int n = R * Cc;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n) return;
+  const int b = blockIdx.y, r = idx / Cc, c = idx - r * Cc;
+  float s = 0.f;
+  for (int k = 0; k < S; k++) s += part[((size_t)b * S + k) * n + idx];
+  out[((size_t)b * R + r) * ldo + c] = s * scale;
+}
+}  // namespace
+
+int launch_bwd_rowsoftmax_fwd(const float* x, int ld, long long M, int n, float scale, float* y, int ldy, cudaStream_t st) {
+  if (M == 0) return 0;
+  rowsoftmax_fwd_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, ld, M, n, scale, y, ldy);
+  return tcx_check_launch("bwd_rowsoftmax_fwd");
+}
+int launch_bwd_rowsoftmax_bwd(const float* P, int ldp, const float* dP, int ldd, long long M, int n, float scale, float* ds, int lds,
+                              cudaStream_t st) {
+  if (M == 0) return 0;
+  rowsoftmax_bwd_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(P, ldp, dP, ldd, M, n, scale, ds, lds);
+  return tcx_check_launch("bwd_rowsoftmax_bwd");
+}
+int launch_bwd_fold_rows(const float* part, int batch, int S, int R, int Cc, float scale, float* out, int ldo, cudaStream_t st) {
+  if (batch == 0 || R == 0) return 0;
+  fold_rows_kernel<<<dim3(cdiv(R * Cc, 256), batch), 256, 0, st>>>(part, S, R, Cc, scale, out, ldo);
+  return tcx_check_launch("bwd_fold_rows");
+}

@@ -674,7 +674,26 @@ class Scale_reduce(nn.Module):
                 self.norm.weight, self.norm.bias, self.norm.eps)
 
     def forward(self, x):
+        if _recording(x, self.sr0.weight):
+            return self._forward_train(x)
         return ops.scale_reduce(x.contiguous(), *self.args())
+
+    def _forward_train(self, x):
+        """Training row (MSTr.py:2225-2249): each strided conv is a patch gather (a copy) + Linear node; the channel-group
+        packing `reshape(B, C, -1).permute(0, 2, 1)` of the NCHW conv output is a copy as well."""
+        B, ntok, C = x.shape
+        S = ops._bridge_side(ntok)
+        outs, off = [], 0
+        for conv, hw, mult in ((self.sr0, S, 1), (self.sr1, S // 2, 2), (self.sr2, S // 4, 5)):
+            n, r, cin = hw * hw * mult, conv.kernel_size[0], C * mult
+            t = x[:, off:off + n].reshape(B, hw // r, r, hw // r, r, cin).permute(0, 1, 3, 5, 2, 4)
+            t = t.reshape(B, (hw // r) ** 2, cin * r * r)
+            y = tcx_autograd.linear(t, conv.weight.reshape(cin, cin * r * r), conv.bias)       # NHWC conv output
+            outs.append(y.permute(0, 2, 1).reshape(B, C, -1).permute(0, 2, 1))
+            off += n
+        outs.append(x[:, off:])
+        n = self.norm
+        return tcx_autograd.layernorm(torch.cat(outs, dim=1), n.weight, n.bias, n.eps)
 
 
 class M_EfficientSelfAtten(nn.Module):
@@ -703,6 +722,12 @@ class M_EfficientSelfAtten(nn.Module):
                 sr.sr2.weight.reshape(320, -1), sr.sr2.bias, sr.norm.weight, sr.norm.bias]
 
     def forward(self, x, residual=None):
+        if _recording(x, self.q.weight):
+            # training row (MSTr.py:2267-2292): Linear / Scale_reduce / attention-core / Linear autograd nodes
+            q = tcx_autograd.linear(x, self.q.weight, self.q.bias)
+            kv = tcx_autograd.linear(self.scale_reduce(x), self.kv.weight, self.kv.bias)
+            y = tcx_autograd.linear(tcx_autograd.attn_core(q, kv, self.scale), self.proj.weight, self.proj.bias)
+            return y if residual is None else residual + y
         return ops.bridge_sr_attn(x.contiguous(), *self.args(), residual=residual)
 
 
@@ -729,6 +754,13 @@ class M_EfficientChannelAtten(nn.Module):
                 self.proj.weight, self.proj.bias]
 
     def forward(self, x, residual=None):
+        if _recording(x, self.q.weight):
+            # training row (MSTr.py:2309-2353): the raw [N, C] -> [C, N] re-reading followed by our token-major layout is a
+            # transposed copy; the attention core and the four Linear layers are autograd nodes on the library's kernels
+            B, N, C = x.shape
+            k, q, v = (tcx_autograd.linear(x, m.weight, m.bias).reshape(B, C, N).transpose(1, 2) for m in (self.k, self.q, self.v))
+            y = tcx_autograd.linear(tcx_autograd.ea_core(k, q, v), self.proj.weight, self.proj.bias)
+            return y if residual is None else residual + y
         return ops.eff_attn(x.contiguous(), self.k.weight, self.k.bias, self.q.weight, self.q.bias,
                             self.v.weight, self.v.bias, self.proj.weight, self.proj.bias,
                             residual=residual, reinterpret=True)
@@ -746,6 +778,9 @@ class BridgLayer_4(nn.Module):
         self.mixffn4 = MixFFN_skip(dims * 8, dims * 32)
 
     def forward(self, inputs):
+        first = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+        if _recording(first, self.norm1.weight):
+            return self._forward_train(inputs)
         if isinstance(inputs, (list, tuple)):
             # a C_k-channel NHWC pixel is C_k/64 consecutive 64-wide tokens
             inputs = ops.bridge_regroup([_nhwc(c) for c in inputs])
@@ -755,6 +790,32 @@ class BridgLayer_4(nn.Module):
                                 [m.args() for m in (self.mixffn1, self.mixffn2, self.mixffn3, self.mixffn4)])
 
 
+def _bridge_tokens_train(maps):
+    """NCHW maps -> [B, Ntok, 64] (MSTr.py:2380-2386): permuted copies."""
+    B = maps[0].shape[0]
+    return torch.cat([m.permute(0, 2, 3, 1).reshape(B, -1, 64) for m in maps], dim=1)
+
+
+def _bridge_layer_train(self, inputs):
+    """BridgLayer_4.forward (MSTr.py:2373-2409) as autograd nodes; slab slicing / concatenation and the two residual
+    additions are ATen copies / adds."""
+    x = _bridge_tokens_train(inputs) if isinstance(inputs, (list, tuple)) else inputs
+    B, ntok, C = x.shape
+    S = ops._bridge_side(ntok)
+    n1, n2 = self.norm1, self.norm2
+    tx1 = x + self.attn(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps))
+    tx = tcx_autograd.layernorm(tx1, n2.weight, n2.bias, n2.eps)
+    parts, off = [], 0
+    for mlp, hw, mult in ((self.mixffn1, S, 1), (self.mixffn2, S // 2, 2), (self.mixffn3, S // 4, 5), (self.mixffn4, S // 8, 8)):
+        n = hw * hw * mult
+        parts.append(mlp(tx[:, off:off + n].reshape(B, hw * hw, C * mult), hw, hw).reshape(B, n, C))
+        off += n
+    return tx1 + torch.cat(parts, dim=1)
+
+
+BridgLayer_4._forward_train = _bridge_layer_train
+
+
 class BridgeBlock_4(nn.Module):
     def __init__(self, dims, head, reduction_ratios, br_ch_att_list):
         super().__init__()
@@ -762,6 +823,12 @@ class BridgeBlock_4(nn.Module):
             setattr(self, 'bridge_layer%d' % (i + 1), BridgLayer_4(dims, head, reduction_ratios, br_ch_att_list[i]))
 
     def tokens(self, x):
+        first = x[0] if isinstance(x, (list, tuple)) else x
+        if _recording(first, self.bridge_layer1.norm1.weight):
+            t = _bridge_tokens_train(x) if isinstance(x, (list, tuple)) else x
+            for i in range(4):
+                t = getattr(self, 'bridge_layer%d' % (i + 1))(t)
+            return t
         if isinstance(x, (list, tuple)):
             x = ops.bridge_regroup([_nhwc(c) for c in x])
         layers = []

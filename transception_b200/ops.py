@@ -101,6 +101,11 @@ _PROTOS = {
     "tcx_mb_factor_attn_bwd": (_i, [_vp, _vp, _pp, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_dwconv_tokens_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_dwconv_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_attn_core_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_attn_core_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_ea_core_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_ea_core_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_ea_core_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -942,3 +947,40 @@ def dwconv_tokens_bwd(x, H, W, w, dy, add_input, need_dx=True):
     _chk(lib.tcx_dwconv_tokens_bwd(_ptr(x), _ptr(_d(w)), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), B, H, W, C, int(add_input), _ptr(ws),
                                    _stream()))
     return dx, dw, db
+
+
+def attn_core_bwd(q, kv, dout, scale):
+    """(dq, dkv) of out = softmax(q k^T * scale) v with kv = [k | v]."""
+    require_cuda(q)
+    lib = load_library()
+    q, kv, dout = q.contiguous(), kv.contiguous(), dout.contiguous()
+    B, Nq, d = q.shape
+    Nk = kv.shape[1]
+    assert d == 64 and kv.shape[2] == 128
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    ws = _ws(lib.tcx_attn_core_bwd_workspace_bytes(B, Nq, Nk), q)
+    _chk(lib.tcx_attn_core_bwd(_ptr(q), _ptr(kv), _ptr(dout), scale, _ptr(dq), _ptr(dkv), B, Nq, Nk, _ptr(ws), _stream()))
+    return dq, dkv
+
+
+def ea_core(k, q, v):
+    """softmax_channels(q) @ (softmax_tokens(k)^T v) on token-major fp32 k, q, v [B, N, C]."""
+    require_cuda(k)
+    lib = load_library()
+    k, q, v = k.contiguous(), q.contiguous(), v.contiguous()
+    B, N, C = k.shape
+    out = torch.empty_like(k)
+    ws = _ws(lib.tcx_ea_core_workspace_bytes(B, N, C), k)
+    _chk(lib.tcx_ea_core_fwd(_ptr(k), _ptr(q), _ptr(v), _ptr(out), B, N, C, _ptr(ws), _stream()))
+    return out
+
+
+def ea_core_bwd(k, q, v, dout):
+    require_cuda(k)
+    lib = load_library()
+    k, q, v, dout = k.contiguous(), q.contiguous(), v.contiguous(), dout.contiguous()
+    B, N, C = k.shape
+    dk, dq, dv = torch.empty_like(k), torch.empty_like(k), torch.empty_like(k)
+    ws = _ws(lib.tcx_ea_core_workspace_bytes(B, N, C), k)
+    _chk(lib.tcx_ea_core_bwd(_ptr(k), _ptr(q), _ptr(v), _ptr(dout), _ptr(dk), _ptr(dq), _ptr(dv), B, N, C, _ptr(ws), _stream()))
+    return dk, dq, dv
