@@ -310,6 +310,28 @@ int tcx_ea_core_fwd(const float* k, const float* q, const float* v, float* out, 
 int tcx_ea_core_bwd(const float* k, const float* q, const float* v, const float* dout, float* dk, float* dq, float* dv, int B, int N,
                     int C, void* ws, void* stream);
 
+/* Encoder glue of the training row.
+ * BatchNorm2d in train mode (batch statistics over the M = B*H*W rows of NHWC x [M][C]) fused with the activation that follows it
+ * in DWConv2d_BN (MSTr.py:355-362, Hardswish = act 2), Conv2d_BN (:399-404, act 0 or 2) and CoordAtt.bn1 (:1331, silu_swish =
+ * act 4).  stat (2*C floats: mean | 1/std) is kept for backward; running_mean / running_var (NULL to skip) receive
+ * nn.BatchNorm2d's momentum update with the unbiased variance. */
+size_t tcx_bn_act_train_workspace_bytes(long long M, int C);
+int tcx_bn_act_train_fwd(const float* x, const float* w, const float* b, float* running_mean, float* running_var, float eps,
+                         float momentum, int act, float* y, float* stat, long long M, int C, void* ws, void* stream);
+int tcx_bn_act_train_bwd(const float* x, const float* dy, const float* stat, const float* w, const float* b, int act, float* dx, float* dw,
+                         float* db, long long M, int C, void* ws, void* stream);
+/* depthwise 3x3, pad 1, stride 1 | 2, no bias (RIPM / ResBlock, MSTr.py:340, :1031) on NHWC x [B,H,W,C] and its gradients */
+int tcx_dwconv3x3_nhwc_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int stride, void* stream);
+size_t tcx_dwconv3x3_nhwc_bwd_workspace_bytes(int B, int H, int W, int C, int stride);
+int tcx_dwconv3x3_nhwc_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H, int W, int C, int stride,
+                           void* ws, void* stream);
+/* CoordAtt (MSTr.py:1322-1348): y [B][H+W][C] = (mean over W | mean over H) of NHWC x; gate out = x * sigmoid(z_h) * sigmoid(z_w)
+ * with z [B][H+W][C] the conv_h | conv_w outputs before the sigmoid */
+int tcx_coord_pool_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
+int tcx_coord_pool_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream);
+int tcx_coord_gate_fwd(const float* x, const float* z, float* out, int B, int H, int W, int C, void* stream);
+int tcx_coord_gate_bwd(const float* x, const float* z, const float* dout, float* dx, float* dz, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,8 +55,16 @@ def layernorm(sd, p, x, eps=1e-5):
     return F.layer_norm(x, (w.shape[0],), w, sd[p + '.bias'], eps)
 
 
+# Training-row tests set this: nn.BatchNorm2d in train mode normalises with the statistics of the batch
+# (F.batch_norm(training=True), what the reference's 21 BatchNorm2d layers do under model.train(), trainer.py:113);
+# the running statistics are not touched here.  Pinned against the live reference by tests/golden/train_golden.pt.
+BN_TRAIN = False
+
+
 def batchnorm_eval(sd, p, x, eps=1e-5):
-    """nn.BatchNorm2d in eval mode (running statistics)."""
+    """nn.BatchNorm2d: eval mode (running statistics) unless BN_TRAIN."""
+    if BN_TRAIN:
+        return F.batch_norm(x, None, None, sd[p + '.weight'], sd[p + '.bias'], True, 0.1, eps)
     return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'], sd[p + '.bias'],
                         False, 0.1, eps)
 

@@ -406,3 +406,207 @@ def test_bridge_block_backward(cuda_lib):
         _check(p.grad, ref, 1e-2, "d " + k, floor)
         n += 1
     assert n > 150
+
+
+@pytest.fixture
+def bn_train():
+    """oracle BatchNorm in train mode (batch statistics) for the duration of a test"""
+    O.BN_TRAIN = True
+    yield
+    O.BN_TRAIN = False
+
+
+@pytest.mark.parametrize("M,C,act", [(1568, 64, 2), (392, 128, 0), (98, 320, 2), (112, 16, 4), (50, 80, 4)])
+def test_bn_act_train(cuda_lib, M, C, act):
+    """BatchNorm2d (batch statistics, running update) + Hardswish / silu_swish: forward, backward, running statistics."""
+    from transception_b200 import autograd as A
+    bn = torch.nn.BatchNorm2d(C)
+    g = torch.Generator().manual_seed(C)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C, generator=g))
+        bn.bias.copy_(0.1 * torch.randn(C, generator=g))
+        bn.running_mean.copy_(0.1 * torch.randn(C, generator=g))
+        bn.running_var.copy_(0.5 + torch.rand(C, generator=g))
+    ref = torch.nn.BatchNorm2d(C)
+    ref.load_state_dict(bn.state_dict())
+    x = _rand(M, C, seed=1, scale=1.5) + 0.2
+    dy = _rand(M, C, seed=2, scale=1e-3)
+    fact = {0: lambda t: t, 2: F.hardswish, 4: O.silu_swish}[act]
+    xr = x.clone().requires_grad_()
+    want = fact(ref.train()(xr.t().reshape(1, C, M, 1))).reshape(C, M).t()
+    want.backward(dy)
+    bn = bn.cuda().train()
+    xg = x.cuda().requires_grad_()
+    got = A.bn_act(xg, bn, act)
+    assert (got.cpu() - want.detach()).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
+    got.backward(dy.cuda())
+    _check(xg.grad, xr.grad, 1e-3, "bn dx", floor=1e-9)
+    _check(bn.weight.grad, ref.weight.grad, 1e-3, "bn dw", floor=1e-9)
+    _check(bn.bias.grad, ref.bias.grad, 1e-3, "bn db", floor=1e-9)
+    assert (bn.running_mean.cpu() - ref.running_mean).abs().max().item() <= 1e-5
+    assert (bn.running_var.cpu() - ref.running_var).abs().max().item() <= 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 14, 14, 64, 2), (2, 14, 14, 64, 1), (1, 7, 9, 128, 2), (2, 7, 7, 320, 1)])
+def test_dwconv3x3_nhwc_backward(cuda_lib, B, H, W, C, stride):
+    from transception_b200 import autograd as A
+    x = _rand(B, H, W, C, seed=1)
+    w = _rand(C, 1, 3, 3, seed=2, scale=0.3)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    want = F.conv2d(xr.permute(0, 3, 1, 2), wr, None, stride, 1, 1, C).permute(0, 2, 3, 1)
+    dy = _rand(*want.shape, seed=3, scale=1e-3)
+    want.backward(dy)
+    xg, wg = x.cuda().requires_grad_(), w.cuda().requires_grad_()
+    got = A.dwconv3x3_nhwc(xg, wg, stride)
+    assert got.shape == want.shape and (got.cpu() - want.detach()).abs().max().item() <= 1e-5
+    got.backward(dy.cuda())
+    _check(xg.grad, xr.grad, 1e-4, "dw3 dx")
+    _check(wg.grad, wr.grad, 1e-4, "dw3 dw")
+
+
+def test_ripm_stage_backward(cuda_lib, bn_train):
+    """Patch_Embed_stage (MSTr.py:725-732): three chained dw3x3 -> 1x1 -> BatchNorm(train) -> Hardswish, first one stride 2."""
+    from networks.MSTr import Patch_Embed_stage
+    torch.manual_seed(2)
+    m = _randomise(Patch_Embed_stage(64, num_path=3, isPool=True))
+    x = _rand(2, 64, 28, 28, seed=1)
+    sd = {"r." + k: v.clone().requires_grad_() if v.is_floating_point() else v.clone() for k, v in m.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    want = O.patch_embed_stage(sd, "r", xr)
+    dys = [_rand(*t.shape, seed=5 + i, scale=1e-3) for i, t in enumerate(want)]
+    torch.autograd.backward(want, dys)
+    mg = m.cuda().train()
+    xg = x.cuda().requires_grad_()
+    got = mg(xg)
+    for a, b in zip(got, want):
+        assert (a.float().cpu() - b.detach()).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
+    torch.autograd.backward(got, [d.cuda() for d in dys])
+    # three chained TF32 1x1 convs each followed by a batch normalisation: 2e-2 (the single-block cases hold 1e-2)
+    _check(xg.grad, xr.grad, 2e-2, "ripm dx")
+    for k, p in mg.named_parameters():
+        _check(p.grad, sd["r." + k].grad, 2e-2, "ripm d " + k, floor=1e-8)
+
+
+def _module_parity_train(m, prefix, oracle_fn, inputs, rel=1e-2):
+    """generic: module on CUDA in train mode vs oracle autograd; inputs = list of tensors passed positionally"""
+    sd = {prefix + "." + k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in m.state_dict().items()}
+    alias = {}
+    for k, v in m.state_dict(keep_vars=True).items():
+        alias.setdefault(id(v), []).append(k)
+    alias = {ks[0]: ks for ks in alias.values()}
+    ir = [t.clone().requires_grad_() for t in inputs]
+    want = oracle_fn(sd, ir)
+    dy = _rand(*want.shape, seed=77, scale=1e-3)
+    want.backward(dy)
+    mg = m.cuda().train()
+    ig = [t.cuda().requires_grad_() for t in inputs]
+    got = mg(ig) if getattr(m, "_list_input", False) else mg(*ig)
+    assert (got.float().cpu() - want.detach()).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    got.backward(dy.cuda())
+    floor = 1e-6 * dy.norm().item()
+    for i, (a, b) in enumerate(zip(ig, ir)):
+        _check(a.grad, b.grad, rel, "d input %d" % i, floor)
+    n = 0
+    for k, p in mg.named_parameters():
+        refs = [sd[prefix + "." + a].grad for a in alias[k] if sd[prefix + "." + a].grad is not None]
+        if not refs:
+            assert p.grad is None, k
+            continue
+        _check(p.grad, sum(refs), rel, "d " + k, floor)
+        n += 1
+    return n
+
+
+def test_resblock_backward(cuda_lib, bn_train):
+    from networks.MSTr import ResBlock
+    torch.manual_seed(4)
+    m = _randomise(ResBlock(128, 128))
+    n = _module_parity_train(m, "r", lambda sd, i: O.resblock(sd, "r", i[0]), [_rand(2, 128, 14, 14, seed=1)])
+    assert n == 3 + 6
+
+
+def test_coordatt_backward(cuda_lib, bn_train):
+    """IFF: CoordAtt (MSTr.py:1322-1348) over 4C concatenated channels."""
+    from networks.MSTr import CoordAtt
+    torch.manual_seed(5)
+    m = _randomise(CoordAtt(256, 128, reduction=16))
+    n = _module_parity_train(m, "c", lambda sd, i: O.coord_att(sd, "c", i[0]), [_rand(2, 256, 14, 12, seed=1)])
+    assert n == 2 + 2 + 2 + 2 + 2
+
+
+def test_mhca_stage_backward(cuda_lib, bn_train):
+    """MHCA_stage (MSTr.py:1412-1441): ResBlock + three MHCA encoders -> concat -> CoordAtt."""
+    from networks.MSTr import MHCA_stage
+    torch.manual_seed(6)
+    m = _randomise(MHCA_stage(64, 128, num_layers=2, num_heads=8, mlp_ratio=4, num_path=3, drop_path_list=[0.0, 0.0], concat='coord'))
+    m._list_input = True
+    ins = [_rand(2, 64, 14, 14, seed=10 + i) for i in range(3)]
+    _module_parity_train(m, "s", lambda sd, i: O.mhca_stage(sd, "s", i, 2), ins)
+
+
+def test_stem_backward(cuda_lib):
+    """OverlapPatchEmbeddings (MSTr.py:299-304): conv 7x7 / 4 + LayerNorm; gradients of the conv and LayerNorm parameters."""
+    from networks.MSTr import OverlapPatchEmbeddings
+    torch.manual_seed(7)
+    m = _randomise(OverlapPatchEmbeddings(64, 7, 4, 3, 3, 64))
+    x = _rand(2, 3, 64, 64, seed=1)
+    sd = {"p." + k: v.clone().requires_grad_() for k, v in m.state_dict().items()}
+    want = O.patch_embed(sd, "p", x)[0]
+    dy = _rand(*want.shape, seed=2, scale=1e-3)
+    want.backward(dy)
+    mg = m.cuda().train()
+    got = mg(x.cuda())[0]
+    assert (got.float().cpu() - want.detach()).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    got.backward(dy.cuda())
+    for k, p in mg.named_parameters():
+        _check(p.grad, sd["p." + k].grad, 1e-2, "stem d " + k)
+
+
+def test_whole_model_train_step(cuda_lib, bn_train):
+    """MSTransception.forward in train mode + 0.4 CE + 0.6 Dice (trainer.py:139-146) + backward: loss and every parameter
+    gradient against torch autograd over the CPU oracle (bs2, same seeded weights); the set of parameters without gradient
+    (dead parameters) must be identical."""
+    from networks.MSTr import MSTransception
+    from oracle import loss_oracle as LO
+    from transception_b200.losses import CeDiceLoss
+    torch.manual_seed(1234)
+    net = _randomise(MSTransception(num_classes=9))
+    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in net.state_dict().items()}
+    alias = {}
+    for k, v in net.state_dict(keep_vars=True).items():
+        alias.setdefault(id(v), []).append(k)
+    alias = {ks[0]: ks for ks in alias.values()}
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 1, 224, 224, generator=gen) * 2 - 1
+    labels = torch.randint(0, 9, (2, 224, 224), generator=gen)
+    logits_ref = O.forward(sd, x)
+    loss_ref = LO.ce_dice(logits_ref, labels, 9)[0]
+    loss_ref.backward()
+    mg = net.cuda().train()
+    logits = mg(x.cuda())
+    err = (logits.float().cpu() - logits_ref.detach()).abs().max().item()
+    assert err <= 5e-2, err
+    loss = CeDiceLoss(9)(logits, labels.cuda())
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    loss.backward()
+    worst, n_grad, n_none = 1.0, 0, 0
+    for k, p in mg.named_parameters():
+        refs = [sd[a].grad for a in alias[k] if sd[a].grad is not None]
+        if not refs:
+            assert p.grad is None, k + ": gradient where the reference has none"
+            n_none += 1
+            continue
+        assert p.grad is not None, k + ": no gradient"
+        ref = sum(refs)
+        got = p.grad.float().cpu()
+        assert torch.isfinite(got).all(), k
+        den = ref.norm().item()
+        if den > 1e-7:
+            cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+            worst = min(worst, cos)
+            assert cos >= 0.99, "%s: cosine %.4f (|ref| %.3e)" % (k, cos, den)
+        n_grad += 1
+    print("train step: loss %.6f (oracle %.6f), %d parameters with gradient (worst cosine %.5f), %d dead" %
+          (loss.item(), loss_ref.item(), n_grad, worst, n_none))
+    assert n_grad > 1000 and n_none > 100

@@ -159,6 +159,85 @@ def ea_core(k, q, v):
     return EaCoreFn.apply(k, q, v)
 
 
+class BnActFn(torch.autograd.Function):
+    """act(BatchNorm2d(x)) with batch statistics on NHWC rows (train mode of DWConv2d_BN / Conv2d_BN / CoordAtt.bn1);
+    the running statistics of the module are updated in place like nn.BatchNorm2d does."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, rm, rv, eps, momentum, act):
+        y, stat = ops.bn_act_train(x, w, b, rm, rv, eps, momentum, act)
+        ctx.save_for_backward(x, stat, w, b)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stat, w, b = ctx.saved_tensors
+        dx, dw, db = ops.bn_act_train_bwd(x, dy, stat, w, b, ctx.act)
+        return dx, dw, db, None, None, None, None, None
+
+
+class DwConv3x3NhwcFn(torch.autograd.Function):
+    """bias-free depthwise 3x3, pad 1, stride 1 | 2 on NHWC maps (RIPM / ResBlock)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        ctx.save_for_backward(x, w)
+        ctx.stride = stride
+        return ops.dwconv3x3_nhwc(x, w, stride)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw = ops.dwconv3x3_nhwc_bwd(x, w, dy, ctx.stride, need_dx=ctx.needs_input_grad[0])
+        return dx, dw, None
+
+
+class CoordPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = (x.shape[1], x.shape[2])
+        return ops.coord_pool(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.coord_pool_bwd(dy, *ctx.hw)
+
+
+class CoordGateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, z):
+        ctx.save_for_backward(x, z)
+        return ops.coord_gate(x, z)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, z = ctx.saved_tensors
+        return ops.coord_gate_bwd(x, z, dout)
+
+
+def bn_act(x, bn, act):
+    """train-mode BatchNorm2d module `bn` + activation on NHWC rows; counts the batch like the module does"""
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not built")
+    y = BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, act)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y
+
+
+def dwconv3x3_nhwc(x, w, stride):
+    return DwConv3x3NhwcFn.apply(x, w, stride)
+
+
+def coord_pool(x):
+    return CoordPoolFn.apply(x)
+
+
+def coord_gate(x, z):
+    return CoordGateFn.apply(x, z)
+
+
 def attn_core(q, kv, scale):
     return AttnCoreFn.apply(q, kv, scale)
 

@@ -1692,6 +1692,45 @@ int tcx_ea_core_bwd(const float* k, const float* q, const float* v, const float*
 }  // extern "C"
 
 extern "C" {
+// ---- encoder glue of the training row: BatchNorm (batch statistics), strided depthwise 3x3, CoordAtt pooling / gating ----
+size_t tcx_bn_act_train_workspace_bytes(long long M, int C) { return 4 * bn_train_scratch_floats(M, C); }
+int tcx_bn_act_train_fwd(const float* x, const float* w, const float* b, float* running_mean, float* running_var, float eps,
+                         float momentum, int act, float* y, float* stat, long long M, int C, void* ws, void* stream) {
+  TCX_REQUIRE(x && w && b && y && stat && ws, "bn_act_train_fwd: null pointer");
+  TCX_REQUIRE(act == ACT_NONE || act == ACT_HARDSWISH || act == ACT_SILU_SWISH, "bn_act_train: activation %d not built", act);
+  return launch_bn_train_fwd(x, w, b, eps, momentum, act, y, stat, running_mean, running_var, M, C, reinterpret_cast<float*>(ws), S(stream));
+}
+int tcx_bn_act_train_bwd(const float* x, const float* dy, const float* stat, const float* w, const float* b, int act, float* dx, float* dw,
+                         float* db, long long M, int C, void* ws, void* stream) {
+  TCX_REQUIRE(x && dy && stat && w && b && dx && dw && db && ws, "bn_act_train_bwd: null pointer");
+  return launch_bn_train_bwd(x, dy, stat, w, b, act, dx, dw, db, M, C, reinterpret_cast<float*>(ws), S(stream));
+}
+int tcx_dwconv3x3_nhwc_fwd(const float* x, const float* w, float* y, int B, int H, int W, int C, int stride, void* stream) {
+  TCX_REQUIRE(x && w && y, "dwconv3x3_nhwc_fwd: null pointer");
+  DwGroup g{x, w, nullptr, y};
+  return launch_dwconv3x3(&g, 1, B, H, W, C, stride, DW_PLAIN, BnParams{}, S(stream));
+}
+size_t tcx_dwconv3x3_nhwc_bwd_workspace_bytes(int B, int H, int W, int C, int stride) {
+  return 4 * dw3s_scratch_floats((long long)B * ((H - 1) / stride + 1) * ((W - 1) / stride + 1), C);
+}
+int tcx_dwconv3x3_nhwc_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H, int W, int C, int stride,
+                           void* ws, void* stream) {
+  TCX_REQUIRE(x && w && dy && ws && (stride == 1 || stride == 2), "dwconv3x3_nhwc_bwd: null pointer or bad stride");
+  return launch_dw3s_bwd(x, w, dy, dx, dw, B, H, W, C, stride, reinterpret_cast<float*>(ws), S(stream));
+}
+int tcx_coord_pool_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) { return launch_coord_pool(x, B, H, W, C, y, S(stream)); }
+int tcx_coord_pool_bwd(const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  return launch_coord_pool_bwd(dy, B, H, W, C, dx, S(stream));
+}
+int tcx_coord_gate_fwd(const float* x, const float* z, float* out, int B, int H, int W, int C, void* stream) {
+  return launch_coord_gate(x, z, B, H, W, C, out, S(stream));
+}
+int tcx_coord_gate_bwd(const float* x, const float* z, const float* dout, float* dx, float* dz, int B, int H, int W, int C, void* stream) {
+  return launch_coord_gate_bwd(x, z, dout, B, H, W, C, dx, dz, S(stream));
+}
+}  // extern "C"
+
+extern "C" {
 
 size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C) { return 4 * (rnd(2 * (size_t)M) + rnd(2 * (size_t)bwd_red_blocks(M) * C) + 64); }
 int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, float eps, float* dx, float* dw, float* db, long long M, int C,

@@ -103,6 +103,25 @@ int launch_bwd_rowsoftmax_bwd(const float* P, int ldp, const float* dP, int ldd,
 // out[b][r][c] (row pitch ldo) = scale * sum_s part[b][s][r][c], r < R, c < Cc
 int launch_bwd_fold_rows(const float* part, int batch, int S, int R, int Cc, float scale, float* out, int ldo, cudaStream_t st);
 
+// ---- encoder glue (bwd_enc.cu) ----
+// BatchNorm with batch statistics + activation (TcxAct: 0 none, 2 Hardswish, 4 silu_swish) on rows x [M][C]:
+// y = act((x - mean) / sqrt(var + eps) * w + b); stat (2C floats) = mean | 1/std for backward; rm / rv (nullable) get the
+// nn.BatchNorm2d running update (momentum, unbiased variance).  scratch: bn_train_scratch_floats
+size_t bn_train_scratch_floats(long long M, int C);
+int launch_bn_train_fwd(const float* x, const float* w, const float* b, float eps, float momentum, int act, float* y, float* stat, float* rm,
+                        float* rv, long long M, int C, float* scratch, cudaStream_t st);
+int launch_bn_train_bwd(const float* x, const float* dy, const float* stat, const float* w, const float* b, int act, float* dx, float* dw,
+                        float* db, long long M, int C, float* scratch, cudaStream_t st);
+// depthwise 3x3 (pad 1, stride 1 | 2, no bias) on NHWC x [B,H,W,C]: dx (nullable) and dw [C][9] (nullable) from dy [B,Ho,Wo,C]
+size_t dw3s_scratch_floats(long long Mo, int C);
+int launch_dw3s_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H, int W, int C, int stride,
+                    float* scratch, cudaStream_t st);
+// CoordAtt (MSTr.py:1322-1348): y [B][H+W][C] = (mean over W | mean over H); gate out = x sigmoid(z_h) sigmoid(z_w) with z [B][H+W][C]
+int launch_coord_pool(const float* x, int B, int H, int W, int C, float* y, cudaStream_t st);
+int launch_coord_pool_bwd(const float* dy, int B, int H, int W, int C, float* dx, cudaStream_t st);
+int launch_coord_gate(const float* x, const float* z, int B, int H, int W, int C, float* out, cudaStream_t st);
+int launch_coord_gate_bwd(const float* x, const float* z, const float* dout, int B, int H, int W, int C, float* dx, float* dz, cudaStream_t st);
+
 // out[i] = sum_s part[s][i], i < n (split-K fold of the weight-gradient partials)
 int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st);
 

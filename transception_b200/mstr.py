@@ -67,11 +67,18 @@ def _bn(bn):
     return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
 
 
-def _check_eval_bn(mod):
-    if mod.training:
+def _check_eval_bn(mod, x=None):
+    """Eval-mode BatchNorm path: fine without autograd; gradients through running statistics are not built."""
+    if x is not None and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in mod.parameters())):
         raise NotImplementedError(
-            "transception_b200: BatchNorm batch-statistics (train mode) kernels are not built yet; "
-            "call .eval() (round-1 scope is the forward path, see DESIGN.md)")
+            "transception_b200: backward through eval-mode BatchNorm (running statistics) is not built; "
+            "call .train() for a training step or wrap inference in torch.no_grad()")
+
+
+def _lin_nhwc(x, conv):
+    """1x1 convolution on an NHWC map as a Linear autograd node."""
+    w = conv.weight
+    return tcx_autograd.linear(x, w.reshape(w.shape[0], w.shape[1]), conv.bias)
 
 
 # --------------------------------------------------------------------------------------
@@ -295,6 +302,19 @@ class OverlapPatchEmbeddings(nn.Module):
         k, s, p = self.proj.kernel_size[0], self.proj.stride[0], self.proj.padding[0]
         H = (x.shape[2] + 2 * p - k) // s + 1
         W = (x.shape[3] + 2 * p - k) // s + 1
+        if _recording(x, self.proj.weight):
+            # training row (MSTr.py:299-304): the 7x7/4 conv is a patch gather (F.unfold: a copy) + Linear node; K = Cin*49
+            # is zero-padded to a multiple of 4 to keep 16-byte row pitches for the gradient GEMMs
+            w = self.proj.weight
+            if x.shape[1] == 1 and w.shape[1] == 3:
+                x = x.repeat(1, 3, 1, 1)                      # MSTr.py:2828-2829
+            patches = torch.nn.functional.unfold(x, k, padding=p, stride=s).transpose(1, 2)
+            kk = patches.shape[-1]
+            pad = (-kk) % 4
+            patches = torch.nn.functional.pad(patches, (0, pad))
+            wmat = torch.nn.functional.pad(w.reshape(w.shape[0], kk), (0, pad))
+            y = tcx_autograd.linear(patches, wmat, self.proj.bias)
+            return tcx_autograd.layernorm(y, self.norm.weight, self.norm.bias, self.norm.eps), H, W
         y = ops.patch_embed_ln(x.contiguous(), self.proj.weight, self.proj.bias, s, p,
                                self.norm.weight, self.norm.bias, self.norm.eps)
         return y, H, W
@@ -318,7 +338,12 @@ class DWConv2d_BN(nn.Module):
         self.bn.bias.data.zero_()
 
     def nhwc(self, x_nhwc, out=None):
-        _check_eval_bn(self)
+        if self.training:
+            # training row (MSTr.py:355-362): depthwise conv, 1x1 conv and BatchNorm(batch statistics)+Hardswish nodes
+            y = tcx_autograd.dwconv3x3_nhwc(x_nhwc, self.dwconv.weight, self.dwconv.stride[0])
+            y = tcx_autograd.bn_act(_lin_nhwc(y, self.pwconv), self.bn, ops.ACT_HARDSWISH)
+            return y if out is None else out.copy_(y)
+        _check_eval_bn(self, x_nhwc)
         return ops.ripm_dwsep_bn_hs(x_nhwc, self.dwconv.stride[0], self.dwconv.weight, self.pwconv.weight,
                                     *_bn(self.bn), out=out)
 
@@ -344,9 +369,14 @@ class Conv2d_BN(nn.Module):
             raise NotImplementedError("Conv2d_BN: only Hardswish / no activation are built")
         self.act_layer = act_layer() if act_layer is not None else nn.Identity()
 
+    def nhwc_train(self, x_nhwc):
+        return tcx_autograd.bn_act(_lin_nhwc(x_nhwc, self.conv), self.bn, ops.ACT_HARDSWISH if self.hardswish else ops.ACT_NONE)
+
     def forward(self, x):
-        _check_eval_bn(self)
         xh = _nhwc(x)
+        if self.training:
+            return _as_nchw(self.nhwc_train(xh))
+        _check_eval_bn(self, x)
         B, H, W, C = xh.shape
         y = ops.linear_bn_act(xh.view(-1, C), self.conv.weight, *_bn(self.bn), hardswish=self.hardswish)
         return _as_nchw(y.view(B, H, W, -1))
@@ -378,6 +408,12 @@ class Patch_Embed_stage(nn.Module):
 
     def nhwc(self, x_nhwc):
         B, H, W, C = x_nhwc.shape
+        if self.training:
+            outs, cur = [], x_nhwc
+            for pe in self.patch_embeds:
+                cur = pe.patch_conv.nhwc(cur)
+                outs.append(cur)
+            return torch.stack(outs, 0)
         s0 = self.patch_embeds[0].stride
         Ho, Wo = (H + 2 - 3) // s0 + 1, (W + 2 - 3) // s0 + 1
         stacked = torch.empty((len(self.patch_embeds), B, Ho, Wo, C), device=x_nhwc.device, dtype=x_nhwc.dtype)
@@ -405,7 +441,12 @@ class ResBlock(nn.Module):
         _xavier_convs([self.conv1.conv, self.dwconv, self.conv2.conv])
 
     def nhwc(self, x_nhwc):
-        _check_eval_bn(self)
+        if self.training:
+            # training row (MSTr.py:1042-1050)
+            f = self.conv1.nhwc_train(x_nhwc)
+            f = tcx_autograd.bn_act(tcx_autograd.dwconv3x3_nhwc(f, self.dwconv.weight, 1), self.norm, ops.ACT_HARDSWISH)
+            return x_nhwc + self.conv2.nhwc_train(f)
+        _check_eval_bn(self, x_nhwc)
         return ops.resblock(x_nhwc, self.conv1.conv.weight, _bn(self.conv1.bn), self.dwconv.weight, _bn(self.norm),
                             self.conv2.conv.weight, _bn(self.conv2.bn))
 
@@ -565,7 +606,14 @@ class CoordAtt(nn.Module):
 
     def nhwc(self, maps):
         """maps: list of NHWC tensors whose channel concatenation is the reference's input."""
-        _check_eval_bn(self)
+        if self.training:
+            # training row (MSTr.py:1322-1348): pooling, gating, the four 1x1 convs and BatchNorm+silu_swish are autograd nodes
+            x = torch.cat(maps, dim=-1) if len(maps) > 1 else maps[0]
+            H = x.shape[1]
+            y = tcx_autograd.bn_act(_lin_nhwc(tcx_autograd.coord_pool(x), self.conv1), self.bn1, ops.ACT_SILU_SWISH)
+            z = torch.cat([_lin_nhwc(y[:, :H], self.conv_h), _lin_nhwc(y[:, H:], self.conv_w)], dim=1)
+            return _lin_nhwc(tcx_autograd.coord_gate(x, z), self.conv_in_out)
+        _check_eval_bn(self, maps[0])
         return ops.iff_coordatt(maps, self.conv1.weight, self.conv1.bias, _bn(self.bn1),
                                 self.conv_h.weight, self.conv_h.bias, self.conv_w.weight, self.conv_w.bias,
                                 self.conv_in_out.weight, self.conv_in_out.bias)
@@ -590,6 +638,14 @@ class MHCA_stage(nn.Module):
     def nhwc(self, stacked):
         """stacked: [P,B,H,W,C] RIPM outputs -> [B,H,W,C_out]."""
         P, B, H, W, C = stacked.shape
+        if self.training:
+            maps = [self.InvRes.nhwc(stacked[0])]
+            for i, enc in enumerate(self.mhca_blks):
+                t = stacked[i].reshape(B, H * W, C)
+                for blk in enc.MHCA_layers:
+                    t = blk(t, (H, W))
+                maps.append(t.reshape(B, H, W, C))
+            return self.aggregate.nhwc(maps)
         # the residual branch only needs path 0 of the RIPM output: it runs on a side stream next to the three
         # transformer branches (a parallel branch of the captured graph)
         main = torch.cuda.current_stream(stacked.device)
@@ -641,8 +697,11 @@ class MSViT(nn.Module):
         t, H, W = self.patch_embed1(x)
         for blk in self.block1:
             t = blk(t, H, W)
-        t = ops.layernorm(t, self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        cur = t.view(B, H, W, -1)
+        if _recording(t, self.norm1.weight):
+            t = tcx_autograd.layernorm(t, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        else:
+            t = ops.layernorm(t, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        cur = t.reshape(B, H, W, -1)
         outs = [cur]
         for s in (2, 3, 4):
             stacked = getattr(self, 'patch_embed_stage%d' % s).nhwc(cur)
@@ -885,15 +944,21 @@ class MSTransception(nn.Module):
                                         is_last=True)
 
     def forward(self, x):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "transception_b200 round 1 builds the forward path only: call under torch.no_grad() "
-                "(backward kernels are scheduled next, see DESIGN.md)")
         ops.require_cuda(x)
+        recording = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if recording and not self.training:
+            raise NotImplementedError(
+                "transception_b200: backward through eval-mode BatchNorm (running statistics) is not built; call .train() "
+                "for a training step or wrap inference in torch.no_grad()")
         # a 1-channel input is read three times by the stem kernel (reference repeats it, MSTr.py:2828-2829)
         maps = self.backbone.nhwc(x)
         if self.have_bridge != "None":
-            maps = [m.permute(0, 2, 3, 1) for m in self.bridge(ops.bridge_regroup(maps))]
+            if recording:
+                # training row: every module below routes to the autograd nodes of transception_b200/autograd.py
+                tokens = torch.cat([m.reshape(m.shape[0], -1, 64) for m in maps], dim=1)
+            else:
+                tokens = ops.bridge_regroup(maps)
+            maps = [m.permute(0, 2, 3, 1) for m in self.bridge(tokens)]
         b, _, _, c = maps[3].shape
         t3 = self.decoder_3(maps[3].reshape(b, -1, c))
         t2 = self.decoder_2(t3, maps[2])

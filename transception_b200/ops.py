@@ -106,6 +106,16 @@ _PROTOS = {
     "tcx_ea_core_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_ea_core_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_ea_core_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_bn_act_train_workspace_bytes": (_sz, [_ll, _i]),
+    "tcx_bn_act_train_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _ll, _i, _vp, _vp]),
+    "tcx_bn_act_train_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
+    "tcx_dwconv3x3_nhwc_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "tcx_dwconv3x3_nhwc_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "tcx_dwconv3x3_nhwc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_coord_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_coord_pool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_coord_gate_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tcx_coord_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -984,3 +994,92 @@ def ea_core_bwd(k, q, v, dout):
     ws = _ws(lib.tcx_ea_core_workspace_bytes(B, N, C), k)
     _chk(lib.tcx_ea_core_bwd(_ptr(k), _ptr(q), _ptr(v), _ptr(dout), _ptr(dk), _ptr(dq), _ptr(dv), B, N, C, _ptr(ws), _stream()))
     return dk, dq, dv
+
+
+ACT_NONE, ACT_HARDSWISH, ACT_SILU_SWISH = 0, 2, 4
+
+
+def bn_act_train(x, w, b, rm, rv, eps, momentum, act):
+    """(y, stat) of BatchNorm2d with batch statistics + activation on NHWC rows x [..., C]; updates rm / rv in place."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    stat = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    ws = _ws(lib.tcx_bn_act_train_workspace_bytes(M, C), x)
+    _chk(lib.tcx_bn_act_train_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(rm), _ptr(rv), eps, momentum, act, _ptr(y), _ptr(stat), M, C,
+                                  _ptr(ws), _stream()))
+    return y, stat
+
+
+def bn_act_train_bwd(x, dy, stat, w, b, act):
+    lib = load_library()
+    x, dy = x.contiguous(), dy.contiguous()
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+    ws = _ws(lib.tcx_bn_act_train_workspace_bytes(M, C), x)
+    _chk(lib.tcx_bn_act_train_bwd(_ptr(x), _ptr(dy), _ptr(stat), _ptr(_d(w)), _ptr(_d(b)), act, _ptr(dx), _ptr(dw), _ptr(db), M, C,
+                                  _ptr(ws), _stream()))
+    return dx, dw, db
+
+
+def dwconv3x3_nhwc(x, w, stride):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, (H - 1) // stride + 1, (W - 1) // stride + 1, C), dtype=x.dtype, device=x.device)
+    _chk(lib.tcx_dwconv3x3_nhwc_fwd(_ptr(x), _ptr(_d(w)), _ptr(y), B, H, W, C, stride, _stream()))
+    return y
+
+
+def dwconv3x3_nhwc_bwd(x, w, dy, stride, need_dx=True):
+    lib = load_library()
+    x, dy = x.contiguous(), dy.contiguous()
+    B, H, W, C = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w)
+    ws = _ws(lib.tcx_dwconv3x3_nhwc_bwd_workspace_bytes(B, H, W, C, stride), x)
+    _chk(lib.tcx_dwconv3x3_nhwc_bwd(_ptr(x), _ptr(_d(w)), _ptr(dy), _ptr(dx), _ptr(dw), B, H, W, C, stride, _ptr(ws), _stream()))
+    return dx, dw
+
+
+def coord_pool(x):
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, H + W, C), dtype=x.dtype, device=x.device)
+    _chk(lib.tcx_coord_pool_fwd(_ptr(x), _ptr(y), B, H, W, C, _stream()))
+    return y
+
+
+def coord_pool_bwd(dy, H, W):
+    lib = load_library()
+    dy = dy.contiguous()
+    B, _, C = dy.shape
+    dx = torch.empty((B, H, W, C), dtype=dy.dtype, device=dy.device)
+    _chk(lib.tcx_coord_pool_bwd(_ptr(dy), _ptr(dx), B, H, W, C, _stream()))
+    return dx
+
+
+def coord_gate(x, z):
+    require_cuda(x)
+    lib = load_library()
+    x, z = x.contiguous(), z.contiguous()
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    _chk(lib.tcx_coord_gate_fwd(_ptr(x), _ptr(z), _ptr(out), B, H, W, C, _stream()))
+    return out
+
+
+def coord_gate_bwd(x, z, dout):
+    lib = load_library()
+    x, z, dout = x.contiguous(), z.contiguous(), dout.contiguous()
+    B, H, W, C = x.shape
+    dx, dz = torch.empty_like(x), torch.empty_like(z)
+    _chk(lib.tcx_coord_gate_bwd(_ptr(x), _ptr(z), _ptr(dout), _ptr(dx), _ptr(dz), B, H, W, C, _stream()))
+    return dx, dz
