@@ -13,6 +13,14 @@ from oracle import mstr_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _inference():
+    """These are the inference-parity tests: with autograd recording the modules route to the training-row nodes
+    (tests/test_gpu_backward.py covers those), so every call here runs under no_grad like utils.py:78-82."""
+    with torch.no_grad():
+        yield
+
 TC_TOL = 2e-2
 FP32_TOL = 1e-4
 
@@ -438,7 +446,9 @@ def test_forward_fails_loudly_on_cpu_tensor(model):
             net(torch.zeros(1, 3, 224, 224))
 
 
-def test_train_mode_refused(model):
+def test_eval_mode_backward_refused(model):
+    """Autograd through eval-mode BatchNorm (running statistics) is the one training configuration that is not built:
+    it must fail loudly instead of silently returning gradients of something else (train mode: test_gpu_backward.py)."""
     net, _ = model
-    with pytest.raises(NotImplementedError):
+    with torch.enable_grad(), pytest.raises(NotImplementedError):
         net(torch.zeros(1, 3, 224, 224, device="cuda"))
