@@ -126,10 +126,166 @@ def cpu_reference_time(torch, steps, warmup, budget_s=150.0):
     return bs * steps / dt, cores, sample, dt / steps * 1e3
 
 
+TRAIN_METRIC = "images/sec fwd+bwd @224x224 bs16 (TransCeption MSTransception train step: forward + 0.4 CE + 0.6 Dice + backward + SGD)"
+
+
+def _train_inputs(torch, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(batch, IN_CH, SIZE, SIZE, generator=g) * 2 - 1
+    labels = torch.randint(0, NCLS, (batch, SIZE, SIZE), generator=g)
+    return x, labels
+
+
+def cpu_reference_train_time(torch, steps, warmup, budget_s=150.0):
+    """The reference's train step (trainer.py:139-149) as restated by the oracle + torch autograd + torch.optim.SGD on the host
+    cores, on a bounded sample (batch halved until the run fits the budget).  Returns (img/s, cores, sample, ms/step)."""
+    from oracle import loss_oracle as LO
+    from oracle import mstr_oracle as O
+    MSTransception = _model_cls()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone())
+          for k, v in MSTransception(num_classes=NCLS, image_size=SIZE).state_dict().items()}
+    leaves = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.SGD(leaves, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    O.BN_TRAIN = True
+
+    def step(x, labels):
+        opt.zero_grad(set_to_none=True)
+        loss = LO.ce_dice(O.forward(sd, x), labels, NCLS)[0]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in leaves if p.grad is not None], max_norm=5, norm_type=2)
+        opt.step()
+
+    bs = 2
+    x, labels = _train_inputs(torch, BATCH, 0)
+    t0 = time.perf_counter(); step(x[:bs], labels[:bs]); t1 = time.perf_counter() - t0
+    total = max(1, steps + warmup - 1)
+    while bs < BATCH and t1 * 2 * total < budget_s:
+        bs *= 2; t1 *= 2
+    for _ in range(max(0, warmup - 1)):
+        step(x[:bs], labels[:bs])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(x[:bs], labels[:bs])
+    dt = time.perf_counter() - t0
+    O.BN_TRAIN = False
+    sample = "%d timed train step(s) of bs%d 224x224 (of the bs16 workload), torch %s CPU fp32 autograd + SGD, %d threads" % (
+        steps, bs, torch.__version__, torch.get_num_threads())
+    return bs * steps / dt, cores, sample, dt / steps * 1e3
+
+
+def train_step_leg(torch, dev, world, rank, K, W):
+    """fwd + loss + bwd (+ gradient all-reduce when world > 1) + clip + SGD step at bs16 per GPU, every FLOP of the model and
+    of the loss on the library's kernels (autograd nodes of transception_b200/autograd.py); clip_grad_norm_ / optim.SGD are the
+    caller's code as in trainer.py:125,148.  Timed with CUDA events; captured as one CUDA graph when world == 1."""
+    import torch.distributed as dist
+    from transception_b200 import ops
+    from transception_b200.losses import CeDiceLoss
+    from transception_b200.shard import GradBucket
+    MSTransception = _model_cls()
+    torch.manual_seed(1234)
+    net = MSTransception(num_classes=NCLS, image_size=SIZE).to(dev).train()
+    crit = CeDiceLoss(NCLS)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    bucket = GradBucket(net.parameters())
+    xh, lh = _train_inputs(torch, BATCH, rank)
+    x, labels = xh.to(dev), lh.to(dev)
+    loss_buf = torch.zeros((), device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(net(x), labels)
+        loss.backward()
+        if world > 1:
+            bucket.allreduce()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=5, norm_type=2)
+        opt.step()
+        loss_buf.copy_(loss.detach())
+
+    n0 = ops.launches()
+    step()
+    launches = ops.launches() - n0
+    torch.cuda.synchronize(dev)
+    first_loss = float(loss_buf)
+    for _ in range(max(W - 1, 2)):
+        step()
+    torch.cuda.synchronize(dev)
+    run, graphed = step, False
+    if world == 1:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            g.replay()
+            torch.cuda.synchronize(dev)
+            run, graphed = g.replay, True
+        except Exception as e:      # report, fall back to eager launches
+            sys.stderr.write("train step: CUDA-graph capture failed (%s); timing eager launches\n" % e)
+            torch.cuda.synchronize(dev)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    # end to end: the step's batch comes from pinned host memory and the loss is read back, every step
+    xp, lp = xh.pin_memory(), lh.pin_memory()
+    lossh = torch.zeros((), dtype=torch.float32).pin_memory()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e2.record()
+    for _ in range(K):
+        x.copy_(xp, non_blocking=True)
+        labels.copy_(lp, non_blocking=True)
+        run()
+        lossh.copy_(loss_buf, non_blocking=True)
+    e3.record()
+    torch.cuda.synchronize(dev)
+    e2e_ms = e2.elapsed_time(e3)
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    imgs = world * BATCH * K
+    return {"metric": TRAIN_METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / K,
+            "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4},
+            "cuda_graph": graphed, "library_calls_per_step": launches, "first_loss": first_loss, "last_loss": float(lossh),
+            "grad_allreduce": "one flat-bucket NCCL all-reduce (average) per step" if world > 1 else None,
+            "dtype": "fp16/TF32 tensor-core forward, TF32 tensor-core + fp32 backward, fp32 master weights and gradients"}
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.mode == "train":
+        ips, cores, sample, ms = cpu_reference_train_time(torch, args.steps, args.warmup)
+        print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "TransCeption Synapse 224x224 bs16 train step (reference algorithm, CPU)"},
+                          "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
         return
     ips, cores, sample, ms = cpu_reference_time(torch, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
@@ -159,12 +315,36 @@ def run_ours(args):
     ops.load_library()
     peaks, peak_kind = _peaks()
 
+    if args.mode == "train":
+        sampler = ClockSampler(local) if rank == 0 else None
+        tr = train_step_leg(torch, dev, world, rank, args.steps, max(args.warmup, 3))
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            line = {"metric": tr["metric"], "value": tr["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": tr["dtype"], "data": "synthetic",
+                    "config": {"workload": "TransCeption Synapse 224x224 bs16 train step per GPU (BASELINE configs[2]/[3] shape): "
+                                           "forward + 0.4 CE + 0.6 Dice + backward + clip + SGD, 9 classes",
+                               "l2": "step footprint (activations saved for backward, > 2 GB) exceeds L2",
+                               "timing": "CUDA events around K steps; max over ranks",
+                               "graph": "whole train step replayed as one CUDA graph" if tr["cuda_graph"] else "eager launches"},
+                    "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_calls_per_step"] * args.steps,
+                    "train": {k: tr[k] for k in ("cuda_graph", "library_calls_per_step", "first_loss", "last_loss", "grad_allreduce")}}
+            if not args.no_cpu and world == 1:
+                ips, cores, sample, _ = cpu_reference_train_time(torch, 1, 1, budget_s=40.0)
+                line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     torch.manual_seed(1234)
     net = MSTransception(num_classes=NCLS, image_size=SIZE).eval().to(dev)
     runner = GraphRunner(net, BATCH, IN_CH, SIZE, device=dev, microbatches=args.microbatches)
     x_host = _make_inputs(torch, BATCH, rank).pin_memory()
     y_host = torch.empty((BATCH, NCLS, SIZE, SIZE), dtype=torch.float32).pin_memory()
     runner.x.copy_(x_host)
+    kernels_per_replay = runner.kernels_per_replay
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
     K, W = args.steps, max(args.warmup, 3)
 
@@ -230,6 +410,18 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = t.tolist()
+    # the training row (fwd + loss + bwd + SGD at the same bs16): reported beside the forward headline; `--mode train` makes
+    # it the line's own metric.  Never allowed to take the forward measurement down with it.
+    train_line = None
+    if MODEL == "MSTransception" and not args.no_train:
+        del runner
+        torch.cuda.empty_cache()
+        try:
+            tr = train_step_leg(torch, dev, world, rank, max(5, min(K, 20)), 3)
+            train_line = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "cuda_graph",
+                                              "library_calls_per_step", "first_loss", "last_loss", "grad_allreduce", "dtype")}
+        except Exception as e:
+            train_line = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         imgs = world * BATCH * K
         line = {"metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
@@ -248,7 +440,7 @@ def run_ours(args):
                         "api": "GraphRunner.run_host(pinned x, pinned logits): every step copies its input H2D, replays "
                                "the forward and copies its logits D2H; the D2H runs on a copy stream and overlaps the "
                                "next step"},
-                "gpu_launches": runner.kernels_per_replay * K}
+                "gpu_launches": kernels_per_replay * K}
         step_ms = dev_ms / K
         rl = []
         for g in legs:
@@ -272,6 +464,7 @@ def run_ours(args):
         if not args.no_cpu and world == 1:
             ips, cores, sample, _ = cpu_reference_time(torch, 3, 1, budget_s=40.0)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        line["train_step"] = train_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -285,6 +478,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward = BASELINE configs[1] (headline); train = the bs16 train step (fwd + loss + bwd + SGD)")
+    ap.add_argument("--no-train", action="store_true", help="forward mode: skip the train_step leg")
     ap.add_argument("--size", type=int, default=SIZE, help="input side (default 224 = the headline workload; 256 = config 5)")
     ap.add_argument("--classes", type=int, default=NCLS)
     ap.add_argument("--in-ch", type=int, default=IN_CH)

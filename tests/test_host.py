@@ -112,3 +112,35 @@ def test_world_size_2_gloo_sharding():
     for rank, ok, ms in res:
         assert ok, "rank %d: gathered shards differ from the unsharded result" % rank
         assert ms == [11.0, 5.0]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transception_b200.shard import GradBucket
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 4), (5,), (2, 2, 2), (7,))]
+    for i, p in enumerate(params[:3]):                         # the last parameter is "dead": no gradient on any rank
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = GradBucket(params).allreduce()
+    want = [(1 + world) / 2.0 * (i + 1) for i in range(3)]     # mean over ranks of (rank+1)*(i+1)
+    ok = all(torch.allclose(p.grad, torch.full_like(p, w)) for p, w in zip(params[:3], want)) and params[3].grad is None
+    q.put((rank, ok, n))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_gradient_allreduce():
+    """one all-reduce (average) over the flat bucket of used-parameter gradients; dead parameters keep grad None."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, n in res:
+        assert ok, "rank %d: averaged gradients wrong" % rank
+        assert n == 12 + 5 + 8
