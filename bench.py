@@ -194,15 +194,21 @@ def train_step_leg(torch, dev, world, rank, K, W):
     x, labels = xh.to(dev), lh.to(dev)
     loss_buf = torch.zeros((), device=dev)
 
-    def step():
+    def fwd_bwd():
         opt.zero_grad(set_to_none=True)
         loss = crit(net(x), labels)
         loss.backward()
-        if world > 1:
-            bucket.allreduce()
+        loss_buf.copy_(loss.detach())
+
+    def update():
         torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=5, norm_type=2)
         opt.step()
-        loss_buf.copy_(loss.detach())
+
+    def step():
+        fwd_bwd()
+        if world > 1:
+            bucket.allreduce()
+        update()
 
     n0 = ops.launches()
     step()
@@ -213,23 +219,41 @@ def train_step_leg(torch, dev, world, rank, K, W):
         step()
     torch.cuda.synchronize(dev)
     run, graphed = step, False
-    if world == 1:
-        try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step()
-            g.replay()
-            torch.cuda.synchronize(dev)
-            run, graphed = g.replay, True
-        except Exception as e:      # report, fall back to eager launches
-            sys.stderr.write("train step: CUDA-graph capture failed (%s); timing eager launches\n" % e)
-            torch.cuda.synchronize(dev)
+
+    def capture(fn):
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    try:
+        if world == 1:
+            g = capture(step)                       # forward + loss + backward + clip + SGD: one graph
+            run = g.replay
+        else:
+            # the NCCL all-reduce stays an eager call between two graphs (forward+loss+backward | clip+SGD): the gradient
+            # tensors are allocated once inside the first capture, so the bucket reads the same addresses every step
+            ga = capture(fwd_bwd)
+            bucket.allreduce()
+            gb = capture(update)
+
+            def run():
+                ga.replay()
+                bucket.allreduce()
+                gb.replay()
+        run()
+        torch.cuda.synchronize(dev)
+        graphed = True
+    except Exception as e:      # report, fall back to eager launches
+        sys.stderr.write("train step: CUDA-graph capture failed (%s); timing eager launches\n" % e)
+        torch.cuda.synchronize(dev)
+        run, graphed = step, False
     for _ in range(2):
         run()
     torch.cuda.synchronize(dev)
@@ -327,7 +351,8 @@ def run_ours(args):
                                            "forward + 0.4 CE + 0.6 Dice + backward + clip + SGD, 9 classes",
                                "l2": "step footprint (activations saved for backward, > 2 GB) exceeds L2",
                                "timing": "CUDA events around K steps; max over ranks",
-                               "graph": "whole train step replayed as one CUDA graph" if tr["cuda_graph"] else "eager launches"},
+                               "graph": ("eager launches" if not tr["cuda_graph"] else "whole train step replayed as one CUDA graph"
+                                         if world == 1 else "forward+loss+backward graph, eager NCCL all-reduce, clip+SGD graph")},
                     "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_calls_per_step"] * args.steps,
                     "train": {k: tr[k] for k in ("cuda_graph", "library_calls_per_step", "first_loss", "last_loss", "grad_allreduce")}}
             if not args.no_cpu and world == 1:
