@@ -612,3 +612,40 @@ def test_whole_model_train_step(cuda_lib, bn_train):
     print("train step: loss %.6f (oracle %.6f), %d parameters with gradient (worst cosine %.5f), %d dead" %
           (loss.item(), loss_ref.item(), n_grad, worst, n_none))
     assert n_grad > 1000 and n_none > 100
+
+
+def test_whole_model_train_step_other_geometry(cuda_lib, bn_train):
+    """BASELINE config 5 geometry (256x256; the stock reference cannot run it, SURVEY §0 defect 4): the train step of
+    MSTransception(image_size=256, num_classes=2) against autograd over the generalised oracle (bridge_geometry reduces to
+    the reference constants at 224, where it is pinned)."""
+    from networks.MSTr import MSTransception
+    from oracle import loss_oracle as LO
+    from transception_b200.losses import CeDiceLoss
+    torch.manual_seed(7)
+    net = _randomise(MSTransception(num_classes=2, image_size=256))
+    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in net.state_dict().items()}
+    alias = {}
+    for k, v in net.state_dict(keep_vars=True).items():
+        alias.setdefault(id(v), []).append(k)
+    alias = {ks[0]: ks for ks in alias.values()}
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 3, 256, 256, generator=gen) * 2 - 1
+    labels = torch.randint(0, 2, (1, 256, 256), generator=gen)
+    loss_ref = LO.ce_dice(O.forward(sd, x), labels, 2)[0]
+    loss_ref.backward()
+    mg = net.cuda().train()
+    loss = CeDiceLoss(2)(mg(x.cuda()), labels.cuda())
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    loss.backward()
+    n = 0
+    for k, p in mg.named_parameters():
+        refs = [sd[a].grad for a in alias[k] if sd[a].grad is not None]
+        if not refs:
+            assert p.grad is None, k
+            continue
+        ref = sum(refs)
+        if ref.norm().item() > 1e-7:
+            cos = F.cosine_similarity(p.grad.float().cpu().flatten(), ref.flatten(), dim=0).item()
+            assert cos >= 0.99, "%s: cosine %.4f" % (k, cos)
+        n += 1
+    assert n > 1000
