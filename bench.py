@@ -291,7 +291,7 @@ def train_step_leg(torch, dev, world, rank, K, W):
     return {"metric": TRAIN_METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / K,
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4},
-            "cuda_graph": graphed, "library_calls_per_step": launches, "first_loss": first_loss, "last_loss": float(lossh),
+            "cuda_graph": graphed, "library_kernels_per_step": launches, "first_loss": first_loss, "last_loss": float(lossh),
             "grad_allreduce": "one flat-bucket NCCL all-reduce (average) per step" if world > 1 else None,
             "dtype": "fp16/TF32 tensor-core forward, TF32 tensor-core + fp32 backward, fp32 master weights and gradients"}
 
@@ -353,8 +353,8 @@ def run_ours(args):
                                "timing": "CUDA events around K steps; max over ranks",
                                "graph": ("eager launches" if not tr["cuda_graph"] else "whole train step replayed as one CUDA graph"
                                          if world == 1 else "forward+loss+backward graph, eager NCCL all-reduce, clip+SGD graph")},
-                    "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_calls_per_step"] * args.steps,
-                    "train": {k: tr[k] for k in ("cuda_graph", "library_calls_per_step", "first_loss", "last_loss", "grad_allreduce")}}
+                    "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_kernels_per_step"] * args.steps,
+                    "train": {k: tr[k] for k in ("cuda_graph", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce")}}
             if not args.no_cpu and world == 1:
                 ips, cores, sample, _ = cpu_reference_train_time(torch, 1, 1, budget_s=40.0)
                 line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
@@ -444,7 +444,7 @@ def run_ours(args):
         try:
             tr = train_step_leg(torch, dev, world, rank, max(5, min(K, 20)), 3)
             train_line = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "cuda_graph",
-                                              "library_calls_per_step", "first_loss", "last_loss", "grad_allreduce", "dtype")}
+                                              "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce", "dtype")}
         except Exception as e:
             train_line = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
