@@ -1559,6 +1559,12 @@ int run_linear_bwd(const void* x, int x16, const float* w, const float* dy, floa
                    int K, float* ws, cudaStream_t st) {
   TCX_REQUIRE(M < (1ll << 31) && N % 4 == 0 && K % 4 == 0, "linear_bwd: N, K must be multiples of 4 (M=%lld N=%d K=%d)", M, N, K);
   Carver c(ws);
+  // dx, dw and db are independent: the weight-gradient chain and the bias sums run on auxiliary streams beside the input
+  // gradient (parallel branches of a captured graph); all scratch regions are disjoint
+  AuxStreams* aux = (M > 0 && ((dx != nullptr) + (dw != nullptr) + (db != nullptr)) > 1) ? aux_streams(st) : nullptr;
+  if (aux) TCX_TRY(fork_streams(aux, st, 2));
+  cudaStream_t sw = aux && dx ? aux->s[0] : st;                 // weight gradient
+  cudaStream_t sb = aux && (dx || dw) ? aux->s[1] : st;         // bias gradient
   if (dx && M > 0) {
     const int npad = (N + 31) / 32 * 32;
     float* wT = c.take((size_t)npad * K);
@@ -1576,18 +1582,22 @@ int run_linear_bwd(const void* x, int x16, const float* w, const float* dy, floa
       float* dyT = c.take((size_t)S * Ms * N);
       float* xT = c.take((size_t)S * Ms * K);
       float* part = c.take((size_t)S * N * K);
-      TCX_TRY(launch_bwd_packT_f32(dy, M, N, N, S, Ms, dyT, st));
-      if (x16) TCX_TRY(launch_bwd_packT_f16(reinterpret_cast<const __half*>(x), M, K, K, S, Ms, xT, st));
-      else TCX_TRY(launch_bwd_packT_f32(F(x), M, K, K, S, Ms, xT, st));
+      TCX_TRY(launch_bwd_packT_f32(dy, M, N, N, S, Ms, dyT, sw));
+      if (x16) TCX_TRY(launch_bwd_packT_f16(reinterpret_cast<const __half*>(x), M, K, K, S, Ms, xT, sw));
+      else TCX_TRY(launch_bwd_packT_f32(F(x), M, K, K, S, Ms, xT, sw));
       GemmParams g = gemm1(dyT, xT, S == 1 ? dw : part, N, K, Ms);
       g.batch = S; g.strideA = (long long)N * Ms; g.strideW = (long long)K * Ms; g.strideC = (long long)N * K;
-      TCX_TRY(launch_gemm(g, st));
-      if (S > 1) TCX_TRY(launch_bwd_fold(part, S, (long long)N * K, dw, st));
+      TCX_TRY(launch_gemm(g, sw));
+      if (S > 1) TCX_TRY(launch_bwd_fold(part, S, (long long)N * K, dw, sw));
     }
   }
   if (db) {
     float* part = c.take((size_t)bwd_red_blocks(M) * N);
-    TCX_TRY(launch_bwd_colsum(dy, M, N, N, part, db, st));
+    TCX_TRY(launch_bwd_colsum(dy, M, N, N, part, db, sb));
+  }
+  if (aux) {      // both forked streams rejoin (an idle one too: stream capture requires every fork to be joined)
+    TCX_TRY(join_stream(aux, 0, st));
+    TCX_TRY(join_stream(aux, 1, st));
   }
   return 0;
 }

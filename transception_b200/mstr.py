@@ -40,6 +40,32 @@ def _side_stream(device):
     return st
 
 
+TRAIN_BRANCH_STREAMS = True    # training row: independent branches of a stage run on their own streams (set False for A/B)
+_BRANCH = {}
+
+
+def _parallel_branches(device, fns):
+    """Run independent branch closures on per-device auxiliary streams, forked from and joined back to the current stream
+    (events only: capturable as parallel branches of a CUDA graph).  Autograd runs each node's backward on the stream its forward
+    ran on, so the backward of the branches overlaps the same way."""
+    if not TRAIN_BRANCH_STREAMS or len(fns) < 2:
+        return [f() for f in fns]
+    key = torch.device(device).index
+    pool = _BRANCH.setdefault(key, [])
+    while len(pool) < len(fns):
+        pool.append(torch.cuda.Stream(device=device))
+    main = torch.cuda.current_stream(device)
+    outs = []
+    for st, f in zip(pool, fns):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            outs.append(f())
+    for st, o in zip(pool, outs):
+        main.wait_stream(st)
+        o.record_stream(main)
+    return outs
+
+
 def _nhwc(x):
     """NCHW-shaped tensor (any strides) -> contiguous [B,H,W,C] (free for channels_last)."""
     return x.permute(0, 2, 3, 1).contiguous()
@@ -639,12 +665,15 @@ class MHCA_stage(nn.Module):
         """stacked: [P,B,H,W,C] RIPM outputs -> [B,H,W,C_out]."""
         P, B, H, W, C = stacked.shape
         if self.training:
-            maps = [self.InvRes.nhwc(stacked[0])]
-            for i, enc in enumerate(self.mhca_blks):
-                t = stacked[i].reshape(B, H * W, C)
-                for blk in enc.MHCA_layers:
-                    t = blk(t, (H, W))
-                maps.append(t.reshape(B, H, W, C))
+            def branch(i):
+                def run():
+                    t = stacked[i].reshape(B, H * W, C)
+                    for blk in self.mhca_blks[i].MHCA_layers:
+                        t = blk(t, (H, W))
+                    return t.reshape(B, H, W, C)
+                return run
+            # the residual block and the three transformer branches are independent until the IFF concatenation
+            maps = _parallel_branches(stacked.device, [lambda: self.InvRes.nhwc(stacked[0])] + [branch(i) for i in range(P)])
             return self.aggregate.nhwc(maps)
         # the residual branch only needs path 0 of the RIPM output: it runs on a side stream next to the three
         # transformer branches (a parallel branch of the captured graph)
@@ -864,12 +893,14 @@ def _bridge_layer_train(self, inputs):
     n1, n2 = self.norm1, self.norm2
     tx1 = x + self.attn(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps))
     tx = tcx_autograd.layernorm(tx1, n2.weight, n2.bias, n2.eps)
-    parts, off = [], 0
+    fns, off = [], 0
     for mlp, hw, mult in ((self.mixffn1, S, 1), (self.mixffn2, S // 2, 2), (self.mixffn3, S // 4, 5), (self.mixffn4, S // 8, 8)):
         n = hw * hw * mult
-        parts.append(mlp(tx[:, off:off + n].reshape(B, hw * hw, C * mult), hw, hw).reshape(B, n, C))
+        fns.append(lambda mlp=mlp, hw=hw, mult=mult, n=n, off=off:
+                   mlp(tx[:, off:off + n].reshape(B, hw * hw, C * mult), hw, hw).reshape(B, n, C))
         off += n
-    return tx1 + torch.cat(parts, dim=1)
+    # the four per-scale Mix-FFNs are independent (MSTr.py:2394-2402)
+    return tx1 + torch.cat(_parallel_branches(x.device, fns), dim=1)
 
 
 BridgLayer_4._forward_train = _bridge_layer_train
