@@ -11,7 +11,7 @@ namespace {
 
 constexpr int RED_COLS = 64;     // columns per block
 constexpr int RED_LANES = 4;     // row lanes per block
-constexpr int RED_MAX_BLOCKS = 296;   // 2 x 148 row blocks (x C/64 column groups)
+constexpr int RED_MAX_BLOCKS = 1184;  // 8 x 148 row blocks (x C/64 column groups): narrow maps (C = 64) still fill the SMs
 
 inline int red_rows_per_block(long long M) {
   long long r = (M + RED_MAX_BLOCKS - 1) / RED_MAX_BLOCKS;
