@@ -215,6 +215,16 @@ def train_step_leg(torch, dev, world, rank, K, W):
     launches = ops.launches() - n0
     torch.cuda.synchronize(dev)
     first_loss = float(loss_buf)
+    grads_match = None
+    if world > 1:
+        # after the all-reduce every rank must hold the same gradients (weights are identical, data differs per rank)
+        fwd_bwd()
+        bucket.allreduce()
+        chk = torch.stack([torch.stack([p.grad.double().sum(), p.grad.double().abs().sum()]) for p in net.parameters()
+                           if p.grad is not None]).sum(0)
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        grads_match = all(torch.equal(allc[0], c) for c in allc)
     for _ in range(max(W - 1, 2)):
         step()
     torch.cuda.synchronize(dev)
@@ -316,6 +326,7 @@ def train_step_leg(torch, dev, world, rank, K, W):
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4},
             "cuda_graph": graphed, "library_kernels_per_step": launches, "first_loss": first_loss, "last_loss": float(lossh),
+            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "grads_identical_across_ranks": grads_match,
             "grad_allreduce": "one flat-bucket NCCL all-reduce (average) per step" if world > 1 else None,
             "dtype": "fp16/TF32 tensor-core forward, TF32 tensor-core + fp32 backward, fp32 master weights and gradients"}
 
@@ -379,7 +390,8 @@ def run_ours(args):
                                          if world == 1 else "forward+loss+backward graph, eager NCCL all-reduce, clip+SGD graph")},
                     "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_kernels_per_step"] * args.steps,
                     "roofline": tr["roofline"],
-                    "train": {k: tr[k] for k in ("cuda_graph", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce")}}
+                    "train": {k: tr[k] for k in ("cuda_graph", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce", "peak_memory_gb",
+                                                   "grads_identical_across_ranks")}}
             if not args.no_cpu and world == 1:
                 ips, cores, sample, _ = cpu_reference_train_time(torch, 1, 1, budget_s=40.0)
                 line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
@@ -469,7 +481,8 @@ def run_ours(args):
         try:
             tr = train_step_leg(torch, dev, world, rank, max(5, min(K, 20)), 3)
             train_line = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "cuda_graph",
-                                              "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce", "dtype")}
+                                              "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce", "dtype",
+                                              "peak_memory_gb")}
         except Exception as e:
             train_line = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:

@@ -61,10 +61,14 @@ class GradBucket:
         if world == 1:
             return n
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
-        off = 0
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)      # averaged inside the collective
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)      # gloo has no AVG
+            flat.mul_(1.0 / world)
+        views, off = [], 0
         for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
+            views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
+        torch._foreach_copy_(grads, views)        # a handful of multi-tensor copies instead of one kernel per parameter
         return n
