@@ -183,87 +183,29 @@ def train_step_leg(torch, dev, world, rank, K, W):
     import torch.distributed as dist
     from transception_b200 import ops
     from transception_b200.losses import CeDiceLoss
-    from transception_b200.shard import GradBucket
+    from transception_b200.runtime import TrainStepGraph
     MSTransception = _model_cls()
     torch.manual_seed(1234)
     net = MSTransception(num_classes=NCLS, image_size=SIZE).to(dev).train()
-    crit = CeDiceLoss(NCLS)
     opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
-    bucket = GradBucket(net.parameters())
     xh, lh = _train_inputs(torch, BATCH, rank)
-    x, labels = xh.to(dev), lh.to(dev)
-    loss_buf = torch.zeros((), device=dev)
-
-    def fwd_bwd():
-        opt.zero_grad(set_to_none=True)
-        loss = crit(net(x), labels)
-        loss.backward()
-        loss_buf.copy_(loss.detach())
-
-    def update():
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=5, norm_type=2)
-        opt.step()
-
-    def step():
-        fwd_bwd()
-        if world > 1:
-            bucket.allreduce()
-        update()
-
-    n0 = ops.launches()
-    step()
-    launches = ops.launches() - n0
+    graphed = True
+    # the public training API of the repo: captures forward + loss + backward (+ all-reduce) + clip + SGD; its warm-up steps
+    # are real steps on this batch
+    runner = TrainStepGraph(net, CeDiceLoss(NCLS), opt, BATCH, IN_CH, SIZE, device=dev, max_norm=5.0, warmup=W, sample=(xh, lh))
+    launches = runner.kernels_per_step
+    x, labels, loss_buf, step, run = runner.x, runner.labels, runner.loss, runner.eager_step, runner.replay
+    first_loss = float(runner.first_loss)
+    run()
     torch.cuda.synchronize(dev)
-    first_loss = float(loss_buf)
     grads_match = None
     if world > 1:
         # after the all-reduce every rank must hold the same gradients (weights are identical, data differs per rank)
-        fwd_bwd()
-        bucket.allreduce()
         chk = torch.stack([torch.stack([p.grad.double().sum(), p.grad.double().abs().sum()]) for p in net.parameters()
                            if p.grad is not None]).sum(0)
         allc = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         grads_match = all(torch.equal(allc[0], c) for c in allc)
-    for _ in range(max(W - 1, 2)):
-        step()
-    torch.cuda.synchronize(dev)
-    run, graphed = step, False
-
-    def capture(fn):
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            fn()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            fn()
-        return g
-
-    try:
-        if world == 1:
-            g = capture(step)                       # forward + loss + backward + clip + SGD: one graph
-            run = g.replay
-        else:
-            # the NCCL all-reduce stays an eager call between two graphs (forward+loss+backward | clip+SGD): the gradient
-            # tensors are allocated once inside the first capture, so the bucket reads the same addresses every step
-            ga = capture(fwd_bwd)
-            bucket.allreduce()
-            gb = capture(update)
-
-            def run():
-                ga.replay()
-                bucket.allreduce()
-                gb.replay()
-        run()
-        torch.cuda.synchronize(dev)
-        graphed = True
-    except Exception as e:      # report, fall back to eager launches
-        sys.stderr.write("train step: CUDA-graph capture failed (%s); timing eager launches\n" % e)
-        torch.cuda.synchronize(dev)
-        run, graphed = step, False
     for _ in range(2):
         run()
     torch.cuda.synchronize(dev)

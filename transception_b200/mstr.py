@@ -44,10 +44,12 @@ TRAIN_BRANCH_STREAMS = True    # training row: independent branches of a stage r
 _BRANCH = {}
 
 
-def _parallel_branches(device, fns):
+def _parallel_branches(device, fns, inputs=()):
     """Run independent branch closures on per-device auxiliary streams, forked from and joined back to the current stream
     (events only: capturable as parallel branches of a CUDA graph).  Autograd runs each node's backward on the stream its forward
-    ran on, so the backward of the branches overlaps the same way."""
+    ran on, so the backward of the branches overlaps the same way.  ``inputs``: tensors allocated on the current stream that the
+    branches read (and keep for backward) — recorded on the branch streams so the caching allocator does not hand their memory
+    out again while a branch kernel may still be reading it; branch outputs are recorded on the current stream likewise."""
     if not TRAIN_BRANCH_STREAMS or len(fns) < 2:
         return [f() for f in fns]
     key = torch.device(device).index
@@ -58,6 +60,8 @@ def _parallel_branches(device, fns):
     outs = []
     for st, f in zip(pool, fns):
         st.wait_stream(main)
+        for t in inputs:
+            t.record_stream(st)
         with torch.cuda.stream(st):
             outs.append(f())
     for st, o in zip(pool, outs):
@@ -673,7 +677,8 @@ class MHCA_stage(nn.Module):
                     return t.reshape(B, H, W, C)
                 return run
             # the residual block and the three transformer branches are independent until the IFF concatenation
-            maps = _parallel_branches(stacked.device, [lambda: self.InvRes.nhwc(stacked[0])] + [branch(i) for i in range(P)])
+            maps = _parallel_branches(stacked.device, [lambda: self.InvRes.nhwc(stacked[0])] + [branch(i) for i in range(P)],
+                                      inputs=(stacked,))
             return self.aggregate.nhwc(maps)
         # the residual branch only needs path 0 of the RIPM output: it runs on a side stream next to the three
         # transformer branches (a parallel branch of the captured graph)
@@ -900,7 +905,7 @@ def _bridge_layer_train(self, inputs):
                    mlp(tx[:, off:off + n].reshape(B, hw * hw, C * mult), hw, hw).reshape(B, n, C))
         off += n
     # the four per-scale Mix-FFNs are independent (MSTr.py:2394-2402)
-    return tx1 + torch.cat(_parallel_branches(x.device, fns), dim=1)
+    return tx1 + torch.cat(_parallel_branches(x.device, fns, inputs=(tx,)), dim=1)
 
 
 BridgLayer_4._forward_train = _bridge_layer_train

@@ -98,3 +98,109 @@ class GraphRunner:
         """Make the current stream wait for every outstanding device-to-host copy of run_host."""
         if hasattr(self, "_copy_stream"):
             torch.cuda.current_stream(self.device).wait_stream(self._copy_stream)
+
+
+class TrainStepGraph:
+    """CUDA-graph runner for the training step of ``trainer.py:139-149``: forward (train mode) -> criterion -> backward ->
+    [gradient all-reduce] -> ``clip_grad_norm_`` -> ``optimizer.step()``.
+
+    An eager step enqueues ~6 600 small kernels and is bound by their host launch cost; replayed as a graph the same step is
+    about twice as fast.  With one process the whole step is ONE graph; with ``torch.distributed`` initialised (world > 1) the
+    step is a forward+loss+backward graph, an eager flat-bucket all-reduce (``shard.GradBucket``: the gradient tensors are
+    allocated once inside the first capture, so the bucket reads the same addresses every step) and a clip+optimizer graph.
+
+    ``criterion(outputs, labels)`` must be sync-free (``transception_b200.losses.CeDiceLoss``; the reference's ``DiceLoss``
+    reads ``.item()`` per class).  Usage::
+
+        runner = TrainStepGraph(net, CeDiceLoss(9), optimizer, batch=16, in_ch=1, size=224, max_norm=5)
+        loss = runner.step(image_batch, label_batch)        # device scalar, valid after the stream reaches it
+
+    The learning-rate schedule of ``trainer.py:151-153`` writes ``param_group['lr']`` on the host; SGD reads it as a Python
+    float at capture time, so call ``recapture()`` when it changes (or use a tensor ``lr`` with ``capturable`` optimizers).
+    """
+
+    def __init__(self, model, criterion, optimizer, batch, in_ch=1, size=224, device="cuda", max_norm=5.0, warmup=3,
+                 label_dtype=torch.int64, sample=None):
+        """``sample`` = (images, labels) of the first batch: the warm-up steps before capture are real training steps on it
+        (otherwise they run on a zero batch)."""
+        import torch.distributed as dist
+        from .shard import GradBucket
+        self.model, self.criterion, self.optimizer = model.train(), criterion, optimizer
+        self.device = torch.device(device)
+        self.max_norm = max_norm
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.bucket = GradBucket(model.parameters())
+        self.x = torch.zeros((batch, in_ch, size, size), device=self.device, dtype=torch.float32)
+        self.labels = torch.zeros((batch, size, size), device=self.device, dtype=label_dtype)
+        self.loss = torch.zeros((), device=self.device)
+        if sample is not None:
+            self.x.copy_(sample[0])
+            self.labels.copy_(sample[1])
+        self._warmup = warmup
+        self.recapture()
+
+    # the three phases of trainer.py:139-149
+    def _fwd_bwd(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.criterion(self.model(self.x), self.labels)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def _update(self):
+        if self.max_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_norm, norm_type=2)
+        self.optimizer.step()
+
+    def eager_step(self):
+        self._fwd_bwd()
+        if self.world > 1:
+            self.bucket.allreduce()
+        self._update()
+
+    def _capture(self, fn):
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def recapture(self):
+        """(Re)build the graphs from the current model / optimizer state.  ``max(warmup, 2)`` eager steps plus the one step the
+        capture recipe runs on a side stream before recording are REAL training steps on the current batch (``steps_done``
+        counts them); recording itself executes nothing."""
+        from . import ops
+        self.steps_done = getattr(self, "steps_done", 0)
+        n0 = ops.launches()
+        self.eager_step()
+        self.kernels_per_step = ops.launches() - n0
+        self.first_loss = self.loss.clone()
+        for _ in range(max(self._warmup - 1, 1)):
+            self.eager_step()
+        self.steps_done += max(self._warmup, 2) + 1
+        torch.cuda.synchronize(self.device)
+        if self.world == 1:
+            self._graphs = (self._capture(self.eager_step),)
+        else:
+            ga = self._capture(self._fwd_bwd)
+            self.bucket.allreduce()
+            self._graphs = (ga, self._capture(self._update))
+
+    def replay(self):
+        """One training step on the batch currently in ``self.x`` / ``self.labels``."""
+        self._graphs[0].replay()
+        if len(self._graphs) > 1:
+            self.bucket.allreduce()
+            self._graphs[1].replay()
+        self.steps_done += 1
+
+    def step(self, x, labels):
+        """Copy a batch in (host pinned or device tensors), run one step, return the device loss scalar."""
+        self.x.copy_(x, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.replay()
+        return self.loss
