@@ -152,6 +152,11 @@ class TrainStepGraph:
         self.optimizer.step()
 
     def eager_step(self):
+        if getattr(self, "_captured", False):
+            # an eager zero_grad(set_to_none=True) + backward would allocate NEW gradient tensors, while the graphs keep
+            # reading and writing the ones they were captured with
+            raise RuntimeError("TrainStepGraph: eager steps after capture break the graphs' static gradient buffers; "
+                               "use step() / replay(), or recapture()")
         self._fwd_bwd()
         if self.world > 1:
             self.bucket.allreduce()
@@ -175,6 +180,7 @@ class TrainStepGraph:
         counts them); recording itself executes nothing."""
         from . import ops
         self.steps_done = getattr(self, "steps_done", 0)
+        self._captured = False
         n0 = ops.launches()
         self.eager_step()
         self.kernels_per_step = ops.launches() - n0
@@ -189,6 +195,7 @@ class TrainStepGraph:
             ga = self._capture(self._fwd_bwd)
             self.bucket.allreduce()
             self._graphs = (ga, self._capture(self._update))
+        self._captured = True
 
     def replay(self):
         """One training step on the batch currently in ``self.x`` / ``self.labels``."""
