@@ -244,8 +244,8 @@ int tcx_seg_loss_bwd(const float* logits, const void* labels, int label_kind, in
  * -> uint8 label map [B][HW] (softmax is monotone; first index wins ties). */
 int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, int K, long long HW, void* stream);
 
-/* ---- training row: backward entries.  Gradients are fp32; the GEMM-shaped parts run on the
- * tcgen05 GEMM with TF32 operands; every reduction over tokens is two-pass in a fixed order (bit-reproducible).  These are
+/* ---- training row: backward entries.  Gradients are fp32 in HBM; the GEMM-shaped parts run on the
+ * tcgen05 kernels with TF32 operands read in place (flag "wgrad_tc" = 0: the round-1 re-layout path); every reduction over tokens is two-pass in a fixed order (bit-reproducible).  These are
  * what the autograd nodes of the drop-in modules (transception_b200/autograd.py) call where the reference relies on ATen's
  * autograd formulas for nn.LayerNorm / nn.Linear / MixFFN_skip (MSTr.py:58-61). ---- */
 
@@ -259,6 +259,18 @@ int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, float eps
 size_t tcx_linear_bwd_workspace_bytes(long long M, int N, int K);
 int tcx_linear_bwd(const void* x, int x_f16, const float* w, const float* dy, float* dx, float* dw, float* db, long long M, int N,
                    int K, void* ws, void* stream);
+
+/* Weight-gradient GEMM with both operands read in place (MN-major tcgen05 tiles; ordered split-K fold inside the kernel:
+ * thread-block clusters over distributed shared memory, then cluster sums through HBM):
+ *   out[z][i][j] = alpha * sum_t a[z][t][i] * b[z][t][j],  z < batch, t < tokens, i < NL, j < KL
+ * a [batch][tokens][lda], b [batch][tokens][ldb]: fmt 2 = both fp32 (TF32 MMA; NL, KL, lda, ldb multiples of 4), fmt 0 = both
+ * fp16, fmt 1 = both bf16 (multiples of 8); out [batch][NL][KL] fp32.
+ * Optional: db [NL] = alpha * column sums of a (batch 1; the bias gradient of nn.Linear — ATen autograd of MSTr.py:58-61 and
+ * every other nn.Linear of the path), outT [batch][KL][NL] = transposed copy, mask_ch > 0 keeps only the diagonal
+ * mask_ch x mask_ch blocks (the per-head contexts of FactorAtt_ConvRelPosEnc, MSTr.py:868-872).  Bit-reproducible. */
+size_t tcx_wgrad_mn_workspace_bytes(long long tokens, int NL, int KL, int batch, int fmt);
+int tcx_wgrad_mn(const void* a, const void* b, int fmt, long long tokens, int NL, int KL, int lda, int ldb, int batch, float alpha,
+                 float* out, float* outT, float* db, int mask_ch, void* ws, void* stream);
 
 /* MixFFN_skip training forward: the arithmetic of tcx_mixffn_skip_fwd (fp16 pipeline only: fc1 / fc2 must be prepared),
  * keeping in `saved` (tcx_mixffn_skip_saved_bytes, opaque) what backward needs: fp16 xn, fc1 output, GELU output and the

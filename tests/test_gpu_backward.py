@@ -2,8 +2,8 @@
 (through the autograd nodes of transception_b200/autograd.py -> C ABI) against torch autograd over the CPU oracle
 (the reference's gradients ARE ATen autograd over its forward ops) on the same seeded weights and inputs.
 
-Tolerance (stated): forward activations are fp16 and the gradient GEMMs run TF32, so per tensor
-relative L2 error <= 1e-2 and cosine >= 0.999 (SURVEY §8d asks cosine >= 0.99); plain LayerNorm backward is fp32
+Tolerance (stated): forward activations are fp16 and the gradient GEMMs run TF32 (operands read in place, fp32 accumulation),
+so per tensor relative L2 error <= 1e-2 and cosine >= 0.999 (SURVEY §8d asks cosine >= 0.99); plain LayerNorm backward is fp32
 arithmetic: <= 1e-4 relative.  Every result must be bit-identical run to run (no atomics).
 """
 import pytest
@@ -17,6 +17,13 @@ pytestmark = pytest.mark.gpu
 
 def _rand(*shape, seed=0, scale=1.0):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def _pfloor(name, floor):
+    """Absolute floor for a parameter gradient: bias gradients are summed on the tensor core in TF32 (the gradient operand is
+    truncated to a 10-bit mantissa), so a bias whose true gradient cancels to zero (keys under a softmax over tokens, a conv
+    bias in front of BatchNorm) is left with ~1e-5..1e-4 of the incoming gradient norm instead of fp32 rounding noise."""
+    return floor * (100.0 if name.endswith("bias") else 1.0)
 
 
 def _check(got, want, rel, what, floor=0.0):
@@ -56,6 +63,35 @@ def test_layernorm_bwd(cuda_lib, M, C, eps):
         assert torch.equal(a, t.grad), "LayerNorm backward is not bit-reproducible"
 
 
+@pytest.mark.parametrize("T,NL,KL,batch", [(256, 128, 64, 0), (64, 64, 64, 0), (100, 64, 64, 0), (777, 256, 64, 0), (5000, 320, 1280, 0),
+                                           (50176, 256, 64, 0), (50176, 64, 256, 0), (6272, 16, 64, 0), (12544, 512, 128, 0),
+                                           (784, 64, 64, 16), (3136, 128, 128, 16), (196, 320, 320, 16), (49, 512, 512, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_wgrad_mn_major(cuda_lib, T, NL, KL, batch, dtype):
+    """out = alpha * a^T b over the token axis with both operands read in place as MN-major tcgen05 tiles (wgrad_tc.cu): every
+    split plan (direct, one cluster, clusters + HBM level), bias sums, head mask, transposed copy.  Exact products of fp16 / bf16
+    inputs accumulate in fp32, so those match fp64 to fp32 rounding (5e-6); fp32 inputs go through TF32 (10-bit mantissa): 2e-3.
+    Bit-reproducible."""
+    from transception_b200 import ops
+    g = torch.Generator().manual_seed(T + NL)
+    a = (torch.randn(((batch,) if batch else ()) + (T, NL), generator=g) * 0.5).to(dtype)
+    b = torch.randn(((batch,) if batch else ()) + (T, KL), generator=g).to(dtype)
+    want = torch.matmul(a.double().transpose(-1, -2), b.double()) * 0.25
+    ch = NL // 8 if batch else 0
+    if ch:
+        want = want * (torch.arange(NL)[:, None] // ch == torch.arange(KL)[None, :] // ch).double()
+    out, outT, db = ops.wgrad_mn(a.cuda(), b.cuda(), alpha=0.25, need_db=not batch, need_T=bool(batch), mask_ch=ch)
+    tol = 2e-3 if dtype == torch.float32 else 5e-6
+    assert (out.double().cpu() - want).norm() <= tol * want.norm()
+    if batch:
+        assert torch.equal(outT, out.transpose(-1, -2))
+    else:
+        wdb = a.double().sum(0) * 0.25
+        assert (db.double().cpu() - wdb).norm() <= tol * wdb.norm()
+    out2, _, db2 = ops.wgrad_mn(a.cuda(), b.cuda(), alpha=0.25, need_db=not batch, need_T=bool(batch), mask_ch=ch)
+    assert torch.equal(out, out2) and (batch or torch.equal(db, db2)), "weight-gradient kernel is not bit-reproducible"
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 64), (777, 64, 256), (50, 2048, 512), (6272, 128, 512), (33, 320, 1280)])
 @pytest.mark.parametrize("x16", [False, True])
 def test_linear_bwd(cuda_lib, M, N, K, x16):
@@ -72,7 +108,8 @@ def test_linear_bwd(cuda_lib, M, N, K, x16):
     dx, dw, db = ops.linear_bwd(xg, w.cuda(), dy.cuda())
     _check(dx, xr.grad, 2e-3, "linear dx")
     _check(dw, wr.grad, 2e-3, "linear dw")
-    _check(db, br.grad, 1e-5, "linear db")
+    # the bias gradient rides on the tensor core (one TF32 MMA per k-step against a tile of ones) instead of an fp32 column sum
+    _check(db, br.grad, 2e-3, "linear db")
     dx2, dw2, db2 = ops.linear_bwd(xg, w.cuda(), dy.cuda())
     assert torch.equal(dx, dx2) and torch.equal(dw, dw2) and torch.equal(db, db2)
     only = ops.linear_bwd(xg, w.cuda(), dy.cuda(), need_dx=False, need_db=False)
@@ -188,7 +225,7 @@ def _grad_parity(module, prefix, oracle_fn, x, dy, rel=1e-2, dead=()):
             assert p.grad is None, k + ": gradient where the reference has none"
             continue
         assert p.grad is not None, k + ": no gradient"
-        _check(p.grad, ref, rel, "d " + k, floor)
+        _check(p.grad, ref, rel, "d " + k, _pfloor(k, floor))
         checked.append(k)
     first = {k: params[k].grad.clone() for k in checked}
     dx1 = xg.grad.clone()
@@ -276,7 +313,7 @@ def test_decoder_layer_backward(cuda_lib, is_last):
         if ref is None:
             assert p.grad is None, k
             continue
-        _check(p.grad, ref, 1e-2, "d " + k, floor)
+        _check(p.grad, ref, 1e-2, "d " + k, _pfloor(k, floor))
         n += 1
     assert n == 2 + 2 * 20 + 3 + (2 if is_last else 0)
 
@@ -403,7 +440,7 @@ def test_bridge_block_backward(cuda_lib):
         if ref is None:
             assert p.grad is None, k
             continue
-        _check(p.grad, ref, 1e-2, "d " + k, floor)
+        _check(p.grad, ref, 1e-2, "d " + k, _pfloor(k, floor))
         n += 1
     assert n > 150
 
@@ -515,7 +552,7 @@ def _module_parity_train(m, prefix, oracle_fn, inputs, rel=1e-2):
         if not refs:
             assert p.grad is None, k
             continue
-        _check(p.grad, sum(refs), rel, "d " + k, floor)
+        _check(p.grad, sum(refs), rel, "d " + k, _pfloor(k, floor))
         n += 1
     return n
 

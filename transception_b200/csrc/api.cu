@@ -66,6 +66,7 @@ static int g_flag_gemm_tc = 1;
 static int g_flag_flash_tc = 1;
 static int g_flag_f16 = 1;
 static int g_flag_ea_tc = 1;     // efficient-attention context on the tensor core (packT + gemm_tc)
+static int g_flag_wgrad_tc = 1;  // Linear backward with operands read in place: MN-major wgrad kernel + MN-major-W dgrad (0 = round-1 packT path)
 static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
@@ -570,6 +571,7 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "mixtail")) f = &g_flag_mixtail;
   else if (!strcmp(name, "ea_tc")) f = &g_flag_ea_tc;
   else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
+  else if (!strcmp(name, "wgrad_tc")) f = &g_flag_wgrad_tc;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
   *f = value;
@@ -1542,23 +1544,60 @@ int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, in
 // ---- training row: backward entries ----------------------------------------------------------
 namespace {
 
+// in-place TF32 Linear backward (wgrad_tc.cu + the MN-major-W mode of gemm_tc): needs 16-byte fp32 row pitches
+bool linear_bwd_mn_ok(long long M, int N, int K) {
+  return g_flag_wgrad_tc && g_flag_gemm_tc && M >= 1 && N % 4 == 0 && K % 4 == 0 && N >= 16 && K >= 16 &&
+         wgrad_tc_eligible(M, N, K, N, K, 4);
+}
+
 size_t linear_bwd_ws_floats(long long M, int N, int K) {
   int S, Ms;
   bwd_wgrad_splits(M, N, K, &S, &Ms);
   const size_t npad = (size_t)(N + 31) / 32 * 32;
-  return rnd(npad * K) + rnd((size_t)S * Ms * N) + rnd((size_t)S * Ms * K) + rnd((size_t)S * N * K) +
-         rnd((size_t)bwd_red_blocks(M) * N) + 64;
+  const size_t old = rnd(npad * K) + rnd((size_t)S * Ms * N) + rnd((size_t)S * Ms * K) + rnd((size_t)S * N * K) +
+                     rnd((size_t)bwd_red_blocks(M) * N) + 64;
+  const size_t mn = rnd((size_t)M * K) + rnd((size_t)N * K) + rnd(wgrad_tc_scratch_floats(M > 0 ? M : 1, N, K, 1, 4)) + 64;
+  return std::max(old, mn);
 }
 
 // nn.Linear backward: y = x w^T + b with x [M][K] (fp32, or fp16 when x16), w [N][K], dy [M][N]:
-//   dx [M][K] = dy w        (tcgen05 GEMM against the transposed weight)
-//   dw [N][K] = dy^T x      (token-split batched tcgen05 GEMM on K-major packs, fold over the splits)
-//   db [N]    = column sums of dy
-// any of dx / dw / db may be null
+//   dx [M][K] = dy w,  dw [N][K] = dy^T x,  db [N] = column sums of dy.   Any of dx / dw / db may be null.
+// Default path (flag "wgrad_tc"): every operand is read IN PLACE as fp32 with TF32 MMAs — dx = dy w takes the [N][K] weight as
+// an MN-major B operand, dw and db come from ONE launch of the MN-major weight-gradient kernel (dy and x as stored, tokens
+// major).  2 launches instead of the 8-9 of the packT path below; same TF32 precision; no scale or range concerns (measured
+// and dropped this round: fp16 gradient operands with a static scale saturate on large caller gradients, bf16 x fp16 mixed
+// operands are rejected by the hardware, and bf16 x bf16 costs a conversion pass and 2.3e-3 relative error).
 int run_linear_bwd(const void* x, int x16, const float* w, const float* dy, float* dx, float* dw, float* db, long long M, int N,
                    int K, float* ws, cudaStream_t st) {
   TCX_REQUIRE(M < (1ll << 31) && N % 4 == 0 && K % 4 == 0, "linear_bwd: N, K must be multiples of 4 (M=%lld N=%d K=%d)", M, N, K);
   Carver c(ws);
+  if (M > 0 && linear_bwd_mn_ok(M, N, K)) {
+    const bool need_w = dw != nullptr || db != nullptr;
+    AuxStreams* aux = dx != nullptr && need_w ? aux_streams(st) : nullptr;
+    if (aux) TCX_TRY(fork_streams(aux, st, 1));
+    cudaStream_t sw = aux ? aux->s[0] : st;
+    if (dx) {
+      GemmParams g = gemm1(dy, w, dx, (int)M, K, N);       // contraction over the N output features; w [N][K] read as stored
+      g.w_mn = 1; g.ldw = K;
+      TCX_TRY(launch_gemm(g, st));
+    }
+    if (need_w) {
+      const float* xx = F(x);
+      if (x16) {           // a saved fp16 activation with no fp32 twin
+        float* t = c.take((size_t)M * K);
+        TCX_TRY(launch_f16_to_f32(reinterpret_cast<const __half*>(x), t, M * K, sw));
+        xx = t;
+      }
+      float* dw_out = dw ? dw : c.take((size_t)N * K);      // bias gradient alone: the product is computed and dropped
+      WgradArgs a{};
+      a.A = dy; a.B = xx; a.fmt = 2; a.Mtok = M; a.NL = N; a.KL = K; a.lda = N; a.ldb = K; a.batch = 1;
+      a.alpha = 1.0f; a.out = dw_out; a.ldo = K; a.db = db;
+      a.scratch = c.take(wgrad_tc_scratch_floats(M, N, K, 1, 4));
+      TCX_TRY(launch_wgrad_tc(a, sw));
+    }
+    if (aux) TCX_TRY(join_stream(aux, 0, st));
+    return 0;
+  }
   // dx, dw and db are independent: the weight-gradient chain and the bias sums run on auxiliary streams beside the input
   // gradient (parallel branches of a captured graph); all scratch regions are disjoint
   AuxStreams* aux = (M > 0 && ((dx != nullptr) + (dw != nullptr) + (db != nullptr)) > 1) ? aux_streams(st) : nullptr;
@@ -1757,6 +1796,22 @@ int tcx_linear_bwd(const void* x, int x_f16, const float* w, const float* dy, fl
                    int K, void* ws, void* stream) {
   TCX_REQUIRE(x && w && dy && ws, "linear_bwd: null pointer");
   return run_linear_bwd(x, x_f16, w, dy, dx, dw, db, M, N, K, reinterpret_cast<float*>(ws), S(stream));
+}
+
+size_t tcx_wgrad_mn_workspace_bytes(long long tokens, int NL, int KL, int batch, int fmt) {
+  return 4 * (wgrad_tc_scratch_floats(tokens > 0 ? tokens : 1, NL, KL, batch, fmt == 2 ? 4 : 2) + 64);
+}
+int tcx_wgrad_mn(const void* a, const void* b, int fmt, long long tokens, int NL, int KL, int lda, int ldb, int batch, float alpha,
+                 float* out, float* outT, float* db, int mask_ch, void* ws, void* stream) {
+  TCX_REQUIRE(a && b && out && ws, "wgrad_mn: null pointer");
+  WgradArgs g{};
+  g.A = a; g.B = b; g.fmt = fmt;
+  g.Mtok = tokens; g.NL = NL; g.KL = KL; g.lda = lda; g.ldb = ldb; g.batch = batch;
+  g.strideA = batch > 1 ? tokens * lda : 0; g.strideB = batch > 1 ? tokens * ldb : 0;
+  g.alpha = alpha; g.out = out; g.ldo = KL; g.stride_out = (long long)NL * KL;
+  g.outT = outT; g.ldt = NL; g.stride_outT = (long long)NL * KL;
+  g.db = db; g.mask_ch = mask_ch; g.scratch = reinterpret_cast<float*>(ws);
+  return launch_wgrad_tc(g, S(stream));
 }
 
 // ---- EfficientAttention (MSTr.py:106-143) training forward / backward ----

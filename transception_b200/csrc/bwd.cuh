@@ -127,3 +127,47 @@ int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStrea
 
 // split plan of the weight-gradient GEMM dW[Nout][Kin] = dY^T X over M tokens
 void bwd_wgrad_splits(long long M, int Nout, int Kin, int* S, int* Ms);
+
+// ---- weight-gradient GEMM with MN-major operands read in place (wgrad_tc.cu) ----
+// out[z][i][j] = alpha * sum_t A[z][t][i] * B[z][t][j]  (fp32 / fp16 / bf16 operands, fp32 result), optional db[i] = alpha * sum_t A[t][i],
+// optional transposed copy outT[z][j][i], optional head mask (keep i / mask_ch == j / mask_ch).  Ordered split-K: bit-reproducible.
+struct WgradArgs {
+  const void* A;         // [batch][Mtok][lda], NL channels used
+  int fmt;               // element format of BOTH operands: 0 fp16, 1 bf16, 2 fp32 (TF32 MMA).  tcgen05 kind::f16 rejects mixed
+                         // A / B formats (illegal instruction on B200)
+  const void* B;         // [batch][Mtok][ldb], KL channels used
+  long long Mtok;
+  int NL, KL, lda, ldb;
+  int batch;
+  long long strideA, strideB;     // elements between batch items (0 with batch 1)
+  float alpha;
+  float* out;            // [batch][NL][ldo]
+  int ldo;
+  long long stride_out;
+  float* outT;           // nullable: [batch][KL][ldt]
+  int ldt;
+  long long stride_outT;
+  float* db;             // nullable (batch 1): [NL]
+  int mask_ch;           // 0 = no mask
+  float* scratch;        // wgrad_tc_scratch_floats(...) floats
+};
+bool wgrad_tc_eligible(long long Mtok, int NL, int KL, int lda, int ldb, int elem_bytes);
+size_t wgrad_tc_scratch_floats(long long Mtok, int NL, int KL, int batch, int elem_bytes);
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st);
+
+// dst = fp16(src * scale), saturating at +-65504 (flag "grad_bf16" = 0: gradient operands carry a static power-of-two scale that
+// the consuming GEMM's epilogue removes; only valid while |dy| * scale stays finite in fp16)
+int launch_f32_to_f16_scaled(const float* src, __half* dst, long long n, float scale, cudaStream_t st);
+int launch_f16_to_f32(const __half* src, float* dst, long long n, cudaStream_t st);
+// up to three tensors -> bf16 (round to nearest even) in ONE launch; src fp32, or fp16 when src_f16
+struct CvtSegs {
+  const void* src[3];
+  void* dst[3];
+  long long count[3];
+  long long chunks[3];   // filled by the launcher
+  int src_f16[3];
+  int n;
+};
+int launch_to_bf16_multi(CvtSegs segs, cudaStream_t st);
+// dst = bf16(src), round to nearest even: the default gradient operand format (fp32's exponent range: no scale, no saturation)
+int launch_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t st);

@@ -145,6 +145,13 @@ struct GemmParams {
   // tensor-core kernel only: A and W point at fp16 data (kind::f16 MMA) / C is written as fp16.  Leading dimensions
   // and strides stay in elements of the respective type.  fp16 output: bias only (no BN / activation / residual).
   int ab16, out16;
+  // tensor-core kernel only: W is stored [K][N] with N contiguous (row pitch ldw, batch stride strideW) and is read in place
+  // as an MN-major tcgen05 operand — the input-gradient GEMM dx = dy W of a Linear reads the forward's [N][K] weight as is.
+  int w_mn;
+  // 16-bit operands only: A and W hold bf16 instead of fp16 (kind::f16 rejects mixed A / B formats on B200)
+  int bf16;
+  // accumulator scale applied before the bias (0 = 1.0): undoes the static scale of fp16 gradient operands
+  float alpha;
 };
 int launch_gemm(const GemmParams& p, cudaStream_t st);
 

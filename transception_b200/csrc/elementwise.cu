@@ -2,7 +2,9 @@
 // All of these are HBM/L2-bound: one warp owns one token row (coalesced float4 along channels),
 // reductions are warp shuffles, no shared-memory staging is needed because a row is read once.
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "bwd.cuh"
 
 namespace {
 
@@ -200,7 +202,116 @@ __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict
   }
 }
 
+// fp32 -> fp16(x * scale), clamped to the finite fp16 range (a gradient operand never becomes inf)
+__global__ void __launch_bounds__(256) f32_to_f16_scaled_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n,
+                                                               float scale) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  auto cv = [scale](float v) { return fminf(fmaxf(v * scale, -65504.f), 65504.f); };
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    __half2 h[4] = {__floats2half2_rn(cv(a.x), cv(a.y)), __floats2half2_rn(cv(a.z), cv(a.w)), __floats2half2_rn(cv(b.x), cv(b.y)),
+                    __floats2half2_rn(cv(b.z), cv(b.w))};
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<uint4*>(h);
+  } else {
+    for (long long j = i; j < n; j++) dst[j] = __float2half_rn(cv(src[j]));
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    __nv_bfloat162 h[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w), __floats2bfloat162_rn(b.x, b.y),
+                           __floats2bfloat162_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<uint4*>(h);
+  } else {
+    for (long long j = i; j < n; j++) dst[j] = __float2bfloat16_rn(src[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+    *reinterpret_cast<float4*>(dst + i) = make_float4(a.x, a.y, b.x, b.y);
+    *reinterpret_cast<float4*>(dst + i + 4) = make_float4(c.x, c.y, d.x, d.y);
+  } else {
+    for (long long j = i; j < n; j++) dst[j] = __half2float(src[j]);
+  }
+}
+
+// up to three independent tensors -> bf16 in one launch (the operands of one Linear backward: dy fp32, x fp16 | fp32, w fp32)
+__global__ void __launch_bounds__(256) to_bf16_multi_kernel(const CvtSegs segs) {
+  long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int k = 0;
+  while (k < segs.n && chunk >= segs.chunks[k]) { chunk -= segs.chunks[k]; k++; }
+  if (k >= segs.n) return;
+  const long long i = chunk * 8, n = segs.count[k];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(segs.dst[k]);
+  if (segs.src_f16[k]) {
+    const __half* src = reinterpret_cast<const __half*>(segs.src[k]);
+    if (i + 8 <= n) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + i);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      __nv_bfloat162 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const float2 f = __half22float2(h[q]); o[q] = __floats2bfloat162_rn(f.x, f.y); }
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<uint4*>(o);
+    } else {
+      for (long long j = i; j < n; j++) dst[j] = __float2bfloat16_rn(__half2float(src[j]));
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(segs.src[k]);
+    if (i + 8 <= n) {
+      const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+      __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w), __floats2bfloat162_rn(b.x, b.y),
+                             __floats2bfloat162_rn(b.z, b.w)};
+      *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<uint4*>(o);
+    } else {
+      for (long long j = i; j < n; j++) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
 }  // namespace
+
+int launch_f16_to_f32(const __half* src, float* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f16_to_f32: pointers must be 16-byte aligned");
+  const long long threads = (n + 7) / 8;
+  f16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, dst, n);
+  return tcx_check_launch("f16_to_f32");
+}
+
+int launch_to_bf16_multi(CvtSegs segs, cudaStream_t st) {
+  long long total = 0;
+  for (int k = 0; k < segs.n; k++) {
+    TCX_REQUIRE((((uintptr_t)segs.src[k] | (uintptr_t)segs.dst[k]) & 15) == 0, "to_bf16: pointers must be 16-byte aligned");
+    segs.chunks[k] = (segs.count[k] + 7) / 8;
+    total += segs.chunks[k];
+  }
+  if (total == 0) return 0;
+  to_bf16_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(segs);
+  return tcx_check_launch("to_bf16_multi");
+}
+
+int launch_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f32_to_bf16: pointers must be 16-byte aligned");
+  const long long threads = (n + 7) / 8;
+  f32_to_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return tcx_check_launch("f32_to_bf16");
+}
+
+int launch_f32_to_f16_scaled(const float* src, __half* dst, long long n, float scale, cudaStream_t st) {
+  if (n <= 0) return 0;
+  TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f32_to_f16_scaled: pointers must be 16-byte aligned");
+  const long long threads = (n + 7) / 8;
+  f32_to_f16_scaled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, dst, n, scale);
+  return tcx_check_launch("f32_to_f16_scaled");
+}
 
 int launch_f32_to_f16(const float* src, void* dst, long long n, cudaStream_t st) {
   if (n <= 0) return 0;

@@ -34,7 +34,7 @@ tcx_encode_tiled_fn tcx_get_encode_tiled() {
 }
 
 int tcx_make_operand_map(CUtensorMap* map, const void* base, int elem_bytes, long long K, long long rows, long long ld,
-                         long long batch, long long batch_stride, int box_k, int box_rows) {
+                         long long batch, long long batch_stride, int box_k, int box_rows, int bf16, int swizzle_base32) {
   tcx_encode_tiled_fn enc = tcx_get_encode_tiled();
   TCX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   if (batch_stride == 0 || batch < 1) { batch = 1; batch_stride = rows * ld; }
@@ -43,9 +43,10 @@ int tcx_make_operand_map(CUtensorMap* map, const void* base, int elem_bytes, lon
   if (strides[1] < strides[0]) strides[1] = strides[0];
   cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_base32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TCX_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): K=%lld rows=%lld ld=%lld batch=%lld stride=%lld",
               (int)r, K, rows, ld, batch, batch_stride);
   return 0;
@@ -171,8 +172,7 @@ __device__ __forceinline__ void slab_dispatch(int act, bool scale, bool res, con
   if constexpr (OUT16) {
     slab_row<ACT_NONE, false, false, true, NC>(v, scv, shv, rrow, orow, sw);
   } else if constexpr (!FULL) {
-    if (res) slab_row<ACT_NONE, false, true, false, NC>(v, scv, shv, rrow, orow, sw);
-    else slab_row<ACT_NONE, false, false, false, NC>(v, scv, shv, rrow, orow, sw);
+    slab_act<ACT_NONE, false, NC>(scale, res, v, scv, shv, rrow, orow, sw);
   } else {
     switch (act) {
       case ACT_GELU: slab_act<ACT_GELU, false, NC>(scale, res, v, scv, shv, rrow, orow, sw); break;
@@ -256,7 +256,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           tc::mbar_wait(&empty[s], ph ^ 1);
           tc::mbar_arrive_expect_tx(&full[s], STAGE_A + STAGE_B);
           tc::tma_load_3d(smem + s * STAGE_A, &maps.a[t.gi], kb * KBE, t.m0, za, &full[s]);
-          tc::tma_load_3d(smem + sp.off_b + s * STAGE_B, &maps.w[t.gi], kb * KBE, t.n0, zw, &full[s]);
+          if (!p.w_mn) {
+            tc::tma_load_3d(smem + sp.off_b + s * STAGE_B, &maps.w[t.gi], kb * KBE, t.n0, zw, &full[s]);
+          } else {
+            // MN-major W: boxes of {KBE columns of N (128 bytes), KBE rows of K}; out-of-range boxes are zero-filled
+#pragma unroll
+            for (int i = 0; i < BN / KBE; i++)
+              tc::tma_load_3d(smem + sp.off_b + s * STAGE_B + i * (KBE * KB_BYTES), &maps.w[t.gi], t.n0 + i * KBE, kb * KBE, zw,
+                              &full[s]);
+          }
           if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -264,7 +272,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc(AB16 ? 0 : 2, BM, BN);
+      const bool wmn = p.w_mn != 0;
+      const uint32_t idesc = tc::umma_idesc(AB16 ? (p.bf16 ? 1 : 0) : 2, BM, BN, 0, wmn ? 1 : 0);
+      // K advance of the B descriptor per MMA (16-byte units): 32 bytes inside the swizzle row when K-major; one MMA's worth of
+      // 128-byte k rows (16 fp16 / 8 tf32) when MN-major
+      const uint64_t bstep = wmn ? (uint64_t)((AB16 ? 16 : 8) * KB_BYTES >> 4) : 2;
       uint32_t s = 0, ph = 0, ti = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
         const uint32_t a = ti & 1;
@@ -275,11 +287,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           tc::mbar_wait(&full[s], ph);
           tc::fence_after_sync();
           const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(smem + s * STAGE_A));
-          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(smem + sp.off_b + s * STAGE_B));
+          const uint32_t baddr = tc::smem_u32(smem + sp.off_b + s * STAGE_B);
+          const uint64_t bd = !wmn ? tc::umma_desc_sw128(baddr)
+                                   : (AB16 ? tc::umma_desc_mn_sw128(baddr, KBE * KB_BYTES) : tc::umma_desc_mn_sw128_base32(baddr, KBE * KB_BYTES));
 #pragma unroll
           for (int k = 0; k < 4; k++) {     // one MMA consumes 32 bytes of K: advance the start address inside the atom
-            if (AB16) tc::umma_f16(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else tc::umma_tf32(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (AB16) tc::umma_f16(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)k * bstep, idesc, (kb | k) != 0);
+            else tc::umma_tf32(acc, ad + (uint64_t)(k * 2), bd + (uint64_t)k * bstep, idesc, (kb | k) != 0);
           }
           tc::umma_commit(&empty[s]);        // frees the smem stage when these MMAs retire
           if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
       const TileCoord t = tile_coord(tile, mt, nt, p.batch, BN);
       const GemmEpi& e = p.g[t.gi].epi;
       const bool has_res = !OUT16 && e.residual != nullptr;
-      const bool has_scale = e.bn.w != nullptr;
+      const bool has_scale = e.bn.w != nullptr || p.alpha != 0.f;
       const int act = e.act;
       const uint32_t a = ti & 1;
       tc::mbar_wait(&acc_full[a], (ti >> 1) & 1);
@@ -436,11 +450,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_kernel(const __grid_con
           float sc = 1.f, sh = 0.f;
           if (col < p.N) {
             const float bias = e.bias ? __ldg(e.bias + col) : 0.f;
-            if (has_scale) {
+            if (e.bn.w != nullptr) {
               float bs, bt;
               bn_fold(e.bn, col, bs, bt);
               sc = bs;
               sh = fmaf(bias, bs, bt);
+            } else if (has_scale) {
+              sc = p.alpha;
+              sh = bias;
             } else {
               sh = bias;
             }
@@ -557,6 +574,8 @@ bool gemm_tc_eligible(const GemmParams& p) {
   if (p.N < 16 || p.K < 16 || p.M < 1) return false;   // ragged / tiny M is clipped by the tensor maps
   const int am = p.ab16 ? 7 : 3, cm = p.out16 ? 7 : 3;     // 16-byte row pitches
   if ((p.K | p.lda | p.ldw) & am) return false;
+  if (p.w_mn && ((p.N & am) || p.alpha < 0.f)) return false;
+  if (p.alpha != 0.f && (p.out16 || p.alpha < 0.f)) return false;
   if (p.ldc & cm) return false;
   if ((p.strideA | p.strideW) & am) return false;
   if (p.strideC & cm) return false;
@@ -565,6 +584,8 @@ bool gemm_tc_eligible(const GemmParams& p) {
     const GemmEpi& e = p.g[i].epi;
     if (e.residual && ((((uintptr_t)e.residual) & 15) || (e.ldr & 3) || (e.strideR & 3))) return false;
     if (p.out16 && (e.residual || e.bn.w || e.act != ACT_NONE)) return false;
+    if (e.ln_out && (p.w_mn || p.alpha != 0.f)) return false;
+    if (p.alpha != 0.f && e.bn.w) return false;
     if (e.ln_out && (!p.ab16 || p.out16 || (p.N & 63) || (e.ld_ln & 7) || (e.stride_ln & 7) || (((uintptr_t)e.ln_out) & 15) ||
                      !e.ln_w || !e.ln_b)) return false;
     if (p.ab16 && (e.bn.w || e.act != ACT_NONE)) return false;
@@ -590,7 +611,10 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t st) {
   for (int i = 0; i < p.groups; i++) {
     const GemmEpi& e = p.g[i].epi;
     TCX_TRY(tcx_make_operand_map(&maps.a[i], p.g[i].A, ae, p.K, p.M, p.lda, p.batch, p.strideA, kbe, BM));
-    TCX_TRY(tcx_make_operand_map(&maps.w[i], p.g[i].W, ae, p.K, p.N, p.ldw, p.batch, p.strideW, kbe, bn));
+    if (p.w_mn)   // storage [K][N]: inner dimension = N, rows = K; box = one 128-byte group of columns x one k-block of rows
+      TCX_TRY(tcx_make_operand_map(&maps.w[i], p.g[i].W, ae, p.N, p.K, p.ldw, p.batch, p.strideW, kbe, kbe, p.bf16, ae == 4));
+    else
+      TCX_TRY(tcx_make_operand_map(&maps.w[i], p.g[i].W, ae, p.K, p.N, p.ldw, p.batch, p.strideW, kbe, bn));
     TCX_TRY(tcx_make_operand_map(&maps.c[i], p.g[i].C, ce, p.N, p.M, p.ldc, p.batch, p.strideC, slabc, 32));
     if (e.residual)
       TCX_TRY(tcx_make_operand_map(&maps.r[i], e.residual, 4, p.N, p.M, e.ldr, p.batch, e.strideR, 32, 32));

@@ -82,9 +82,40 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return d;
 }
-// instruction descriptor, fp32 accumulate, both operands K-major. fmt: 0 f16, 1 bf16, 2 tf32
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand tile, 128-byte swizzle (the operand's M/N index is the contiguous one in memory, e.g. dy [tokens][C] as
+// the A operand of dW = dy^T x).  Canonical layout in 16-byte units ((8,n),(8,k)):((1,LBO),(8,SBO)): one k index = one 128-byte
+// row of 64 fp16 / 32 tf32 M/N elements, 8 consecutive k rows = one 1024-byte swizzle atom, the next 8 k rows SBO further, the
+// next 64 / 32 M/N elements LBO further.  A TMA box {64|32 elements along M/N, KT rows along K} with SWIZZLE_128B lands exactly
+// like this with SBO = 1024 and LBO = KT * 128 (the box size).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major tile of 32-bit (TF32) elements: the only layout tcgen05 accepts for these is the 128-byte swizzle with a 32-byte
+// base (layout type 1, Swizzle<2,5,2>: 32-byte chunk index ^= row index mod 4; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+// One k index = one 128-byte row of 32 elements, 4 consecutive k rows = one 512-byte atom, the next 4 k rows SBO = 512 further,
+// the next 32 M/N elements LBO further.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// instruction descriptor, fp32 accumulate. fmt: 0 f16, 1 bf16, 2 tf32; a_mn / b_mn: the operand is MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t umma_idesc2(int afmt, int bfmt, int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N, int a_mn = 0, int b_mn = 0) {
+  return umma_idesc2(fmt, fmt, M, N, a_mn, b_mn);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -174,4 +205,4 @@ tcx_encode_tiled_fn tcx_get_encode_tiled();
 // rank-3 K-major operand map: dims {K, rows, batch}, row pitch ld (elements), batch stride (elements; 0 -> batch dim 1),
 // box {box_k, box_rows, 1}, 128-byte swizzle, zero OOB fill. elem_bytes 4 (fp32/tf32) or 2 (bf16).
 int tcx_make_operand_map(CUtensorMap* map, const void* base, int elem_bytes, long long K, long long rows, long long ld,
-                         long long batch, long long batch_stride, int box_k, int box_rows);
+                         long long batch, long long batch_stride, int box_k, int box_rows, int bf16 = 0, int swizzle_base32 = 0);

@@ -93,6 +93,8 @@ _PROTOS = {
     "tcx_layernorm_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
     "tcx_linear_bwd_workspace_bytes": (_sz, [_ll, _i, _i]),
     "tcx_linear_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "tcx_wgrad_mn_workspace_bytes": (_sz, [_ll, _i, _i, _i, _i]),
+    "tcx_wgrad_mn": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp]),
     "tcx_eff_attn_saved_bytes": (_sz, [_i, _i, _i]),
     "tcx_eff_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_eff_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -867,6 +869,29 @@ def linear_bwd(x, w, dy, need_dx=True, need_dw=True, need_db=True):
     _chk(lib.tcx_linear_bwd(_ptr16(x) if x16 else _ptr(x), int(x16), _ptr(_d(w)), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), M, N, K,
                             _ptr(ws), _stream()))
     return dx, dw, db
+
+
+_WGRAD_FMT = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
+
+
+def wgrad_mn(a, b, alpha=1.0, need_db=False, need_T=False, mask_ch=0):
+    """out[z] = alpha * a[z]^T b[z] over the token axis (a [.., T, NL], b [.., T, KL], both fp32 (TF32 MMA), both fp16 or both
+    bf16, optional leading batch dim): the MN-major tcgen05 weight-gradient kernel.  Returns (out, outT or None, db or None)."""
+    require_cuda(a)
+    if a.dtype != b.dtype or a.dtype not in _WGRAD_FMT or not (a.is_contiguous() and b.is_contiguous()):
+        raise RuntimeError("wgrad_mn: operands must be contiguous and both fp32, both fp16 or both bf16")
+    lib = load_library()
+    fmt = _WGRAD_FMT[a.dtype]
+    batch = a.shape[0] if a.dim() == 3 else 1
+    T, NL, KL = a.shape[-2], a.shape[-1], b.shape[-1]
+    shape = (batch, NL, KL) if a.dim() == 3 else (NL, KL)
+    out = torch.empty(shape, dtype=torch.float32, device=a.device)
+    outT = torch.empty(shape[:-2] + (KL, NL), dtype=torch.float32, device=a.device) if need_T else None
+    db = torch.empty(NL, dtype=torch.float32, device=a.device) if need_db else None
+    ws = _ws(lib.tcx_wgrad_mn_workspace_bytes(T, NL, KL, batch, fmt), a)
+    _chk(lib.tcx_wgrad_mn(a.data_ptr(), b.data_ptr(), fmt, T, NL, KL, NL, KL, batch, alpha, _ptr(out), _ptr(outT), _ptr(db), mask_ch,
+                          _ptr(ws), _stream()))
+    return out, outT, db
 
 
 def mixffn_skip_train(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):
