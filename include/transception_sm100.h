@@ -272,6 +272,22 @@ size_t tcx_wgrad_mn_workspace_bytes(long long tokens, int NL, int KL, int batch,
 int tcx_wgrad_mn(const void* a, const void* b, int fmt, long long tokens, int NL, int KL, int lda, int ldb, int batch, float alpha,
                  float* out, float* outT, float* db, int mask_ch, void* ws, void* stream);
 
+/* ---- multi-tensor optimizer step (trainer.py:125,148: clip_grad_norm_ [optional] + optim.SGD(momentum, weight_decay)) over a
+ * device-resident tensor table.  All table arguments are DEVICE arrays built once by the caller: *_ptrs = one pointer per tensor,
+ * numel / offsets = int64 per tensor, blocks = int32 pairs (tensor index, chunk index) — one per thread block, a chunk being
+ * tcx_mt_chunk() elements.  lr, coef and out live in device memory (a learning-rate schedule is a 4-byte copy, not a re-capture).
+ *   tcx_mt_gather : flat[offsets[t] + i] = src[t][i]                      (the gradient all-reduce bucket, no concatenation pass)
+ *   tcx_mt_sqnorm : out[0] = ||all gradients||_2 (ordered fold, bit-reproducible), out[1] = min(1, max_norm / (out[0] + 1e-6))
+ *                   (1 when max_norm <= 0); part = nblocks floats of scratch
+ *   tcx_mt_sgd    : d = coef * g + weight_decay * p;  buf = momentum * buf + d;  p -= lr * buf;  w16[t] = half(p) where non-NULL
+ *                   (the prepared fp16 GEMM copy of tcx_prepare_weight_f16 stays current without a conversion launch) ---- */
+int tcx_mt_chunk(void);
+int tcx_mt_gather(const void* src_ptrs, const void* numel, const void* offsets, const void* blocks, int nblocks, float* flat, void* stream);
+int tcx_mt_sqnorm(const void* grad_ptrs, const void* numel, const void* blocks, int nblocks, float* part, float max_norm, float* out,
+                  void* stream);
+int tcx_mt_sgd(const void* param_ptrs, const void* grad_ptrs, const void* buf_ptrs, const void* w16_ptrs, const void* numel,
+               const void* blocks, int nblocks, const float* lr, const float* coef, float momentum, float weight_decay, void* stream);
+
 /* MixFFN_skip training forward: the arithmetic of tcx_mixffn_skip_fwd (fp16 pipeline only: fc1 / fc2 must be prepared),
  * keeping in `saved` (tcx_mixffn_skip_saved_bytes, opaque) what backward needs: fp16 xn, fc1 output, GELU output and the
  * fp32 LayerNorm input.  tcx_mixffn_skip_bwd: dy [B*N][C] = dL/dy -> dxn [B*N][C] (NULL: skipped) and the eight parameter

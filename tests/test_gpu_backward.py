@@ -705,7 +705,7 @@ def test_train_step_graph_matches_eager(cuda_lib):
 
     net_a, opt_a = make()
     # 2 eager warm-up steps + the one real step PyTorch's capture recipe runs on a side stream before recording
-    runner = TrainStepGraph(net_a, CeDiceLoss(9), opt_a, batch=2, warmup=2, sample=(x, labels))
+    runner = TrainStepGraph(net_a, CeDiceLoss(9), opt_a, batch=2, warmup=2, max_norm=5.0, sample=(x, labels))
     assert runner.steps_done == 3
     losses = [float(runner.step(x, labels)) for _ in range(2)]                                      # + 2 replayed steps
     net_b, opt_b = make()
@@ -722,3 +722,97 @@ def test_train_step_graph_matches_eager(cuda_lib):
     assert eager[-1] < eager[0]
     for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
         assert torch.equal(a, b), k + ": graph-replayed training diverged from eager training"
+
+
+def test_fused_sgd_matches_torch_sgd(cuda_lib):
+    """optim.FusedSGD (multi-tensor kernels, device-side lr and clip coefficient) against clip_grad_norm_ + torch.optim.SGD
+    (trainer.py:125,148) on tensors of ragged sizes, over several steps with a changing learning rate."""
+    from transception_b200.optim import FusedSGD
+    g = torch.Generator().manual_seed(3)
+    shapes = [(7,), (64, 64), (4097,), (320, 1280), (3, 5, 7), (1,), (12289,)]
+    pa = [torch.randn(s, generator=g).cuda().requires_grad_() for s in shapes]
+    pb = [p.detach().clone().requires_grad_() for p in pa]
+    unused = torch.randn(5).cuda().requires_grad_()          # never receives a gradient: must be left alone
+    oa = FusedSGD(pa + [unused], lr=0.05, momentum=0.9, weight_decay=1e-4, max_norm=0.5)
+    ob = torch.optim.SGD(pb, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    for it, lr in enumerate((0.05, 0.05, 0.01, 0.2)):
+        grads = [torch.randn(s, generator=g).cuda() * (0.1 + it) for s in shapes]
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad, q.grad = gr.clone(), gr.clone()
+        for grp in oa.param_groups + ob.param_groups:
+            grp["lr"] = lr
+        oa.step()
+        norm = torch.nn.utils.clip_grad_norm_(pb, max_norm=0.5, norm_type=2)
+        ob.step()
+        assert abs(float(oa.norm_coef[0]) - float(norm)) <= 1e-5 * float(norm)
+        for p, q in zip(pa, pb):
+            assert (p - q).abs().max().item() <= 2e-6 * max(1.0, q.abs().max().item()), (it, tuple(p.shape))
+    assert unused.grad is None and "momentum_buffer" not in oa.state.get(unused, {})
+    for p, q in zip(pa, pb):
+        assert (oa.state[p]["momentum_buffer"] - ob.state[q]["momentum_buffer"]).abs().max().item() <= 1e-5
+
+
+def test_train_step_graph_fused_sgd(cuda_lib):
+    """TrainStepGraph + FusedSGD: graph-replayed training equals the same steps launched eagerly bit for bit, tracks
+    torch.optim.SGD training closely, keeps the forward's fp16 weight copies current without conversion launches, and follows a
+    per-iteration learning-rate schedule (trainer.py:151-153) without re-capture."""
+    from networks.MSTr import MSTransception
+    from transception_b200 import ops
+    from transception_b200.losses import CeDiceLoss
+    from transception_b200.optim import FusedSGD
+    from transception_b200.runtime import TrainStepGraph
+    gen = torch.Generator().manual_seed(0)
+    x = (torch.rand(2, 1, 224, 224, generator=gen) * 2 - 1).cuda()
+    labels = torch.randint(0, 9, (2, 224, 224), generator=gen).cuda()
+    lrs = [0.05, 0.05, 0.05, 0.03, 0.02, 0.0]
+
+    def make(fused):
+        torch.manual_seed(1234)
+        net = MSTransception(num_classes=9).cuda().train()
+        cls = FusedSGD if fused else torch.optim.SGD
+        return net, cls(net.parameters(), lr=lrs[0], momentum=0.9, weight_decay=1e-4)
+
+    net_a, opt_a = make(True)
+    with torch.no_grad():
+        net_a.eval()(x)              # the inference path prepares fp16 copies the training path never touches: they must not go stale
+    runner = TrainStepGraph(net_a, CeDiceLoss(9), opt_a, batch=2, warmup=2, sample=(x, labels))
+    assert runner.steps_done == 3
+    losses = []
+    for lr in lrs[3:]:
+        for grp in opt_a.param_groups:
+            grp["lr"] = lr                                   # what trainer.py:151-153 does every iteration
+        if lr == 0.0:
+            before = {k: v.clone() for k, v in net_a.named_parameters()}
+        losses.append(float(runner.step(x, labels)))
+    # lr = 0 in the last step: momentum still moves, the weights must not
+    for k, v in net_a.named_parameters():
+        assert torch.equal(v, before[k]), k + ": the update graph did not pick up the new learning rate"
+    crit = CeDiceLoss(9)
+
+    def eager(net, opt):
+        out = []
+        for lr in lrs:
+            for grp in opt.param_groups:
+                grp["lr"] = lr
+            opt.zero_grad(set_to_none=True)
+            loss = crit(net(x), labels)
+            loss.backward()
+            opt.step()
+            out.append(float(loss.detach()))
+        return out
+    net_b, opt_b = make(True)
+    eb = eager(net_b, opt_b)
+    assert losses == eb[3:], (losses, eb)
+    for (k, a), (_, b) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+        assert torch.equal(a, b), k + ": graph-replayed FusedSGD training diverged from eager FusedSGD training"
+    net_c, opt_c = make(False)
+    ec = eager(net_c, opt_c)
+    assert all(abs(a - b) <= 2e-3 * abs(b) for a, b in zip(eb, ec)), (eb, ec)
+    assert ec[-2] < ec[0]
+    # the prepared fp16 copies follow the raw-pointer updates: eval logits of the graph-trained net == a fresh eval of its weights
+    net_a.eval()
+    with torch.no_grad():
+        y1 = net_a(x)
+        ops.invalidate_prepared(net_a)
+        y2 = net_a(x)
+    assert torch.equal(y1, y2), "stale fp16 weight copies after FusedSGD updates"

@@ -69,6 +69,7 @@ static int g_flag_ea_tc = 1;     // efficient-attention context on the tensor co
 static int g_flag_wgrad_tc = 1;  // Linear backward with operands read in place: MN-major wgrad kernel + MN-major-W dgrad (0 = round-1 packT path)
 static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
+int g_tcx_max_ctas = 0;          // > 0: cap on the grid of the persistent tcgen05 kernels (lets kernels of parallel graph branches co-run)
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
 bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
 
@@ -572,6 +573,7 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "ea_tc")) f = &g_flag_ea_tc;
   else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
   else if (!strcmp(name, "wgrad_tc")) f = &g_flag_wgrad_tc;
+  else if (!strcmp(name, "max_ctas")) f = &g_tcx_max_ctas;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
   *f = value;

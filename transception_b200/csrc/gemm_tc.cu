@@ -545,7 +545,8 @@ int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cuda
   }
   TCX_REQUIRE(sp.stages >= 2 && sp.total <= SMEM_BUDGET, "gemm_tc: smem plan does not fit (BN=%d stages=%d)", BN, sp.stages);
   const int ntiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.groups * p.batch;
-  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  int grid = ntiles < sm_count() ? ntiles : sm_count();
+  if (g_tcx_max_ctas > 0 && grid > g_tcx_max_ctas) grid = g_tcx_max_ctas;
   // algorithmic bytes: every operand read once, the output written once
   const double ae = AB16 ? 2.0 : 4.0, ce = OUT16 ? 2.0 : 4.0;
   double bytes = 0.0;

@@ -408,8 +408,9 @@ void wgrad_tc_plan(long long Mtok, int NL, int KL, int batch, int eb, int* S, in
     const int cs = idx < 4 ? (1 << idx) : WG_MAX_SPLIT;
     const int s2 = idx < 4 ? 1 : idx - 2;          // 2 .. WG_MAX_S2
     const int s = cs * s2;
-    if (s > 1 && (tiles * s > 160 || (long long)(s - 1) * tokens_per(s) >= Mtok)) continue;     // one wave, no empty split
-    const long long waves = (tiles * s + 147) / 148;
+    const long long cap = g_tcx_max_ctas > 0 ? g_tcx_max_ctas : 160;
+    if (s > 1 && (tiles * s > cap || (long long)(s - 1) * tokens_per(s) >= Mtok)) continue;     // one wave, no empty split
+    const long long waves = (tiles * s + (g_tcx_max_ctas > 0 ? g_tcx_max_ctas : 148) - 1) / (g_tcx_max_ctas > 0 ? g_tcx_max_ctas : 148);
     const double cost = (double)waves * (double)((kb_total + s - 1) / s) * 0.3 + (s > 1 ? 2.5 : 0.0) + (s2 > 1 ? 3.0 : 0.0);
     if (cost < best) { best = cost; best_cs = cs; best_s2 = s2; }
   }

@@ -95,6 +95,10 @@ _PROTOS = {
     "tcx_linear_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
     "tcx_wgrad_mn_workspace_bytes": (_sz, [_ll, _i, _i, _i, _i]),
     "tcx_wgrad_mn": (_i, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _vp]),
+    "tcx_mt_chunk": (_i, []),
+    "tcx_mt_gather": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "tcx_mt_sqnorm": (_i, [_vp, _vp, _vp, _i, _vp, _f, _vp, _vp]),
+    "tcx_mt_sgd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _vp]),
     "tcx_eff_attn_saved_bytes": (_sz, [_i, _i, _i]),
     "tcx_eff_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_eff_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -213,6 +217,24 @@ import weakref
 
 _prepared = {}
 USE_F16 = True
+_raw_gen = 0          # bumped whenever weights are updated through raw pointers (FusedSGD / captured train-step graphs)
+
+
+class _Prep:
+    """Registry entry of one prepared weight: weak reference, the version / storage / raw-update generation the fp16 copy was
+    made from, the copy, the patchify-conv permutation (or None), and whether an optimizer keeps the copy current itself."""
+    __slots__ = ("ref", "version", "ptr", "w16", "conv", "gen", "tracked")
+
+    def current(self, w):
+        return (self.ref() is w and self.version == w._version and self.ptr == w.data_ptr() and
+                (self.tracked or self.gen == _raw_gen))
+
+
+def bump_raw_generation():
+    """Weights were just updated in place through raw pointers (no ``_version`` bump): prepared copies that no optimizer table
+    keeps current are converted again by the next forward that uses them."""
+    global _raw_gen
+    _raw_gen += 1
 
 
 def prepare_weight(w, conv=None):
@@ -225,12 +247,17 @@ def prepare_weight(w, conv=None):
         w = base
     key = id(w)
     ent = _prepared.get(key)
-    if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2] == w.data_ptr():
+    if ent is not None and ent.current(w):
         return
     lib = load_library()
-    if ent is not None and ent[2] != w.data_ptr():
-        lib.tcx_forget_weight(ent[2])
-    w16 = torch.empty(w.numel(), dtype=torch.float16, device=w.device)
+    if ent is not None and ent.ptr != w.data_ptr():
+        lib.tcx_forget_weight(ent.ptr)
+    if ent is not None and ent.ref() is w and ent.ptr == w.data_ptr() and ent.w16.numel() == w.numel() and ent.w16.device == w.device:
+        w16 = ent.w16         # same storage: convert into the existing copy (its address may be baked into graphs / optimizer tables)
+        tracked = ent.tracked
+    else:
+        w16 = torch.empty(w.numel(), dtype=torch.float16, device=w.device)
+        tracked = False
     src = w.detach()
     if not src.is_contiguous():
         raise RuntimeError("transception_b200: weight matrices must be contiguous")
@@ -244,11 +271,50 @@ def prepare_weight(w, conv=None):
 
     def _gone(_ref, key=key, ptr=ptr):
         e = _prepared.get(key)
-        if e is not None and e[2] == ptr and e[0]() is None:
+        if e is not None and e.ptr == ptr and e.ref() is None:
             _prepared.pop(key, None)
             if _lib is not None:
                 _lib.tcx_forget_weight(ptr)
-    _prepared[key] = (weakref.ref(w, _gone), w._version, ptr, w16)
+    e = _Prep()
+    e.ref, e.version, e.ptr, e.w16, e.conv, e.gen, e.tracked = weakref.ref(w, _gone), w._version, ptr, w16, conv, _raw_gen, tracked
+    _prepared[key] = e
+
+
+def prepared_copy(w, track=False):
+    """(fp16 copy, conv) of a parameter the forward has prepared, or None.  ``conv`` is the (N, Cin, r) of a patchify-conv
+    weight whose copy is K-permuted (refreshed with tcx_prepare_conv_weight_f16), else None.  ``track``: the caller (an
+    optimizer table) takes over keeping the copy current after its raw-pointer updates."""
+    ent = _prepared.get(id(w))
+    if ent is None or ent.ref() is not w or ent.ptr != w.data_ptr():
+        return None
+    if track:
+        ent.tracked = True
+    return ent.w16, ent.conv
+
+
+def refresh_prepared(w):
+    """Re-convert the prepared copy of ``w`` from its current values on the current stream (a weight changed through a raw
+    pointer or ``.data``, which does not move the version counter)."""
+    ent = _prepared.get(id(w))
+    if ent is None or ent.ref() is not w:
+        return
+    lib = load_library()
+    if ent.conv is not None:
+        rc = lib.tcx_prepare_conv_weight_f16(w.data_ptr(), ent.w16.data_ptr(), ent.conv[0], ent.conv[1], ent.conv[2], _stream())
+    else:
+        rc = lib.tcx_prepare_weight_f16(w.data_ptr(), ent.w16.data_ptr(), w.numel(), _stream())
+    if rc != 0:
+        raise RuntimeError("libtransception_sm100: " + lib.tcx_last_error().decode())
+
+
+def invalidate_prepared(model=None):
+    """Forget the version stamps of the prepared fp16 copies (of ``model``'s parameters, or all): the next forward converts
+    them again.  Needed after in-place writes through ``p.data`` (EMA swaps, hand-written optimizers), which do not bump
+    ``_version``; also used to force the conversions INTO a captured forward graph."""
+    ids = None if model is None else {id(p) for p in model.parameters()}
+    for key, ent in _prepared.items():
+        if ids is None or key in ids:
+            ent.version = -1
 
 
 def _table(tensors, mats=()):

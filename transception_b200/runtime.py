@@ -102,31 +102,44 @@ class GraphRunner:
 
 class TrainStepGraph:
     """CUDA-graph runner for the training step of ``trainer.py:139-149``: forward (train mode) -> criterion -> backward ->
-    [gradient all-reduce] -> ``clip_grad_norm_`` -> ``optimizer.step()``.
+    [gradient all-reduce] -> [``clip_grad_norm_``] -> ``optimizer.step()``.
 
-    An eager step enqueues ~6 600 small kernels and is bound by their host launch cost; replayed as a graph the same step is
-    about twice as fast.  With one process the whole step is ONE graph; with ``torch.distributed`` initialised (world > 1) the
-    step is a forward+loss+backward graph, an eager flat-bucket all-reduce (``shard.GradBucket``: the gradient tensors are
-    allocated once inside the first capture, so the bucket reads the same addresses every step) and a clip+optimizer graph.
+    An eager step enqueues several thousand small kernels and is bound by their host launch cost; replayed as graphs the same
+    step is about twice as fast.  The step is captured in pieces so that every table the optimizer needs is built OUTSIDE
+    capture from the static gradient addresses of the first graph:
+
+    * graph A: forward + loss + backward (the gradient tensors are allocated inside this capture and keep their addresses);
+    * with ``transception_b200.optim.FusedSGD``: graph B = the fused clip + SGD update (single process), or graph B = gather the
+      gradients into the optimizer's flat bucket, an eager NCCL all-reduce (average) of that bucket, graph C = the update read
+      from the bucket (``torch.distributed`` initialised, world > 1).  The fused update also refreshes the fp16 GEMM copies the
+      forward reads, and takes the learning rate from a device scalar: assign ``param_group['lr']`` as ``trainer.py:151-153``
+      does and call ``step()`` — no re-capture;
+    * with any other ``torch.optim`` optimizer: graph B = ``clip_grad_norm_`` + ``optimizer.step()`` as written by the caller
+      (``shard.GradBucket`` all-reduce before it when world > 1).  ``torch.optim.SGD`` reads ``lr`` as a Python float at capture
+      time, so a schedule needs ``recapture()`` there — use ``FusedSGD``.
 
     ``criterion(outputs, labels)`` must be sync-free (``transception_b200.losses.CeDiceLoss``; the reference's ``DiceLoss``
     reads ``.item()`` per class).  Usage::
 
-        runner = TrainStepGraph(net, CeDiceLoss(9), optimizer, batch=16, in_ch=1, size=224, max_norm=5)
+        opt = FusedSGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        runner = TrainStepGraph(net, CeDiceLoss(9), opt, batch=16, in_ch=1, size=224)
         loss = runner.step(image_batch, label_batch)        # device scalar, valid after the stream reaches it
 
-    The learning-rate schedule of ``trainer.py:151-153`` writes ``param_group['lr']`` on the host; SGD reads it as a Python
-    float at capture time, so call ``recapture()`` when it changes (or use a tensor ``lr`` with ``capturable`` optimizers).
+    ``max_norm`` defaults to None like the reference (``--grad_clipping`` is off by default).
     """
 
-    def __init__(self, model, criterion, optimizer, batch, in_ch=1, size=224, device="cuda", max_norm=5.0, warmup=3,
+    def __init__(self, model, criterion, optimizer, batch, in_ch=1, size=224, device="cuda", max_norm=None, warmup=3,
                  label_dtype=torch.int64, sample=None):
         """``sample`` = (images, labels) of the first batch: the warm-up steps before capture are real training steps on it
         (otherwise they run on a zero batch)."""
         import torch.distributed as dist
+        from .optim import FusedSGD
         from .shard import GradBucket
         self.model, self.criterion, self.optimizer = model.train(), criterion, optimizer
         self.device = torch.device(device)
+        self.fused = isinstance(optimizer, FusedSGD)
+        if self.fused and max_norm is not None:
+            optimizer.max_norm = max_norm
         self.max_norm = max_norm
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket = GradBucket(model.parameters())
@@ -139,14 +152,40 @@ class TrainStepGraph:
         self._warmup = warmup
         self.recapture()
 
-    # the three phases of trainer.py:139-149
+    # the phases of trainer.py:139-149
     def _fwd_bwd(self):
+        from . import ops
+        if not self.fused:
+            # a torch optimizer moves the weights without telling the library: convert the fp16 GEMM copies again in every
+            # forward (inside the captured graph too — otherwise a replay would keep multiplying with the weights of capture time)
+            ops.invalidate_prepared(self.model)
         self.optimizer.zero_grad(set_to_none=True)
         loss = self.criterion(self.model(self.x), self.labels)
         loss.backward()
         self.loss.copy_(loss.detach())
 
+    def _allreduce(self):
+        """Average the gradients over the ranks: the optimizer's flat bucket (fused) or shard.GradBucket."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        if self.fused:
+            flat = self._flat
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.mul_(1.0 / self.world)
+        else:
+            self.bucket.allreduce()
+
+    def _gather(self):
+        self._flat = self.optimizer.gather_grads()
+
     def _update(self):
+        if self.fused:
+            self.optimizer.step(from_flat=self.world > 1)
+            return
         if self.max_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_norm, norm_type=2)
         self.optimizer.step()
@@ -158,16 +197,18 @@ class TrainStepGraph:
             raise RuntimeError("TrainStepGraph: eager steps after capture break the graphs' static gradient buffers; "
                                "use step() / replay(), or recapture()")
         self._fwd_bwd()
-        if self.world > 1:
-            self.bucket.allreduce()
+        if self.world > 1 and self.fused:
+            self._gather()
+        self._allreduce()
         self._update()
 
-    def _capture(self, fn):
-        side = torch.cuda.Stream(self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            fn()
-        torch.cuda.current_stream(self.device).wait_stream(side)
+    def _capture(self, fn, prerun=True):
+        if prerun:
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -175,9 +216,11 @@ class TrainStepGraph:
         return g
 
     def recapture(self):
-        """(Re)build the graphs from the current model / optimizer state.  ``max(warmup, 2)`` eager steps plus the one step the
-        capture recipe runs on a side stream before recording are REAL training steps on the current batch (``steps_done``
-        counts them); recording itself executes nothing."""
+        """(Re)build the graphs from the current model / optimizer state.  ``max(warmup, 2)`` eager steps (they are the warm-up
+        of the capture recipe) plus one more step completed while capturing are REAL training steps on the current batch
+        (``steps_done`` counts them); recording itself executes nothing.  Order: capture graph A, replay it so the static
+        gradient tensors hold real values, [capture + replay the gather graph, all-reduce], capture the update graph and replay
+        it once — every graph is replayed exactly once per step, so captured training equals eager training bit for bit."""
         from . import ops
         self.steps_done = getattr(self, "steps_done", 0)
         self._captured = False
@@ -187,22 +230,44 @@ class TrainStepGraph:
         self.first_loss = self.loss.clone()
         for _ in range(max(self._warmup - 1, 1)):
             self.eager_step()
-        self.steps_done += max(self._warmup, 2) + 1
+        self.steps_done += max(self._warmup, 2)
         torch.cuda.synchronize(self.device)
-        if self.world == 1:
-            self._graphs = (self._capture(self.eager_step),)
-        else:
-            ga = self._capture(self._fwd_bwd)
-            self.bucket.allreduce()
-            self._graphs = (ga, self._capture(self._update))
+        ga = self._capture(self._fwd_bwd, prerun=False)
+        ga.replay()
+        graphs = [ga]
+        if self.fused:
+            # the optimizer's tables (device arrays of parameter / gradient / momentum / fp16-copy pointers) are built here, eagerly,
+            # from the static gradient tensors of graph A: nothing is uploaded under capture
+            for gi, group in enumerate(self.optimizer.param_groups):
+                self.optimizer._group_table(gi, group)
+        if self.world > 1 and self.fused:
+            gg = self._capture(self._gather, prerun=False)
+            gg.replay()
+            graphs.append(gg)
+        self._graphs = graphs
+        if self.world > 1:
+            self._allreduce()
+        gu = self._capture(self._update, prerun=False)
+        gu.replay()
+        graphs.append(gu)
+        self.steps_done += 1
+        if self.fused:
+            ops.bump_raw_generation()
         self._captured = True
 
     def replay(self):
         """One training step on the batch currently in ``self.x`` / ``self.labels``."""
+        from . import ops
+        if self.fused:
+            self.optimizer.sync_lr()         # a changed param_group['lr'] reaches the device scalar the update graph reads
         self._graphs[0].replay()
-        if len(self._graphs) > 1:
-            self.bucket.allreduce()
-            self._graphs[1].replay()
+        if self.world > 1:
+            if self.fused:
+                self._graphs[1].replay()
+            self._allreduce()
+        self._graphs[-1].replay()
+        if self.fused:
+            ops.bump_raw_generation()
         self.steps_done += 1
 
     def step(self, x, labels):
