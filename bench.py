@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py — headline measurement for the TransCeption hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode train|forward]
 
-Workload (BASELINE.json configs[1]): TransCeption (MSTransception, 9 classes) Synapse-shaped 224x224 bs16
-fp32 *forward*, synthetic data, seeded random-init weights.  One step = one forward of one batch of 16 images
-on each GPU (weak scaling: N GPUs -> N independent batches, no data-path collective; the gradient all-reduce
-belongs to the training configs).
+Headline (default, `--mode train`) = BASELINE.json's metric, "images/sec fwd+bwd @224x224 bs16": one step = forward in train mode
++ 0.4 CE + 0.6 Dice + backward + SGD(momentum 0.9, weight decay 1e-4) on one batch of 16 synthetic 224x224 images per GPU
+(trainer.py:139-149; the reference's --grad_clipping is off by default, so no clip), seeded random-init weights; N GPUs =
+N ranks x 16 images (weak scaling) with one NCCL all-reduce (average) of the flat gradient bucket per step.
 
 Printed JSON (one line, rank 0):
-  value     images/s with the batch resident in HBM (CUDA-graph replay, CUDA-event timed, L2 flushed between steps)
-  e2e       images/s through the public call with pinned HOST buffers: H2D input copy + forward + D2H logits copy
-  roofline  the kernel with the largest share of the step (the tcgen05 GEMM), timed live with CUDA events;
-            roofline_other_kernels carries the same leg for the flash attention, dw+LN and MB attention kernels
-  cpu_baseline  the CPU oracle (a PyTorch restatement of the reference forward) on this box's host cores
-`--impl reference` times that same CPU implementation as its own arm.
+  value          images/s with the batch resident in HBM (the step replayed as CUDA graphs, CUDA-event timed, max over ranks)
+  e2e            images/s through the public call TrainStepGraph.step(pinned images, pinned labels): H2D copies + step + D2H loss
+  roofline       the kernel with the largest share of the step, timed live with CUDA events; roofline_other_kernels the next ones
+  roofline_step  the whole step against SURVEY section 8(d)'s algorithmic FLOPs / bytes
+  forward_step   the inference forward (BASELINE configs[1]) at the same batch: device-resident and end to end
+  gpu_baseline   the oracle (PyTorch restatement of the reference) on this same B200, TF32 on, eager and CUDA graph
+  cpu_baseline   the same oracle on this box's host cores (bounded sample) + bs16 parity of our numbers against it
+`--mode forward` prints the round-1 forward line (configs[1]) as the line's own metric.  `--impl reference` times the CPU
+implementation of the selected mode as its own arm.
 """
 import argparse
 import json
@@ -127,6 +130,13 @@ def cpu_reference_time(torch, steps, warmup, budget_s=150.0):
 
 
 TRAIN_METRIC = "images/sec fwd+bwd @224x224 bs16 (TransCeption MSTransception train step: forward + 0.4 CE + 0.6 Dice + backward + SGD)"
+TRAIN_WORKLOAD = ("TransCeption Synapse 224x224 bs16 train step per GPU (BASELINE configs[2]/[3] shape): forward + 0.4 CE + 0.6 Dice + "
+                  "backward + SGD(momentum 0.9, wd 1e-4), 9 classes")
+FWD_WORKLOAD = "TransCeption Synapse 224x224 bs16 fp32 forward (BASELINE configs[1]), per-GPU batch 16, 9 class logits"
+# SURVEY section 8(d) / BASELINE.md section 2: algorithmic work of the whole model, per image
+FWD_GFLOP_PER_IMG = 16.88            # forward; a train step is 3x (backward = dgrad + wgrad)
+FWD_MB_PER_IMG_BF16 = 34.0           # activation traffic at fused-kernel boundaries (encoder + bridge), bf16
+WEIGHT_MB_BF16 = 72.7                # once per batch
 
 
 def _train_inputs(torch, batch, seed):
@@ -155,8 +165,8 @@ def cpu_reference_train_time(torch, steps, warmup, budget_s=150.0):
         opt.zero_grad(set_to_none=True)
         loss = LO.ce_dice(O.forward(sd, x), labels, NCLS)[0]
         loss.backward()
-        torch.nn.utils.clip_grad_norm_([p for p in leaves if p.grad is not None], max_norm=5, norm_type=2)
         opt.step()
+        return float(loss.detach())
 
     bs = 2
     x, labels = _train_inputs(torch, BATCH, 0)
@@ -176,48 +186,157 @@ def cpu_reference_train_time(torch, steps, warmup, budget_s=150.0):
     return bs * steps / dt, cores, sample, dt / steps * 1e3
 
 
+def cpu_train_parity(torch, first_loss_ours):
+    """bs16 parity inside the cpu_baseline leg: the loss of the FIRST train step (same seeded weights, same synthetic batch)
+    from the CPU oracle against the one our step reported.  One CPU forward in train mode (no backward)."""
+    from oracle import loss_oracle as LO
+    from oracle import mstr_oracle as O
+    MSTransception = _model_cls()
+    torch.manual_seed(1234)
+    sd = {k: v.clone() for k, v in MSTransception(num_classes=NCLS, image_size=SIZE).state_dict().items()}
+    x, labels = _train_inputs(torch, BATCH, 0)
+    O.BN_TRAIN = True
+    try:
+        with torch.no_grad():
+            ref = float(LO.ce_dice(O.forward(sd, x), labels, NCLS)[0])
+    finally:
+        O.BN_TRAIN = False
+    return {"first_step_loss_oracle_bs16": ref, "first_step_loss_ours_bs16": first_loss_ours,
+            "rel_diff": abs(first_loss_ours - ref) / abs(ref), "tolerance": 2e-3}
+
+
+def gpu_baseline_leg(torch, dev, mode):
+    """The honest GPU opponent: the oracle — a plain-PyTorch restatement of the reference — on
+    this same B200 with TF32 matmuls/convs ON, eager and replayed as a CUDA graph.  Test/bench infrastructure like cpu_baseline:
+    nothing of it is on the product path."""
+    from oracle import loss_oracle as LO
+    from oracle import mstr_oracle as O
+    MSTransception = _model_cls()
+    out = {"what": "oracle port (PyTorch ops = the reference's own op sequence) on cuda:0, TF32 on", "batch": BATCH}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        torch.manual_seed(1234)
+        sd = {k: v.to(dev) for k, v in MSTransception(num_classes=NCLS, image_size=SIZE).state_dict().items()}
+        xh, lh = _train_inputs(torch, BATCH, 0)
+        x, labels = xh.to(dev), lh.to(dev)
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / n
+
+        def graphed(fn):
+            st = torch.cuda.Stream(dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(st)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return g.replay
+
+        with torch.no_grad():
+            f = lambda: O.forward(sd, x)      # noqa: E731
+            ms = timed(f, 10)
+            out["forward_eager_ms"], out["forward_eager_img_s"] = ms, BATCH / ms * 1e3
+            try:
+                ms = timed(graphed(f), 10)
+                out["forward_graph_ms"], out["forward_graph_img_s"] = ms, BATCH / ms * 1e3
+            except Exception as e:  # noqa: BLE001
+                out["forward_graph_error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+        if mode == "train":
+            leaves = {k: (v.clone().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+            params = [v for v in leaves.values() if v.requires_grad]
+            opt = torch.optim.SGD(params, lr=0.05, momentum=0.9, weight_decay=1e-4)
+            O.BN_TRAIN = True
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                loss = LO.ce_dice(O.forward(leaves, x), labels, NCLS)[0]
+                loss.backward()
+                opt.step()
+            try:
+                ms = timed(step, 5)
+                out["train_eager_ms"], out["train_eager_img_s"] = ms, BATCH / ms * 1e3
+                try:
+                    ms = timed(graphed(step), 5)
+                    out["train_graph_ms"], out["train_graph_img_s"] = ms, BATCH / ms * 1e3
+                except Exception as e:  # noqa: BLE001
+                    out["train_graph_error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+            finally:
+                O.BN_TRAIN = False
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        torch.cuda.empty_cache()
+    return out
+
+
+def _traffic_table():
+    """DRAM bytes per launch of the profiled kernels from the committed ncu --set full captures (profiles/r02_traffic.json:
+    {kernel: {"dram_bytes_per_launch": ..., "source": "profiles/..."}}); absent entries report traffic = null."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p))
+    except (OSError, ValueError):
+        return {}
+
+
 def train_step_leg(torch, dev, world, rank, K, W):
-    """fwd + loss + bwd (+ gradient all-reduce when world > 1) + clip + SGD step at bs16 per GPU, every FLOP of the model and
-    of the loss on the library's kernels (autograd nodes of transception_b200/autograd.py); clip_grad_norm_ / optim.SGD are the
-    caller's code as in trainer.py:125,148.  Timed with CUDA events; captured as one CUDA graph when world == 1."""
+    """fwd + loss + bwd (+ gradient all-reduce when world > 1) + SGD step at bs16 per GPU, every FLOP of the model, of the loss
+    and of the optimizer on the library's kernels (autograd nodes of transception_b200/autograd.py, optim.FusedSGD).  Timed with
+    CUDA events over graph replays (runtime.TrainStepGraph: the repo's public training runner)."""
     import torch.distributed as dist
     from transception_b200 import ops
     from transception_b200.losses import CeDiceLoss
+    from transception_b200.optim import FusedSGD
     from transception_b200.runtime import TrainStepGraph
     MSTransception = _model_cls()
     torch.manual_seed(1234)
     net = MSTransception(num_classes=NCLS, image_size=SIZE).to(dev).train()
-    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt = FusedSGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     xh, lh = _train_inputs(torch, BATCH, rank)
-    graphed = True
-    # the public training API of the repo: captures forward + loss + backward (+ all-reduce) + clip + SGD; its warm-up steps
-    # are real steps on this batch
-    runner = TrainStepGraph(net, CeDiceLoss(NCLS), opt, BATCH, IN_CH, SIZE, device=dev, max_norm=5.0, warmup=W, sample=(xh, lh))
+    runner = TrainStepGraph(net, CeDiceLoss(NCLS), opt, BATCH, IN_CH, SIZE, device=dev, warmup=W, sample=(xh, lh))
     launches = runner.kernels_per_step
-    x, labels, loss_buf, step, run = runner.x, runner.labels, runner.loss, runner.eager_step, runner.replay
+    x, labels, loss_buf, run = runner.x, runner.labels, runner.loss, runner.replay
     first_loss = float(runner.first_loss)
     run()
     torch.cuda.synchronize(dev)
-    grads_match = None
+    grads_match = weights_match = None
     if world > 1:
         # SURVEY 8d config 4: the all-reduced gradient must equal the mean of the ranks' own gradients (identical weights,
         # rank-specific data, per-rank BatchNorm statistics) and be identical on every rank afterwards
         runner._graphs[0].replay()          # forward + loss + backward graph: writes the static gradient tensors
         torch.cuda.synchronize(dev)
-        with_grad = [p for p in net.parameters() if p.grad is not None]
-        sample = [with_grad[i] for i in (0, len(with_grad) // 3, 2 * len(with_grad) // 3, len(with_grad) - 1)]
-        own = torch.cat([p.grad.flatten()[:4096].clone() for p in sample])
+        tab = opt._tables[0]
+        with_grad = tab["used"]
+        pick = [0, len(with_grad) // 3, 2 * len(with_grad) // 3, len(with_grad) - 1]
+        own = torch.cat([with_grad[i].grad.flatten()[:4096].clone() for i in pick])
         gathered = [torch.empty_like(own) for _ in range(world)]
         dist.all_gather(gathered, own)
         want = torch.stack(gathered).mean(0)
-        runner.bucket.allreduce()
-        got = torch.cat([p.grad.flatten()[:4096] for p in sample])
+        runner._graphs[1].replay()          # gather into the flat bucket
+        runner._allreduce()
+        offs = tab["offs"].tolist()
+        got = torch.cat([tab["flat"][offs[i]:offs[i] + min(4096, with_grad[i].numel())] for i in pick])
         mean_ok = bool((got - want).abs().max() <= 1e-6 * want.abs().max() + 1e-12)
-        chk = torch.stack([torch.stack([p.grad.double().sum(), p.grad.double().abs().sum()]) for p in with_grad]).sum(0)
+        chk = torch.stack([tab["flat"].double().sum(), tab["flat"].double().abs().sum()])
         allc = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         grads_match = mean_ok and all(torch.equal(allc[0], c) for c in allc)
-        runner._graphs[1].replay()          # clip + SGD graph
+        runner._graphs[-1].replay()         # SGD update from the reduced bucket
+        ops.bump_raw_generation()
     for _ in range(2):
         run()
     torch.cuda.synchronize(dev)
@@ -233,62 +352,87 @@ def train_step_leg(torch, dev, world, rank, K, W):
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    # end to end: the step's batch comes from pinned host memory and the loss is read back, every step
+    # end to end through the public call: the step's batch comes from pinned host memory and the loss is read back, every step
     xp, lp = xh.pin_memory(), lh.pin_memory()
     lossh = torch.zeros((), dtype=torch.float32).pin_memory()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
     e2.record()
     for _ in range(K):
-        x.copy_(xp, non_blocking=True)
-        labels.copy_(lp, non_blocking=True)
-        run()
-        lossh.copy_(loss_buf, non_blocking=True)
+        lossh.copy_(runner.step(xp, lp), non_blocking=True)
     e3.record()
     torch.cuda.synchronize(dev)
     e2e_ms = e2.elapsed_time(e3)
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # data-parallel training keeps the replicas identical: every rank's weights after the same number of steps
+        chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum().reshape(1)
+        allw = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allw, chk)
+        weights_match = all(torch.equal(allw[0], c) for c in allw)
     ms, e2e_ms = t.tolist()
-    # roofline leg of the dominant kernel of the step (the tcgen05 GEMM: forward, dgrad and token-split wgrad launches), timed live
-    # with CUDA-event pairs on the launching streams over one eager step; algorithmic bytes are counted by the library per launch
-    rl = None
+    last_loss = float(lossh)
+    # roofline legs: the kernels with the largest shares of the step, each timed live with CUDA-event pairs on the launching
+    # stream over one eager step (serial: no stream forks, no PDL); algorithmic bytes are counted by the library per launch
+    legs, traffic = [], _traffic_table()
     try:
         peaks, peak_kind = _peaks()
-        ops.profile_enable("gemm_tc")
-        torch.cuda.synchronize(dev)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # the measurement is over: this eager step (new gradient tensors) retires the captured graphs
-        t0.record()
-        runner._fwd_bwd()
-        if world > 1:
-            runner.bucket.allreduce()
-        runner._update()
-        t1.record()
-        torch.cuda.synchronize(dev)
-        k_ms, k_n, k_work = ops.profile_read_work()
+        ops.set_flag("fork", 0)
+        ops.set_flag("pdl", 0)
+        from transception_b200 import mstr as _mstr
+        _mstr.TRAIN_BRANCH_STREAMS = False
+        runner._captured = False             # the measurement is over: eager steps (new gradient tensors) retire the graphs
+        for kname in ("gemm_tc", "wgrad_tc", "dwln", "bwd_ln_rows", "bwd_dw_wgrad", "dwconv3x3"):
+            ops.profile_enable(kname)
+            torch.cuda.synchronize(dev)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(200_000_000)   # ~0.1 s spin: the host enqueues the step behind it, so brackets see back-to-back kernels
+            t0.record()
+            runner.eager_step()
+            t1.record()
+            torch.cuda.synchronize(dev)
+            k_ms, k_n, k_work = ops.profile_read_work()
+            ops.profile_enable("")
+            if k_n and k_work > 0:
+                ach = k_work / (k_ms * 1e-3) / 1e9
+                tr = traffic.get(kname, {})
+                legs.append({"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / peaks["hbm_gbs"], "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                             "algorithmic_bytes_per_launch": k_work / k_n, "launches_per_step": k_n, "avg_launch_ms": k_ms / k_n,
+                             "ms_per_step": k_ms, "share_of_step": k_ms / t0.elapsed_time(t1),
+                             "share_basis": "event-bracketed launches of one eager, serial (no forks / PDL) step of %.1f ms; event pairs "
+                                            "add 2-4 us per launch, so small-kernel numbers are lower bounds" % t0.elapsed_time(t1),
+                             "peak_source": peak_kind + " hbm copy"})
+        legs.sort(key=lambda r: -r["ms_per_step"])
+    except Exception as e:  # noqa: BLE001
+        legs = [{"error": "%s: %s" % (type(e).__name__, e)}]
         ops.profile_enable("")
-        if k_n:
-            ach = k_work / (k_ms * 1e-3) / 1e9
-            rl = {"kernel": "gemm_tc", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": ach / peaks["hbm_gbs"], "traffic": None, "launches_per_step": k_n, "avg_launch_ms": k_ms / k_n,
-                  "ms_per_step": k_ms, "share_of_step": k_ms / (ms / K),
-                  "share_basis": "sum of the event-bracketed launch durations of one eager step over the graph-replayed step time "
-                                 "(%.1f ms); launches overlap on forked streams and event pairs add 2-4 us each, so the share is an "
-                                 "upper bound" % (ms / K),
-                  "peak_source": peak_kind + " hbm copy"}
-    except Exception as e:
-        rl = {"error": "%s: %s" % (type(e).__name__, e)}
-        ops.profile_enable("")
+    finally:
+        ops.set_flag("fork", 1)
+        ops.set_flag("pdl", 1)
     imgs = world * BATCH * K
-    return {"metric": TRAIN_METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / K, "roofline": rl,
+    step_s = ms / K * 1e-3
+    peaks, peak_kind = _peaks()
+    tf = 3 * FWD_GFLOP_PER_IMG * BATCH / step_s / 1e3
+    tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    return {"metric": TRAIN_METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / K,
+            "roofline": legs[0] if legs else None, "roofline_other_kernels": legs[1:],
+            "roofline_step": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                              "basis": "SURVEY 8(d): 3 x %.2f GFLOP per image (forward algorithmic FLOPs of the whole model; backward = "
+                                       "dgrad + wgrad) x %d images per GPU over the measured step; %s bf16 sustained peak"
+                                       % (FWD_GFLOP_PER_IMG, BATCH, peak_kind)},
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4},
-            "cuda_graph": graphed, "library_kernels_per_step": launches, "first_loss": first_loss, "last_loss": float(lossh),
-            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "allreduced_grads_equal_rank_mean_and_identical_across_ranks": grads_match,
-            "grad_allreduce": "one flat-bucket NCCL all-reduce (average) per step" if world > 1 else None,
-            "dtype": "fp16/TF32 tensor-core forward, TF32 tensor-core + fp32 backward, fp32 master weights and gradients"}
+                    "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4,
+                    "api": "TrainStepGraph.step(pinned images, pinned labels) + loss read back, every step"},
+            "cuda_graph": True, "library_kernels_per_step": launches, "first_loss": first_loss, "last_loss": last_loss,
+            "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "allreduced_grads_equal_rank_mean_and_identical_across_ranks": grads_match,
+            "weights_identical_across_ranks_after_training": weights_match,
+            "grad_allreduce": ("gradients gathered into one flat fp32 bucket by one kernel, one NCCL all-reduce (average), the fused "
+                               "update reads the bucket in place") if world > 1 else None,
+            "dtype": "fp16 storage / fp16+TF32 tensor-core forward, TF32 tensor-core backward (operands read in place), fp32 "
+                     "accumulation, gradients, master weights and optimizer state"}
 
 
 def run_reference(args):
@@ -298,68 +442,26 @@ def run_reference(args):
         return
     if args.mode == "train":
         ips, cores, sample, ms = cpu_reference_train_time(torch, args.steps, args.warmup)
-        print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "TransCeption Synapse 224x224 bs16 train step (reference algorithm, CPU)"},
-                          "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
-        return
-    ips, cores, sample, ms = cpu_reference_time(torch, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TransCeption Synapse 224x224 bs16 fp32 forward (reference algorithm, CPU)"},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line))
+        metric, workload = TRAIN_METRIC, TRAIN_WORKLOAD
+    else:
+        ips, cores, sample, ms = cpu_reference_time(torch, args.steps, args.warmup)
+        metric, workload = METRIC, FWD_WORKLOAD
+    print(json.dumps({"impl": "reference", "metric": metric, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+                      "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
 
 
-def run_ours(args):
-    import torch
+def forward_leg(torch, dev, world, rank, local, K, W, args, with_kernel_legs):
+    """The inference forward (BASELINE configs[1]) at bs16: device-resident graph replay with an L2 flush between steps, end to
+    end through GraphRunner.run_host, and (optionally) the per-kernel roofline legs."""
     import torch.distributed as dist
     from transception_b200 import ops
     from transception_b200.runtime import GraphRunner
     MSTransception = _model_cls()
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ops.load_library()
     peaks, peak_kind = _peaks()
-
-    if args.mode == "train":
-        sampler = ClockSampler(local) if rank == 0 else None
-        tr = train_step_leg(torch, dev, world, rank, args.steps, max(args.warmup, 3))
-        clocks = sampler.stop() if sampler else None
-        if rank == 0:
-            line = {"metric": tr["metric"], "value": tr["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
-                    "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                    "vs_baseline": None, "dtype": tr["dtype"], "data": "synthetic",
-                    "config": {"workload": "TransCeption Synapse 224x224 bs16 train step per GPU (BASELINE configs[2]/[3] shape): "
-                                           "forward + 0.4 CE + 0.6 Dice + backward + clip + SGD, 9 classes",
-                               "l2": "step footprint (activations saved for backward, > 2 GB) exceeds L2",
-                               "timing": "CUDA events around K steps; max over ranks",
-                               "graph": ("eager launches" if not tr["cuda_graph"] else "whole train step replayed as one CUDA graph"
-                                         if world == 1 else "forward+loss+backward graph, eager NCCL all-reduce, clip+SGD graph")},
-                    "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_kernels_per_step"] * args.steps,
-                    "roofline": tr["roofline"],
-                    "train": {k: tr[k] for k in ("cuda_graph", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce", "peak_memory_gb",
-                                                   "allreduced_grads_equal_rank_mean_and_identical_across_ranks")}}
-            if not args.no_cpu and world == 1:
-                ips, cores, sample, _ = cpu_reference_train_time(torch, 1, 1, budget_s=40.0)
-                line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
-            print(json.dumps(line))
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     torch.manual_seed(1234)
     net = MSTransception(num_classes=NCLS, image_size=SIZE).eval().to(dev)
     runner = GraphRunner(net, BATCH, IN_CH, SIZE, device=dev, microbatches=args.microbatches)
@@ -368,7 +470,6 @@ def run_ours(args):
     runner.x.copy_(x_host)
     kernels_per_replay = runner.kernels_per_replay
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    K, W = args.steps, max(args.warmup, 3)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -405,6 +506,8 @@ def run_ours(args):
     # ---- per-kernel roofline legs, timed live (eager launches, CUDA events on the launching stream) --------
     # work = algorithmic bytes (HBM-bound kernels) or FLOPs (flash) summed by the library over the timed launches
     KERNELS = (("gemm_tc", "hbm"), ("dwln", "hbm"), ("mb_fused16", "hbm"), ("flash_tc", "tensor"), ("flash_ffma", "tensor"))
+    if not with_kernel_legs:
+        KERNELS = ()
     legs = []
     reps = max(3, min(K, 5))
     ops.set_flag("fork", 0)      # serial kernels for attribution: concurrent branches would share SMs inside a bracket
@@ -432,62 +535,127 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = t.tolist()
-    # the training row (fwd + loss + bwd + SGD at the same bs16): reported beside the forward headline; `--mode train` makes
-    # it the line's own metric.  Never allowed to take the forward measurement down with it.
-    train_line = None
-    if MODEL == "MSTransception" and not args.no_train:
-        del runner
-        torch.cuda.empty_cache()
-        try:
-            tr = train_step_leg(torch, dev, world, rank, max(5, min(K, 20)), 3)
-            train_line = {k: tr[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "cuda_graph",
-                                              "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce", "dtype",
-                                              "peak_memory_gb")}
-        except Exception as e:
-            train_line = {"error": "%s: %s" % (type(e).__name__, e)}
+    imgs = world * BATCH * K
+    out = {"metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s", "ms_per_step": dev_ms / K, "clocks": clocks,
+           "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
+                   "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
+                   "api": "GraphRunner.run_host(pinned x, pinned logits): every step copies its input H2D, replays the forward and "
+                          "copies its logits D2H; the D2H runs on a copy stream and overlaps the next step"},
+           "gpu_launches": kernels_per_replay * K, "kernels_per_forward": kernels_per_replay,
+           "dtype": "f16/tf32 tensor-core MMA, f32 accumulate, f32 IO"}
+    step_s = dev_ms / K * 1e-3
+    tf = FWD_GFLOP_PER_IMG * BATCH / step_s / 1e3
+    gbs = (FWD_MB_PER_IMG_BF16 * BATCH + WEIGHT_MB_BF16) / 1e3 / step_s
+    tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    out["roofline_step"] = {"tensor": {"achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak},
+                            "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]},
+                            "basis": "SURVEY 8(d): %.2f GFLOP and %.1f MB (bf16 fused-kernel boundaries) per image + %.1f MB weights per batch"
+                                     % (FWD_GFLOP_PER_IMG, FWD_MB_PER_IMG_BF16, WEIGHT_MB_BF16)}
+    traffic = _traffic_table()
+    rl = []
+    for g in legs:
+        if g["bound"] == "hbm":
+            ach, peak, unit, src = g["work"] / (g["ms"] * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s", peak_kind + " hbm copy"
+        else:
+            peak = tpeak
+            ach, unit, src = g["work"] / (g["ms"] * 1e-3) / 1e12, "TFLOP/s", peak_kind + " bf16 sustained"
+        tr = traffic.get(g["kernel"], {})
+        rl.append({"kernel": g["kernel"], "bound": g["bound"], "achieved": ach, "peak": peak, "unit": unit,
+                   "frac": ach / peak, "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                   "launches_per_step": g["launches_per_step"],
+                   "avg_launch_ms": g["ms"] / g["n"], "ms_per_step": g["per_step_ms"],
+                   "share_of_step": g["per_step_ms"] / g["eager_step_ms"],
+                   "share_basis": "eager, serial (no fork / PDL) forward of %.2f ms bracketed in the same run; the "
+                                  "event pair around every launch adds ~2-4 us, so small-kernel times are upper bounds"
+                                  % g["eager_step_ms"],
+                   "peak_source": src})
+    rl.sort(key=lambda r: -r["ms_per_step"])
+    out["kernel_legs"] = rl
+    del runner, net
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from transception_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.load_library()
+    K, W = args.steps, max(args.warmup, 3)
+    headline = MODEL == "MSTransception" and (SIZE, NCLS, IN_CH) == (224, 9, 1)
+
+    if args.mode == "train":
+        sampler = ClockSampler(local) if rank == 0 else None
+        tr = train_step_leg(torch, dev, world, rank, K, W)
+        clocks = sampler.stop() if sampler else None
+        fwd = None
+        if not args.no_forward:
+            try:
+                fwd = forward_leg(torch, dev, world, rank, local, max(5, min(K, 20)), 3, args, with_kernel_legs=False)
+                fwd.pop("clocks", None)
+            except Exception as e:  # noqa: BLE001
+                fwd = {"error": "%s: %s" % (type(e).__name__, e)}
+        if rank == 0:
+            line = {"metric": tr["metric"] if headline else tr["metric"] + " [non-headline workload: %s %dx%d %d classes]" % (MODEL, SIZE, SIZE, NCLS),
+                    "value": tr["value"], "unit": "images/s", "n_gpus": world, "steps": K,
+                    "warmup": W, "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": tr["dtype"], "data": "synthetic",
+                    "config": {"workload": TRAIN_WORKLOAD if headline else "TransCeption %s %dx%d bs16 train step, %d classes" % (MODEL, SIZE, SIZE, NCLS),
+                               "l2": "step footprint (activations saved for backward, > 2 GB) exceeds L2",
+                               "timing": "CUDA events around K steps; max over ranks",
+                               "graph": ("forward+loss+backward graph and fused-SGD graph" if world == 1 else
+                                         "forward+loss+backward graph, gradient-gather graph, eager NCCL all-reduce, fused-SGD graph")},
+                    "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_kernels_per_step"] * K,
+                    "roofline": tr["roofline"], "roofline_other_kernels": tr["roofline_other_kernels"], "roofline_step": tr["roofline_step"],
+                    "train": {k: tr[k] for k in ("cuda_graph", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce",
+                                                   "peak_memory_gb", "allreduced_grads_equal_rank_mean_and_identical_across_ranks",
+                                                   "weights_identical_across_ranks_after_training")},
+                    "forward_step": fwd}
+            if world == 1 and not args.no_gpu_baseline:
+                try:
+                    line["gpu_baseline"] = gpu_baseline_leg(torch, dev, "train")
+                except Exception as e:  # noqa: BLE001
+                    line["gpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            if not args.no_cpu and world == 1:
+                ips, cores, sample, _ = cpu_reference_train_time(torch, 1, 1, budget_s=40.0)
+                line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+                if headline:
+                    line["cpu_baseline"]["parity_bs16"] = cpu_train_parity(torch, tr["first_loss"])
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fwd = forward_leg(torch, dev, world, rank, local, K, W, args, with_kernel_legs=True)
     if rank == 0:
-        imgs = world * BATCH * K
-        line = {"metric": METRIC, "value": imgs / (dev_ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f16/tf32 tensor-core MMA, f32 accumulate, f32 IO", "data": "synthetic",
-                "config": {"workload": "TransCeption Synapse %dx%d bs16 fp32 forward (%s), "
-                                       "per-GPU batch 16, %d class logits" % (
-                                           SIZE, SIZE, "BASELINE configs[1]" if SIZE == 224 and NCLS == 9 and MODEL == "MSTransception" else
-                                           "non-headline workload: " + MODEL, NCLS),
+        line = {"metric": METRIC, "value": fwd["value"], "unit": "images/s", "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": fwd["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": fwd["dtype"], "data": "synthetic",
+                "config": {"workload": FWD_WORKLOAD if headline else "TransCeption %s %dx%d bs16 fp32 forward, %d class logits [non-headline]" % (MODEL, SIZE, SIZE, NCLS),
                            "l2": "256 MiB memset between timed steps (untimed); step footprint > L2",
                            "timing": "per-step CUDA events on the replay stream, summed; max over ranks",
                            "graph": "whole forward replayed as one CUDA graph"},
-                "clocks": clocks,
-                "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
-                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
-                        "api": "GraphRunner.run_host(pinned x, pinned logits): every step copies its input H2D, replays "
-                               "the forward and copies its logits D2H; the D2H runs on a copy stream and overlaps the "
-                               "next step"},
-                "gpu_launches": kernels_per_replay * K}
-        step_ms = dev_ms / K
-        rl = []
-        for g in legs:
-            if g["bound"] == "hbm":
-                ach, peak, unit, src = g["work"] / (g["ms"] * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s", peak_kind + " hbm copy"
-            else:
-                peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-                ach, unit, src = g["work"] / (g["ms"] * 1e-3) / 1e12, "TFLOP/s", peak_kind + " bf16 sustained"
-            rl.append({"kernel": g["kernel"], "bound": g["bound"], "achieved": ach, "peak": peak, "unit": unit,
-                       "frac": ach / peak, "traffic": None, "launches_per_step": g["launches_per_step"],
-                       "avg_launch_ms": g["ms"] / g["n"], "ms_per_step": g["per_step_ms"],
-                       "share_of_step": g["per_step_ms"] / g["eager_step_ms"],
-                       "share_basis": "eager, serial (no fork / PDL) forward of %.2f ms bracketed in the same run; the "
-                                      "event pair around every launch adds ~2-4 us, so small-kernel times are upper bounds"
-                                      % g["eager_step_ms"],
-                       "peak_source": src})
-        rl.sort(key=lambda r: -r["ms_per_step"])
+                "clocks": fwd["clocks"], "e2e": fwd["e2e"], "gpu_launches": fwd["gpu_launches"], "roofline_step": fwd["roofline_step"]}
+        rl = fwd["kernel_legs"]
         if rl:
             line["roofline"] = rl[0]                 # the kernel with the largest share of the step
             line["roofline_other_kernels"] = rl[1:]
+        if world == 1 and not args.no_gpu_baseline:
+            try:
+                line["gpu_baseline"] = gpu_baseline_leg(torch, dev, "forward")
+            except Exception as e:  # noqa: BLE001
+                line["gpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         if not args.no_cpu and world == 1:
             ips, cores, sample, _ = cpu_reference_time(torch, 3, 1, budget_s=40.0)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
-        line["train_step"] = train_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -501,9 +669,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
-                    help="forward = BASELINE configs[1] (headline); train = the bs16 train step (fwd + loss + bwd + SGD)")
-    ap.add_argument("--no-train", action="store_true", help="forward mode: skip the train_step leg")
+    ap.add_argument("--mode", default="train", choices=["forward", "train"],
+                    help="train = BASELINE.json's metric (fwd+bwd bs16 train step, the headline); forward = configs[1]")
+    ap.add_argument("--no-forward", action="store_true", help="train mode: skip the forward_step leg")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the gpu_baseline leg (oracle on the same GPU)")
     ap.add_argument("--size", type=int, default=SIZE, help="input side (default 224 = the headline workload; 256 = config 5)")
     ap.add_argument("--classes", type=int, default=NCLS)
     ap.add_argument("--in-ch", type=int, default=IN_CH)
