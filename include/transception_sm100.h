@@ -290,14 +290,14 @@ int tcx_mt_sgd(const void* param_ptrs, const void* grad_ptrs, const void* buf_pt
 
 /* MixFFN_skip training forward: the arithmetic of tcx_mixffn_skip_fwd (fp16 pipeline only: fc1 / fc2 must be prepared),
  * keeping in `saved` (tcx_mixffn_skip_saved_bytes, opaque) what backward needs: fp16 xn, fc1 output, GELU output and the
- * fp32 LayerNorm input.  tcx_mixffn_skip_bwd: dy [B*N][C] = dL/dy -> dxn [B*N][C] (NULL: skipped) and the eight parameter
+ * fp32 LayerNorm input.  xn32 (nullable) = the fp32 xn the forward was given: the in-place TF32 operand of fc1's weight gradient.  tcx_mixffn_skip_bwd: dy [B*N][C] = dL/dy -> dxn [B*N][C] (NULL: skipped) and the eight parameter
  * gradients dp = {d fc1_w, d fc1_b, d dw_w, d dw_b, d ln_w, d ln_b, d fc2_w, d fc2_b} (device pointers, shapes of p). */
 size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4);
 int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
                               int W, int C, int C4, void* saved, void* stream);
 size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4);
-int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, float* dxn, void* const* dp, int B,
-                        int H, int W, int C, int C4, void* ws, void* stream);
+int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, const float* xn32, float* dxn,
+                        void* const* dp, int B, int H, int W, int C, int C4, void* ws, void* stream);
 
 /* EfficientAttention (MSTr.py:106-143) training forward (arithmetic of tcx_eff_attn_fwd with reinterpret = 0; fp16 pipeline
  * only) and backward.  `saved` keeps the fp16 LayerNorm output, K | Q | V, the channel-softmax queries, the context and

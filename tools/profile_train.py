@@ -17,7 +17,8 @@ def main():
     torch.manual_seed(1234)
     net = MSTransception(num_classes=9).to(dev).train()
     crit = CeDiceLoss(9)
-    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    from transception_b200.optim import FusedSGD
+    opt = FusedSGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(16, 1, 224, 224, generator=g) * 2 - 1).to(dev)
     labels = torch.randint(0, 9, (16, 224, 224), generator=g).to(dev)
@@ -26,7 +27,6 @@ def main():
         opt.zero_grad(set_to_none=True)
         loss = crit(net(x), labels)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=5, norm_type=2)
         opt.step()
         return loss
 

@@ -44,17 +44,19 @@ class MixFFNSkipFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b):
+        x = x.contiguous()
         y, saved = ops.mixffn_skip_train(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b)
-        ctx.save_for_backward(saved, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)
+        # x (the LayerNorm output) is kept in fp32: fc1's weight gradient reads it in place as a TF32 operand
+        ctx.save_for_backward(saved, x, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)
         ctx.geom = (x.shape[0], H, W, eps)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        saved, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b = ctx.saved_tensors
+        saved, x, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b = ctx.saved_tensors
         B, H, W, eps = ctx.geom
         dx, g = ops.mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
-                                    need_dx=ctx.needs_input_grad[0])
+                                    need_dx=ctx.needs_input_grad[0], xn=x)
         return (dx, None, None, None) + tuple(g)
 
 

@@ -2112,10 +2112,14 @@ int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_ep
 size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4) {
   const long long M = (long long)B * N;
   const size_t lin = std::max(linear_bwd_ws_floats(M, C, C4), linear_bwd_ws_floats(M, C4, C));
-  return 4 * (2 * rnd((size_t)M * C4) + rnd(2 * (size_t)M) + rnd(9 * (size_t)C4) + rnd(10 * (size_t)bwd_red_blocks(M) * C4) + lin + 64);
+  const size_t part = std::max((size_t)10 * bwd_red_blocks(M) * C4, (size_t)10 * dw_bwd_fused_blocks(M, C4) * C4);
+  return 4 * (3 * rnd((size_t)M * C4) + rnd(2 * (size_t)M) + rnd(9 * (size_t)C4) + rnd(part) + rnd(2 * (size_t)bwd_red_blocks(M) * C4) +
+              2 * lin + 64);
 }
-int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, float* dxn, void* const* dp, int B,
-                        int H, int W, int C, int C4, void* ws, void* stream) {
+// xn32 (nullable): the fp32 LayerNorm output the forward was given (the TF32 operand of fc1's weight gradient); without it the
+// saved fp16 copy is converted.
+int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, const float* xn32, float* dxn,
+                        void* const* dp, int B, int H, int W, int C, int C4, void* ws, void* stream) {
   TCX_REQUIRE(dy && p && saved && dp && ws, "mixffn_skip_bwd: null pointer");
   for (int i = 0; i < 8; i++) TCX_REQUIRE(dp[i] != nullptr, "mixffn_skip_bwd: gradient slot %d is null", i);
   cudaStream_t st = S(stream);
@@ -2124,11 +2128,38 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
   Carver c(ws);
   float* da = c.take((size_t)M * C4);      // dL/d a (fc2 input), later dL/d h
   float* du = c.take((size_t)M * C4);      // dL/d u (LayerNorm input)
+  float* a32 = c.take((size_t)M * C4);     // GELU(LN(u)) recomputed in fp32
   float* stats = c.take(2 * (size_t)M);
   float* wflip = c.take(9 * (size_t)C4);
-  float* part = c.take(10 * (size_t)bwd_red_blocks(M) * C4);
-  float* lin = c.take(0);
+  float* part = c.take(std::max((size_t)10 * bwd_red_blocks(M) * C4, (size_t)10 * dw_bwd_fused_blocks(M, C4) * C4));
+  float* part_ln = c.take(2 * (size_t)bwd_red_blocks(M) * C4);
+  float* lin = c.take(linear_bwd_ws_floats(M, C, C4) > linear_bwd_ws_floats(M, C4, C) ? linear_bwd_ws_floats(M, C, C4)
+                                                                                       : linear_bwd_ws_floats(M, C4, C));
+  float* lin2 = c.take(0);
   auto G = [&](int i) { return reinterpret_cast<float*>(dp[i]); };
+  const bool fused = g_flag_wgrad_tc && ln_bwd_fused_ok(M, C4) && linear_bwd_mn_ok(M, C, C4) && linear_bwd_mn_ok(M, C4, C);
+  if (fused) {
+    // critical chain on `st`: dgrad fc2 -> LN/GELU backward -> depthwise backward -> dgrad fc1; the weight gradients and the
+    // folds of the parameter sums hang off it on an auxiliary stream (nothing downstream of this call waits on them but the join)
+    AuxStreams* aux = aux_streams(st);
+    cudaStream_t sa = aux ? aux->s[1] : st;
+    TCX_TRY(run_linear_bwd(nullptr, 0, F(p[6]), dy, da, nullptr, nullptr, M, C, C4, lin, st));               // da = dy W2
+    TCX_TRY(launch_ln_bwd_fused(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, a32, M, C4, part_ln, st));
+    float* dh = da;
+    TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part, st));
+    if (aux) {
+      TCX_REQUIRE(cudaEventRecord(aux->fork, st) == cudaSuccess && cudaStreamWaitEvent(sa, aux->fork, 0) == cudaSuccess,
+                  "mixffn_skip_bwd: fork failed");
+    }
+    TCX_TRY(run_linear_bwd(a32, 0, F(p[6]), dy, nullptr, G(6), G(7), M, C, C4, lin2, sa));                   // dW2 = dy^T a, db2
+    TCX_TRY(launch_bwd_ln_fold(part_ln, ln_bwd_fused_blocks(M), C4, G(4), G(5), sa));
+    TCX_TRY(launch_bwd_dw_fold(part, dw_bwd_fused_blocks(M, C4), C4, G(2), G(3), sa));
+    // fc1: dxn = dh W1 on the main stream, dW1 = dh^T xn beside it
+    const void* xn = xn32 ? (const void*)xn32 : (const void*)s.xn16;
+    TCX_TRY(run_linear_bwd(xn, xn32 ? 0 : 1, F(p[0]), dh, dxn, G(0), G(1), M, C4, C, lin, st));
+    if (aux) TCX_TRY(join_stream(aux, 1, st));
+    return 0;
+  }
   // fc2: a16 [M][C4] -> y [M][C]
   TCX_TRY(run_linear_bwd(s.a16, 1, F(p[6]), dy, da, G(6), G(7), M, C, C4, lin, st));
   // GELU(LayerNorm(u))

@@ -397,6 +397,15 @@ int launch_bwd_colsum(const float* x, long long M, int C, int ld, float* part, f
   return launch_bwd_fold(part, nblk, C, out, st);
 }
 
+int launch_bwd_ln_fold(const float* part, int nblk, int C, float* dgamma, float* dbeta, cudaStream_t st) {
+  bwd_ln_fold_kernel<<<cdiv(2 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dgamma, dbeta);
+  return tcx_check_launch("bwd_ln_fold");
+}
+int launch_bwd_dw_fold(const float* part, int nblk, int C, float* dw, float* db, cudaStream_t st) {
+  bwd_dw_fold_kernel<<<cdiv(10 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dw, db);
+  return tcx_check_launch("bwd_dw_fold");
+}
+
 int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
                   float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st) {
   TCX_REQUIRE(C % 4 == 0 && C > 0, "bwd_ln: C %% 4 != 0 (C=%d)", C);
@@ -405,6 +414,10 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
     cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
     return 0;
+  }
+  if (ln_bwd_fused_ok(M, C)) {      // one pass over (u, dz) instead of a row pass + a column pass
+    TCX_TRY(launch_ln_bwd_fused(u, dz, gamma, beta, eps, gelu, du, nullptr, M, C, part, st));
+    return launch_bwd_ln_fold(part, ln_bwd_fused_blocks(M), C, dgamma, dbeta, st);
   }
   const unsigned rb = (unsigned)((M + 7) / 8);
   const int rows = red_rows_per_block(M), nblk = bwd_red_blocks(M);

@@ -48,6 +48,21 @@ int launch_bwd_colsum(const float* x, long long M, int C, int ld, float* part, f
 int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
                   float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st);
 
+// fused forms (bwd_mix.cu): one pass per tensor.  launch_bwd_ln uses the fused kernel by itself whenever ln_bwd_fused_ok.
+bool ln_bwd_fused_ok(long long M, int C);
+int ln_bwd_fused_blocks(long long M);
+// du = LayerNorm (gelu: GELU o LayerNorm) backward of dz at u; act (nullable, gelu only) = fp32 GELU(LN(u)); part: 2 * blocks * C
+// column partials to be folded with launch_bwd_ln_fold
+int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
+                        float* act, long long M, int C, float* part, cudaStream_t st);
+int launch_bwd_ln_fold(const float* part, int nblk, int C, float* dgamma, float* dbeta, cudaStream_t st);
+// Mix-FFN depthwise conv backward in one pass: dh = du + conv^T(du), part = 10 * blocks * C filter / bias partials (fold with
+// launch_bwd_dw_fold); h is the fp16 fc1 output
+int dw_bwd_fused_blocks(long long M, int C);
+int launch_dw_bwd_fused(const float* du, const __half* h, const float* w, float* dh, int B, int H, int W, int C, float* part,
+                        cudaStream_t st);
+int launch_bwd_dw_fold(const float* part, int nblk, int C, float* dw, float* db, cudaStream_t st);
+
 // depthwise 3x3 (stride 1, pad 1, DWConv MSTr.py:26-31) weight / bias gradient:
 //   dw[c][ky][kx] = sum_p du[p][c] * h[p + (ky-1, kx-1)][c],  db[c] = sum_p du[p][c];   h is fp16 [B,H,W,C]
 // part: 10 * bwd_red_blocks(B*H*W) * C floats

@@ -1,0 +1,255 @@
+// Fused backward of the Mix-FFN middle (MixFFN_skip.forward MSTr.py:59: a = GELU(LN(u)), u = dw3x3(h) + b + h) and of plain
+// LayerNorm: the round-1 path read every [tokens][C] tensor three to four times (row pass, column pass, flip + conv as input
+// gradient, weight-gradient pass) in seven launches; here
+//   ln_bwd_fused  : ONE pass over (u, dz): per-row statistics, du, optionally a = GELU(LN(u)) in fp32 (the TF32 operand of fc2's
+//                   weight gradient), and the per-column sums of d gamma / d beta carried in registers across the rows of a warp;
+//   dw_bwd_fused  : ONE pass over (du, h): dh = du + conv^T(du) (input gradient incl. the skip) and the 9 + 1 per-channel filter /
+//                   bias sums, 4 channels per thread with 16-byte accesses;
+// each leaves one partial per block, folded in block order by the existing fold kernels (bit-reproducible, no atomics).
+#include "bwd.cuh"
+
+namespace {
+
+constexpr int LF_WARPS = 8;
+constexpr int LF_MAX_BLOCKS = 296;
+
+__device__ __forceinline__ void gelu_parts(float z, float& gelu, float& dgelu) {
+  const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * z * z);
+  gelu = z * cdf;
+  dgelu = fmaf(z, pdf, cdf);
+}
+
+// One warp per row, NV float4 chunks per lane (columns lane*4 + 128*j); rows are dealt round-robin over all warps of the grid.
+// part: [gridDim.x][2][C] = (sum g*xhat | sum g) of the rows this block handled.
+template <int NV, bool GELU>
+__global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ dz,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                    float* __restrict__ du, float* __restrict__ act, long long M, int C,
+                                                                    float* __restrict__ part) {
+  __shared__ float sm[LF_WARPS][2][NV * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invC = 1.0f / (float)C;
+  float4 g4[NV], b4[NV];
+  bool live[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const int c = lane * 4 + 128 * j;
+    live[j] = c < C;
+    g4[j] = live[j] ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b4[j] = (GELU && live[j]) ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float ag[NV][4], ab[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; j++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) { ag[j][q] = 0.f; ab[j][q] = 0.f; }
+
+  const long long stride = (long long)gridDim.x * LF_WARPS;
+  for (long long row = (long long)blockIdx.x * LF_WARPS + warp; row < M; row += stride) {
+    const float* ur = u + row * C;
+    const float* dr = dz + row * C;
+    float4 x4[NV], d4[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const int c = lane * 4 + 128 * j;
+      x4[j] = live[j] ? *reinterpret_cast<const float4*>(ur + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d4[j] = live[j] ? *reinterpret_cast<const float4*>(dr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (x4[j].x + x4[j].y) + (x4[j].z + x4[j].w);
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      if (!live[j]) continue;
+      const float a = x4[j].x - mean, b = x4[j].y - mean, c = x4[j].z - mean, d = x4[j].w - mean;
+      q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + eps);
+    float xh[NV][4], g[NV][4], ge[NV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const float xv[4] = {x4[j].x, x4[j].y, x4[j].z, x4[j].w}, dv[4] = {d4[j].x, d4[j].y, d4[j].z, d4[j].w};
+      const float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w}, bv[4] = {b4[j].x, b4[j].y, b4[j].z, b4[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        xh[j][k] = (xv[k] - mean) * rstd;
+        float gg = dv[k];
+        ge[j][k] = 0.f;
+        if (GELU) {
+          float dg;
+          gelu_parts(fmaf(xh[j][k], gv[k], bv[k]), ge[j][k], dg);
+          gg *= dg;
+        }
+        g[j][k] = live[j] ? gg : 0.f;
+        const float dxh = g[j][k] * gv[k];
+        s1 += dxh;
+        s2 = fmaf(dxh, xh[j][k], s2);
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      if (!live[j]) continue;
+      const int c = lane * 4 + 128 * j;
+      const float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        o[k] = rstd * (g[j][k] * gv[k] - s1 - xh[j][k] * s2);
+        ag[j][k] = fmaf(g[j][k], xh[j][k], ag[j][k]);
+        ab[j][k] += g[j][k];
+      }
+      *reinterpret_cast<float4*>(du + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (GELU && act) *reinterpret_cast<float4*>(act + row * C + c) = make_float4(ge[j][0], ge[j][1], ge[j][2], ge[j][3]);
+    }
+  }
+  // block partial: the eight warps' register sums, added in warp order
+#pragma unroll
+  for (int j = 0; j < NV; j++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      sm[warp][0][lane * 4 + 128 * j + k] = ag[j][k];
+      sm[warp][1][lane * 4 + 128 * j + k] = ab[j][k];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += LF_WARPS * 32) {
+    const int t = i / C, c = i - t * C;
+    float a = sm[0][t][c];
+#pragma unroll
+    for (int w = 1; w < LF_WARPS; w++) a += sm[w][t][c];
+    part[((size_t)blockIdx.x * 2 + t) * C + c] = a;
+  }
+}
+
+// depthwise 3x3 (stride 1, pad 1) backward on NHWC rows, C channels: one thread = one pixel lane x 4 channels.
+//   dh[p][c] = du[p][c] + sum_t w[c][t] du[p - off(t)][c]                 (input gradient of u = conv(h) + b + h)
+//   part[blk][t][c] = sum_{p in block} du[p][c] h[p + off(t)][c], t < 9;  part[blk][9][c] = sum du[p][c]
+constexpr int DB_CT = 16;            // channel threads per block (x 4 channels = 64 channels)
+constexpr int DB_PL = 16;            // pixel lanes per block
+
+__global__ void __launch_bounds__(DB_CT * DB_PL) dw_bwd_fused_kernel(const float* __restrict__ du, const __half* __restrict__ h,
+                                                                    const float* __restrict__ w, float* __restrict__ dh, int B, int H, int W,
+                                                                    int C, int pix_per_block, float* __restrict__ part) {
+  __shared__ float sm[DB_PL][10][DB_CT * 4 + 4];
+  const int ct = threadIdx.x % DB_CT, pl = threadIdx.x / DB_CT;
+  const int c = (blockIdx.y * DB_CT + ct) * 4;
+  const bool cl = c < C;
+  const long long M = (long long)B * H * W;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
+  float wt[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) wt[t][k] = cl ? __ldg(w + (size_t)(c + k) * 9 + t) : 0.f;
+  float acc[10][4];
+#pragma unroll
+  for (int t = 0; t < 10; t++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc[t][k] = 0.f;
+  if (cl) {
+    for (long long p = p0 + pl; p < p1; p += DB_PL) {
+      const int px = (int)(p % W), py = (int)((p / W) % H);
+      const float4 gc = *reinterpret_cast<const float4*>(du + p * C + c);
+      float o[4] = {gc.x, gc.y, gc.z, gc.w};
+      acc[9][0] += gc.x; acc[9][1] += gc.y; acc[9][2] += gc.z; acc[9][3] += gc.w;
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+          const int t = ky * 3 + kx;
+          // weight gradient: neighbour of h at +offset
+          const int yy = py + ky - 1, xx = px + kx - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const long long nb = p + (long long)(ky - 1) * W + (kx - 1);
+            const uint2 raw = *reinterpret_cast<const uint2*>(h + nb * C + c);
+            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            acc[t][0] = fmaf(gc.x, h01.x, acc[t][0]); acc[t][1] = fmaf(gc.y, h01.y, acc[t][1]);
+            acc[t][2] = fmaf(gc.z, h23.x, acc[t][2]); acc[t][3] = fmaf(gc.w, h23.y, acc[t][3]);
+          }
+          // input gradient: du at -offset, same tap
+          const int ys = py - (ky - 1), xs = px - (kx - 1);
+          if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
+            const long long nb = p - (long long)(ky - 1) * W - (kx - 1);
+            const float4 gn = (t == 4) ? gc : *reinterpret_cast<const float4*>(du + nb * C + c);
+            o[0] = fmaf(wt[t][0], gn.x, o[0]); o[1] = fmaf(wt[t][1], gn.y, o[1]);
+            o[2] = fmaf(wt[t][2], gn.z, o[2]); o[3] = fmaf(wt[t][3], gn.w, o[3]);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(dh + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 10; t++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) sm[pl][t][ct * 4 + k] = acc[t][k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * DB_CT * 4; i += DB_CT * DB_PL) {
+    const int t = i / (DB_CT * 4), cc = i - t * (DB_CT * 4);
+    const int col = blockIdx.y * DB_CT * 4 + cc;
+    if (col >= C) continue;
+    float a = sm[0][t][cc];
+#pragma unroll
+    for (int l = 1; l < DB_PL; l++) a += sm[l][t][cc];
+    part[((size_t)blockIdx.x * 10 + t) * C + col] = a;
+  }
+}
+
+}  // namespace
+
+bool ln_bwd_fused_ok(long long M, int C) { return M > 0 && C % 4 == 0 && C >= 4 && C <= 512; }
+int ln_bwd_fused_blocks(long long M) {
+  long long nb = (M + LF_WARPS * 4 - 1) / (LF_WARPS * 4);       // >= 4 rows per warp
+  if (nb > LF_MAX_BLOCKS) nb = LF_MAX_BLOCKS;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+// part: 2 * ln_bwd_fused_blocks(M) * C floats.  act (nullable, gelu only): fp32 GELU(LN(u)).  The column sums still need
+// launch_bwd_ln_fold(part, nblk, C, dgamma, dbeta).
+int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
+                        float* act, long long M, int C, float* part, cudaStream_t st) {
+  TCX_REQUIRE(ln_bwd_fused_ok(M, C), "ln_bwd_fused: C must be a multiple of 4, <= 512 (M=%lld C=%d)", M, C);
+  TCX_REQUIRE(du != dz, "ln_bwd_fused: du may not alias dz");
+  const int nblk = ln_bwd_fused_blocks(M);
+  ProfScope prof("ln_bwd_fused", st, (double)M * C * (gelu && act ? 16.0 : 12.0));
+#define LNB(NV)                                                                                                         \
+  do {                                                                                                                  \
+    if (gelu) ln_bwd_fused_kernel<NV, true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, M, C, part); \
+    else ln_bwd_fused_kernel<NV, false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, M, C, part); \
+  } while (0)
+  if (C <= 128) LNB(1);
+  else if (C <= 256) LNB(2);
+  else LNB(4);
+#undef LNB
+  return tcx_check_launch("ln_bwd_fused");
+}
+
+int dw_bwd_fused_blocks(long long M, int C) {
+  const int slabs = (C + DB_CT * 4 - 1) / (DB_CT * 4);
+  long long nb = (2 * 148 + slabs - 1) / slabs;                   // about two waves of blocks over all channel slabs
+  const long long maxb = (M + 4 * DB_PL - 1) / (4 * DB_PL);       // >= 4 pixels per lane
+  if (nb > maxb) nb = maxb;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+// part: 10 * dw_bwd_fused_blocks(M, C) * C floats; fold with launch_bwd_dw_fold(part, nblk, C, dw, db).
+int launch_dw_bwd_fused(const float* du, const __half* h, const float* w, float* dh, int B, int H, int W, int C, float* part,
+                        cudaStream_t st) {
+  const long long M = (long long)B * H * W;
+  TCX_REQUIRE(C % 4 == 0 && M > 0, "dw_bwd_fused: C must be a multiple of 4 (C=%d)", C);
+  TCX_REQUIRE(du != dh, "dw_bwd_fused: dh may not alias du");
+  const int nblk = dw_bwd_fused_blocks(M, C);
+  const int ppb = (int)((M + nblk - 1) / nblk);
+  const dim3 grid(nblk, (C + DB_CT * 4 - 1) / (DB_CT * 4));
+  ProfScope prof("dw_bwd_fused", st, (double)M * C * 10.0);
+  dw_bwd_fused_kernel<<<grid, DB_CT * DB_PL, 0, st>>>(du, h, w, dh, B, H, W, C, ppb, part);
+  return tcx_check_launch("dw_bwd_fused");
+}

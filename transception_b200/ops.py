@@ -125,7 +125,7 @@ _PROTOS = {
     "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "tcx_mixffn_skip_bwd": (_i, [_vp, _pp, _f, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mixffn_skip_bwd": (_i, [_vp, _pp, _f, _vp, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 EXPORTS = tuple(_PROTOS)
 
@@ -974,8 +974,9 @@ def mixffn_skip_train(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
     return y, saved
 
 
-def mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, need_dx=True):
-    """(dxn, [8 parameter gradients in slot order]) of MixFFN_skip."""
+def mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, need_dx=True, xn=None):
+    """(dxn, [8 parameter gradients in slot order]) of MixFFN_skip.  ``xn``: the fp32 forward input (optional; the saved fp16
+    copy is converted when it is absent)."""
     require_cuda(dy)
     lib = load_library()
     dy = dy.contiguous()
@@ -986,7 +987,8 @@ def mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2
     tab = _table(params)
     gtab = (ctypes.c_void_p * 8)(*[_ptr(g) for g in grads])
     ws = _ws(lib.tcx_mixffn_skip_bwd_workspace_bytes(B, H * W, C, C4), dy)
-    _chk(lib.tcx_mixffn_skip_bwd(_ptr(dy), tab, eps, _ptr(saved), _ptr(dxn), gtab, B, H, W, C, C4, _ptr(ws), _stream()))
+    _chk(lib.tcx_mixffn_skip_bwd(_ptr(dy), tab, eps, _ptr(saved), _ptr(xn.contiguous() if xn is not None else None), _ptr(dxn), gtab,
+                                 B, H, W, C, C4, _ptr(ws), _stream()))
     return dxn, grads
 
 
