@@ -249,10 +249,12 @@ int tcx_argmax_classes_fwd(const float* logits, unsigned char* labels, int B, in
  * what the autograd nodes of the drop-in modules (transception_b200/autograd.py) call where the reference relies on ATen's
  * autograd formulas for nn.LayerNorm / nn.Linear / MixFFN_skip (MSTr.py:58-61). ---- */
 
-/* nn.LayerNorm backward: x [M][C] (the forward input), dy [M][C] -> dx [M][C], dw [C], db [C] */
+/* nn.LayerNorm backward: x [M][C] (the forward input), dy [M][C] -> dx [M][C], dw [C], db [C].  dres (nullable) [M][C] is added
+ * to dx: the gradient arriving over the residual connection around the norm (x + f(LN(x)), MSTr.py:164-173, :935-946), so the
+ * sum autograd would run as a separate pass happens in the same kernel. */
 size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C);
-int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, float eps, float* dx, float* dw, float* db, long long M, int C,
-                      void* ws, void* stream);
+int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, const float* dres, float eps, float* dx, float* dw, float* db,
+                      long long M, int C, void* ws, void* stream);
 
 /* nn.Linear backward for y = x w^T + b: x [M][K] (fp32, or fp16 when x_f16), w [N][K], dy [M][N] ->
  * dx [M][K] = dy w, dw [N][K] = dy^T x, db [N] = column sums of dy; any of dx / dw / db may be NULL (skipped). */

@@ -24,6 +24,28 @@ class LayerNormFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class LayerNormResFn(torch.autograd.Function):
+    """(LN(x), x) for the pre-norm residual pattern y = x + f(LN(x)) (MSTr.py:164-173, :935-946): the second output is x itself,
+    handed to the residual connection, so that BOTH gradients of x arrive at this node and the LayerNorm backward kernel adds
+    them in its own pass (no separate accumulation kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        x = x.contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.eps = eps
+        ctx.set_materialize_grads(False)
+        return ops.layernorm(x, w, b, eps), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, w = ctx.saved_tensors
+        if dy is None:
+            return dres, None, None, None
+        dx, dw, db = ops.layernorm_bwd(x, w, dy, ctx.eps, dres=dres)
+        return dx, dw, db, None
+
+
 class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
@@ -43,12 +65,14 @@ class MixFFNSkipFn(torch.autograd.Function):
     """y = fc2(GELU(LN(dw3x3(fc1 x) + fc1 x))) (MSTr.py:58-61) on x [B, N, C]."""
 
     @staticmethod
-    def forward(ctx, x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b):
+    def forward(ctx, x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b, residual=None):
         x = x.contiguous()
-        y, saved = ops.mixffn_skip_train(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b)
+        y, saved = ops.mixffn_skip_train(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
+                                         residual=residual.contiguous() if residual is not None else None)
         # x (the LayerNorm output) is kept in fp32: fc1's weight gradient reads it in place as a TF32 operand
         ctx.save_for_backward(saved, x, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)
         ctx.geom = (x.shape[0], H, W, eps)
+        ctx.has_res = residual is not None
         return y
 
     @staticmethod
@@ -57,38 +81,42 @@ class MixFFNSkipFn(torch.autograd.Function):
         B, H, W, eps = ctx.geom
         dx, g = ops.mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
                                     need_dx=ctx.needs_input_grad[0], xn=x)
-        return (dx, None, None, None) + tuple(g)
+        return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None,)        # the residual input receives dy as it is
 
 
 class EffAttnFn(torch.autograd.Function):
     """EfficientAttention.forward (MSTr.py:106-143) on tokens x [B, N, C] (the NCHW round trip of the caller is a view)."""
 
     @staticmethod
-    def forward(ctx, x, kw, kb, qw, qb, vw, vb, rw, rb):
-        y, saved = ops.eff_attn_train(x, kw, kb, qw, qb, vw, vb, rw, rb)
+    def forward(ctx, x, kw, kb, qw, qb, vw, vb, rw, rb, residual=None):
+        y, saved = ops.eff_attn_train(x, kw, kb, qw, qb, vw, vb, rw, rb,
+                                      residual=residual.contiguous() if residual is not None else None)
         ctx.save_for_backward(saved, kw, kb, qw, qb, vw, vb, rw, rb)
+        ctx.has_res = residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         saved, *params = ctx.saved_tensors
         dx, g = ops.eff_attn_bwd(dy, saved, *params, need_dx=ctx.needs_input_grad[0])
-        return (dx,) + tuple(g)
+        return (dx,) + tuple(g) + (dy if ctx.has_res else None,)
 
 
-def eff_attn(x, kw, kb, qw, qb, vw, vb, rw, rb):
-    return EffAttnFn.apply(x, kw, kb, qw, qb, vw, vb, rw, rb)
+def eff_attn(x, kw, kb, qw, qb, vw, vb, rw, rb, residual=None):
+    return EffAttnFn.apply(x, kw, kb, qw, qb, vw, vb, rw, rb, residual)
 
 
 class FactorAttFn(torch.autograd.Function):
     """FactorAtt_ConvRelPosEnc.forward (MSTr.py:852-886) on LayerNorm output x [B, N, C]."""
 
     @staticmethod
-    def forward(ctx, x, H, W, heads, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb):
+    def forward(ctx, x, H, W, heads, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb, residual=None):
+        x = x.contiguous()
         y, ws = ops.mb_factor_attn(x, H, W, heads, None, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
-                                   keep_ws=True)
+                                   residual=residual.contiguous() if residual is not None else None, keep_ws=True)
         ctx.save_for_backward(x, ws, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb)
         ctx.geom = (H, W, heads)
+        ctx.has_res = residual is not None
         return y
 
     @staticmethod
@@ -97,7 +125,7 @@ class FactorAttFn(torch.autograd.Function):
         H, W, heads = ctx.geom
         dx, g = ops.mb_factor_attn_bwd(dy, x, ws, H, W, heads, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], projw, projb,
                                        need_dx=ctx.needs_input_grad[0])
-        return (dx, None, None, None) + tuple(g)
+        return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None,)
 
 
 class DwConvTokensFn(torch.autograd.Function):
@@ -117,9 +145,9 @@ class DwConvTokensFn(torch.autograd.Function):
         return dx, None, None, dw, db, None
 
 
-def factor_att(x, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb):
+def factor_att(x, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb, residual=None):
     return FactorAttFn.apply(x, H, W, heads, qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2],
-                             projw, projb)
+                             projw, projb, residual)
 
 
 def dwconv_tokens(x, H, W, w, b, add_input):
@@ -248,9 +276,14 @@ def layernorm(x, w, b, eps):
     return LayerNormFn.apply(x, w, b, eps)
 
 
+def layernorm_res(x, w, b, eps):
+    """(LN(x), x): feed the second result to the residual input of the node that closes the skip connection."""
+    return LayerNormResFn.apply(x, w, b, eps)
+
+
 def linear(x, w, b=None):
     return LinearFn.apply(x, w, b)
 
 
-def mixffn_skip(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b):
-    return MixFFNSkipFn.apply(x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)
+def mixffn_skip(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):
+    return MixFFNSkipFn.apply(x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b, residual)

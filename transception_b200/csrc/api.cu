@@ -1784,13 +1784,13 @@ int tcx_coord_gate_bwd(const float* x, const float* z, const float* dout, float*
 extern "C" {
 
 size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C) { return 4 * (rnd(2 * (size_t)M) + rnd(2 * (size_t)bwd_red_blocks(M) * C) + 64); }
-int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, float eps, float* dx, float* dw, float* db, long long M, int C,
-                      void* ws, void* stream) {
+int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, const float* dres, float eps, float* dx, float* dw, float* db,
+                      long long M, int C, void* ws, void* stream) {
   TCX_REQUIRE(x && w && dy && dx && dw && db && ws, "layernorm_bwd: null pointer");
   Carver c(ws);
   float* stats = c.take(2 * (size_t)M);
   float* part = c.take(2 * (size_t)bwd_red_blocks(M) * C);
-  return launch_bwd_ln(x, dy, w, nullptr, eps, 0, dx, dw, db, M, C, stats, part, S(stream));
+  return launch_bwd_ln(x, dy, w, nullptr, eps, 0, dx, dw, db, M, C, stats, part, S(stream), dres);
 }
 
 size_t tcx_linear_bwd_workspace_bytes(long long M, int N, int K) { return 4 * linear_bwd_ws_floats(M, N, K); }
@@ -2144,7 +2144,7 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
     AuxStreams* aux = aux_streams(st);
     cudaStream_t sa = aux ? aux->s[1] : st;
     TCX_TRY(run_linear_bwd(nullptr, 0, F(p[6]), dy, da, nullptr, nullptr, M, C, C4, lin, st));               // da = dy W2
-    TCX_TRY(launch_ln_bwd_fused(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, a32, M, C4, part_ln, st));
+    TCX_TRY(launch_ln_bwd_fused(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, a32, nullptr, M, C4, part_ln, st));
     float* dh = da;
     TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part, st));
     if (aux) {

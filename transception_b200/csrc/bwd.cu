@@ -407,7 +407,7 @@ int launch_bwd_dw_fold(const float* part, int nblk, int C, float* dw, float* db,
 }
 
 int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
-                  float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st) {
+                  float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st, const float* dres) {
   TCX_REQUIRE(C % 4 == 0 && C > 0, "bwd_ln: C %% 4 != 0 (C=%d)", C);
   TCX_REQUIRE(du != dz, "bwd_ln: du may not alias dz");
   if (M == 0) {
@@ -416,7 +416,7 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
     return 0;
   }
   if (ln_bwd_fused_ok(M, C)) {      // one pass over (u, dz) instead of a row pass + a column pass
-    TCX_TRY(launch_ln_bwd_fused(u, dz, gamma, beta, eps, gelu, du, nullptr, M, C, part, st));
+    TCX_TRY(launch_ln_bwd_fused(u, dz, gamma, beta, eps, gelu, du, nullptr, dres, M, C, part, st));
     return launch_bwd_ln_fold(part, ln_bwd_fused_blocks(M), C, dgamma, dbeta, st);
   }
   const unsigned rb = (unsigned)((M + 7) / 8);
@@ -435,7 +435,9 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
     TCX_TRY(tcx_check_launch("bwd_ln_cols"));
   }
   bwd_ln_fold_kernel<<<cdiv(2 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dgamma, dbeta);
-  return tcx_check_launch("bwd_ln_fold");
+  TCX_TRY(tcx_check_launch("bwd_ln_fold"));
+  if (dres) return launch_add_inplace(du, dres, M * C, st);
+  return 0;
 }
 
 int launch_bwd_dwconv_wgrad(const float* du, const __half* h, int B, int H, int W, int C, float* dw, float* db, float* part,

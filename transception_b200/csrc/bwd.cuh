@@ -46,15 +46,18 @@ int launch_bwd_colsum(const float* x, long long M, int C, int ld, float* part, f
 // du [M][C] = dL/du, dgamma / dbeta [C].  stats: 2*M floats (mean, rstd written by the row pass, read by the column
 // pass); part: 2 * bwd_red_blocks(M) * C floats.  du may not alias dz.
 int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
-                  float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st);
+                  float* dgamma, float* dbeta, long long M, int C, float* stats, float* part, cudaStream_t st,
+                  const float* dres = nullptr);
 
 // fused forms (bwd_mix.cu): one pass per tensor.  launch_bwd_ln uses the fused kernel by itself whenever ln_bwd_fused_ok.
 bool ln_bwd_fused_ok(long long M, int C);
 int ln_bwd_fused_blocks(long long M);
 // du = LayerNorm (gelu: GELU o LayerNorm) backward of dz at u; act (nullable, gelu only) = fp32 GELU(LN(u)); part: 2 * blocks * C
 // column partials to be folded with launch_bwd_ln_fold
+// dres (nullable): added to du — the gradient arriving over the residual connection around the LayerNorm
 int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
-                        float* act, long long M, int C, float* part, cudaStream_t st);
+                        float* act, const float* dres, long long M, int C, float* part, cudaStream_t st);
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st);
 int launch_bwd_ln_fold(const float* part, int nblk, int C, float* dgamma, float* dbeta, cudaStream_t st);
 // Mix-FFN depthwise conv backward in one pass: dh = du + conv^T(du), part = 10 * blocks * C filter / bias partials (fold with
 // launch_bwd_dw_fold); h is the fp16 fc1 output

@@ -25,7 +25,8 @@ __device__ __forceinline__ void gelu_parts(float z, float& gelu, float& dgelu) {
 template <int NV, bool GELU>
 __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ dz,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                                    float* __restrict__ du, float* __restrict__ act, long long M, int C,
+                                                                    float* __restrict__ du, float* __restrict__ act,
+                                                                    const float* __restrict__ dres, long long M, int C,
                                                                     float* __restrict__ part) {
   __shared__ float sm[LF_WARPS][2][NV * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,6 +103,10 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float
         o[k] = rstd * (g[j][k] * gv[k] - s1 - xh[j][k] * s2);
         ag[j][k] = fmaf(g[j][k], xh[j][k], ag[j][k]);
         ab[j][k] += g[j][k];
+      }
+      if (dres) {        // gradient arriving over the residual connection around this LayerNorm
+        const float4 r = *reinterpret_cast<const float4*>(dres + row * C + c);
+        o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
       }
       *reinterpret_cast<float4*>(du + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (GELU && act) *reinterpret_cast<float4*>(act + row * C + c) = make_float4(ge[j][0], ge[j][1], ge[j][2], ge[j][3]);
@@ -201,7 +206,23 @@ __global__ void __launch_bounds__(DB_CT * DB_PL) dw_bwd_fused_kernel(const float
   }
 }
 
+__global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(y)[i];
+  const float4 b = reinterpret_cast<const float4*>(x)[i];
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  reinterpret_cast<float4*>(y)[i] = a;
+}
+
 }  // namespace
+
+int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
+  TCX_REQUIRE(n % 4 == 0 && (((uintptr_t)y | (uintptr_t)x) & 15) == 0, "add_inplace: n %% 4 != 0 or unaligned");
+  if (n == 0) return 0;
+  add_inplace_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(y, x, n / 4);
+  return tcx_check_launch("add_inplace");
+}
 
 bool ln_bwd_fused_ok(long long M, int C) { return M > 0 && C % 4 == 0 && C >= 4 && C <= 512; }
 int ln_bwd_fused_blocks(long long M) {
@@ -214,15 +235,15 @@ int ln_bwd_fused_blocks(long long M) {
 // part: 2 * ln_bwd_fused_blocks(M) * C floats.  act (nullable, gelu only): fp32 GELU(LN(u)).  The column sums still need
 // launch_bwd_ln_fold(part, nblk, C, dgamma, dbeta).
 int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
-                        float* act, long long M, int C, float* part, cudaStream_t st) {
+                        float* act, const float* dres, long long M, int C, float* part, cudaStream_t st) {
   TCX_REQUIRE(ln_bwd_fused_ok(M, C), "ln_bwd_fused: C must be a multiple of 4, <= 512 (M=%lld C=%d)", M, C);
   TCX_REQUIRE(du != dz, "ln_bwd_fused: du may not alias dz");
   const int nblk = ln_bwd_fused_blocks(M);
   ProfScope prof("ln_bwd_fused", st, (double)M * C * (gelu && act ? 16.0 : 12.0));
 #define LNB(NV)                                                                                                         \
   do {                                                                                                                  \
-    if (gelu) ln_bwd_fused_kernel<NV, true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, M, C, part); \
-    else ln_bwd_fused_kernel<NV, false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, M, C, part); \
+    if (gelu) ln_bwd_fused_kernel<NV, true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part); \
+    else ln_bwd_fused_kernel<NV, false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part); \
   } while (0)
   if (C <= 128) LNB(1);
   else if (C <= 256) LNB(2);

@@ -144,11 +144,12 @@ class MixFFN_skip(nn.Module):
         return (self.fc1.weight, self.fc1.bias, self.dwconv.dwconv.weight, self.dwconv.dwconv.bias,
                 self.norm1.weight, self.norm1.bias, self.norm1.eps, self.fc2.weight, self.fc2.bias)
 
-    def forward(self, x, H, W):
+    def forward(self, x, H, W, residual=None):
+        """``residual`` (extension, optional): added to the result inside the fc2 kernel — the caller's skip connection."""
         if _recording(x, self.fc1.weight):
             # training row: forward + backward on the library's kernels (transception_b200/autograd.py)
-            return tcx_autograd.mixffn_skip(x, H, W, *self.args())
-        return ops.mixffn_skip(x, H, W, *self.args())
+            return tcx_autograd.mixffn_skip(x, H, W, *self.args(), residual=residual)
+        return ops.mixffn_skip(x, H, W, *self.args(), residual=residual)
 
 
 # --------------------------------------------------------------------------------------
@@ -199,8 +200,10 @@ class EfficientTransformerBlock(nn.Module):
             # training row: every op is an autograd node backed by the library's forward + backward kernels; the two
             # residual additions are the only ATen arithmetic (MSTr.py:164-173)
             n1, n2 = self.norm1, self.norm2
-            tx = x + tcx_autograd.eff_attn(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps), *self.attn.args())
-            return tx + self.mlp(tcx_autograd.layernorm(tx, n2.weight, n2.bias, n2.eps), H, W)
+            xn, xr = tcx_autograd.layernorm_res(x, n1.weight, n1.bias, n1.eps)
+            tx = tcx_autograd.eff_attn(xn, *self.attn.args(), residual=xr)          # x + attn(LN(x)): the add is the kernel's epilogue
+            xn, xr = tcx_autograd.layernorm_res(tx, n2.weight, n2.bias, n2.eps)
+            return self.mlp(xn, H, W, residual=xr)
         return ops.eff_block(x, H, W, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.attn.args(),
                              self.norm2.weight, self.norm2.bias, self.mlp.args())
 
@@ -542,13 +545,13 @@ class FactorAtt_ConvRelPosEnc(nn.Module):
                 [m.weight for m in c.conv_list], [m.bias for m in c.conv_list], list(c.head_splits),
                 self.proj.weight, self.proj.bias)
 
-    def forward(self, x, size):
+    def forward(self, x, size, residual=None):
         H, W = size
         if _recording(x, self.qkv.weight):
             heads, _, qkvw, qkvb, cw, cb, splits, pw, pb = self.args()
             ops._check_crpe(splits, cw, heads)
-            return tcx_autograd.factor_att(x, H, W, heads, qkvw, qkvb, cw, cb, pw, pb)
-        return ops.mb_factor_attn(x.contiguous(), H, W, *self.args(), residual=None)
+            return tcx_autograd.factor_att(x, H, W, heads, qkvw, qkvb, cw, cb, pw, pb, residual=residual)
+        return ops.mb_factor_attn(x.contiguous(), H, W, *self.args(), residual=residual)
 
 
 class MHCABlock(nn.Module):
@@ -569,8 +572,10 @@ class MHCABlock(nn.Module):
             # library's kernels; the two residual additions are ATen adds
             n1, n2 = self.norm1, self.norm2
             x = self.cpe(x, size)
-            x = x + self.factoratt_crpe(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps), size)
-            return x + self.mlp(tcx_autograd.layernorm(x, n2.weight, n2.bias, n2.eps), size[0], size[1])
+            xn, xr = tcx_autograd.layernorm_res(x, n1.weight, n1.bias, n1.eps)
+            x = self.factoratt_crpe(xn, size, residual=xr)
+            xn, xr = tcx_autograd.layernorm_res(x, n2.weight, n2.bias, n2.eps)
+            return self.mlp(xn, size[0], size[1], residual=xr)
         return ops.mhca_blocks(x.contiguous().unsqueeze(0), size[0], size[1], [[self]])[0]
 
 

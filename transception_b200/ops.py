@@ -90,7 +90,7 @@ _PROTOS = {
     "tcx_final_expand_head_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_final_expand_head_fwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_layernorm_bwd_workspace_bytes": (_sz, [_ll, _i]),
-    "tcx_layernorm_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
+    "tcx_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _vp, _vp]),
     "tcx_linear_bwd_workspace_bytes": (_sz, [_ll, _i, _i]),
     "tcx_linear_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
     "tcx_wgrad_mn_workspace_bytes": (_sz, [_ll, _i, _i, _i, _i]),
@@ -907,16 +907,17 @@ def argmax_classes(logits):
 
 
 # ---- training row: backward entries (include/transception_sm100.h, "training row") ------------------------------
-def layernorm_bwd(x, w, dy, eps):
-    """(dx, dw, db) of nn.LayerNorm over the last dim."""
+def layernorm_bwd(x, w, dy, eps, dres=None):
+    """(dx, dw, db) of nn.LayerNorm over the last dim; ``dres`` (optional, shape of x) is added to dx in the same kernel."""
     require_cuda(x)
     lib = load_library()
     x, dy = x.contiguous(), dy.contiguous()
+    dres = dres.contiguous() if dres is not None else None
     C = x.shape[-1]
     M = x.numel() // C
     dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
     ws = _ws(lib.tcx_layernorm_bwd_workspace_bytes(M, C), x)
-    _chk(lib.tcx_layernorm_bwd(_ptr(x), _ptr(_d(w)), _ptr(dy), eps, _ptr(dx), _ptr(dw), _ptr(db), M, C, _ptr(ws), _stream()))
+    _chk(lib.tcx_layernorm_bwd(_ptr(x), _ptr(_d(w)), _ptr(dy), _ptr(dres), eps, _ptr(dx), _ptr(dw), _ptr(db), M, C, _ptr(ws), _stream()))
     return dx, dw, db
 
 
