@@ -1933,8 +1933,9 @@ static size_t mb_attn_bwd_ws_floats(int B, int N, int C) {
   bwd_wgrad_splits(N, C, C, &S, &Ms);
   const size_t pack = (size_t)B * S * C * Ms, ch = (size_t)B * ea_bwd_chunks(N) * C;
   const size_t lin = std::max(linear_bwd_ws_floats(M, C, C), linear_bwd_ws_floats(M, 3 * C, C));
-  return 6 * rnd(bnc) + rnd(3 * bnc) + 3 * rnd(bcc) + 2 * rnd(pack) + rnd((size_t)B * S * C * C) + 3 * rnd(ch) +
-         rnd(bwd_dwk_wgrad_part_floats(7, M, C)) + lin + 64;
+  return 6 * rnd(bnc) + rnd(3 * bnc) + 3 * rnd(bcc) + 2 * rnd(pack) +
+         rnd(std::max((size_t)B * S * C * C, wgrad_tc_scratch_floats(N, C, C, B, 4))) + 3 * rnd(ch) +
+         rnd(std::max(bwd_dwk_wgrad_part_floats(7, M, C), bwd_dwk3_wgrad_part_floats(M, C))) + lin + 64;
 }
 size_t tcx_mb_factor_attn_bwd_workspace_bytes(int B, int N, int C) { return 4 * mb_attn_bwd_ws_floats(B, N, C); }
 
@@ -1971,16 +1972,27 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
   float* dctxT = c.take(bcc);
   float* packA = c.take((size_t)B * SP * C * Ms);
   float* packB = c.take((size_t)B * SP * C * Ms);
-  float* part = c.take((size_t)B * SP * C * C);
+  float* part = c.take(std::max((size_t)B * SP * C * C, wgrad_tc_scratch_floats(N, C, C, B, 4)));
   float* pm = c.take(ch);
   float* ps = c.take(ch);
   float* sp = c.take(ch);
-  float* wpart = c.take(bwd_dwk_wgrad_part_floats(7, M, C));
+  float* wpart = c.take(std::max(bwd_dwk_wgrad_part_floats(7, M, C), bwd_dwk3_wgrad_part_floats(M, C)));
   float* lin = c.take(0);
   auto G = [&](int i) { return reinterpret_cast<float*>(dp[i]); };
   const int win[3] = {3, 5, 7}, c0[3] = {0, 2 * Ch, 5 * Ch}, cg[3] = {2 * Ch, 3 * Ch, 3 * Ch};
+  const bool mn = g_flag_wgrad_tc && g_flag_gemm_tc && wgrad_tc_eligible(N, C, C, C, C, 4) && ld % 4 == 0;
+  const float* cw3[3] = {F(p[2]), F(p[4]), F(p[6])};
+  const float* cb3[3] = {F(p[3]), F(p[5]), F(p[7])};
   auto ctx_gemm = [&](const float* a, int lda_, const float* b_, int ldb_, float sc, float* out, float* outT) -> int {
     // out[b] = sc * mask(a[b]^T b_[b]) over the tokens of image b
+    if (mn) {      // both operands read in place (MN-major), head mask, scale and transposed copy inside the kernel's fold
+      WgradArgs w{};
+      w.A = a; w.B = b_; w.fmt = 2; w.Mtok = N; w.NL = C; w.KL = C; w.lda = lda_; w.ldb = ldb_; w.batch = B;
+      w.strideA = (long long)N * lda_; w.strideB = (long long)N * ldb_;
+      w.alpha = sc; w.out = out; w.ldo = C; w.stride_out = (long long)C * C;
+      w.outT = outT; w.ldt = C; w.stride_outT = (long long)C * C; w.mask_ch = Ch; w.scratch = part;
+      return launch_wgrad_tc(w, st);
+    }
     TCX_TRY(launch_bwd_packT_batched_f32(a, B, N, C, lda_, SP, Ms, Ms, packA, st));
     TCX_TRY(launch_bwd_packT_batched_f32(b_, B, N, C, ldb_, SP, Ms, Ms, packB, st));
     GemmParams g = gemm1(packA, packB, part, C, C, Ms);
@@ -2001,19 +2013,33 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
   // recompute: P = softmax over tokens of k, ctx = per-head P^T v, conv_v = crpe depthwise convolutions of v
   TCX_TRY(launch_bwd_ksoftmax32(k, ld, B, N, C, pm, ps, P, st));
   TCX_TRY(ctx_gemm(P, C, v, ld, 1.0f, ctx, nullptr));
-  for (int j = 0; j < 3; j++)
-    TCX_TRY(launch_bwd_dwk(win[j], v + c0[j], ld, F(p[2 + 2 * j]), F(p[3 + 2 * j]), convv + c0[j], C, B, H, W, cg[j], 0, 0, st));
+  if (mn) {
+    TCX_TRY(launch_bwd_dwk3(v, ld, cw3, cb3, 2 * Ch, 5 * Ch, convv, C, B, H, W, C, 0, 0, st));
+  } else {
+    for (int j = 0; j < 3; j++)
+      TCX_TRY(launch_bwd_dwk(win[j], v + c0[j], ld, F(p[2 + 2 * j]), F(p[3 + 2 * j]), convv + c0[j], C, B, H, W, cg[j], 0, 0, st));
+  }
   // x_out = scale * q ctx + q * conv_v
   TCX_TRY(tok_gemm(dxo, C, ctx, dqfa, C, nullptr));                       // d(q ctx)/dq, before the scale
   TCX_TRY(ctx_gemm(q, ld, dxo, C, scale, dctx, dctxT));                   // dctx = scale * mask(q^T dxo)
   TCX_TRY(launch_mb_bwd_dq(dxo, dqfa, convv, q, ld, scale, M, C, dqkv, ld, st));   // dq; convv <- d conv_v
-  for (int j = 0; j < 3; j++)
-    TCX_TRY(launch_bwd_dwk(win[j], convv + c0[j], C, F(p[2 + 2 * j]), nullptr, dvconv + c0[j], C, B, H, W, cg[j], 1, 0, st));
+  if (mn) {
+    TCX_TRY(launch_bwd_dwk3(convv, C, cw3, nullptr, 2 * Ch, 5 * Ch, dvconv, C, B, H, W, C, 1, 0, st));
+  } else {
+    for (int j = 0; j < 3; j++)
+      TCX_TRY(launch_bwd_dwk(win[j], convv + c0[j], C, F(p[2 + 2 * j]), nullptr, dvconv + c0[j], C, B, H, W, cg[j], 1, 0, st));
+  }
   TCX_TRY(tok_gemm(P, C, dctxT, dqkv + 2 * C, ld, dvconv));               // dv = P dctx + conv^T(d conv_v)
   TCX_TRY(tok_gemm(v, ld, dctx, dP, C, nullptr));                         // dP = v dctx^T
   TCX_TRY(launch_bwd_colsoftmax(P, dP, B, N, C, sp, dqkv + C, ld, st));   // dk
-  for (int j = 0; j < 3; j++)
-    TCX_TRY(launch_bwd_dwk_wgrad(win[j], convv + c0[j], C, v + c0[j], ld, B, H, W, cg[j], G(2 + 2 * j), G(3 + 2 * j), wpart, st));
+  if (mn) {
+    float* dw3[3] = {G(2), G(4), G(6)};
+    float* db3[3] = {G(3), G(5), G(7)};
+    TCX_TRY(launch_bwd_dwk3_wgrad(convv, C, v, ld, B, H, W, C, 2 * Ch, 5 * Ch, dw3, db3, wpart, st));
+  } else {
+    for (int j = 0; j < 3; j++)
+      TCX_TRY(launch_bwd_dwk_wgrad(win[j], convv + c0[j], C, v + c0[j], ld, B, H, W, cg[j], G(2 + 2 * j), G(3 + 2 * j), wpart, st));
+  }
   // qkv Linear
   return run_linear_bwd(xn, 0, F(p[0]), dqkv, dxn, G(0), G(1), M, 3 * C, C, lin, st);
 }
@@ -2045,8 +2071,8 @@ size_t tcx_attn_core_bwd_workspace_bytes(int B, int Nq, int Nk) {
   int S, Ms, Msk;
   attn_core_plan(Nq, Nk, &S, &Ms, &Msk);
   const size_t sc = (size_t)B * Nq * Nk;
-  return 4 * (2 * rnd(sc) + rnd((size_t)B * S * Nk * Ms) + rnd((size_t)B * S * 64 * Ms) + rnd((size_t)B * S * Nk * 64) +
-              rnd((size_t)B * 64 * Msk) + 64);
+  return 4 * (2 * rnd(sc) + rnd((size_t)B * S * Nk * Ms) + rnd((size_t)B * S * 64 * Ms) +
+              rnd(std::max((size_t)B * S * Nk * 64, wgrad_tc_scratch_floats(Nq, Nk, 64, B, 4))) + rnd((size_t)B * 64 * Msk) + 64);
 }
 int tcx_attn_core_bwd(const float* q, const float* kv, const float* dout, float scale, float* dq, float* dkv, int B, int Nq, int Nk,
                       void* ws, void* stream) {
@@ -2062,7 +2088,7 @@ int tcx_attn_core_bwd(const float* q, const float* kv, const float* dout, float 
   float* dS = c.take(sc);          // dP -> dS (scaled)
   float* big = c.take((size_t)B * SP * Nk * Ms);     // P^T / dS^T, K-major over the query tokens, split-major
   float* small = c.take((size_t)B * SP * 64 * Ms);   // dout^T / q^T
-  float* part = c.take((size_t)B * SP * Nk * 64);
+  float* part = c.take(std::max((size_t)B * SP * Nk * 64, wgrad_tc_scratch_floats(Nq, Nk, 64, B, 4)));
   float* kT = c.take((size_t)B * 64 * Msk);
   const float* k = kv; const float* v = kv + 64;
   const long long M = (long long)B * Nq;
@@ -2084,8 +2110,27 @@ int tcx_attn_core_bwd(const float* q, const float* kv, const float* dout, float 
   TCX_TRY(scores(q, k, P));
   TCX_TRY(launch_bwd_rowsoftmax_fwd(P, Nk, M, Nk, scale, P, Nk, st));
   TCX_TRY(scores(dout, v, dS));                                         // dP = dout v^T
-  TCX_TRY(over_queries(P, dout, 1.0f, dkv + 64));                       // dv = P^T dout
+  const bool mn = g_flag_wgrad_tc && g_flag_gemm_tc && wgrad_tc_eligible(Nq, Nk, 64, Nk, 64, 4);
+  // out[b] (Nk x 64, pitch 128) = big_src[b]^T (Nk x Nq) small_src[b] (Nq x 64): the score-sized operand is read in place by the
+  // MN-major weight-gradient kernel (the round-1 path re-laid 305 MB of scores twice per layer)
+  auto over_queries_mn = [&](const float* big_src, const float* small_src, float* out) -> int {
+    WgradArgs a{};
+    a.A = big_src; a.B = small_src; a.fmt = 2; a.Mtok = Nq; a.NL = Nk; a.KL = 64; a.lda = Nk; a.ldb = 64; a.batch = B;
+    a.strideA = (long long)Nq * Nk; a.strideB = (long long)Nq * 64;
+    a.alpha = 1.0f; a.out = out; a.ldo = 128; a.stride_out = (long long)Nk * 128;
+    a.scratch = part;
+    return launch_wgrad_tc(a, st);
+  };
+  if (mn) TCX_TRY(over_queries_mn(P, dout, dkv + 64));                  // dv = P^T dout
+  else TCX_TRY(over_queries(P, dout, 1.0f, dkv + 64));
   TCX_TRY(launch_bwd_rowsoftmax_bwd(P, Nk, dS, Nk, M, Nk, scale, dS, Nk, st));
+  if (mn) {
+    GemmParams g = gemm1(dS, k, dq, Nq, 64, Nk);                         // dq = dS k, k [Nk][64] (pitch 128) read in place
+    g.w_mn = 1; g.ldw = 128;
+    g.batch = B; g.strideA = (long long)Nq * Nk; g.strideW = (long long)Nk * 128; g.strideC = (long long)Nq * 64;
+    TCX_TRY(launch_gemm(g, st));
+    return over_queries_mn(dS, q, dkv);                                  // dk = dS^T q
+  }
   TCX_TRY(launch_bwd_packT_batched_f32(k, B, Nk, 64, 128, 1, Msk, Msk, kT, st));
   {
     GemmParams g = gemm1(dS, kT, dq, Nq, 64, Nk);                        // dq = dS k

@@ -106,6 +106,12 @@ int launch_bwd_dwk(int K, const float* x, int ldx, const float* w, const float* 
 size_t bwd_dwk_wgrad_part_floats(int K, long long M, int Cg);
 int launch_bwd_dwk_wgrad(int K, const float* g, int ldg, const float* x, int ldx, int B, int H, int W, int Cg, float* dw, float* db,
                          float* part, cudaStream_t st);
+// the three crpe windows (3x3 | 5x5 | 7x7 on channel ranges [0,c1) | [c1,c2) | [c2,C)) in one launch: w[j] [Cg_j][K_j^2], b[j] nullable
+int launch_bwd_dwk3(const float* x, int ldx, const float* const* w, const float* const* b, int c1, int c2, float* y, int ldy, int B, int H,
+                    int W, int C, int flip, int add, cudaStream_t st);
+size_t bwd_dwk3_wgrad_part_floats(long long M, int C);
+int launch_bwd_dwk3_wgrad(const float* g, int ldg, const float* x, int ldx, int B, int H, int W, int C, int c1, int c2, float* const* dw,
+                          float* const* db, float* part, cudaStream_t st);
 // out[b] = scale * sum_s part[b][s] restricted to the diagonal Ch x Ch blocks of the R x R matrix (zero elsewhere), outT transposed
 int launch_bwd_fold_mask(const float* part, int batch, int S, int R, int Ch, float scale, float* out, float* outT, cudaStream_t st);
 // dq[r][c] (pitch ldo) = scale * dqfa + dxo * convv;  convv <- dxo * q (the gradient of the conv output), q rows of pitch ldq

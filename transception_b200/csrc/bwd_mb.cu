@@ -92,6 +92,121 @@ __global__ void __launch_bounds__(256) dwk_fold_kernel(const float* __restrict__
   if (t < KK) dw[(size_t)c * KK + t] = s; else if (db) db[c] = s;
 }
 
+// ---- the three crpe windows (3x3 on heads 0-1, 5x5 on heads 2-4, 7x7 on heads 5-7: channel ranges [0,c1), [c1,c2), [c2,C)) in ONE
+// launch each: forward / input-gradient conv, and the filter / bias gradient with a single fold ----
+struct Crpe3 {
+  const float* w[3];     // [Cg_j][K_j*K_j]
+  const float* b[3];     // [Cg_j] or null
+  int c1, c2;            // channel boundaries
+};
+template <int K, bool FLIP>
+__device__ __forceinline__ float dwk_point(const float* __restrict__ x, int ldx, const float* __restrict__ wc, long long p, int px, int py,
+                                           int H, int W, int c, float acc) {
+#pragma unroll
+  for (int ky = 0; ky < K; ky++) {
+    const int dy = FLIP ? K / 2 - ky : ky - K / 2;
+    const int yy = py + dy;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < K; kx++) {
+      const int dx = FLIP ? K / 2 - kx : kx - K / 2;
+      const int xx = px + dx;
+      if (xx < 0 || xx >= W) continue;
+      acc = fmaf(__ldg(wc + ky * K + kx), x[(p + (long long)dy * W + dx) * ldx + c], acc);
+    }
+  }
+  return acc;
+}
+template <bool FLIP, bool ADD>
+__global__ void __launch_bounds__(256) dwk3_kernel(const float* __restrict__ x, int ldx, Crpe3 f, float* __restrict__ y, int ldy, int B,
+                                                   int H, int W, int C) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * H * W * C;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long p = idx / C;
+  const int px = (int)(p % W), py = (int)((p / W) % H);
+  float acc;
+  if (c < f.c1) {
+    acc = (f.b[0] && !FLIP) ? f.b[0][c] : 0.f;
+    acc = dwk_point<3, FLIP>(x, ldx, f.w[0] + (size_t)c * 9, p, px, py, H, W, c, acc);
+  } else if (c < f.c2) {
+    acc = (f.b[1] && !FLIP) ? f.b[1][c - f.c1] : 0.f;
+    acc = dwk_point<5, FLIP>(x, ldx, f.w[1] + (size_t)(c - f.c1) * 25, p, px, py, H, W, c, acc);
+  } else {
+    acc = (f.b[2] && !FLIP) ? f.b[2][c - f.c2] : 0.f;
+    acc = dwk_point<7, FLIP>(x, ldx, f.w[2] + (size_t)(c - f.c2) * 49, p, px, py, H, W, c, acc);
+  }
+  if (ADD) y[p * ldy + c] += acc; else y[p * ldy + c] = acc;
+}
+
+template <int K>
+__device__ __forceinline__ void dwk_wgrad_rows(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx, int H, int W,
+                                               int c, long long r0, long long r1, float (&acc)[50]) {
+  for (long long r = r0 + threadIdx.y; r < r1; r += RL) {
+    const int px = (int)(r % W), py = (int)((r / W) % H);
+    const float gv = g[r * ldg + c];
+    acc[49] += gv;
+#pragma unroll
+    for (int ky = 0; ky < K; ky++) {
+      const int yy = py + ky - K / 2;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < K; kx++) {
+        const int xx = px + kx - K / 2;
+        if (xx < 0 || xx >= W) continue;
+        acc[ky * K + kx] = fmaf(gv, x[(r + (long long)(ky - K / 2) * W + (kx - K / 2)) * ldx + c], acc[ky * K + kx]);
+      }
+    }
+  }
+}
+// partials [blk][50][C]: taps 0 .. K*K-1 of the channel's window, slot 49 = bias sum
+__global__ void __launch_bounds__(RC * RL) dwk3_wgrad_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx,
+                                                             int B, int H, int W, int C, int c1, int c2, int rows, float* __restrict__ part) {
+  __shared__ float sm[RL][RC];
+  const int c = blockIdx.y * RC + threadIdx.x;
+  const long long M = (long long)B * H * W;
+  const long long r0 = (long long)blockIdx.x * rows;
+  const long long r1 = r0 + rows < M ? r0 + rows : M;
+  float acc[50];
+#pragma unroll
+  for (int t = 0; t < 50; t++) acc[t] = 0.f;
+  if (c < C) {
+    if (c < c1) dwk_wgrad_rows<3>(g, ldg, x, ldx, H, W, c, r0, r1, acc);
+    else if (c < c2) dwk_wgrad_rows<5>(g, ldg, x, ldx, H, W, c, r0, r1, acc);
+    else dwk_wgrad_rows<7>(g, ldg, x, ldx, H, W, c, r0, r1, acc);
+  }
+#pragma unroll
+  for (int t = 0; t < 50; t++) {
+    sm[threadIdx.y][threadIdx.x] = acc[t];
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      float s = sm[0][threadIdx.x];
+#pragma unroll
+      for (int l = 1; l < RL; l++) s += sm[l][threadIdx.x];
+      part[((size_t)blockIdx.x * 50 + t) * C + c] = s;
+    }
+    __syncthreads();
+  }
+}
+struct Crpe3Out {
+  float* dw[3];
+  float* db[3];
+  int c1, c2;
+};
+__global__ void __launch_bounds__(256) dwk3_fold_kernel(const float* __restrict__ part, int nblk, int C, Crpe3Out o) {
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int n = 50 * C;
+  const float s = bwd_fold_sum(part, nblk, n, i, i < n);
+  if (threadIdx.y != 0 || i >= n) return;
+  const int t = i / C, c = i - t * C;
+  const int j = c < o.c1 ? 0 : (c < o.c2 ? 1 : 2);
+  const int cc = c - (j == 0 ? 0 : (j == 1 ? o.c1 : o.c2));
+  const int KK = j == 0 ? 9 : (j == 1 ? 25 : 49);
+  if (t == 49) { if (o.db[j]) o.db[j][cc] = s; }
+  else if (t < KK) o.dw[j][(size_t)cc * KK + t] = s;
+}
+
 template <int K>
 int dwk_launch(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int B, int H, int W, int Cg, bool flip, bool add,
                cudaStream_t st) {
@@ -215,6 +330,35 @@ int launch_bwd_dwk_wgrad(int K, const float* g, int ldg, const float* x, int ldx
   if (K == 7) return dwk_wgrad_launch<7>(g, ldg, x, ldx, B, H, W, Cg, dw, db, part, st);
   tcx_set_error("bwd_dwk_wgrad: window %d not built (3, 5, 7)", K);
   return -1;
+}
+int launch_bwd_dwk3(const float* x, int ldx, const float* const* w, const float* const* b, int c1, int c2, float* y, int ldy, int B, int H,
+                    int W, int C, int flip, int add, cudaStream_t st) {
+  const long long total = (long long)B * H * W * C;
+  if (total == 0) return 0;
+  Crpe3 f;
+  for (int j = 0; j < 3; j++) { f.w[j] = w[j]; f.b[j] = b ? b[j] : nullptr; }
+  f.c1 = c1; f.c2 = c2;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (!flip && !add) dwk3_kernel<false, false><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  else if (!flip && add) dwk3_kernel<false, true><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  else if (flip && !add) dwk3_kernel<true, false><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  else dwk3_kernel<true, true><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  return tcx_check_launch("bwd_dwk3");
+}
+size_t bwd_dwk3_wgrad_part_floats(long long M, int C) { return (size_t)bwd_red_blocks(M) * 50 * C; }
+int launch_bwd_dwk3_wgrad(const float* g, int ldg, const float* x, int ldx, int B, int H, int W, int C, int c1, int c2, float* const* dw,
+                          float* const* db, float* part, cudaStream_t st) {
+  const long long M = (long long)B * H * W;
+  if (M == 0 || C == 0) return 0;
+  const int nblk = bwd_red_blocks(M);
+  const int rows = (int)((M + nblk - 1) / nblk + RL - 1) / RL * RL;
+  dwk3_wgrad_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(g, ldg, x, ldx, B, H, W, C, c1, c2, rows, part);
+  TCX_TRY(tcx_check_launch("bwd_dwk3_wgrad"));
+  Crpe3Out o;
+  for (int j = 0; j < 3; j++) { o.dw[j] = dw[j]; o.db[j] = db[j]; }
+  o.c1 = c1; o.c2 = c2;
+  dwk3_fold_kernel<<<cdiv(50 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, o);
+  return tcx_check_launch("bwd_dwk3_fold");
 }
 int launch_bwd_fold_mask(const float* part, int batch, int S, int R, int Ch, float scale, float* out, float* outT, cudaStream_t st) {
   if (batch == 0 || R == 0) return 0;
