@@ -312,12 +312,20 @@ size_t tcx_eff_attn_bwd_workspace_bytes(int B, int N, int C);
 int tcx_eff_attn_bwd(const float* dy, const void* const* p, const void* saved, float* dxn, void* const* dp, int B, int N, int C,
                      void* ws, void* stream);
 
-/* FactorAtt_ConvRelPosEnc (MSTr.py:852-886) backward.  The training forward is tcx_mb_factor_attn_fwd itself: its workspace
- * (q | k | v rows, attention output) must be kept and passed as fwd_ws, with the same xn.  dy [B*N][C] -> dxn (NULL: skipped),
- * dp = gradients of {qkv_w,qkv_b,crpe_w3,crpe_b3,crpe_w5,crpe_b5,crpe_w7,crpe_b7,proj_w,proj_b}.  8 heads. */
+/* FactorAtt_ConvRelPosEnc (MSTr.py:852-886) training forward on the fp16 pipeline (qkv GEMM -> fused per-head attention + conv
+ * relative position encoding -> projection GEMM + residual: the kernels of the inference path; qkv / proj weights must be
+ * prepared).  `saved` (tcx_mb_factor_attn_saved_bytes) keeps the fp16 q | k | v rows and the fp16 attention output for backward. */
+size_t tcx_mb_factor_attn_saved_bytes(int B, int N, int C);
+size_t tcx_mb_factor_attn_train_workspace_bytes(int B, int N, int C);
+int tcx_mb_factor_attn_train_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W, int C,
+                                 int heads, void* saved, void* ws, void* stream);
+
+/* FactorAtt_ConvRelPosEnc backward.  fwd_ws = the workspace of tcx_mb_factor_attn_fwd (saved_f16 = 0: fp32 q | k | v rows, context,
+ * attention output) or the `saved` buffer of tcx_mb_factor_attn_train_fwd (saved_f16 = 1), with the same xn.  dy [B*N][C] -> dxn
+ * (NULL: skipped), dp = gradients of {qkv_w,qkv_b,crpe_w3,crpe_b3,crpe_w5,crpe_b5,crpe_w7,crpe_b7,proj_w,proj_b}.  8 heads. */
 size_t tcx_mb_factor_attn_bwd_workspace_bytes(int B, int N, int C);
-int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* p, const void* fwd_ws, float* dxn, void* const* dp,
-                           int B, int H, int W, int C, int heads, void* ws, void* stream);
+int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* p, const void* fwd_ws, int saved_f16, float* dxn,
+                           void* const* dp, int B, int H, int W, int C, int heads, void* ws, void* stream);
 
 /* ConvPosEnc / DWConv (MSTr.py:744-752, :26-31) backward of y = dw3x3(x) + b (+ x when add_input): dx, dw [C][9], db [C]
  * (dx may be NULL; dw NULL skips dw and db) */

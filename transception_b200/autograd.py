@@ -112,8 +112,14 @@ class FactorAttFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, H, W, heads, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb, residual=None):
         x = x.contiguous()
-        y, ws = ops.mb_factor_attn(x, H, W, heads, None, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
-                                   residual=residual.contiguous() if residual is not None else None, keep_ws=True)
+        res = residual.contiguous() if residual is not None else None
+        ctx.f16 = ops.USE_F16
+        if ctx.f16:       # the fp16 pipeline of the inference path (fused per-head attention kernel), keeping fp16 q | k | v and output
+            y, ws = ops.mb_factor_attn_train(x, H, W, heads, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
+                                             residual=res)
+        else:
+            y, ws = ops.mb_factor_attn(x, H, W, heads, None, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
+                                       residual=res, keep_ws=True)
         ctx.save_for_backward(x, ws, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb)
         ctx.geom = (H, W, heads)
         ctx.has_res = residual is not None
@@ -124,7 +130,7 @@ class FactorAttFn(torch.autograd.Function):
         x, ws, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb = ctx.saved_tensors
         H, W, heads = ctx.geom
         dx, g = ops.mb_factor_attn_bwd(dy, x, ws, H, W, heads, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], projw, projb,
-                                       need_dx=ctx.needs_input_grad[0])
+                                       need_dx=ctx.needs_input_grad[0], saved_f16=ctx.f16)
         return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None,)
 
 

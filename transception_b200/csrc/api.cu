@@ -745,6 +745,52 @@ int tcx_mb_factor_attn_fwd(const float* xn, const void* const* p, const float* r
   return run_mb_attn(1, xs, ps, residual ? rs : nullptr, ys, B, H, W, C, heads, qkv, ctx, att, S(stream));
 }
 
+// training forward of FactorAtt_ConvRelPosEnc on the fp16 pipeline (the kernels of the inference path): saved = fp16 q | k | v rows
+// and the fp16 attention output; ws = fp16 xn + per-head contexts
+size_t tcx_mb_factor_attn_saved_bytes(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  return 4 * (rnd(3 * bnc / 2 + 64) + rnd(bnc / 2 + 64) + 64);
+}
+size_t tcx_mb_factor_attn_train_workspace_bytes(int B, int N, int C) {
+  const size_t bnc = (size_t)B * N * C;
+  return 4 * (rnd(bnc / 2 + 64) + rnd((size_t)B * C * C) + 64);
+}
+int tcx_mb_factor_attn_train_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W, int C,
+                                 int heads, void* saved, void* ws, void* stream) {
+  TCX_REQUIRE(xn && p && y && saved && ws, "mb_factor_attn_train_fwd: null pointer");
+  TCX_REQUIRE(heads == 8 && C % heads == 0, "mb_factor_attn_train_fwd: built for 8 heads");
+  const __half* wqkv = w16_of(p[0]);
+  const __half* wproj = w16_of(p[8]);
+  TCX_REQUIRE(wqkv && wproj, "mb_factor_attn_train_fwd: qkv / proj weights are not prepared (tcx_prepare_weight_f16)");
+  cudaStream_t st = S(stream);
+  const int M = B * H * W, Ch = C / heads;
+  const size_t bnc = (size_t)M * C;
+  Carver sv(saved);
+  __half* qkv16 = H16(sv.take(3 * bnc / 2 + 64));
+  __half* att16 = H16(sv.take(bnc / 2 + 64));
+  Carver c(ws);
+  __half* xn16 = H16(c.take(bnc / 2 + 64));
+  float* ctx = c.take((size_t)B * C * C);
+  TCX_TRY(launch_f32_to_f16(xn, xn16, (long long)bnc, st));
+  {
+    GemmParams gp = gemm1(F(xn16), F(wqkv), reinterpret_cast<float*>(qkv16), M, 3 * C, C);
+    gp.ab16 = 1; gp.out16 = 1;
+    gp.g[0].epi.bias = F(p[1]);
+    TCX_TRY(launch_gemm(gp, st));
+  }
+  {
+    Mb16Args a{};
+    a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.scale = 1.0f / sqrtf((float)Ch);
+    a.qkv[0] = qkv16; a.ctx[0] = ctx; a.out[0] = att16;
+    for (int j = 0; j < 3; j++) { a.cw[0][j] = F(p[2 + 2 * j]); a.cb[0][j] = F(p[3 + 2 * j]); }
+    TCX_TRY(launch_mb_attention16(a, 1, st));
+  }
+  GemmParams gp = gemm1(F(att16), F(wproj), y, M, C, C);
+  gp.ab16 = 1;
+  gp.g[0].epi.bias = F(p[9]); gp.g[0].epi.residual = residual; gp.g[0].epi.ldr = C;
+  return launch_gemm(gp, st);
+}
+
 // ---- MHCA blocks -------------------------------------------------------------------------
 size_t tcx_mhca_blocks_workspace_bytes(int G, int B, int N, int C) {
   const size_t bnc = (size_t)B * N * C;
@@ -1933,14 +1979,14 @@ static size_t mb_attn_bwd_ws_floats(int B, int N, int C) {
   bwd_wgrad_splits(N, C, C, &S, &Ms);
   const size_t pack = (size_t)B * S * C * Ms, ch = (size_t)B * ea_bwd_chunks(N) * C;
   const size_t lin = std::max(linear_bwd_ws_floats(M, C, C), linear_bwd_ws_floats(M, 3 * C, C));
-  return 6 * rnd(bnc) + rnd(3 * bnc) + 3 * rnd(bcc) + 2 * rnd(pack) +
+  return 6 * rnd(bnc) + 2 * rnd(3 * bnc) + 3 * rnd(bcc) + 2 * rnd(pack) +
          rnd(std::max((size_t)B * S * C * C, wgrad_tc_scratch_floats(N, C, C, B, 4))) + 3 * rnd(ch) +
          rnd(std::max(bwd_dwk_wgrad_part_floats(7, M, C), bwd_dwk3_wgrad_part_floats(M, C))) + lin + 64;
 }
 size_t tcx_mb_factor_attn_bwd_workspace_bytes(int B, int N, int C) { return 4 * mb_attn_bwd_ws_floats(B, N, C); }
 
-int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* p, const void* fwd_ws, float* dxn, void* const* dp,
-                           int B, int H, int W, int C, int heads, void* ws, void* stream) {
+int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* p, const void* fwd_ws, int saved_f16, float* dxn,
+                           void* const* dp, int B, int H, int W, int C, int heads, void* ws, void* stream) {
   TCX_REQUIRE(dy && xn && p && fwd_ws && dp && ws, "mb_factor_attn_bwd: null pointer");
   TCX_REQUIRE(heads == 8 && C % heads == 0 && C % 4 == 0, "mb_factor_attn_bwd: built for 8 heads (crpe windows 3/5/7 on 2/3/3 heads)");
   for (int i = 0; i < 10; i++) TCX_REQUIRE(dp[i] != nullptr, "mb_factor_attn_bwd: gradient slot %d is null", i);
@@ -1949,17 +1995,28 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
   const long long M = (long long)B * N;
   const size_t bnc = (size_t)M * C, bcc = (size_t)B * C * C;
   const float scale = 1.0f / sqrtf((float)Ch);
-  // forward buffers (tcx_mb_factor_attn_fwd carve order): q | k | v rows, context, attention output before the projection
+  // forward buffers: fp32 (tcx_mb_factor_attn_fwd carve order: q | k | v rows, context, attention output before the projection)
+  // or the fp16 pair of tcx_mb_factor_attn_train_fwd (q | k | v rows, attention output), widened to fp32 here
   Carver f(const_cast<void*>(fwd_ws));
-  const float* qkv = f.take(3 * bnc);
-  f.take(bcc);
-  const float* att = f.take(bnc);
+  Carver c(ws);
+  const float* qkv;
+  const void* att;
+  if (saved_f16) {
+    const __half* qkv16 = H16(f.take(3 * bnc / 2 + 64));
+    att = H16(f.take(bnc / 2 + 64));
+    float* q32 = c.take(3 * bnc);
+    TCX_TRY(launch_f16_to_f32(qkv16, q32, (long long)(3 * bnc), st));
+    qkv = q32;
+  } else {
+    qkv = f.take(3 * bnc);
+    f.take(bcc);
+    att = f.take(bnc);
+  }
   const float* q = qkv; const float* k = qkv + C; const float* v = qkv + 2 * C;
   const int ld = 3 * C;
   int SP, Ms;
   bwd_wgrad_splits(N, C, C, &SP, &Ms);
   const size_t ch = (size_t)B * ea_bwd_chunks(N) * C;
-  Carver c(ws);
   float* dxo = c.take(bnc);
   float* P = c.take(bnc);
   float* dP = c.take(bnc);
@@ -2009,7 +2066,7 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
     return launch_gemm(g, st);
   };
   // projection: att [M][C] -> y
-  TCX_TRY(run_linear_bwd(att, 0, F(p[8]), dy, dxo, G(8), G(9), M, C, C, lin, st));
+  TCX_TRY(run_linear_bwd(att, saved_f16, F(p[8]), dy, dxo, G(8), G(9), M, C, C, lin, st));
   // recompute: P = softmax over tokens of k, ctx = per-head P^T v, conv_v = crpe depthwise convolutions of v
   TCX_TRY(launch_bwd_ksoftmax32(k, ld, B, N, C, pm, ps, P, st));
   TCX_TRY(ctx_gemm(P, C, v, ld, 1.0f, ctx, nullptr));
@@ -2023,6 +2080,15 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
   TCX_TRY(tok_gemm(dxo, C, ctx, dqfa, C, nullptr));                       // d(q ctx)/dq, before the scale
   TCX_TRY(ctx_gemm(q, ld, dxo, C, scale, dctx, dctxT));                   // dctx = scale * mask(q^T dxo)
   TCX_TRY(launch_mb_bwd_dq(dxo, dqfa, convv, q, ld, scale, M, C, dqkv, ld, st));   // dq; convv <- d conv_v
+  // the crpe filter / bias gradients need only d conv_v and v: they leave the critical stream here and rejoin at the end
+  AuxStreams* auxw = mn ? aux_streams(st) : nullptr;
+  if (auxw) {
+    TCX_REQUIRE(cudaEventRecord(auxw->fork, st) == cudaSuccess && cudaStreamWaitEvent(auxw->s[2], auxw->fork, 0) == cudaSuccess,
+                "mb_factor_attn_bwd: fork failed");
+    float* dw3[3] = {G(2), G(4), G(6)};
+    float* db3[3] = {G(3), G(5), G(7)};
+    TCX_TRY(launch_bwd_dwk3_wgrad(convv, C, v, ld, B, H, W, C, 2 * Ch, 5 * Ch, dw3, db3, wpart, auxw->s[2]));
+  }
   if (mn) {
     TCX_TRY(launch_bwd_dwk3(convv, C, cw3, nullptr, 2 * Ch, 5 * Ch, dvconv, C, B, H, W, C, 1, 0, st));
   } else {
@@ -2032,7 +2098,9 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
   TCX_TRY(tok_gemm(P, C, dctxT, dqkv + 2 * C, ld, dvconv));               // dv = P dctx + conv^T(d conv_v)
   TCX_TRY(tok_gemm(v, ld, dctx, dP, C, nullptr));                         // dP = v dctx^T
   TCX_TRY(launch_bwd_colsoftmax(P, dP, B, N, C, sp, dqkv + C, ld, st));   // dk
-  if (mn) {
+  if (auxw) {
+    // already running beside the main chain
+  } else if (mn) {
     float* dw3[3] = {G(2), G(4), G(6)};
     float* db3[3] = {G(3), G(5), G(7)};
     TCX_TRY(launch_bwd_dwk3_wgrad(convv, C, v, ld, B, H, W, C, 2 * Ch, 5 * Ch, dw3, db3, wpart, st));
@@ -2041,7 +2109,9 @@ int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* 
       TCX_TRY(launch_bwd_dwk_wgrad(win[j], convv + c0[j], C, v + c0[j], ld, B, H, W, cg[j], G(2 + 2 * j), G(3 + 2 * j), wpart, st));
   }
   // qkv Linear
-  return run_linear_bwd(xn, 0, F(p[0]), dqkv, dxn, G(0), G(1), M, 3 * C, C, lin, st);
+  TCX_TRY(run_linear_bwd(xn, 0, F(p[0]), dqkv, dxn, G(0), G(1), M, 3 * C, C, lin, st));
+  if (auxw) TCX_TRY(join_stream(auxw, 2, st));
+  return 0;
 }
 
 // ---- ConvPosEnc / DWConv (MSTr.py:744-752, :26-31) backward: y = dw3x3(x) + b (+ x) ----
@@ -2053,12 +2123,15 @@ int tcx_dwconv_tokens_bwd(const float* x, const float* w, const float* dy, float
   TCX_REQUIRE(x && w && dy && ws, "dwconv_tokens_bwd: null pointer");
   cudaStream_t st = S(stream);
   const long long M = (long long)B * H * W;
+  AuxStreams* aux = dx && dw ? aux_streams(st) : nullptr;
+  if (aux) TCX_TRY(fork_streams(aux, st, 1));
   if (dx) {
     if (add_input)
       TCX_REQUIRE(cudaMemcpyAsync(dx, dy, sizeof(float) * M * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess, "dwconv_tokens_bwd: copy failed");
     TCX_TRY(launch_bwd_dwk(3, dy, C, w, nullptr, dx, C, B, H, W, C, 1, add_input ? 1 : 0, st));
   }
-  if (dw) TCX_TRY(launch_bwd_dwk_wgrad(3, dy, C, x, C, B, H, W, C, dw, db, reinterpret_cast<float*>(ws), st));
+  if (dw) TCX_TRY(launch_bwd_dwk_wgrad(3, dy, C, x, C, B, H, W, C, dw, db, reinterpret_cast<float*>(ws), aux ? aux->s[0] : st));
+  if (aux) TCX_TRY(join_stream(aux, 0, st));
   return 0;
 }
 

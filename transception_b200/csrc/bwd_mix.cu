@@ -20,6 +20,96 @@ __device__ __forceinline__ void gelu_parts(float z, float& gelu, float& dgelu) {
   dgelu = fmaf(z, pdf, cdf);
 }
 
+// C <= 64: half a warp per row (16 lanes x float4), two rows per warp — the 64-channel maps (stage 1, bridge tokens, the last
+// decoder layer: 50 176 to 97 216 rows) would leave half of every warp idle in the kernel below.
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <bool GELU>
+__global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused64_kernel(const float* __restrict__ u, const float* __restrict__ dz,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      float eps, float* __restrict__ du, float* __restrict__ act,
+                                                                      const float* __restrict__ dres, long long M, int C,
+                                                                      float* __restrict__ part) {
+  __shared__ float sm[LF_WARPS * 2][2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, hw = lane >> 4;
+  const float invC = 1.0f / (float)C;
+  const int c = hl * 4;
+  const bool live = c < C;
+  const float4 g4 = live ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b4 = (GELU && live) ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)gridDim.x * LF_WARPS * 2;
+  // both halves of a warp run the same number of iterations (full-mask shuffles): out-of-range rows compute on zeros
+  for (long long base = (long long)blockIdx.x * LF_WARPS * 2 + warp * 2; base < M; base += stride) {
+    const long long row = base + hw;
+    const bool rl = row < M && live;
+    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = x4;
+    if (rl) {
+      x4 = *reinterpret_cast<const float4*>(u + row * C + c);
+      d4 = *reinterpret_cast<const float4*>(dz + row * C + c);
+    }
+    const float mean = half_sum((x4.x + x4.y) + (x4.z + x4.w)) * invC;
+    float q = 0.f;
+    if (live) {
+      const float a = x4.x - mean, b = x4.y - mean, cc = x4.z - mean, d = x4.w - mean;
+      q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(cc, cc, q); q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(half_sum(q) * invC + eps);
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+    float xh[4], g[4], ge[4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      xh[k] = (xv[k] - mean) * rstd;
+      float gg = dv[k];
+      ge[k] = 0.f;
+      if (GELU) {
+        float dg;
+        gelu_parts(fmaf(xh[k], gv[k], bv[k]), ge[k], dg);
+        gg *= dg;
+      }
+      g[k] = rl ? gg : 0.f;
+      const float dxh = g[k] * gv[k];
+      s1 += dxh;
+      s2 = fmaf(dxh, xh[k], s2);
+    }
+    s1 = half_sum(s1) * invC;
+    s2 = half_sum(s2) * invC;
+    if (rl) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        o[k] = rstd * (g[k] * gv[k] - s1 - xh[k] * s2);
+        ag[k] = fmaf(g[k], xh[k], ag[k]);
+        ab[k] += g[k];
+      }
+      if (dres) {
+        const float4 r = *reinterpret_cast<const float4*>(dres + row * C + c);
+        o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+      }
+      *reinterpret_cast<float4*>(du + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (GELU && act) *reinterpret_cast<float4*>(act + row * C + c) = make_float4(ge[0], ge[1], ge[2], ge[3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    sm[warp * 2 + hw][0][c + k] = ag[k];
+    sm[warp * 2 + hw][1][c + k] = ab[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += LF_WARPS * 32) {
+    const int t = i / C, cc = i - t * C;
+    float a = sm[0][t][cc];
+#pragma unroll
+    for (int w = 1; w < LF_WARPS * 2; w++) a += sm[w][t][cc];
+    part[((size_t)blockIdx.x * 2 + t) * C + cc] = a;
+  }
+}
+
 // One warp per row, NV float4 chunks per lane (columns lane*4 + 128*j); rows are dealt round-robin over all warps of the grid.
 // part: [gridDim.x][2][C] = (sum g*xhat | sum g) of the rows this block handled.
 template <int NV, bool GELU>
@@ -136,21 +226,23 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float
 constexpr int DB_CT = 16;            // channel threads per block (x 4 channels = 64 channels)
 constexpr int DB_PL = 16;            // pixel lanes per block
 
-__global__ void __launch_bounds__(DB_CT * DB_PL) dw_bwd_fused_kernel(const float* __restrict__ du, const __half* __restrict__ h,
+__global__ void __launch_bounds__(DB_CT * DB_PL, 2) dw_bwd_fused_kernel(const float* __restrict__ du, const __half* __restrict__ h,
                                                                     const float* __restrict__ w, float* __restrict__ dh, int B, int H, int W,
                                                                     int C, int pix_per_block, float* __restrict__ part) {
   __shared__ float sm[DB_PL][10][DB_CT * 4 + 4];
+  __shared__ float4 swt[9][DB_CT];          // this block's 64 channels x 9 taps (kept out of the register file: two blocks per SM)
   const int ct = threadIdx.x % DB_CT, pl = threadIdx.x / DB_CT;
   const int c = (blockIdx.y * DB_CT + ct) * 4;
   const bool cl = c < C;
   const long long M = (long long)B * H * W;
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   const long long p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
-  float wt[9][4];
-#pragma unroll
-  for (int t = 0; t < 9; t++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) wt[t][k] = cl ? __ldg(w + (size_t)(c + k) * 9 + t) : 0.f;
+  for (int i = threadIdx.x; i < 9 * DB_CT * 4; i += DB_CT * DB_PL) {
+    const int t = i / (DB_CT * 4), cc = i - t * (DB_CT * 4);
+    const int col = blockIdx.y * DB_CT * 4 + cc;
+    reinterpret_cast<float*>(&swt[t][0])[cc] = col < C ? __ldg(w + (size_t)col * 9 + t) : 0.f;
+  }
+  __syncthreads();
   float acc[10][4];
 #pragma unroll
   for (int t = 0; t < 10; t++)
@@ -182,8 +274,9 @@ __global__ void __launch_bounds__(DB_CT * DB_PL) dw_bwd_fused_kernel(const float
           if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
             const long long nb = p - (long long)(ky - 1) * W - (kx - 1);
             const float4 gn = (t == 4) ? gc : *reinterpret_cast<const float4*>(du + nb * C + c);
-            o[0] = fmaf(wt[t][0], gn.x, o[0]); o[1] = fmaf(wt[t][1], gn.y, o[1]);
-            o[2] = fmaf(wt[t][2], gn.z, o[2]); o[3] = fmaf(wt[t][3], gn.w, o[3]);
+            const float4 wv = swt[t][ct];
+            o[0] = fmaf(wv.x, gn.x, o[0]); o[1] = fmaf(wv.y, gn.y, o[1]);
+            o[2] = fmaf(wv.z, gn.z, o[2]); o[3] = fmaf(wv.w, gn.w, o[3]);
           }
         }
       }
@@ -245,7 +338,10 @@ int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, con
     if (gelu) ln_bwd_fused_kernel<NV, true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part); \
     else ln_bwd_fused_kernel<NV, false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part); \
   } while (0)
-  if (C <= 128) LNB(1);
+  if (C <= 64) {
+    if (gelu) ln_bwd_fused64_kernel<true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part);
+    else ln_bwd_fused64_kernel<false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part);
+  } else if (C <= 128) LNB(1);
   else if (C <= 256) LNB(2);
   else LNB(4);
 #undef LNB

@@ -104,7 +104,10 @@ _PROTOS = {
     "tcx_eff_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_eff_attn_bwd": (_i, [_vp, _pp, _vp, _vp, _pp, _i, _i, _i, _vp, _vp]),
     "tcx_mb_factor_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
-    "tcx_mb_factor_attn_bwd": (_i, [_vp, _vp, _pp, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mb_factor_attn_bwd": (_i, [_vp, _vp, _pp, _vp, _i, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mb_factor_attn_saved_bytes": (_sz, [_i, _i, _i]),
+    "tcx_mb_factor_attn_train_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_mb_factor_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tcx_dwconv_tokens_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_dwconv_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_attn_core_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -1022,8 +1025,25 @@ def eff_attn_bwd(dy, saved, kw, kb, qw, qb, vw, vb, rw, rb, need_dx=True):
     return dxn, grads
 
 
-def mb_factor_attn_bwd(dy, xn, fwd_ws, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb, need_dx=True):
-    """(dxn, [10 parameter gradients in slot order]) of FactorAtt_ConvRelPosEnc; fwd_ws = mb_factor_attn(..., keep_ws=True)[1]."""
+def mb_factor_attn_train(xn, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, head_splits, projw, projb, residual=None):
+    """Training forward of FactorAtt_ConvRelPosEnc on the fp16 pipeline: (y, saved) with ``saved`` the opaque buffer that
+    mb_factor_attn_bwd(..., saved_f16=True) consumes."""
+    require_cuda(xn)
+    lib = load_library()
+    xn = xn.contiguous()
+    B, N, C = xn.shape
+    _check_crpe(head_splits, crpe_w, heads)
+    y = torch.empty_like(xn)
+    saved = _ws(lib.tcx_mb_factor_attn_saved_bytes(B, N, C), xn)
+    ws = _ws(lib.tcx_mb_factor_attn_train_workspace_bytes(B, N, C), xn)
+    tab = _table([qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2], projw, projb], mats=(0, 8))
+    _chk(lib.tcx_mb_factor_attn_train_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, H, W, C, heads, _ptr(saved), _ptr(ws), _stream()))
+    return y, saved
+
+
+def mb_factor_attn_bwd(dy, xn, fwd_ws, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb, need_dx=True, saved_f16=False):
+    """(dxn, [10 parameter gradients in slot order]) of FactorAtt_ConvRelPosEnc; fwd_ws = mb_factor_attn(..., keep_ws=True)[1], or
+    the ``saved`` buffer of mb_factor_attn_train with ``saved_f16``."""
     require_cuda(dy)
     lib = load_library()
     dy, xn = dy.contiguous(), xn.contiguous()
@@ -1034,7 +1054,8 @@ def mb_factor_attn_bwd(dy, xn, fwd_ws, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, 
     tab = _table(params)
     gtab = (ctypes.c_void_p * 10)(*[_ptr(g) for g in grads])
     ws = _ws(lib.tcx_mb_factor_attn_bwd_workspace_bytes(B, N, C), dy)
-    _chk(lib.tcx_mb_factor_attn_bwd(_ptr(dy), _ptr(xn), tab, _ptr(fwd_ws), _ptr(dxn), gtab, B, H, W, C, heads, _ptr(ws), _stream()))
+    _chk(lib.tcx_mb_factor_attn_bwd(_ptr(dy), _ptr(xn), tab, _ptr(fwd_ws), int(saved_f16), _ptr(dxn), gtab, B, H, W, C, heads, _ptr(ws),
+                                    _stream()))
     return dxn, grads
 
 
