@@ -7,9 +7,10 @@ import torch
 from transception_b200 import inference as INF
 
 
-def _reference_loop(image, net, patch_size):
+def _reference_loop(image, net, patch_size, device="cuda"):
     """utils.py:65-92 verbatim in behaviour: per slice cubic zoom, ToTensor + Normalize, bs-1 forward,
-    argmax(softmax), nearest zoom back."""
+    argmax(softmax), nearest zoom back.  Pinned to the real utils.test_single_volume by
+    tests/test_reference_callers.py::test_reference_loop_restatement_is_pinned_to_utils."""
     from scipy.ndimage import zoom
     from torchvision import transforms
     prediction = np.zeros(image.shape, dtype=np.uint8)
@@ -19,7 +20,7 @@ def _reference_loop(image, net, patch_size):
         x, y = sl.shape
         if x != patch_size[0] or y != patch_size[1]:
             sl = zoom(sl, (patch_size[0] / x, patch_size[1] / y), order=3)
-        inp = tf(sl).unsqueeze(0).float().cuda()
+        inp = tf(sl).unsqueeze(0).float().to(device)
         with torch.no_grad():
             out = torch.argmax(torch.softmax(net(inp), dim=1), dim=1).squeeze(0).cpu().numpy()
         prediction[ind] = zoom(out, (x / patch_size[0], y / patch_size[1]), order=0) if (x, y) != tuple(patch_size) else out

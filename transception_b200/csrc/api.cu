@@ -249,12 +249,16 @@ struct AuxStreams {
   bool ok = false;
 };
 static std::mutex g_aux_mu;
-static std::unordered_map<const void*, AuxStreams> g_aux;   // one set per calling stream (independent forward chains)
+// one set per (device, calling stream): the legacy default stream has the same handle on every device, and one process may
+// drive several GPUs (nn.DataParallel, trainer.py:110-111)
+static std::unordered_map<unsigned long long, AuxStreams> g_aux;
 static int g_flag_fork = 1;
 AuxStreams* aux_streams(cudaStream_t st) {
   if (!g_flag_fork) return nullptr;
   std::lock_guard<std::mutex> lk(g_aux_mu);
-  AuxStreams& a = g_aux[reinterpret_cast<const void*>(st)];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  AuxStreams& a = g_aux[(unsigned long long)reinterpret_cast<uintptr_t>(st) * 64ull + (unsigned long long)(dev & 63)];
   if (!a.ok) {
     bool good = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < TCX_AUX && good; i++)
