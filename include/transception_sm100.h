@@ -327,6 +327,18 @@ size_t tcx_mb_factor_attn_bwd_workspace_bytes(int B, int N, int C);
 int tcx_mb_factor_attn_bwd(const float* dy, const float* xn, const void* const* p, const void* fwd_ws, int saved_f16, float* dxn,
                            void* const* dp, int B, int H, int W, int C, int heads, void* ws, void* stream);
 
+/* Bridge attention core softmax(q k^T * scale) v (MSTr.py:2281-2285) for training, flash style in both directions.
+ * tcx_flash_attn_train_fwd = tcx_flash_attn_fwd + lse [B][Nq]: the row log2-sum-exp of q k^T * scale * log2(e).
+ * tcx_flash_attn_bwd: q [B][Nq][64], kv [B][Nk][128] (k | v), out = the forward output, lse, dout [B][Nq][64] -> dq [B][Nq][64],
+ * dkv [B][Nk][128]: one tcgen05 kernel per (image, 128-row kv tile) recomputes the probabilities tile by tile (no score-sized
+ * tensor in HBM), dK / dV accumulate in tensor memory, the 7 dQ partials are folded in tile order.  fp16 operands; dout is
+ * scaled by one power of two derived from its absolute maximum on the device.  Bit-reproducible. */
+int tcx_flash_attn_train_fwd(const float* q, const float* kv, float* out, float* lse, int B, int Nq, int Nk, float scale, void* ws,
+                             void* stream);
+size_t tcx_flash_attn_bwd_workspace_bytes(int B, int Nq, int Nk);
+int tcx_flash_attn_bwd(const float* q, const float* kv, const float* out, const float* lse, const float* dout, float scale, float* dq,
+                       float* dkv, int B, int Nq, int Nk, void* ws, void* stream);
+
 /* ConvPosEnc / DWConv (MSTr.py:744-752, :26-31) backward of y = dw3x3(x) + b (+ x when add_input): dx, dw [C][9], db [C]
  * (dx may be NULL; dw NULL skips dw and db) */
 size_t tcx_dwconv_tokens_bwd_workspace_bytes(int B, int H, int W, int C);

@@ -816,3 +816,30 @@ def test_train_step_graph_fused_sgd(cuda_lib):
         ops.invalidate_prepared(net_a)
         y2 = net_a(x)
     assert torch.equal(y1, y2), "stale fp16 weight copies after FusedSGD updates"
+
+
+@pytest.mark.parametrize("B,Nq,Nk,big", [(2, 300, 64, False), (1, 128, 128, False), (3, 777, 200, False), (2, 6076, 784, False),
+                                         (1, 1000, 784, True)])
+def test_flash_attention_backward(cuda_lib, B, Nq, Nk, big):
+    """The tcgen05 flash backward of softmax(q k^T / 8) v (MSTr.py:2281-2285) against torch autograd in fp64: ragged query / kv
+    tile edges, the production shape, large scores (|s| up to ~20), gradients of the magnitude a per-pixel loss produces.
+    fp16 operands with fp32 accumulation and a per-call dO scale: relative L2 <= 5e-3.  Bit-reproducible."""
+    from transception_b200 import ops
+    g = torch.Generator().manual_seed(Nq + Nk)
+    q = torch.randn(B, Nq, 64, generator=g) * (2.5 if big else 1.0)
+    kv = torch.randn(B, Nk, 128, generator=g) * (2.5 if big else 1.0)
+    dout = torch.randn(B, Nq, 64, generator=g) * 1e-6
+    qr, kvr = q.double().requires_grad_(), kv.double().requires_grad_()
+    k, v = kvr[..., :64], kvr[..., 64:]
+    want = torch.softmax(qr @ k.transpose(1, 2) * 0.125, dim=-1) @ v
+    want.backward(dout.double())
+    out, lse = ops.flash_attn_train(q.cuda(), kv.cuda(), 0.125)
+    assert (out.cpu().double() - want.detach()).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    ref_lse = torch.logsumexp(qr.detach() @ k.detach().transpose(1, 2) * 0.125, dim=-1) * 1.4426950408889634
+    assert (lse.cpu().double() - ref_lse).abs().max().item() <= 2e-2
+    dq, dkv = ops.flash_attn_bwd(q.cuda(), kv.cuda(), out, lse, dout.cuda(), 0.125)
+    for got, ref, name in ((dq, qr.grad, "dq"), (dkv[..., :64], kvr.grad[..., :64], "dk"), (dkv[..., 64:], kvr.grad[..., 64:], "dv")):
+        err = (got.cpu().double() - ref).norm().item() / ref.norm().item()
+        assert torch.isfinite(got).all() and err <= 5e-3, "%s: relative L2 %.3e" % (name, err)
+    dq2, dkv2 = ops.flash_attn_bwd(q.cuda(), kv.cuda(), out, lse, dout.cuda(), 0.125)
+    assert torch.equal(dq, dq2) and torch.equal(dkv, dkv2), "flash backward is not bit-reproducible"

@@ -160,19 +160,33 @@ def dwconv_tokens(x, H, W, w, b, add_input):
     return DwConvTokensFn.apply(x, H, W, w, b, add_input)
 
 
+FLASH_BWD = True      # bridge attention backward on the tcgen05 flash kernel (False: the GEMM-recompute path with materialised scores)
+
+
 class AttnCoreFn(torch.autograd.Function):
-    """softmax(q k^T * scale) v of M_EfficientSelfAtten (MSTr.py:2281-2285): tcgen05 flash kernel forward, GEMM-recompute backward."""
+    """softmax(q k^T * scale) v of M_EfficientSelfAtten (MSTr.py:2281-2285): tcgen05 flash kernels in both directions (the forward
+    keeps the row log-sum-exp; the backward recomputes the probabilities tile by tile — no score-sized tensor in HBM)."""
 
     @staticmethod
     def forward(ctx, q, kv, scale):
-        ctx.save_for_backward(q, kv)
+        q, kv = q.contiguous(), kv.contiguous()
         ctx.scale = scale
-        return ops.flash_attn(q.contiguous(), kv.contiguous(), scale)
+        ctx.flash = FLASH_BWD
+        if ctx.flash:
+            out, lse = ops.flash_attn_train(q, kv, scale)
+            ctx.save_for_backward(q, kv, out, lse)
+            return out
+        ctx.save_for_backward(q, kv)
+        return ops.flash_attn(q, kv, scale)
 
     @staticmethod
     def backward(ctx, dout):
-        q, kv = ctx.saved_tensors
-        dq, dkv = ops.attn_core_bwd(q, kv, dout, ctx.scale)
+        if ctx.flash:
+            q, kv, out, lse = ctx.saved_tensors
+            dq, dkv = ops.flash_attn_bwd(q, kv, out, lse, dout, ctx.scale)
+        else:
+            q, kv = ctx.saved_tensors
+            dq, dkv = ops.attn_core_bwd(q, kv, dout, ctx.scale)
         return dq, dkv, None
 
 

@@ -1075,6 +1075,21 @@ int tcx_flash_attn_fwd(const float* q, const float* kv, float* out, int B, int N
   return launch_flash_ffma(q, kv, out, B, Nq, Nk, scale, S(stream));
 }
 
+/* training forward: the fp32-io flash kernel + the row log2-sum-exp the flash backward consumes */
+int tcx_flash_attn_train_fwd(const float* q, const float* kv, float* out, float* lse, int B, int Nq, int Nk, float scale, void* ws,
+                             void* stream) {
+  TCX_REQUIRE(q && kv && out && lse && ws, "flash_attn_train_fwd: null pointer");
+  TCX_REQUIRE(flash_tc_enabled(), "flash_attn_train_fwd: needs the tcgen05 flash kernel (flag flash_tc)");
+  return launch_flash_tc(q, kv, out, B, Nq, Nk, scale, ws, S(stream), lse);
+}
+size_t tcx_flash_attn_bwd_workspace_bytes(int B, int Nq, int Nk) { return 4 * (flash_bwd_workspace_floats(B, Nq, Nk) + 64); }
+int tcx_flash_attn_bwd(const float* q, const float* kv, const float* out, const float* lse, const float* dout, float scale, float* dq,
+                       float* dkv, int B, int Nq, int Nk, void* ws, void* stream) {
+  TCX_REQUIRE(q && kv && out && lse && dout && dq && dkv && ws, "flash_attn_bwd: null pointer");
+  if (B == 0 || Nq == 0 || Nk == 0) return 0;
+  return launch_flash_bwd(q, kv, out, lse, dout, scale, dq, dkv, B, Nq, Nk, reinterpret_cast<float*>(ws), S(stream));
+}
+
 int tcx_flash_attn_f16_fwd(const void* q16, const void* kv16, void* out16, int B, int Nq, int Nk, float scale, void* ws,
                            void* stream) {
   TCX_REQUIRE(B >= 0 && Nq >= 0 && Nk >= 1, "flash_attn_f16: bad sizes B=%d Nq=%d Nk=%d", B, Nq, Nk);

@@ -438,11 +438,9 @@ int launch_mb_attention(const MbAttnArgs& a, cudaStream_t st) {
     constexpr int TN = 8;
     dim3 grid(cdiv(N, TN), a.B, a.groups);
     const size_t smem = (size_t)(a.C * Ch + TN * a.C) * sizeof(float);
-    static bool attr_done = false;
-    if (smem > 48 * 1024 && !attr_done) {
+    static PerDeviceOnce once;
+    if (smem > 48 * 1024 && once.first())
       cudaFuncSetAttribute(mb_apply_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      attr_done = true;
-    }
     TCX_REQUIRE(smem <= 100 * 1024, "mb_attn: smem too large");
     mb_apply_kernel<TN><<<grid, 256, smem, st>>>(gs, a.H, a.W, a.C, Ch);
     TCX_TRY(tcx_check_launch("mb_apply"));

@@ -26,7 +26,11 @@ int launch_mb_attention(const MbAttnArgs& a, cudaStream_t st);
 int launch_flash_ffma(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, cudaStream_t st);
 size_t flash_tc_workspace_bytes(int B, int Nk);
 int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
-                    cudaStream_t st);
+                    cudaStream_t st, float* lse = nullptr);
+// flash backward (flash_bwd.cu): lse = the row log2-sum-exp written by launch_flash_tc
+size_t flash_bwd_workspace_floats(int B, int Nq, int Nk);
+int launch_flash_bwd(const float* q, const float* kv, const float* out, const float* lse, const float* dout, float scale, float* dq,
+                     float* dkv, int B, int Nq, int Nk, float* ws, cudaStream_t st);
 int launch_flash_tc16(const void* q16, const void* kv16, void* out16, int B, int Nq, int Nk, float scale, void* ws,
                       cudaStream_t st);
 bool flash_tc_enabled();

@@ -63,6 +63,20 @@ inline cudaError_t tcx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute (dynamic shared memory opt-in) is per DEVICE: one process may drive several GPUs (nn.DataParallel), so
+// the "done once" guards of the launchers are per device.  first() is true the first time it is called on the current device.
+struct PerDeviceOnce {
+  unsigned long long mask = 0;
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+  }
+};
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- activations -----------------------------------------------------------------------

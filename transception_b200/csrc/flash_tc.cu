@@ -87,7 +87,7 @@ __device__ __forceinline__ void load_s_row(uint32_t tS, uint32_t (&s)[FT_BN]) {
 template <bool Q16, bool O16>
 __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_constant__ FlashMaps maps,
                                                                  const void* __restrict__ qv, void* __restrict__ outv,
-                                                                 int B, int Nq, int Nk, float qscale) {
+                                                                 float* __restrict__ lse, int B, int Nq, int Nk, float qscale) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -372,6 +372,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) flash_tc_kernel(const __grid_co
       }
       if (valid) {
         const float inv = 1.f / l;
+        // row log2-sum-exp of the scaled scores (training: the backward kernel recomputes P = 2^(s c - lse) from it)
+        if (lse) lse[(long long)b * Nq + row] = m + log2f(l);
         if (O16) {
           uint4* __restrict__ orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(outv) + ((long long)b * Nq + row) * FT_D);
 #pragma unroll
@@ -447,15 +449,14 @@ size_t flash_tc_workspace_bytes(int B, int Nk) {
   return align_up((size_t)B * Nk * 64 * 2, 1024) + align_up((size_t)B * 64 * Nkp * 2, 1024);
 }
 
-static int flash_tc_launch(const FlashMaps& maps, const void* q, void* out, int B, int Nq, int Nk, float scale, bool f16io,
+static int flash_tc_launch(const FlashMaps& maps, const void* q, void* out, float* lse, int B, int Nq, int Nk, float scale, bool f16io,
                            cudaStream_t st) {
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(flash_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(flash_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     TCX_REQUIRE(e == cudaSuccess, "flash_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    done = true;
   }
   static int sms = 0;
   if (!sms) {
@@ -469,14 +470,14 @@ static int flash_tc_launch(const FlashMaps& maps, const void* q, void* out, int 
   const float qscale = scale * 1.4426950408889634f;
   ProfScope prof("flash_tc", st, 4.0 * B * (double)Nq * Nk * FT_D);   // QK^T + PV FLOPs
   cudaError_t le;
-  if (f16io) le = tcx_launch_pdl(flash_tc_kernel<true, true>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, B, Nq, Nk, qscale);
-  else le = tcx_launch_pdl(flash_tc_kernel<false, false>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, B, Nq, Nk, qscale);
+  if (f16io) le = tcx_launch_pdl(flash_tc_kernel<true, true>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, lse, B, Nq, Nk, qscale);
+  else le = tcx_launch_pdl(flash_tc_kernel<false, false>, dim3(min(npairs, sms)), dim3(FT_THREADS), (size_t)FT_SMEM, st, maps, q, out, lse, B, Nq, Nk, qscale);
   TCX_REQUIRE(le == cudaSuccess, "flash_tc: launch failed: %s", cudaGetErrorString(le));
   return tcx_check_launch("flash_tc");
 }
 
 int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, int Nk, float scale, void* ws,
-                    cudaStream_t st) {
+                    cudaStream_t st, float* lse) {
   TCX_REQUIRE(ws != nullptr && ((uintptr_t)ws & 127) == 0, "flash_tc: workspace must be 128-byte aligned");
   const int Nkp = (Nk + 7) / 8 * 8;
   __half* k16 = reinterpret_cast<__half*>(ws);
@@ -490,7 +491,7 @@ int launch_flash_tc(const float* q, const float* kv, float* out, int B, int Nq, 
   TCX_TRY(tcx_make_operand_map(&maps.k, k16, 2, 64, Nk, 64, B, (long long)Nk * 64, 64, FT_BN));
   TCX_TRY(tcx_make_operand_map(&maps.vt, vt16, 2, Nkp, 64, Nkp, B, (long long)64 * Nkp, 64, 64));
   maps.q = maps.k;   // unused by the fp32-query kernel
-  return flash_tc_launch(maps, q, out, B, Nq, Nk, scale, false, st);
+  return flash_tc_launch(maps, q, out, lse, B, Nq, Nk, scale, false, st);
 }
 
 // fp16 form: q16 [B][Nq][64], kv16 [B][Nk][128] (k | v), out16 [B][Nq][64]; ws holds V^T only
@@ -508,5 +509,5 @@ int launch_flash_tc16(const void* q16, const void* kv16, void* out16, int B, int
   TCX_TRY(tcx_make_operand_map(&maps.k, kv16, 2, 64, Nk, 128, B, (long long)Nk * 128, 64, FT_BN));
   TCX_TRY(tcx_make_operand_map(&maps.vt, vt16, 2, Nkp, 64, Nkp, B, (long long)64 * Nkp, 64, 64));
   TCX_TRY(tcx_make_operand_map(&maps.q, q16, 2, 64, Nq, 64, B, (long long)Nq * 64, 64, FT_BM));
-  return flash_tc_launch(maps, q16, out16, B, Nq, Nk, scale, true, st);
+  return flash_tc_launch(maps, q16, out16, nullptr, B, Nq, Nk, scale, true, st);
 }

@@ -476,10 +476,12 @@ __global__ void __launch_bounds__(MBF_THREADS) mb_fused16_kernel(const Mb16Args 
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* what) {
   static std::mutex mu;
-  static std::unordered_map<const void*, size_t> granted;
+  static std::unordered_map<unsigned long long, size_t> granted;       // per (device, kernel): the attribute is per device
   if (bytes <= 48 * 1024) return 0;
   std::lock_guard<std::mutex> lk(mu);
-  size_t& g = granted[reinterpret_cast<const void*>(kernel)];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& g = granted[(unsigned long long)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kernel)) * 64ull + (unsigned long long)(dev & 63)];
   if (bytes > g) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { tcx_set_error("%s: cannot opt in to %zu bytes of shared memory: %s", what, bytes, cudaGetErrorString(e)); return -1; }

@@ -536,12 +536,11 @@ SmemPlan make_plan(int bn, bool has_res, bool ln) {
 
 template <int BN, bool AB16, bool OUT16, bool LN = false>
 int launch_cfg(const TmaSet& maps, const GemmParams& p, const SmemPlan& sp, cudaStream_t st) {
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, AB16, OUT16, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SMEM_BUDGET);
     TCX_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    done = true;
   }
   TCX_REQUIRE(sp.stages >= 2 && sp.total <= SMEM_BUDGET, "gemm_tc: smem plan does not fit (BN=%d stages=%d)", BN, sp.stages);
   const int ntiles = cdiv(p.M, BM) * cdiv(p.N, BN) * p.groups * p.batch;

@@ -246,11 +246,10 @@ int launch_head_tc(const float* x, const float* w, int B, int H, int W, const fl
     TCX_TRY(mk(&maps.w, w, 1024, 128));
     TCX_TRY(mk(&maps.g, ws, 256, 32));
   }
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM);
     TCX_REQUIRE(e == cudaSuccess, "head_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    done = true;
   }
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);

@@ -365,11 +365,9 @@ int launch_patch_embed_ln(const float* x, long long xs_b, long long xs_c, int B,
   const bool grey = xs_c == 0;           // one plane read three times
   const int cin = grey ? 1 : 3;
   const size_t smem = (size_t)(cin * 49 * 64 + cin * PE_IN * 36) * sizeof(float);
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;
+  if (once.first())
     cudaFuncSetAttribute(patch_embed_ln_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((147 * 64 + 3 * PE_IN * 36) * sizeof(float)));
-    done = true;
-  }
   dim3 grid(cdiv(Wo, PE_T), cdiv(Ho, PE_T), B);
   if (grey) tcx_launch_pdl(patch_embed_ln_kernel<1>, grid, dim3(256), smem, st, x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);
   else tcx_launch_pdl(patch_embed_ln_kernel<3>, grid, dim3(256), smem, st, x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);

@@ -374,11 +374,10 @@ template <int C4>
 int mixtail_launch(const MixTailArgs& a, cudaStream_t st) {
   using K = MtCfg<C4>;
   static_assert(K::SMEM <= 227 * 1024, "mixtail smem budget");
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(mixtail_kernel<C4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
     TCX_REQUIRE(e == cudaSuccess, "mixtail: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    done = true;
   }
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);

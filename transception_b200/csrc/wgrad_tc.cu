@@ -462,12 +462,11 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   TCX_TRY(tcx_make_operand_map(&maps.a, a.A, eb, a.NL, a.Mtok, a.lda, a.batch, a.strideA, boxc, WG_KT, a.fmt == 1, eb == 4));
   TCX_TRY(tcx_make_operand_map(&maps.b, a.B, eb, a.KL, a.Mtok, a.ldb, a.batch, a.strideB, boxc, WG_KT, a.fmt == 1, eb == 4));
   const size_t smem = 1024 + WG_RING_BYTES + WG_ONES_BYTES + WG_BM * 4 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     TCX_REQUIRE(e == cudaSuccess, "wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   const unsigned grid = (unsigned)(tiles * p.S * a.batch);
   ProfScope prof("wgrad_tc", st, (double)a.batch * a.Mtok * (a.NL + a.KL) * eb + (double)a.batch * a.NL * a.KL * 4.0);

@@ -112,6 +112,9 @@ _PROTOS = {
     "tcx_dwconv_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_attn_core_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_attn_core_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tcx_flash_attn_train_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "tcx_flash_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_flash_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_ea_core_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_ea_core_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_ea_core_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -204,13 +207,22 @@ def _ptr16(t):
     return t.data_ptr()
 
 
+def _aligned(t):
+    """The kernels read parameters with 16-byte accesses / TMA.  nn.DataParallel's replicas are views into coalesced broadcast
+    buffers at arbitrary 4-byte offsets: such a tensor is copied to a fresh (256-byte aligned) allocation for the call.  The copy
+    may be dropped as soon as the kernels are enqueued: the caching allocator re-uses the block in stream order."""
+    if t is None or t.data_ptr() % 16 == 0:
+        return t
+    return t.detach().clone()
+
+
 def _ptr(t):
     if t is None:
         return None
     if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
         raise RuntimeError("transception_b200: expected a contiguous fp32 CUDA tensor, got %s %s contiguous=%s on %s"
                            % (tuple(t.shape), t.dtype, t.is_contiguous(), t.device))
-    return t.data_ptr()
+    return _aligned(t).data_ptr()
 
 
 # ---- prepared (fp16) GEMM weights ----------------------------------------------------------------
@@ -320,9 +332,16 @@ def invalidate_prepared(model=None):
             ent.version = -1
 
 
+_KEEP = __import__("collections").deque(maxlen=64)
+
+
 def _table(tensors, mats=()):
     """Host array of device pointers; slots listed in ``mats`` are GEMM weight matrices (prepared on first use)."""
     arr = (ctypes.c_void_p * len(tensors))()
+    aligned = [_aligned(t) for t in tensors]
+    if any(a is not t for a, t in zip(aligned, tensors)):
+        _KEEP.append(aligned)        # re-aligned replicas (and their prepared copies) must outlive the C call that follows
+    tensors = aligned
     for i in mats:
         prepare_weight(tensors[i])
     for i, t in enumerate(tensors):
@@ -667,6 +686,7 @@ def bridge_layer(x, n1w, n1b, ln_eps, channel_att, attn_slots, scale, n2w, n2b, 
     slots = [n1w, n1b] + attn_slots + [n2w, n2b]
     for a in mix_args_list:
         slots.extend(_mix_slots(a)[0])
+    slots = [_aligned(t) for t in slots]
     mats = [18 + 8 * k + j for k in range(4) for j in (0, 6)]
     if channel_att:
         mats += [2, 4, 6, 8]
@@ -686,6 +706,7 @@ def _bridge_layer_slots(n1w, n1b, channel_att, attn_slots, n2w, n2b, mix_args_li
     slots = [n1w, n1b] + attn_slots + [n2w, n2b]
     for a in mix_args_list:
         slots.extend(_mix_slots(a)[0])
+    slots = [_aligned(t) for t in slots]
     mats = [18 + 8 * k + j for k in range(4) for j in (0, 6)]
     if channel_att:
         mats += [2, 4, 6, 8]
@@ -812,6 +833,7 @@ def dual_patch_embed(x_nhwc, pe1, pe2, ln_eps):
     (w1, b1, nw1, nb1, k1, s1, p1, d1), (w2, b2, nw2, nb2, k2, s2, p2, d2) = pe1, pe2
     if s1 != s2 or d1 != d2:
         raise NotImplementedError("the two patch-merging branches must share stride and dilation")
+    w1, w2 = _aligned(w1), _aligned(w2)
     C = w1.shape[0]
     H1, W1 = (H + 2 * p1 - d1 * (k1 - 1) - 1) // s1 + 1, (W + 2 * p1 - d1 * (k1 - 1) - 1) // s1 + 1
     H2, W2 = (H + 2 * p2 - d1 * (k2 - 1) - 1) // s1 + 1, (W + 2 * p2 - d1 * (k2 - 1) - 1) // s1 + 1
@@ -1085,6 +1107,36 @@ def attn_core_bwd(q, kv, dout, scale):
     dq, dkv = torch.empty_like(q), torch.empty_like(kv)
     ws = _ws(lib.tcx_attn_core_bwd_workspace_bytes(B, Nq, Nk), q)
     _chk(lib.tcx_attn_core_bwd(_ptr(q), _ptr(kv), _ptr(dout), scale, _ptr(dq), _ptr(dkv), B, Nq, Nk, _ptr(ws), _stream()))
+    return dq, dkv
+
+
+def flash_attn_train(q, kv, scale):
+    """(out, lse) of softmax(q k^T * scale) v on the tcgen05 flash kernel; lse feeds flash_attn_bwd."""
+    require_cuda(q)
+    lib = load_library()
+    q, kv = q.contiguous(), kv.contiguous()
+    B, Nq, D = q.shape
+    Nk = kv.shape[1]
+    if D != 64 or kv.shape[2] != 128 or kv.shape[0] != B:
+        raise RuntimeError("flash_attn: expected q [B,Nq,64] and kv [B,Nk,128], got %s %s" % (tuple(q.shape), tuple(kv.shape)))
+    out = torch.empty_like(q)
+    lse = torch.empty((B, Nq), dtype=torch.float32, device=q.device)
+    ws = _ws(lib.tcx_flash_attn_workspace_bytes(B, Nk), q)
+    _chk(lib.tcx_flash_attn_train_fwd(_ptr(q), _ptr(kv), _ptr(out), _ptr(lse), B, Nq, Nk, scale, _ptr(ws), _stream()))
+    return out, lse
+
+
+def flash_attn_bwd(q, kv, out, lse, dout, scale):
+    """(dq, dkv) of the bridge attention core on the tcgen05 flash backward kernel."""
+    require_cuda(q)
+    lib = load_library()
+    q, kv, out, dout = q.contiguous(), kv.contiguous(), out.contiguous(), dout.contiguous()
+    B, Nq, _ = q.shape
+    Nk = kv.shape[1]
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    ws = _ws(lib.tcx_flash_attn_bwd_workspace_bytes(B, Nq, Nk), q)
+    _chk(lib.tcx_flash_attn_bwd(_ptr(q), _ptr(kv), _ptr(out), _ptr(lse), _ptr(dout), scale, _ptr(dq), _ptr(dkv), B, Nq, Nk, _ptr(ws),
+                                _stream()))
     return dq, dkv
 
 
