@@ -50,8 +50,11 @@ def test_dataparallel_train_step_equals_sequential_replicas(cuda_lib):
     assert abs(loss_a.item() - loss_b.item()) <= 1e-6 * abs(loss_b.item())
     n = 0
     for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-        assert (p.grad is None) == (q.grad is None), k
-        if p.grad is not None:
+        if q.grad is None:
+            # a dead parameter: nn.DataParallel's Broadcast node hands back a zero gradient where a single module leaves None
+            assert p.grad is None or not p.grad.any(), k
+        else:
+            assert p.grad is not None, k
             den = q.grad.norm().item()
             assert (p.grad - q.grad).norm().item() <= 1e-5 * den + 1e-12, k
             n += 1

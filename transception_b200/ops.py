@@ -207,13 +207,20 @@ def _ptr16(t):
     return t.data_ptr()
 
 
+_KEEP = __import__("collections").deque(maxlen=512)
+
+
 def _aligned(t):
     """The kernels read parameters with 16-byte accesses / TMA.  nn.DataParallel's replicas are views into coalesced broadcast
-    buffers at arbitrary 4-byte offsets: such a tensor is copied to a fresh (256-byte aligned) allocation for the call.  The copy
-    may be dropped as soon as the kernels are enqueued: the caching allocator re-uses the block in stream order."""
+    buffers at arbitrary 4-byte offsets: such a tensor is copied to a fresh (256-byte aligned) allocation for the call.  The
+    copy has to stay alive until the kernels that read it are ENQUEUED (afterwards the caching allocator re-uses the block in
+    stream order; the library joins its auxiliary streams before a call returns) — a clone dropped before the launch would hand
+    its block to the next clone.  _KEEP holds the last few hundred of them, far more than one call takes."""
     if t is None or t.data_ptr() % 16 == 0:
         return t
-    return t.detach().clone()
+    c = t.detach().clone()
+    _KEEP.append(c)
+    return c
 
 
 def _ptr(t):
@@ -332,16 +339,10 @@ def invalidate_prepared(model=None):
             ent.version = -1
 
 
-_KEEP = __import__("collections").deque(maxlen=64)
-
-
 def _table(tensors, mats=()):
     """Host array of device pointers; slots listed in ``mats`` are GEMM weight matrices (prepared on first use)."""
     arr = (ctypes.c_void_p * len(tensors))()
-    aligned = [_aligned(t) for t in tensors]
-    if any(a is not t for a, t in zip(aligned, tensors)):
-        _KEEP.append(aligned)        # re-aligned replicas (and their prepared copies) must outlive the C call that follows
-    tensors = aligned
+    tensors = [_aligned(t) for t in tensors]       # re-aligned replicas (and their prepared copies) live on in _KEEP
     for i in mats:
         prepare_weight(tensors[i])
     for i, t in enumerate(tensors):
