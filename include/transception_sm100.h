@@ -382,6 +382,22 @@ int tcx_coord_pool_bwd(const float* dy, float* dx, int B, int H, int W, int C, v
 int tcx_coord_gate_fwd(const float* x, const float* z, float* out, int B, int H, int W, int C, void* stream);
 int tcx_coord_gate_bwd(const float* x, const float* z, const float* dout, float* dx, float* dz, int B, int H, int W, int C, void* stream);
 
+/* Training row of the bridge (MSTr.py:2373-2409): the token buffer [B][Ntok][64] <-> its four dense per-scale slabs [B][n_k][64]
+ * (n_k = (S/2^k)^2 * {1,2,5,8}) in ONE launch each way — the `tx[:, a:b].reshape(...)` slices and `torch.cat` of :2394-2403 and
+ * their gradients (each is the other's adjoint).  tcx_bridge_merge_fwd adds `residual` [B][Ntok][64] when it is not NULL
+ * (`tx1 + cat(...)`, :2405). */
+int tcx_bridge_split_fwd(const float* tokens, void* const* slabs, int B, int S, void* stream);
+int tcx_bridge_merge_fwd(const void* const* slabs, const float* residual, float* tokens, int B, int S, void* stream);
+/* Scale_reduce (MSTr.py:2225-2247) WITHOUT its LayerNorm as one forward / one backward call: packed [B][Nred][64]; `saved`
+ * (tcx_scale_reduce_saved_bytes) keeps the three im2row matrices for the weight gradients.  p = {sr0_w,sr0_b,sr1_w,sr1_b,sr2_w,sr2_b};
+ * backward writes EVERY row of dx [B][Ntok][64] and dp = the six parameter gradients in the order of p. */
+size_t tcx_scale_reduce_saved_bytes(int B, int S);
+size_t tcx_scale_reduce_train_workspace_bytes(int B, int S);
+int tcx_scale_reduce_train_fwd(const float* x, const void* const* p, float* packed, int B, int S, void* saved, void* ws, void* stream);
+size_t tcx_scale_reduce_bwd_workspace_bytes(int B, int S);
+int tcx_scale_reduce_bwd(const float* dpacked, const void* const* p, const void* saved, float* dx, void* const* dp, int B, int S,
+                         void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

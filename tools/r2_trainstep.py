@@ -9,6 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transception_b200 import MSTransception, mstr, ops  # noqa: E402
 from transception_b200.losses import CeDiceLoss  # noqa: E402
+from transception_b200.optim import FusedSGD  # noqa: E402
 from transception_b200.runtime import TrainStepGraph  # noqa: E402
 
 
@@ -19,7 +20,7 @@ def run(cfg):
         ops.set_flag(k, int(v))
     torch.manual_seed(1234)
     net = MSTransception(num_classes=9).cuda().train()
-    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt = FusedSGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(16, 1, 224, 224, generator=g) * 2 - 1).cuda()
     y = torch.randint(0, 9, (16, 224, 224), generator=g).cuda()

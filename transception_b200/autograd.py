@@ -47,18 +47,79 @@ class LayerNormResFn(torch.autograd.Function):
 
 
 class LinearFn(torch.autograd.Function):
+    """y = x w^T + b (+ residual, added in the GEMM epilogue: the skip connection that the projection closes)."""
+
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, residual=None):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        return ops.linear(x, w, b)
+        ctx.has_res = residual is not None
+        return ops.linear(x, w, b, residual=residual.contiguous() if residual is not None else None)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dx, dw, db = ops.linear_bwd(x, w, dy, need_dx=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[1],
                                     need_db=ctx.has_bias and ctx.needs_input_grad[2])
-        return dx, dw, db
+        return dx, dw, db, (dy if ctx.has_res else None)
+
+
+class BridgeSplitFn(torch.autograd.Function):
+    """Token buffer [B, Ntok, 64] -> the four dense per-scale slabs (MSTr.py:2394-2402 slices, :2432-2435): one launch; the
+    gradient is the merge of the four slab gradients (one launch, every row written: no zero fill, no accumulation)."""
+
+    @staticmethod
+    def forward(ctx, tokens):
+        return tuple(ops.bridge_split(tokens))
+
+    @staticmethod
+    def backward(ctx, d0, d1, d2, d3):
+        return ops.bridge_merge([d0, d1, d2, d3])
+
+
+class BridgeMergeFn(torch.autograd.Function):
+    """cat of the four slabs along the token axis (+ residual) (MSTr.py:2380-2386, :2403-2405) and its adjoint."""
+
+    @staticmethod
+    def forward(ctx, m0, m1, m2, m3, residual=None):
+        ctx.shapes = [m.shape for m in (m0, m1, m2, m3)]
+        ctx.has_res = residual is not None
+        return ops.bridge_merge([m0, m1, m2, m3], residual)
+
+    @staticmethod
+    def backward(ctx, dt):
+        ds = ops.bridge_split(dt)
+        return tuple(d.view(sh) for d, sh in zip(ds, ctx.shapes)) + ((dt if ctx.has_res else None),)
+
+
+class ScaleReducePackFn(torch.autograd.Function):
+    """Scale_reduce up to (not including) its LayerNorm (MSTr.py:2225-2247): three strided convs as im2row + GEMM, channel-group
+    packing, raw stage-4 rows copied through.  One node: the four slab slices of x do not exist for autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1, w2, b2):
+        packed, saved = ops.scale_reduce_pack_train(x, [w0, b0, w1, b1, w2, b2])
+        ctx.save_for_backward(saved, w0, b0, w1, b1, w2, b2)
+        ctx.ntok = x.shape[1]
+        return packed
+
+    @staticmethod
+    def backward(ctx, dpacked):
+        saved, *params = ctx.saved_tensors
+        dx, g = ops.scale_reduce_pack_bwd(dpacked, saved, params, ctx.ntok)
+        return (dx,) + tuple(g)
+
+
+def bridge_split(tokens):
+    return BridgeSplitFn.apply(tokens)
+
+
+def bridge_merge(slabs, residual=None):
+    return BridgeMergeFn.apply(slabs[0], slabs[1], slabs[2], slabs[3], residual)
+
+
+def scale_reduce_pack(x, w0, b0, w1, b1, w2, b2):
+    return ScaleReducePackFn.apply(x, w0, b0, w1, b1, w2, b2)
 
 
 class MixFFNSkipFn(torch.autograd.Function):
@@ -301,8 +362,8 @@ def layernorm_res(x, w, b, eps):
     return LayerNormResFn.apply(x, w, b, eps)
 
 
-def linear(x, w, b=None):
-    return LinearFn.apply(x, w, b)
+def linear(x, w, b=None, residual=None):
+    return LinearFn.apply(x, w, b, residual)
 
 
 def mixffn_skip(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):

@@ -69,6 +69,7 @@ static int g_flag_ea_tc = 1;     // efficient-attention context on the tensor co
 static int g_flag_wgrad_tc = 1;  // Linear backward with operands read in place: MN-major wgrad kernel + MN-major-W dgrad (0 = round-1 packT path)
 static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
+int g_tcx_smem_kb = 0;
 int g_tcx_max_ctas = 0;          // > 0: cap on the grid of the persistent tcgen05 kernels (lets kernels of parallel graph branches co-run)
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
 bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
@@ -578,6 +579,7 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
   else if (!strcmp(name, "wgrad_tc")) f = &g_flag_wgrad_tc;
   else if (!strcmp(name, "max_ctas")) f = &g_tcx_max_ctas;
+  else if (!strcmp(name, "smem_kb")) f = &g_tcx_smem_kb;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
   *f = value;
@@ -2311,6 +2313,140 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
   TCX_TRY(launch_bwd_dwconv_wgrad(du, s.h16, B, H, W, C4, G(2), G(3), part, st));
   // fc1: xn16 [M][C] -> h [M][C4]
   return run_linear_bwd(s.xn16, 1, F(p[0]), dh, dxn, G(0), G(1), M, C4, C, lin, st);
+}
+
+// ---- training row of the bridge: slab split / merge and Scale_reduce as single nodes (no ATen slicing, zero fills or accumulation
+// adds around them) ----
+int tcx_bridge_split_fwd(const float* tokens, void* const* slabs, int B, int S0, void* stream) {
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  TCX_REQUIRE(tokens && slabs, "bridge_split: null pointer");
+  UngroupArgs a{};
+  a.src = tokens;
+  for (int i = 0; i < 4; i++) { a.dst[i] = reinterpret_cast<float*>(slabs[i]); TCX_REQUIRE(a.dst[i], "bridge_split: slab %d is null", i); }
+  for (int i = 0; i < 5; i++) a.tok_off[i] = g.off[i];
+  a.ntok = g.ntok; a.B = B;
+  return launch_ungroup(a, S(stream));
+}
+// tokens = regroup(slabs) (+ residual): BridgLayer_4's `tx1 + cat(...)` (MSTr.py:2403-2405) / the token buffer of :2380-2386
+int tcx_bridge_merge_fwd(const void* const* slabs, const float* residual, float* tokens, int B, int S0, void* stream) {
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  TCX_REQUIRE(tokens && slabs, "bridge_merge: null pointer");
+  RegroupArgs a{};
+  for (int i = 0; i < 4; i++) { a.src[i] = F(slabs[i]); TCX_REQUIRE(a.src[i], "bridge_merge: slab %d is null", i); }
+  for (int i = 0; i < 5; i++) a.tok_off[i] = g.off[i];
+  a.dst = tokens; a.ntok = g.ntok; a.B = B; a.res = residual;
+  return launch_regroup(a, S(stream));
+}
+
+namespace {
+const int kSrRatio[3] = {8, 4, 2};
+struct SrSaved { float* A[3]; size_t floats; };
+SrSaved sr_saved(void* base, int B, const BridgeGeom& g) {
+  Carver c(base);
+  SrSaved s;
+  for (int k = 0; k < 3; k++) s.A[k] = c.take((size_t)B * g.pp * g.ch[k] * kSrRatio[k] * kSrRatio[k]);
+  s.floats = c.off + 64;
+  return s;
+}
+}  // namespace
+
+size_t tcx_scale_reduce_saved_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  return 4 * sr_saved(nullptr, B, g).floats;
+}
+size_t tcx_scale_reduce_train_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  size_t n = 64;
+  for (int k = 0; k < 3; k++) n += rnd((size_t)B * g.pp * g.ch[k]);
+  return 4 * n;
+}
+// Scale_reduce without its LayerNorm (MSTr.py:2225-2247): packed [B][nred][64]; the im2row matrices stay in `saved` for the
+// weight gradients.  p = {sr0_w, sr0_b, sr1_w, sr1_b, sr2_w, sr2_b}
+int tcx_scale_reduce_train_fwd(const float* x, const void* const* p, float* packed, int B, int S0, void* saved, void* ws, void* stream) {
+  TCX_REQUIRE(x && p && packed && saved && ws, "scale_reduce_train_fwd: null pointer");
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  cudaStream_t st = S(stream);
+  const SrSaved sv = sr_saved(saved, B, g);
+  Carver c(ws);
+  SrPackArgs a{};
+  const long long xs_b = (long long)g.ntok * 64;
+  AuxStreams* aux = aux_streams(st);
+  if (aux) TCX_TRY(fork_streams(aux, st, 2));
+  for (int k = 0; k < 3; k++) {          // three independent im2row -> GEMM chains
+    const int r = kSrRatio[k], Cin = g.ch[k];
+    const int K = Cin * r * r, M = B * g.pp;
+    cudaStream_t sk = (aux && k > 0) ? aux->s[k - 1] : st;
+    float* conv = c.take((size_t)M * Cin);
+    TCX_TRY(launch_sr_im2row(x + (long long)g.off[k] * 64, xs_b, g.hw[k], Cin, r, B, sv.A[k], sk));
+    GemmParams gp = gemm1(sv.A[k], F(p[2 * k]), conv, M, Cin, K);
+    gp.g[0].epi.bias = F(p[2 * k + 1]);
+    TCX_TRY(launch_gemm(gp, sk));
+    a.conv[k] = conv; a.gmul[k] = Cin / 64; a.pp[k] = g.pp;
+  }
+  if (aux)
+    for (int k = 0; k < 2; k++) TCX_TRY(join_stream(aux, k, st));
+  a.x = x; a.xs_b = xs_b; a.raw_tok0 = g.off[3];
+  for (int i = 0; i < 4; i++) a.red_off[i] = g.red_off[i];
+  a.nred = g.nred; a.B = B; a.lnw = nullptr; a.lnb = nullptr; a.eps = 0.f; a.out = packed;
+  return launch_sr_pack_ln(a, st);
+}
+
+size_t tcx_scale_reduce_bwd_workspace_bytes(int B, int S0) {
+  BridgeGeom g;
+  if (!bridge_geom(S0, g)) return 0;
+  size_t n = 64;
+  for (int k = 0; k < 3; k++) {
+    const long long M = (long long)B * g.pp;
+    const int Cin = g.ch[k], K = Cin * kSrRatio[k] * kSrRatio[k];
+    n += rnd((size_t)M * Cin) + rnd((size_t)M * K) + rnd(linear_bwd_ws_floats(M, Cin, K));
+  }
+  return 4 * n;
+}
+// dpacked [B][nred][64] -> dx [B][ntok][64] (EVERY row written: three conv slabs + the raw stage-4 rows) and dp = {dsr0_w, dsr0_b,
+// dsr1_w, dsr1_b, dsr2_w, dsr2_b}
+int tcx_scale_reduce_bwd(const float* dpacked, const void* const* p, const void* saved, float* dx, void* const* dp, int B, int S0,
+                         void* ws, void* stream) {
+  TCX_REQUIRE(dpacked && p && saved && dx && dp && ws, "scale_reduce_bwd: null pointer");
+  for (int i = 0; i < 6; i++) TCX_REQUIRE(dp[i] != nullptr, "scale_reduce_bwd: gradient slot %d is null", i);
+  BridgeGeom g;
+  TCX_REQUIRE(bridge_geom(S0, g), "bridge: stage-1 side %d must be a positive multiple of 8", S0);
+  cudaStream_t st = S(stream);
+  const SrSaved sv = sr_saved(const_cast<void*>(saved), B, g);
+  Carver c(ws);
+  const long long xs_b = (long long)g.ntok * 64;
+  float* dconv[3]; float* dA[3]; float* lin[3];
+  SrUnpackArgs u{};
+  for (int k = 0; k < 3; k++) {
+    const long long M = (long long)B * g.pp;
+    const int Cin = g.ch[k], K = Cin * kSrRatio[k] * kSrRatio[k];
+    dconv[k] = c.take((size_t)M * Cin); dA[k] = c.take((size_t)M * K); lin[k] = c.take(linear_bwd_ws_floats(M, Cin, K));
+    u.dconv[k] = dconv[k]; u.gmul[k] = Cin / 64; u.pp[k] = g.pp;
+  }
+  u.dred = dpacked; u.dx = dx; u.xs_b = xs_b; u.raw_tok0 = g.off[3];
+  for (int i = 0; i < 4; i++) u.red_off[i] = g.red_off[i];
+  u.nred = g.nred; u.B = B;
+  TCX_TRY(launch_sr_unpack(u, st));
+  // aux stream 0 of `st` belongs to the weight-gradient launch inside run_linear_bwd(st): the side chains take 1 and 2
+  AuxStreams* aux = aux_streams(st);
+  if (aux) {
+    TCX_REQUIRE(cudaEventRecord(aux->fork, st) == cudaSuccess && cudaStreamWaitEvent(aux->s[1], aux->fork, 0) == cudaSuccess &&
+                cudaStreamWaitEvent(aux->s[2], aux->fork, 0) == cudaSuccess, "scale_reduce_bwd: fork failed");
+  }
+  for (int k = 0; k < 3; k++) {
+    const long long M = (long long)B * g.pp;
+    const int r = kSrRatio[k], Cin = g.ch[k], K = Cin * r * r;
+    cudaStream_t sk = (aux && k > 0) ? aux->s[k] : st;
+    TCX_TRY(run_linear_bwd(sv.A[k], 0, F(p[2 * k]), dconv[k], dA[k], reinterpret_cast<float*>(dp[2 * k]),
+                           reinterpret_cast<float*>(dp[2 * k + 1]), M, Cin, K, lin[k], sk));
+    TCX_TRY(launch_sr_row2im(dA[k], xs_b, g.hw[k], Cin, r, B, dx + (long long)g.off[k] * 64, sk));
+  }
+  if (aux) { TCX_TRY(join_stream(aux, 1, st)); TCX_TRY(join_stream(aux, 2, st)); }
+  return 0;
 }
 
 }  // extern "C"

@@ -189,6 +189,84 @@ __global__ void __launch_bounds__(RC * RL) dwk3_wgrad_kernel(const float* __rest
     __syncthreads();
   }
 }
+
+// ---- crpe filter gradients, row-sweep form.  The kernel above gives every thread all K*K taps of its channel and a handful of
+// pixels (50 accumulators, 49 loads per pixel, a 50-round block fold, and a partial buffer of M/16 * 50 * C floats: 128 us on the
+// 28x28 maps).  Here a thread owns ONE tap row ky at a time and sweeps whole image rows with a K-wide register window of x sliding
+// along the row: 2 loads and K FMAs per pixel, K accumulators; (32 channels x 8 row lanes) per block, one block per 8 image rows,
+// so the partial buffer is B*H/8 * 50 * C floats.  The association order is fixed (lane order, then block order in the fold).
+constexpr int WC = 32, WL = 8;
+template <int K>
+__device__ __forceinline__ void dwk_wgrad_sweep(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx, int H, int W,
+                                                int c, int ky, int row0, int row1, float (&acc)[7], float& bsum) {
+  for (int row = row0 + (int)threadIdx.y; row < row1; row += WL) {
+    const int b = row / H, py = row - b * H;
+    const int yy = py + ky - K / 2;
+    if (yy < 0 || yy >= H) continue;
+    const float* grow = g + (size_t)row * W * ldg + c;
+    const float* xrow = x + (size_t)(b * H + yy) * W * ldx + c;
+    float win[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const int xx = j - K / 2;
+      win[j] = (xx >= 0 && xx < W) ? xrow[(size_t)xx * ldx] : 0.f;
+    }
+#pragma unroll 4
+    for (int px = 0; px < W; px++) {
+      const float gv = grow[(size_t)px * ldg];
+      const int xn = px + 1 + K / 2;
+      const float nx = xn < W ? xrow[(size_t)xn * ldx] : 0.f;
+      if (ky == K / 2) bsum += gv;
+#pragma unroll
+      for (int j = 0; j < K; j++) acc[j] = fmaf(gv, win[j], acc[j]);
+#pragma unroll
+      for (int j = 0; j + 1 < K; j++) win[j] = win[j + 1];
+      win[K - 1] = nx;
+    }
+  }
+}
+// partials [blk][50][C] in the layout of the kernel above (tap ky*K + kx of the channel's own window, slot 49 = bias sum); only
+// the slots of the channel's window are written (the fold reads only those)
+__global__ void __launch_bounds__(WC * WL) dwk3_wgrad_sweep_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ x,
+                                                                   int ldx, int B, int H, int W, int C, int c1, int c2, int rows,
+                                                                   float* __restrict__ part) {
+  __shared__ float sm[WL][8][WC];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.y * WC + tx;
+  const int K = c < c1 ? 3 : (c < c2 ? 5 : 7);
+  const int nrow = B * H;
+  const int row0 = blockIdx.x * rows;
+  const int row1 = row0 + rows < nrow ? row0 + rows : nrow;
+  float bsum = 0.f;
+  for (int ky = 0; ky < 7; ky++) {
+    float acc[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) acc[j] = 0.f;
+    const bool live = c < C && ky < K;
+    if (live) {
+      if (K == 3) dwk_wgrad_sweep<3>(g, ldg, x, ldx, H, W, c, ky, row0, row1, acc, bsum);
+      else if (K == 5) dwk_wgrad_sweep<5>(g, ldg, x, ldx, H, W, c, ky, row0, row1, acc, bsum);
+      else dwk_wgrad_sweep<7>(g, ldg, x, ldx, H, W, c, ky, row0, row1, acc, bsum);
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) sm[ty][j][tx] = acc[j];
+    if (ky == 6) sm[ty][7][tx] = bsum;
+    __syncthreads();
+    if (ty < 7 && live && ty < K) {          // lane ty folds tap kx = ty of this tap row
+      float s = sm[0][ty][tx];
+#pragma unroll
+      for (int l = 1; l < WL; l++) s += sm[l][ty][tx];
+      part[((size_t)blockIdx.x * 50 + ky * K + ty) * C + c] = s;
+    }
+    if (ky == 6 && ty == 7 && c < C) {
+      float s = sm[0][7][tx];
+#pragma unroll
+      for (int l = 1; l < WL; l++) s += sm[l][7][tx];
+      part[((size_t)blockIdx.x * 50 + 49) * C + c] = s;
+    }
+    __syncthreads();
+  }
+}
 struct Crpe3Out {
   float* dw[3];
   float* db[3];
@@ -197,12 +275,12 @@ struct Crpe3Out {
 __global__ void __launch_bounds__(256) dwk3_fold_kernel(const float* __restrict__ part, int nblk, int C, Crpe3Out o) {
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int n = 50 * C;
-  const float s = bwd_fold_sum(part, nblk, n, i, i < n);
-  if (threadIdx.y != 0 || i >= n) return;
   const int t = i / C, c = i - t * C;
   const int j = c < o.c1 ? 0 : (c < o.c2 ? 1 : 2);
   const int cc = c - (j == 0 ? 0 : (j == 1 ? o.c1 : o.c2));
   const int KK = j == 0 ? 9 : (j == 1 ? 25 : 49);
+  const float s = bwd_fold_sum(part, nblk, n, i, i < n && (t == 49 || t < KK));     // slots outside the channel's window are never written
+  if (threadIdx.y != 0 || i >= n) return;
   if (t == 49) { if (o.db[j]) o.db[j][cc] = s; }
   else if (t < KK) o.dw[j][(size_t)cc * KK + t] = s;
 }
@@ -350,9 +428,12 @@ int launch_bwd_dwk3_wgrad(const float* g, int ldg, const float* x, int ldx, int 
                           float* const* db, float* part, cudaStream_t st) {
   const long long M = (long long)B * H * W;
   if (M == 0 || C == 0) return 0;
-  const int nblk = bwd_red_blocks(M);
-  const int rows = (int)((M + nblk - 1) / nblk + RL - 1) / RL * RL;
-  dwk3_wgrad_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(g, ldg, x, ldx, B, H, W, C, c1, c2, rows, part);
+  // image rows per block: 8 (one per lane), more only if that would exceed the partial buffer sized by bwd_dwk3_wgrad_part_floats
+  const int nrow = B * H, cap = bwd_red_blocks(M);
+  int rows = WL;
+  while (cdiv(nrow, rows) > cap) rows += WL;
+  const int nblk = cdiv(nrow, rows);
+  dwk3_wgrad_sweep_kernel<<<dim3(nblk, cdiv(C, WC)), dim3(WC, WL), 0, st>>>(g, ldg, x, ldx, B, H, W, C, c1, c2, rows, part);
   TCX_TRY(tcx_check_launch("bwd_dwk3_wgrad"));
   Crpe3Out o;
   for (int j = 0; j < 3; j++) { o.dw[j] = dw[j]; o.db[j] = db[j]; }

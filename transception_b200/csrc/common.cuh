@@ -35,6 +35,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 extern int g_tcx_pdl;   // flag "pdl" (default 1)
+extern int g_tcx_smem_kb;    // flag "smem_kb" (default 0 = whole SM): shared-memory budget of the tcgen05 GEMM kernels
 extern int g_tcx_max_ctas;   // flag "max_ctas" (default 0 = one CTA per SM)
 template <typename... KArgs, typename... Args>
 inline cudaError_t tcx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -521,7 +521,10 @@ SmemPlan make_plan(int bn, bool has_res, bool ln) {
   const int stage = STAGE_A + bn * KB_BYTES;
   const int sub = EPI_WARPS * 2 * SUB_BYTES;
   const int fixed = sub + (has_res ? sub : 0) + (ln ? EPI_WARPS * SUB_BYTES : 0) + EPI_WARPS * COL_BYTES + 512;
-  int stages = (SMEM_BUDGET - 1024 - fixed) / stage;
+  int budget = SMEM_BUDGET;
+  if (g_tcx_smem_kb > 0 && bn <= 128 && g_tcx_smem_kb * 1024 < budget) budget = g_tcx_smem_kb * 1024;   // BN = 256 owns all of TMEM anyway
+  int stages = (budget - 1024 - fixed) / stage;
+  if (stages < 2) stages = 2;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   sp.stages = stages;
   sp.off_b = stages * STAGE_A;

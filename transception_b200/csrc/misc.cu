@@ -112,7 +112,26 @@ __global__ void __launch_bounds__(256) regroup_kernel(RegroupArgs a) {
   for (int i = 1; i < 4; i++) if (r >= (long long)a.tok_off[i] * 16) k = i;
   const long long local = r - (long long)a.tok_off[k] * 16;
   const long long n_k = (long long)(a.tok_off[k + 1] - a.tok_off[k]) * 16;
-  reinterpret_cast<float4*>(a.dst)[idx] = reinterpret_cast<const float4*>(a.src[k])[(long long)b * n_k + local];
+  float4 v = reinterpret_cast<const float4*>(a.src[k])[(long long)b * n_k + local];
+  if (a.res) {
+    const float4 r4 = reinterpret_cast<const float4*>(a.res)[idx];
+    v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+  }
+  reinterpret_cast<float4*>(a.dst)[idx] = v;
+}
+
+__global__ void __launch_bounds__(256) ungroup_kernel(UngroupArgs a) {
+  const long long per_img = (long long)a.ntok * 16;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_img * a.B) return;
+  const int b = (int)(idx / per_img);
+  const long long r = idx % per_img;
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < 4; i++) if (r >= (long long)a.tok_off[i] * 16) k = i;
+  const long long local = r - (long long)a.tok_off[k] * 16;
+  const long long n_k = (long long)(a.tok_off[k + 1] - a.tok_off[k]) * 16;
+  reinterpret_cast<float4*>(a.dst[k])[(long long)b * n_k + local] = reinterpret_cast<const float4*>(a.src)[idx];
 }
 
 // =====================================================================================
@@ -139,6 +158,25 @@ __global__ void __launch_bounds__(256) sr_im2row_kernel(const float* __restrict_
   A[((long long)(b * P + i) * P + j) * K + ((long long)cin * r + ky) * r + kx] = v;
 }
 
+// the same permutation backwards: dx[b][(i*r+ky)*HW + j*r+kx][cin] = dA[(b,i,j)][(cin,ky,kx)]  (coalesced on the dx side)
+__global__ void __launch_bounds__(256) sr_row2im_kernel(const float* __restrict__ dA, long long xs_b, int HW, int Cin, int r,
+                                                        int B, float* __restrict__ dx) {
+  const int P = HW / r;
+  const long long K = (long long)Cin * r * r;
+  const long long total = (long long)B * P * P * K;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cin = (int)(idx % Cin);
+  long long t = idx / Cin;
+  const int kx = (int)(t % r); t /= r;
+  const int ky = (int)(t % r); t /= r;
+  const int j = (int)(t % P); t /= P;
+  const int i = (int)(t % P);
+  const int b = (int)(t / P);
+  dx[(long long)b * xs_b + ((long long)(i * r + ky) * HW + (j * r + kx)) * Cin + cin] =
+      dA[((long long)(b * P + i) * P + j) * K + ((long long)cin * r + ky) * r + kx];
+}
+
 // pack conv outputs + raw stage-4 tokens into the reduced sequence and LayerNorm(64) it.
 // reduced token t of image b: scale k, t_local = (c % g)*49 + s, feature f = c // g  
 __global__ void __launch_bounds__(256) sr_pack_ln_kernel(SrPackArgs a) {
@@ -160,12 +198,39 @@ __global__ void __launch_bounds__(256) sr_pack_ln_kernel(SrPackArgs a) {
     const float* src = a.conv[k] + ((long long)b * pp + s) * (64 * g) + cm;
     v0 = src[lane * g]; v1 = src[(lane + 32) * g];
   }
+  float* dst = a.out + row * 64;
+  if (!a.lnw) {            // training row: the LayerNorm is its own autograd node
+    dst[lane] = v0; dst[lane + 32] = v1;
+    return;
+  }
   const float mean = warp_sum(v0 + v1) * (1.f / 64.f);
   const float d0 = v0 - mean, d1 = v1 - mean;
   const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.f / 64.f) + a.eps);
-  float* dst = a.out + row * 64;
   dst[lane] = d0 * rstd * a.lnw[lane] + a.lnb[lane];
   dst[lane + 32] = d1 * rstd * a.lnw[lane + 32] + a.lnb[lane + 32];
+}
+
+// gradient of the packing above (no LayerNorm): one warp per reduced row scatters it to its conv output / raw token row
+__global__ void __launch_bounds__(256) sr_unpack_kernel(SrUnpackArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)a.B * a.nred) return;
+  const int b = (int)(row / a.nred), t = (int)(row % a.nred);
+  const float* src = a.dred + row * 64;
+  const float v0 = src[lane], v1 = src[lane + 32];
+  if (t >= a.red_off[3]) {
+    float* dst = a.dx + (long long)b * a.xs_b + (long long)(a.raw_tok0 + t - a.red_off[3]) * 64;
+    dst[lane] = v0; dst[lane + 32] = v1;
+  } else {
+    int k = 0;
+    if (t >= a.red_off[1]) k = 1;
+    if (t >= a.red_off[2]) k = 2;
+    const int g = a.gmul[k], pp = a.pp[k];
+    const int tl = t - a.red_off[k];
+    const int cm = tl / pp, s = tl % pp;
+    float* dst = a.dconv[k] + ((long long)b * pp + s) * (64 * g) + cm;
+    dst[lane * g] = v0; dst[(lane + 32) * g] = v1;
+  }
 }
 
 // ---- fp16 forms -------------------------------------------------------------------------------------------------
@@ -378,6 +443,25 @@ int launch_regroup(const RegroupArgs& a, cudaStream_t st) {
   const long long total = (long long)a.B * a.ntok * 16;
   regroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
   return tcx_check_launch("bridge_regroup");
+}
+
+int launch_ungroup(const UngroupArgs& a, cudaStream_t st) {
+  const long long total = (long long)a.B * a.ntok * 16;
+  ungroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  return tcx_check_launch("bridge_ungroup");
+}
+
+int launch_sr_unpack(const SrUnpackArgs& a, cudaStream_t st) {
+  const long long rows = (long long)a.B * a.nred;
+  sr_unpack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
+  return tcx_check_launch("sr_unpack");
+}
+
+int launch_sr_row2im(const float* dA, long long xs_b, int HW, int Cin, int r, int B, float* dx, cudaStream_t st) {
+  const int P = HW / r;
+  const long long total = (long long)B * P * P * Cin * r * r;
+  sr_row2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dA, xs_b, HW, Cin, r, B, dx);
+  return tcx_check_launch("sr_row2im");
 }
 
 int launch_sr_im2row(const float* x, long long xs_b, int HW, int Cin, int r, int B, float* A, cudaStream_t st) {

@@ -9,8 +9,18 @@ struct RegroupArgs {
   float* dst;            // [B][ntok][64]
   int tok_off[5];        // token offsets of the four slabs (+ total)
   int ntok, B;
+  const float* res;      // optional [B][ntok][64] added to the regrouped tokens (the skip connection of BridgLayer_4, MSTr.py:2405)
 };
 int launch_regroup(const RegroupArgs& a, cudaStream_t st);
+// the inverse: token buffer -> four dense per-scale slabs [B][n_k][64] (training row: the Mix-FFN inputs of a bridge layer, the
+// maps handed to the decoder, and the gradient of launch_regroup)
+struct UngroupArgs {
+  const float* src;      // [B][ntok][64]
+  float* dst[4];
+  int tok_off[5];
+  int ntok, B;
+};
+int launch_ungroup(const UngroupArgs& a, cudaStream_t st);
 
 int launch_sr_im2row(const float* x, long long xs_b, int HW, int Cin, int r, int B, float* A, cudaStream_t st);
 
@@ -27,7 +37,21 @@ struct SrPackArgs {
   float eps;
   float* out;            // [B][nred][64]
 };
-int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st);
+int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st);      // lnw == null: pack only (the training row normalises separately)
+// gradient of the packing: d(reduced sequence) -> d(conv outputs) and the raw stage-4 rows of d(token buffer)
+struct SrUnpackArgs {
+  const float* dred;     // [B][nred][64]
+  float* dconv[3];       // [B*pp][64*g]
+  float* dx;             // token-buffer gradient: rows raw_tok0.. of every image are written
+  long long xs_b;
+  int raw_tok0;
+  int red_off[4];
+  int gmul[3], pp[3];
+  int nred, B;
+};
+int launch_sr_unpack(const SrUnpackArgs& a, cudaStream_t st);
+// gradient of launch_sr_im2row (non-overlapping patches: a permutation): dA [B*P*P][Cin*r*r] -> the slab of d(token buffer)
+int launch_sr_row2im(const float* dA, long long xs_b, int HW, int Cin, int r, int B, float* dx, cudaStream_t st);
 
 int launch_sr_im2row16(const void* x16, long long xs_b, int HW, int Cin, int r, int B, void* A16, cudaStream_t st);
 int launch_conv_weight_perm16(const float* w, void* o16, int N, int Cin, int r, cudaStream_t st);

@@ -18,6 +18,7 @@
 //    ones (any layout of an all-ones tile is valid), accumulated in 64 spare TMEM columns and folded the same way.
 //  * optional head mask (Multi-Branch attention: only the diagonal Ch x Ch blocks of the C x C context are real) and a
 //    transposed second copy of the result for the consumers that need ctx^T.
+#include <algorithm>
 #include <cuda_fp16.h>
 #include "bwd.cuh"
 #include "tc.cuh"
@@ -62,6 +63,7 @@ struct WgradParams {
   long long stride_out, stride_outT;
   int mask_ch;           // > 0: keep only elements with i / mask_ch == j / mask_ch
   int fmt;               // 0 fp16, 1 bf16, 2 fp32 operands (TF32 MMA)
+  int ring;              // bytes of the pipeline ring (flag "smem_kb": a smaller ring lets two CTAs of different kernels share an SM)
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE;
   float* sTile = reinterpret_cast<float*>(smem);                     // [128][BN] fp32, float4 index XOR-swizzled by (row & 7)
-  uint8_t* sOnes = smem + WG_RING_BYTES;
+  uint8_t* sOnes = smem + p.ring;
   float* sDb = reinterpret_cast<float*>(sOnes + WG_ONES_BYTES);      // [128]
   uint64_t* full = reinterpret_cast<uint64_t*>(sDb + WG_BM);
   uint64_t* empty = full + WG_MAX_STAGES;
@@ -447,7 +449,16 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   p.stride_out = a.stride_out; p.stride_outT = a.stride_outT; p.mask_ch = a.mask_ch; p.fmt = a.fmt;
   const int boxc = 128 / eb;
   const int stage = (WG_BM / boxc + p.BN / boxc) * WG_BOX_BYTES;
-  p.stages = WG_RING_BYTES / stage;
+  // the ring must hold the parked fp32 tile (128 x BN x 4 bytes) and at least two stages; 16-bit BN = 256 tiles own all 512
+  // TMEM columns, so two of them can never share an SM: they keep the full ring
+  p.ring = WG_RING_BYTES;
+  if (g_tcx_smem_kb > 0 && p.BN <= 128) {
+    int want = g_tcx_smem_kb * 1024 - (1024 + WG_ONES_BYTES + WG_BM * 4 + 256);
+    const int need = std::max(WG_BM * p.BN * 4, 2 * stage);
+    if (want < need) want = need;
+    if (want < p.ring) p.ring = want / 1024 * 1024;
+  }
+  p.stages = p.ring / stage;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   const int tiles = p.ntm * p.ntn;
   if (p.S2 > 1) {
@@ -461,7 +472,7 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   WgradMaps maps;
   TCX_TRY(tcx_make_operand_map(&maps.a, a.A, eb, a.NL, a.Mtok, a.lda, a.batch, a.strideA, boxc, WG_KT, a.fmt == 1, eb == 4));
   TCX_TRY(tcx_make_operand_map(&maps.b, a.B, eb, a.KL, a.Mtok, a.ldb, a.batch, a.strideB, boxc, WG_KT, a.fmt == 1, eb == 4));
-  const size_t smem = 1024 + WG_RING_BYTES + WG_ONES_BYTES + WG_BM * 4 + 256;
+  const size_t smem = 1024 + (size_t)p.ring + WG_ONES_BYTES + WG_BM * 4 + 256;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -777,21 +777,12 @@ class Scale_reduce(nn.Module):
         return ops.scale_reduce(x.contiguous(), *self.args())
 
     def _forward_train(self, x):
-        """Training row (MSTr.py:2225-2249): each strided conv is a patch gather (a copy) + Linear node; the channel-group
-        packing `reshape(B, C, -1).permute(0, 2, 1)` of the NCHW conv output is a copy as well."""
-        B, ntok, C = x.shape
-        S = ops._bridge_side(ntok)
-        outs, off = [], 0
-        for conv, hw, mult in ((self.sr0, S, 1), (self.sr1, S // 2, 2), (self.sr2, S // 4, 5)):
-            n, r, cin = hw * hw * mult, conv.kernel_size[0], C * mult
-            t = x[:, off:off + n].reshape(B, hw // r, r, hw // r, r, cin).permute(0, 1, 3, 5, 2, 4)
-            t = t.reshape(B, (hw // r) ** 2, cin * r * r)
-            y = tcx_autograd.linear(t, conv.weight.reshape(cin, cin * r * r), conv.bias)       # NHWC conv output
-            outs.append(y.permute(0, 2, 1).reshape(B, C, -1).permute(0, 2, 1))
-            off += n
-        outs.append(x[:, off:])
+        """Training row (MSTr.py:2225-2249): the three strided convs (im2row + GEMM), the channel-group packing and the raw
+        stage-4 rows are ONE autograd node on the library's kernels; the LayerNorm is the usual node."""
+        packed = tcx_autograd.scale_reduce_pack(x, self.sr0.weight, self.sr0.bias, self.sr1.weight, self.sr1.bias,
+                                                self.sr2.weight, self.sr2.bias)
         n = self.norm
-        return tcx_autograd.layernorm(torch.cat(outs, dim=1), n.weight, n.bias, n.eps)
+        return tcx_autograd.layernorm(packed, n.weight, n.bias, n.eps)
 
 
 class M_EfficientSelfAtten(nn.Module):
@@ -824,8 +815,7 @@ class M_EfficientSelfAtten(nn.Module):
             # training row (MSTr.py:2267-2292): Linear / Scale_reduce / attention-core / Linear autograd nodes
             q = tcx_autograd.linear(x, self.q.weight, self.q.bias)
             kv = tcx_autograd.linear(self.scale_reduce(x), self.kv.weight, self.kv.bias)
-            y = tcx_autograd.linear(tcx_autograd.attn_core(q, kv, self.scale), self.proj.weight, self.proj.bias)
-            return y if residual is None else residual + y
+            return tcx_autograd.linear(tcx_autograd.attn_core(q, kv, self.scale), self.proj.weight, self.proj.bias, residual)
         return ops.bridge_sr_attn(x.contiguous(), *self.args(), residual=residual)
 
 
@@ -857,8 +847,7 @@ class M_EfficientChannelAtten(nn.Module):
             # transposed copy; the attention core and the four Linear layers are autograd nodes on the library's kernels
             B, N, C = x.shape
             k, q, v = (tcx_autograd.linear(x, m.weight, m.bias).reshape(B, C, N).transpose(1, 2) for m in (self.k, self.q, self.v))
-            y = tcx_autograd.linear(tcx_autograd.ea_core(k, q, v), self.proj.weight, self.proj.bias)
-            return y if residual is None else residual + y
+            return tcx_autograd.linear(tcx_autograd.ea_core(k, q, v), self.proj.weight, self.proj.bias, residual)
         return ops.eff_attn(x.contiguous(), self.k.weight, self.k.bias, self.q.weight, self.q.bias,
                             self.v.weight, self.v.bias, self.proj.weight, self.proj.bias,
                             residual=residual, reinterpret=True)
@@ -889,28 +878,29 @@ class BridgLayer_4(nn.Module):
 
 
 def _bridge_tokens_train(maps):
-    """NCHW maps -> [B, Ntok, 64] (MSTr.py:2380-2386): permuted copies."""
-    B = maps[0].shape[0]
-    return torch.cat([m.permute(0, 2, 3, 1).reshape(B, -1, 64) for m in maps], dim=1)
+    """NCHW-shaped maps -> [B, Ntok, 64] (MSTr.py:2380-2386): one regroup launch (its gradient: one split launch)."""
+    return tcx_autograd.bridge_merge([_nhwc(m) for m in maps])
 
 
 def _bridge_layer_train(self, inputs):
-    """BridgLayer_4.forward (MSTr.py:2373-2409) as autograd nodes; slab slicing / concatenation and the two residual
-    additions are ATen copies / adds."""
+    """BridgLayer_4.forward (MSTr.py:2373-2409) as autograd nodes.  Both skip connections use the pre-norm pattern of
+    LayerNormResFn (the two gradients of x / tx1 meet inside the LayerNorm backward kernel); the attention's output projection
+    adds its skip in the GEMM epilogue; the four per-scale slabs come from / go back into the token buffer in one launch each
+    (BridgeSplitFn / BridgeMergeFn), so the layer runs no ATen slice, cat, fill or add kernels."""
     x = _bridge_tokens_train(inputs) if isinstance(inputs, (list, tuple)) else inputs
     B, ntok, C = x.shape
     S = ops._bridge_side(ntok)
     n1, n2 = self.norm1, self.norm2
-    tx1 = x + self.attn(tcx_autograd.layernorm(x, n1.weight, n1.bias, n1.eps))
-    tx = tcx_autograd.layernorm(tx1, n2.weight, n2.bias, n2.eps)
-    fns, off = [], 0
-    for mlp, hw, mult in ((self.mixffn1, S, 1), (self.mixffn2, S // 2, 2), (self.mixffn3, S // 4, 5), (self.mixffn4, S // 8, 8)):
-        n = hw * hw * mult
-        fns.append(lambda mlp=mlp, hw=hw, mult=mult, n=n, off=off:
-                   mlp(tx[:, off:off + n].reshape(B, hw * hw, C * mult), hw, hw).reshape(B, n, C))
-        off += n
+    xn, xres = tcx_autograd.layernorm_res(x, n1.weight, n1.bias, n1.eps)
+    tx1 = self.attn(xn, residual=xres)
+    tx, tx1res = tcx_autograd.layernorm_res(tx1, n2.weight, n2.bias, n2.eps)
+    slabs = tcx_autograd.bridge_split(tx)
+    fns = []
+    for mlp, hw, slab in zip((self.mixffn1, self.mixffn2, self.mixffn3, self.mixffn4), (S, S // 2, S // 4, S // 8), slabs):
+        fns.append(lambda mlp=mlp, hw=hw, slab=slab: mlp(slab, hw, hw))
     # the four per-scale Mix-FFNs are independent (MSTr.py:2394-2402)
-    return tx1 + torch.cat(_parallel_branches(x.device, fns, inputs=(tx,)), dim=1)
+    ys = _parallel_branches(x.device, fns, inputs=tuple(slabs))
+    return tcx_autograd.bridge_merge(ys, tx1res)
 
 
 BridgLayer_4._forward_train = _bridge_layer_train
@@ -945,6 +935,9 @@ class BridgeBlock_4(nn.Module):
         B, ntok, C = t.shape
         outs, off = [], 0
         S = ops._bridge_side(ntok)      # 56 at 224x224 (the reference hard-codes 56/28/14/7, MSTr.py:2432-2435)
+        if _recording(t, self.bridge_layer1.norm1.weight):
+            # training row: the four dense slabs in one launch (NCHW-shaped views of NHWC storage, like the slices below)
+            return [m.reshape(B, S >> k, S >> k, -1).permute(0, 3, 1, 2) for k, m in enumerate(tcx_autograd.bridge_split(t))]
         for hw, mult in ((S, 1), (S // 2, 2), (S // 4, 5), (S // 8, 8)):
             n = hw * hw * mult
             outs.append(t[:, off:off + n, :].reshape(B, hw, hw, C * mult).permute(0, 3, 1, 2))
@@ -996,7 +989,7 @@ class MSTransception(nn.Module):
         if self.have_bridge != "None":
             if recording:
                 # training row: every module below routes to the autograd nodes of transception_b200/autograd.py
-                tokens = torch.cat([m.reshape(m.shape[0], -1, 64) for m in maps], dim=1)
+                tokens = tcx_autograd.bridge_merge(maps)
             else:
                 tokens = ops.bridge_regroup(maps)
             maps = [m.permute(0, 2, 3, 1) for m in self.bridge(tokens)]

@@ -75,6 +75,13 @@ _PROTOS = {
     "tcx_iff_coordatt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_iff_coordatt_fwd": (_i, [_pp, _pp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_regroup_fwd": (_i, [_pp, _vp, _i, _i, _vp]),
+    "tcx_bridge_split_fwd": (_i, [_vp, _pp, _i, _i, _vp]),
+    "tcx_bridge_merge_fwd": (_i, [_pp, _vp, _vp, _i, _i, _vp]),
+    "tcx_scale_reduce_saved_bytes": (_sz, [_i, _i]),
+    "tcx_scale_reduce_train_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_scale_reduce_train_fwd": (_i, [_vp, _pp, _vp, _i, _i, _vp, _vp, _vp]),
+    "tcx_scale_reduce_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "tcx_scale_reduce_bwd": (_i, [_vp, _pp, _vp, _vp, _pp, _i, _i, _vp, _vp]),
     "tcx_scale_reduce_workspace_bytes": (_sz, [_i, _i]),
     "tcx_scale_reduce_fwd": (_i, [_vp, _pp, _f, _vp, _i, _i, _vp, _vp]),
     "tcx_bridge_sr_attn_workspace_bytes": (_sz, [_i, _i]),
@@ -582,6 +589,73 @@ def bridge_regroup(maps):
     out = torch.empty((B, ntok, 64), device=maps[0].device, dtype=maps[0].dtype)
     _chk(lib.tcx_bridge_regroup_fwd(_table(maps), _ptr(out), B, S, _stream()))
     return out
+
+
+_BRIDGE_MULT = (1, 2, 5, 8)
+
+
+def bridge_split(tokens):
+    """[B, Ntok, 64] token buffer -> its four dense per-scale slabs [B, (S/2^k)^2, 64*{1,2,5,8}] (one launch)."""
+    require_cuda(tokens)
+    lib = load_library()
+    tokens = tokens.contiguous()
+    B, ntok, C = tokens.shape
+    S = _bridge_side(ntok)
+    outs = [torch.empty((B, (S >> k) ** 2, 64 * m), device=tokens.device, dtype=tokens.dtype) for k, m in enumerate(_BRIDGE_MULT)]
+    tab = (ctypes.c_void_p * 4)(*[_ptr(o) for o in outs])
+    _chk(lib.tcx_bridge_split_fwd(_ptr(tokens), tab, B, S, _stream()))
+    return outs
+
+
+def bridge_merge(slabs, residual=None):
+    """Four per-scale slabs (any shape with B leading and (S/2^k)^2 * 64*{1,2,5,8} elements per image) -> [B, Ntok, 64]
+    (+ residual), one launch."""
+    require_cuda(slabs[0])
+    lib = load_library()
+    slabs = [m.contiguous() for m in slabs]
+    B = slabs[0].shape[0]
+    S = int(round((slabs[0].numel() // (B * 64)) ** 0.5))
+    per = [(S >> k) ** 2 * m for k, m in enumerate(_BRIDGE_MULT)]
+    if S <= 0 or S % 8 or [m.numel() for m in slabs] != [B * n * 64 for n in per]:
+        raise RuntimeError("bridge_merge: expected slabs of %s tokens per image, got %s" % (per, [tuple(m.shape) for m in slabs]))
+    out = torch.empty((B, sum(per), 64), device=slabs[0].device, dtype=slabs[0].dtype)
+    if residual is not None:
+        residual = residual.contiguous()
+        if residual.shape != out.shape:
+            raise RuntimeError("bridge_merge: residual %s does not match %s" % (tuple(residual.shape), tuple(out.shape)))
+    tab = (ctypes.c_void_p * 4)(*[_ptr(m) for m in slabs])
+    _chk(lib.tcx_bridge_merge_fwd(tab, _ptr(residual), _ptr(out), B, S, _stream()))
+    return out
+
+
+def scale_reduce_pack_train(x, params):
+    """Scale_reduce without its LayerNorm: (packed [B, Nred, 64], saved).  params = [sr0_w, sr0_b, sr1_w, sr1_b, sr2_w, sr2_b]."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, ntok, C = x.shape
+    S = _bridge_side(ntok)
+    nred = (S // 8) ** 2 * 16
+    packed = torch.empty((B, nred, 64), device=x.device, dtype=x.dtype)
+    saved = _ws(lib.tcx_scale_reduce_saved_bytes(B, S), x)
+    ws = _ws(lib.tcx_scale_reduce_train_workspace_bytes(B, S), x)
+    _chk(lib.tcx_scale_reduce_train_fwd(_ptr(x), _table(params), _ptr(packed), B, S, _ptr(saved), _ptr(ws), _stream()))
+    return packed, saved
+
+
+def scale_reduce_pack_bwd(dpacked, saved, params, ntok):
+    """(dx [B, Ntok, 64], six parameter gradients) of scale_reduce_pack_train."""
+    require_cuda(dpacked)
+    lib = load_library()
+    dpacked = dpacked.contiguous()
+    B = dpacked.shape[0]
+    S = _bridge_side(ntok)
+    dx = torch.empty((B, ntok, 64), device=dpacked.device, dtype=dpacked.dtype)
+    grads = [torch.empty_like(p) for p in params]
+    gtab = (ctypes.c_void_p * 6)(*[_ptr(g) for g in grads])
+    ws = _ws(lib.tcx_scale_reduce_bwd_workspace_bytes(B, S), dpacked)
+    _chk(lib.tcx_scale_reduce_bwd(_ptr(dpacked), _table(params), _ptr(saved), _ptr(dx), gtab, B, S, _ptr(ws), _stream()))
+    return dx, grads
 
 
 def scale_reduce(x, s0w, s0b, s1w, s1b, s2w, s2b, lnw, lnb, eps):
