@@ -398,6 +398,16 @@ size_t tcx_scale_reduce_bwd_workspace_bytes(int B, int S);
 int tcx_scale_reduce_bwd(const float* dpacked, const void* const* p, const void* saved, float* dx, void* const* dp, int B, int S,
                          void* ws, void* stream);
 
+/* Training row of the class head: pixel shuffle x4 + LayerNorm(64) of FinalPatchExpand_X4 (MSTr.py:212-227) + the 1x1 conv to
+ * classes (:288-289), on the expand output e [B*H*W][16*64] -> NCHW logits [B][ncls][4H][4W] (the arithmetic of the second half
+ * of tcx_final_expand_head_fwd).  tcx_final_head_bwd: ONE pass over e and dlogits -> de (layout of e) and the gradients of
+ * {ln_w, ln_b, cls_w [ncls][64], cls_b}; ncls <= 16.  No [pixels][64] tensor is written in either direction. */
+int tcx_final_head_train_fwd(const float* e, const float* lnw, const float* lnb, float eps, const float* cls_w, const float* cls_b,
+                             int ncls, float* logits_nchw, int B, int H, int W, void* stream);
+size_t tcx_final_head_bwd_workspace_bytes(int B, int H, int W);
+int tcx_final_head_bwd(const float* e, const float* dlogits, const float* lnw, const float* lnb, float eps, const float* cls_w, int ncls,
+                       float* de, float* dlnw, float* dlnb, float* dcls_w, float* dcls_b, int B, int H, int W, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,29 @@ class ScaleReducePackFn(torch.autograd.Function):
         return (dx,) + tuple(g)
 
 
+class FinalHeadFn(torch.autograd.Function):
+    """Pixel shuffle x4 + LayerNorm(64) (FinalPatchExpand_X4, MSTr.py:212-227) + 1x1 conv to classes (:288-289) on the expand
+    output e [B, H*W, 1024] -> NCHW logits.  One kernel each way; no [pixels, 64] tensor is written in either direction."""
+
+    @staticmethod
+    def forward(ctx, e, H, W, lnw, lnb, eps, cw, cb):
+        e = e.contiguous()
+        ctx.save_for_backward(e, lnw, lnb, cw)
+        ctx.geom = (H, W, eps)
+        return ops.final_head_train(e, H, W, lnw, lnb, eps, cw, cb)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        e, lnw, lnb, cw = ctx.saved_tensors
+        H, W, eps = ctx.geom
+        de, dlnw, dlnb, dcw, dcb = ops.final_head_bwd(e, dlogits, H, W, lnw, lnb, eps, cw)
+        return de, None, None, dlnw, dlnb, None, dcw, dcb
+
+
+def final_head(e, H, W, lnw, lnb, eps, cw, cb):
+    return FinalHeadFn.apply(e, H, W, lnw, lnb, eps, cw, cb)
+
+
 def bridge_split(tokens):
     return BridgeSplitFn.apply(tokens)
 

@@ -2449,4 +2449,27 @@ int tcx_scale_reduce_bwd(const float* dpacked, const void* const* p, const void*
   return 0;
 }
 
+// ---- training row of the class head: FinalPatchExpand_X4's pixel shuffle + LayerNorm(64) (MSTr.py:212-227) and the 1x1 conv to
+// classes (:288-289) on the expand output e [B*H*W][1024] (the Linear node before it stays a Linear node) ----
+int tcx_final_head_train_fwd(const float* e, const float* lnw, const float* lnb, float eps, const float* cls_w, const float* cls_b,
+                             int ncls, float* logits_nchw, int B, int H, int W, void* stream) {
+  TCX_REQUIRE(e && lnw && lnb && cls_w && cls_b && logits_nchw, "final_head_train_fwd: null pointer");
+  return launch_final_head(e, B, H, W, lnw, lnb, eps, cls_w, cls_b, ncls, logits_nchw, S(stream));
+}
+size_t tcx_final_head_bwd_workspace_bytes(int B, int H, int W) { return 4 * (final_head_bwd_part_floats(B, H, W) + 64); }
+// dlogits [B][ncls][4H][4W] -> de [B*H*W][1024] and d{ln_w, ln_b, cls_w, cls_b}
+int tcx_final_head_bwd(const float* e, const float* dlogits, const float* lnw, const float* lnb, float eps, const float* cls_w, int ncls,
+                       float* de, float* dlnw, float* dlnb, float* dcls_w, float* dcls_b, int B, int H, int W, void* ws, void* stream) {
+  TCX_REQUIRE(e && dlogits && lnw && lnb && cls_w && de && dlnw && dlnb && dcls_w && dcls_b && ws, "final_head_bwd: null pointer");
+  cudaStream_t st = S(stream);
+  float* part = reinterpret_cast<float*>(ws);
+  int nblk = 0;
+  TCX_TRY(launch_final_head_bwd(e, dlogits, B, H, W, lnw, eps, cls_w, ncls, de, part, &nblk, st));
+  AuxStreams* aux = aux_streams(st);
+  if (aux) TCX_TRY(fork_streams(aux, st, 1));
+  TCX_TRY(launch_final_head_bwd_fold(part, nblk, lnw, lnb, cls_w, ncls, dlnw, dlnb, dcls_w, dcls_b, aux ? aux->s[0] : st));
+  if (aux) TCX_TRY(join_stream(aux, 0, st));
+  return 0;
+}
+
 }  // extern "C"

@@ -2,6 +2,7 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "misc.cuh"
+#include "bwd.cuh"
 
 namespace {
 
@@ -422,6 +423,199 @@ __global__ void __launch_bounds__(128) final_head_kernel(const float* __restrict
   }
 }
 
+// ---- training row of the class head (MSTr.py:212-227 pixel shuffle + LayerNorm(64), :288-289 1x1 conv to classes) ----
+// Backward of final_head_kernel in ONE pass over the expand output e [B*H*W][16*64]: one thread per output pixel recomputes the
+// LayerNorm statistics of its 64-float row, forms d(LN out) = sum_k dlogit_k cw[k][:] from the NCHW logit gradients (no
+// [pixels][64] gradient tensor in memory), applies the LayerNorm backward and writes de in the UNSHUFFLED layout of e (the
+// pixel shuffle is a row permutation).  Every parameter gradient follows from two per-block sums over pixels,
+//   G[k][c] = sum_p dlogit[p][k] xhat[p][c],   s[k] = sum_p dlogit[p][k]:
+//   d cw[k][c] = lnw[c] G[k][c] + lnb[c] s[k],  d cb[k] = s[k],  d lnw[c] = sum_k cw[k][c] G[k][c],  d lnb[c] = sum_k cw[k][c] s[k],
+// accumulated per block through a shared-memory tile (xhat of the block's 128 pixels) in a fixed order, folded by
+// final_head_fold_kernel in block order: bit-reproducible.
+constexpr int FH_K = 16;         // class slots (ncls <= 16)
+constexpr int FH_WARPS = 8;
+constexpr int FH_ST = 6;         // quads in flight per warp (cp.async ring: 1 KB of rows + 256 B of logit gradients per stage)
+constexpr int FH_DYN_SMEM = FH_WARPS * FH_ST * (64 * 16 + 64 * 4);
+__device__ __forceinline__ void fh_cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fh_cp4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fh_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fh_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// Work layout: a half-warp owns a pixel, lane (l & 15) its channels 4l .. 4l+3 (one float4 of the 256-byte row), so the 64-wide
+// row reductions are 4 shuffle steps, the class weights cw[k][c] * lnw[c] and the G accumulators of the lane's four channels
+// live in registers, and no shared memory is touched inside the loop.  A warp walks "quads" (the 4 horizontally adjacent output
+// pixels of one (b, 4h + p1, w): 1 KB contiguous in e): half-warp h takes pixels p2 = h and h + 2; the next quad's rows are
+// loaded before the current one is processed: every lane copies ITS two float4 and two logit gradients of the next FH_ST - 1 quads
+// into a per-warp shared-memory ring with cp.async and later reads back only what it copied itself (no barrier needed) — the bytes
+// in flight per SM (8 warps x 5 quads x 1.25 KB) no longer depend on registers.
+template <int KC>
+__global__ void __launch_bounds__(FH_WARPS * 32, 1) final_head_bwd_kernel(const float* __restrict__ e, const float* __restrict__ dlogits,
+                                                                          int B, int H, int W, const float* __restrict__ lnw,
+                                                                          const float* __restrict__ cw, float eps, int ncls,
+                                                                          float* __restrict__ de, float* __restrict__ part) {
+  __shared__ float s_red[FH_WARPS][FH_K * 64 + FH_K];
+  extern __shared__ float4 fh_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* sx = fh_dyn + (size_t)warp * FH_ST * 64;                                                   // [FH_ST][64] float4
+  float* sd = reinterpret_cast<float*>(fh_dyn + (size_t)FH_WARPS * FH_ST * 64) + (size_t)warp * FH_ST * 64;   // [FH_ST][64] float
+  const int hl = lane & 15, half = lane >> 4;
+  const int c4 = hl * 4;
+  const int Ho = H * 4, Wo = W * 4;
+  const long long plane = (long long)Ho * Wo;
+  const int nquad = B * Ho * W;            // < 2^31 (checked by the launcher): 32-bit index arithmetic in the loop
+  float wr[KC][4], g[KC][4], sk[KC];
+#pragma unroll
+  for (int k = 0; k < KC; k++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      wr[k][j] = k < ncls ? cw[k * 64 + c4 + j] * lnw[c4 + j] : 0.f;
+      g[k][j] = 0.f;
+    }
+    sk[k] = 0.f;
+  }
+  // quad qq -> float offset of its 256 floats in e, and the address of class hl's logit gradient of pixel p2 = half
+  auto locate = [&](int qq, long long& eoff, const float*& dptr) {
+    const unsigned t = (unsigned)qq / (unsigned)W;          // b * Ho + ho
+    const unsigned w = (unsigned)qq - t * (unsigned)W;
+    const unsigned b = t / (unsigned)Ho;
+    const unsigned ho = t - b * (unsigned)Ho;
+    eoff = ((((long long)b * H + (ho >> 2)) * W + w) * 16 + (ho & 3) * 4) * 64;
+    dptr = dlogits + ((long long)b * ncls + hl) * plane + (long long)ho * Wo + 4 * w + half;
+  };
+  const int stride = (int)gridDim.x * FH_WARPS;
+  int q = (int)blockIdx.x * FH_WARPS + warp;
+  // lane hl < ncls of a half-warp fetches the logit gradient of class hl for the half-warp's two pixels (broadcast by shuffle when
+  // it is needed), so the next quads' rows AND gradients are in flight while the current quad is processed
+  long long offs[FH_ST];                   // e offsets of the quads in flight (ring, indexed like the smem slots)
+  auto issue = [&](int qq, int slot_, long long& eoff) {
+    if (qq < nquad) {
+      const float* d;
+      locate(qq, eoff, d);
+      const float* src = e + eoff + c4;
+      fh_cp16(sx + slot_ * 64 + lane * 2, src + half * 64);
+      fh_cp16(sx + slot_ * 64 + lane * 2 + 1, src + (half + 2) * 64);
+      if (hl < ncls) {
+        fh_cp4(sd + slot_ * 64 + lane * 2, d);
+        fh_cp4(sd + slot_ * 64 + lane * 2 + 1, d + 2);
+      }
+    }
+    fh_commit();
+  };
+#pragma unroll
+  for (int st = 0; st < FH_ST; st++) offs[st] = 0;
+#pragma unroll
+  for (int st = 0; st < FH_ST - 1; st++) issue(q + st * stride, st, offs[st]);
+  // the loop body is unrolled FH_ST times so that ring slots (and offs[]) are compile-time indices
+  for (; q < nquad;) {
+#pragma unroll
+    for (int slot = 0; slot < FH_ST; slot++) {
+      if (q >= nquad) break;
+      const int nslot = (slot + FH_ST - 1) % FH_ST;
+      issue(q + (FH_ST - 1) * stride, nslot, offs[nslot]);
+      fh_wait<FH_ST - 1>();                  // the oldest group (this quad) has landed
+      const long long off = offs[slot];
+      const float4 ca = sx[slot * 64 + lane * 2], cb = sx[slot * 64 + lane * 2 + 1];
+      const float cda = hl < ncls ? sd[slot * 64 + lane * 2] : 0.f, cdb = hl < ncls ? sd[slot * 64 + lane * 2 + 1] : 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 2; pp++) {        // pixel p2 = half + 2 * pp
+      const float4 xv = pp ? cb : ca;
+      const float dmine = pp ? cdb : cda;
+      float dl[KC];
+#pragma unroll
+      for (int k = 0; k < KC; k++) dl[k] = __shfl_sync(0xffffffffu, dmine, (lane & 16) | k);     // 0 beyond ncls
+      float x[4] = {xv.x, xv.y, xv.z, xv.w};
+      float sum = (x[0] + x[1]) + (x[2] + x[3]);
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+      const float mean = sum * (1.f / 64.f);
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) { x[j] -= mean; var = fmaf(x[j], x[j], var); }
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) var += __shfl_xor_sync(0xffffffffu, var, m);
+      const float rstd = rsqrtf(var * (1.f / 64.f) + eps);
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        x[j] *= rstd;                        // xhat
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+          a[j] = fmaf(dl[k], wr[k][j], a[j]);
+          g[k][j] = fmaf(dl[k], x[j], g[k][j]);
+        }
+        s1 += a[j];
+        s2 = fmaf(a[j], x[j], s2);
+      }
+#pragma unroll
+      for (int k = 0; k < KC; k++) sk[k] += dl[k];
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+      }
+      s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
+      *reinterpret_cast<float4*>(de + off + (half + 2 * pp) * 64 + c4) =
+          make_float4(rstd * (a[0] - s1 - x[0] * s2), rstd * (a[1] - s1 - x[1] * s2), rstd * (a[2] - s1 - x[2] * s2),
+                      rstd * (a[3] - s1 - x[3] * s2));
+    }
+      q += stride;
+    }
+  }
+  // warp sum = half 0 + half 1, then the eight warps in warp order
+#pragma unroll
+  for (int k = 0; k < KC; k++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float o = __shfl_xor_sync(0xffffffffu, g[k][j], 16);
+      if (half == 0) s_red[warp][k * 64 + c4 + j] = g[k][j] + o;
+    }
+    const float o = __shfl_xor_sync(0xffffffffu, sk[k], 16);
+    if (lane == 0) s_red[warp][FH_K * 64 + k] = sk[k] + o;
+  }
+  __syncthreads();
+  float* pb = part + (size_t)blockIdx.x * (FH_K * 64 + FH_K);
+  for (int i = threadIdx.x; i < FH_K * 64 + FH_K; i += FH_WARPS * 32) {
+    const int k = i < FH_K * 64 ? i >> 6 : i - FH_K * 64;
+    float s = 0.f;
+    if (k < KC) {
+      s = s_red[0][i];
+#pragma unroll
+      for (int wv = 1; wv < FH_WARPS; wv++) s += s_red[wv][i];
+    }
+    pb[i] = s;
+  }
+}
+
+// fold of the block partials (ordered, bwd_fold_sum), then the four parameter gradients from the folded G | s
+__global__ void __launch_bounds__(256) final_head_fold_kernel(const float* __restrict__ part, int nblk, float* __restrict__ Gs) {
+  const int n = FH_K * 64 + FH_K;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const float s = bwd_fold_sum(part, nblk, n, i, i < n);
+  if (threadIdx.y == 0 && i < n) Gs[i] = s;
+}
+__global__ void __launch_bounds__(256) final_head_params_kernel(const float* __restrict__ G, const float* __restrict__ lnw,
+                                                                const float* __restrict__ lnb, const float* __restrict__ cw, int ncls,
+                                                                float* __restrict__ dlnw, float* __restrict__ dlnb, float* __restrict__ dcw,
+                                                                float* __restrict__ dcb) {
+  const float* sk = G + FH_K * 64;
+  for (int i = threadIdx.x; i < ncls * 64; i += 256) {
+    const int k = i >> 6, c = i & 63;
+    dcw[i] = fmaf(lnw[c], G[k * 64 + c], lnb[c] * sk[k]);
+  }
+  if (threadIdx.x < ncls) dcb[threadIdx.x] = sk[threadIdx.x];
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float a = 0.f, b2 = 0.f;
+    for (int k = 0; k < ncls; k++) { a = fmaf(cw[k * 64 + c], G[k * 64 + c], a); b2 = fmaf(cw[k * 64 + c], sk[k], b2); }
+    dlnw[c] = a; dlnb[c] = b2;
+  }
+}
+
 }  // namespace
 
 int launch_patch_embed_ln(const float* x, long long xs_b, long long xs_c, int B, int Hin, int Win, const float* w,
@@ -506,6 +700,41 @@ int launch_final_head(const float* in, int B, int H, int W, const float* lnw, co
   const long long total = (long long)B * H * 4 * W * 4;
   final_head_kernel<32><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(in, B, H, W, lnw, lnb, eps, cw, cb, ncls, out);
   return tcx_check_launch("final_head");
+}
+
+int final_head_bwd_blocks(int B, int H, int W) {
+  const long long quads = (long long)B * H * 4 * W;
+  long long nblk = 148;                           // one resident block per SM; every warp strides over the quads
+  if (nblk * FH_WARPS > quads) nblk = (quads + FH_WARPS - 1) / FH_WARPS;
+  return (int)(nblk < 1 ? 1 : nblk);
+}
+size_t final_head_bwd_part_floats(int B, int H, int W) { return (size_t)(final_head_bwd_blocks(B, H, W) + 1) * (FH_K * 64 + FH_K); }
+int launch_final_head_bwd(const float* e, const float* dlogits, int B, int H, int W, const float* lnw, float eps, const float* cw,
+                          int ncls, float* de, float* part, int* nblk_out, cudaStream_t st) {
+  TCX_REQUIRE(ncls >= 1 && ncls <= FH_K, "final_head_bwd: ncls=%d out of range (1..%d)", ncls, FH_K);
+  TCX_REQUIRE((long long)B * H * W > 0 && (long long)B * H * 4 * W * 4 < (1ll << 31), "final_head_bwd: empty or too large a batch");
+  const int grid = final_head_bwd_blocks(B, H, W);
+  static PerDeviceOnce once;
+  if (once.first()) {
+    cudaError_t ce = cudaFuncSetAttribute(final_head_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_DYN_SMEM);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(final_head_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_DYN_SMEM);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(final_head_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_DYN_SMEM);
+    TCX_REQUIRE(ce == cudaSuccess, "final_head_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
+  }
+  if (ncls <= 4) final_head_bwd_kernel<4><<<grid, FH_WARPS * 32, FH_DYN_SMEM, st>>>(e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
+  else if (ncls <= 10) final_head_bwd_kernel<10><<<grid, FH_WARPS * 32, FH_DYN_SMEM, st>>>(e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
+  else final_head_bwd_kernel<16><<<grid, FH_WARPS * 32, FH_DYN_SMEM, st>>>(e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
+  *nblk_out = grid;
+  return tcx_check_launch("final_head_bwd");
+}
+// part: the block partials of launch_final_head_bwd followed by one more slot (the folded sums)
+int launch_final_head_bwd_fold(float* part, int nblk, const float* lnw, const float* lnb, const float* cw, int ncls, float* dlnw,
+                               float* dlnb, float* dcw, float* dcb, cudaStream_t st) {
+  float* Gs = part + (size_t)nblk * (FH_K * 64 + FH_K);
+  final_head_fold_kernel<<<(FH_K * 64 + FH_K + 31) / 32, dim3(32, 8), 0, st>>>(part, nblk, Gs);
+  TCX_TRY(tcx_check_launch("final_head_fold"));
+  final_head_params_kernel<<<1, 256, 0, st>>>(Gs, lnw, lnb, cw, ncls, dlnw, dlnb, dcw, dcb);
+  return tcx_check_launch("final_head_params");
 }
 
 int launch_sr_im2row16(const void* x16, long long xs_b, int HW, int Cin, int r, int B, void* A16, cudaStream_t st) {

@@ -69,6 +69,14 @@ int launch_shuffle_ln(const float* in, int B, int H, int W, int s, int c, const 
 int launch_final_head(const float* in, int B, int H, int W, const float* lnw, const float* lnb, float eps,
                       const float* cw, const float* cb, int ncls, float* out, cudaStream_t st);
 
+// backward of launch_final_head: de in the layout of e; part: final_head_bwd_part_floats floats (block partials of the parameter
+// sums, folded into the four parameter gradients by launch_final_head_bwd_fold — any stream ordered after the first launch)
+size_t final_head_bwd_part_floats(int B, int H, int W);
+int launch_final_head_bwd(const float* e, const float* dlogits, int B, int H, int W, const float* lnw, float eps, const float* cw,
+                          int ncls, float* de, float* part, int* nblk_out, cudaStream_t st);
+int launch_final_head_bwd_fold(float* part, int nblk, const float* lnw, const float* lnb, const float* cw, int ncls, float* dlnw,
+                               float* dlnb, float* dcw, float* dcb, cudaStream_t st);
+
 // fused FinalPatchExpand_X4 + LayerNorm + class head (head_tc.cu)
 bool head_tc_eligible(const float* x, const float* w, int ncls);
 size_t head_tc_workspace_floats();

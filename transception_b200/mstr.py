@@ -307,18 +307,14 @@ class MyDecoderLayer(nn.Module):
         shuffles and the NCHW view of the logits are copies."""
         t = tcx_autograd.linear(torch.cat([x1, x2], dim=-1), self.concat_linear.weight, self.concat_linear.bias)
         t = self.layer_former_2(self.layer_former_1(t, h, w), h, w)
-        up = self.layer_up(t)
         if self.last_layer is None:
-            return up
-        # 1x1 conv to n_class planes = Linear over the 64 channels; the class rows are zero-padded to a multiple of 16 so
-        # that the gradient GEMMs keep 16-byte row pitches
-        cw, cb = self.last_layer.weight, self.last_layer.bias
-        k = cw.shape[0]
-        kp = (k + 15) // 16 * 16
-        wpad = torch.nn.functional.pad(cw.view(k, -1), (0, 0, 0, kp - k))
-        bpad = torch.nn.functional.pad(cb, (0, kp - k))
-        logits = tcx_autograd.linear(up, wpad, bpad)[..., :k]
-        return logits.view(x1.shape[0], 4 * h, 4 * w, k).permute(0, 3, 1, 2)
+            return self.layer_up(t)
+        # expand Linear node, then pixel shuffle + LayerNorm + 1x1 conv to n_class planes as ONE node writing NCHW logits
+        up, cw, cb = self.layer_up, self.last_layer.weight, self.last_layer.bias
+        if t.shape[-1] != 64 or cw.shape[0] > 16:
+            raise NotImplementedError("the training class head is built for dim 64 and at most 16 classes")
+        e = tcx_autograd.linear(t, up.expand.weight)
+        return tcx_autograd.final_head(e, h, w, up.norm.weight, up.norm.bias, up.norm.eps, cw, cb)
 
 
 # --------------------------------------------------------------------------------------

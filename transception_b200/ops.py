@@ -75,6 +75,9 @@ _PROTOS = {
     "tcx_iff_coordatt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_iff_coordatt_fwd": (_i, [_pp, _pp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_regroup_fwd": (_i, [_pp, _vp, _i, _i, _vp]),
+    "tcx_final_head_train_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "tcx_final_head_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tcx_final_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_split_fwd": (_i, [_vp, _pp, _i, _i, _vp]),
     "tcx_bridge_merge_fwd": (_i, [_pp, _vp, _vp, _i, _i, _vp]),
     "tcx_scale_reduce_saved_bytes": (_sz, [_i, _i]),
@@ -859,6 +862,37 @@ def final_expand_head(x, H, W, ew, lnw, lnb, eps, cw, cb):
                                        _ptr(_d(cw).reshape(ncls, 64)), _ptr(_d(cb)), ncls, _ptr(y), B, H, W,
                                        _ptr(ws), _stream()))
     return y
+
+
+def final_head_train(e, H, W, lnw, lnb, eps, cw, cb):
+    """Pixel shuffle x4 + LayerNorm(64) + class head on the expand output e [B, H*W, 1024] -> NCHW logits [B, ncls, 4H, 4W]."""
+    require_cuda(e)
+    lib = load_library()
+    e = e.contiguous()
+    B = e.shape[0]
+    if e.shape[-1] != 1024 or e.numel() != B * H * W * 1024:
+        raise NotImplementedError("final_head_train is built for dim 64 (expand output 16 * 64 wide)")
+    ncls = cw.shape[0]
+    y = torch.empty((B, ncls, 4 * H, 4 * W), device=e.device, dtype=e.dtype)
+    _chk(lib.tcx_final_head_train_fwd(_ptr(e), _ptr(_d(lnw)), _ptr(_d(lnb)), eps, _ptr(_d(cw).reshape(ncls, 64)), _ptr(_d(cb)), ncls,
+                                      _ptr(y), B, H, W, _stream()))
+    return y
+
+
+def final_head_bwd(e, dlogits, H, W, lnw, lnb, eps, cw):
+    """(de, d ln_w, d ln_b, d cls_w, d cls_b) of final_head_train."""
+    require_cuda(e)
+    lib = load_library()
+    dlogits = dlogits.contiguous()
+    B, ncls = dlogits.shape[0], dlogits.shape[1]
+    if ncls > 16:
+        raise NotImplementedError("final_head_bwd is built for at most 16 classes (got %d)" % ncls)
+    de = torch.empty_like(e)
+    dlnw, dlnb, dcw, dcb = torch.empty_like(lnw), torch.empty_like(lnb), torch.empty_like(cw), torch.empty(ncls, device=e.device, dtype=e.dtype)
+    ws = _ws(lib.tcx_final_head_bwd_workspace_bytes(B, H, W), e)
+    _chk(lib.tcx_final_head_bwd(_ptr(e), _ptr(dlogits), _ptr(_d(lnw)), _ptr(_d(lnb)), eps, _ptr(_d(cw).reshape(ncls, 64)), ncls, _ptr(de),
+                                _ptr(dlnw), _ptr(dlnb), _ptr(dcw), _ptr(dcb), B, H, W, _ptr(ws), _stream()))
+    return de, dlnw, dlnb, dcw, dcb
 
 
 # ------------------------------------------------------------------------------------------------
