@@ -408,6 +408,11 @@ size_t tcx_final_head_bwd_workspace_bytes(int B, int H, int W);
 int tcx_final_head_bwd(const float* e, const float* dlogits, const float* lnw, const float* lnb, float eps, const float* cls_w, int ncls,
                        float* de, float* dlnw, float* dlnb, float* dcls_w, float* dcls_b, int B, int H, int W, void* ws, void* stream);
 
+/* Training row of the stem conv (OverlapPatchEmbeddings.proj, MSTr.py:299-304): forward = tcx_patch_embed_ln_fwd with
+ * lnw = lnb = NULL (the conv output; the LayerNorm is a separate node); its weight gradient is tcx_linear_bwd on the patch matrix
+ * patches [B*Ho*Wo][Kp] (Kp >= 147, a multiple of 4; columns (ci, ky, kx), zero beyond 147 and outside the image) built here. */
+int tcx_patch_im2row_fwd(const float* x, int B, int Cin, int H, int W, float* patches, int Kp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,28 @@ class ScaleReducePackFn(torch.autograd.Function):
         return (dx,) + tuple(g)
 
 
+class PatchEmbedConvFn(torch.autograd.Function):
+    """OverlapPatchEmbeddings.proj (7x7 / 4 conv, MSTr.py:299-302) on the image batch: exact fp32 forward on the fused stem kernel;
+    the image needs no gradient, the weight gradient is one im2row launch + the Linear weight-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return ops.patch_embed_conv(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("transception_b200: gradient with respect to the input image is not built")
+        dw, db = ops.patch_embed_conv_bwd(x, w, dy)
+        return None, dw, db
+
+
+def patch_embed_conv(x, w, b):
+    return PatchEmbedConvFn.apply(x, w, b)
+
+
 class FinalHeadFn(torch.autograd.Function):
     """Pixel shuffle x4 + LayerNorm(64) (FinalPatchExpand_X4, MSTr.py:212-227) + 1x1 conv to classes (:288-289) on the expand
     output e [B, H*W, 1024] -> NCHW logits.  One kernel each way; no [pixels, 64] tensor is written in either direction."""

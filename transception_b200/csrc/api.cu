@@ -2472,4 +2472,13 @@ int tcx_final_head_bwd(const float* e, const float* dlogits, const float* lnw, c
   return 0;
 }
 
+// ---- training row of the stem (MSTr.py:299-304): the patch matrix of the 7x7 / 4 conv, needed only by its weight gradient
+// (dW = dy^T A through tcx_linear_bwd); the forward is tcx_patch_embed_ln_fwd with lnw = lnb = NULL (conv output, no LayerNorm) ----
+int tcx_patch_im2row_fwd(const float* x, int B, int Cin, int H, int W, float* patches, int Kp, void* stream) {
+  TCX_REQUIRE(x && patches, "patch_im2row: null pointer");
+  TCX_REQUIRE(Cin == 1 || Cin == 3, "patch_im2row: Cin must be 1 or 3 (got %d)", Cin);
+  const long long plane = (long long)H * W;
+  return launch_patch_im2row(x, Cin * plane, Cin == 1 ? 0 : plane, B, H, W, Kp, patches, S(stream));
+}
+
 }  // extern "C"

@@ -86,6 +86,12 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
   const int oy = oy0 + py, ox = ox0 + px;
   if (oy < Ho && ox < Wo) {
     float* __restrict__ o = out + (((long long)b * Ho + oy) * Wo + ox) * 64 + cg * 16;
+    if (!lnw) {        // training row: the conv output itself (the LayerNorm is its own autograd node)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        reinterpret_cast<float4*>(o)[j] = make_float4(acc[j * 4], acc[j * 4 + 1], acc[j * 4 + 2], acc[j * 4 + 3]);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       float4 r;
@@ -97,6 +103,24 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
       reinterpret_cast<float4*>(o)[j] = r;
     }
   }
+}
+
+// patches of the stem conv for its weight gradient: A[(b, oy, ox)][(ci, ky, kx)], row pitch Kp >= 147 (zero beyond 147 and
+// outside the image); xs_c = 0: the grey plane stands for all three input channels (MSTr.py:2828-2829)
+__global__ void __launch_bounds__(256) patch_im2row_kernel(const float* __restrict__ x, long long xs_b, long long xs_c, int Hin, int Win,
+                                                           int Ho, int Wo, int Kp, long long total, float* __restrict__ A) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % Kp);
+  const long long r = idx / Kp;
+  const int ox = (int)(r % Wo), oy = (int)((r / Wo) % Ho), b = (int)(r / ((long long)Wo * Ho));
+  float v = 0.f;
+  if (k < 147) {
+    const int ci = k / 49, t = k - ci * 49, ky = t / 7, kx = t - ky * 7;
+    const int gy = oy * PE_S - 3 + ky, gx = ox * PE_S - 3 + kx;
+    if (gy >= 0 && gy < Hin && gx >= 0 && gx < Win) v = x[(long long)b * xs_b + ci * xs_c + (long long)gy * Win + gx];
+  }
+  A[idx] = v;
 }
 
 // =====================================================================================
@@ -631,6 +655,15 @@ int launch_patch_embed_ln(const float* x, long long xs_b, long long xs_c, int B,
   if (grey) tcx_launch_pdl(patch_embed_ln_kernel<1>, grid, dim3(256), smem, st, x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);
   else tcx_launch_pdl(patch_embed_ln_kernel<3>, grid, dim3(256), smem, st, x, xs_b, xs_c, Hin, Win, w, bias, lnw, lnb, eps, Ho, Wo, out);
   return tcx_check_launch("patch_embed_ln");
+}
+
+int launch_patch_im2row(const float* x, long long xs_b, long long xs_c, int B, int Hin, int Win, int Kp, float* A, cudaStream_t st) {
+  const int Ho = (Hin + 6 - 7) / 4 + 1, Wo = (Win + 6 - 7) / 4 + 1;
+  const long long total = (long long)B * Ho * Wo * Kp;
+  TCX_REQUIRE(Kp >= 147, "patch_im2row: row pitch %d < 147", Kp);
+  if (total == 0) return 0;
+  patch_im2row_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, xs_b, xs_c, Hin, Win, Ho, Wo, Kp, total, A);
+  return tcx_check_launch("patch_im2row");
 }
 
 int launch_regroup(const RegroupArgs& a, cudaStream_t st) {

@@ -4,6 +4,9 @@
 int launch_patch_embed_ln(const float* x, long long xs_b, long long xs_c, int B, int Hin, int Win, const float* w,
                           const float* bias, const float* lnw, const float* lnb, float eps, float* out, cudaStream_t st);
 
+// lnw == null: the conv output without the LayerNorm.  launch_patch_im2row: the conv's patch matrix [B*Ho*Wo][Kp] (Kp >= 147)
+int launch_patch_im2row(const float* x, long long xs_b, long long xs_c, int B, int Hin, int Win, int Kp, float* A, cudaStream_t st);
+
 struct RegroupArgs {
   const float* src[4];   // NHWC maps, dense
   float* dst;            // [B][ntok][64]

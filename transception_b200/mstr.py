@@ -332,9 +332,12 @@ class OverlapPatchEmbeddings(nn.Module):
         H = (x.shape[2] + 2 * p - k) // s + 1
         W = (x.shape[3] + 2 * p - k) // s + 1
         if _recording(x, self.proj.weight):
-            # training row (MSTr.py:299-304): the 7x7/4 conv is a patch gather (F.unfold: a copy) + Linear node; K = Cin*49
-            # is zero-padded to a multiple of 4 to keep 16-byte row pitches for the gradient GEMMs
+            # training row (MSTr.py:299-304): conv node (fused stem kernel; the patch matrix is built only for the weight
+            # gradient) + LayerNorm node
             w = self.proj.weight
+            if tuple(w.shape) == (64, 3, 7, 7) and s == 4 and p == 3 and x.shape[1] in (1, 3) and not x.requires_grad:
+                y = tcx_autograd.patch_embed_conv(x, w, self.proj.bias)
+                return tcx_autograd.layernorm(y, self.norm.weight, self.norm.bias, self.norm.eps), H, W
             if x.shape[1] == 1 and w.shape[1] == 3:
                 x = x.repeat(1, 3, 1, 1)                      # MSTr.py:2828-2829
             patches = torch.nn.functional.unfold(x, k, padding=p, stride=s).transpose(1, 2)

@@ -75,6 +75,7 @@ _PROTOS = {
     "tcx_iff_coordatt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_iff_coordatt_fwd": (_i, [_pp, _pp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_regroup_fwd": (_i, [_pp, _vp, _i, _i, _vp]),
+    "tcx_patch_im2row_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "tcx_final_head_train_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "tcx_final_head_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "tcx_final_head_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -437,6 +438,35 @@ def patch_embed_ln(x, w, b, stride, padding, lnw, lnb, eps):
     _chk(lib.tcx_patch_embed_ln_fwd(_ptr(x), B, Cin, H, W, _ptr(_d(w)), _ptr(_d(b)), _ptr(_d(lnw)), _ptr(_d(lnb)),
                                     eps, _ptr(out), _stream()))
     return out
+
+
+def patch_embed_conv(x, w, b):
+    """The stem conv alone (no LayerNorm): [B, Ho*Wo, 64] tokens."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    if tuple(w.shape) != (64, 3, 7, 7):
+        raise NotImplementedError("patch_embed_conv is built for the stage-1 stem (3->64, 7x7, stride 4, pad 3)")
+    Ho, Wo = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+    out = torch.empty((B, Ho * Wo, 64), device=x.device, dtype=x.dtype)
+    _chk(lib.tcx_patch_embed_ln_fwd(_ptr(x), B, Cin, H, W, _ptr(_d(w)), _ptr(_d(b)), None, None, 0.0, _ptr(out), _stream()))
+    return out
+
+
+def patch_embed_conv_bwd(x, w, dy):
+    """(dw [64, 3, 7, 7], db [64]) of patch_embed_conv: one im2row launch + the Linear weight-gradient kernel."""
+    require_cuda(x)
+    lib = load_library()
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    Ho, Wo = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+    Kp = 148
+    patches = torch.empty((B * Ho * Wo, Kp), device=x.device, dtype=torch.float32)
+    _chk(lib.tcx_patch_im2row_fwd(_ptr(x), B, Cin, H, W, _ptr(patches), Kp, _stream()))
+    wpad = torch.empty((64, Kp), device=x.device, dtype=torch.float32)       # shape only: dx is not requested
+    _, dwp, db = linear_bwd(patches, wpad, dy.reshape(-1, 64), need_dx=False)
+    return dwp[:, :147].reshape(w.shape), db
 
 
 def dwconv_tokens(x, H, W, w, b, add_input):
