@@ -140,6 +140,67 @@ __global__ void __launch_bounds__(256) dwk3_kernel(const float* __restrict__ x, 
   if (ADD) y[p * ldy + c] += acc; else y[p * ldy + c] = acc;
 }
 
+// ---- row-sweep form of dwk3_kernel.  Above, every output element loads its K*K taps AND its K*K filter values (the latter at a
+// stride of K*K floats across the lanes of a warp: 32 cache lines per load instruction).  Here a thread owns (channel, image row):
+// the channel's filter sits in registers, a K x K register window of x slides along the row, so an output costs K loads.
+constexpr int SC = 32, SL = 8;
+template <int K, bool FLIP, bool ADD>
+__device__ __forceinline__ void dwk_sweep_row(const float* __restrict__ x, int ldx, const float* __restrict__ wc, float bias,
+                                              float* __restrict__ y, int ldy, int H, int W, int c, int b, int py) {
+  float wr[K][K], win[K][K];
+#pragma unroll
+  for (int a = 0; a < K; a++)
+#pragma unroll
+    for (int j = 0; j < K; j++) wr[a][j] = __ldg(wc + (FLIP ? (K - 1 - a) * K + (K - 1 - j) : a * K + j));
+  const float* xr[K];
+  bool rv[K];
+#pragma unroll
+  for (int a = 0; a < K; a++) {
+    const int yy = py + a - K / 2;
+    rv[a] = yy >= 0 && yy < H;
+    xr[a] = x + ((size_t)(b * H + (rv[a] ? yy : py)) * W) * ldx + c;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const int xx = j - K / 2;
+      win[a][j] = (rv[a] && xx >= 0 && xx < W) ? xr[a][(size_t)xx * ldx] : 0.f;
+    }
+  }
+  float* yr = y + ((size_t)(b * H + py) * W) * ldy + c;
+  for (int px = 0; px < W; px++) {
+    const int xn = px + 1 + K / 2;
+    float nx[K];
+#pragma unroll
+    for (int a = 0; a < K; a++) nx[a] = (rv[a] && xn < W) ? xr[a][(size_t)xn * ldx] : 0.f;
+    float acc = bias;
+#pragma unroll
+    for (int a = 0; a < K; a++)
+#pragma unroll
+      for (int j = 0; j < K; j++) acc = fmaf(wr[a][j], win[a][j], acc);
+    if (ADD) yr[(size_t)px * ldy] += acc; else yr[(size_t)px * ldy] = acc;
+#pragma unroll
+    for (int a = 0; a < K; a++) {
+#pragma unroll
+      for (int j = 0; j + 1 < K; j++) win[a][j] = win[a][j + 1];
+      win[a][K - 1] = nx[a];
+    }
+  }
+}
+template <bool FLIP, bool ADD>
+__global__ void __launch_bounds__(SC * SL) dwk3_sweep_kernel(const float* __restrict__ x, int ldx, Crpe3 f, float* __restrict__ y, int ldy,
+                                                             int B, int H, int W, int C) {
+  const int c = blockIdx.y * SC + threadIdx.x;
+  const int row = blockIdx.x * SL + threadIdx.y;
+  if (c >= C || row >= B * H) return;
+  const int b = row / H, py = row - b * H;
+  if (c < f.c1) {
+    dwk_sweep_row<3, FLIP, ADD>(x, ldx, f.w[0] + (size_t)c * 9, (f.b[0] && !FLIP) ? f.b[0][c] : 0.f, y, ldy, H, W, c, b, py);
+  } else if (c < f.c2) {
+    dwk_sweep_row<5, FLIP, ADD>(x, ldx, f.w[1] + (size_t)(c - f.c1) * 25, (f.b[1] && !FLIP) ? f.b[1][c - f.c1] : 0.f, y, ldy, H, W, c, b, py);
+  } else {
+    dwk_sweep_row<7, FLIP, ADD>(x, ldx, f.w[2] + (size_t)(c - f.c2) * 49, (f.b[2] && !FLIP) ? f.b[2][c - f.c2] : 0.f, y, ldy, H, W, c, b, py);
+  }
+}
+
 template <int K>
 __device__ __forceinline__ void dwk_wgrad_rows(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx, int H, int W,
                                                int c, long long r0, long long r1, float (&acc)[50]) {
@@ -416,11 +477,11 @@ int launch_bwd_dwk3(const float* x, int ldx, const float* const* w, const float*
   Crpe3 f;
   for (int j = 0; j < 3; j++) { f.w[j] = w[j]; f.b[j] = b ? b[j] : nullptr; }
   f.c1 = c1; f.c2 = c2;
-  const unsigned grid = (unsigned)((total + 255) / 256);
-  if (!flip && !add) dwk3_kernel<false, false><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
-  else if (!flip && add) dwk3_kernel<false, true><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
-  else if (flip && !add) dwk3_kernel<true, false><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
-  else dwk3_kernel<true, true><<<grid, 256, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  const dim3 grid(cdiv(B * H, SL), cdiv(C, SC)), block(SC, SL);
+  if (!flip && !add) dwk3_sweep_kernel<false, false><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  else if (!flip && add) dwk3_sweep_kernel<false, true><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  else if (flip && !add) dwk3_sweep_kernel<true, false><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  else dwk3_sweep_kernel<true, true><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
   return tcx_check_launch("bwd_dwk3");
 }
 size_t bwd_dwk3_wgrad_part_floats(long long M, int C) { return (size_t)bwd_red_blocks(M) * 50 * C; }

@@ -741,11 +741,24 @@ class MSViT(nn.Module):
             t = ops.layernorm(t, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         cur = t.reshape(B, H, W, -1)
         outs = [cur]
+        cut = getattr(self, '_grad_cut', None)
         for s in (2, 3, 4):
             stacked = getattr(self, 'patch_embed_stage%d' % s).nhwc(cur)
             cur = getattr(self, 'mhca_stage%d' % s).nhwc(stacked)
             outs.append(cur)
+            if s == 2 and cut is not None and torch.is_grad_enabled() and cur.requires_grad:
+                # data-parallel training (runtime.TrainStepGraph): the backward is run in two pieces so that the gradient
+                # all-reduce of everything behind this point overlaps the backward of stages 1-2.  The maps that cross the
+                # cut continue as leaves; the runner feeds their gradients back into the originals (EARLY_MODULES below).
+                origs = list(outs)
+                outs = [o.detach().requires_grad_(True) for o in origs]
+                cur = outs[-1]
+                del cut[:]
+                cut.extend(zip(origs, outs))
         return outs
+
+    # the modules in front of the cut above (their gradients are complete only after the second backward piece)
+    EARLY_MODULES = ('patch_embed1', 'block1', 'norm1', 'patch_embed_stage2', 'mhca_stage2')
 
     def forward(self, x):
         return [_as_nchw(m) for m in self.nhwc(x)]

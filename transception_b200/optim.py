@@ -34,10 +34,22 @@ class FusedSGD(torch.optim.Optimizer):
         self.max_norm = max_norm
         self._tables, self._lr_t, self._lr_seen = {}, {}, {}
         self.norm_coef = None           # device [norm, coef] of the last step (max_norm set)
+        self._tail_ids = None           # set_bucket_tail: parameters placed at the END of the flat bucket
+
+    def set_bucket_tail(self, params):
+        """Order the flat gradient bucket as [all other parameters | ``params``] (each part in registration order).  The data-parallel
+        runner all-reduces the head while the backward of the tail's layers is still running (``gather_grads(part)``)."""
+        self._tail_ids = {id(p) for p in params}
+        self._tables.clear()
 
     # ---- tables ---------------------------------------------------------------------------------------------------------------
     def _group_table(self, gi, group):
         used = [p for p in group["params"] if p.grad is not None]
+        n_head = len(used)
+        if self._tail_ids:
+            head = [p for p in used if id(p) not in self._tail_ids]
+            used = head + [p for p in used if id(p) in self._tail_ids]
+            n_head = len(head)
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in used)
         tab = self._tables.get(gi)
         if tab is not None and tab["key"] == key:
@@ -74,9 +86,12 @@ class FusedSGD(torch.optim.Optimizer):
                 special.append(p)                       # K-permuted patchify-conv copy: refreshed by its own conversion kernel
             else:
                 w16.append(pc[0].data_ptr())
-        blocks = []
+        blocks, head_blocks = [], 0
         for t, n in enumerate(numel):
             blocks.extend((t, c) for c in range((n + chunk - 1) // chunk))
+            if t == n_head - 1:
+                head_blocks = len(blocks)
+        head_elems = offs[n_head] if n_head < len(used) else total
 
         def i64(vals):
             return torch.tensor(vals, dtype=torch.int64).to(dev)
@@ -86,6 +101,7 @@ class FusedSGD(torch.optim.Optimizer):
             "gflat": i64([flat.data_ptr() + 4 * o for o in offs]), "buf": i64([b.data_ptr() for b in bufs]), "w16": i64(w16),
             "numel": i64(numel), "offs": i64(offs), "blocks": torch.tensor(blocks, dtype=torch.int32).to(dev),
             "nblocks": len(blocks), "part": torch.empty(len(blocks), dtype=torch.float32, device=dev),
+            "head_blocks": head_blocks, "head_elems": head_elems,
             "keep": (bufs, [p.grad for p in used]),
         }
         if gi not in self._lr_t:
@@ -102,17 +118,25 @@ class FusedSGD(torch.optim.Optimizer):
                 self._lr_seen[gi] = float(group["lr"])
 
     # ---- data-parallel bucket ---------------------------------------------------------------------------------------------------
-    def gather_grads(self):
-        """Gather every used gradient into the flat bucket (one launch) and return it: the all-reduce operand."""
+    def gather_grads(self, part=None):
+        """Gather the used gradients into the flat bucket (one launch) and return the slice written: the all-reduce operand.
+        ``part`` = 0 / 1: only the head / the tail of the bucket (``set_bucket_tail``)."""
         lib = ops.load_library()
         if len(self.param_groups) != 1:
             raise NotImplementedError("FusedSGD.gather_grads needs a single parameter group")
         tab = self._group_table(0, self.param_groups[0])
         if tab is None:
             return None
-        ops._chk(lib.tcx_mt_gather(tab["g"].data_ptr(), tab["numel"].data_ptr(), tab["offs"].data_ptr(), tab["blocks"].data_ptr(),
-                                   tab["nblocks"], tab["flat"].data_ptr(), ops._stream()))
-        return tab["flat"]
+        b0, b1 = 0, tab["nblocks"]
+        e0, e1 = 0, tab["total"]
+        if part == 0:
+            b1, e1 = tab["head_blocks"], tab["head_elems"]
+        elif part == 1:
+            b0, e0 = tab["head_blocks"], tab["head_elems"]
+        if b1 > b0:
+            ops._chk(lib.tcx_mt_gather(tab["g"].data_ptr(), tab["numel"].data_ptr(), tab["offs"].data_ptr(),
+                                       tab["blocks"].data_ptr() + 8 * b0, b1 - b0, tab["flat"].data_ptr(), ops._stream()))
+        return tab["flat"][e0:e1]
 
     # ---- step -------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()

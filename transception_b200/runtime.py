@@ -109,9 +109,11 @@ class TrainStepGraph:
     capture from the static gradient addresses of the first graph:
 
     * graph A: forward + loss + backward (the gradient tensors are allocated inside this capture and keep their addresses);
-    * with ``transception_b200.optim.FusedSGD``: graph B = the fused clip + SGD update (single process), or graph B = gather the
-      gradients into the optimizer's flat bucket, an eager NCCL all-reduce (average) of that bucket, graph C = the update read
-      from the bucket (``torch.distributed`` initialised, world > 1).  The fused update also refreshes the fp16 GEMM copies the
+    * with ``transception_b200.optim.FusedSGD``: graph B = the fused clip + SGD update (single process).  With
+      ``torch.distributed`` initialised (world > 1) the backward is cut between encoder stages 2 and 3 (``MSViT._grad_cut``):
+      graph A1 = forward + loss + backward down to the cut (decoder, bridge, stages 4 and 3: 98 % of the gradient elements),
+      gathered into the head of the optimizer's flat bucket and all-reduced (NCCL, average) ASYNCHRONOUSLY while graph A2 = the
+      backward of stages 2 and 1 runs; the small tail of the bucket follows, then graph C = the update read from the bucket.  The fused update also refreshes the fp16 GEMM copies the
       forward reads, and takes the learning rate from a device scalar: assign ``param_group['lr']`` as ``trainer.py:151-153``
       does and call ``step()`` — no re-capture;
     * with any other ``torch.optim`` optimizer: graph B = ``clip_grad_norm_`` + ``optimizer.step()`` as written by the caller
@@ -143,6 +145,12 @@ class TrainStepGraph:
         self.max_norm = max_norm
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket = GradBucket(model.parameters())
+        # split backward / overlapped all-reduce: needs the fused optimizer's bucket and a model with the cut (MSViT)
+        bb = getattr(model, "backbone", None)
+        self.overlap = self.fused and self.world > 1 and bb is not None and hasattr(bb, "EARLY_MODULES")
+        if self.overlap:
+            early = [p for name in bb.EARLY_MODULES for p in getattr(bb, name).parameters()]
+            optimizer.set_bucket_tail(early)
         self.x = torch.zeros((batch, in_ch, size, size), device=self.device, dtype=torch.float32)
         self.labels = torch.zeros((batch, size, size), device=self.device, dtype=label_dtype)
         self.loss = torch.zeros((), device=self.device)
@@ -163,6 +171,37 @@ class TrainStepGraph:
         loss = self.criterion(self.model(self.x), self.labels)
         loss.backward()
         self.loss.copy_(loss.detach())
+
+    def _fwd_bwd1(self):
+        """Forward + loss + the backward down to the cut between encoder stages 2 and 3."""
+        bb = self.model.backbone
+        bb._grad_cut = []
+        try:
+            self.optimizer.zero_grad(set_to_none=True)
+            loss = self.criterion(self.model(self.x), self.labels)
+            loss.backward()
+            self._cut = list(bb._grad_cut)
+        finally:
+            bb._grad_cut = None
+        self.loss.copy_(loss.detach())
+
+    def _bwd2(self):
+        """The rest of the backward: the gradients that arrived at the cut continue into stages 2 and 1."""
+        origs = [o for o, _ in self._cut]
+        grads = [leaf.grad for _, leaf in self._cut]
+        self._cut = None
+        torch.autograd.backward(origs, grads)
+
+    def _reduce(self, flat, async_op=False):
+        import torch.distributed as dist
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        if async_op:
+            w.wait()
+            w = None
+        flat.mul_(1.0 / self.world)
+        return w
 
     def _allreduce(self):
         """Average the gradients over the ranks: the optimizer's flat bucket (fused) or shard.GradBucket."""
@@ -196,7 +235,11 @@ class TrainStepGraph:
             # reading and writing the ones they were captured with
             raise RuntimeError("TrainStepGraph: eager steps after capture break the graphs' static gradient buffers; "
                                "use step() / replay(), or recapture()")
-        self._fwd_bwd()
+        if self.overlap:
+            self._fwd_bwd1()
+            self._bwd2()
+        else:
+            self._fwd_bwd()
         if self.world > 1 and self.fused:
             self._gather()
         self._allreduce()
@@ -232,6 +275,8 @@ class TrainStepGraph:
             self.eager_step()
         self.steps_done += max(self._warmup, 2)
         torch.cuda.synchronize(self.device)
+        if self.overlap:
+            return self._recapture_overlap()
         ga = self._capture(self._fwd_bwd, prerun=False)
         ga.replay()
         graphs = [ga]
@@ -255,9 +300,77 @@ class TrainStepGraph:
             ops.bump_raw_generation()
         self._captured = True
 
+    def _recapture_overlap(self):
+        """world > 1 with the fused optimizer: A1 (forward + loss + backward to the cut), A2 (backward of stages 2-1), the two
+        bucket gathers and the update as five graphs; see ``replay``."""
+        from . import ops
+        a1 = self._capture(self._fwd_bwd1, prerun=False)
+        a2 = self._capture(self._bwd2, prerun=False)       # continues the autograd graph recorded (not executed) by A1's capture
+        a1.replay()
+        a2.replay()                                         # the static gradient tensors of both pieces hold real values now
+        for gi, group in enumerate(self.optimizer.param_groups):
+            self.optimizer._group_table(gi, group)
+        g1 = self._capture(lambda: setattr(self, "_flat_head", self.optimizer.gather_grads(0)), prerun=False)
+        g2 = self._capture(lambda: setattr(self, "_flat_tail", self.optimizer.gather_grads(1)), prerun=False)
+        g1.replay()
+        g2.replay()
+        self._reduce(self._flat_head)
+        self._reduce(self._flat_tail)
+        gu = self._capture(self._update, prerun=False)
+        gu.replay()
+        self._graphs = [a1, g1, a2, g2, gu]
+        self.steps_done += 1
+        ops.bump_raw_generation()
+        self._captured = True
+
+    def _replay_overlap(self):
+        a1, g1, a2, g2, gu = self._graphs
+        self.optimizer.sync_lr()
+        a1.replay()
+        g1.replay()
+        work = self._reduce(self._flat_head, async_op=True)      # on the collective's stream, behind A1 + the head gather
+        a2.replay()                                              # stages 2-1 backward runs beside it
+        g2.replay()
+        self._reduce(self._flat_tail)
+        if work is not None:
+            work.wait()                                          # the current stream waits for the head all-reduce
+        gu.replay()
+
+    # the pieces of one data-parallel step, for checks that look at the gradients between them (bench.py)
+    def replay_backward(self):
+        """Forward + loss + the whole backward: the static ``p.grad`` tensors hold this rank's own gradients afterwards."""
+        if self.overlap:
+            self._graphs[0].replay()
+            self._graphs[2].replay()
+        else:
+            self._graphs[0].replay()
+
+    def replay_reduce(self):
+        """Gather into the flat bucket and average it over the ranks (no overlap); returns the bucket."""
+        if self.overlap:
+            self._graphs[1].replay()
+            self._graphs[3].replay()
+            self._reduce(self._flat_head)
+            self._reduce(self._flat_tail)
+        elif self.world > 1 and self.fused:
+            self._graphs[1].replay()
+            self._allreduce()
+        return self.optimizer._tables[0]["flat"] if self.fused else None
+
+    def replay_update(self):
+        from . import ops
+        self._graphs[-1].replay()
+        if self.fused:
+            ops.bump_raw_generation()
+
     def replay(self):
         """One training step on the batch currently in ``self.x`` / ``self.labels``."""
         from . import ops
+        if self.overlap:
+            self._replay_overlap()
+            ops.bump_raw_generation()
+            self.steps_done += 1
+            return
         if self.fused:
             self.optimizer.sync_lr()         # a changed param_group['lr'] reaches the device scalar the update graph reads
         self._graphs[0].replay()
