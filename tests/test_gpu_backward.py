@@ -629,7 +629,7 @@ def test_whole_model_train_step(cuda_lib, bn_train):
     loss = CeDiceLoss(9)(logits, labels.cuda())
     assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
     loss.backward()
-    worst, n_grad, n_none = 1.0, 0, 0
+    worst, worst_rel, n_grad, n_none, e2, r2 = 1.0, 0.0, 0, 0, 0.0, 0.0
     for k, p in mg.named_parameters():
         refs = [sd[a].grad for a in alias[k] if sd[a].grad is not None]
         if not refs:
@@ -641,13 +641,21 @@ def test_whole_model_train_step(cuda_lib, bn_train):
         got = p.grad.float().cpu()
         assert torch.isfinite(got).all(), k
         den = ref.norm().item()
+        err = (got - ref).norm().item()
+        e2 += err * err
+        r2 += den * den
         if den > 1e-7:
             cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
             worst = min(worst, cos)
+            worst_rel = max(worst_rel, err / den)
             assert cos >= 0.99, "%s: cosine %.4f (|ref| %.3e)" % (k, cos, den)
+            # per tensor relative L2: fp16 / TF32 tensor-core operands against fp32 autograd
+            assert err <= 0.1 * den, "%s: relative L2 %.3e (|ref| %.3e)" % (k, err / den, den)
         n_grad += 1
-    print("train step: loss %.6f (oracle %.6f), %d parameters with gradient (worst cosine %.5f), %d dead" %
-          (loss.item(), loss_ref.item(), n_grad, worst, n_none))
+    total_rel = (e2 / r2) ** 0.5
+    print("train step: loss %.6f (oracle %.6f), %d parameters with gradient (worst cosine %.5f, worst relative L2 %.3e, "
+          "relative L2 of the whole gradient %.3e), %d dead" % (loss.item(), loss_ref.item(), n_grad, worst, worst_rel, total_rel, n_none))
+    assert total_rel <= 2e-2, "relative L2 of the whole gradient %.3e" % total_rel
     assert n_grad > 1000 and n_none > 100
 
 

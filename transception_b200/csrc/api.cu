@@ -2285,14 +2285,15 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
     TCX_TRY(run_linear_bwd(nullptr, 0, F(p[6]), dy, da, nullptr, nullptr, M, C, C4, lin, st));               // da = dy W2
     TCX_TRY(launch_ln_bwd_fused(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, a32, nullptr, M, C4, part_ln, st));
     float* dh = da;
-    TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part, st));
+    int dw_nblk = 0;
+    TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part, st, &dw_nblk));
     if (aux) {
       TCX_REQUIRE(cudaEventRecord(aux->fork, st) == cudaSuccess && cudaStreamWaitEvent(sa, aux->fork, 0) == cudaSuccess,
                   "mixffn_skip_bwd: fork failed");
     }
     TCX_TRY(run_linear_bwd(a32, 0, F(p[6]), dy, nullptr, G(6), G(7), M, C, C4, lin2, sa));                   // dW2 = dy^T a, db2
     TCX_TRY(launch_bwd_ln_fold(part_ln, ln_bwd_fused_blocks(M), C4, G(4), G(5), sa));
-    TCX_TRY(launch_bwd_dw_fold(part, dw_bwd_fused_blocks(M, C4), C4, G(2), G(3), sa));
+    TCX_TRY(launch_bwd_dw_fold(part, dw_nblk, C4, G(2), G(3), sa));
     // fc1: dxn = dh W1 on the main stream, dW1 = dh^T xn beside it
     const void* xn = xn32 ? (const void*)xn32 : (const void*)s.xn16;
     TCX_TRY(run_linear_bwd(xn, xn32 ? 0 : 1, F(p[0]), dh, dxn, G(0), G(1), M, C4, C, lin, st));
@@ -2303,14 +2304,15 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
   TCX_TRY(run_linear_bwd(s.a16, 1, F(p[6]), dy, da, G(6), G(7), M, C, C4, lin, st));
   // GELU(LayerNorm(u))
   TCX_TRY(launch_bwd_ln(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, G(4), G(5), M, C4, stats, part, st));
-  // u = dw3x3(h) + b + h
+  // u = dw3x3(h) + b + h: input gradient and the filter / bias sums in one pass (row-sweep kernel), then the fold
   float* dh = da;
-  TCX_TRY(launch_bwd_flip9(F(p[2]), wflip, C4, st));
   {
-    DwGroup g{du, wflip, nullptr, dh};
-    TCX_TRY(launch_dwconv3x3(&g, 1, B, H, W, C4, 1, DW_ADD_INPUT, BnParams{}, st));
+    (void)wflip;
+    int dw_nblk = 0;
+    float* part_dw = part + 2 * (size_t)bwd_red_blocks(M) * C4;       // behind the LayerNorm partials still being folded
+    TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part_dw, st, &dw_nblk));
+    TCX_TRY(launch_bwd_dw_fold(part_dw, dw_nblk, C4, G(2), G(3), st));
   }
-  TCX_TRY(launch_bwd_dwconv_wgrad(du, s.h16, B, H, W, C4, G(2), G(3), part, st));
   // fc1: xn16 [M][C] -> h [M][C4]
   return run_linear_bwd(s.xn16, 1, F(p[0]), dh, dxn, G(0), G(1), M, C4, C, lin, st);
 }

@@ -63,7 +63,7 @@ int launch_bwd_ln_fold(const float* part, int nblk, int C, float* dgamma, float*
 // launch_bwd_dw_fold); h is the fp16 fc1 output
 int dw_bwd_fused_blocks(long long M, int C);
 int launch_dw_bwd_fused(const float* du, const __half* h, const float* w, float* dh, int B, int H, int W, int C, float* part,
-                        cudaStream_t st);
+                        cudaStream_t st, int* nblk_out);
 int launch_bwd_dw_fold(const float* part, int nblk, int C, float* dw, float* db, cudaStream_t st);
 
 // depthwise 3x3 (stride 1, pad 1, DWConv MSTr.py:26-31) weight / bias gradient:

@@ -299,6 +299,94 @@ __global__ void __launch_bounds__(DB_CT * DB_PL, 2) dw_bwd_fused_kernel(const fl
   }
 }
 
+// ---- row-sweep form of dw_bwd_fused_kernel: a thread owns (2 channels, image row) and slides 3x3 register windows of du and h
+// along the row — 6 loads per pixel instead of 17, the channel's filter in registers; (32 channel pairs x 8 rows) per block, the
+// block's (9 + 1) x 64 partial sums folded over its 8 row lanes in lane order.  Same outputs and partial layout as above.
+constexpr int DS_C = 32, DS_L = 8;
+__global__ void __launch_bounds__(DS_C * DS_L) dw_bwd_sweep_kernel(const float* __restrict__ du, const __half* __restrict__ h,
+                                                                   const float* __restrict__ w, float* __restrict__ dh, int B, int H, int W,
+                                                                   int C, int rows, float* __restrict__ part) {
+  __shared__ float sm[DS_L][10][DS_C * 2];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = (blockIdx.y * DS_C + tx) * 2;
+  const bool cl = c < C;                       // C is even
+  const int nrow = B * H;
+  const int row0 = blockIdx.x * rows;
+  const int row1 = row0 + rows < nrow ? row0 + rows : nrow;
+  float2 wt[9];
+  float2 acc[10];
+#pragma unroll
+  for (int t = 0; t < 9; t++) wt[t] = cl ? make_float2(__ldg(w + (size_t)c * 9 + t), __ldg(w + (size_t)(c + 1) * 9 + t)) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 10; t++) acc[t] = make_float2(0.f, 0.f);
+  if (cl) {
+    for (int row = row0 + ty; row < row1; row += DS_L) {
+      const int b = row / H, py = row - b * H;
+      const float* gr[3];
+      const __half* hr[3];
+      bool rv[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const int yy = py + a - 1;
+        rv[a] = yy >= 0 && yy < H;
+        const size_t base = ((size_t)(b * H + (rv[a] ? yy : py)) * W) * C + c;
+        gr[a] = du + base;
+        hr[a] = h + base;
+      }
+      auto ldg2 = [&](int a, int xx) {
+        return (rv[a] && xx >= 0 && xx < W) ? *reinterpret_cast<const float2*>(gr[a] + (size_t)xx * C) : make_float2(0.f, 0.f);
+      };
+      auto ldh2 = [&](int a, int xx) {
+        return (rv[a] && xx >= 0 && xx < W) ? __half22float2(*reinterpret_cast<const __half2*>(hr[a] + (size_t)xx * C)) : make_float2(0.f, 0.f);
+      };
+      float2 gd[3][3], hh[3][3];               // [row a][col j] = value at (py + a - 1, px + j - 1)
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        gd[a][0] = make_float2(0.f, 0.f); hh[a][0] = make_float2(0.f, 0.f);
+        gd[a][1] = ldg2(a, 0); hh[a][1] = ldh2(a, 0);
+        gd[a][2] = ldg2(a, 1); hh[a][2] = ldh2(a, 1);
+      }
+      float* orow = dh + ((size_t)row * W) * C + c;
+      for (int px = 0; px < W; px++) {
+        float2 ng[3], nh[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) { ng[a] = ldg2(a, px + 2); nh[a] = ldh2(a, px + 2); }
+        const float2 g = gd[1][1];
+        float2 o = g;
+        acc[9].x += g.x; acc[9].y += g.y;
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+          for (int kx = 0; kx < 3; kx++) {
+            const int t = ky * 3 + kx;
+            const float2 gn = gd[2 - ky][2 - kx];          // du at p - off(t)
+            o.x = fmaf(wt[t].x, gn.x, o.x); o.y = fmaf(wt[t].y, gn.y, o.y);
+            acc[t].x = fmaf(g.x, hh[ky][kx].x, acc[t].x);  // h at p + off(t)
+            acc[t].y = fmaf(g.y, hh[ky][kx].y, acc[t].y);
+          }
+        *reinterpret_cast<float2*>(orow + (size_t)px * C) = o;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          gd[a][0] = gd[a][1]; gd[a][1] = gd[a][2]; gd[a][2] = ng[a];
+          hh[a][0] = hh[a][1]; hh[a][1] = hh[a][2]; hh[a][2] = nh[a];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 10; t++) { sm[ty][t][tx * 2] = acc[t].x; sm[ty][t][tx * 2 + 1] = acc[t].y; }
+  __syncthreads();
+  for (int i = ty * DS_C + tx; i < 10 * DS_C * 2; i += DS_C * DS_L) {
+    const int t = i / (DS_C * 2), cc = i - t * (DS_C * 2);
+    const int col = blockIdx.y * DS_C * 2 + cc;
+    if (col >= C) continue;
+    float a = sm[0][t][cc];
+#pragma unroll
+    for (int l = 1; l < DS_L; l++) a += sm[l][t][cc];
+    part[((size_t)blockIdx.x * 10 + t) * C + col] = a;
+  }
+}
+
 __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n4) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
@@ -348,25 +436,34 @@ int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, con
   return tcx_check_launch("ln_bwd_fused");
 }
 
+// partial blocks of launch_dw_bwd_fused for a B x H x W map: one block per DS_L image rows, more rows per block only when that
+// would exceed `cap` blocks.  (M, C) sizing form kept for the workspace formulas: an upper bound for any H, W with H*W*B = M, W >= 2.
+static int dw_sweep_rows(int nrow, int cap) {
+  int rows = DS_L;
+  while ((nrow + rows - 1) / rows > cap) rows += DS_L;
+  return rows;
+}
+constexpr int DW_SWEEP_MAX_BLOCKS = 1184;
 int dw_bwd_fused_blocks(long long M, int C) {
-  const int slabs = (C + DB_CT * 4 - 1) / (DB_CT * 4);
-  long long nb = (2 * 148 + slabs - 1) / slabs;                   // about two waves of blocks over all channel slabs
-  const long long maxb = (M + 4 * DB_PL - 1) / (4 * DB_PL);       // >= 4 pixels per lane
-  if (nb > maxb) nb = maxb;
+  (void)C;
+  long long nb = (M / 2 + DS_L - 1) / DS_L;            // image rows <= M / 2 for W >= 2
+  if (nb > DW_SWEEP_MAX_BLOCKS) nb = DW_SWEEP_MAX_BLOCKS;
   if (nb < 1) nb = 1;
   return (int)nb;
 }
 
-// part: 10 * dw_bwd_fused_blocks(M, C) * C floats; fold with launch_bwd_dw_fold(part, nblk, C, dw, db).
+// part: 10 * dw_bwd_fused_blocks(M, C) * C floats; fold with launch_bwd_dw_fold(part, *nblk_out, C, dw, db).
 int launch_dw_bwd_fused(const float* du, const __half* h, const float* w, float* dh, int B, int H, int W, int C, float* part,
-                        cudaStream_t st) {
+                        cudaStream_t st, int* nblk_out) {
   const long long M = (long long)B * H * W;
-  TCX_REQUIRE(C % 4 == 0 && M > 0, "dw_bwd_fused: C must be a multiple of 4 (C=%d)", C);
+  TCX_REQUIRE(C % 4 == 0 && M > 0 && M < (1ll << 31), "dw_bwd_fused: C must be a multiple of 4 (C=%d)", C);
   TCX_REQUIRE(du != dh, "dw_bwd_fused: dh may not alias du");
-  const int nblk = dw_bwd_fused_blocks(M, C);
-  const int ppb = (int)((M + nblk - 1) / nblk);
-  const dim3 grid(nblk, (C + DB_CT * 4 - 1) / (DB_CT * 4));
+  const int nrow = B * H;
+  const int rows = dw_sweep_rows(nrow, W >= 2 ? dw_bwd_fused_blocks(M, C) : 1);
+  const int nblk = (nrow + rows - 1) / rows;
+  const dim3 grid(nblk, (C + DS_C * 2 - 1) / (DS_C * 2));
   ProfScope prof("dw_bwd_fused", st, (double)M * C * 10.0);
-  dw_bwd_fused_kernel<<<grid, DB_CT * DB_PL, 0, st>>>(du, h, w, dh, B, H, W, C, ppb, part);
+  dw_bwd_sweep_kernel<<<grid, dim3(DS_C, DS_L), 0, st>>>(du, h, w, dh, B, H, W, C, rows, part);
+  if (nblk_out) *nblk_out = nblk;
   return tcx_check_launch("dw_bwd_fused");
 }

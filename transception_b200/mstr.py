@@ -991,7 +991,9 @@ class MSTransception(nn.Module):
 
     def forward(self, x):
         ops.require_cuda(x)
-        recording = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # (an nn.DataParallel replica holds its weights as plain attributes: ``parameters()`` is empty there, attribute access works)
+        recording = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                                 self.backbone.norm1.weight.requires_grad or self.decoder_0.concat_linear.weight.requires_grad)
         if recording and not self.training:
             raise NotImplementedError(
                 "transception_b200: backward through eval-mode BatchNorm (running statistics) is not built; call .train() "

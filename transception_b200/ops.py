@@ -1152,7 +1152,8 @@ def mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2
     tab = _table(params)
     gtab = (ctypes.c_void_p * 8)(*[_ptr(g) for g in grads])
     ws = _ws(lib.tcx_mixffn_skip_bwd_workspace_bytes(B, H * W, C, C4), dy)
-    _chk(lib.tcx_mixffn_skip_bwd(_ptr(dy), tab, eps, _ptr(saved), _ptr(xn.contiguous() if xn is not None else None), _ptr(dxn), gtab,
+    xn = xn.contiguous() if xn is not None else None
+    _chk(lib.tcx_mixffn_skip_bwd(_ptr(dy), tab, eps, _ptr(saved), _ptr(xn), _ptr(dxn), gtab,
                                  B, H, W, C, C4, _ptr(ws), _stream()))
     return dxn, grads
 
