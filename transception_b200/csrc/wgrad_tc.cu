@@ -19,6 +19,7 @@
 //  * optional head mask (Multi-Branch attention: only the diagonal Ch x Ch blocks of the C x C context are real) and a
 //    transposed second copy of the result for the consumers that need ctx^T.
 #include <algorithm>
+#include <mutex>
 #include <cuda_fp16.h>
 #include "bwd.cuh"
 #include "tc.cuh"
@@ -399,6 +400,34 @@ unsigned g_ticket_next = 0;
 // latency-bound), the cluster fold costs ~2.5 us and the second (HBM) level ~3 us more.  So: pick the split count that minimises
 //   waves * k-blocks-per-CTA * 0.3 us + fold overheads,   S in {1, 2, 4, 8} (one cluster) or 8 * S2 with S2 <= 16,
 // keeping tiles * S * batch within about one wave of the 148 SMs.
+// CTAs of this kernel that can be resident at once for cluster size cs (index log2 cs): a cluster needs cs free SMs inside ONE GPC, so
+// with 8 GPCs of 18-20 SMs only 16 clusters of 8 fit — 128 CTAs, not 148 (cudaOccupancyMaxActiveClusters; measured per device once).
+// A plan with more CTAs than that runs in two waves.
+static int wgrad_capacity(int cs) {
+  static int cap[64][4];                       // [device][log2 cs], 0 = not measured yet
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  const int li = cs == 1 ? 0 : (cs == 2 ? 1 : (cs == 4 ? 2 : 3));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cap[dev & 63][li];
+  if (c == 0) {
+    int n = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148 * 8); cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = 1024 + WG_RING_BYTES + WG_ONES_BYTES + WG_BM * 4 + 256;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaFuncSetAttribute(wgrad_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, wgrad_tc_kernel<4>, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = cs == 1 ? 148 : 128 / cs; }     // query failed: the B200 values
+    c = n * cs;
+  }
+  return c;
+}
+
 void wgrad_tc_plan(long long Mtok, int NL, int KL, int batch, int eb, int* S, int* Ms, int* BN, int* CS, int* S2) {
   const int bn = wg_bn(KL, eb);
   const long long tiles = (long long)cdiv(NL, WG_BM) * cdiv(KL, bn) * batch;
@@ -410,9 +439,9 @@ void wgrad_tc_plan(long long Mtok, int NL, int KL, int batch, int eb, int* S, in
     const int cs = idx < 4 ? (1 << idx) : WG_MAX_SPLIT;
     const int s2 = idx < 4 ? 1 : idx - 2;          // 2 .. WG_MAX_S2
     const int s = cs * s2;
-    const long long cap = g_tcx_max_ctas > 0 ? g_tcx_max_ctas : 160;
+    const long long cap = g_tcx_max_ctas > 0 ? g_tcx_max_ctas : wgrad_capacity(cs);
     if (s > 1 && (tiles * s > cap || (long long)(s - 1) * tokens_per(s) >= Mtok)) continue;     // one wave, no empty split
-    const long long waves = (tiles * s + (g_tcx_max_ctas > 0 ? g_tcx_max_ctas : 148) - 1) / (g_tcx_max_ctas > 0 ? g_tcx_max_ctas : 148);
+    const long long waves = (tiles * s + cap - 1) / cap;
     const double cost = (double)waves * (double)((kb_total + s - 1) / s) * 0.3 + (s > 1 ? 2.5 : 0.0) + (s2 > 1 ? 3.0 : 0.0);
     if (cost < best) { best = cost; best_cs = cs; best_s2 = s2; }
   }
