@@ -70,6 +70,8 @@ static int g_flag_wgrad_tc = 1;  // Linear backward with operands read in place:
 static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
 int g_tcx_smem_kb = 0;
+int g_tcx_wgrad_ctas = 0;
+int g_tcx_wgrad_idle = 0;
 int g_tcx_max_ctas = 0;          // > 0: cap on the grid of the persistent tcgen05 kernels (lets kernels of parallel graph branches co-run)
 bool tcx_flag_gemm_tc() { return g_flag_gemm_tc != 0; }
 bool flash_tc_enabled() { return g_flag_flash_tc != 0; }
@@ -580,6 +582,8 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "wgrad_tc")) f = &g_flag_wgrad_tc;
   else if (!strcmp(name, "max_ctas")) f = &g_tcx_max_ctas;
   else if (!strcmp(name, "smem_kb")) f = &g_tcx_smem_kb;
+  else if (!strcmp(name, "wgrad_ctas")) f = &g_tcx_wgrad_ctas;
+  else if (!strcmp(name, "wgrad_idle")) f = &g_tcx_wgrad_idle;
   if (!f) { tcx_set_error("unknown flag %s", name); return -1; }
   const int old = *f;
   *f = value;
@@ -1850,13 +1854,18 @@ int tcx_coord_gate_bwd(const float* x, const float* z, const float* dout, float*
 
 extern "C" {
 
-size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C) { return 4 * (rnd(2 * (size_t)M) + rnd(2 * (size_t)bwd_red_blocks(M) * C) + 64); }
+// floats of the LayerNorm-backward column partials: the two-pass kernels leave bwd_red_blocks(M) blocks, the one-pass ones
+// ln_bwd_fused_blocks(M, C) (more than that on wide rows)
+static size_t ln_part_floats(long long M, int C) {
+  return 2 * (size_t)std::max(bwd_red_blocks(M), ln_bwd_fused_ok(M, C) ? ln_bwd_fused_blocks(M, C) : 0) * C;
+}
+size_t tcx_layernorm_bwd_workspace_bytes(long long M, int C) { return 4 * (rnd(2 * (size_t)M) + rnd(ln_part_floats(M, C)) + 64); }
 int tcx_layernorm_bwd(const float* x, const float* w, const float* dy, const float* dres, float eps, float* dx, float* dw, float* db,
                       long long M, int C, void* ws, void* stream) {
   TCX_REQUIRE(x && w && dy && dx && dw && db && ws, "layernorm_bwd: null pointer");
   Carver c(ws);
   float* stats = c.take(2 * (size_t)M);
-  float* part = c.take(2 * (size_t)bwd_red_blocks(M) * C);
+  float* part = c.take(ln_part_floats(M, C));
   return launch_bwd_ln(x, dy, w, nullptr, eps, 0, dx, dw, db, M, C, stats, part, S(stream), dres);
 }
 
@@ -2252,7 +2261,7 @@ size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4) {
   const long long M = (long long)B * N;
   const size_t lin = std::max(linear_bwd_ws_floats(M, C, C4), linear_bwd_ws_floats(M, C4, C));
   const size_t part = std::max((size_t)10 * bwd_red_blocks(M) * C4, (size_t)10 * dw_bwd_fused_blocks(M, C4) * C4);
-  return 4 * (3 * rnd((size_t)M * C4) + rnd(2 * (size_t)M) + rnd(9 * (size_t)C4) + rnd(part) + rnd(2 * (size_t)bwd_red_blocks(M) * C4) +
+  return 4 * (3 * rnd((size_t)M * C4) + rnd(2 * (size_t)M) + rnd(9 * (size_t)C4) + rnd(part) + 2 * rnd(ln_part_floats(M, C4)) +
               2 * lin + 64);
 }
 // xn32 (nullable): the fp32 LayerNorm output the forward was given (the TF32 operand of fc1's weight gradient); without it the
@@ -2271,7 +2280,8 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
   float* stats = c.take(2 * (size_t)M);
   float* wflip = c.take(9 * (size_t)C4);
   float* part = c.take(std::max((size_t)10 * bwd_red_blocks(M) * C4, (size_t)10 * dw_bwd_fused_blocks(M, C4) * C4));
-  float* part_ln = c.take(2 * (size_t)bwd_red_blocks(M) * C4);
+  float* part_ln = c.take(ln_part_floats(M, C4));
+  float* part_ln2 = c.take(ln_part_floats(M, C4));      // second-path LayerNorm partials (kept apart from `part`)
   float* lin = c.take(linear_bwd_ws_floats(M, C, C4) > linear_bwd_ws_floats(M, C4, C) ? linear_bwd_ws_floats(M, C, C4)
                                                                                        : linear_bwd_ws_floats(M, C4, C));
   float* lin2 = c.take(0);
@@ -2292,7 +2302,7 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
                   "mixffn_skip_bwd: fork failed");
     }
     TCX_TRY(run_linear_bwd(a32, 0, F(p[6]), dy, nullptr, G(6), G(7), M, C, C4, lin2, sa));                   // dW2 = dy^T a, db2
-    TCX_TRY(launch_bwd_ln_fold(part_ln, ln_bwd_fused_blocks(M), C4, G(4), G(5), sa));
+    TCX_TRY(launch_bwd_ln_fold(part_ln, ln_bwd_fused_blocks(M, C4), C4, G(4), G(5), sa));
     TCX_TRY(launch_bwd_dw_fold(part, dw_nblk, C4, G(2), G(3), sa));
     // fc1: dxn = dh W1 on the main stream, dW1 = dh^T xn beside it
     const void* xn = xn32 ? (const void*)xn32 : (const void*)s.xn16;
@@ -2303,13 +2313,13 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
   // fc2: a16 [M][C4] -> y [M][C]
   TCX_TRY(run_linear_bwd(s.a16, 1, F(p[6]), dy, da, G(6), G(7), M, C, C4, lin, st));
   // GELU(LayerNorm(u))
-  TCX_TRY(launch_bwd_ln(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, G(4), G(5), M, C4, stats, part, st));
+  TCX_TRY(launch_bwd_ln(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, G(4), G(5), M, C4, stats, part_ln2, st));
   // u = dw3x3(h) + b + h: input gradient and the filter / bias sums in one pass (row-sweep kernel), then the fold
   float* dh = da;
   {
     (void)wflip;
     int dw_nblk = 0;
-    float* part_dw = part + 2 * (size_t)bwd_red_blocks(M) * C4;       // behind the LayerNorm partials still being folded
+    float* part_dw = part;
     TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part_dw, st, &dw_nblk));
     TCX_TRY(launch_bwd_dw_fold(part_dw, dw_nblk, C4, G(2), G(3), st));
   }

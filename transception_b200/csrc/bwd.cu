@@ -417,7 +417,7 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
   }
   if (ln_bwd_fused_ok(M, C)) {      // one pass over (u, dz) instead of a row pass + a column pass
     TCX_TRY(launch_ln_bwd_fused(u, dz, gamma, beta, eps, gelu, du, nullptr, dres, M, C, part, st));
-    return launch_bwd_ln_fold(part, ln_bwd_fused_blocks(M), C, dgamma, dbeta, st);
+    return launch_bwd_ln_fold(part, ln_bwd_fused_blocks(M, C), C, dgamma, dbeta, st);
   }
   const unsigned rb = (unsigned)((M + 7) / 8);
   const int rows = red_rows_per_block(M), nblk = bwd_red_blocks(M);

@@ -51,7 +51,7 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
 
 // fused forms (bwd_mix.cu): one pass per tensor.  launch_bwd_ln uses the fused kernel by itself whenever ln_bwd_fused_ok.
 bool ln_bwd_fused_ok(long long M, int C);
-int ln_bwd_fused_blocks(long long M);
+int ln_bwd_fused_blocks(long long M, int C);   // partial buffer: 2 * ln_bwd_fused_blocks(M, C) * C floats (may exceed bwd_red_blocks(M) for C > 512)
 // du = LayerNorm (gelu: GELU o LayerNorm) backward of dz at u; act (nullable, gelu only) = fp32 GELU(LN(u)); part: 2 * blocks * C
 // column partials to be folded with launch_bwd_ln_fold
 // dres (nullable): added to du — the gradient arriving over the residual connection around the LayerNorm

@@ -220,6 +220,112 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float
   }
 }
 
+// Wide rows (512 < C <= 2048: the Mix-FFN hidden width of the 320- and 512-channel maps, 784 to 3 136 rows): one BLOCK per row,
+// a thread owns the float4 chunks (t + 256 j) * 4 of every row its block handles, so the column sums of d gamma / d beta stay in
+// its registers and are written as the block partial without any shared-memory fold; the three row reductions (mean, variance,
+// the two LayerNorm-backward means) go through 8 per-warp partials added in warp order.
+constexpr int LW_T = 256, LW_NV = 2;
+__device__ __forceinline__ float lw_block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = red[0];
+#pragma unroll
+  for (int w = 1; w < LW_T / 32; w++) s += red[w];
+  return s;
+}
+template <bool GELU>
+__global__ void __launch_bounds__(LW_T) ln_bwd_wide_kernel(const float* __restrict__ u, const float* __restrict__ dz,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                           float* __restrict__ du, float* __restrict__ act, const float* __restrict__ dres,
+                                                           long long M, int C, float* __restrict__ part) {
+  __shared__ float red[4][LW_T / 32];
+  const float invC = 1.0f / (float)C;
+  float4 g4[LW_NV], b4[LW_NV];
+  bool live[LW_NV];
+  float ag[LW_NV][4], ab[LW_NV][4];
+#pragma unroll
+  for (int j = 0; j < LW_NV; j++) {
+    const int c = (threadIdx.x + LW_T * j) * 4;
+    live[j] = c < C;
+    g4[j] = live[j] ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b4[j] = (GELU && live[j]) ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ag[j][k] = 0.f; ab[j][k] = 0.f; }
+  }
+  for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+    float4 x4[LW_NV], d4[LW_NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LW_NV; j++) {
+      const int c = (threadIdx.x + LW_T * j) * 4;
+      x4[j] = live[j] ? *reinterpret_cast<const float4*>(u + row * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d4[j] = live[j] ? *reinterpret_cast<const float4*>(dz + row * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (x4[j].x + x4[j].y) + (x4[j].z + x4[j].w);
+    }
+    const float mean = lw_block_sum(s, red[0]) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LW_NV; j++) {
+      if (!live[j]) continue;
+      const float a = x4[j].x - mean, b = x4[j].y - mean, c = x4[j].z - mean, d = x4[j].w - mean;
+      q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(lw_block_sum(q, red[1]) * invC + eps);
+    float xh[LW_NV][4], g[LW_NV][4], ge[LW_NV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LW_NV; j++) {
+      const float xv[4] = {x4[j].x, x4[j].y, x4[j].z, x4[j].w}, dv[4] = {d4[j].x, d4[j].y, d4[j].z, d4[j].w};
+      const float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w}, bv[4] = {b4[j].x, b4[j].y, b4[j].z, b4[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        xh[j][k] = live[j] ? (xv[k] - mean) * rstd : 0.f;
+        float gg = dv[k];
+        ge[j][k] = 0.f;
+        if (GELU) {
+          float dg;
+          gelu_parts(fmaf(xh[j][k], gv[k], bv[k]), ge[j][k], dg);
+          gg *= dg;
+        }
+        g[j][k] = live[j] ? gg : 0.f;
+        const float dxh = g[j][k] * gv[k];
+        s1 += dxh;
+        s2 = fmaf(dxh, xh[j][k], s2);
+      }
+    }
+    s1 = lw_block_sum(s1, red[2]) * invC;
+    s2 = lw_block_sum(s2, red[3]) * invC;
+#pragma unroll
+    for (int j = 0; j < LW_NV; j++) {
+      if (!live[j]) continue;
+      const int c = (threadIdx.x + LW_T * j) * 4;
+      const float gv[4] = {g4[j].x, g4[j].y, g4[j].z, g4[j].w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        o[k] = rstd * (g[j][k] * gv[k] - s1 - xh[j][k] * s2);
+        ag[j][k] = fmaf(g[j][k], xh[j][k], ag[j][k]);
+        ab[j][k] += g[j][k];
+      }
+      if (dres) {
+        const float4 r = *reinterpret_cast<const float4*>(dres + row * C + c);
+        o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+      }
+      *reinterpret_cast<float4*>(du + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (GELU && act) *reinterpret_cast<float4*>(act + row * C + c) = make_float4(ge[j][0], ge[j][1], ge[j][2], ge[j][3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LW_NV; j++) {
+    if (!live[j]) continue;
+    const int c = (threadIdx.x + LW_T * j) * 4;
+    *reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * 2 + 0) * C + c) = make_float4(ag[j][0], ag[j][1], ag[j][2], ag[j][3]);
+    *reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * 2 + 1) * C + c) = make_float4(ab[j][0], ab[j][1], ab[j][2], ab[j][3]);
+  }
+}
+
 // depthwise 3x3 (stride 1, pad 1) backward on NHWC rows, C channels: one thread = one pixel lane x 4 channels.
 //   dh[p][c] = du[p][c] + sum_t w[c][t] du[p - off(t)][c]                 (input gradient of u = conv(h) + b + h)
 //   part[blk][t][c] = sum_{p in block} du[p][c] h[p + off(t)][c], t < 9;  part[blk][9][c] = sum du[p][c]
@@ -405,9 +511,10 @@ int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
   return tcx_check_launch("add_inplace");
 }
 
-bool ln_bwd_fused_ok(long long M, int C) { return M > 0 && C % 4 == 0 && C >= 4 && C <= 512; }
-int ln_bwd_fused_blocks(long long M) {
-  long long nb = (M + LF_WARPS * 4 - 1) / (LF_WARPS * 4);       // >= 4 rows per warp
+bool ln_bwd_fused_ok(long long M, int C) { return M > 0 && C % 4 == 0 && C >= 4 && C <= LW_T * LW_NV * 4; }
+int ln_bwd_fused_blocks(long long M, int C) {
+  long long nb = C > 512 ? (M + 1) / 2                            // wide rows: one block per row, >= 2 rows per block
+                         : (M + LF_WARPS * 4 - 1) / (LF_WARPS * 4);       // >= 4 rows per warp
   if (nb > LF_MAX_BLOCKS) nb = LF_MAX_BLOCKS;
   if (nb < 1) nb = 1;
   return (int)nb;
@@ -417,9 +524,15 @@ int ln_bwd_fused_blocks(long long M) {
 // launch_bwd_ln_fold(part, nblk, C, dgamma, dbeta).
 int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
                         float* act, const float* dres, long long M, int C, float* part, cudaStream_t st) {
-  TCX_REQUIRE(ln_bwd_fused_ok(M, C), "ln_bwd_fused: C must be a multiple of 4, <= 512 (M=%lld C=%d)", M, C);
+  TCX_REQUIRE(ln_bwd_fused_ok(M, C), "ln_bwd_fused: C must be a multiple of 4, <= 2048 (M=%lld C=%d)", M, C);
   TCX_REQUIRE(du != dz, "ln_bwd_fused: du may not alias dz");
-  const int nblk = ln_bwd_fused_blocks(M);
+  const int nblk = ln_bwd_fused_blocks(M, C);
+  if (C > 512) {
+    ProfScope prof("ln_bwd_fused", st, (double)M * C * (gelu && act ? 16.0 : 12.0));
+    if (gelu) ln_bwd_wide_kernel<true><<<nblk, LW_T, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part);
+    else ln_bwd_wide_kernel<false><<<nblk, LW_T, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part);
+    return tcx_check_launch("ln_bwd_wide");
+  }
   ProfScope prof("ln_bwd_fused", st, (double)M * C * (gelu && act ? 16.0 : 12.0));
 #define LNB(NV)                                                                                                         \
   do {                                                                                                                  \

@@ -36,6 +36,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #endif
 extern int g_tcx_pdl;   // flag "pdl" (default 1)
 extern int g_tcx_smem_kb;    // flag "smem_kb" (default 0 = whole SM): shared-memory budget of the tcgen05 GEMM kernels
+extern int g_tcx_wgrad_ctas;   // flag "wgrad_ctas" (0 = resident-cluster capacity): CTA budget of one weight-gradient launch
+extern int g_tcx_wgrad_idle;   // flag "wgrad_idle": allow splits that leave some CTAs without tokens
 extern int g_tcx_max_ctas;   // flag "max_ctas" (default 0 = one CTA per SM)
 template <typename... KArgs, typename... Args>
 inline cudaError_t tcx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

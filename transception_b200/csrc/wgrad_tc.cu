@@ -396,8 +396,9 @@ unsigned g_ticket_next = 0;
 }  // namespace
 
 // ---- split plan ------------------------------------------------------------------------------------------------------------------
-// Measured on B200 (profiles/r02_wgrad_probe.txt): one CTA streams a k-block (64 tokens) in ~0.3 us whatever the tile width (TMA
-// latency-bound), the cluster fold costs ~2.5 us and the second (HBM) level ~3 us more.  So: pick the split count that minimises
+// Measured on B200 (tools/r2_wgrad_sweep.py, profiles/r02_wgrad_sweep.txt): one CTA streams its 48-64 KB k-blocks (64 tokens) at
+// ~57 GB/s, i.e. ~0.8 us each (the TMA unit of one SM, 128-byte rows), the cluster fold costs ~2.5 us and the second (HBM) level
+// ~3 us more; a launch has ~7 us of fixed cost.  So: pick the split count that minimises
 //   waves * k-blocks-per-CTA * 0.3 us + fold overheads,   S in {1, 2, 4, 8} (one cluster) or 8 * S2 with S2 <= 16,
 // keeping tiles * S * batch within about one wave of the 148 SMs.
 // CTAs of this kernel that can be resident at once for cluster size cs (index log2 cs): a cluster needs cs free SMs inside ONE GPC, so
@@ -439,10 +440,14 @@ void wgrad_tc_plan(long long Mtok, int NL, int KL, int batch, int eb, int* S, in
     const int cs = idx < 4 ? (1 << idx) : WG_MAX_SPLIT;
     const int s2 = idx < 4 ? 1 : idx - 2;          // 2 .. WG_MAX_S2
     const int s = cs * s2;
-    const long long cap = g_tcx_max_ctas > 0 ? g_tcx_max_ctas : wgrad_capacity(cs);
-    if (s > 1 && (tiles * s > cap || (long long)(s - 1) * tokens_per(s) >= Mtok)) continue;     // one wave, no empty split
+    long long cap = g_tcx_max_ctas > 0 ? g_tcx_max_ctas : wgrad_capacity(cs);
+    if (g_tcx_wgrad_ctas > 0 && cap > g_tcx_wgrad_ctas) cap = g_tcx_wgrad_ctas;
+    // one wave.  Splits are whole 64-token k-blocks, so a few CTAs of a fine split may get no tokens (they park a zero tile): that is
+    // accepted as long as the split still shortens the longest CTA (49 k-blocks: 8 -> 7 each, 32 -> 2 each, 25 CTAs busy)
+    if (s > 1 && tiles * s > cap) continue;
+    if (g_tcx_wgrad_idle ? (s > 2 && (kb_total + s - 1) / s >= (kb_total + s / 2 - 1) / (s / 2)) : (s > 1 && (long long)(s - 1) * tokens_per(s) >= Mtok)) continue;
     const long long waves = (tiles * s + cap - 1) / cap;
-    const double cost = (double)waves * (double)((kb_total + s - 1) / s) * 0.3 + (s > 1 ? 2.5 : 0.0) + (s2 > 1 ? 3.0 : 0.0);
+    const double cost = (double)waves * (double)((kb_total + s - 1) / s) * 0.8 + (s > 1 ? 2.5 : 0.0) + (s2 > 1 ? 3.0 : 0.0);
     if (cost < best) { best = cost; best_cs = cs; best_s2 = s2; }
   }
   *CS = best_cs; *S2 = best_s2; *S = best_cs * best_s2; *Ms = (int)tokens_per(*S); *BN = bn;
