@@ -2294,15 +2294,21 @@ int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, con
     cudaStream_t sa = aux ? aux->s[1] : st;
     TCX_TRY(run_linear_bwd(nullptr, 0, F(p[6]), dy, da, nullptr, nullptr, M, C, C4, lin, st));               // da = dy W2
     TCX_TRY(launch_ln_bwd_fused(s.u, da, F(p[4]), F(p[5]), ln_eps, 1, du, a32, nullptr, M, C4, part_ln, st));
-    float* dh = da;
-    int dw_nblk = 0;
-    TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part, st, &dw_nblk));
+    // fc2's weight gradient and the LayerNorm parameter sums need only a32 / part_ln: they leave the chain HERE, beside the
+    // depthwise backward; the depthwise filter fold follows on the same stream once that kernel is done (second event)
     if (aux) {
       TCX_REQUIRE(cudaEventRecord(aux->fork, st) == cudaSuccess && cudaStreamWaitEvent(sa, aux->fork, 0) == cudaSuccess,
                   "mixffn_skip_bwd: fork failed");
     }
     TCX_TRY(run_linear_bwd(a32, 0, F(p[6]), dy, nullptr, G(6), G(7), M, C, C4, lin2, sa));                   // dW2 = dy^T a, db2
     TCX_TRY(launch_bwd_ln_fold(part_ln, ln_bwd_fused_blocks(M, C4), C4, G(4), G(5), sa));
+    float* dh = da;
+    int dw_nblk = 0;
+    TCX_TRY(launch_dw_bwd_fused(du, s.h16, F(p[2]), dh, B, H, W, C4, part, st, &dw_nblk));
+    if (aux) {
+      TCX_REQUIRE(cudaEventRecord(aux->join[2], st) == cudaSuccess && cudaStreamWaitEvent(sa, aux->join[2], 0) == cudaSuccess,
+                  "mixffn_skip_bwd: second fork failed");
+    }
     TCX_TRY(launch_bwd_dw_fold(part, dw_nblk, C4, G(2), G(3), sa));
     // fc1: dxn = dh W1 on the main stream, dW1 = dh^T xn beside it
     const void* xn = xn32 ? (const void*)xn32 : (const void*)s.xn16;
