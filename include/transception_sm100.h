@@ -296,7 +296,8 @@ int tcx_mt_sgd(const void* param_ptrs, const void* grad_ptrs, const void* buf_pt
  * gradients dp = {d fc1_w, d fc1_b, d dw_w, d dw_b, d ln_w, d ln_b, d fc2_w, d fc2_b} (device pointers, shapes of p). */
 size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4);
 int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
-                              int W, int C, int C4, void* saved, void* stream);
+                              int W, int C, int C4, void* saved, const void* xn16, void* stream);   /* xn16 (nullable): fp16 twin of xn
+                              from tcx_layernorm_dual_fwd, read in place (then tcx_mixffn_skip_bwd needs xn32) */
 size_t tcx_mixffn_skip_bwd_workspace_bytes(int B, int N, int C, int C4);
 int tcx_mixffn_skip_bwd(const float* dy, const void* const* p, float ln_eps, const void* saved, const float* xn32, float* dxn,
                         void* const* dp, int B, int H, int W, int C, int C4, void* ws, void* stream);
@@ -318,7 +319,7 @@ int tcx_eff_attn_bwd(const float* dy, const void* const* p, const void* saved, f
 size_t tcx_mb_factor_attn_saved_bytes(int B, int N, int C);
 size_t tcx_mb_factor_attn_train_workspace_bytes(int B, int N, int C);
 int tcx_mb_factor_attn_train_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W, int C,
-                                 int heads, void* saved, void* ws, void* stream);
+                                 int heads, void* saved, void* ws, const void* xn16, void* stream);
 
 /* FactorAtt_ConvRelPosEnc backward.  fwd_ws = the workspace of tcx_mb_factor_attn_fwd (saved_f16 = 0: fp32 q | k | v rows, context,
  * attention output) or the `saved` buffer of tcx_mb_factor_attn_train_fwd (saved_f16 = 1), with the same xn.  dy [B*N][C] -> dxn
@@ -412,6 +413,11 @@ int tcx_final_head_bwd(const float* e, const float* dlogits, const float* lnw, c
  * lnw = lnb = NULL (the conv output; the LayerNorm is a separate node); its weight gradient is tcx_linear_bwd on the patch matrix
  * patches [B*Ho*Wo][Kp] (Kp >= 147, a multiple of 4; columns (ci, ky, kx), zero beyond 147 and outside the image) built here. */
 int tcx_patch_im2row_fwd(const float* x, int B, int Cin, int H, int W, float* patches, int Kp, void* stream);
+
+/* LayerNorm with two outputs from one pass: y32 (fp32, kept for the backward) and y16 (fp16: the GEMM operand of the node that
+ * follows — the `xn16` argument of tcx_mixffn_skip_train_fwd / tcx_mb_factor_attn_train_fwd).  C in {64, 128, 256, 320, 512}. */
+int tcx_layernorm_dual_fwd(const float* x, const float* w, const float* b, float* y32, void* y16, long long M, int C, float eps,
+                           void* stream);
 
 #ifdef __cplusplus
 }

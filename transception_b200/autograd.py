@@ -35,10 +35,15 @@ class LayerNormResFn(torch.autograd.Function):
         ctx.save_for_backward(x, w)
         ctx.eps = eps
         ctx.set_materialize_grads(False)
-        return ops.layernorm(x, w, b, eps), x.view_as(x)
+        # third output: the fp16 twin of LN(x) from the same pass (the GEMM operand of the node that follows), or an empty tensor
+        y, y16 = ops.layernorm_dual(x, w, b, eps)
+        if y16 is None:
+            y16 = x.new_empty(0, dtype=torch.float16)
+        ctx.mark_non_differentiable(y16)
+        return y, x.view_as(x), y16
 
     @staticmethod
-    def backward(ctx, dy, dres):
+    def backward(ctx, dy, dres, _d16):
         x, w = ctx.saved_tensors
         if dy is None:
             return dres, None, None, None
@@ -171,10 +176,10 @@ class MixFFNSkipFn(torch.autograd.Function):
     """y = fc2(GELU(LN(dw3x3(fc1 x) + fc1 x))) (MSTr.py:58-61) on x [B, N, C]."""
 
     @staticmethod
-    def forward(ctx, x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b, residual=None):
+    def forward(ctx, x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b, residual=None, x16=None):
         x = x.contiguous()
         y, saved = ops.mixffn_skip_train(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
-                                         residual=residual.contiguous() if residual is not None else None)
+                                         residual=residual.contiguous() if residual is not None else None, xn16=x16)
         # x (the LayerNorm output) is kept in fp32: fc1's weight gradient reads it in place as a TF32 operand
         ctx.save_for_backward(saved, x, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b)
         ctx.geom = (x.shape[0], H, W, eps)
@@ -187,7 +192,7 @@ class MixFFNSkipFn(torch.autograd.Function):
         B, H, W, eps = ctx.geom
         dx, g = ops.mixffn_skip_bwd(dy, saved, B, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
                                     need_dx=ctx.needs_input_grad[0], xn=x)
-        return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None,)        # the residual input receives dy as it is
+        return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None, None)   # the residual input receives dy as it is
 
 
 class EffAttnFn(torch.autograd.Function):
@@ -216,13 +221,13 @@ class FactorAttFn(torch.autograd.Function):
     """FactorAtt_ConvRelPosEnc.forward (MSTr.py:852-886) on LayerNorm output x [B, N, C]."""
 
     @staticmethod
-    def forward(ctx, x, H, W, heads, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb, residual=None):
+    def forward(ctx, x, H, W, heads, qkvw, qkvb, w3, b3, w5, b5, w7, b7, projw, projb, residual=None, x16=None):
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
         ctx.f16 = ops.USE_F16
         if ctx.f16:       # the fp16 pipeline of the inference path (fused per-head attention kernel), keeping fp16 q | k | v and output
             y, ws = ops.mb_factor_attn_train(x, H, W, heads, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
-                                             residual=res)
+                                             residual=res, xn16=x16)
         else:
             y, ws = ops.mb_factor_attn(x, H, W, heads, None, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], [2, 3, 3], projw, projb,
                                        residual=res, keep_ws=True)
@@ -237,7 +242,7 @@ class FactorAttFn(torch.autograd.Function):
         H, W, heads = ctx.geom
         dx, g = ops.mb_factor_attn_bwd(dy, x, ws, H, W, heads, qkvw, qkvb, [w3, w5, w7], [b3, b5, b7], projw, projb,
                                        need_dx=ctx.needs_input_grad[0], saved_f16=ctx.f16)
-        return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None,)
+        return (dx, None, None, None) + tuple(g) + (dy if ctx.has_res else None, None)
 
 
 class DwConvTokensFn(torch.autograd.Function):
@@ -259,7 +264,7 @@ class DwConvTokensFn(torch.autograd.Function):
 
 def factor_att(x, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, projw, projb, residual=None):
     return FactorAttFn.apply(x, H, W, heads, qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2],
-                             projw, projb, residual)
+                             projw, projb, residual, _f16_twin(x))
 
 
 def dwconv_tokens(x, H, W, w, b, add_input):
@@ -403,13 +408,23 @@ def layernorm(x, w, b, eps):
 
 
 def layernorm_res(x, w, b, eps):
-    """(LN(x), x): feed the second result to the residual input of the node that closes the skip connection."""
-    return LayerNormResFn.apply(x, w, b, eps)
+    """(LN(x), x): feed the second result to the residual input of the node that closes the skip connection.  LN(x) carries its
+    fp16 twin as ``._tcx_f16`` (read by mixffn_skip / factor_att below, which then skip their own conversion kernel)."""
+    y, xr, y16 = LayerNormResFn.apply(x, w, b, eps)
+    if y16.numel():
+        y._tcx_f16 = y16
+    return y, xr
 
 
 def linear(x, w, b=None, residual=None):
     return LinearFn.apply(x, w, b, residual)
 
 
+def _f16_twin(x):
+    """The fp16 copy a LayerNorm node attached to its output (layernorm_res), if it is still that tensor's layout."""
+    t = getattr(x, "_tcx_f16", None)
+    return t if t is not None and t.shape == x.shape and x.is_contiguous() else None
+
+
 def mixffn_skip(x, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):
-    return MixFFNSkipFn.apply(x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b, residual)
+    return MixFFNSkipFn.apply(x, H, W, eps, fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b, residual, _f16_twin(x))

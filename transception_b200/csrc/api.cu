@@ -596,6 +596,14 @@ int tcx_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
   return launch_layernorm(x, w, b, y, M, C, eps, S(stream));
 }
 
+// LayerNorm with two outputs from one pass: fp32 (kept for the backward) and fp16 (the GEMM operand of the node that follows)
+int tcx_layernorm_dual_fwd(const float* x, const float* w, const float* b, float* y32, void* y16, long long M, int C, float eps,
+                           void* stream) {
+  TCX_REQUIRE(x && w && b && y32 && y16, "layernorm_dual_fwd: null pointer");
+  TCX_REQUIRE(C == 64 || C == 128 || C == 256 || C == 320 || C == 512, "layernorm_dual_fwd: C=%d is not one of 64/128/256/320/512", C);
+  return run_ln16_1(x, w, b, reinterpret_cast<__half*>(y16), y32, M, C, eps, S(stream));
+}
+
 int tcx_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, int M, int N,
                    int K, int act, void* stream) {
   return launch_linear(x, w, bias, residual, y, M, N, K, act, S(stream));
@@ -766,7 +774,7 @@ size_t tcx_mb_factor_attn_train_workspace_bytes(int B, int N, int C) {
   return 4 * (rnd(bnc / 2 + 64) + rnd((size_t)B * C * C) + 64);
 }
 int tcx_mb_factor_attn_train_fwd(const float* xn, const void* const* p, const float* residual, float* y, int B, int H, int W, int C,
-                                 int heads, void* saved, void* ws, void* stream) {
+                                 int heads, void* saved, void* ws, const void* xn16_in, void* stream) {
   TCX_REQUIRE(xn && p && y && saved && ws, "mb_factor_attn_train_fwd: null pointer");
   TCX_REQUIRE(heads == 8 && C % heads == 0, "mb_factor_attn_train_fwd: built for 8 heads");
   const __half* wqkv = w16_of(p[0]);
@@ -779,9 +787,10 @@ int tcx_mb_factor_attn_train_fwd(const float* xn, const void* const* p, const fl
   __half* qkv16 = H16(sv.take(3 * bnc / 2 + 64));
   __half* att16 = H16(sv.take(bnc / 2 + 64));
   Carver c(ws);
-  __half* xn16 = H16(c.take(bnc / 2 + 64));
+  __half* xn16_ws = H16(c.take(bnc / 2 + 64));
   float* ctx = c.take((size_t)B * C * C);
-  TCX_TRY(launch_f32_to_f16(xn, xn16, (long long)bnc, st));
+  if (!xn16_in) TCX_TRY(launch_f32_to_f16(xn, xn16_ws, (long long)bnc, st));      // no fp16 twin from the LayerNorm in front
+  const __half* xn16 = xn16_in ? reinterpret_cast<const __half*>(xn16_in) : xn16_ws;
   {
     GemmParams gp = gemm1(F(xn16), F(wqkv), reinterpret_cast<float*>(qkv16), M, 3 * C, C);
     gp.ab16 = 1; gp.out16 = 1;
@@ -2246,14 +2255,16 @@ int tcx_attn_core_bwd(const float* q, const float* kv, const float* dout, float 
 
 size_t tcx_mixffn_skip_saved_bytes(int B, int N, int C, int C4) { return 4 * mix_saved(nullptr, (long long)B * N, C, C4).floats; }
 int tcx_mixffn_skip_train_fwd(const float* xn, const void* const* p, float ln_eps, const float* residual, float* y, int B, int H,
-                              int W, int C, int C4, void* saved, void* stream) {
+                              int W, int C, int C4, void* saved, const void* xn16, void* stream) {
   TCX_REQUIRE(xn && p && y && saved, "mixffn_skip_train_fwd: null pointer");
   Mix16 m{};
   TCX_REQUIRE(mix16_fill(p, m), "mixffn_skip_train_fwd: fc1 / fc2 weights are not prepared (tcx_prepare_weight_f16)");
   const long long M = (long long)B * H * W;
   MixSaved s = mix_saved(saved, M, C, C4);
-  TCX_TRY(launch_f32_to_f16(xn, s.xn16, M * C, S(stream)));
-  m.xn = s.xn16; m.res = residual; m.y = y; m.u_save = s.u;
+  // xn16 (nullable): the fp16 twin of xn written by the LayerNorm in front (tcx_layernorm_dual_fwd), read in place — the copy in
+  // `saved` is then NOT written, and tcx_mixffn_skip_bwd must be given xn32; without it xn is converted here
+  if (!xn16) TCX_TRY(launch_f32_to_f16(xn, s.xn16, M * C, S(stream)));
+  m.xn = xn16 ? reinterpret_cast<const __half*>(xn16) : s.xn16; m.res = residual; m.y = y; m.u_save = s.u;
   return run_mixffn16(1, &m, ln_eps, B, H, W, C, C4, s.h16, s.a16, S(stream));
 }
 

@@ -118,7 +118,8 @@ _PROTOS = {
     "tcx_mb_factor_attn_bwd": (_i, [_vp, _vp, _pp, _vp, _i, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_mb_factor_attn_saved_bytes": (_sz, [_i, _i, _i]),
     "tcx_mb_factor_attn_train_workspace_bytes": (_sz, [_i, _i, _i]),
-    "tcx_mb_factor_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tcx_mb_factor_attn_train_fwd": (_i, [_vp, _pp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tcx_layernorm_dual_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _vp]),
     "tcx_dwconv_tokens_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_dwconv_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_attn_core_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -140,7 +141,7 @@ _PROTOS = {
     "tcx_coord_gate_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tcx_coord_gate_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tcx_mixffn_skip_saved_bytes": (_sz, [_i, _i, _i, _i]),
-    "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tcx_mixffn_skip_train_fwd": (_i, [_vp, _pp, _f, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tcx_mixffn_skip_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_mixffn_skip_bwd": (_i, [_vp, _pp, _f, _vp, _vp, _vp, _pp, _i, _i, _i, _i, _i, _vp, _vp]),
 }
@@ -378,6 +379,24 @@ def layernorm(x, w, b, eps):
     C = x.shape[-1]
     _chk(lib.tcx_layernorm_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), x.numel() // C, C, eps, _stream()))
     return y
+
+
+LN_DUAL_WIDTHS = (64, 128, 256, 320, 512)
+
+
+def layernorm_dual(x, w, b, eps):
+    """(LN(x) in fp32, the same values in fp16) from one pass — the fp16 twin is the GEMM operand of the training node that
+    follows (mixffn_skip_train / mb_factor_attn_train ``xn16=``).  Returns (y, None) for widths the dual kernel is not built for."""
+    require_cuda(x)
+    C = x.shape[-1]
+    if not USE_F16 or C not in LN_DUAL_WIDTHS:
+        return layernorm(x, w, b, eps), None
+    lib = load_library()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _chk(lib.tcx_layernorm_dual_fwd(_ptr(x), _ptr(_d(w)), _ptr(_d(b)), _ptr(y), _ptr16(y16), x.numel() // C, C, eps, _stream()))
+    return y, y16
 
 
 def linear(x, w, b=None, act=0, residual=None):
@@ -1125,7 +1144,7 @@ def wgrad_mn(a, b, alpha=1.0, need_db=False, need_T=False, mask_ch=0):
     return out, outT, db
 
 
-def mixffn_skip_train(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None):
+def mixffn_skip_train(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b, residual=None, xn16=None):
     """Training forward of MixFFN_skip: (y, saved) with ``saved`` the opaque buffer mixffn_skip_bwd consumes."""
     require_cuda(xn)
     lib = load_library()
@@ -1135,7 +1154,9 @@ def mixffn_skip_train(xn, H, W, fc1w, fc1b, dww, dwb, lnw, lnb, eps, fc2w, fc2b,
     y = torch.empty_like(xn)
     saved = _ws(lib.tcx_mixffn_skip_saved_bytes(B, N, C, C4), xn)
     tab = _table([fc1w, fc1b, dww, dwb, lnw, lnb, fc2w, fc2b], mats=(0, 6))
-    _chk(lib.tcx_mixffn_skip_train_fwd(_ptr(xn), tab, eps, _ptr(residual), _ptr(y), B, H, W, C, C4, _ptr(saved), _stream()))
+    if xn16 is not None and xn16.shape != xn.shape:
+        raise RuntimeError("mixffn_skip_train: xn16 %s does not match xn %s" % (tuple(xn16.shape), tuple(xn.shape)))
+    _chk(lib.tcx_mixffn_skip_train_fwd(_ptr(xn), tab, eps, _ptr(residual), _ptr(y), B, H, W, C, C4, _ptr(saved), _ptr16(xn16), _stream()))
     return y, saved
 
 
@@ -1187,7 +1208,7 @@ def eff_attn_bwd(dy, saved, kw, kb, qw, qb, vw, vb, rw, rb, need_dx=True):
     return dxn, grads
 
 
-def mb_factor_attn_train(xn, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, head_splits, projw, projb, residual=None):
+def mb_factor_attn_train(xn, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, head_splits, projw, projb, residual=None, xn16=None):
     """Training forward of FactorAtt_ConvRelPosEnc on the fp16 pipeline: (y, saved) with ``saved`` the opaque buffer that
     mb_factor_attn_bwd(..., saved_f16=True) consumes."""
     require_cuda(xn)
@@ -1199,7 +1220,10 @@ def mb_factor_attn_train(xn, H, W, heads, qkvw, qkvb, crpe_w, crpe_b, head_split
     saved = _ws(lib.tcx_mb_factor_attn_saved_bytes(B, N, C), xn)
     ws = _ws(lib.tcx_mb_factor_attn_train_workspace_bytes(B, N, C), xn)
     tab = _table([qkvw, qkvb, crpe_w[0], crpe_b[0], crpe_w[1], crpe_b[1], crpe_w[2], crpe_b[2], projw, projb], mats=(0, 8))
-    _chk(lib.tcx_mb_factor_attn_train_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, H, W, C, heads, _ptr(saved), _ptr(ws), _stream()))
+    if xn16 is not None and xn16.shape != xn.shape:
+        raise RuntimeError("mb_factor_attn_train: xn16 %s does not match xn %s" % (tuple(xn16.shape), tuple(xn.shape)))
+    _chk(lib.tcx_mb_factor_attn_train_fwd(_ptr(xn), tab, _ptr(residual), _ptr(y), B, H, W, C, heads, _ptr(saved), _ptr(ws), _ptr16(xn16),
+                                          _stream()))
     return y, saved
 
 
