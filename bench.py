@@ -379,6 +379,7 @@ def train_step_leg(torch, dev, world, rank, K, W):
         ops.set_flag("fork", 0)
         ops.set_flag("pdl", 0)
         from transception_b200 import mstr as _mstr
+        _branch_streams = _mstr.TRAIN_BRANCH_STREAMS
         _mstr.TRAIN_BRANCH_STREAMS = False
         runner._captured = False             # the measurement is over: eager steps (new gradient tensors) retire the graphs
         for kname in ("gemm_tc", "wgrad_tc", "dw_bwd_fused", "ln_bwd_fused", "dwln", "dwconv3x3"):
@@ -403,12 +404,37 @@ def train_step_leg(torch, dev, world, rank, K, W):
                                             "add 2-4 us per launch, so small-kernel numbers are lower bounds" % t0.elapsed_time(t1),
                              "peak_source": peak_kind + " hbm copy"})
         legs.sort(key=lambda r: -r["ms_per_step"])
+        if world == 1 and legs:
+            # the denominator of the shares: the SAME serial configuration (no stream forks, no PDL, no branch streams) captured
+            # as a CUDA graph and replayed — its time is the sum of the step's kernel durations (host enqueue cost removed), the
+            # quantity the ncu launch list under profiles/ sums
+            serial = TrainStepGraph(net, CeDiceLoss(NCLS), opt, BATCH, IN_CH, SIZE, device=dev, warmup=1, sample=(xh, lh))
+            serial.replay()
+            torch.cuda.synchronize(dev)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(3):
+                serial.replay()
+            s1.record()
+            torch.cuda.synchronize(dev)
+            serial_ms = s0.elapsed_time(s1) / 3
+            for leg in legs:
+                leg["share_of_step"] = leg["ms_per_step"] / serial_ms
+                leg["share_basis"] = ("event-bracketed launches of one eager, serial (no forks / PDL / branch streams) step, over the "
+                                      "replay time of that serial step captured as a CUDA graph (%.1f ms = the sum of its kernel "
+                                      "durations); event pairs add 2-4 us per launch, so small-kernel numbers are upper bounds of the "
+                                      "share" % serial_ms)
+            del serial
     except Exception as e:  # noqa: BLE001
         legs = [{"error": "%s: %s" % (type(e).__name__, e)}]
         ops.profile_enable("")
     finally:
         ops.set_flag("fork", 1)
         ops.set_flag("pdl", 1)
+        try:
+            _mstr.TRAIN_BRANCH_STREAMS = _branch_streams
+        except NameError:
+            pass
     imgs = world * BATCH * K
     step_s = ms / K * 1e-3
     peaks, peak_kind = _peaks()
