@@ -851,3 +851,60 @@ def test_flash_attention_backward(cuda_lib, B, Nq, Nk, big):
         assert torch.isfinite(got).all() and err <= 5e-3, "%s: relative L2 %.3e" % (name, err)
     dq2, dkv2 = ops.flash_attn_bwd(q.cuda(), kv.cuda(), out, lse, dout.cuda(), 0.125)
     assert torch.equal(dq, dq2) and torch.equal(dkv, dkv2), "flash backward is not bit-reproducible"
+
+
+def test_split_backward_and_bucket_parts(cuda_lib):
+    """The pieces of the overlapped data-parallel step (runtime.TrainStepGraph, world > 1) on one GPU: the backward cut between
+    encoder stages 2 and 3 (MSViT._grad_cut) followed by the second piece gives bit-identical gradients to one backward pass; after
+    the first piece exactly the parameters in front of the cut are still without gradient; FusedSGD.set_bucket_tail orders the flat
+    bucket as [behind the cut | in front of it] and gather_grads(0) / gather_grads(1) fill exactly those two parts."""
+    from networks.MSTr import MSTransception
+    from transception_b200.losses import CeDiceLoss
+    from transception_b200.optim import FusedSGD
+    gen = torch.Generator().manual_seed(0)
+    x = (torch.rand(2, 1, 224, 224, generator=gen) * 2 - 1).cuda()
+    labels = torch.randint(0, 9, (2, 224, 224), generator=gen).cuda()
+    torch.manual_seed(1234)
+    net = MSTransception(num_classes=9).cuda().train()
+    crit = CeDiceLoss(9)
+    crit(net(x), labels).backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    net.zero_grad(set_to_none=True)
+    bb = net.backbone
+    early = {id(p) for name in bb.EARLY_MODULES for p in getattr(bb, name).parameters()}
+    bb._grad_cut = []
+    try:
+        crit(net(x), labels).backward()
+        cut = list(bb._grad_cut)
+    finally:
+        bb._grad_cut = None
+    assert len(cut) == 2
+    for k, p in net.named_parameters():
+        if k in ref:
+            assert (p.grad is None) == (id(p) in early), k
+    torch.autograd.backward([o for o, _ in cut], [leaf.grad for _, leaf in cut])
+    for k, p in net.named_parameters():
+        assert (p.grad is not None) == (k in ref), k
+        if k in ref:
+            assert torch.equal(p.grad, ref[k]), k + ": split backward differs from the single pass"
+    # bucket order and the two gathers
+    opt = FusedSGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt.set_bucket_tail([p for p in net.parameters() if id(p) in early])
+    head = opt.gather_grads(0)
+    tab = opt._tables[0]
+    used = tab["used"]
+    n_head = sum(1 for p in used if id(p) not in early)
+    assert all(id(p) not in early for p in used[:n_head]) and all(id(p) in early for p in used[n_head:])
+    assert 0 < n_head < len(used) and head.numel() == tab["head_elems"] and head.numel() > 0.9 * tab["total"]
+    offs = tab["offs"].tolist()
+    flat = tab["flat"]
+    assert float(flat[tab["head_elems"]:].abs().sum()) == 0.0                       # the tail has not been gathered yet
+    tail = opt.gather_grads(1)
+    assert head.numel() + tail.numel() == tab["total"]
+    for i in (0, n_head - 1, n_head, len(used) - 1):
+        p = used[i]
+        assert torch.equal(flat[offs[i]:offs[i] + p.numel()], p.grad.flatten()), i
+    whole = flat.clone()
+    flat.zero_()
+    opt.gather_grads()
+    assert torch.equal(flat, whole)
