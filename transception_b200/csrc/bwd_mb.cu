@@ -117,31 +117,9 @@ __device__ __forceinline__ float dwk_point(const float* __restrict__ x, int ldx,
   }
   return acc;
 }
-template <bool FLIP, bool ADD>
-__global__ void __launch_bounds__(256) dwk3_kernel(const float* __restrict__ x, int ldx, Crpe3 f, float* __restrict__ y, int ldy, int B,
-                                                   int H, int W, int C) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)B * H * W * C;
-  if (idx >= total) return;
-  const int c = (int)(idx % C);
-  const long long p = idx / C;
-  const int px = (int)(p % W), py = (int)((p / W) % H);
-  float acc;
-  if (c < f.c1) {
-    acc = (f.b[0] && !FLIP) ? f.b[0][c] : 0.f;
-    acc = dwk_point<3, FLIP>(x, ldx, f.w[0] + (size_t)c * 9, p, px, py, H, W, c, acc);
-  } else if (c < f.c2) {
-    acc = (f.b[1] && !FLIP) ? f.b[1][c - f.c1] : 0.f;
-    acc = dwk_point<5, FLIP>(x, ldx, f.w[1] + (size_t)(c - f.c1) * 25, p, px, py, H, W, c, acc);
-  } else {
-    acc = (f.b[2] && !FLIP) ? f.b[2][c - f.c2] : 0.f;
-    acc = dwk_point<7, FLIP>(x, ldx, f.w[2] + (size_t)(c - f.c2) * 49, p, px, py, H, W, c, acc);
-  }
-  if (ADD) y[p * ldy + c] += acc; else y[p * ldy + c] = acc;
-}
-
-// ---- row-sweep form of dwk3_kernel.  Above, every output element loads its K*K taps AND its K*K filter values (the latter at a
-// stride of K*K floats across the lanes of a warp: 32 cache lines per load instruction).  Here a thread owns (channel, image row):
+// ---- the three crpe windows in one launch, row-sweep form.  (The first version gave every output element its own thread, which
+// loaded its K*K taps AND its K*K filter values — the latter at a stride of K*K floats across the lanes of a warp, 32 cache lines
+// per load instruction: 28 us on the 14x14 maps against 13 us here.)  A thread owns (channel, image row):
 // the channel's filter sits in registers, a K x K register window of x slides along the row, so an output costs K loads.
 constexpr int SC = 32, SL = 8;
 template <int K, bool FLIP, bool ADD>
@@ -221,39 +199,9 @@ __device__ __forceinline__ void dwk_wgrad_rows(const float* __restrict__ g, int 
     }
   }
 }
-// partials [blk][50][C]: taps 0 .. K*K-1 of the channel's window, slot 49 = bias sum
-__global__ void __launch_bounds__(RC * RL) dwk3_wgrad_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx,
-                                                             int B, int H, int W, int C, int c1, int c2, int rows, float* __restrict__ part) {
-  __shared__ float sm[RL][RC];
-  const int c = blockIdx.y * RC + threadIdx.x;
-  const long long M = (long long)B * H * W;
-  const long long r0 = (long long)blockIdx.x * rows;
-  const long long r1 = r0 + rows < M ? r0 + rows : M;
-  float acc[50];
-#pragma unroll
-  for (int t = 0; t < 50; t++) acc[t] = 0.f;
-  if (c < C) {
-    if (c < c1) dwk_wgrad_rows<3>(g, ldg, x, ldx, H, W, c, r0, r1, acc);
-    else if (c < c2) dwk_wgrad_rows<5>(g, ldg, x, ldx, H, W, c, r0, r1, acc);
-    else dwk_wgrad_rows<7>(g, ldg, x, ldx, H, W, c, r0, r1, acc);
-  }
-#pragma unroll
-  for (int t = 0; t < 50; t++) {
-    sm[threadIdx.y][threadIdx.x] = acc[t];
-    __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
-      float s = sm[0][threadIdx.x];
-#pragma unroll
-      for (int l = 1; l < RL; l++) s += sm[l][threadIdx.x];
-      part[((size_t)blockIdx.x * 50 + t) * C + c] = s;
-    }
-    __syncthreads();
-  }
-}
-
-// ---- crpe filter gradients, row-sweep form.  The kernel above gives every thread all K*K taps of its channel and a handful of
-// pixels (50 accumulators, 49 loads per pixel, a 50-round block fold, and a partial buffer of M/16 * 50 * C floats: 128 us on the
-// 28x28 maps).  Here a thread owns ONE tap row ky at a time and sweeps whole image rows with a K-wide register window of x sliding
+// ---- crpe filter gradients, row-sweep form.  (The first version gave every thread all K*K taps of its channel and a handful of
+// pixels: 50 accumulators, 49 loads per pixel, a 50-round block fold and a partial buffer of M/16 * 50 * C floats — 128 us on the
+// 28x28 maps.)  Partials [blk][50][C]: taps 0 .. K*K-1 of the channel's window, slot 49 = bias sum.  A thread owns ONE tap row ky at a time and sweeps whole image rows with a K-wide register window of x sliding
 // along the row: 2 loads and K FMAs per pixel, K accumulators; (32 channels x 8 row lanes) per block, one block per 8 image rows,
 // so the partial buffer is B*H/8 * 50 * C floats.  The association order is fixed (lane order, then block order in the fold).
 constexpr int WC = 32, WL = 8;

@@ -326,88 +326,12 @@ __global__ void __launch_bounds__(LW_T) ln_bwd_wide_kernel(const float* __restri
   }
 }
 
-// depthwise 3x3 (stride 1, pad 1) backward on NHWC rows, C channels: one thread = one pixel lane x 4 channels.
+// depthwise 3x3 (stride 1, pad 1) backward on NHWC rows, C channels, in ONE pass:
 //   dh[p][c] = du[p][c] + sum_t w[c][t] du[p - off(t)][c]                 (input gradient of u = conv(h) + b + h)
 //   part[blk][t][c] = sum_{p in block} du[p][c] h[p + off(t)][c], t < 9;  part[blk][9][c] = sum du[p][c]
-constexpr int DB_CT = 16;            // channel threads per block (x 4 channels = 64 channels)
-constexpr int DB_PL = 16;            // pixel lanes per block
-
-__global__ void __launch_bounds__(DB_CT * DB_PL, 2) dw_bwd_fused_kernel(const float* __restrict__ du, const __half* __restrict__ h,
-                                                                    const float* __restrict__ w, float* __restrict__ dh, int B, int H, int W,
-                                                                    int C, int pix_per_block, float* __restrict__ part) {
-  __shared__ float sm[DB_PL][10][DB_CT * 4 + 4];
-  __shared__ float4 swt[9][DB_CT];          // this block's 64 channels x 9 taps (kept out of the register file: two blocks per SM)
-  const int ct = threadIdx.x % DB_CT, pl = threadIdx.x / DB_CT;
-  const int c = (blockIdx.y * DB_CT + ct) * 4;
-  const bool cl = c < C;
-  const long long M = (long long)B * H * W;
-  const long long p0 = (long long)blockIdx.x * pix_per_block;
-  const long long p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
-  for (int i = threadIdx.x; i < 9 * DB_CT * 4; i += DB_CT * DB_PL) {
-    const int t = i / (DB_CT * 4), cc = i - t * (DB_CT * 4);
-    const int col = blockIdx.y * DB_CT * 4 + cc;
-    reinterpret_cast<float*>(&swt[t][0])[cc] = col < C ? __ldg(w + (size_t)col * 9 + t) : 0.f;
-  }
-  __syncthreads();
-  float acc[10][4];
-#pragma unroll
-  for (int t = 0; t < 10; t++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) acc[t][k] = 0.f;
-  if (cl) {
-    for (long long p = p0 + pl; p < p1; p += DB_PL) {
-      const int px = (int)(p % W), py = (int)((p / W) % H);
-      const float4 gc = *reinterpret_cast<const float4*>(du + p * C + c);
-      float o[4] = {gc.x, gc.y, gc.z, gc.w};
-      acc[9][0] += gc.x; acc[9][1] += gc.y; acc[9][2] += gc.z; acc[9][3] += gc.w;
-#pragma unroll
-      for (int ky = 0; ky < 3; ky++) {
-#pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-          const int t = ky * 3 + kx;
-          // weight gradient: neighbour of h at +offset
-          const int yy = py + ky - 1, xx = px + kx - 1;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const long long nb = p + (long long)(ky - 1) * W + (kx - 1);
-            const uint2 raw = *reinterpret_cast<const uint2*>(h + nb * C + c);
-            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-            const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-            acc[t][0] = fmaf(gc.x, h01.x, acc[t][0]); acc[t][1] = fmaf(gc.y, h01.y, acc[t][1]);
-            acc[t][2] = fmaf(gc.z, h23.x, acc[t][2]); acc[t][3] = fmaf(gc.w, h23.y, acc[t][3]);
-          }
-          // input gradient: du at -offset, same tap
-          const int ys = py - (ky - 1), xs = px - (kx - 1);
-          if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
-            const long long nb = p - (long long)(ky - 1) * W - (kx - 1);
-            const float4 gn = (t == 4) ? gc : *reinterpret_cast<const float4*>(du + nb * C + c);
-            const float4 wv = swt[t][ct];
-            o[0] = fmaf(wv.x, gn.x, o[0]); o[1] = fmaf(wv.y, gn.y, o[1]);
-            o[2] = fmaf(wv.z, gn.z, o[2]); o[3] = fmaf(wv.w, gn.w, o[3]);
-          }
-        }
-      }
-      *reinterpret_cast<float4*>(dh + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < 10; t++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) sm[pl][t][ct * 4 + k] = acc[t][k];
-  __syncthreads();
-  for (int i = threadIdx.x; i < 10 * DB_CT * 4; i += DB_CT * DB_PL) {
-    const int t = i / (DB_CT * 4), cc = i - t * (DB_CT * 4);
-    const int col = blockIdx.y * DB_CT * 4 + cc;
-    if (col >= C) continue;
-    float a = sm[0][t][cc];
-#pragma unroll
-    for (int l = 1; l < DB_PL; l++) a += sm[l][t][cc];
-    part[((size_t)blockIdx.x * 10 + t) * C + col] = a;
-  }
-}
-
-// ---- row-sweep form of dw_bwd_fused_kernel: a thread owns (2 channels, image row) and slides 3x3 register windows of du and h
-// along the row — 6 loads per pixel instead of 17, the channel's filter in registers; (32 channel pairs x 8 rows) per block, the
-// block's (9 + 1) x 64 partial sums folded over its 8 row lanes in lane order.  Same outputs and partial layout as above.
+// Row sweep: a thread owns (2 channels, image row) and slides 3x3 register windows of du and h along the row — 6 loads per pixel
+// (the first version, one thread per pixel x 4 channels, took 17), the channel's filter in registers; (32 channel pairs x 8 rows)
+// per block, the block's (9 + 1) x 64 partial sums folded over its 8 row lanes in lane order.
 constexpr int DS_C = 32, DS_L = 8;
 __global__ void __launch_bounds__(DS_C * DS_L) dw_bwd_sweep_kernel(const float* __restrict__ du, const __half* __restrict__ h,
                                                                    const float* __restrict__ w, float* __restrict__ dh, int B, int H, int W,
