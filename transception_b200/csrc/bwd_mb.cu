@@ -99,24 +99,6 @@ struct Crpe3 {
   const float* b[3];     // [Cg_j] or null
   int c1, c2;            // channel boundaries
 };
-template <int K, bool FLIP>
-__device__ __forceinline__ float dwk_point(const float* __restrict__ x, int ldx, const float* __restrict__ wc, long long p, int px, int py,
-                                           int H, int W, int c, float acc) {
-#pragma unroll
-  for (int ky = 0; ky < K; ky++) {
-    const int dy = FLIP ? K / 2 - ky : ky - K / 2;
-    const int yy = py + dy;
-    if (yy < 0 || yy >= H) continue;
-#pragma unroll
-    for (int kx = 0; kx < K; kx++) {
-      const int dx = FLIP ? K / 2 - kx : kx - K / 2;
-      const int xx = px + dx;
-      if (xx < 0 || xx >= W) continue;
-      acc = fmaf(__ldg(wc + ky * K + kx), x[(p + (long long)dy * W + dx) * ldx + c], acc);
-    }
-  }
-  return acc;
-}
 // ---- the three crpe windows in one launch, row-sweep form.  (The first version gave every output element its own thread, which
 // loaded its K*K taps AND its K*K filter values — the latter at a stride of K*K floats across the lanes of a warp, 32 cache lines
 // per load instruction: 28 us on the 14x14 maps against 13 us here.)  A thread owns (channel, image row):
