@@ -419,6 +419,10 @@ int tcx_patch_im2row_fwd(const float* x, int B, int Cin, int H, int W, float* pa
 int tcx_layernorm_dual_fwd(const float* x, const float* w, const float* b, float* y32, void* y16, long long M, int C, float eps,
                            void* stream);
 
+/* out = srcs[0] + srcs[1] + ... (n <= 16 fp32 tensors of `numel` elements, added in index order): the gradient of a parameter that
+ * the blocks of an MHCAEncoder share (ConvPosEnc / ConvRelPosEnc, MSTr.py:966-978) from the per-block gradients, one launch. */
+int tcx_sum_tensors(const void* const* srcs, int n, long long numel, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,27 @@ class ScaleReducePackFn(torch.autograd.Function):
         return (dx,) + tuple(g)
 
 
+class FanOutFn(torch.autograd.Function):
+    """n aliases of a parameter that n blocks share (the ConvPosEnc / ConvRelPosEnc of an MHCAEncoder, MSTr.py:966-978): every
+    block differentiates its own alias, and the n gradients are added by ONE kernel here — instead of n - 1 accumulation kernels
+    interleaved with the blocks' backward chains."""
+
+    @staticmethod
+    def forward(ctx, w, n):
+        return tuple(w.view_as(w) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        live = [g for g in gs if g is not None]
+        if not live:
+            return None, None
+        return (live[0] if len(live) == 1 else ops.sum_tensors(live)), None
+
+
+def fan_out(w, n):
+    return FanOutFn.apply(w, n)
+
+
 class PatchEmbedConvFn(torch.autograd.Function):
     """OverlapPatchEmbeddings.proj (7x7 / 4 conv, MSTr.py:299-302) on the image batch: exact fp32 forward on the fused stem kernel;
     the image needs no gradient, the weight gradient is one im2row launch + the Linear weight-gradient kernel."""

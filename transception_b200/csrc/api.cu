@@ -2510,4 +2510,11 @@ int tcx_patch_im2row_fwd(const float* x, int B, int Cin, int H, int W, float* pa
   return launch_patch_im2row(x, Cin * plane, Cin == 1 ? 0 : plane, B, H, W, Kp, patches, S(stream));
 }
 
+// out = sum of n <= 16 equally sized fp32 tensors, added in index order: the gradient of a parameter shared by the blocks of an
+// MHCAEncoder (ConvPosEnc / ConvRelPosEnc, MSTr.py:966-978) from the gradients each block produced
+int tcx_sum_tensors(const void* const* srcs, int n, long long numel, float* out, void* stream) {
+  TCX_REQUIRE(srcs && out, "sum_tensors: null pointer");
+  return launch_sum_tensors(reinterpret_cast<const float* const*>(srcs), n, numel, out, S(stream));
+}
+
 }  // extern "C"

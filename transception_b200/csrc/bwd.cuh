@@ -58,6 +58,7 @@ int ln_bwd_fused_blocks(long long M, int C);   // partial buffer: 2 * ln_bwd_fus
 int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, const float* beta, float eps, int gelu, float* du,
                         float* act, const float* dres, long long M, int C, float* part, cudaStream_t st);
 int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st);
+int launch_sum_tensors(const float* const* srcs, int n, long long numel, float* out, cudaStream_t st);
 int launch_bwd_ln_fold(const float* part, int nblk, int C, float* dgamma, float* dbeta, cudaStream_t st);
 // Mix-FFN depthwise conv backward in one pass: dh = du + conv^T(du), part = 10 * blocks * C filter / bias partials (fold with
 // launch_bwd_dw_fold); h is the fp16 fc1 output

@@ -426,7 +426,29 @@ __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ y,
   reinterpret_cast<float4*>(y)[i] = a;
 }
 
+// out = ((s0 + s1) + s2) + ... over n <= 16 equally sized tensors (the gradients a parameter shared by the blocks of an encoder
+// receives from each of them): one launch instead of n - 1 accumulation kernels, fixed order
+struct SumSrcs {
+  const float* p[16];
+};
+__global__ void __launch_bounds__(256) sum_tensors_kernel(SumSrcs s, int n, long long numel, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= numel) return;
+  float a = s.p[0][i];
+  for (int k = 1; k < n; k++) a += s.p[k][i];
+  out[i] = a;
+}
+
 }  // namespace
+
+int launch_sum_tensors(const float* const* srcs, int n, long long numel, float* out, cudaStream_t st) {
+  TCX_REQUIRE(n >= 1 && n <= 16, "sum_tensors: 1..16 sources (got %d)", n);
+  if (numel == 0) return 0;
+  SumSrcs s{};
+  for (int k = 0; k < n; k++) { TCX_REQUIRE(srcs[k] != nullptr, "sum_tensors: source %d is null", k); s.p[k] = srcs[k]; }
+  sum_tensors_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, st>>>(s, n, numel, out);
+  return tcx_check_launch("sum_tensors");
+}
 
 int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
   TCX_REQUIRE(n % 4 == 0 && (((uintptr_t)y | (uintptr_t)x) & 15) == 0, "add_inplace: n %% 4 != 0 or unaligned");

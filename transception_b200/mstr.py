@@ -70,6 +70,22 @@ def _parallel_branches(device, fns, inputs=()):
     return outs
 
 
+# Parameters shared by the blocks of an MHCAEncoder (its ConvPosEnc / ConvRelPosEnc): in the training row every block takes its
+# own alias from a fan-out node (autograd.FanOutFn), so the per-block gradients are added once, by one kernel.  Per thread:
+# nn.DataParallel runs its replicas in threads.
+_FANOUT = __import__("threading").local()
+
+
+def _shared(p):
+    """The alias reserved for this use of a shared parameter, or the parameter itself outside an MHCAEncoder training forward."""
+    d = getattr(_FANOUT, "d", None)
+    if d:
+        pool = d.get(id(p))
+        if pool:
+            return pool.pop()
+    return p
+
+
 def _nhwc(x):
     """NCHW-shaped tensor (any strides) -> contiguous [B,H,W,C] (free for channels_last)."""
     return x.permute(0, 2, 3, 1).contiguous()
@@ -497,7 +513,7 @@ class ConvPosEnc(nn.Module):
     def forward(self, x, size):
         H, W = size
         if _recording(x, self.proj.weight):
-            return tcx_autograd.dwconv_tokens(x, H, W, self.proj.weight, self.proj.bias, True)
+            return tcx_autograd.dwconv_tokens(x, H, W, _shared(self.proj.weight), _shared(self.proj.bias), True)
         return ops.dwconv_tokens(x.contiguous(), H, W, self.proj.weight, self.proj.bias, add_input=True)
 
 
@@ -548,6 +564,7 @@ class FactorAtt_ConvRelPosEnc(nn.Module):
         H, W = size
         if _recording(x, self.qkv.weight):
             heads, _, qkvw, qkvb, cw, cb, splits, pw, pb = self.args()
+            cw, cb = [_shared(w) for w in cw], [_shared(b) for b in cb]
             ops._check_crpe(splits, cw, heads)
             return tcx_autograd.factor_att(x, H, W, heads, qkvw, qkvb, cw, cb, pw, pb, residual=residual)
         return ops.mb_factor_attn(x.contiguous(), H, W, *self.args(), residual=residual)
@@ -590,13 +607,25 @@ class MHCAEncoder(nn.Module):
                       qk_scale=qk_scale, shared_cpe=self.cpe, shared_crpe=self.crpe)
             for idx in range(self.num_layers)])
 
+    def run_blocks_train(self, x, size):
+        """The blocks one after the other on tokens x [B, N, C] (training row); the parameters they share (ConvPosEnc,
+        ConvRelPosEnc) are handed out as per-block aliases of a fan-out node, see _shared."""
+        L = len(self.MHCA_layers)
+        shared = [self.cpe.proj.weight, self.cpe.proj.bias] + [t for c in self.crpe.conv_list for t in (c.weight, c.bias)]
+        prev = getattr(_FANOUT, "d", None)
+        _FANOUT.d = {id(p): list(tcx_autograd.fan_out(p, L)) for p in shared if p.requires_grad} if L > 1 else None
+        try:
+            for blk in self.MHCA_layers:
+                x = blk(x, size)
+        finally:
+            _FANOUT.d = prev
+        return x
+
     def forward(self, x, size):
         H, W = size
         B = x.shape[0]
         if _recording(x, self.cpe.proj.weight):
-            for blk in self.MHCA_layers:
-                x = blk(x, size)
-            return _as_nchw(x.reshape(B, H, W, -1))
+            return _as_nchw(self.run_blocks_train(x, size).reshape(B, H, W, -1))
         y = ops.mhca_blocks(x.contiguous().unsqueeze(0), H, W, [list(self.MHCA_layers)])[0]
         return _as_nchw(y.view(B, H, W, -1))
 
@@ -675,9 +704,7 @@ class MHCA_stage(nn.Module):
         if self.training:
             def branch(i):
                 def run():
-                    t = stacked[i].reshape(B, H * W, C)
-                    for blk in self.mhca_blks[i].MHCA_layers:
-                        t = blk(t, (H, W))
+                    t = self.mhca_blks[i].run_blocks_train(stacked[i].reshape(B, H * W, C), (H, W))
                     return t.reshape(B, H, W, C)
                 return run
             # the residual block and the three transformer branches are independent until the IFF concatenation

@@ -75,6 +75,7 @@ _PROTOS = {
     "tcx_iff_coordatt_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tcx_iff_coordatt_fwd": (_i, [_pp, _pp, _f, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tcx_bridge_regroup_fwd": (_i, [_pp, _vp, _i, _i, _vp]),
+    "tcx_sum_tensors": (_i, [_pp, _i, _ll, _vp, _vp]),
     "tcx_patch_im2row_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "tcx_final_head_train_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "tcx_final_head_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -456,6 +457,22 @@ def patch_embed_ln(x, w, b, stride, padding, lnw, lnb, eps):
     out = torch.empty((B, Ho * Wo, 64), device=x.device, dtype=x.dtype)
     _chk(lib.tcx_patch_embed_ln_fwd(_ptr(x), B, Cin, H, W, _ptr(_d(w)), _ptr(_d(b)), _ptr(_d(lnw)), _ptr(_d(lnb)),
                                     eps, _ptr(out), _stream()))
+    return out
+
+
+def sum_tensors(ts):
+    """ts[0] + ts[1] + ... (up to 16 equally shaped fp32 tensors, index order) in one launch."""
+    require_cuda(ts[0])
+    lib = load_library()
+    ts = [t.contiguous() for t in ts]
+    out = torch.empty_like(ts[0])
+    while len(ts) > 16:                      # deeper fan-outs: fold the first 16 and continue
+        head = torch.empty_like(ts[0])
+        tab = (ctypes.c_void_p * 16)(*[_ptr(t) for t in ts[:16]])
+        _chk(lib.tcx_sum_tensors(tab, 16, head.numel(), _ptr(head), _stream()))
+        ts = [head] + ts[16:]
+    tab = (ctypes.c_void_p * len(ts))(*[_ptr(t) for t in ts])
+    _chk(lib.tcx_sum_tensors(tab, len(ts), out.numel(), _ptr(out), _stream()))
     return out
 
 
