@@ -38,34 +38,73 @@ __device__ __forceinline__ void fold_lanes(float (&acc)[K], float (*sm)[RC]) {
   }
 }
 
-// partial sums of (x - mean)^2 per column; mean = sum[c] / M
-__global__ void __launch_bounds__(RC * RL) bn_var_kernel(const float* __restrict__ x, const float* __restrict__ sum, long long M, int C,
-                                                         int rows, float* __restrict__ part) {
+// ---- batch statistics in ONE pass over x + one fold (6 -> 3 launches per BatchNorm forward).  A block leaves, per column, the
+// sums of d = x - shift and d^2 over its rows with shift = the column's value in the block's first row (close to the data, so the
+// shifted sums lose nothing) and its row count; the fold combines the blocks' (count, mean, M2) with Chan's update in block order —
+// a fixed association, and the same variance as the two-pass form up to fp32 rounding.
+__global__ void __launch_bounds__(RC * RL) bn_stats_kernel(const float* __restrict__ x, long long M, int C, int rows, float* __restrict__ part) {
   __shared__ float sm[RL][RC];
   const int c = blockIdx.y * RC + threadIdx.x;
   const long long r0 = (long long)blockIdx.x * rows, r1 = r0 + rows < M ? r0 + rows : M;
-  float acc[1] = {0.f};
-  if (c < C) {
-    const float mean = sum[c] / (float)M;
-    for (long long r = r0 + threadIdx.y; r < r1; r += RL) { const float d = x[r * C + c] - mean; acc[0] = fmaf(d, d, acc[0]); }
+  float acc[2] = {0.f, 0.f};
+  float shift = 0.f;
+  if (c < C && r0 < r1) {
+    shift = x[r0 * C + c];
+    for (long long r = r0 + threadIdx.y; r < r1; r += RL) {
+      const float d = x[r * C + c] - shift;
+      acc[0] += d;
+      acc[1] = fmaf(d, d, acc[1]);
+    }
   }
-  fold_lanes<1>(acc, sm);
-  if (threadIdx.y == 0 && c < C) part[(size_t)blockIdx.x * C + c] = acc[0];
+  fold_lanes<2>(acc, sm);
+  if (threadIdx.y == 0 && c < C) {
+    float* p = part + (size_t)blockIdx.x * 3 * C;
+    p[c] = acc[0]; p[C + c] = acc[1]; p[2 * C + c] = shift;
+  }
 }
-// stat[0][c] = mean, stat[1][c] = 1/sqrt(var + eps); running statistics as nn.BatchNorm2d (momentum, unbiased variance)
-__global__ void __launch_bounds__(256) bn_finish_kernel(const float* __restrict__ sum, const float* __restrict__ ssq, long long M, int C,
-                                                        float eps, float momentum, float* __restrict__ stat, float* __restrict__ rm,
-                                                        float* __restrict__ rv) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
-  const float mean = sum[c] / (float)M, var = ssq[c] / (float)M;
+// one thread row of 8 lanes per column: lane l walks blocks l, l+8, ... (Chan), then the eight lane results are combined in lane order
+__global__ void __launch_bounds__(256) bn_stats_fold_kernel(const float* __restrict__ part, int nblk, int rows, long long M, int C, float eps,
+                                                            float momentum, float* __restrict__ stat, float* __restrict__ rm,
+                                                            float* __restrict__ rv) {
+  __shared__ float sn[8][32], smean[8][32], sm2[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x, l = threadIdx.y;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  if (c < C) {
+    for (int b = l; b < nblk; b += 8) {
+      const long long r0 = (long long)b * rows;
+      const long long cnt = (r0 + rows < M ? r0 + rows : M) - r0;
+      if (cnt <= 0) continue;
+      const float* p = part + (size_t)b * 3 * C;
+      const float nb = (float)cnt, s1 = p[c], s2 = p[C + c], sh = p[2 * C + c];
+      const float mb = sh + s1 / nb, m2b = s2 - s1 * s1 / nb;
+      const float tot = n + nb, delta = mb - mean;
+      mean += delta * (nb / tot);
+      m2 += m2b + delta * delta * (n * nb / tot);
+      n = tot;
+    }
+  }
+  sn[l][threadIdx.x] = n; smean[l][threadIdx.x] = mean; sm2[l][threadIdx.x] = m2;
+  __syncthreads();
+  if (l != 0 || c >= C) return;
+  n = sn[0][threadIdx.x]; mean = smean[0][threadIdx.x]; m2 = sm2[0][threadIdx.x];
+  for (int k = 1; k < 8; k++) {
+    const float nb = sn[k][threadIdx.x];
+    if (nb <= 0.f) continue;
+    const float tot = n + nb, delta = smean[k][threadIdx.x] - mean;
+    mean += delta * (nb / tot);
+    m2 += sm2[k][threadIdx.x] + delta * delta * (n * nb / tot);
+    n = tot;
+  }
+  const float var = m2 / (float)M;
   stat[c] = mean;
   stat[C + c] = rsqrtf(var + eps);
   if (rm) {
     rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
-    rv[c] = (1.f - momentum) * rv[c] + momentum * (M > 1 ? ssq[c] / (float)(M - 1) : var);
+    rv[c] = (1.f - momentum) * rv[c] + momentum * (M > 1 ? m2 / (float)(M - 1) : var);
   }
 }
+// stat[0][c] = mean, stat[1][c] = 1/sqrt(var + eps) (written by the fold above; running statistics as nn.BatchNorm2d: momentum,
+// unbiased variance)
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat, const float* __restrict__ w,
                                                        const float* __restrict__ b, int act, long long n, int C, float* __restrict__ y) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -250,33 +289,35 @@ inline int rows_for(long long M, int nblk) { return (int)((M + nblk - 1) / nblk 
 }  // namespace
 
 // BatchNorm (batch statistics) + activation forward.  stat: 2*C floats (mean | 1/std) kept for backward; scratch: C * (2 + 2*blocks)
-size_t bn_train_scratch_floats(long long M, int C) { return (size_t)C * (2 + 2 * (size_t)bwd_red_blocks(M)) + 64; }
+size_t bn_train_scratch_floats(long long M, int C) { return (size_t)C * (2 + 3 * (size_t)bwd_red_blocks(M)) + 64; }
 int launch_bn_train_fwd(const float* x, const float* w, const float* b, float eps, float momentum, int act, float* y, float* stat, float* rm,
                         float* rv, long long M, int C, float* scratch, cudaStream_t st) {
   TCX_REQUIRE(M > 0 && C > 0, "bn_train_fwd: empty input");
   const int nblk = bwd_red_blocks(M);
-  float* sum = scratch; float* ssq = scratch + C; float* part = scratch + 2 * C;
-  TCX_TRY(launch_bwd_colsum(x, M, C, C, part, sum, st));
-  bn_var_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(x, sum, M, C, rows_for(M, nblk), part);
-  TCX_TRY(tcx_check_launch("bn_var"));
-  TCX_TRY(launch_bwd_fold(part, nblk, C, ssq, st));
-  bn_finish_kernel<<<cdiv(C, 256), 256, 0, st>>>(sum, ssq, M, C, eps, momentum, stat, rm, rv);
-  TCX_TRY(tcx_check_launch("bn_finish"));
+  const int rows = rows_for(M, nblk);
+  float* part = scratch + 2 * C;
+  bn_stats_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(x, M, C, rows, part);
+  TCX_TRY(tcx_check_launch("bn_stats"));
+  bn_stats_fold_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(part, nblk, rows, M, C, eps, momentum, stat, rm, rv);
+  TCX_TRY(tcx_check_launch("bn_stats_fold"));
   bn_apply_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(x, stat, w, b, act, M * C, C, y);
   return tcx_check_launch("bn_apply");
 }
+// dw and db adjacent in memory (db == dw + C: the binding allocates them as one [2][C] tensor): the fold writes them in place
 int launch_bn_train_bwd(const float* x, const float* dy, const float* stat, const float* w, const float* b, int act, float* dx, float* dw,
                         float* db, long long M, int C, float* scratch, cudaStream_t st) {
   const int nblk = bwd_red_blocks(M);
-  float* dwdb = scratch; float* part = scratch + 2 * C;
+  const bool adjacent = db == dw + C;
+  float* dwdb = adjacent ? dw : scratch; float* part = scratch + 2 * C;
   bn_bwd_cols_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(x, dy, stat, w, b, act, M, C, rows_for(M, nblk), part);
   TCX_TRY(tcx_check_launch("bn_bwd_cols"));
   TCX_TRY(launch_bwd_fold(part, nblk, 2 * (long long)C, dwdb, st));       // partial layout [blk][2][C] -> [dw | db]
   bn_bwd_dx_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(x, dy, stat, w, b, act, dwdb, M, C, dx);
   TCX_TRY(tcx_check_launch("bn_bwd_dx"));
-  TCX_REQUIRE(cudaMemcpyAsync(dw, dwdb, sizeof(float) * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
-                  cudaMemcpyAsync(db, dwdb + C, sizeof(float) * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess,
-              "bn_train_bwd: gradient copy failed");
+  if (!adjacent)
+    TCX_REQUIRE(cudaMemcpyAsync(dw, dwdb, sizeof(float) * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
+                    cudaMemcpyAsync(db, dwdb + C, sizeof(float) * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess,
+                "bn_train_bwd: gradient copy failed");
   return 0;
 }
 

@@ -1367,7 +1367,9 @@ def bn_act_train_bwd(x, dy, stat, w, b, act):
     x, dy = x.contiguous(), dy.contiguous()
     C = x.shape[-1]
     M = x.numel() // C
-    dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+    dx = torch.empty_like(x)
+    dwdb = torch.empty((2, C), dtype=w.dtype, device=w.device)       # adjacent: the fold kernel writes both in place
+    dw, db = dwdb[0], dwdb[1]
     ws = _ws(lib.tcx_bn_act_train_workspace_bytes(M, C), x)
     _chk(lib.tcx_bn_act_train_bwd(_ptr(x), _ptr(dy), _ptr(stat), _ptr(_d(w)), _ptr(_d(b)), act, _ptr(dx), _ptr(dw), _ptr(db), M, C,
                                   _ptr(ws), _stream()))
