@@ -314,27 +314,6 @@ def train_step_leg(torch, dev, world, rank, K, W):
     run()
     torch.cuda.synchronize(dev)
     grads_match = weights_match = None
-    if world > 1:
-        # SURVEY 8d config 4: the all-reduced gradient must equal the mean of the ranks' own gradients (identical weights,
-        # rank-specific data, per-rank BatchNorm statistics) and be identical on every rank afterwards
-        runner.replay_backward()            # forward + loss + backward graph(s): write the static gradient tensors
-        torch.cuda.synchronize(dev)
-        tab = opt._tables[0]
-        with_grad = tab["used"]
-        pick = [0, len(with_grad) // 3, 2 * len(with_grad) // 3, len(with_grad) - 1]
-        own = torch.cat([with_grad[i].grad.flatten()[:4096].clone() for i in pick])
-        gathered = [torch.empty_like(own) for _ in range(world)]
-        dist.all_gather(gathered, own)
-        want = torch.stack(gathered).mean(0)
-        runner.replay_reduce()              # gather into the flat bucket + all-reduce (average)
-        offs = tab["offs"].tolist()
-        got = torch.cat([tab["flat"][offs[i]:offs[i] + min(4096, with_grad[i].numel())] for i in pick])
-        mean_ok = bool((got - want).abs().max() <= 1e-6 * want.abs().max() + 1e-12)
-        chk = torch.stack([tab["flat"].double().sum(), tab["flat"].double().abs().sum()])
-        allc = [torch.empty_like(chk) for _ in range(world)]
-        dist.all_gather(allc, chk)
-        grads_match = mean_ok and all(torch.equal(allc[0], c) for c in allc)
-        runner.replay_update()              # SGD update from the reduced bucket
     for _ in range(2):
         run()
     torch.cuda.synchronize(dev)
@@ -371,6 +350,33 @@ def train_step_leg(torch, dev, world, rank, K, W):
         weights_match = all(torch.equal(allw[0], c) for c in allw)
     ms, e2e_ms = t.tolist()
     last_loss = float(lossh)
+    if world > 1:
+        # SURVEY 8d config 4: the all-reduced gradient must equal the mean of the ranks' own gradients (identical weights,
+        # rank-specific data, per-rank BatchNorm statistics) and be identical on every rank afterwards.  The check replays the
+        # step's pieces; a runner that holds the whole step as ONE graph (single_graph=True) is replaced by one with separate
+        # graphs for it (the timing is over: the optimizer's tables may be re-built)
+        overlap_kind = "one graph, collectives captured" if getattr(runner, "single_graph", False) and getattr(runner, "overlap", False) else "separate graphs"
+        if getattr(runner, "single_graph", False) and getattr(runner, "overlap", False):
+            runner = TrainStepGraph(net, CeDiceLoss(NCLS), opt, BATCH, IN_CH, SIZE, device=dev, warmup=1, sample=(xh, lh), single_graph=False)
+        runner.replay_backward()            # forward + loss + backward graph(s): write the static gradient tensors
+        torch.cuda.synchronize(dev)
+        tab = opt._tables[0]
+        with_grad = tab["used"]
+        pick = [0, len(with_grad) // 3, 2 * len(with_grad) // 3, len(with_grad) - 1]
+        own = torch.cat([with_grad[i].grad.flatten()[:4096].clone() for i in pick])
+        gathered = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(gathered, own)
+        want = torch.stack(gathered).mean(0)
+        runner.replay_reduce()              # gather into the flat bucket + all-reduce (average)
+        offs = tab["offs"].tolist()
+        got = torch.cat([tab["flat"][offs[i]:offs[i] + min(4096, with_grad[i].numel())] for i in pick])
+        mean_ok = bool((got - want).abs().max() <= 1e-6 * want.abs().max() + 1e-12)
+        chk = torch.stack([tab["flat"].double().sum(), tab["flat"].double().abs().sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        grads_match = mean_ok and all(torch.equal(allc[0], c) for c in allc)
+        runner.replay_update()              # SGD update from the reduced bucket
+        torch.cuda.synchronize(dev)
     # roofline legs: the kernels with the largest shares of the step, each timed live with CUDA-event pairs on the launching
     # stream over one eager step (serial: no stream forks, no PDL); algorithmic bytes are counted by the library per launch
     legs, traffic = [], _traffic_table()
@@ -455,8 +461,8 @@ def train_step_leg(torch, dev, world, rank, K, W):
             "weights_identical_across_ranks_after_training": weights_match,
             "grad_allreduce": ("backward cut between encoder stages 2 and 3: the gradients behind the cut (98 % of the elements) are "
                                "gathered into the head of one flat fp32 bucket and all-reduced (NCCL, average) asynchronously while "
-                               "the backward of stages 2-1 runs; the tail follows; the fused update reads the bucket in place"
-                               if getattr(runner, "overlap", False) else
+                               "the backward of stages 2-1 runs; the tail follows; the fused update reads the bucket in place (timed runner: "
+                               + overlap_kind + ")" if getattr(runner, "overlap", False) else
                                "gradients gathered into one flat fp32 bucket by one kernel, one NCCL all-reduce (average), the fused "
                                "update reads the bucket in place") if world > 1 else None,
             "dtype": "fp16 storage / fp16+TF32 tensor-core forward, TF32 tensor-core backward (operands read in place), fp32 "

@@ -35,6 +35,28 @@ class FusedSGD(torch.optim.Optimizer):
         self._tables, self._lr_t, self._lr_seen = {}, {}, {}
         self.norm_coef = None           # device [norm, coef] of the last step (max_norm set)
         self._tail_ids = None           # set_bucket_tail: parameters placed at the END of the flat bucket
+        self._frozen = False            # freeze_tables: the tables are used as they are (graph capture with late-bound gradient pointers)
+
+    def freeze_tables(self, on=True):
+        """While frozen, the device tables built by the last eager step are used as they are, whatever ``p.grad`` currently is:
+        a graph capture that contains the gathers / the update records the tables' ADDRESSES, and ``refresh_grad_ptrs()`` writes
+        the addresses of the gradient tensors allocated inside that capture into them afterwards."""
+        if on and not self._tables:
+            raise RuntimeError("FusedSGD.freeze_tables: no tables yet (run one eager step first)")
+        if self._frozen and not on:
+            self._tables.clear()          # their gradient pointers belong to a captured graph: rebuild from the next eager step
+        self._frozen = bool(on)
+
+    def refresh_grad_ptrs(self):
+        """Rewrite the gradient-pointer tables in place from the current ``p.grad`` tensors of the SAME parameters (same order)."""
+        for tab in self._tables.values():
+            used = tab["used"]
+            if any(p.grad is None or p.grad.numel() != p.numel() or not p.grad.is_contiguous() or p.grad.dtype != torch.float32
+                   for p in used):
+                raise RuntimeError("FusedSGD.refresh_grad_ptrs: a parameter of the table has no (contiguous fp32) gradient")
+            tab["g"].copy_(torch.tensor([p.grad.data_ptr() for p in used], dtype=torch.int64))
+            tab["key"] = tuple((p.data_ptr(), p.grad.data_ptr()) for p in used)
+            tab["keep"] = (tab["keep"][0], [p.grad for p in used])
 
     def set_bucket_tail(self, params):
         """Order the flat gradient bucket as [all other parameters | ``params``] (each part in registration order).  The data-parallel
@@ -44,6 +66,8 @@ class FusedSGD(torch.optim.Optimizer):
 
     # ---- tables ---------------------------------------------------------------------------------------------------------------
     def _group_table(self, gi, group):
+        if self._frozen:
+            return self._tables.get(gi)
         used = [p for p in group["params"] if p.grad is not None]
         n_head = len(used)
         if self._tail_ids:
