@@ -2,6 +2,7 @@
 // and backward (DWConv2d_BN MSTr.py:355-362, Conv2d_BN :399-404, CoordAtt.bn1 :1331), the strided depthwise 3x3 of RIPM
 // (input and weight gradients), and the pooling / gating of CoordAtt (:1322-1348).  NHWC fp32, rows = pixels.
 // Reductions over pixels are two-pass and ordered (bit-reproducible).
+#include <algorithm>
 #include "bwd.cuh"
 
 namespace {
@@ -293,7 +294,8 @@ size_t bn_train_scratch_floats(long long M, int C) { return (size_t)C * (2 + 3 *
 int launch_bn_train_fwd(const float* x, const float* w, const float* b, float eps, float momentum, int act, float* y, float* stat, float* rm,
                         float* rv, long long M, int C, float* scratch, cudaStream_t st) {
   TCX_REQUIRE(M > 0 && C > 0, "bn_train_fwd: empty input");
-  const int nblk = bwd_red_blocks(M);
+  // two blocks per SM are enough to stream x; the fold walks nblk / 8 partials per lane with a dependent Chan update each
+  const int nblk = std::min(bwd_red_blocks(M), 296);
   const int rows = rows_for(M, nblk);
   float* part = scratch + 2 * C;
   bn_stats_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(x, M, C, rows, part);
