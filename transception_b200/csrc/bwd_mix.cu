@@ -44,13 +44,23 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused64_kernel(const flo
   float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
   const long long stride = (long long)gridDim.x * LF_WARPS * 2;
   // both halves of a warp run the same number of iterations (full-mask shuffles): out-of-range rows compute on zeros
-  for (long long base = (long long)blockIdx.x * LF_WARPS * 2 + warp * 2; base < M; base += stride) {
+  // the next row's operands are loaded before the current row is reduced (one-deep software pipeline: the two shuffle reductions
+  // of a row no longer wait for HBM)
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long base = (long long)blockIdx.x * LF_WARPS * 2 + warp * 2;
+  float4 nx4 = zero4, nd4 = zero4;
+  if (base + hw < M && live) {
+    nx4 = *reinterpret_cast<const float4*>(u + (base + hw) * C + c);
+    nd4 = *reinterpret_cast<const float4*>(dz + (base + hw) * C + c);
+  }
+  for (; base < M; base += stride) {
     const long long row = base + hw;
     const bool rl = row < M && live;
-    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = x4;
-    if (rl) {
-      x4 = *reinterpret_cast<const float4*>(u + row * C + c);
-      d4 = *reinterpret_cast<const float4*>(dz + row * C + c);
+    const float4 x4 = nx4, d4 = nd4;
+    nx4 = zero4; nd4 = zero4;
+    if (row + stride < M && live) {
+      nx4 = *reinterpret_cast<const float4*>(u + (row + stride) * C + c);
+      nd4 = *reinterpret_cast<const float4*>(dz + (row + stride) * C + c);
     }
     const float mean = half_sum((x4.x + x4.y) + (x4.z + x4.w)) * invC;
     float q = 0.f;
