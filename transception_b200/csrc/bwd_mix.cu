@@ -147,16 +147,27 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float
     for (int q = 0; q < 4; q++) { ag[j][q] = 0.f; ab[j][q] = 0.f; }
 
   const long long stride = (long long)gridDim.x * LF_WARPS;
-  for (long long row = (long long)blockIdx.x * LF_WARPS + warp; row < M; row += stride) {
-    const float* ur = u + row * C;
-    const float* dr = dz + row * C;
+  // one-deep software pipeline over rows: the next row's operands are in flight while this row is reduced
+  float4 nx4[NV], nd4[NV];
+  long long row = (long long)blockIdx.x * LF_WARPS + warp;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const int c = lane * 4 + 128 * j;
+    const bool ld = live[j] && row < M;
+    nx4[j] = ld ? *reinterpret_cast<const float4*>(u + row * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    nd4[j] = ld ? *reinterpret_cast<const float4*>(dz + row * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (; row < M; row += stride) {
     float4 x4[NV], d4[NV];
     float s = 0.f;
+    const long long nrow = row + stride;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
       const int c = lane * 4 + 128 * j;
-      x4[j] = live[j] ? *reinterpret_cast<const float4*>(ur + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      d4[j] = live[j] ? *reinterpret_cast<const float4*>(dr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x4[j] = nx4[j]; d4[j] = nd4[j];
+      const bool ld = live[j] && nrow < M;
+      nx4[j] = ld ? *reinterpret_cast<const float4*>(u + nrow * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      nd4[j] = ld ? *reinterpret_cast<const float4*>(dz + nrow * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       s += (x4[j].x + x4[j].y) + (x4[j].z + x4[j].w);
     }
     const float mean = warp_sum(s) * invC;
