@@ -126,37 +126,60 @@ __global__ void __launch_bounds__(256) patch_im2row_kernel(const float* __restri
 // =====================================================================================
 // bridge: NHWC maps -> [B][Ntok][64] token buffer (a C_k-channel pixel = C_k/64 consecutive tokens)
 // =====================================================================================
+// four float4 per thread (independent loads in flight: these are pure 25 MB copies at bs16)
+constexpr int RG_UNROLL = 4;
+__device__ __forceinline__ void regroup_locate(const int* tok_off, long long per_img, long long idx, int& b, int& k, long long& slab_idx) {
+  b = (int)(idx / per_img);
+  const long long r = idx - (long long)b * per_img;
+  k = 0;
+#pragma unroll
+  for (int i = 1; i < 4; i++) if (r >= (long long)tok_off[i] * 16) k = i;
+  const long long local = r - (long long)tok_off[k] * 16;
+  const long long n_k = (long long)(tok_off[k + 1] - tok_off[k]) * 16;
+  slab_idx = (long long)b * n_k + local;
+}
 __global__ void __launch_bounds__(256) regroup_kernel(RegroupArgs a) {
   const long long per_img = (long long)a.ntok * 16;   // float4 per image
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= per_img * a.B) return;
-  const int b = (int)(idx / per_img);
-  const long long r = idx % per_img;
-  int k = 0;
+  const long long total = per_img * a.B;
+  const long long base = ((long long)blockIdx.x * RG_UNROLL) * 256 + threadIdx.x;
+  float4 v[RG_UNROLL], r4[RG_UNROLL];
 #pragma unroll
-  for (int i = 1; i < 4; i++) if (r >= (long long)a.tok_off[i] * 16) k = i;
-  const long long local = r - (long long)a.tok_off[k] * 16;
-  const long long n_k = (long long)(a.tok_off[k + 1] - a.tok_off[k]) * 16;
-  float4 v = reinterpret_cast<const float4*>(a.src[k])[(long long)b * n_k + local];
-  if (a.res) {
-    const float4 r4 = reinterpret_cast<const float4*>(a.res)[idx];
-    v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+  for (int u = 0; u < RG_UNROLL; u++) {
+    const long long idx = base + (long long)u * 256;
+    if (idx >= total) continue;
+    int b, k; long long si;
+    regroup_locate(a.tok_off, per_img, idx, b, k, si);
+    v[u] = reinterpret_cast<const float4*>(a.src[k])[si];
+    if (a.res) r4[u] = reinterpret_cast<const float4*>(a.res)[idx];
   }
-  reinterpret_cast<float4*>(a.dst)[idx] = v;
+#pragma unroll
+  for (int u = 0; u < RG_UNROLL; u++) {
+    const long long idx = base + (long long)u * 256;
+    if (idx >= total) continue;
+    float4 o = v[u];
+    if (a.res) { o.x += r4[u].x; o.y += r4[u].y; o.z += r4[u].z; o.w += r4[u].w; }
+    reinterpret_cast<float4*>(a.dst)[idx] = o;
+  }
 }
 
 __global__ void __launch_bounds__(256) ungroup_kernel(UngroupArgs a) {
   const long long per_img = (long long)a.ntok * 16;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= per_img * a.B) return;
-  const int b = (int)(idx / per_img);
-  const long long r = idx % per_img;
-  int k = 0;
+  const long long total = per_img * a.B;
+  const long long base = ((long long)blockIdx.x * RG_UNROLL) * 256 + threadIdx.x;
+  float4 v[RG_UNROLL];
 #pragma unroll
-  for (int i = 1; i < 4; i++) if (r >= (long long)a.tok_off[i] * 16) k = i;
-  const long long local = r - (long long)a.tok_off[k] * 16;
-  const long long n_k = (long long)(a.tok_off[k + 1] - a.tok_off[k]) * 16;
-  reinterpret_cast<float4*>(a.dst[k])[(long long)b * n_k + local] = reinterpret_cast<const float4*>(a.src)[idx];
+  for (int u = 0; u < RG_UNROLL; u++) {
+    const long long idx = base + (long long)u * 256;
+    if (idx < total) v[u] = reinterpret_cast<const float4*>(a.src)[idx];
+  }
+#pragma unroll
+  for (int u = 0; u < RG_UNROLL; u++) {
+    const long long idx = base + (long long)u * 256;
+    if (idx >= total) continue;
+    int b, k; long long si;
+    regroup_locate(a.tok_off, per_img, idx, b, k, si);
+    reinterpret_cast<float4*>(a.dst[k])[si] = v[u];
+  }
 }
 
 // =====================================================================================
@@ -668,13 +691,13 @@ int launch_patch_im2row(const float* x, long long xs_b, long long xs_c, int B, i
 
 int launch_regroup(const RegroupArgs& a, cudaStream_t st) {
   const long long total = (long long)a.B * a.ntok * 16;
-  regroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  regroup_kernel<<<(unsigned)((total + 256 * RG_UNROLL - 1) / (256 * RG_UNROLL)), 256, 0, st>>>(a);
   return tcx_check_launch("bridge_regroup");
 }
 
 int launch_ungroup(const UngroupArgs& a, cudaStream_t st) {
   const long long total = (long long)a.B * a.ntok * 16;
-  ungroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  ungroup_kernel<<<(unsigned)((total + 256 * RG_UNROLL - 1) / (256 * RG_UNROLL)), 256, 0, st>>>(a);
   return tcx_check_launch("bridge_ungroup");
 }
 
