@@ -186,43 +186,47 @@ __global__ void __launch_bounds__(256) ungroup_kernel(UngroupArgs a) {
 // Scale_reduce (reference MSTr.py:2225-2249)
 // im2row of the non-overlapping r x r patches in the conv weight's native (cin, ky, kx) K order
 // =====================================================================================
+// one thread = four consecutive input channels of one patch position: a 16-byte access on the NHWC side, four scalar accesses on the
+// patch-matrix side (whose K order (cin, ky, kx) is the conv weight's own); Cin % 4 == 0
 __global__ void __launch_bounds__(256) sr_im2row_kernel(const float* __restrict__ x, long long xs_b, int HW, int Cin, int r,
                                                         int B, float* __restrict__ A) {
   // x: per image [HW][HW][Cin] at x + b*xs_b ; A: [B*P*P][Cin*r*r], P = HW/r
-  const int P = HW / r;
-  const long long K = (long long)Cin * r * r;
-  const long long total = (long long)B * P * P * K;
+  const int P = HW / r, C4 = Cin >> 2, rr = r * r;
+  const long long K = (long long)Cin * rr;
+  const long long total = (long long)B * P * P * rr * C4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  // read-coalesced ordering: (b, i, j, ky, kx, cin)
-  const int cin = (int)(idx % Cin);
-  long long t = idx / Cin;
+  // read-coalesced ordering: (b, i, j, ky, kx, cin / 4)
+  const int cin = (int)(idx % C4) * 4;
+  long long t = idx / C4;
   const int kx = (int)(t % r); t /= r;
   const int ky = (int)(t % r); t /= r;
   const int j = (int)(t % P); t /= P;
   const int i = (int)(t % P);
   const int b = (int)(t / P);
-  const float v = x[(long long)b * xs_b + ((long long)(i * r + ky) * HW + (j * r + kx)) * Cin + cin];
-  A[((long long)(b * P + i) * P + j) * K + ((long long)cin * r + ky) * r + kx] = v;
+  const float4 v = *reinterpret_cast<const float4*>(x + (long long)b * xs_b + ((long long)(i * r + ky) * HW + (j * r + kx)) * Cin + cin);
+  float* dst = A + ((long long)(b * P + i) * P + j) * K + ((long long)cin * r + ky) * r + kx;
+  dst[0] = v.x; dst[rr] = v.y; dst[2 * rr] = v.z; dst[3 * rr] = v.w;
 }
 
 // the same permutation backwards: dx[b][(i*r+ky)*HW + j*r+kx][cin] = dA[(b,i,j)][(cin,ky,kx)]  (coalesced on the dx side)
 __global__ void __launch_bounds__(256) sr_row2im_kernel(const float* __restrict__ dA, long long xs_b, int HW, int Cin, int r,
                                                         int B, float* __restrict__ dx) {
-  const int P = HW / r;
-  const long long K = (long long)Cin * r * r;
-  const long long total = (long long)B * P * P * K;
+  const int P = HW / r, C4 = Cin >> 2, rr = r * r;
+  const long long K = (long long)Cin * rr;
+  const long long total = (long long)B * P * P * rr * C4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int cin = (int)(idx % Cin);
-  long long t = idx / Cin;
+  const int cin = (int)(idx % C4) * 4;
+  long long t = idx / C4;
   const int kx = (int)(t % r); t /= r;
   const int ky = (int)(t % r); t /= r;
   const int j = (int)(t % P); t /= P;
   const int i = (int)(t % P);
   const int b = (int)(t / P);
-  dx[(long long)b * xs_b + ((long long)(i * r + ky) * HW + (j * r + kx)) * Cin + cin] =
-      dA[((long long)(b * P + i) * P + j) * K + ((long long)cin * r + ky) * r + kx];
+  const float* src = dA + ((long long)(b * P + i) * P + j) * K + ((long long)cin * r + ky) * r + kx;
+  *reinterpret_cast<float4*>(dx + (long long)b * xs_b + ((long long)(i * r + ky) * HW + (j * r + kx)) * Cin + cin) =
+      make_float4(src[0], src[rr], src[2 * rr], src[3 * rr]);
 }
 
 // pack conv outputs + raw stage-4 tokens into the reduced sequence and LayerNorm(64) it.
@@ -709,14 +713,16 @@ int launch_sr_unpack(const SrUnpackArgs& a, cudaStream_t st) {
 
 int launch_sr_row2im(const float* dA, long long xs_b, int HW, int Cin, int r, int B, float* dx, cudaStream_t st) {
   const int P = HW / r;
-  const long long total = (long long)B * P * P * Cin * r * r;
+  TCX_REQUIRE(Cin % 4 == 0 && (xs_b % 4) == 0, "sr_row2im: Cin and the image stride must be multiples of 4 (Cin=%d)", Cin);
+  const long long total = (long long)B * P * P * Cin * r * r / 4;
   sr_row2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dA, xs_b, HW, Cin, r, B, dx);
   return tcx_check_launch("sr_row2im");
 }
 
 int launch_sr_im2row(const float* x, long long xs_b, int HW, int Cin, int r, int B, float* A, cudaStream_t st) {
   const int P = HW / r;
-  const long long total = (long long)B * P * P * Cin * r * r;
+  TCX_REQUIRE(Cin % 4 == 0 && (xs_b % 4) == 0, "sr_im2row: Cin and the image stride must be multiples of 4 (Cin=%d)", Cin);
+  const long long total = (long long)B * P * P * Cin * r * r / 4;
   sr_im2row_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, xs_b, HW, Cin, r, B, A);
   return tcx_check_launch("sr_im2row");
 }
