@@ -293,7 +293,7 @@ def _traffic_table():
         return {}
 
 
-def train_step_leg(torch, dev, world, rank, K, W):
+def train_step_leg(torch, dev, world, rank, K, W, with_kernel_legs=True):
     """fwd + loss + bwd (+ gradient all-reduce when world > 1) + SGD step at bs16 per GPU, every FLOP of the model, of the loss
     and of the optimizer on the library's kernels (autograd nodes of transception_b200/autograd.py, optim.FusedSGD).  Timed with
     CUDA events over graph replays (runtime.TrainStepGraph: the repo's public training runner)."""
@@ -307,6 +307,8 @@ def train_step_leg(torch, dev, world, rank, K, W):
     net = MSTransception(num_classes=NCLS, image_size=SIZE).to(dev).train()
     opt = FusedSGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     xh, lh = _train_inputs(torch, BATCH, rank)
+    pdl_chain = ops.set_flag("pdl_chain", 0)      # read the flag (set_flag returns the previous value) ...
+    ops.set_flag("pdl_chain", pdl_chain)          # ... and put it back
     runner = TrainStepGraph(net, CeDiceLoss(NCLS), opt, BATCH, IN_CH, SIZE, device=dev, warmup=W, sample=(xh, lh))
     launches = runner.kernels_per_step
     x, labels, loss_buf, run = runner.x, runner.labels, runner.loss, runner.replay
@@ -381,6 +383,8 @@ def train_step_leg(torch, dev, world, rank, K, W):
     # stream over one eager step (serial: no stream forks, no PDL); algorithmic bytes are counted by the library per launch
     legs, traffic = [], _traffic_table()
     try:
+        if not with_kernel_legs:
+            raise StopIteration
         peaks, peak_kind = _peaks()
         ops.set_flag("fork", 0)
         ops.set_flag("pdl", 0)
@@ -431,6 +435,8 @@ def train_step_leg(torch, dev, world, rank, K, W):
                                       "durations); event pairs add 2-4 us per launch, so small-kernel numbers are upper bounds of the "
                                       "share" % serial_ms)
             del serial
+    except StopIteration:
+        legs = []
     except Exception as e:  # noqa: BLE001
         legs = [{"error": "%s: %s" % (type(e).__name__, e)}]
         ops.profile_enable("")
@@ -455,7 +461,7 @@ def train_step_leg(torch, dev, world, rank, K, W):
             "e2e": {"value": imgs / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4,
                     "api": "TrainStepGraph.step(pinned images, pinned labels) + loss read back, every step"},
-            "cuda_graph": True, "library_kernels_per_step": launches, "first_loss": first_loss, "last_loss": last_loss,
+            "cuda_graph": True, "pdl_chain": pdl_chain, "library_kernels_per_step": launches, "first_loss": first_loss, "last_loss": last_loss,
             "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
             "allreduced_grads_equal_rank_mean_and_identical_across_ranks": grads_match,
             "weights_identical_across_ranks_after_training": weights_match,
@@ -628,7 +634,7 @@ def run_ours(args):
 
     if args.mode == "train":
         sampler = ClockSampler(local) if rank == 0 else None
-        tr = train_step_leg(torch, dev, world, rank, K, W)
+        tr = train_step_leg(torch, dev, world, rank, K, W, with_kernel_legs=not args.no_legs)
         clocks = sampler.stop() if sampler else None
         fwd = None
         if not args.no_forward:
@@ -650,7 +656,7 @@ def run_ours(args):
                                          "stage 2-1 backward graph, bucket-tail gather graph + all-reduce, fused-SGD graph")},
                     "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_kernels_per_step"] * K,
                     "roofline": tr["roofline"], "roofline_other_kernels": tr["roofline_other_kernels"], "roofline_step": tr["roofline_step"],
-                    "train": {k: tr[k] for k in ("cuda_graph", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce",
+                    "train": {k: tr[k] for k in ("cuda_graph", "pdl_chain", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce",
                                                    "peak_memory_gb", "allreduced_grads_equal_rank_mean_and_identical_across_ranks",
                                                    "weights_identical_across_ranks_after_training")},
                     "forward_step": fwd}
@@ -708,6 +714,7 @@ def main():
                     help="train = BASELINE.json's metric (fwd+bwd bs16 train step, the headline); forward = configs[1]")
     ap.add_argument("--no-forward", action="store_true", help="train mode: skip the forward_step leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the gpu_baseline leg (oracle on the same GPU)")
+    ap.add_argument("--no-legs", action="store_true", help="train mode: skip the per-kernel roofline legs (quick A/B runs)")
     ap.add_argument("--size", type=int, default=SIZE, help="input side (default 224 = the headline workload; 256 = config 5)")
     ap.add_argument("--classes", type=int, default=NCLS)
     ap.add_argument("--in-ch", type=int, default=IN_CH)

@@ -27,7 +27,9 @@ const char* tcx_version(void);
 const char* tcx_last_error(void);
 /* 1 when a usable sm_100 device is current, else 0 (with tcx_last_error set) */
 int tcx_device_ok(void);
-/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc","f16_pipeline","fork","pdl","mixtail","ea_tc"}; value 0/1; returns previous value */
+/* back-end switches for A/B measurement: name in {"gemm_tc","flash_tc","f16_pipeline","fork","pdl","pdl_chain","mixtail","ea_tc","wgrad_tc",
+ * "max_ctas","smem_kb","wgrad_ctas","wgrad_idle"}; returns the previous value.  "pdl" = programmatic dependent launch on the tensor-core pipeline
+ * kernels; "pdl_chain" (library default 0, the Python host sets ops.PDL_CHAIN) = the same attribute on the CUDA-core kernels of the training row. */
 int tcx_set_flag(const char* name, int value);
 
 /* number of kernels this library has enqueued so far in this process (bench.py's gpu_launches) */

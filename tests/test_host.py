@@ -58,6 +58,58 @@ def test_constructor_contract():
     assert net.decoder_0.last_layer.weight.shape[0] == 2
 
 
+def _kernel_body(src, name):
+    """Text of the body of ``__global__ ... name(...) { ... }`` (every definition concatenated)."""
+    out = []
+    for m in re.finditer(r"__global__[^;{}]*?\b%s\s*\(" % re.escape(name), src):
+        i, depth = m.end() - 1, 0
+        while True:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            if depth == 0:
+                break
+            i += 1
+        b = src.index("{", i)
+        assert src[i + 1:b].strip() == "", name
+        j, depth = b, 0
+        while True:
+            depth += {"{": 1, "}": -1}.get(src[j], 0)
+            if depth == 0:
+                break
+            j += 1
+        out.append(src[b + 1:j])
+    return out
+
+
+def test_every_kernel_launched_with_the_pdl_attribute_waits_for_its_predecessor():
+    """A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start before the kernel in front of it
+    has finished; it must execute griddepcontrol.wait before touching anything that kernel wrote.  Static check over the
+    sources: kernels launched through tcx_launch_chain start with PDL_TOP() (trigger + wait as the first statement), kernels
+    launched through tcx_launch_pdl contain a pdl_wait()."""
+    csrc = os.path.join(ROOT, "transception_b200", "csrc")
+    texts = {f: open(os.path.join(csrc, f)).read() for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh"))}
+    everything = "\n".join(texts.values())
+    chain = set(re.findall(r"tcx_launch_chain\(\s*([A-Za-z_][A-Za-z0-9_]*)", everything))
+    pdl = set(re.findall(r"tcx_launch_pdl\(\s*([A-Za-z_][A-Za-z0-9_]*)", everything))
+    for helper_param in ("kernel", "void"):     # the helpers' own declarations: tcx_launch_pdl(void (*kernel)(KArgs...), ...)
+        chain.discard(helper_param)
+        pdl.discard(helper_param)
+    assert len(chain) >= 60 and len(pdl) >= 15, (len(chain), len(pdl))
+    for name in sorted(chain):
+        bodies = _kernel_body(everything, name)
+        assert bodies, "no definition found for %s" % name
+        for body in bodies:
+            assert body.lstrip().startswith("PDL_TOP();"), "%s is launched with the PDL attribute but does not start with PDL_TOP()" % name
+    for name in sorted(pdl):
+        bodies = _kernel_body(everything, name)
+        assert bodies, "no definition found for %s" % name
+        for body in bodies:
+            assert "pdl_wait()" in body or "PDL_TOP()" in body, "%s is launched with the PDL attribute but never waits" % name
+    # and nothing is launched the plain way from a file whose kernels were converted (a plain launch after a converted kernel
+    # would be correct, but the list above is meant to be complete)
+    for f in ("bwd.cu", "bwd_enc.cu", "bwd_mb.cu", "bwd_mix.cu", "flash_bwd.cu", "loss.cu", "optim.cu", "misc.cu", "elementwise.cu"):
+        assert "<<<" not in texts[f], f
+
+
 def test_no_cpu_fallback():
     from networks.MSTr import MSTransception
     net = MSTransception(num_classes=9).eval()

@@ -69,6 +69,7 @@ static int g_flag_ea_tc = 1;     // efficient-attention context on the tensor co
 static int g_flag_wgrad_tc = 1;  // Linear backward with operands read in place: MN-major wgrad kernel + MN-major-W dgrad (0 = round-1 packT path)
 static int g_flag_mixtail = 0;   // fused dw+LN+GELU+fc2: bit-identical but slower (8 producer warps vs 16 in dwln), see DESIGN.md §4
 int g_tcx_pdl = 1;
+int g_tcx_pdl_chain = 0;      // PDL attribute on the training-row kernels launched through tcx_launch_chain (the Python host sets it: ops.PDL_CHAIN)
 int g_tcx_smem_kb = 0;
 int g_tcx_wgrad_ctas = 0;
 int g_tcx_wgrad_idle = 0;
@@ -579,6 +580,7 @@ int tcx_set_flag(const char* name, int value) {
   else if (!strcmp(name, "mixtail")) f = &g_flag_mixtail;
   else if (!strcmp(name, "ea_tc")) f = &g_flag_ea_tc;
   else if (!strcmp(name, "pdl")) f = &g_tcx_pdl;
+  else if (!strcmp(name, "pdl_chain")) f = &g_tcx_pdl_chain;
   else if (!strcmp(name, "wgrad_tc")) f = &g_flag_wgrad_tc;
   else if (!strcmp(name, "max_ctas")) f = &g_tcx_max_ctas;
   else if (!strcmp(name, "smem_kb")) f = &g_tcx_smem_kb;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void block_fold_lanes(float (&acc)[K], float (*sm)[K]
 
 __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_colsum_kernel(const float* __restrict__ x, long long M, int C, int ld,
                                                                          int rows, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RED_LANES][1][RED_COLS];
   const int c = blockIdx.y * RED_COLS + threadIdx.x;
   const long long r0 = (long long)blockIdx.x * rows;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_colsum_kernel(const 
 
 // out[i] = sum_s part[s*n + i]
 __global__ void __launch_bounds__(256) bwd_fold_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ out) {
+  PDL_TOP();
   const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
   const float s = bwd_fold_sum(part, S, n, i, i < n);
   if (threadIdx.y == 0 && i < n) out[i] = s;
@@ -69,6 +71,7 @@ template <bool GELU>
 __global__ void __launch_bounds__(256) bwd_ln_rows_kernel(const float* __restrict__ u, const float* __restrict__ dz,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                           float* __restrict__ du, float* __restrict__ stats, long long M, int C) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_ln_cols_kernel(const
                                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                           const float* __restrict__ stats, long long M, int C, int rows,
                                                                           float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RED_LANES][2][RED_COLS];
   const int c = blockIdx.y * RED_COLS + threadIdx.x;
   const long long r0 = (long long)blockIdx.x * rows;
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_ln_cols_kernel(const
 // partials [nblk][2][C] -> dgamma, dbeta
 __global__ void __launch_bounds__(256) bwd_ln_fold_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dgamma,
                                                           float* __restrict__ dbeta) {
+  PDL_TOP();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const float s = bwd_fold_sum(part, nblk, 2 * C, i, i < 2 * C);
   if (threadIdx.y != 0 || i >= 2 * C) return;
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(256) bwd_ln_fold_kernel(const float* __restric
 // depthwise 3x3 weight gradient: partials [blk][10][C] (9 taps + bias)
 __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_dw_wgrad_kernel(const float* __restrict__ du, const __half* __restrict__ h,
                                                                            int B, int H, int W, int C, int rows, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RED_LANES][10][RED_COLS];
   const int c = blockIdx.y * RED_COLS + threadIdx.x;
   const long long M = (long long)B * H * W;
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) bwd_dw_wgrad_kernel(cons
 // partials [nblk][10][C] -> dw [C][9], db [C]
 __global__ void __launch_bounds__(256) bwd_dw_fold_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dw,
                                                           float* __restrict__ db) {
+  PDL_TOP();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const float s = bwd_fold_sum(part, nblk, 10 * C, i, i < 10 * C);
   if (threadIdx.y != 0 || i >= 10 * C) return;
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(256) bwd_dw_fold_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) bwd_flip9_kernel(const float* __restrict__ w, float* __restrict__ wf, int n) {
+  PDL_TOP();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int c = i / 9, t = i - c * 9;
@@ -230,6 +238,7 @@ __global__ void __launch_bounds__(256) bwd_flip9_kernel(const float* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_packT_kernel(const T* __restrict__ src, long long M, int C, int ld, int S, int Ms, int pitch,
                                                         float* __restrict__ dst) {
+  PDL_TOP();
   __shared__ float tile[32][33];
   const long long t0 = (long long)blockIdx.x * 32;      // padded token index s*Ms + m (Ms % 32 == 0: a tile never straddles splits)
   const int c0 = blockIdx.y * 32;
@@ -260,7 +269,7 @@ int launch_packT(const T* src, int batch, long long M, int C, int ld, int S, int
   if (M == 0 || C == 0 || batch == 0) return 0;
   dim3 grid((unsigned)((long long)S * Ms / 32), (unsigned)cdiv(C, 32), (unsigned)batch);
   ProfScope prof("bwd_packT", st, (double)batch * M * C * (sizeof(T) + 4.0));
-  bwd_packT_kernel<T><<<grid, 256, 0, st>>>(src, M, C, ld, S, Ms, pitch, dst);
+  tcx_launch_chain(bwd_packT_kernel<T>, dim3(grid), dim3(256), 0, st, src, M, C, ld, S, Ms, pitch, dst);
   return tcx_check_launch("bwd_packT");
 }
 
@@ -270,6 +279,7 @@ constexpr int EA_CHUNK = 128;   // token rows per block
 
 __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_kstats_kernel(const __half* __restrict__ k, int ld, int N, int C,
                                                                             float* __restrict__ pm, float* __restrict__ ps) {
+  PDL_TOP();
   __shared__ float sm[RED_LANES][1][RED_COLS];
   __shared__ float bm[RED_COLS];
   const int c = blockIdx.z * RED_COLS + threadIdx.x;
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_prep_kernel(const
                                                                           int N, int C, const float* __restrict__ pm,
                                                                           const float* __restrict__ ps, float* __restrict__ P32,
                                                                           float* __restrict__ V32) {
+  PDL_TOP();
   const int c = blockIdx.z * RED_COLS + threadIdx.x;
   if (c >= C) return;
   const int b = blockIdx.y, chunks = gridDim.x;
@@ -322,6 +333,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_prep_kernel(const
 // chunk partials of sum_n P dP per (image, channel)
 __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_pdp_kernel(const float* __restrict__ P, const float* __restrict__ dP, int N, int C,
                                                                          float* __restrict__ sp) {
+  PDL_TOP();
   __shared__ float sm[RED_LANES][1][RED_COLS];
   const int c = blockIdx.z * RED_COLS + threadIdx.x;
   const int b = blockIdx.y, chunks = gridDim.x;
@@ -338,6 +350,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_pdp_kernel(const 
 // dK = P (dP - sum_n P dP) -> dkqv[:, 0:C] (row pitch ldo)
 __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_dk_kernel(const float* __restrict__ P, const float* __restrict__ dP, int N, int C,
                                                                         const float* __restrict__ sp, float* __restrict__ dk, int ldo) {
+  PDL_TOP();
   const int c = blockIdx.z * RED_COLS + threadIdx.x;
   if (c >= C) return;
   const int b = blockIdx.y, chunks = gridDim.x;
@@ -352,6 +365,7 @@ __global__ void __launch_bounds__(RED_COLS * RED_LANES) ea_bwd_dk_kernel(const f
 // channel softmax backward, one warp per token: dQ = Qs (dQs - sum_c Qs dQs) -> dq (row pitch ldo)
 __global__ void __launch_bounds__(256) ea_bwd_dq_kernel(const __half* __restrict__ qs, const float* __restrict__ dqs, long long M, int C,
                                                         float* __restrict__ dq, int ldo) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -364,6 +378,7 @@ __global__ void __launch_bounds__(256) ea_bwd_dq_kernel(const __half* __restrict
 // out[b][i] = sum_s part[(b*S + s)*n + i]; optional transposed copy outT[b][j*R + i'] of the R x R matrix
 __global__ void __launch_bounds__(256) bwd_fold_batched_kernel(const float* __restrict__ part, int S, int R, float* __restrict__ out,
                                                                float* __restrict__ outT) {
+  PDL_TOP();
   const int n = R * R;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
@@ -383,7 +398,7 @@ int bwd_red_blocks(long long M) {
 
 int launch_bwd_fold(const float* part, int S, long long n, float* out, cudaStream_t st) {
   if (n == 0) return 0;
-  bwd_fold_kernel<<<(unsigned)((n + 31) / 32), dim3(32, 8), 0, st>>>(part, S, n, out);
+  tcx_launch_chain(bwd_fold_kernel, dim3((unsigned)((n + 31) / 32)), dim3(dim3(32, 8)), 0, st, part, S, n, out);
   return tcx_check_launch("bwd_fold");
 }
 
@@ -392,17 +407,17 @@ int launch_bwd_colsum(const float* x, long long M, int C, int ld, float* part, f
   const int rows = red_rows_per_block(M), nblk = bwd_red_blocks(M);
   if (M == 0) return cudaMemsetAsync(out, 0, sizeof(float) * C, st) == cudaSuccess ? 0 : -1;
   ProfScope prof("bwd_colsum", st, (double)M * C * 4.0);
-  bwd_colsum_kernel<<<dim3(nblk, cdiv(C, RED_COLS)), dim3(RED_COLS, RED_LANES), 0, st>>>(x, M, C, ld, rows, part);
+  tcx_launch_chain(bwd_colsum_kernel, dim3(dim3(nblk, cdiv(C, RED_COLS))), dim3(dim3(RED_COLS, RED_LANES)), 0, st, x, M, C, ld, rows, part);
   TCX_TRY(tcx_check_launch("bwd_colsum"));
   return launch_bwd_fold(part, nblk, C, out, st);
 }
 
 int launch_bwd_ln_fold(const float* part, int nblk, int C, float* dgamma, float* dbeta, cudaStream_t st) {
-  bwd_ln_fold_kernel<<<cdiv(2 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dgamma, dbeta);
+  tcx_launch_chain(bwd_ln_fold_kernel, dim3(cdiv(2 * C, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, C, dgamma, dbeta);
   return tcx_check_launch("bwd_ln_fold");
 }
 int launch_bwd_dw_fold(const float* part, int nblk, int C, float* dw, float* db, cudaStream_t st) {
-  bwd_dw_fold_kernel<<<cdiv(10 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dw, db);
+  tcx_launch_chain(bwd_dw_fold_kernel, dim3(cdiv(10 * C, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, C, dw, db);
   return tcx_check_launch("bwd_dw_fold");
 }
 
@@ -423,18 +438,18 @@ int launch_bwd_ln(const float* u, const float* dz, const float* gamma, const flo
   const int rows = red_rows_per_block(M), nblk = bwd_red_blocks(M);
   {
     ProfScope prof("bwd_ln_rows", st, (double)M * C * 12.0);
-    if (gelu) bwd_ln_rows_kernel<true><<<rb, 256, 0, st>>>(u, dz, gamma, beta, eps, du, stats, M, C);
-    else bwd_ln_rows_kernel<false><<<rb, 256, 0, st>>>(u, dz, gamma, beta, eps, du, stats, M, C);
+    if (gelu) tcx_launch_chain(bwd_ln_rows_kernel<true>, dim3(rb), dim3(256), 0, st, u, dz, gamma, beta, eps, du, stats, M, C);
+    else tcx_launch_chain(bwd_ln_rows_kernel<false>, dim3(rb), dim3(256), 0, st, u, dz, gamma, beta, eps, du, stats, M, C);
     TCX_TRY(tcx_check_launch("bwd_ln_rows"));
   }
   {
     ProfScope prof("bwd_ln_cols", st, (double)M * C * 8.0);
     const dim3 grid(nblk, cdiv(C, RED_COLS)), block(RED_COLS, RED_LANES);
-    if (gelu) bwd_ln_cols_kernel<true><<<grid, block, 0, st>>>(u, dz, gamma, beta, stats, M, C, rows, part);
-    else bwd_ln_cols_kernel<false><<<grid, block, 0, st>>>(u, dz, gamma, beta, stats, M, C, rows, part);
+    if (gelu) tcx_launch_chain(bwd_ln_cols_kernel<true>, dim3(grid), dim3(block), 0, st, u, dz, gamma, beta, stats, M, C, rows, part);
+    else tcx_launch_chain(bwd_ln_cols_kernel<false>, dim3(grid), dim3(block), 0, st, u, dz, gamma, beta, stats, M, C, rows, part);
     TCX_TRY(tcx_check_launch("bwd_ln_cols"));
   }
-  bwd_ln_fold_kernel<<<cdiv(2 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dgamma, dbeta);
+  tcx_launch_chain(bwd_ln_fold_kernel, dim3(cdiv(2 * C, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, C, dgamma, dbeta);
   TCX_TRY(tcx_check_launch("bwd_ln_fold"));
   if (dres) return launch_add_inplace(du, dres, M * C, st);
   return 0;
@@ -447,15 +462,15 @@ int launch_bwd_dwconv_wgrad(const float* du, const __half* h, int B, int H, int 
   const int rows = red_rows_per_block(M), nblk = bwd_red_blocks(M);
   {
     ProfScope prof("bwd_dw_wgrad", st, (double)M * C * 6.0);
-    bwd_dw_wgrad_kernel<<<dim3(nblk, cdiv(C, RED_COLS)), dim3(RED_COLS, RED_LANES), 0, st>>>(du, h, B, H, W, C, rows, part);
+    tcx_launch_chain(bwd_dw_wgrad_kernel, dim3(dim3(nblk, cdiv(C, RED_COLS))), dim3(dim3(RED_COLS, RED_LANES)), 0, st, du, h, B, H, W, C, rows, part);
     TCX_TRY(tcx_check_launch("bwd_dw_wgrad"));
   }
-  bwd_dw_fold_kernel<<<cdiv(10 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, dw, db);
+  tcx_launch_chain(bwd_dw_fold_kernel, dim3(cdiv(10 * C, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, C, dw, db);
   return tcx_check_launch("bwd_dw_fold");
 }
 
 int launch_bwd_flip9(const float* w, float* wflip, int C, cudaStream_t st) {
-  bwd_flip9_kernel<<<cdiv(9 * C, 256), 256, 0, st>>>(w, wflip, 9 * C);
+  tcx_launch_chain(bwd_flip9_kernel, dim3(cdiv(9 * C, 256)), dim3(256), 0, st, w, wflip, 9 * C);
   return tcx_check_launch("bwd_flip9");
 }
 
@@ -474,7 +489,7 @@ int launch_bwd_packT_batched_f16(const __half* src, int batch, int N, int C, int
 
 int launch_bwd_fold_batched(const float* part, int batch, int S, int R, float* out, float* outT, cudaStream_t st) {
   if (batch == 0 || R == 0) return 0;
-  bwd_fold_batched_kernel<<<dim3(cdiv(R * R, 256), batch), 256, 0, st>>>(part, S, R, out, outT);
+  tcx_launch_chain(bwd_fold_batched_kernel, dim3(dim3(cdiv(R * R, 256), batch)), dim3(256), 0, st, part, S, R, out, outT);
   return tcx_check_launch("bwd_fold_batched");
 }
 
@@ -484,18 +499,18 @@ int launch_ea_bwd_prep(const __half* k, const __half* v, int ld, int B, int N, i
                        cudaStream_t st) {
   if (B == 0 || N == 0) return 0;
   const dim3 grid(ea_bwd_chunks(N), B, cdiv(C, RED_COLS)), block(RED_COLS, RED_LANES);
-  ea_bwd_kstats_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps);
+  tcx_launch_chain(ea_bwd_kstats_kernel, dim3(grid), dim3(block), 0, st, k, ld, N, C, pm, ps);
   TCX_TRY(tcx_check_launch("ea_bwd_kstats"));
-  ea_bwd_prep_kernel<<<grid, block, 0, st>>>(k, v, ld, N, C, pm, ps, P32, V32);
+  tcx_launch_chain(ea_bwd_prep_kernel, dim3(grid), dim3(block), 0, st, k, v, ld, N, C, pm, ps, P32, V32);
   return tcx_check_launch("ea_bwd_prep");
 }
 
 int launch_bwd_colsoftmax(const float* P, const float* dP, int B, int N, int C, float* sp, float* dk, int ldo, cudaStream_t st) {
   if (B == 0 || N == 0) return 0;
   const dim3 grid(ea_bwd_chunks(N), B, cdiv(C, RED_COLS)), block(RED_COLS, RED_LANES);
-  ea_bwd_pdp_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp);
+  tcx_launch_chain(ea_bwd_pdp_kernel, dim3(grid), dim3(block), 0, st, P, dP, N, C, sp);
   TCX_TRY(tcx_check_launch("ea_bwd_pdp"));
-  ea_bwd_dk_kernel<<<grid, block, 0, st>>>(P, dP, N, C, sp, dk, ldo);
+  tcx_launch_chain(ea_bwd_dk_kernel, dim3(grid), dim3(block), 0, st, P, dP, N, C, sp, dk, ldo);
   return tcx_check_launch("ea_bwd_dk");
 }
 
@@ -504,7 +519,7 @@ int launch_ea_bwd_softmax(const float* P, const float* dP, const __half* qs, con
   if (B == 0 || N == 0) return 0;
   TCX_TRY(launch_bwd_colsoftmax(P, dP, B, N, C, sp, dkqv, 3 * C, st));
   const long long M = (long long)B * N;
-  ea_bwd_dq_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(qs, dqs, M, C, dkqv + C, 3 * C);
+  tcx_launch_chain(ea_bwd_dq_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, st, qs, dqs, M, C, dkqv + C, 3 * C);
   return tcx_check_launch("ea_bwd_dq");
 }
 

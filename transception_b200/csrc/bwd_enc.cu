@@ -44,6 +44,7 @@ __device__ __forceinline__ void fold_lanes(float (&acc)[K], float (*sm)[RC]) {
 // shifted sums lose nothing) and its row count; the fold combines the blocks' (count, mean, M2) with Chan's update in block order —
 // a fixed association, and the same variance as the two-pass form up to fp32 rounding.
 __global__ void __launch_bounds__(RC * RL) bn_stats_kernel(const float* __restrict__ x, long long M, int C, int rows, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RL][RC];
   const int c = blockIdx.y * RC + threadIdx.x;
   const long long r0 = (long long)blockIdx.x * rows, r1 = r0 + rows < M ? r0 + rows : M;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(RC * RL) bn_stats_kernel(const float* __restri
 __global__ void __launch_bounds__(256) bn_stats_fold_kernel(const float* __restrict__ part, int nblk, int rows, long long M, int C, float eps,
                                                             float momentum, float* __restrict__ stat, float* __restrict__ rm,
                                                             float* __restrict__ rv) {
+  PDL_TOP();
   __shared__ float sn[8][32], smean[8][32], sm2[8][32];
   const int c = blockIdx.x * 32 + threadIdx.x, l = threadIdx.y;
   float n = 0.f, mean = 0.f, m2 = 0.f;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) bn_stats_fold_kernel(const float* __restr
 // unbiased variance)
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ stat, const float* __restrict__ w,
                                                        const float* __restrict__ b, int act, long long n, int C, float* __restrict__ y) {
+  PDL_TOP();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int c = (int)(i % C);
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(RC * RL) bn_bwd_cols_kernel(const float* __res
                                                               const float* __restrict__ stat, const float* __restrict__ w,
                                                               const float* __restrict__ b, int act, long long M, int C, int rows,
                                                               float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RL][RC];
   const int c = blockIdx.y * RC + threadIdx.x;
   const long long r0 = (long long)blockIdx.x * rows, r1 = r0 + rows < M ? r0 + rows : M;
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(RC * RL) bn_bwd_cols_kernel(const float* __res
 __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ stat,
                                                         const float* __restrict__ w, const float* __restrict__ b, int act,
                                                         const float* __restrict__ dwdb, long long M, int C, float* __restrict__ dx) {
+  PDL_TOP();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= M * C) return;
   const int c = (int)(i % C);
@@ -153,6 +158,7 @@ __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict_
 // depthwise 3x3, pad 1, stride s: input gradient  dx[b,yi,xi,c] = sum_t w[c][t] dy[b,(yi+1-ky)/s,(xi+1-kx)/s,c]
 __global__ void __launch_bounds__(256) dw3s_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int B, int H, int W, int C,
                                                          int s, int Ho, int Wo, float* __restrict__ dx) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * H * W * C) return;
   const int c = (int)(idx % C);
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(256) dw3s_dgrad_kernel(const float* __restrict
 // weight gradient partials [blk][9][C]: dw[c][t] = sum_{b,yo,xo} dy[b,yo,xo,c] x[b, yo s - 1 + ky, xo s - 1 + kx, c]
 __global__ void __launch_bounds__(RC * RL) dw3s_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int B, int H, int W,
                                                              int C, int s, int Ho, int Wo, int rows, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RL][RC];
   const int c = blockIdx.y * RC + threadIdx.x;
   const long long M = (long long)B * Ho * Wo;
@@ -212,6 +219,7 @@ __global__ void __launch_bounds__(RC * RL) dw3s_wgrad_kernel(const float* __rest
   }
 }
 __global__ void __launch_bounds__(256) dw3s_fold_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dw) {
+  PDL_TOP();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const float s = bwd_fold_sum(part, nblk, 9 * C, i, i < 9 * C);
   if (threadIdx.y != 0 || i >= 9 * C) return;
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(256) dw3s_fold_kernel(const float* __restrict_
 
 // CoordAtt pooling: y [B][H+W][C]: rows 0..H-1 = mean over W, rows H.. = mean over H.  One thread per output element.
 __global__ void __launch_bounds__(256) coord_pool_kernel(const float* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * (H + W) * C) return;
   const int c = (int)(idx % C);
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(256) coord_pool_kernel(const float* __restrict
   y[idx] = s;
 }
 __global__ void __launch_bounds__(256) coord_pool_bwd_kernel(const float* __restrict__ dy, int B, int H, int W, int C, float* __restrict__ dx) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * H * W * C) return;
   const int c = (int)(idx % C);
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(256) coord_pool_bwd_kernel(const float* __rest
 // gate: out = x * sigmoid(zw[b,w,c]) * sigmoid(zh[b,h,c]);  z [B][H+W][C] (rows 0..H-1 = zh, H.. = zw)
 __global__ void __launch_bounds__(256) coord_gate_kernel(const float* __restrict__ x, const float* __restrict__ z, int B, int H, int W, int C,
                                                          const float* __restrict__ dout, float* __restrict__ out) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * H * W * C) return;
   const int c = (int)(idx % C);
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(256) coord_gate_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) coord_gate_bwd_z_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                                                const float* __restrict__ dout, int B, int H, int W, int C,
                                                                float* __restrict__ dz) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)B * (H + W) * C) return;
   const int c = (int)(idx % C);
@@ -298,11 +310,11 @@ int launch_bn_train_fwd(const float* x, const float* w, const float* b, float ep
   const int nblk = std::min(bwd_red_blocks(M), 296);
   const int rows = rows_for(M, nblk);
   float* part = scratch + 2 * C;
-  bn_stats_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(x, M, C, rows, part);
+  tcx_launch_chain(bn_stats_kernel, dim3(dim3(nblk, cdiv(C, RC))), dim3(dim3(RC, RL)), 0, st, x, M, C, rows, part);
   TCX_TRY(tcx_check_launch("bn_stats"));
-  bn_stats_fold_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(part, nblk, rows, M, C, eps, momentum, stat, rm, rv);
+  tcx_launch_chain(bn_stats_fold_kernel, dim3(cdiv(C, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, rows, M, C, eps, momentum, stat, rm, rv);
   TCX_TRY(tcx_check_launch("bn_stats_fold"));
-  bn_apply_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(x, stat, w, b, act, M * C, C, y);
+  tcx_launch_chain(bn_apply_kernel, dim3((unsigned)((M * C + 255) / 256)), dim3(256), 0, st, x, stat, w, b, act, M * C, C, y);
   return tcx_check_launch("bn_apply");
 }
 // dw and db adjacent in memory (db == dw + C: the binding allocates them as one [2][C] tensor): the fold writes them in place
@@ -311,10 +323,10 @@ int launch_bn_train_bwd(const float* x, const float* dy, const float* stat, cons
   const int nblk = bwd_red_blocks(M);
   const bool adjacent = db == dw + C;
   float* dwdb = adjacent ? dw : scratch; float* part = scratch + 2 * C;
-  bn_bwd_cols_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(x, dy, stat, w, b, act, M, C, rows_for(M, nblk), part);
+  tcx_launch_chain(bn_bwd_cols_kernel, dim3(dim3(nblk, cdiv(C, RC))), dim3(dim3(RC, RL)), 0, st, x, dy, stat, w, b, act, M, C, rows_for(M, nblk), part);
   TCX_TRY(tcx_check_launch("bn_bwd_cols"));
   TCX_TRY(launch_bwd_fold(part, nblk, 2 * (long long)C, dwdb, st));       // partial layout [blk][2][C] -> [dw | db]
-  bn_bwd_dx_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(x, dy, stat, w, b, act, dwdb, M, C, dx);
+  tcx_launch_chain(bn_bwd_dx_kernel, dim3((unsigned)((M * C + 255) / 256)), dim3(256), 0, st, x, dy, stat, w, b, act, dwdb, M, C, dx);
   TCX_TRY(tcx_check_launch("bn_bwd_dx"));
   if (!adjacent)
     TCX_REQUIRE(cudaMemcpyAsync(dw, dwdb, sizeof(float) * C, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
@@ -328,35 +340,35 @@ int launch_dw3s_bwd(const float* x, const float* w, const float* dy, float* dx, 
                     float* scratch, cudaStream_t st) {
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   if (dx) {
-    dw3s_dgrad_kernel<<<(unsigned)(((long long)B * H * W * C + 255) / 256), 256, 0, st>>>(dy, w, B, H, W, C, stride, Ho, Wo, dx);
+    tcx_launch_chain(dw3s_dgrad_kernel, dim3((unsigned)(((long long)B * H * W * C + 255) / 256)), dim3(256), 0, st, dy, w, B, H, W, C, stride, Ho, Wo, dx);
     TCX_TRY(tcx_check_launch("dw3s_dgrad"));
   }
   if (dw) {
     const long long Mo = (long long)B * Ho * Wo;
     const int nblk = bwd_red_blocks(Mo);
-    dw3s_wgrad_kernel<<<dim3(nblk, cdiv(C, RC)), dim3(RC, RL), 0, st>>>(dy, x, B, H, W, C, stride, Ho, Wo, rows_for(Mo, nblk), scratch);
+    tcx_launch_chain(dw3s_wgrad_kernel, dim3(dim3(nblk, cdiv(C, RC))), dim3(dim3(RC, RL)), 0, st, dy, x, B, H, W, C, stride, Ho, Wo, rows_for(Mo, nblk), scratch);
     TCX_TRY(tcx_check_launch("dw3s_wgrad"));
-    dw3s_fold_kernel<<<cdiv(9 * C, 32), dim3(32, 8), 0, st>>>(scratch, nblk, C, dw);
+    tcx_launch_chain(dw3s_fold_kernel, dim3(cdiv(9 * C, 32)), dim3(dim3(32, 8)), 0, st, scratch, nblk, C, dw);
     TCX_TRY(tcx_check_launch("dw3s_fold"));
   }
   return 0;
 }
 
 int launch_coord_pool(const float* x, int B, int H, int W, int C, float* y, cudaStream_t st) {
-  coord_pool_kernel<<<(unsigned)(((long long)B * (H + W) * C + 255) / 256), 256, 0, st>>>(x, B, H, W, C, y);
+  tcx_launch_chain(coord_pool_kernel, dim3((unsigned)(((long long)B * (H + W) * C + 255) / 256)), dim3(256), 0, st, x, B, H, W, C, y);
   return tcx_check_launch("coord_pool");
 }
 int launch_coord_pool_bwd(const float* dy, int B, int H, int W, int C, float* dx, cudaStream_t st) {
-  coord_pool_bwd_kernel<<<(unsigned)(((long long)B * H * W * C + 255) / 256), 256, 0, st>>>(dy, B, H, W, C, dx);
+  tcx_launch_chain(coord_pool_bwd_kernel, dim3((unsigned)(((long long)B * H * W * C + 255) / 256)), dim3(256), 0, st, dy, B, H, W, C, dx);
   return tcx_check_launch("coord_pool_bwd");
 }
 int launch_coord_gate(const float* x, const float* z, int B, int H, int W, int C, float* out, cudaStream_t st) {
-  coord_gate_kernel<<<(unsigned)(((long long)B * H * W * C + 255) / 256), 256, 0, st>>>(x, z, B, H, W, C, nullptr, out);
+  tcx_launch_chain(coord_gate_kernel, dim3((unsigned)(((long long)B * H * W * C + 255) / 256)), dim3(256), 0, st, x, z, B, H, W, C, nullptr, out);
   return tcx_check_launch("coord_gate");
 }
 int launch_coord_gate_bwd(const float* x, const float* z, const float* dout, int B, int H, int W, int C, float* dx, float* dz, cudaStream_t st) {
-  coord_gate_kernel<<<(unsigned)(((long long)B * H * W * C + 255) / 256), 256, 0, st>>>(x, z, B, H, W, C, dout, dx);
+  tcx_launch_chain(coord_gate_kernel, dim3((unsigned)(((long long)B * H * W * C + 255) / 256)), dim3(256), 0, st, x, z, B, H, W, C, dout, dx);
   TCX_TRY(tcx_check_launch("coord_gate_dx"));
-  coord_gate_bwd_z_kernel<<<(unsigned)(((long long)B * (H + W) * C + 255) / 256), 256, 0, st>>>(x, z, dout, B, H, W, C, dz);
+  tcx_launch_chain(coord_gate_bwd_z_kernel, dim3((unsigned)(((long long)B * (H + W) * C + 255) / 256)), dim3(256), 0, st, x, z, dout, B, H, W, C, dz);
   return tcx_check_launch("coord_gate_dz");
 }

@@ -14,6 +14,7 @@ constexpr int RC = 64, RL = 4;       // (64 columns x 4 row lanes) reduction blo
 template <int K, bool FLIP, bool ADD>
 __global__ void __launch_bounds__(256) dwk_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                                   const float* __restrict__ b, float* __restrict__ y, int ldy, int B, int H, int W, int Cg) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long total = (long long)B * H * W * Cg;
   if (idx >= total) return;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256) dwk_kernel(const float* __restrict__ x, i
 template <int K>
 __global__ void __launch_bounds__(RC * RL) dwk_wgrad_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ x, int ldx,
                                                             int B, int H, int W, int Cg, int rows, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[RL][RC];
   const int c = blockIdx.y * RC + threadIdx.x;
   const long long M = (long long)B * H * W;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(RC * RL) dwk_wgrad_kernel(const float* __restr
 // partials [nblk][KK + 1][Cg] -> dw [Cg][KK], db [Cg] (db may be null)
 __global__ void __launch_bounds__(256) dwk_fold_kernel(const float* __restrict__ part, int nblk, int KK, int Cg, float* __restrict__ dw,
                                                        float* __restrict__ db) {
+  PDL_TOP();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int n = (KK + 1) * Cg;
   const float s = bwd_fold_sum(part, nblk, n, i, i < n);
@@ -148,6 +151,7 @@ __device__ __forceinline__ void dwk_sweep_row(const float* __restrict__ x, int l
 template <bool FLIP, bool ADD>
 __global__ void __launch_bounds__(SC * SL) dwk3_sweep_kernel(const float* __restrict__ x, int ldx, Crpe3 f, float* __restrict__ y, int ldy,
                                                              int B, int H, int W, int C) {
+  PDL_TOP();
   const int c = blockIdx.y * SC + threadIdx.x;
   const int row = blockIdx.x * SL + threadIdx.y;
   if (c >= C || row >= B * H) return;
@@ -221,6 +225,7 @@ __device__ __forceinline__ void dwk_wgrad_sweep(const float* __restrict__ g, int
 __global__ void __launch_bounds__(WC * WL) dwk3_wgrad_sweep_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ x,
                                                                    int ldx, int B, int H, int W, int C, int c1, int c2, int rows,
                                                                    float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[WL][8][WC];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.y * WC + tx;
@@ -264,6 +269,7 @@ struct Crpe3Out {
   int c1, c2;
 };
 __global__ void __launch_bounds__(256) dwk3_fold_kernel(const float* __restrict__ part, int nblk, int C, Crpe3Out o) {
+  PDL_TOP();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int n = 50 * C;
   const int t = i / C, c = i - t * C;
@@ -282,10 +288,10 @@ int dwk_launch(const float* x, int ldx, const float* w, const float* b, float* y
   const long long total = (long long)B * H * W * Cg;
   if (total == 0) return 0;
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (!flip && !add) dwk_kernel<K, false, false><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
-  else if (!flip && add) dwk_kernel<K, false, true><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
-  else if (flip && !add) dwk_kernel<K, true, false><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
-  else dwk_kernel<K, true, true><<<grid, 256, 0, st>>>(x, ldx, w, b, y, ldy, B, H, W, Cg);
+  if (!flip && !add) tcx_launch_chain(dwk_kernel<K, false, false>, dim3(grid), dim3(256), 0, st, x, ldx, w, b, y, ldy, B, H, W, Cg);
+  else if (!flip && add) tcx_launch_chain(dwk_kernel<K, false, true>, dim3(grid), dim3(256), 0, st, x, ldx, w, b, y, ldy, B, H, W, Cg);
+  else if (flip && !add) tcx_launch_chain(dwk_kernel<K, true, false>, dim3(grid), dim3(256), 0, st, x, ldx, w, b, y, ldy, B, H, W, Cg);
+  else tcx_launch_chain(dwk_kernel<K, true, true>, dim3(grid), dim3(256), 0, st, x, ldx, w, b, y, ldy, B, H, W, Cg);
   return tcx_check_launch("bwd_dwk");
 }
 template <int K>
@@ -295,15 +301,16 @@ int dwk_wgrad_launch(const float* g, int ldg, const float* x, int ldx, int B, in
   if (M == 0 || Cg == 0) return 0;
   const int nblk = bwd_red_blocks(M);
   const int rows = (int)((M + nblk - 1) / nblk + RL - 1) / RL * RL;
-  dwk_wgrad_kernel<K><<<dim3(nblk, cdiv(Cg, RC)), dim3(RC, RL), 0, st>>>(g, ldg, x, ldx, B, H, W, Cg, rows, part);
+  tcx_launch_chain(dwk_wgrad_kernel<K>, dim3(dim3(nblk, cdiv(Cg, RC))), dim3(dim3(RC, RL)), 0, st, g, ldg, x, ldx, B, H, W, Cg, rows, part);
   TCX_TRY(tcx_check_launch("bwd_dwk_wgrad"));
-  dwk_fold_kernel<<<cdiv((K * K + 1) * Cg, 32), dim3(32, 8), 0, st>>>(part, nblk, K * K, Cg, dw, db);
+  tcx_launch_chain(dwk_fold_kernel, dim3(cdiv((K * K + 1) * Cg, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, K * K, Cg, dw, db);
   return tcx_check_launch("bwd_dwk_fold");
 }
 
 // out[b][i][j] = scale * sum_s part[b][s][i][j] inside the diagonal blocks of size Ch, 0 outside; outT = transposed copy
 __global__ void __launch_bounds__(256) fold_mask_kernel(const float* __restrict__ part, int S, int R, int Ch, float scale,
                                                         float* __restrict__ out, float* __restrict__ outT) {
+  PDL_TOP();
   const int n = R * R;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= n) return;
@@ -321,6 +328,7 @@ __global__ void __launch_bounds__(256) fold_mask_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) mb_dq_kernel(const float* __restrict__ dxo, const float* __restrict__ dqfa, float* __restrict__ convv,
                                                     const float* __restrict__ q, int ldq, float scale, long long M, int C,
                                                     float* __restrict__ dq, int ldo) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= M * C) return;
   const long long r = idx / C;
@@ -334,6 +342,7 @@ constexpr int CHUNK = 128;
 // column softmax over the N tokens of each image (k rows of pitch ld): chunk partials, then P [B*N][C]
 __global__ void __launch_bounds__(RC * RL) kstats32_kernel(const float* __restrict__ k, int ld, int N, int C, float* __restrict__ pm,
                                                            float* __restrict__ ps) {
+  PDL_TOP();
   __shared__ float sm[RL][RC];
   __shared__ float bm[RC];
   const int c = blockIdx.z * RC + threadIdx.x;
@@ -366,6 +375,7 @@ __global__ void __launch_bounds__(RC * RL) kstats32_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(RC * RL) ksoftmax32_kernel(const float* __restrict__ k, int ld, int N, int C, const float* __restrict__ pm,
                                                              const float* __restrict__ ps, float* __restrict__ P) {
+  PDL_TOP();
   const int c = blockIdx.z * RC + threadIdx.x;
   if (c >= C) return;
   const int b = blockIdx.y, chunks = gridDim.x;
@@ -408,10 +418,10 @@ int launch_bwd_dwk3(const float* x, int ldx, const float* const* w, const float*
   for (int j = 0; j < 3; j++) { f.w[j] = w[j]; f.b[j] = b ? b[j] : nullptr; }
   f.c1 = c1; f.c2 = c2;
   const dim3 grid(cdiv(B * H, SL), cdiv(C, SC)), block(SC, SL);
-  if (!flip && !add) dwk3_sweep_kernel<false, false><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
-  else if (!flip && add) dwk3_sweep_kernel<false, true><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
-  else if (flip && !add) dwk3_sweep_kernel<true, false><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
-  else dwk3_sweep_kernel<true, true><<<grid, block, 0, st>>>(x, ldx, f, y, ldy, B, H, W, C);
+  if (!flip && !add) tcx_launch_chain(dwk3_sweep_kernel<false, false>, dim3(grid), dim3(block), 0, st, x, ldx, f, y, ldy, B, H, W, C);
+  else if (!flip && add) tcx_launch_chain(dwk3_sweep_kernel<false, true>, dim3(grid), dim3(block), 0, st, x, ldx, f, y, ldy, B, H, W, C);
+  else if (flip && !add) tcx_launch_chain(dwk3_sweep_kernel<true, false>, dim3(grid), dim3(block), 0, st, x, ldx, f, y, ldy, B, H, W, C);
+  else tcx_launch_chain(dwk3_sweep_kernel<true, true>, dim3(grid), dim3(block), 0, st, x, ldx, f, y, ldy, B, H, W, C);
   return tcx_check_launch("bwd_dwk3");
 }
 size_t bwd_dwk3_wgrad_part_floats(long long M, int C) { return (size_t)bwd_red_blocks(M) * 50 * C; }
@@ -424,31 +434,31 @@ int launch_bwd_dwk3_wgrad(const float* g, int ldg, const float* x, int ldx, int 
   int rows = WL;
   while (cdiv(nrow, rows) > cap) rows += WL;
   const int nblk = cdiv(nrow, rows);
-  dwk3_wgrad_sweep_kernel<<<dim3(nblk, cdiv(C, WC)), dim3(WC, WL), 0, st>>>(g, ldg, x, ldx, B, H, W, C, c1, c2, rows, part);
+  tcx_launch_chain(dwk3_wgrad_sweep_kernel, dim3(dim3(nblk, cdiv(C, WC))), dim3(dim3(WC, WL)), 0, st, g, ldg, x, ldx, B, H, W, C, c1, c2, rows, part);
   TCX_TRY(tcx_check_launch("bwd_dwk3_wgrad"));
   Crpe3Out o;
   for (int j = 0; j < 3; j++) { o.dw[j] = dw[j]; o.db[j] = db[j]; }
   o.c1 = c1; o.c2 = c2;
-  dwk3_fold_kernel<<<cdiv(50 * C, 32), dim3(32, 8), 0, st>>>(part, nblk, C, o);
+  tcx_launch_chain(dwk3_fold_kernel, dim3(cdiv(50 * C, 32)), dim3(dim3(32, 8)), 0, st, part, nblk, C, o);
   return tcx_check_launch("bwd_dwk3_fold");
 }
 int launch_bwd_fold_mask(const float* part, int batch, int S, int R, int Ch, float scale, float* out, float* outT, cudaStream_t st) {
   if (batch == 0 || R == 0) return 0;
-  fold_mask_kernel<<<dim3(cdiv(R * R, 256), batch), 256, 0, st>>>(part, S, R, Ch, scale, out, outT);
+  tcx_launch_chain(fold_mask_kernel, dim3(dim3(cdiv(R * R, 256), batch)), dim3(256), 0, st, part, S, R, Ch, scale, out, outT);
   return tcx_check_launch("bwd_fold_mask");
 }
 int launch_mb_bwd_dq(const float* dxo, const float* dqfa, float* convv, const float* q, int ldq, float scale, long long M, int C, float* dq,
                      int ldo, cudaStream_t st) {
   if (M == 0) return 0;
-  mb_dq_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, st>>>(dxo, dqfa, convv, q, ldq, scale, M, C, dq, ldo);
+  tcx_launch_chain(mb_dq_kernel, dim3((unsigned)((M * C + 255) / 256)), dim3(256), 0, st, dxo, dqfa, convv, q, ldq, scale, M, C, dq, ldo);
   return tcx_check_launch("mb_bwd_dq");
 }
 int launch_bwd_ksoftmax32(const float* k, int ld, int B, int N, int C, float* pm, float* ps, float* P, cudaStream_t st) {
   if (B == 0 || N == 0) return 0;
   const dim3 grid(cdiv(N, CHUNK), B, cdiv(C, RC)), block(RC, RL);
-  kstats32_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps);
+  tcx_launch_chain(kstats32_kernel, dim3(grid), dim3(block), 0, st, k, ld, N, C, pm, ps);
   TCX_TRY(tcx_check_launch("bwd_kstats32"));
-  ksoftmax32_kernel<<<grid, block, 0, st>>>(k, ld, N, C, pm, ps, P);
+  tcx_launch_chain(ksoftmax32_kernel, dim3(grid), dim3(block), 0, st, k, ld, N, C, pm, ps, P);
   return tcx_check_launch("bwd_ksoftmax32");
 }
 
@@ -457,6 +467,7 @@ namespace {
 // one warp per row of n elements (pitch ld): y = softmax(scale * x)
 __global__ void __launch_bounds__(256) rowsoftmax_fwd_kernel(const float* __restrict__ x, int ld, long long M, int n, float scale,
                                                              float* __restrict__ y, int ldy) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -473,6 +484,7 @@ __global__ void __launch_bounds__(256) rowsoftmax_fwd_kernel(const float* __rest
 // ds = scale * P (dP - sum_c P dP)   (ds may alias dP)
 __global__ void __launch_bounds__(256) rowsoftmax_bwd_kernel(const float* __restrict__ P, int ldp, const float* dP, int ldd, long long M,
                                                              int n, float scale, float* ds, int lds) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -487,6 +499,7 @@ __global__ void __launch_bounds__(256) rowsoftmax_bwd_kernel(const float* __rest
 // out[(b*R + r)*ldo + c] = scale * sum_s part[((b*S + s)*R + r)*Cc + c]
 __global__ void __launch_bounds__(256) fold_rows_kernel(const float* __restrict__ part, int S, int R, int Cc, float scale,
                                                         float* __restrict__ out, int ldo) {
+  PDL_TOP();
   const int n = R * Cc;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= n) return;
@@ -499,17 +512,17 @@ __global__ void __launch_bounds__(256) fold_rows_kernel(const float* __restrict_
 
 int launch_bwd_rowsoftmax_fwd(const float* x, int ld, long long M, int n, float scale, float* y, int ldy, cudaStream_t st) {
   if (M == 0) return 0;
-  rowsoftmax_fwd_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(x, ld, M, n, scale, y, ldy);
+  tcx_launch_chain(rowsoftmax_fwd_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, st, x, ld, M, n, scale, y, ldy);
   return tcx_check_launch("bwd_rowsoftmax_fwd");
 }
 int launch_bwd_rowsoftmax_bwd(const float* P, int ldp, const float* dP, int ldd, long long M, int n, float scale, float* ds, int lds,
                               cudaStream_t st) {
   if (M == 0) return 0;
-  rowsoftmax_bwd_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(P, ldp, dP, ldd, M, n, scale, ds, lds);
+  tcx_launch_chain(rowsoftmax_bwd_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, st, P, ldp, dP, ldd, M, n, scale, ds, lds);
   return tcx_check_launch("bwd_rowsoftmax_bwd");
 }
 int launch_bwd_fold_rows(const float* part, int batch, int S, int R, int Cc, float scale, float* out, int ldo, cudaStream_t st) {
   if (batch == 0 || R == 0) return 0;
-  fold_rows_kernel<<<dim3(cdiv(R * Cc, 256), batch), 256, 0, st>>>(part, S, R, Cc, scale, out, ldo);
+  tcx_launch_chain(fold_rows_kernel, dim3(dim3(cdiv(R * Cc, 256), batch)), dim3(256), 0, st, part, S, R, Cc, scale, out, ldo);
   return tcx_check_launch("bwd_fold_rows");
 }

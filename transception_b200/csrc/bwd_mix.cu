@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused64_kernel(const flo
                                                                       float eps, float* __restrict__ du, float* __restrict__ act,
                                                                       const float* __restrict__ dres, long long M, int C,
                                                                       float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[LF_WARPS * 2][2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hl = lane & 15, hw = lane >> 4;
   const float invC = 1.0f / (float)C;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(LF_WARPS * 32) ln_bwd_fused_kernel(const float
                                                                     float* __restrict__ du, float* __restrict__ act,
                                                                     const float* __restrict__ dres, long long M, int C,
                                                                     float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[LF_WARPS][2][NV * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invC = 1.0f / (float)C;
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(LW_T) ln_bwd_wide_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                            float* __restrict__ du, float* __restrict__ act, const float* __restrict__ dres,
                                                            long long M, int C, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float red[4][LW_T / 32];
   const float invC = 1.0f / (float)C;
   float4 g4[LW_NV], b4[LW_NV];
@@ -357,6 +360,7 @@ constexpr int DS_C = 32, DS_L = 8;
 __global__ void __launch_bounds__(DS_C * DS_L) dw_bwd_sweep_kernel(const float* __restrict__ du, const __half* __restrict__ h,
                                                                    const float* __restrict__ w, float* __restrict__ dh, int B, int H, int W,
                                                                    int C, int rows, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float sm[DS_L][10][DS_C * 2];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.y * DS_C + tx) * 2;
@@ -439,6 +443,7 @@ __global__ void __launch_bounds__(DS_C * DS_L) dw_bwd_sweep_kernel(const float* 
 }
 
 __global__ void __launch_bounds__(256) add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n4) {
+  PDL_TOP();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
   float4 a = reinterpret_cast<float4*>(y)[i];
@@ -453,6 +458,7 @@ struct SumSrcs {
   const float* p[16];
 };
 __global__ void __launch_bounds__(256) sum_tensors_kernel(SumSrcs s, int n, long long numel, float* __restrict__ out) {
+  PDL_TOP();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= numel) return;
   float a = s.p[0][i];
@@ -467,14 +473,14 @@ int launch_sum_tensors(const float* const* srcs, int n, long long numel, float* 
   if (numel == 0) return 0;
   SumSrcs s{};
   for (int k = 0; k < n; k++) { TCX_REQUIRE(srcs[k] != nullptr, "sum_tensors: source %d is null", k); s.p[k] = srcs[k]; }
-  sum_tensors_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, st>>>(s, n, numel, out);
+  tcx_launch_chain(sum_tensors_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), 0, st, s, n, numel, out);
   return tcx_check_launch("sum_tensors");
 }
 
 int launch_add_inplace(float* y, const float* x, long long n, cudaStream_t st) {
   TCX_REQUIRE(n % 4 == 0 && (((uintptr_t)y | (uintptr_t)x) & 15) == 0, "add_inplace: n %% 4 != 0 or unaligned");
   if (n == 0) return 0;
-  add_inplace_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(y, x, n / 4);
+  tcx_launch_chain(add_inplace_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, st, y, x, n / 4);
   return tcx_check_launch("add_inplace");
 }
 
@@ -496,19 +502,19 @@ int launch_ln_bwd_fused(const float* u, const float* dz, const float* gamma, con
   const int nblk = ln_bwd_fused_blocks(M, C);
   if (C > 512) {
     ProfScope prof("ln_bwd_fused", st, (double)M * C * (gelu && act ? 16.0 : 12.0));
-    if (gelu) ln_bwd_wide_kernel<true><<<nblk, LW_T, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part);
-    else ln_bwd_wide_kernel<false><<<nblk, LW_T, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part);
+    if (gelu) tcx_launch_chain(ln_bwd_wide_kernel<true>, dim3(nblk), dim3(LW_T), 0, st, u, dz, gamma, beta, eps, du, act, dres, M, C, part);
+    else tcx_launch_chain(ln_bwd_wide_kernel<false>, dim3(nblk), dim3(LW_T), 0, st, u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part);
     return tcx_check_launch("ln_bwd_wide");
   }
   ProfScope prof("ln_bwd_fused", st, (double)M * C * (gelu && act ? 16.0 : 12.0));
 #define LNB(NV)                                                                                                         \
   do {                                                                                                                  \
-    if (gelu) ln_bwd_fused_kernel<NV, true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part); \
-    else ln_bwd_fused_kernel<NV, false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part); \
+    if (gelu) tcx_launch_chain(ln_bwd_fused_kernel<NV, true>, dim3(nblk), dim3(LF_WARPS * 32), 0, st, u, dz, gamma, beta, eps, du, act, dres, M, C, part); \
+    else tcx_launch_chain(ln_bwd_fused_kernel<NV, false>, dim3(nblk), dim3(LF_WARPS * 32), 0, st, u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part); \
   } while (0)
   if (C <= 64) {
-    if (gelu) ln_bwd_fused64_kernel<true><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, act, dres, M, C, part);
-    else ln_bwd_fused64_kernel<false><<<nblk, LF_WARPS * 32, 0, st>>>(u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part);
+    if (gelu) tcx_launch_chain(ln_bwd_fused64_kernel<true>, dim3(nblk), dim3(LF_WARPS * 32), 0, st, u, dz, gamma, beta, eps, du, act, dres, M, C, part);
+    else tcx_launch_chain(ln_bwd_fused64_kernel<false>, dim3(nblk), dim3(LF_WARPS * 32), 0, st, u, dz, gamma, beta, eps, du, nullptr, dres, M, C, part);
   } else if (C <= 128) LNB(1);
   else if (C <= 256) LNB(2);
   else LNB(4);
@@ -543,7 +549,7 @@ int launch_dw_bwd_fused(const float* du, const __half* h, const float* w, float*
   const int nblk = (nrow + rows - 1) / rows;
   const dim3 grid(nblk, (C + DS_C * 2 - 1) / (DS_C * 2));
   ProfScope prof("dw_bwd_fused", st, (double)M * C * 10.0);
-  dw_bwd_sweep_kernel<<<grid, dim3(DS_C, DS_L), 0, st>>>(du, h, w, dh, B, H, W, C, rows, part);
+  tcx_launch_chain(dw_bwd_sweep_kernel, dim3(grid), dim3(dim3(DS_C, DS_L)), 0, st, du, h, w, dh, B, H, W, C, rows, part);
   if (nblk_out) *nblk_out = nblk;
   return tcx_check_launch("dw_bwd_fused");
 }

@@ -33,8 +33,17 @@ struct ProfScope {
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// First statement of a kernel launched through tcx_launch_chain: let the next kernel of the stream be scheduled, then block
+// until the preceding kernel has completed and flushed.  Nothing is read before the wait, so the only thing that overlaps
+// the predecessor is this kernel's own launch and block scheduling.
+#define PDL_TOP()  \
+  do {             \
+    pdl_trigger(); \
+    pdl_wait();    \
+  } while (0)
 #endif
 extern int g_tcx_pdl;   // flag "pdl" (default 1)
+extern int g_tcx_pdl_chain;   // flag "pdl_chain": the training-row kernels (backward, loss, optimizer, glue) carry the attribute too
 extern int g_tcx_smem_kb;    // flag "smem_kb" (default 0 = whole SM): shared-memory budget of the tcgen05 GEMM kernels
 extern int g_tcx_wgrad_ctas;   // flag "wgrad_ctas" (0 = resident-cluster capacity): CTA budget of one weight-gradient launch
 extern int g_tcx_wgrad_idle;   // flag "wgrad_idle": allow splits that leave some CTAs without tokens
@@ -48,6 +57,20 @@ inline cudaError_t tcx_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_tcx_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Launch of a kernel that starts with PDL_TOP() (the CUDA-core kernels of the training row): same attribute as tcx_launch_pdl,
+// switched by "pdl" AND "pdl_chain".  Errors are picked up by the tcx_check_launch that follows every launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t tcx_launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (g_tcx_pdl && g_tcx_pdl_chain) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

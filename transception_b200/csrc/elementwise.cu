@@ -15,6 +15,7 @@ struct LnGroups {
 // One warp per row, row held in registers (NV float4 per lane), exact two-pass statistics.
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnGroups gs, long long M, int C, float eps) {
+  PDL_TOP();
   const LnGroup& g = gs.g[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -66,6 +67,7 @@ struct DwGroups {
 template <int EPI>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwGroups gs, int B, int H, int W, int C, int stride,
                                                         int Ho, int Wo, BnParams bn) {
+  PDL_TOP();
   const DwGroup& g = gs.g[blockIdx.y];
   const int cv = C >> 2;
   const long long total = (long long)B * Ho * Wo * cv;
@@ -119,6 +121,7 @@ struct MixMidGroups {
 // C4-wide row stays in registers between the convolution and the LayerNorm.
 template <int NV>
 __global__ void __launch_bounds__(256) mixffn_mid_kernel(const MixMidGroups gs, int B, int H, int W, int C4, float eps) {
+  PDL_TOP();
   const MixMidGroup& g = gs.g[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(256) mixffn_mid_kernel(const MixMidGroups gs, 
 
 // fp32 -> fp16 (round to nearest, saturating), 8 elements per thread
 __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  PDL_TOP();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict
 // fp32 -> fp16(x * scale), clamped to the finite fp16 range (a gradient operand never becomes inf)
 __global__ void __launch_bounds__(256) f32_to_f16_scaled_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n,
                                                                float scale) {
+  PDL_TOP();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   auto cv = [scale](float v) { return fminf(fmaxf(v * scale, -65504.f), 65504.f); };
   if (i + 8 <= n) {
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(256) f32_to_f16_scaled_kernel(const float* __r
 }
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  PDL_TOP();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
@@ -230,6 +236,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+  PDL_TOP();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const uint4 raw = *reinterpret_cast<const uint4*>(src + i);
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restric
 
 // up to three independent tensors -> bf16 in one launch (the operands of one Linear backward: dy fp32, x fp16 | fp32, w fp32)
 __global__ void __launch_bounds__(256) to_bf16_multi_kernel(const CvtSegs segs) {
+  PDL_TOP();
   long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int k = 0;
   while (k < segs.n && chunk >= segs.chunks[k]) { chunk -= segs.chunks[k]; k++; }
@@ -281,7 +289,7 @@ int launch_f16_to_f32(const __half* src, float* dst, long long n, cudaStream_t s
   if (n <= 0) return 0;
   TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f16_to_f32: pointers must be 16-byte aligned");
   const long long threads = (n + 7) / 8;
-  f16_to_f32_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, dst, n);
+  tcx_launch_chain(f16_to_f32_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, src, dst, n);
   return tcx_check_launch("f16_to_f32");
 }
 
@@ -293,7 +301,7 @@ int launch_to_bf16_multi(CvtSegs segs, cudaStream_t st) {
     total += segs.chunks[k];
   }
   if (total == 0) return 0;
-  to_bf16_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(segs);
+  tcx_launch_chain(to_bf16_multi_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, segs);
   return tcx_check_launch("to_bf16_multi");
 }
 
@@ -301,7 +309,7 @@ int launch_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t st
   if (n <= 0) return 0;
   TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f32_to_bf16: pointers must be 16-byte aligned");
   const long long threads = (n + 7) / 8;
-  f32_to_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  tcx_launch_chain(f32_to_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   return tcx_check_launch("f32_to_bf16");
 }
 
@@ -309,7 +317,7 @@ int launch_f32_to_f16_scaled(const float* src, __half* dst, long long n, float s
   if (n <= 0) return 0;
   TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f32_to_f16_scaled: pointers must be 16-byte aligned");
   const long long threads = (n + 7) / 8;
-  f32_to_f16_scaled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, dst, n, scale);
+  tcx_launch_chain(f32_to_f16_scaled_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, src, dst, n, scale);
   return tcx_check_launch("f32_to_f16_scaled");
 }
 
@@ -317,7 +325,7 @@ int launch_f32_to_f16(const float* src, void* dst, long long n, cudaStream_t st)
   if (n <= 0) return 0;
   TCX_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "f32_to_f16: pointers must be 16-byte aligned");
   const long long threads = (n + 7) / 8;
-  f32_to_f16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), n);
+  tcx_launch_chain(f32_to_f16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, src, reinterpret_cast<__half*>(dst), n);
   return tcx_check_launch("f32_to_f16");
 }
 
@@ -340,7 +348,7 @@ int launch_layernorm_grouped(const LnGroup* g, int groups, long long M, int C, f
   LnGroups gs{};
   for (int i = 0; i < groups; i++) gs.g[i] = g[i];
   dim3 grid((unsigned)((M + 7) / 8), groups);
-#define CALL(NV) layernorm_kernel<NV><<<grid, 256, 0, st>>>(gs, M, C, eps)
+#define CALL(NV) tcx_launch_chain(layernorm_kernel<NV>, dim3(grid), dim3(256), 0, st, gs, M, C, eps)
   DISPATCH_NV(C, CALL);
 #undef CALL
   return tcx_check_launch("layernorm");
@@ -360,9 +368,9 @@ int launch_dwconv3x3(const DwGroup* g, int groups, int B, int H, int W, int C, i
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)B * Ho * Wo * (C / 4);
   dim3 grid((unsigned)((total + 255) / 256), groups);
-  if (epi == DW_PLAIN) dwconv3x3_kernel<DW_PLAIN><<<grid, 256, 0, st>>>(gs, B, H, W, C, stride, Ho, Wo, bn);
-  else if (epi == DW_ADD_INPUT) dwconv3x3_kernel<DW_ADD_INPUT><<<grid, 256, 0, st>>>(gs, B, H, W, C, stride, Ho, Wo, bn);
-  else dwconv3x3_kernel<DW_BN_HS><<<grid, 256, 0, st>>>(gs, B, H, W, C, stride, Ho, Wo, bn);
+  if (epi == DW_PLAIN) tcx_launch_chain(dwconv3x3_kernel<DW_PLAIN>, dim3(grid), dim3(256), 0, st, gs, B, H, W, C, stride, Ho, Wo, bn);
+  else if (epi == DW_ADD_INPUT) tcx_launch_chain(dwconv3x3_kernel<DW_ADD_INPUT>, dim3(grid), dim3(256), 0, st, gs, B, H, W, C, stride, Ho, Wo, bn);
+  else tcx_launch_chain(dwconv3x3_kernel<DW_BN_HS>, dim3(grid), dim3(256), 0, st, gs, B, H, W, C, stride, Ho, Wo, bn);
   return tcx_check_launch("dwconv3x3");
 }
 
@@ -373,7 +381,7 @@ int launch_mixffn_mid(const MixMidGroup* g, int groups, int B, int H, int W, int
   const long long total = (long long)B * H * W;
   dim3 grid((unsigned)((total + 7) / 8), groups);
   ProfScope prof("mixffn_mid", st);
-#define CALL(NV) mixffn_mid_kernel<NV><<<grid, 256, 0, st>>>(gs, B, H, W, C4, eps)
+#define CALL(NV) tcx_launch_chain(mixffn_mid_kernel<NV>, dim3(grid), dim3(256), 0, st, gs, B, H, W, C4, eps)
   DISPATCH_NV(C4, CALL);
 #undef CALL
   return tcx_check_launch("mixffn_mid");

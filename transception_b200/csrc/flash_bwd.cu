@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_bwd_kernel(const __grid_c
                                                                   const float* __restrict__ dsum, const float* __restrict__ scale_ptr,
                                                                   float* __restrict__ dq_part, float* __restrict__ dkv, int B, int Nq,
                                                                   int Nk, float scale, float qscale) {
+  PDL_TOP();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* kv_full = reinterpret_cast<uint64_t*>(smem + FB_OFF_BAR);
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_bwd_kernel(const __grid_c
 
 // ---- pre-pass 1: absolute maximum of dO (as ordered uint bits: atomicMax is order-independent, hence deterministic) ----
 __global__ void __launch_bounds__(256) fb_absmax_kernel(const float* __restrict__ x, long long n4, unsigned* __restrict__ out) {
+  PDL_TOP();
   __shared__ unsigned sm[8];
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(256) fb_prep_kernel(const float* __restrict__ 
                                                       const float* __restrict__ kv, const unsigned* __restrict__ absmax, __half* __restrict__ q16,
                                                       __half* __restrict__ do16, __half* __restrict__ kv16, float* __restrict__ dsum,
                                                       float* __restrict__ scale_out, long long Mq, long long Mkv) {
+  PDL_TOP();
   const float amax = __uint_as_float(*absmax);
   int e = 0;
   if (amax > 0.f) frexpf(amax, &e);                 // amax = f * 2^e, f in [0.5, 1)
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(256) fb_prep_kernel(const float* __restrict__ 
 // ---- dq = (1 / s) * sum_j part[j] in tile order ----
 __global__ void __launch_bounds__(256) fb_fold_dq_kernel(const float* __restrict__ part, int nkt, long long n4, const float* __restrict__ scale_ptr,
                                                          float* __restrict__ dq) {
+  PDL_TOP();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
   const float inv = 1.0f / *scale_ptr;
@@ -351,9 +355,9 @@ int launch_flash_bwd(const float* q, const float* kv, const float* out, const fl
   float* small = take(64);            // [0] = absmax bits, [1] = scale
   float* part = take((size_t)nkt * mq * FB_D);
   TCX_REQUIRE(cudaMemsetAsync(small, 0, 8, st) == cudaSuccess, "flash_bwd: memset failed");
-  fb_absmax_kernel<<<296, 256, 0, st>>>(dout, mq * FB_D / 4, reinterpret_cast<unsigned*>(small));
+  tcx_launch_chain(fb_absmax_kernel, dim3(296), dim3(256), 0, st, dout, mq * FB_D / 4, reinterpret_cast<unsigned*>(small));
   TCX_TRY(tcx_check_launch("fb_absmax"));
-  fb_prep_kernel<<<(unsigned)((mq + mkv + 7) / 8), 256, 0, st>>>(q, dout, out, kv, reinterpret_cast<const unsigned*>(small), q16, do16, kv16,
+  tcx_launch_chain(fb_prep_kernel, dim3((unsigned)((mq + mkv + 7) / 8)), dim3(256), 0, st, q, dout, out, kv, reinterpret_cast<const unsigned*>(small), q16, do16, kv16,
                                                                   dsum, small + 1, mq, mkv);
   TCX_TRY(tcx_check_launch("fb_prep"));
   FbMaps maps;
@@ -367,10 +371,10 @@ int launch_flash_bwd(const float* q, const float* kv, const float* out, const fl
   }
   {
     ProfScope prof("flash_bwd", st, 10.0 * B * (double)Nq * Nk * FB_D);     // five 2*Nq*Nk*64 contractions
-    flash_bwd_kernel<<<B * nkt, FB_THREADS, FB_SMEM, st>>>(maps, lse, dsum, small + 1, part, dkv, B, Nq, Nk, scale,
+    tcx_launch_chain(flash_bwd_kernel, dim3(B * nkt), dim3(FB_THREADS), FB_SMEM, st, maps, lse, dsum, small + 1, part, dkv, B, Nq, Nk, scale,
                                                            scale * 1.4426950408889634f);
     TCX_TRY(tcx_check_launch("flash_bwd"));
   }
-  fb_fold_dq_kernel<<<(unsigned)((mq * FB_D / 4 + 255) / 256), 256, 0, st>>>(part, nkt, mq * FB_D / 4, small + 1, dq);
+  tcx_launch_chain(fb_fold_dq_kernel, dim3((unsigned)((mq * FB_D / 4 + 255) / 256)), dim3(256), 0, st, part, nkt, mq * FB_D / 4, small + 1, dq);
   return tcx_check_launch("fb_fold_dq");
 }

@@ -52,6 +52,7 @@ __device__ __forceinline__ float pixel_probs(const float* __restrict__ base, int
 }
 
 __global__ void __launch_bounds__(256) seg_loss_partial_kernel(SegLossArgs a, float* __restrict__ partial) {
+  PDL_TOP();
   __shared__ float red[8][NV];
   const long long npix = (long long)a.B * a.HW;
   float acc[NV];
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) seg_loss_partial_kernel(SegLossArgs a, fl
 // stats layout (floats): [0] ce sum, [1] bad labels, [2..) I, Z, Y (KMAX each); out: loss, ce, dice, bad, class-wise dice[K]
 __global__ void __launch_bounds__(64) seg_loss_final_kernel(SegLossArgs a, const float* __restrict__ partial, int nblk, float* __restrict__ stats,
                                                             float* __restrict__ out) {
+  PDL_TOP();
   __shared__ float tot[NV];
   if (threadIdx.x < NV) {
     float v = 0.f;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(64) seg_loss_final_kernel(SegLossArgs a, const
 
 __global__ void __launch_bounds__(256) seg_loss_grad_kernel(SegLossArgs a, const float* __restrict__ stats, const float* __restrict__ grad_out,
                                                             float* __restrict__ dlogits) {
+  PDL_TOP();
   __shared__ float ca[KMAX], cb[KMAX];     // d dice / d p_c = -ca[c] * t_c + cb[c] * p_c
   if (threadIdx.x < KMAX) {
     const int c = threadIdx.x;
@@ -173,6 +176,7 @@ __global__ void __launch_bounds__(256) seg_loss_grad_kernel(SegLossArgs a, const
 // monotone, so the arg max is taken on the logits; first index wins ties like torch.argmax).  9x fewer bytes cross PCIe than logits.
 __global__ void __launch_bounds__(256) argmax_classes_kernel(const float* __restrict__ logits, unsigned char* __restrict__ out, int B, int K,
                                                              long long HW) {
+  PDL_TOP();
   const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
   if (n >= (long long)B * HW) return;
   const long long b = n / HW, hw = n - b * HW;
@@ -209,10 +213,10 @@ int launch_seg_loss_fwd(const SegLossArgs& a, float* out, float* ws, cudaStream_
   float* partial = ws + NV;
   {
     ProfScope prof("seg_loss_partial", st, (double)npix * (a.K * 4.0 + 4.0));
-    seg_loss_partial_kernel<<<nblk, 256, 0, st>>>(a, partial);
+    tcx_launch_chain(seg_loss_partial_kernel, dim3(nblk), dim3(256), 0, st, a, partial);
     TCX_TRY(tcx_check_launch("seg_loss_partial"));
   }
-  seg_loss_final_kernel<<<1, 64, 0, st>>>(a, partial, nblk, stats, out);
+  tcx_launch_chain(seg_loss_final_kernel, dim3(1), dim3(64), 0, st, a, partial, nblk, stats, out);
   return tcx_check_launch("seg_loss_final");
 }
 
@@ -221,7 +225,7 @@ int launch_seg_loss_bwd(const SegLossArgs& a, const float* ws, const float* grad
   const long long npix = (long long)a.B * a.HW;
   if (npix == 0) return 0;
   ProfScope prof("seg_loss_grad", st, (double)npix * (a.K * 8.0 + 4.0));
-  seg_loss_grad_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(a, ws, grad_out, dlogits);
+  tcx_launch_chain(seg_loss_grad_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, a, ws, grad_out, dlogits);
   return tcx_check_launch("seg_loss_grad");
 }
 
@@ -230,6 +234,6 @@ int launch_argmax_classes(const float* logits, unsigned char* out, int B, int K,
   const long long npix = (long long)B * HW;
   if (npix == 0) return 0;
   ProfScope prof("argmax_classes", st, (double)npix * (K * 4.0 + 1.0));
-  argmax_classes_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(logits, out, B, K, HW);
+  tcx_launch_chain(argmax_classes_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, st, logits, out, B, K, HW);
   return tcx_check_launch("argmax_classes");
 }

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) patch_embed_ln_kernel(const float* __rest
 // outside the image); xs_c = 0: the grey plane stands for all three input channels (MSTr.py:2828-2829)
 __global__ void __launch_bounds__(256) patch_im2row_kernel(const float* __restrict__ x, long long xs_b, long long xs_c, int Hin, int Win,
                                                            int Ho, int Wo, int Kp, long long total, float* __restrict__ A) {
+  PDL_TOP();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const int k = (int)(idx % Kp);
@@ -139,6 +140,7 @@ __device__ __forceinline__ void regroup_locate(const int* tok_off, long long per
   slab_idx = (long long)b * n_k + local;
 }
 __global__ void __launch_bounds__(256) regroup_kernel(RegroupArgs a) {
+  PDL_TOP();
   const long long per_img = (long long)a.ntok * 16;   // float4 per image
   const long long total = per_img * a.B;
   const long long base = ((long long)blockIdx.x * RG_UNROLL) * 256 + threadIdx.x;
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) regroup_kernel(RegroupArgs a) {
 }
 
 __global__ void __launch_bounds__(256) ungroup_kernel(UngroupArgs a) {
+  PDL_TOP();
   const long long per_img = (long long)a.ntok * 16;
   const long long total = per_img * a.B;
   const long long base = ((long long)blockIdx.x * RG_UNROLL) * 256 + threadIdx.x;
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(256) ungroup_kernel(UngroupArgs a) {
 // patch-matrix side (whose K order (cin, ky, kx) is the conv weight's own); Cin % 4 == 0
 __global__ void __launch_bounds__(256) sr_im2row_kernel(const float* __restrict__ x, long long xs_b, int HW, int Cin, int r,
                                                         int B, float* __restrict__ A) {
+  PDL_TOP();
   // x: per image [HW][HW][Cin] at x + b*xs_b ; A: [B*P*P][Cin*r*r], P = HW/r
   const int P = HW / r, C4 = Cin >> 2, rr = r * r;
   const long long K = (long long)Cin * rr;
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(256) sr_im2row_kernel(const float* __restrict_
 // the same permutation backwards: dx[b][(i*r+ky)*HW + j*r+kx][cin] = dA[(b,i,j)][(cin,ky,kx)]  (coalesced on the dx side)
 __global__ void __launch_bounds__(256) sr_row2im_kernel(const float* __restrict__ dA, long long xs_b, int HW, int Cin, int r,
                                                         int B, float* __restrict__ dx) {
+  PDL_TOP();
   const int P = HW / r, C4 = Cin >> 2, rr = r * r;
   const long long K = (long long)Cin * rr;
   const long long total = (long long)B * P * P * rr * C4;
@@ -232,6 +237,7 @@ __global__ void __launch_bounds__(256) sr_row2im_kernel(const float* __restrict_
 // pack conv outputs + raw stage-4 tokens into the reduced sequence and LayerNorm(64) it.
 // reduced token t of image b: scale k, t_local = (c % g)*49 + s, feature f = c // g  
 __global__ void __launch_bounds__(256) sr_pack_ln_kernel(SrPackArgs a) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)a.B * a.nred) return;
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(256) sr_pack_ln_kernel(SrPackArgs a) {
 
 // gradient of the packing above (no LayerNorm): one warp per reduced row scatters it to its conv output / raw token row
 __global__ void __launch_bounds__(256) sr_unpack_kernel(SrUnpackArgs a) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)a.B * a.nred) return;
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(256) sr_im2row16_kernel(const __half* __restri
 // [N][Cin][r][r] fp32 conv weight -> [N][(ky, kx, cin)] fp16
 __global__ void __launch_bounds__(256) conv_weight_perm16_kernel(const float* __restrict__ w, __half* __restrict__ o, int N, int Cin,
                                                                  int r) {
+  PDL_TOP();
   const long long total = (long long)N * Cin * r * r;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -358,6 +366,7 @@ __global__ void __launch_bounds__(256) sr_pack_ln16_kernel(SrPackArgs a, const _
 // grid (HW, 4, 2B), one thread per channel (coalesced): blockIdx.z < B -> the row mean of map row blockIdx.x,
 // otherwise the column mean of map column blockIdx.x.  Fixed summation order: deterministic, no atomics.
 __global__ void __launch_bounds__(512) iff_pool_kernel(IffSrc src, int B, int HW, int C, float* __restrict__ pooled) {
+  PDL_TOP();
   const int i = blockIdx.x, s = blockIdx.y;
   const bool col = (int)blockIdx.z >= B;
   const int b = col ? blockIdx.z - B : blockIdx.z;
@@ -376,6 +385,7 @@ __global__ void __launch_bounds__(512) iff_pool_kernel(IffSrc src, int B, int HW
 // gated[b,h,w,k] = x_src(k)[b,h,w,k%C] * a_w[b,w,k] * a_h[b,h,k]
 __global__ void __launch_bounds__(256) iff_gate_kernel(IffSrc src, int B, int H, int W, int C, const float* __restrict__ ah,
                                                        const float* __restrict__ aw, float* __restrict__ out) {
+  PDL_TOP();
   const int c4n = C >> 2;
   const long long total = (long long)B * H * W * 4 * c4n;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,6 +412,7 @@ __global__ void __launch_bounds__(256) iff_gate_kernel(IffSrc src, int B, int H,
 __global__ void __launch_bounds__(256) shuffle_ln_kernel(const float* __restrict__ in, int B, int H, int W, int s, int c,
                                                          const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                          float eps, float* __restrict__ out) {
+  PDL_TOP();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int Ho = H * s, Wo = W * s;
@@ -436,6 +447,7 @@ __global__ void __launch_bounds__(128) final_head_kernel(const float* __restrict
                                                          const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                          float eps, const float* __restrict__ cw, const float* __restrict__ cb,
                                                          int ncls, float* __restrict__ out) {
+  PDL_TOP();
   __shared__ float wsm[MAXCLS * 64 + MAXCLS + 128];
   float* wl = wsm;                       // [ncls][64]  with LN weight folded in
   float* bl = wsm + MAXCLS * 64;         // [ncls]      bias + sum(lnb*cw)
@@ -508,6 +520,7 @@ __global__ void __launch_bounds__(FH_WARPS * 32, 1) final_head_bwd_kernel(const 
                                                                           int B, int H, int W, const float* __restrict__ lnw,
                                                                           const float* __restrict__ cw, float eps, int ncls,
                                                                           float* __restrict__ de, float* __restrict__ part) {
+  PDL_TOP();
   __shared__ float s_red[FH_WARPS][FH_K * 64 + FH_K];
   extern __shared__ float4 fh_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -644,6 +657,7 @@ __global__ void __launch_bounds__(FH_WARPS * 32, 1) final_head_bwd_kernel(const 
 
 // fold of the block partials (ordered, bwd_fold_sum), then the four parameter gradients from the folded G | s
 __global__ void __launch_bounds__(256) final_head_fold_kernel(const float* __restrict__ part, int nblk, float* __restrict__ Gs) {
+  PDL_TOP();
   const int n = FH_K * 64 + FH_K;
   const int i = blockIdx.x * 32 + threadIdx.x;
   const float s = bwd_fold_sum(part, nblk, n, i, i < n);
@@ -653,6 +667,7 @@ __global__ void __launch_bounds__(256) final_head_params_kernel(const float* __r
                                                                 const float* __restrict__ lnb, const float* __restrict__ cw, int ncls,
                                                                 float* __restrict__ dlnw, float* __restrict__ dlnb, float* __restrict__ dcw,
                                                                 float* __restrict__ dcb) {
+  PDL_TOP();
   const float* sk = G + FH_K * 64;
   for (int i = threadIdx.x; i < ncls * 64; i += 256) {
     const int k = i >> 6, c = i & 63;
@@ -689,25 +704,25 @@ int launch_patch_im2row(const float* x, long long xs_b, long long xs_c, int B, i
   const long long total = (long long)B * Ho * Wo * Kp;
   TCX_REQUIRE(Kp >= 147, "patch_im2row: row pitch %d < 147", Kp);
   if (total == 0) return 0;
-  patch_im2row_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, xs_b, xs_c, Hin, Win, Ho, Wo, Kp, total, A);
+  tcx_launch_chain(patch_im2row_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, xs_b, xs_c, Hin, Win, Ho, Wo, Kp, total, A);
   return tcx_check_launch("patch_im2row");
 }
 
 int launch_regroup(const RegroupArgs& a, cudaStream_t st) {
   const long long total = (long long)a.B * a.ntok * 16;
-  regroup_kernel<<<(unsigned)((total + 256 * RG_UNROLL - 1) / (256 * RG_UNROLL)), 256, 0, st>>>(a);
+  tcx_launch_chain(regroup_kernel, dim3((unsigned)((total + 256 * RG_UNROLL - 1) / (256 * RG_UNROLL))), dim3(256), 0, st, a);
   return tcx_check_launch("bridge_regroup");
 }
 
 int launch_ungroup(const UngroupArgs& a, cudaStream_t st) {
   const long long total = (long long)a.B * a.ntok * 16;
-  ungroup_kernel<<<(unsigned)((total + 256 * RG_UNROLL - 1) / (256 * RG_UNROLL)), 256, 0, st>>>(a);
+  tcx_launch_chain(ungroup_kernel, dim3((unsigned)((total + 256 * RG_UNROLL - 1) / (256 * RG_UNROLL))), dim3(256), 0, st, a);
   return tcx_check_launch("bridge_ungroup");
 }
 
 int launch_sr_unpack(const SrUnpackArgs& a, cudaStream_t st) {
   const long long rows = (long long)a.B * a.nred;
-  sr_unpack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
+  tcx_launch_chain(sr_unpack_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, a);
   return tcx_check_launch("sr_unpack");
 }
 
@@ -715,7 +730,7 @@ int launch_sr_row2im(const float* dA, long long xs_b, int HW, int Cin, int r, in
   const int P = HW / r;
   TCX_REQUIRE(Cin % 4 == 0 && (xs_b % 4) == 0, "sr_row2im: Cin and the image stride must be multiples of 4 (Cin=%d)", Cin);
   const long long total = (long long)B * P * P * Cin * r * r / 4;
-  sr_row2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dA, xs_b, HW, Cin, r, B, dx);
+  tcx_launch_chain(sr_row2im_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, dA, xs_b, HW, Cin, r, B, dx);
   return tcx_check_launch("sr_row2im");
 }
 
@@ -723,13 +738,13 @@ int launch_sr_im2row(const float* x, long long xs_b, int HW, int Cin, int r, int
   const int P = HW / r;
   TCX_REQUIRE(Cin % 4 == 0 && (xs_b % 4) == 0, "sr_im2row: Cin and the image stride must be multiples of 4 (Cin=%d)", Cin);
   const long long total = (long long)B * P * P * Cin * r * r / 4;
-  sr_im2row_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, xs_b, HW, Cin, r, B, A);
+  tcx_launch_chain(sr_im2row_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, xs_b, HW, Cin, r, B, A);
   return tcx_check_launch("sr_im2row");
 }
 
 int launch_sr_pack_ln(const SrPackArgs& a, cudaStream_t st) {
   const long long rows = (long long)a.B * a.nred;
-  sr_pack_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
+  tcx_launch_chain(sr_pack_ln_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, a);
   return tcx_check_launch("sr_pack_ln");
 }
 
@@ -737,14 +752,14 @@ int launch_iff_pool(const IffSrc& src, int B, int HW, int C, float* pooled, cuda
   dim3 grid(HW, 4, 2 * B);
   int threads = (C + 31) / 32 * 32;
   if (threads > 512) threads = 512;
-  iff_pool_kernel<<<grid, threads, 0, st>>>(src, B, HW, C, pooled);
+  tcx_launch_chain(iff_pool_kernel, dim3(grid), dim3(threads), 0, st, src, B, HW, C, pooled);
   return tcx_check_launch("iff_pool");
 }
 
 int launch_iff_gate(const IffSrc& src, int B, int H, int W, int C, const float* ah, const float* aw, float* out,
                     cudaStream_t st) {
   const long long total = (long long)B * H * W * C;
-  iff_gate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, B, H, W, C, ah, aw, out);
+  tcx_launch_chain(iff_gate_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, src, B, H, W, C, ah, aw, out);
   return tcx_check_launch("iff_gate");
 }
 
@@ -752,7 +767,7 @@ int launch_shuffle_ln(const float* in, int B, int H, int W, int s, int c, const 
                       float* out, cudaStream_t st) {
   TCX_REQUIRE(c <= 256, "patch_expand: c=%d > 256", c);
   const long long rows = (long long)B * H * s * W * s;
-  shuffle_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, B, H, W, s, c, lnw, lnb, eps, out);
+  tcx_launch_chain(shuffle_ln_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, in, B, H, W, s, c, lnw, lnb, eps, out);
   return tcx_check_launch("shuffle_ln");
 }
 
@@ -760,7 +775,7 @@ int launch_final_head(const float* in, int B, int H, int W, const float* lnw, co
                       const float* cw, const float* cb, int ncls, float* out, cudaStream_t st) {
   TCX_REQUIRE(ncls >= 1 && ncls <= 32, "final_head: ncls=%d out of range (1..32)", ncls);
   const long long total = (long long)B * H * 4 * W * 4;
-  final_head_kernel<32><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(in, B, H, W, lnw, lnb, eps, cw, cb, ncls, out);
+  tcx_launch_chain(final_head_kernel<32>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, st, in, B, H, W, lnw, lnb, eps, cw, cb, ncls, out);
   return tcx_check_launch("final_head");
 }
 
@@ -783,9 +798,9 @@ int launch_final_head_bwd(const float* e, const float* dlogits, int B, int H, in
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(final_head_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_DYN_SMEM);
     TCX_REQUIRE(ce == cudaSuccess, "final_head_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce));
   }
-  if (ncls <= 4) final_head_bwd_kernel<4><<<grid, FH_WARPS * 32, FH_DYN_SMEM, st>>>(e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
-  else if (ncls <= 10) final_head_bwd_kernel<10><<<grid, FH_WARPS * 32, FH_DYN_SMEM, st>>>(e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
-  else final_head_bwd_kernel<16><<<grid, FH_WARPS * 32, FH_DYN_SMEM, st>>>(e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
+  if (ncls <= 4) tcx_launch_chain(final_head_bwd_kernel<4>, dim3(grid), dim3(FH_WARPS * 32), FH_DYN_SMEM, st, e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
+  else if (ncls <= 10) tcx_launch_chain(final_head_bwd_kernel<10>, dim3(grid), dim3(FH_WARPS * 32), FH_DYN_SMEM, st, e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
+  else tcx_launch_chain(final_head_bwd_kernel<16>, dim3(grid), dim3(FH_WARPS * 32), FH_DYN_SMEM, st, e, dlogits, B, H, W, lnw, cw, eps, ncls, de, part);
   *nblk_out = grid;
   return tcx_check_launch("final_head_bwd");
 }
@@ -793,9 +808,9 @@ int launch_final_head_bwd(const float* e, const float* dlogits, int B, int H, in
 int launch_final_head_bwd_fold(float* part, int nblk, const float* lnw, const float* lnb, const float* cw, int ncls, float* dlnw,
                                float* dlnb, float* dcw, float* dcb, cudaStream_t st) {
   float* Gs = part + (size_t)nblk * (FH_K * 64 + FH_K);
-  final_head_fold_kernel<<<(FH_K * 64 + FH_K + 31) / 32, dim3(32, 8), 0, st>>>(part, nblk, Gs);
+  tcx_launch_chain(final_head_fold_kernel, dim3((FH_K * 64 + FH_K + 31) / 32), dim3(dim3(32, 8)), 0, st, part, nblk, Gs);
   TCX_TRY(tcx_check_launch("final_head_fold"));
-  final_head_params_kernel<<<1, 256, 0, st>>>(Gs, lnw, lnb, cw, ncls, dlnw, dlnb, dcw, dcb);
+  tcx_launch_chain(final_head_params_kernel, dim3(1), dim3(256), 0, st, Gs, lnw, lnb, cw, ncls, dlnw, dlnb, dcw, dcb);
   return tcx_check_launch("final_head_params");
 }
 
@@ -812,7 +827,7 @@ int launch_sr_im2row16(const void* x16, long long xs_b, int HW, int Cin, int r, 
 int launch_conv_weight_perm16(const float* w, void* o16, int N, int Cin, int r, cudaStream_t st) {
   const long long total = (long long)N * Cin * r * r;
   if (total == 0) return 0;
-  conv_weight_perm16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, reinterpret_cast<__half*>(o16), N, Cin, r);
+  tcx_launch_chain(conv_weight_perm16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, w, reinterpret_cast<__half*>(o16), N, Cin, r);
   return tcx_check_launch("conv_weight_perm16");
 }
 

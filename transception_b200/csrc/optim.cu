@@ -22,6 +22,7 @@ __device__ unsigned g_mt_ticket = 0;
 __global__ void __launch_bounds__(MT_THREADS) mt_gather_kernel(const float* const* __restrict__ src, const long long* __restrict__ numel,
                                                                const long long* __restrict__ offset, const int2* __restrict__ blocks,
                                                                float* __restrict__ flat) {
+  PDL_TOP();
   const int2 bk = blocks[blockIdx.x];
   const long long n = numel[bk.x], i0 = (long long)bk.y * MT_CHUNK;
   const float* s = src[bk.x];
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_gather_kernel(const float* cons
 __global__ void __launch_bounds__(MT_THREADS) mt_sqnorm_kernel(const float* const* __restrict__ g, const long long* __restrict__ numel,
                                                                const int2* __restrict__ blocks, int nblocks, float* __restrict__ part,
                                                                float max_norm, float* __restrict__ out /* [norm, coef] */) {
+  PDL_TOP();
   __shared__ float sm[MT_THREADS];
   __shared__ bool last;
   const int2 bk = blocks[blockIdx.x];
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sgd_kernel(float* const* __rest
                                                             const long long* __restrict__ numel, const int2* __restrict__ blocks,
                                                             const float* __restrict__ lr_ptr, const float* __restrict__ coef_ptr,
                                                             float momentum, float wd) {
+  PDL_TOP();
   const int2 bk = blocks[blockIdx.x];
   const long long n = numel[bk.x], i0 = (long long)bk.y * MT_CHUNK;
   float* pp = p[bk.x];
@@ -104,7 +107,7 @@ int tcx_mt_chunk(void) { return MT_CHUNK; }
 int tcx_mt_gather(const void* src_ptrs, const void* numel, const void* offsets, const void* blocks, int nblocks, float* flat, void* stream) {
   TCX_REQUIRE(src_ptrs && numel && offsets && blocks && flat, "mt_gather: null pointer");
   if (nblocks <= 0) return 0;
-  mt_gather_kernel<<<nblocks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  tcx_launch_chain(mt_gather_kernel, dim3(nblocks), dim3(MT_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const float* const*>(src_ptrs), reinterpret_cast<const long long*>(numel), reinterpret_cast<const long long*>(offsets),
       reinterpret_cast<const int2*>(blocks), flat);
   return tcx_check_launch("mt_gather");
@@ -114,7 +117,7 @@ int tcx_mt_sqnorm(const void* grad_ptrs, const void* numel, const void* blocks, 
                   void* stream) {
   TCX_REQUIRE(grad_ptrs && numel && blocks && part && out, "mt_sqnorm: null pointer");
   if (nblocks <= 0) return 0;
-  mt_sqnorm_kernel<<<nblocks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  tcx_launch_chain(mt_sqnorm_kernel, dim3(nblocks), dim3(MT_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const float* const*>(grad_ptrs), reinterpret_cast<const long long*>(numel), reinterpret_cast<const int2*>(blocks), nblocks,
       part, max_norm, out);
   return tcx_check_launch("mt_sqnorm");
@@ -124,7 +127,7 @@ int tcx_mt_sgd(const void* param_ptrs, const void* grad_ptrs, const void* buf_pt
                const void* blocks, int nblocks, const float* lr, const float* coef, float momentum, float weight_decay, void* stream) {
   TCX_REQUIRE(param_ptrs && grad_ptrs && buf_ptrs && w16_ptrs && numel && blocks && lr, "mt_sgd: null pointer");
   if (nblocks <= 0) return 0;
-  mt_sgd_kernel<<<nblocks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  tcx_launch_chain(mt_sgd_kernel, dim3(nblocks), dim3(MT_THREADS), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<float* const*>(const_cast<void*>(param_ptrs)), reinterpret_cast<const float* const*>(grad_ptrs),
       reinterpret_cast<float* const*>(const_cast<void*>(buf_ptrs)), reinterpret_cast<__half* const*>(const_cast<void*>(w16_ptrs)),
       reinterpret_cast<const long long*>(numel), reinterpret_cast<const int2*>(blocks), lr, coef, momentum, weight_decay);

@@ -16,6 +16,10 @@ MHCA_NP = 24
 
 _lib = None
 _lock = threading.Lock()
+# Programmatic dependent launch on the CUDA-core kernels of the training row (library flag "pdl_chain", csrc/common.cuh
+# tcx_launch_chain): 1 = those kernels carry the attribute like the tensor-core pipeline kernels do.  The environment
+# variable TCX_PDL_CHAIN overrides it at load time (measurement aid: A/B runs of bench.py).
+PDL_CHAIN = 0
 _launches = 0          # C-ABI calls issued (each enqueues >= 1 kernel); see kernel_launch_estimate in bench.py
 
 _vp, _i, _f, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t
@@ -164,6 +168,7 @@ def load_library():
             for name, (res, args) in _PROTOS.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
+            lib.tcx_set_flag(b"pdl_chain", int(os.environ.get("TCX_PDL_CHAIN", PDL_CHAIN)))
             _lib = lib
     return _lib
 
