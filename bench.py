@@ -629,6 +629,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.load_library()
+    for fv in args.flag:
+        name, _, val = fv.partition("=")
+        ops.set_flag(name, int(val))
     K, W = args.steps, max(args.warmup, 3)
     headline = MODEL == "MSTransception" and (SIZE, NCLS, IN_CH) == (224, 9, 1)
 
@@ -655,6 +658,7 @@ def run_ours(args):
                                          "forward+loss+backward-to-the-cut graph, bucket-head gather graph, async NCCL all-reduce beside the "
                                          "stage 2-1 backward graph, bucket-tail gather graph + all-reduce, fused-SGD graph")},
                     "clocks": clocks, "e2e": tr["e2e"], "gpu_launches": tr["library_kernels_per_step"] * K,
+                    **({"flags": list(args.flag)} if args.flag else {}),
                     "roofline": tr["roofline"], "roofline_other_kernels": tr["roofline_other_kernels"], "roofline_step": tr["roofline_step"],
                     "train": {k: tr[k] for k in ("cuda_graph", "pdl_chain", "library_kernels_per_step", "first_loss", "last_loss", "grad_allreduce",
                                                    "peak_memory_gb", "allreduced_grads_equal_rank_mean_and_identical_across_ranks",
@@ -715,6 +719,8 @@ def main():
     ap.add_argument("--no-forward", action="store_true", help="train mode: skip the forward_step leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the gpu_baseline leg (oracle on the same GPU)")
     ap.add_argument("--no-legs", action="store_true", help="train mode: skip the per-kernel roofline legs (quick A/B runs)")
+    ap.add_argument("--flag", action="append", default=[], metavar="NAME=VALUE",
+                    help="library back-end switch for A/B runs (tcx_set_flag), e.g. --flag pdl=0; recorded in config.flags")
     ap.add_argument("--size", type=int, default=SIZE, help="input side (default 224 = the headline workload; 256 = config 5)")
     ap.add_argument("--classes", type=int, default=NCLS)
     ap.add_argument("--in-ch", type=int, default=IN_CH)
