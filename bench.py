@@ -720,7 +720,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the gpu_baseline leg (oracle on the same GPU)")
     ap.add_argument("--no-legs", action="store_true", help="train mode: skip the per-kernel roofline legs (quick A/B runs)")
     ap.add_argument("--flag", action="append", default=[], metavar="NAME=VALUE",
-                    help="library back-end switch for A/B runs (tcx_set_flag), e.g. --flag pdl=0; recorded in config.flags")
+                    help="library back-end switch for A/B runs (tcx_set_flag), e.g. --flag pdl=0; recorded in the line as `flags`")
     ap.add_argument("--size", type=int, default=SIZE, help="input side (default 224 = the headline workload; 256 = config 5)")
     ap.add_argument("--classes", type=int, default=NCLS)
     ap.add_argument("--in-ch", type=int, default=IN_CH)
