@@ -196,3 +196,26 @@ def test_world_size_2_gloo_gradient_allreduce():
     for rank, ok, n in res:
         assert ok, "rank %d: averaged gradients wrong" % rank
         assert n == 12 + 5 + 8
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): under torchrun only rank 0 works and prints; the other
+    ranks exit 0 silently.  Rank 0's line carries the keys of the contract with `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "", (r.returncode, r.stdout[-300:], r.stderr[-300:])
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--mode", "forward", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
